@@ -1,0 +1,197 @@
+/* mptg.h -- C ABI of the B200-native planning hot path (libmptg.so).
+ *
+ * Drop-in boundary for UNC-Robotics/mpt's data-parallel hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference root).  No torch / C++ types in
+ * any signature: plain pointers, sizes and opaque handles.  Every function returns an int status
+ * (MPTG_OK == 0, negative = error); mptg_last_error() gives the text.  There is NO CPU fallback: if
+ * the CUDA device, the kernel image or a launch is unavailable the call fails with MPTG_ERR_CUDA.
+ *
+ * Conventions
+ *  - A "state" is the concatenation of the scalars of the space's parts, in part order:
+ *      LP(dim)  : dim scalars                     (Eigen::Matrix<S,dim,1>, src/mpt/lp_space.hpp:44-54)
+ *      SO2(dim) : dim angles                      (src/mpt/so2_space.hpp:44-65)
+ *      SO3      : quaternion coeffs (x,y,z,w)     (Eigen::Quaternion::coeffs(), src/mpt/so3_space.hpp:52-55)
+ *    e.g. SE(3) = {SO3 weight 50, LP(p=2,dim=3) weight 1}: 7 scalars qx qy qz qw tx ty tz
+ *    (rotation is tuple element 0, src/mpt/se3_space.hpp:53-79).
+ *  - Host buffers are array-of-states (AoS), row-major, `scalar` bytes per element (4 or 8).
+ *  - Node identity is the dense uint32 index in insertion order (the host keeps index -> Node*).
+ *  - Functions ending in _dev take DEVICE pointers valid on the context's device and are enqueued
+ *    on the context stream without synchronising; the plain forms take HOST pointers, do the
+ *    host<->device copies on the context stream and return after the results are in host memory.
+ *  - A handle is single-owner: one host thread drives one context (one GPU, one stream).
+ */
+#ifndef MPTG_H
+#define MPTG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPTG_ABI_VERSION 1
+#define MPTG_MAX_PARTS 8
+#define MPTG_MAX_SCALARS 64 /* max scalars per state */
+#define MPTG_MAX_K 128      /* max neighbours per query */
+#define MPTG_NO_INDEX 0xFFFFFFFFu
+
+enum mptg_status {
+    MPTG_OK = 0,
+    MPTG_ERR_BAD_ARG = -1,
+    MPTG_ERR_OOM = -2,
+    MPTG_ERR_CUDA = -3,
+    MPTG_ERR_NCCL = -4,
+    MPTG_ERR_CAPACITY = -5,
+    MPTG_ERR_UNSUPPORTED = -6
+};
+
+enum mptg_part_kind { MPTG_PART_LP = 1, MPTG_PART_SO2 = 2, MPTG_PART_SO3 = 3 };
+enum mptg_scalar { MPTG_F32 = 4, MPTG_F64 = 8 };
+enum mptg_knn_strategy { MPTG_KNN_AUTO = 0, MPTG_KNN_BRUTE = 1, MPTG_KNN_BVH = 2 };
+enum mptg_geom_kind { MPTG_GEOM_GRID = 1, MPTG_GEOM_SHAPES = 2, MPTG_GEOM_LINKARM = 3, MPTG_GEOM_MESH = 4 };
+
+/* One factor of a Cartesian product space.  Replaces the compile-time metric tags
+ * LP<p>, SO2<p>, SO3, Scaled<M,ratio>, Cartesian<...> (src/mpt/impl/metrics.hpp:40-42,
+ * src/mpt/{lp,so2,so3,scaled,cartesian}_space.hpp).  distance = sum_i weight_i * d_i. */
+typedef struct mptg_space_part {
+    int32_t kind;  /* mptg_part_kind */
+    int32_t p;     /* LP/SO2 norm: 1, 2, or 0 for infinity */
+    int32_t dim;   /* LP/SO2: number of scalars; SO3: ignored (4 scalars) */
+    int32_t _pad;
+    double weight; /* Scaled<> ratio; 1.0 when unscaled.  Applied as d*weight in `scalar` precision */
+} mptg_space_part;
+
+typedef struct mptg_space_desc {
+    int32_t n_parts;
+    int32_t scalar; /* mptg_scalar */
+    mptg_space_part part[MPTG_MAX_PARTS];
+} mptg_space_desc;
+
+typedef struct mptg_ctx mptg_ctx;
+typedef struct mptg_knn mptg_knn;
+typedef struct mptg_geom mptg_geom;
+
+/* ------------------------------------------------------------------ context */
+int mptg_abi_version(void);
+/* device < 0 selects the current CUDA device.  Creates the context stream. */
+int mptg_ctx_create(int device, mptg_ctx** out);
+int mptg_ctx_destroy(mptg_ctx* ctx);
+int mptg_sync(mptg_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL for creation failures). Never NULL. */
+const char* mptg_last_error(const mptg_ctx* ctx);
+/* cudaStream_t of the context, as an opaque pointer (so callers can order their own work). */
+void* mptg_ctx_stream(mptg_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t mptg_ctx_launch_count(const mptg_ctx* ctx);
+/* Scalars per state for a space (sum of part sizes); < 0 on a malformed descriptor. */
+int mptg_space_scalars(const mptg_space_desc* space);
+/* space.dimensions() of the reference (LP: dim, SO2: dim, SO3: 3, sum over parts) used by
+ * src/mpt/impl/rrg_rewire_neighbors.hpp:60 and src/mpt/impl/pprm/pprm.hpp:146. */
+int mptg_space_dimensions(const mptg_space_desc* space);
+
+/* ------------------------------------------------------ metric (a4, a5) */
+/* Space::distance(a,b) for n state pairs.  Replaces nigh::metric::Space<T,M>::distance as used at
+ * src/mpt/discrete_motion_validator.hpp:78, impl/prrt_star/prrt_star.hpp:535, goal_state.hpp:65. */
+int mptg_distance_batch(mptg_ctx* ctx, const mptg_space_desc* space, const void* a, const void* b,
+                        uint32_t n, void* dist_out);
+/* interpolate(space,a,b,t) for n triples; t has n scalars.  Replaces the overloads at
+ * src/mpt/lp_space.hpp:44-54, so2_space.hpp:44-65, so3_space.hpp:44-83, scaled_space.hpp:44-51,
+ * cartesian_space.hpp:44-67. */
+int mptg_interpolate_batch(mptg_ctx* ctx, const mptg_space_desc* space, const void* a, const void* b,
+                           const void* t, uint32_t n, void* out);
+
+/* ------------------------------------------------------------ kNN (a1-a3) */
+/* nigh::Nigh<Node*,Space,NodeKey,Concurrency,Strategy> nn(space)  (impl/prrt/prrt.hpp:121-122). */
+int mptg_knn_create(mptg_ctx* ctx, const mptg_space_desc* space, uint32_t capacity, mptg_knn** out);
+int mptg_knn_destroy(mptg_knn* knn);
+int mptg_knn_set_strategy(mptg_knn* knn, int strategy /* mptg_knn_strategy */);
+/* nn.insert(node) for a batch (impl/prrt/prrt.hpp:186,447; prrt_star.hpp:278,619; pprm.hpp:337).
+ * Indices first .. first+count-1 are assigned in order. */
+int mptg_knn_insert(mptg_knn* knn, const void* states, uint32_t count, uint32_t* first_index_out);
+int mptg_knn_insert_dev(mptg_knn* knn, const void* states_dev, uint32_t count, uint32_t* first_index_out);
+/* nn.size() */
+uint32_t mptg_knn_size(const mptg_knn* knn);
+/* Read back `count` stored states starting at index `first` (AoS, host). */
+int mptg_knn_get_states(mptg_knn* knn, uint32_t first, uint32_t count, void* states_out);
+/* nn.nearest(q) (k == 1) and nn.nearest(nbh, q, k, r) (impl/prrt/prrt.hpp:406-409,
+ * prrt_star.hpp:505-508, rrg_rewire_neighbors.hpp:65-67,125-128, pprm.hpp:304) for Q queries.
+ * Result row q holds count_out[q] <= k neighbours, ascending by (distance, index); unused slots are
+ * MPTG_NO_INDEX / +inf.  radius < 0 or +inf means unbounded; otherwise only distance <= radius
+ * is kept (if more than k qualify the k nearest are returned and count_out[q] == k).
+ * dist_out has Q*k scalars of the space's scalar type.  count_out may be NULL. */
+int mptg_knn_query(mptg_knn* knn, const void* queries, uint32_t Q, uint32_t k, double radius,
+                   uint32_t* idx_out, void* dist_out, uint32_t* count_out);
+int mptg_knn_query_dev(mptg_knn* knn, const void* queries_dev, uint32_t Q, uint32_t k, double radius,
+                       uint32_t* idx_out_dev, void* dist_out_dev, uint32_t* count_out_dev);
+/* Build / refresh the spatial index now (otherwise done lazily by the AUTO strategy). */
+int mptg_knn_build_index(mptg_knn* knn);
+/* Counters of the last query call: [0]=distance evaluations, [1]=index nodes visited, [2]=indexed
+ * points, [3]=strategy used (mptg_knn_strategy). */
+int mptg_knn_last_stats(mptg_knn* knn, uint64_t stats_out[4]);
+/* Multi-GPU merge step: `parts` candidate lists per query (each k wide, ascending, global indices),
+ * laid out [parts][Q][k] in device memory, merged to the k best by (distance, index).
+ * Used after an all-gather of per-shard results (tree points sharded across GPUs). */
+int mptg_knn_merge_dev(mptg_ctx* ctx, int scalar, uint32_t parts, uint32_t Q, uint32_t k,
+                       const uint32_t* idx_in_dev, const void* dist_in_dev, uint32_t* idx_out_dev,
+                       void* dist_out_dev, uint32_t* count_out_dev);
+
+/* ------------------------------------------------ scenario geometry (a7-a10) */
+/* Occupancy grid, 1 byte per cell (non-zero = obstacle), row-major width*height.
+ * Replaces PNG2dScenario's std::vector<bool> isObstacle_ (demo/png_2d_scenario.hpp:86,104-110).
+ * States are LP(2): (x, y) in pixels.  Cells whose linear index falls outside [0, w*h) -- the
+ * reference reads out of bounds there -- are treated as obstacles. */
+int mptg_grid_create(mptg_ctx* ctx, int scalar, int32_t width, int32_t height, const uint8_t* occupancy,
+                     mptg_geom** out);
+/* Balls (centres in `dim`-D, point and closed-form segment tests) and 2-D rectangles (bisected to
+ * 1 unit).  Replaces shape::Circle / shape::Rect (demo/shape_hierarchy.hpp:168-273), the scenario
+ * loops of demo/holonomic_2d_point_scenario.hpp:95-113 and the sphere scenario of
+ * test/planner_integration_test.hpp:128-150.  centres: n_balls*dim doubles; radii: n_balls doubles;
+ * rects: n_rects*4 doubles (x0,y0,x1,y1), only with dim == 2. */
+int mptg_shapes_create(mptg_ctx* ctx, int scalar, int32_t dim, int32_t n_balls, const double* centres,
+                       const double* radii, int32_t n_rects, const double* rects, mptg_geom** out);
+/* Planar N-link arm among circles.  Replaces LinkManipulatorScenario::valid/link/bisectLink
+ * (demo/link_manipulator_scenario.hpp:99-138).  States are LP(n_links) joint angles. */
+int mptg_linkarm_create(mptg_ctx* ctx, int scalar, int32_t n_links, const double* lengths,
+                        double link_radius, int32_t n_circles, const double* cx_cy_r, mptg_geom** out);
+/* Rigid robot mesh vs static environment mesh (triangle soups, 9 floats per triangle).  Replaces
+ * fcl::BVHModel<OBBRSS> + fcl::collide in SE3RigidBodyScenario::valid
+ * (demo/se3_rigid_body_scenario.hpp:164-204,282-296).  The robot mesh is used as given (the
+ * reference recentres it on the vertex mean at load time, :181-193 -- do that before calling).
+ * States are SE(3): qx qy qz qw tx ty tz. */
+int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t n_tri_robot, const float* robot_tris,
+                          uint32_t n_tri_env, const float* env_tris, mptg_geom** out);
+int mptg_geom_destroy(mptg_geom* geom);
+int mptg_geom_kind(const mptg_geom* geom);
+
+/* scenario.valid(q) for n states -> ok_out[i] in {0,1}.  (impl/prrt/prrt.hpp:439,
+ * prrt_star.hpp:539, pprm.hpp:299) */
+int mptg_valid_batch(mptg_geom* geom, const void* states, uint32_t n, uint8_t* ok_out);
+int mptg_valid_batch_dev(mptg_geom* geom, const void* states_dev, uint32_t n, uint8_t* ok_out_dev);
+/* scenario.link(a,b) for n edges -> ok_out[i] in {0,1}.  (impl/prrt/prrt.hpp:454-457,
+ * prrt_star.hpp:659-662, pprm.hpp:364-366).  Semantics per geometry kind:
+ *   GRID    valid(a) && valid(b) && midpoint bisection until |b-a|^2 < 1   (png_2d_scenario.hpp:112-117,152-165)
+ *   SHAPES  balls: closed-form point-segment distance; rects: endpoints + bisection (shape_hierarchy.hpp:184-203,228-270)
+ *   LINKARM valid(a) && valid(b) && bisection until |a-b|_inf < 0.02        (link_manipulator_scenario.hpp:118-138)
+ *   MESH    DiscreteMotionValidator with step size `step` over `space`      (discrete_motion_validator.hpp:71-130);
+ *           `from` is assumed valid and not checked, exactly as the reference (:72-73).
+ * `space` / `step` are only read for MESH (pass NULL / 0 otherwise). */
+int mptg_link_batch(mptg_geom* geom, const mptg_space_desc* space, const void* from, const void* to,
+                    uint32_t n, double step, uint8_t* ok_out);
+int mptg_link_batch_dev(mptg_geom* geom, const mptg_space_desc* space, const void* from_dev,
+                        const void* to_dev, uint32_t n, double step, uint8_t* ok_out_dev);
+/* Counters of the last valid/link call on this geometry: [0]=states checked, [1]=BV pair tests,
+ * [2]=primitive (triangle-pair / circle / cell) tests, [3]=work items. */
+int mptg_geom_last_stats(mptg_geom* geom, uint64_t stats_out[4]);
+
+/* --------------------------------------------------------- planner stages */
+/* Steer: out[i] = d[i] > range ? interpolate(space, near[i], sample[i], range/d[i]) : sample[i]
+ * (impl/prrt/prrt.hpp:430-434, impl/prrt_star/prrt_star.hpp:529-536).  If dist_out != NULL it
+ * receives distance(near[i], out[i]) recomputed after steering (PRRT* does, :535; PRRT does not). */
+int mptg_steer_batch(mptg_ctx* ctx, const mptg_space_desc* space, const void* near, const void* sample,
+                     const void* d, uint32_t n, double range, void* out, void* dist_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPTG_H */
