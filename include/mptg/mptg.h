@@ -106,6 +106,10 @@ int mptg_interpolate_batch(mptg_ctx* ctx, const mptg_space_desc* space, const vo
 int mptg_knn_create(mptg_ctx* ctx, const mptg_space_desc* space, uint32_t capacity, mptg_knn** out);
 int mptg_knn_destroy(mptg_knn* knn);
 int mptg_knn_set_strategy(mptg_knn* knn, int strategy /* mptg_knn_strategy */);
+/* Multi-GPU sharding: reported index = local_index * mul + add (default 1, 0).  With tree points
+ * dealt round-robin to G ranks (global index g lives on rank g % G at local slot g / G) rank r
+ * sets mul = G, add = r and every result carries global indices. */
+int mptg_knn_set_index_map(mptg_knn* knn, uint32_t mul, uint32_t add);
 /* nn.insert(node) for a batch (impl/prrt/prrt.hpp:186,447; prrt_star.hpp:278,619; pprm.hpp:337).
  * Indices first .. first+count-1 are assigned in order. */
 int mptg_knn_insert(mptg_knn* knn, const void* states, uint32_t count, uint32_t* first_index_out);

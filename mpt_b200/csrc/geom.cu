@@ -1,0 +1,632 @@
+// geom.cu -- batched state / edge validity for the occupancy grid, balls & rectangles and the planar
+// N-link arm, plus the geometry part of the C ABI.
+//
+// Edge checks of these scenarios are recursive midpoint bisections in the reference
+// (demo/png_2d_scenario.hpp:152-165, demo/shape_hierarchy.hpp:191-203,
+// demo/link_manipulator_scenario.hpp:125-138).  The recursion tree depends only on the floating
+// point endpoints (mid = (a+b)/2, stop test on the CURRENT pair), and the answer is the AND over
+// every midpoint in that tree, so visiting order is free.  One warp takes one edge: lane L walks
+// the five top levels along the path given by its bits (re-probing the shared midpoints) and then
+// runs the rest of its subtree depth first with an explicit stack; a warp vote per iteration stops
+// all lanes at the first invalid probe.  All midpoints are produced by the same sequence of
+// floating point operations as the reference's recursion, so decisions are bit-identical.
+#include "geom.cuh"
+
+namespace mptg {
+
+// ------------------------------------------------------------------ validators
+template <typename S>
+struct GridValidator {
+    static constexpr int MAXD = 2;
+    static constexpr int MAXDEPTH = 48;
+    const uint32_t* bits;
+    int width, height;
+    __device__ __forceinline__ int dims() const { return 2; }
+    // demo/png_2d_scenario.hpp:104-110.  Out-of-range linear index (the reference reads out of
+    // bounds there) -> obstacle.
+    __device__ __forceinline__ bool valid(const S* q) const {
+        const int x = (int)(q[0] + S(0.5));
+        const int y = (int)(q[1] + S(0.5));
+        const long long idx = (long long)width * y + x;
+        if (idx < 0 || idx >= (long long)width * height) return false;
+        return ((__ldg(bits + (idx >> 5)) >> (idx & 31)) & 1u) == 0;
+    }
+    __device__ __forceinline__ bool endpointsValid(const S* a, const S* b) const { return valid(a) && valid(b); }
+    // :155-158  (b - a).squaredNorm() < 1
+    __device__ __forceinline__ bool stop(const S* a, const S* b) const {
+        const S dx = b[0] - a[0], dy = b[1] - a[1];
+        return dx * dx + dy * dy < S(1);
+    }
+};
+
+template <typename S>
+struct ShapesValidator {
+    static constexpr int MAXD = 2;
+    static constexpr int MAXDEPTH = 48;
+    const S* rects;
+    int nRects;
+    __device__ __forceinline__ int dims() const { return 2; }
+    // shape_hierarchy.hpp:177-182, AND over rectangles
+    __device__ __forceinline__ bool valid(const S* p) const {
+        for (int j = 0; j < nRects; ++j) {
+            const S* r = rects + 4 * j;
+            if (p[0] >= r[0] && p[0] <= r[2] && p[1] >= r[1] && p[1] <= r[3]) return false;
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool endpointsValid(const S* a, const S* b) const { return valid(a) && valid(b); }
+    __device__ __forceinline__ bool stop(const S* a, const S* b) const {  // :194-197
+        const S dx = b[0] - a[0], dy = b[1] - a[1];
+        return dx * dx + dy * dy < S(1);
+    }
+};
+
+// shape_hierarchy.hpp:259-270 for 2-D points
+template <typename S>
+__device__ __forceinline__ S distPointSegmentSquared2(const S* pt, const S* s0, const S* s1) {
+    const S vx = s1[0] - s0[0], vy = s1[1] - s0[1];
+    const S wx = pt[0] - s0[0], wy = pt[1] - s0[1];
+    const S c1 = vx * wx + vy * wy;
+    if (c1 <= S(0)) return wx * wx + wy * wy;
+    const S c2 = vx * vx + vy * vy;
+    if (c2 <= c1) {
+        const S ex = pt[0] - s1[0], ey = pt[1] - s1[1];
+        return ex * ex + ey * ey;
+    }
+    const S f = fp::div_(c1, c2);
+    const S ex = s0[0] - pt[0] + vx * f, ey = s0[1] - pt[1] + vy * f;
+    return ex * ex + ey * ey;
+}
+
+template <typename S, int MAXD_>
+struct ArmValidator {
+    static constexpr int MAXD = MAXD_;
+    static constexpr int MAXDEPTH = 8;  // beyond the 5 split levels: |a-b|_inf up to 0.02 * 2^13 rad
+    const S* lengths;
+    const S* circles;
+    int nLinks, nCircles;
+    S linkRadius;
+    __device__ __forceinline__ int dims() const { return nLinks; }
+    // demo/link_manipulator_scenario.hpp:99-116
+    __device__ bool valid(const S* q) const {
+        S from[2] = {S(0), S(0)}, to[2];
+        S angle = S(0);
+        for (int i = 0; i < nLinks; ++i) {
+            angle = angle + q[i];
+            S sn, cs;
+            fp::sincos_(angle, &sn, &cs);
+            const S len = lengths[i];
+            to[0] = from[0] + len * cs;
+            to[1] = from[1] + len * sn;
+            for (int c = 0; c < nCircles; ++c) {
+                const S rr = circles[3 * c + 2] + linkRadius;
+                if (!(distPointSegmentSquared2<S>(circles + 3 * c, from, to) > rr * rr)) return false;
+            }
+            from[0] = to[0];
+            from[1] = to[1];
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool endpointsValid(const S* a, const S* b) const { return valid(a) && valid(b); }
+    // :127-131  (a - b).lpNorm<Infinity>() < 0.02
+    __device__ __forceinline__ bool stop(const S* a, const S* b) const {
+        S m = S(0);
+        for (int i = 0; i < nLinks; ++i) {
+            const S d = fp::abs_(a[i] - b[i]);
+            m = d > m ? d : m;
+        }
+        return m < S(0.02);
+    }
+};
+
+// ------------------------------------------------------------------ bisection edge kernel
+constexpr int SPLIT_LEVELS = 5;  // 32 lanes = 32 subtrees at depth 5
+
+template <typename S, typename V>
+__global__ void __launch_bounds__(256) bisectLinkKernel(const V v, const S* __restrict__ from, const S* __restrict__ to,
+                                                        uint32_t n, uint8_t* __restrict__ ok,
+                                                        unsigned long long* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
+    const int D = v.dims();
+    unsigned long long probes = 0;
+    bool overflow = false;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += warpsPerGrid) {
+        S a[V::MAXD], b[V::MAXD], mid[V::MAXD];
+        for (int i = 0; i < D; ++i) {
+            a[i] = from[(size_t)e * D + i];
+            b[i] = to[(size_t)e * D + i];
+        }
+        // endpoints (all lanes compute the same thing; lane 0's answer is used)
+        bool good = v.endpointsValid(a, b);
+        good = __shfl_sync(FULL_MASK_, good, 0);
+        bool done = !good;
+        // top levels: follow this lane's path
+        if (!done) {
+            for (int level = 0; level < SPLIT_LEVELS; ++level) {
+                if (v.stop(a, b)) {
+                    done = true;  // subtree ends here: nothing below to check
+                    break;
+                }
+                for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
+                ++probes;
+                if (!v.valid(mid)) {
+                    good = false;
+                    done = true;
+                    break;
+                }
+                if ((lane >> (SPLIT_LEVELS - 1 - level)) & 1) {
+                    for (int i = 0; i < D; ++i) a[i] = mid[i];
+                } else {
+                    for (int i = 0; i < D; ++i) b[i] = mid[i];
+                }
+            }
+        }
+        // Lanes whose path stopped early duplicate a sibling's (empty) subtree: nothing left to do.
+        // Depth-first over the remaining subtree.  Only the right end of each pending right half is
+        // stacked: its left end is always the right end of the leaf just finished (the rightmost
+        // leaf of a left subtree ends exactly at the parent's midpoint).
+        S stackB[V::MAXDEPTH][V::MAXD];
+        int sp = 0;
+        bool havePair = !done;
+        while (true) {
+            const unsigned bad = __ballot_sync(FULL_MASK_, !good);
+            if (bad) {
+                good = false;
+                break;
+            }
+            if (!__any_sync(FULL_MASK_, havePair)) break;
+            if (havePair) {
+                if (v.stop(a, b)) {
+                    // leaf: continue with the next pending right half (current b, stacked b)
+                    if (sp > 0) {
+                        --sp;
+                        for (int i = 0; i < D; ++i) {
+                            a[i] = b[i];
+                            b[i] = stackB[sp][i];
+                        }
+                    } else {
+                        havePair = false;
+                    }
+                } else {
+                    for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
+                    ++probes;
+                    if (!v.valid(mid)) {
+                        good = false;
+                    } else if (sp >= V::MAXDEPTH) {
+                        overflow = true;
+                        good = false;
+                    } else {
+                        // remember the right half (mid, b), continue with the left half (a, mid)
+                        for (int i = 0; i < D; ++i) {
+                            stackB[sp][i] = b[i];
+                            b[i] = mid[i];
+                        }
+                        ++sp;
+                    }
+                }
+            }
+        }
+        if (lane == 0) ok[e] = good ? 1 : 0;
+    }
+    // counters
+    for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(FULL_MASK_, probes, o);
+    if (lane == 0 && stats) {
+        atomicAdd(stats + 2, probes);
+    }
+    if (overflow && stats) atomicOr(stats + 4, (unsigned long long)GEOM_ERR_STACK);
+}
+
+template <typename S, typename V>
+__global__ void validKernel(const V v, const S* __restrict__ states, uint32_t n, uint8_t* __restrict__ ok) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S q[V::MAXD];
+    const int D = v.dims();
+    for (int c = 0; c < D; ++c) q[c] = states[(size_t)i * D + c];
+    ok[i] = v.valid(q) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ balls (any dimension)
+template <typename S>
+struct BallsData {
+    const S* balls;  // nBalls * (dim + 1)
+    int nBalls, dim;
+    const S* rects;
+    int nRects;
+};
+
+// shape_hierarchy.hpp:222-226 + rect point test; holonomic_2d_point_scenario.hpp:95-103
+template <typename S>
+__global__ void shapesValidKernel(BallsData<S> g, const S* __restrict__ states, uint32_t n, uint8_t* __restrict__ ok) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S* p = states + (size_t)i * g.dim;
+    bool good = true;
+    for (int j = 0; j < g.nBalls && good; ++j) {
+        const S* c = g.balls + (size_t)j * (g.dim + 1);
+        S acc = S(0);
+        for (int d = 0; d < g.dim; ++d) {
+            const S e = p[d] - c[d];
+            acc = (d == 0) ? e * e : acc + e * e;
+        }
+        good = acc > c[g.dim] * c[g.dim];
+    }
+    for (int j = 0; j < g.nRects && good; ++j) {
+        const S* r = g.rects + 4 * j;
+        good = !(p[0] >= r[0] && p[0] <= r[2] && p[1] >= r[1] && p[1] <= r[3]);
+    }
+    ok[i] = good ? 1 : 0;
+}
+
+// Circle::segmentIsValid (shape_hierarchy.hpp:228-231,259-270), generalised to `dim` coordinates
+// (test/planner_integration_test.hpp:143-149 uses the 3-D form).  One thread per edge.
+// ok[] is AND-ed with the result (the rect bisection kernel may have written it first).
+template <typename S>
+__global__ void ballsLinkKernel(BallsData<S> g, const S* __restrict__ from, const S* __restrict__ to, uint32_t n,
+                                uint8_t* __restrict__ ok, int andWithExisting) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S* s0 = from + (size_t)i * g.dim;
+    const S* s1 = to + (size_t)i * g.dim;
+    bool good = true;
+    for (int j = 0; j < g.nBalls && good; ++j) {
+        const S* pt = g.balls + (size_t)j * (g.dim + 1);
+        S c1 = S(0), c2 = S(0), ww = S(0);
+        for (int d = 0; d < g.dim; ++d) {
+            const S vv = s1[d] - s0[d], w = pt[d] - s0[d];
+            c1 = (d == 0) ? vv * w : c1 + vv * w;
+            c2 = (d == 0) ? vv * vv : c2 + vv * vv;
+            ww = (d == 0) ? w * w : ww + w * w;
+        }
+        S dist2;
+        if (c1 <= S(0)) {
+            dist2 = ww;
+        } else if (c2 <= c1) {
+            S acc = S(0);
+            for (int d = 0; d < g.dim; ++d) {
+                const S e = pt[d] - s1[d];
+                acc = (d == 0) ? e * e : acc + e * e;
+            }
+            dist2 = acc;
+        } else {
+            const S f = fp::div_(c1, c2);
+            S acc = S(0);
+            for (int d = 0; d < g.dim; ++d) {
+                const S vv = s1[d] - s0[d];
+                const S e = s0[d] - pt[d] + vv * f;
+                acc = (d == 0) ? e * e : acc + e * e;
+            }
+            dist2 = acc;
+        }
+        good = dist2 > pt[g.dim] * pt[g.dim];
+    }
+    if (andWithExisting) good = good && ok[i];
+    ok[i] = good ? 1 : 0;
+}
+
+}  // namespace mptg
+
+using namespace mptg;
+
+namespace {
+
+int warpGrid(mptg_ctx* ctx, uint32_t n) {
+    // persistent-style: enough 8-warp CTAs to fill the machine, never more than one warp per edge
+    const uint32_t want = (n + 7) / 8;
+    const uint32_t cap = (uint32_t)ctx->smCount * 8;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+template <typename S>
+int uploadScalars(mptg_ctx* ctx, const double* src, size_t count, void** dst) {
+    std::vector<S> tmp(count);
+    for (size_t i = 0; i < count; ++i) tmp[i] = (S)src[i];
+    MPTG_CUDA(ctx, cudaMalloc(dst, (count ? count : 1) * sizeof(S)));
+    if (count) MPTG_CUDA(ctx, cudaMemcpy(*dst, tmp.data(), count * sizeof(S), cudaMemcpyHostToDevice));
+    return MPTG_OK;
+}
+
+int newGeom(mptg_ctx* ctx, int kind, int scalar, mptg_geom** out) {
+    auto* g = new mptg_geom();
+    g->ctx = ctx;
+    g->kind = kind;
+    g->scalar = scalar;
+    cudaError_t e = cudaMalloc(&g->devStats, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(g->devStats, 0, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        delete g;
+        return fail(ctx, MPTG_ERR_CUDA, "geometry create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return MPTG_OK;
+}
+
+template <typename S>
+int validDevT(mptg_geom* g, const S* states, uint32_t n, uint8_t* ok) {
+    mptg_ctx* ctx = g->ctx;
+    const dim3 grid((n + 127) / 128), block(128);
+    switch (g->kind) {
+        case MPTG_GEOM_GRID: {
+            GridValidator<S> v{g->gridBits, g->width, g->height};
+            validKernel<S, GridValidator<S>><<<grid, block, 0, ctx->stream>>>(v, states, n, ok);
+            break;
+        }
+        case MPTG_GEOM_SHAPES: {
+            BallsData<S> b{(const S*)g->balls, g->nBalls, g->dim, (const S*)g->rects, g->nRects};
+            shapesValidKernel<S><<<grid, block, 0, ctx->stream>>>(b, states, n, ok);
+            break;
+        }
+        case MPTG_GEOM_LINKARM: {
+#define MPTG_ARM_VALID(MD)                                                                                         \
+    {                                                                                                              \
+        ArmValidator<S, MD> v{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
+        validKernel<S, ArmValidator<S, MD>><<<grid, block, 0, ctx->stream>>>(v, states, n, ok);                    \
+    }
+            if (g->nLinks <= 8) MPTG_ARM_VALID(8)
+            else if (g->nLinks <= 16) MPTG_ARM_VALID(16)
+            else if (g->nLinks <= 32) MPTG_ARM_VALID(32)
+            else MPTG_ARM_VALID(64)
+#undef MPTG_ARM_VALID
+            break;
+        }
+        default: return fail(ctx, MPTG_ERR_BAD_ARG, "valid: unknown geometry kind %d", g->kind);
+    }
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+
+template <typename S>
+int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) {
+    mptg_ctx* ctx = g->ctx;
+    const dim3 wgrid(warpGrid(ctx, n)), wblock(256);
+    switch (g->kind) {
+        case MPTG_GEOM_GRID: {
+            GridValidator<S> v{g->gridBits, g->width, g->height};
+            bisectLinkKernel<S, GridValidator<S>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats);
+            MPTG_LAUNCHED(ctx);
+            break;
+        }
+        case MPTG_GEOM_SHAPES: {
+            int haveRects = 0;
+            if (g->nRects > 0) {
+                ShapesValidator<S> v{(const S*)g->rects, g->nRects};
+                bisectLinkKernel<S, ShapesValidator<S>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats);
+                MPTG_LAUNCHED(ctx);
+                haveRects = 1;
+            }
+            BallsData<S> b{(const S*)g->balls, g->nBalls, g->dim, (const S*)g->rects, g->nRects};
+            ballsLinkKernel<S><<<(n + 127) / 128, 128, 0, ctx->stream>>>(b, from, to, n, ok, haveRects);
+            MPTG_LAUNCHED(ctx);
+            break;
+        }
+        case MPTG_GEOM_LINKARM: {
+#define MPTG_ARM_LINK(MD)                                                                                          \
+    {                                                                                                              \
+        ArmValidator<S, MD> v{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
+        bisectLinkKernel<S, ArmValidator<S, MD>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats); \
+    }
+            if (g->nLinks <= 8) MPTG_ARM_LINK(8)
+            else if (g->nLinks <= 16) MPTG_ARM_LINK(16)
+            else if (g->nLinks <= 32) MPTG_ARM_LINK(32)
+            else MPTG_ARM_LINK(64)
+#undef MPTG_ARM_LINK
+            MPTG_LAUNCHED(ctx);
+            break;
+        }
+        default: return fail(ctx, MPTG_ERR_BAD_ARG, "link: unknown geometry kind %d", g->kind);
+    }
+    return MPTG_OK;
+}
+
+int resetStats(mptg_geom* g) {
+    MPTG_CUDA(g->ctx, cudaMemsetAsync(g->devStats, 0, 8 * sizeof(unsigned long long), g->ctx->stream));
+    return MPTG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptg_grid_create(mptg_ctx* ctx, int scalar, int32_t width, int32_t height, const uint8_t* occupancy, mptg_geom** out) {
+    if (!ctx || !out || !occupancy || width <= 0 || height <= 0 || (scalar != MPTG_F32 && scalar != MPTG_F64))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_grid_create: bad argument");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    mptg_geom* g;
+    int rc = newGeom(ctx, MPTG_GEOM_GRID, scalar, &g);
+    if (rc) return rc;
+    g->D = 2;
+    g->width = width;
+    g->height = height;
+    const size_t cells = (size_t)width * height, words = (cells + 31) / 32;
+    std::vector<uint32_t> bits(words, 0u);
+    for (size_t i = 0; i < cells; ++i)
+        if (occupancy[i]) bits[i >> 5] |= 1u << (i & 31);
+    cudaError_t e = cudaMalloc(&g->gridBits, words * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(g->gridBits, bits.data(), words * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        mptg_geom_destroy(g);
+        return fail(ctx, MPTG_ERR_CUDA, "mptg_grid_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return MPTG_OK;
+}
+
+int mptg_shapes_create(mptg_ctx* ctx, int scalar, int32_t dim, int32_t nBalls, const double* centres, const double* radii,
+                       int32_t nRects, const double* rects, mptg_geom** out) {
+    if (!ctx || !out || dim < 1 || dim > MPTG_MAX_SCALARS || nBalls < 0 || nRects < 0 || (nBalls && (!centres || !radii)) ||
+        (nRects && (!rects || dim != 2)) || (scalar != MPTG_F32 && scalar != MPTG_F64))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_shapes_create: bad argument (rectangles need dim == 2)");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    mptg_geom* g;
+    int rc = newGeom(ctx, MPTG_GEOM_SHAPES, scalar, &g);
+    if (rc) return rc;
+    g->D = g->dim = dim;
+    g->nBalls = nBalls;
+    g->nRects = nRects;
+    std::vector<double> packed((size_t)nBalls * (dim + 1));
+    for (int j = 0; j < nBalls; ++j) {
+        for (int d = 0; d < dim; ++d) packed[(size_t)j * (dim + 1) + d] = centres[(size_t)j * dim + d];
+        packed[(size_t)j * (dim + 1) + dim] = radii[j];
+    }
+    rc = scalar == MPTG_F32 ? uploadScalars<float>(ctx, packed.data(), packed.size(), &g->balls)
+                            : uploadScalars<double>(ctx, packed.data(), packed.size(), &g->balls);
+    if (!rc)
+        rc = scalar == MPTG_F32 ? uploadScalars<float>(ctx, rects, (size_t)nRects * 4, &g->rects)
+                                : uploadScalars<double>(ctx, rects, (size_t)nRects * 4, &g->rects);
+    if (rc) {
+        mptg_geom_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return MPTG_OK;
+}
+
+int mptg_linkarm_create(mptg_ctx* ctx, int scalar, int32_t nLinks, const double* lengths, double linkRadius,
+                        int32_t nCircles, const double* cxcyr, mptg_geom** out) {
+    if (!ctx || !out || nLinks < 1 || nLinks > MPTG_MAX_SCALARS || !lengths || nCircles < 0 || (nCircles && !cxcyr) ||
+        (scalar != MPTG_F32 && scalar != MPTG_F64))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_linkarm_create: bad argument");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    mptg_geom* g;
+    int rc = newGeom(ctx, MPTG_GEOM_LINKARM, scalar, &g);
+    if (rc) return rc;
+    g->D = g->nLinks = nLinks;
+    g->nCircles = nCircles;
+    g->linkRadius = linkRadius;
+    rc = scalar == MPTG_F32 ? uploadScalars<float>(ctx, lengths, nLinks, &g->lengths)
+                            : uploadScalars<double>(ctx, lengths, nLinks, &g->lengths);
+    if (!rc)
+        rc = scalar == MPTG_F32 ? uploadScalars<float>(ctx, cxcyr, (size_t)nCircles * 3, &g->circles)
+                                : uploadScalars<double>(ctx, cxcyr, (size_t)nCircles * 3, &g->circles);
+    if (rc) {
+        mptg_geom_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return MPTG_OK;
+}
+
+int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris,
+                          mptg_geom** out) {
+    if (!ctx || !out || (nr && !robotTris) || (ne && !envTris)) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_mesh_pair_create: bad argument");
+    if (scalar != MPTG_F32) return fail(ctx, MPTG_ERR_UNSUPPORTED, "mptg_mesh_pair_create: only MPTG_F32 meshes are supported");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    mptg_geom* g;
+    int rc = newGeom(ctx, MPTG_GEOM_MESH, scalar, &g);
+    if (rc) return rc;
+    g->D = 7;
+    rc = meshCreate(ctx, scalar, nr, robotTris, ne, envTris, &g->mesh);
+    if (rc) {
+        mptg_geom_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return MPTG_OK;
+}
+
+int mptg_geom_destroy(mptg_geom* g) {
+    if (!g) return MPTG_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->gridBits);
+    cudaFree(g->balls);
+    cudaFree(g->rects);
+    cudaFree(g->lengths);
+    cudaFree(g->circles);
+    cudaFree(g->devStats);
+    if (g->mesh) meshDestroy(g->mesh);
+    delete g;
+    return MPTG_OK;
+}
+
+int mptg_geom_kind(const mptg_geom* g) { return g ? g->kind : 0; }
+
+int mptg_valid_batch_dev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+    if (!g || (n && (!states || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_valid_batch: bad argument");
+    if (n == 0) return MPTG_OK;
+    MPTG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    int rc = resetStats(g);
+    if (rc) return rc;
+    if (g->kind == MPTG_GEOM_MESH) return meshValidDev(g, states, n, ok);
+    return g->scalar == MPTG_F32 ? validDevT<float>(g, (const float*)states, n, ok) : validDevT<double>(g, (const double*)states, n, ok);
+}
+
+int mptg_link_batch_dev(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
+                        uint8_t* ok) {
+    if (!g || (n && (!from || !to || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_link_batch: bad argument");
+    if (n == 0) return MPTG_OK;
+    MPTG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    int rc = resetStats(g);
+    if (rc) return rc;
+    if (g->kind == MPTG_GEOM_MESH) {
+        if (!space || spaceScalars(space) != 7 || space->scalar != g->scalar || !(step > 0))
+            return fail(g->ctx, MPTG_ERR_BAD_ARG, "mptg_link_batch: mesh edges need an SE(3) space of the mesh's scalar type and step > 0");
+        return meshLinkDev(g, space, from, to, n, step, ok);
+    }
+    return g->scalar == MPTG_F32 ? linkDevT<float>(g, (const float*)from, (const float*)to, n, ok)
+                                 : linkDevT<double>(g, (const double*)from, (const double*)to, n, ok);
+}
+
+static int checkDeviceErrors(mptg_geom* g) {
+    // called after a synchronise: surface device-side error flags
+    unsigned long long host[8];
+    MPTG_CUDA(g->ctx, cudaMemcpy(host, g->devStats, sizeof host, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) g->stats[i] = host[i];
+    if (host[4] & GEOM_ERR_STACK) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: traversal stack overflow (edge too long / geometry too deep)");
+    if (host[4] & GEOM_ERR_STEPS) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: too many interpolation steps on one edge");
+    return MPTG_OK;
+}
+
+int mptg_valid_batch(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+    if (!g || (n && (!states || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_valid_batch: bad argument");
+    if (n == 0) return MPTG_OK;
+    mptg_ctx* ctx = g->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)n * g->D * g->scalar;
+    void* dIn;
+    void* dOut;
+    int rc = scratch(ctx, 0, sb, &dIn);
+    if (rc) return rc;
+    rc = scratch(ctx, 1, n, &dOut);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(dIn, states, sb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mptg_valid_batch_dev(g, dIn, n, (uint8_t*)dOut);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(ok, dOut, n, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return checkDeviceErrors(g);
+}
+
+int mptg_link_batch(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
+                    uint8_t* ok) {
+    if (!g || (n && (!from || !to || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_link_batch: bad argument");
+    if (n == 0) return MPTG_OK;
+    mptg_ctx* ctx = g->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)n * g->D * g->scalar, sbp = (sb + 255) & ~(size_t)255;
+    void* dIn;
+    void* dOut;
+    int rc = scratch(ctx, 0, 2 * sbp, &dIn);
+    if (rc) return rc;
+    rc = scratch(ctx, 1, n, &dOut);
+    if (rc) return rc;
+    void* dTo = (char*)dIn + sbp;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(dIn, from, sb, cudaMemcpyHostToDevice, ctx->stream));
+    MPTG_CUDA(ctx, cudaMemcpyAsync(dTo, to, sb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mptg_link_batch_dev(g, space, dIn, dTo, n, step, (uint8_t*)dOut);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(ok, dOut, n, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return checkDeviceErrors(g);
+}
+
+int mptg_geom_last_stats(mptg_geom* g, uint64_t out[4]) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_geom_last_stats: bad argument");
+    MPTG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
+    MPTG_CUDA(g->ctx, cudaStreamSynchronize(g->ctx->stream));
+    int rc = checkDeviceErrors(g);
+    for (int i = 0; i < 4; ++i) out[i] = g->stats[i];
+    return rc;
+}
+}

@@ -1,0 +1,541 @@
+// knn.cu -- device-resident batched nearest-neighbour structure.
+//
+// Replaces nigh::Nigh<Node*,Space,NodeKey,Concurrency,Strategy> as used by the planners
+// (src/mpt/impl/prrt/prrt.hpp:121-122,186,406-409,447; impl/prrt_star/prrt_star.hpp:182-183,278,
+// 505-508,559-562,619; impl/pprm/pprm.hpp:80-81,304,337; impl/rrg_rewire_neighbors.hpp:65-67,125-128).
+//
+// Layout in HBM: structure-of-arrays, row c holds scalar c of every stored state
+// (pts[c*stride + i]); stride is the capacity rounded to 256 so every row is 1 KB aligned and a warp
+// reads 32 consecutive points of a row with one 128 B transaction.
+//
+// Two exact search engines share one distance function and one (distance, index) total order:
+//   * tiled brute force (this file): one warp per query, 8 queries per CTA share point tiles staged
+//     in shared memory; per-warp sorted top-k in registers (topk.cuh).  Used for small trees and as
+//     the scan of the not-yet-indexed tail.
+//   * wide bounding-box tree (knn_bvh.cuh): 32-ary hierarchy over a spatially sorted copy,
+//     warp-cooperative traversal.  Used for large trees.
+#include "common.cuh"
+#include "knn_bvh.cuh"
+#include "space.cuh"
+#include "topk.cuh"
+
+namespace mptg {
+
+// ---------------------------------------------------------------------------------------------
+// brute force
+// ---------------------------------------------------------------------------------------------
+template <typename S>
+struct BruteArgs {
+    const S* pts;
+    uint32_t stride;
+    uint32_t begin, end;  // scan points [begin, end)
+    const S* queries;     // AoS
+    uint32_t Q, k;
+    S radius;
+    uint32_t chunk;  // points per split (multiple of tile)
+    uint32_t tile;   // points per shared-memory tile (multiple of 32)
+    uint32_t idxMul, idxAdd;
+    uint32_t* idxOut;  // [split][Q][k]
+    S* distOut;
+    uint32_t* countOut;  // [Q], only written when gridDim.y == 1
+    DevSpace<S> sp;
+};
+
+constexpr int BRUTE_WARPS = 8;
+
+template <typename S, int SHAPE, int KPL>
+__global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteKernel(const BruteArgs<S> a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* tile = reinterpret_cast<S*>(smemRaw);                    // [D][a.tile]
+    S* qsm = tile + (size_t)a.sp.D * a.tile;                    // [BRUTE_WARPS][D]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q = blockIdx.x * BRUTE_WARPS + warp;
+    const bool active = q < a.Q;
+
+    // query -> shared (generic path reads it from there) and registers (fast paths)
+    S* myq = qsm + warp * D;
+    if (active)
+        for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+    __syncwarp();
+    S qr[7];
+    if (SHAPE == SHAPE_SE3) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) qr[c] = active ? myq[c] : S(0);
+    } else if (SHAPE == SHAPE_L2_2 || SHAPE == SHAPE_L2_3) {
+#pragma unroll
+        for (int c = 0; c < (SHAPE == SHAPE_L2_2 ? 2 : 3); ++c) qr[c] = active ? myq[c] : S(0);
+    }
+
+    WarpTopK<S, KPL> top;
+    top.init(a.k);
+
+    // prefilter threshold on the squared translation distance (fast paths): skip when surely d > thr
+    S thr2 = fp::consts<S>::inf();
+    auto refreshThr = [&]() {
+        S thr = top.kthD < a.radius ? top.kthD : a.radius;
+        if (SHAPE == SHAPE_SE3 && a.sp.weighted[1]) thr = fp::div_(thr, a.sp.weight[1]) * (S(1) + S(8) * fp::consts<S>::eps());
+        S t2 = thr * thr;
+        thr2 = t2 + t2 * (S(16) * fp::consts<S>::eps());  // generous slack: sqrt/round can only shrink d by < 1 ulp
+    };
+    refreshThr();
+
+    const uint32_t splitBegin = a.begin + blockIdx.y * a.chunk;
+    const uint32_t splitEnd = min(a.end, splitBegin + a.chunk);
+
+    for (uint32_t t0 = splitBegin; t0 < splitEnd; t0 += a.tile) {
+        const uint32_t cnt = min(a.tile, splitEnd - t0);
+        __syncthreads();  // previous tile fully consumed
+        for (int c = 0; c < D; ++c) {
+            const S* row = a.pts + (size_t)c * a.stride + t0;
+            for (uint32_t p = threadIdx.x; p < cnt; p += blockDim.x) tile[(size_t)c * a.tile + p] = __ldg(row + p);
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (uint32_t base = 0; base < cnt; base += 32) {
+            const uint32_t p = base + lane;
+            const bool have = p < cnt;
+            const uint32_t pp = have ? p : 0;
+            const uint32_t gi = (t0 + pp) * a.idxMul + a.idxAdd;
+            S dist;
+            bool cand = have;
+            if (SHAPE == SHAPE_SE3) {
+                const S d0 = tile[4 * a.tile + pp] - qr[4], d1 = tile[5 * a.tile + pp] - qr[5],
+                        d2 = tile[6 * a.tile + pp] - qr[6];
+                S s = d0 * d0;
+                s = fp::fma_(d1, d1, s);
+                s = fp::fma_(d2, d2, s);
+                cand = cand && s <= thr2;
+                if (!__any_sync(FULL_MASK, cand)) continue;
+                S dt = fp::sqrt_(s);
+                if (a.sp.weighted[1]) dt = dt * a.sp.weight[1];
+                S dr = dev::so3Dist<S>(tile[0 * a.tile + pp], tile[1 * a.tile + pp], tile[2 * a.tile + pp],
+                                       tile[3 * a.tile + pp], qr[0], qr[1], qr[2], qr[3]);
+                if (a.sp.weighted[0]) dr = dr * a.sp.weight[0];
+                dist = dr + dt;
+            } else if (SHAPE == SHAPE_L2_2 || SHAPE == SHAPE_L2_3) {
+                const S d0 = tile[0 * a.tile + pp] - qr[0], d1 = tile[1 * a.tile + pp] - qr[1];
+                S s = d0 * d0;
+                s = fp::fma_(d1, d1, s);
+                if (SHAPE == SHAPE_L2_3) {
+                    const S d2 = tile[2 * a.tile + pp] - qr[2];
+                    s = fp::fma_(d2, d2, s);
+                }
+                cand = cand && s <= thr2;
+                if (!__any_sync(FULL_MASK, cand)) continue;
+                dist = fp::sqrt_(s);
+            } else {
+                dist = dev::distance<S>(
+                    a.sp, [&](int c) { return tile[(size_t)c * a.tile + pp]; }, [&](int c) { return myq[c]; });
+            }
+            const S oldKth = top.kthD;
+            top.offer(cand, dist, gi, a.radius, lane);
+            if (SHAPE != SHAPE_GENERIC && top.kthD != oldKth) refreshThr();
+        }
+    }
+    if (active) {
+        const size_t row = ((size_t)blockIdx.y * a.Q + q) * a.k;
+        const uint32_t count = top.store(a.k, a.idxOut + row, a.distOut + row, lane);
+        if (gridDim.y == 1 && a.countOut && lane == 0) a.countOut[q] = count;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// merge of `parts` sorted candidate lists per query (split-N brute force, tail + index, multi-GPU)
+// ---------------------------------------------------------------------------------------------
+template <typename S, int KPL>
+__global__ void __launch_bounds__(256) knnMergeKernel(uint32_t parts, uint32_t Q, uint32_t k, const uint32_t* idxIn,
+                                                      const S* distIn, uint32_t* idxOut, S* distOut,
+                                                      uint32_t* countOut) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    WarpTopK<S, KPL> top;
+    top.init(k);
+    for (uint32_t part = 0; part < parts; ++part) {
+        const size_t row = ((size_t)part * Q + q) * k;
+        for (uint32_t base = 0; base < k; base += 32) {
+            const uint32_t j = base + lane;
+            const bool have = j < k;
+            const S d = have ? distIn[row + j] : fp::consts<S>::inf();
+            const uint32_t i = have ? idxIn[row + j] : MPTG_NO_INDEX;
+            top.offer(have && i != MPTG_NO_INDEX, d, i, fp::consts<S>::inf(), lane);
+        }
+    }
+    const uint32_t count = top.store(k, idxOut + (size_t)q * k, distOut + (size_t)q * k, lane);
+    if (countOut && lane == 0) countOut[q] = count;
+}
+
+// AoS -> SoA append
+template <typename S>
+__global__ void knnScatterKernel(const S* aos, uint32_t count, int D, S* pts, uint32_t stride, uint32_t first) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * (uint32_t)D) return;
+    const uint32_t i = t / D, c = t % D;
+    pts[(size_t)c * stride + first + i] = aos[t];
+}
+template <typename S>
+__global__ void knnGatherKernel(const S* pts, uint32_t stride, uint32_t first, uint32_t count, int D, S* aos) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * (uint32_t)D) return;
+    const uint32_t i = t / D, c = t % D;
+    aos[t] = pts[(size_t)c * stride + first + i];
+}
+
+}  // namespace mptg
+
+using namespace mptg;
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct mptg_knn {
+    mptg_ctx* ctx = nullptr;
+    mptg_space_desc space{};
+    int D = 0;
+    int scalar = MPTG_F32;
+    SpaceShape shape = SHAPE_GENERIC;
+    uint32_t capacity = 0, stride = 0, size = 0;
+    void* pts = nullptr;  // SoA [D][stride]
+    int strategy = MPTG_KNN_AUTO;
+    uint32_t idxMul = 1, idxAdd = 0;
+    uint64_t stats[4] = {0, 0, 0, 0};
+    KnnIndex index;  // knn_bvh.cuh
+};
+
+namespace {
+
+template <typename S>
+int launchMerge(mptg_ctx* ctx, uint32_t parts, uint32_t Q, uint32_t k, const uint32_t* idxIn, const S* distIn,
+                uint32_t* idxOut, S* distOut, uint32_t* countOut) {
+    if (Q == 0) return MPTG_OK;
+    const dim3 grid((Q + 7) / 8), block(256);
+    if (k <= 32) knnMergeKernel<S, 1><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
+    else if (k <= 64) knnMergeKernel<S, 2><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
+    else knnMergeKernel<S, 4><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+
+template <typename S, int SHAPE>
+int launchBruteShape(mptg_ctx* ctx, const BruteArgs<S>& a, dim3 grid, size_t smem) {
+    const dim3 block(BRUTE_WARPS * 32);
+#define MPTG_BRUTE(KPL)                                                                                              \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            MPTG_CUDA(ctx, cudaFuncSetAttribute(knnBruteKernel<S, SHAPE, KPL>,                                       \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        knnBruteKernel<S, SHAPE, KPL><<<grid, block, smem, ctx->stream>>>(a);                                        \
+    } while (0)
+    if (a.k <= 32) MPTG_BRUTE(1);
+    else if (a.k <= 64) MPTG_BRUTE(2);
+    else MPTG_BRUTE(4);
+#undef MPTG_BRUTE
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+
+// Scan points [begin,end) for all queries; results (k per query) to idxOut/distOut/countOut (device).
+template <typename S>
+int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uint32_t Q, uint32_t k, double radius,
+              uint32_t* idxOut, S* distOut, uint32_t* countOut) {
+    mptg_ctx* ctx = knn->ctx;
+    const int D = knn->D;
+    // tile: <= 32 KB of shared memory, multiple of 32 points, <= 1024
+    uint32_t tile = (uint32_t)((32 * 1024) / (D * sizeof(S)));
+    tile = tile > 1024 ? 1024 : (tile / 32) * 32;
+    if (tile < 32) tile = 32;
+    const uint32_t n = end - begin;
+    const uint32_t qBlocks = (Q + BRUTE_WARPS - 1) / BRUTE_WARPS;
+    // split the scan so that the grid fills the machine (~4 CTAs per SM) when there are few queries
+    uint32_t splits = 1;
+    const uint32_t wantCtas = (uint32_t)ctx->smCount * 4;
+    if (qBlocks < wantCtas) {
+        splits = (wantCtas + qBlocks - 1) / qBlocks;
+        const uint32_t maxSplits = (n + tile - 1) / tile;
+        if (splits > maxSplits) splits = maxSplits ? maxSplits : 1;
+        if (splits > 64) splits = 64;
+    }
+    uint32_t chunk = (n + splits - 1) / splits;
+    chunk = ((chunk + tile - 1) / tile) * tile;
+    if (chunk == 0) chunk = tile;
+    splits = n ? (n + chunk - 1) / chunk : 1;
+
+    BruteArgs<S> a{};
+    a.pts = (const S*)knn->pts;
+    a.stride = knn->stride;
+    a.begin = begin;
+    a.end = end;
+    a.queries = queries;
+    a.Q = Q;
+    a.k = k;
+    a.radius = (radius >= 0 && radius == radius) ? (S)radius : fp::consts<S>::inf();
+    a.chunk = chunk;
+    a.tile = tile;
+    a.idxMul = knn->idxMul;
+    a.idxAdd = knn->idxAdd;
+    a.sp = makeDevSpace<S>(knn->space);
+    a.countOut = countOut;
+    uint32_t* scrIdx = nullptr;
+    S* scrDist = nullptr;
+    if (splits > 1) {
+        void* p0;
+        void* p1;
+        int rc = scratch(ctx, 2, (size_t)splits * Q * k * sizeof(uint32_t), &p0);
+        if (rc) return rc;
+        rc = scratch(ctx, 3, (size_t)splits * Q * k * sizeof(S), &p1);
+        if (rc) return rc;
+        scrIdx = (uint32_t*)p0;
+        scrDist = (S*)p1;
+        a.idxOut = scrIdx;
+        a.distOut = scrDist;
+    } else {
+        a.idxOut = idxOut;
+        a.distOut = distOut;
+    }
+    const size_t smem = ((size_t)D * tile + (size_t)BRUTE_WARPS * D) * sizeof(S);
+    const dim3 grid(qBlocks, splits);
+    int rc;
+    switch (knn->shape) {
+        case SHAPE_SE3: rc = launchBruteShape<S, SHAPE_SE3>(ctx, a, grid, smem); break;
+        case SHAPE_L2_2: rc = launchBruteShape<S, SHAPE_L2_2>(ctx, a, grid, smem); break;
+        case SHAPE_L2_3: rc = launchBruteShape<S, SHAPE_L2_3>(ctx, a, grid, smem); break;
+        default: rc = launchBruteShape<S, SHAPE_GENERIC>(ctx, a, grid, smem); break;
+    }
+    if (rc) return rc;
+    if (splits > 1) rc = launchMerge<S>(ctx, splits, Q, k, scrIdx, scrDist, idxOut, distOut, countOut);
+    knn->stats[0] += (uint64_t)n * Q;
+    return rc;
+}
+
+template <typename S>
+int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double radius, uint32_t* idxOut, S* distOut,
+              uint32_t* countOut) {
+    mptg_ctx* ctx = knn->ctx;
+    knn->stats[0] = knn->stats[1] = 0;
+    int strategy = knn->strategy;
+    if (strategy == MPTG_KNN_AUTO) strategy = knnAutoStrategy(knn->size, Q, knn->index);
+    uint32_t indexed = 0;
+    if (strategy == MPTG_KNN_BVH) {
+        int rc = knnEnsureIndex<S>(ctx, knn->index, knn->space, (const S*)knn->pts, knn->stride, knn->size);
+        if (rc) return rc;
+        indexed = knn->index.count;
+    }
+    knn->stats[2] = indexed;
+    knn->stats[3] = (uint64_t)strategy;
+    if (indexed == 0) return bruteScan<S>(knn, 0, knn->size, queries, Q, k, radius, idxOut, distOut, countOut);
+
+    // indexed prefix via the tree, unindexed tail by brute force, then merge the two lists
+    const bool tail = indexed < knn->size;
+    uint32_t* i0 = idxOut;
+    S* d0 = distOut;
+    if (tail) {
+        void* p0;
+        void* p1;
+        int rc = scratch(ctx, 4, (size_t)2 * Q * k * sizeof(uint32_t), &p0);
+        if (rc) return rc;
+        rc = scratch(ctx, 5, (size_t)2 * Q * k * sizeof(S), &p1);
+        if (rc) return rc;
+        i0 = (uint32_t*)p0;
+        d0 = (S*)p1;
+    }
+    int rc = knnBvhQuery<S>(ctx, knn->index, knn->space, queries, Q, k, radius, knn->idxMul, knn->idxAdd, i0, d0,
+                            tail ? nullptr : countOut, knn->stats);
+    if (rc) return rc;
+    if (tail) {
+        rc = bruteScan<S>(knn, indexed, knn->size, queries, Q, k, radius, i0 + (size_t)Q * k, d0 + (size_t)Q * k, nullptr);
+        if (rc) return rc;
+        rc = launchMerge<S>(ctx, 2, Q, k, i0, d0, idxOut, distOut, countOut);
+    }
+    return rc;
+}
+
+template <typename S>
+int insertDevT(mptg_knn* knn, const S* aosDev, uint32_t count) {
+    const uint32_t total = count * (uint32_t)knn->D;
+    knnScatterKernel<S><<<(total + 255) / 256, 256, 0, knn->ctx->stream>>>(aosDev, count, knn->D, (S*)knn->pts,
+                                                                             knn->stride, knn->size);
+    MPTG_LAUNCHED(knn->ctx);
+    return MPTG_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int mptg_knn_create(mptg_ctx* ctx, const mptg_space_desc* space, uint32_t capacity, mptg_knn** out) {
+    if (!ctx || !space || !out || capacity == 0) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_knn_create: bad argument");
+    const int D = spaceScalars(space);
+    if (D <= 0) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_knn_create: malformed space descriptor");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto* k = new mptg_knn();
+    k->ctx = ctx;
+    k->space = *space;
+    k->D = D;
+    k->scalar = space->scalar;
+    k->shape = classifySpace(*space);
+    k->capacity = capacity;
+    k->stride = ((capacity + 255u) / 256u) * 256u;
+    cudaError_t e = cudaMalloc(&k->pts, (size_t)D * k->stride * space->scalar);
+    if (e != cudaSuccess) {
+        delete k;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? MPTG_ERR_OOM : MPTG_ERR_CUDA, "mptg_knn_create: cudaMalloc(%zu) failed: %s",
+                    (size_t)D * k->stride * space->scalar, cudaGetErrorString(e));
+    }
+    *out = k;
+    return MPTG_OK;
+}
+
+int mptg_knn_destroy(mptg_knn* knn) {
+    if (!knn) return MPTG_OK;
+    cudaSetDevice(knn->ctx->device);
+    cudaStreamSynchronize(knn->ctx->stream);
+    knnIndexFree(knn->index);
+    cudaFree(knn->pts);
+    delete knn;
+    return MPTG_OK;
+}
+
+int mptg_knn_set_strategy(mptg_knn* knn, int strategy) {
+    if (!knn || strategy < MPTG_KNN_AUTO || strategy > MPTG_KNN_BVH) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_set_strategy: bad argument");
+    knn->strategy = strategy;
+    return MPTG_OK;
+}
+
+int mptg_knn_set_index_map(mptg_knn* knn, uint32_t mul, uint32_t add) {
+    if (!knn || mul == 0) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_set_index_map: bad argument");
+    knn->idxMul = mul;
+    knn->idxAdd = add;
+    return MPTG_OK;
+}
+
+uint32_t mptg_knn_size(const mptg_knn* knn) { return knn ? knn->size : 0; }
+
+int mptg_knn_insert_dev(mptg_knn* knn, const void* statesDev, uint32_t count, uint32_t* firstOut) {
+    if (!knn || (!statesDev && count)) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_insert: bad argument");
+    if ((uint64_t)knn->size + count > knn->capacity)
+        return fail(knn->ctx, MPTG_ERR_CAPACITY, "mptg_knn_insert: %u + %u exceeds capacity %u", knn->size, count, knn->capacity);
+    if (firstOut) *firstOut = knn->size;
+    if (count == 0) return MPTG_OK;
+    MPTG_CUDA(knn->ctx, cudaSetDevice(knn->ctx->device));
+    int rc = knn->scalar == MPTG_F32 ? insertDevT<float>(knn, (const float*)statesDev, count)
+                                     : insertDevT<double>(knn, (const double*)statesDev, count);
+    if (rc) return rc;
+    knn->size += count;
+    return MPTG_OK;
+}
+
+int mptg_knn_insert(mptg_knn* knn, const void* states, uint32_t count, uint32_t* firstOut) {
+    if (!knn || (!states && count)) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_insert: bad argument");
+    if ((uint64_t)knn->size + count > knn->capacity)
+        return fail(knn->ctx, MPTG_ERR_CAPACITY, "mptg_knn_insert: %u + %u exceeds capacity %u", knn->size, count, knn->capacity);
+    if (count == 0) {
+        if (firstOut) *firstOut = knn->size;
+        return MPTG_OK;
+    }
+    mptg_ctx* ctx = knn->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)count * knn->D * knn->scalar;
+    void* stage;
+    int rc = scratch(ctx, 0, bytes, &stage);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(stage, states, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mptg_knn_insert_dev(knn, stage, count, firstOut);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller may reuse `states`
+    return MPTG_OK;
+}
+
+int mptg_knn_get_states(mptg_knn* knn, uint32_t first, uint32_t count, void* out) {
+    if (!knn || !out || (uint64_t)first + count > knn->size) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_get_states: bad range");
+    if (count == 0) return MPTG_OK;
+    mptg_ctx* ctx = knn->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)count * knn->D * knn->scalar;
+    void* stage;
+    int rc = scratch(ctx, 0, bytes, &stage);
+    if (rc) return rc;
+    const uint32_t total = count * (uint32_t)knn->D;
+    if (knn->scalar == MPTG_F32)
+        knnGatherKernel<float><<<(total + 255) / 256, 256, 0, ctx->stream>>>((const float*)knn->pts, knn->stride, first, count, knn->D, (float*)stage);
+    else
+        knnGatherKernel<double><<<(total + 255) / 256, 256, 0, ctx->stream>>>((const double*)knn->pts, knn->stride, first, count, knn->D, (double*)stage);
+    MPTG_LAUNCHED(ctx);
+    MPTG_CUDA(ctx, cudaMemcpyAsync(out, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
+int mptg_knn_query_dev(mptg_knn* knn, const void* queriesDev, uint32_t Q, uint32_t k, double radius,
+                       uint32_t* idxOutDev, void* distOutDev, uint32_t* countOutDev) {
+    if (!knn || (!queriesDev && Q) || !idxOutDev || !distOutDev)
+        return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_query: bad argument");
+    if (k == 0 || k > MPTG_MAX_K) return fail(knn->ctx, MPTG_ERR_BAD_ARG, "mptg_knn_query: k=%u out of range 1..%d", k, MPTG_MAX_K);
+    if (Q == 0) return MPTG_OK;
+    MPTG_CUDA(knn->ctx, cudaSetDevice(knn->ctx->device));
+    return knn->scalar == MPTG_F32
+               ? queryDevT<float>(knn, (const float*)queriesDev, Q, k, radius, idxOutDev, (float*)distOutDev, countOutDev)
+               : queryDevT<double>(knn, (const double*)queriesDev, Q, k, radius, idxOutDev, (double*)distOutDev, countOutDev);
+}
+
+int mptg_knn_query(mptg_knn* knn, const void* queries, uint32_t Q, uint32_t k, double radius, uint32_t* idxOut,
+                   void* distOut, uint32_t* countOut) {
+    if (!knn || (!queries && Q) || !idxOut || !distOut) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_query: bad argument");
+    if (k == 0 || k > MPTG_MAX_K) return fail(knn->ctx, MPTG_ERR_BAD_ARG, "mptg_knn_query: k=%u out of range 1..%d", k, MPTG_MAX_K);
+    if (Q == 0) return MPTG_OK;
+    mptg_ctx* ctx = knn->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qBytes = (size_t)Q * knn->D * knn->scalar;
+    const size_t iBytes = (size_t)Q * k * sizeof(uint32_t), dBytes = (size_t)Q * k * knn->scalar, cBytes = (size_t)Q * sizeof(uint32_t);
+    void* dq;
+    void* dout;
+    int rc = scratch(ctx, 0, qBytes, &dq);
+    if (rc) return rc;
+    rc = scratch(ctx, 1, iBytes + dBytes + cBytes, &dout);
+    if (rc) return rc;
+    // dist first (8-byte aligned for f64), then idx, then counts
+    void* dDist = dout;
+    uint32_t* dIdx = (uint32_t*)((char*)dout + dBytes);
+    uint32_t* dCnt = (uint32_t*)((char*)dout + dBytes + iBytes);
+    MPTG_CUDA(ctx, cudaMemcpyAsync(dq, queries, qBytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = mptg_knn_query_dev(knn, dq, Q, k, radius, dIdx, dDist, dCnt);
+    if (rc) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(distOut, dDist, dBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaMemcpyAsync(idxOut, dIdx, iBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (countOut) MPTG_CUDA(ctx, cudaMemcpyAsync(countOut, dCnt, cBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
+int mptg_knn_build_index(mptg_knn* knn) {
+    if (!knn) return fail(nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_build_index: null handle");
+    MPTG_CUDA(knn->ctx, cudaSetDevice(knn->ctx->device));
+    knn->index.count = 0;  // force a rebuild over everything stored so far
+    return knn->scalar == MPTG_F32
+               ? knnBuildIndex<float>(knn->ctx, knn->index, knn->space, (const float*)knn->pts, knn->stride, knn->size)
+               : knnBuildIndex<double>(knn->ctx, knn->index, knn->space, (const double*)knn->pts, knn->stride, knn->size);
+}
+
+int mptg_knn_last_stats(mptg_knn* knn, uint64_t out[4]) {
+    if (!knn || !out) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_last_stats: bad argument");
+    // device-side counters of the tree search are folded in on demand
+    int rc = knnIndexReadStats(knn->ctx, knn->index, knn->stats);
+    if (rc) return rc;
+    for (int i = 0; i < 4; ++i) out[i] = knn->stats[i];
+    return MPTG_OK;
+}
+
+int mptg_knn_merge_dev(mptg_ctx* ctx, int scalar, uint32_t parts, uint32_t Q, uint32_t k, const uint32_t* idxIn,
+                       const void* distIn, uint32_t* idxOut, void* distOut, uint32_t* countOut) {
+    if (!ctx || !idxIn || !distIn || !idxOut || !distOut || parts == 0 || k == 0 || k > MPTG_MAX_K)
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_knn_merge_dev: bad argument");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (scalar == MPTG_F32) return launchMerge<float>(ctx, parts, Q, k, idxIn, (const float*)distIn, idxOut, (float*)distOut, countOut);
+    if (scalar == MPTG_F64) return launchMerge<double>(ctx, parts, Q, k, idxIn, (const double*)distIn, idxOut, (double*)distOut, countOut);
+    return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_knn_merge_dev: bad scalar");
+}
+
+}  // extern "C"

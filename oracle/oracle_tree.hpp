@@ -147,7 +147,7 @@ struct BoxTree {
                 if (ad > S(1)) ad = S(1);
                 if (ad < S(0)) ad = S(0);
                 // acos01 is a polynomial and not proven monotone in the last ulp: shave the bound
-                d = fp::acos01(ad) * (S(1) - S(4) * fp::consts<S>::eps());
+                d = fp::acos01(ad) * (S(1) - S(8) * fp::consts<S>::eps());
             }
             if (part.weight != 1.0) d = d * S(part.weight);
             total = (i == 0) ? d : total + d;

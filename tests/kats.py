@@ -1,0 +1,99 @@
+"""The reference's own known-answer tests for the hot-path arithmetic,
+transcribed as data so that the CPU oracle AND the CUDA kernels are checked against the same table.
+
+Each entry cites the reference test it restates (paths relative to the reference root).  Expected
+values are computed with the same double-precision expressions the reference test writes
+(Python floats are IEEE doubles).  `tol` None means exact equality, as in the reference's EXPECT ==.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+import mpt_b200 as m
+
+F64 = m.F64
+PI = math.pi
+
+
+def angle_axis(angle, axis):
+    """Eigen::AngleAxisd(angle, axis) -> quaternion coeffs (x,y,z,w)."""
+    s, c = math.sin(angle / 2), math.cos(angle / 2)
+    return [axis[0] * s, axis[1] * s, axis[2] * s, c]
+
+
+def to_angle_axis(q):
+    """Eigen::AngleAxisd(Quaterniond) -> (angle, axis)."""
+    n = math.sqrt(q[0] ** 2 + q[1] ** 2 + q[2] ** 2)
+    angle = 2 * math.atan2(n, abs(q[3]))
+    if q[3] < 0:
+        n = -n
+    return angle, [q[0] / n, q[1] / n, q[2] / n]
+
+
+AXIS = [v / math.sqrt(14.0) for v in (-1.0, 2.0, 3.0)]
+SQRT20 = math.sqrt(0.0 + 2.0 * 2.0 + 4.0 * 4.0)
+
+
+def distance_kats():
+    """-> list of (name, space, a, b, expected, tol)"""
+    k = []
+    k.append(("lp_space_test.cpp:39-50", m.lp_space(3, 2, F64), [1, 2, 3], [1, 0, -1], SQRT20, None))
+    k.append(("scaled_space_test.cpp:40-52", m.lp_space(3, 2, F64, 5.0 / 2.0), [1, 2, 3], [1, 0, -1], SQRT20 * 5 / 2, None))
+    so2 = m.so2_space(1, 1, F64)
+    for a, b, e in ((1.0, 1.0, 0.0), (0.0, 2.0, 2.0), (2.0, 0.0, 2.0), (-1.0, 3.0, 2 * PI - 4.0), (3.0, -1.0, 2 * PI - 4.0)):
+        k.append(("so2_space_test.cpp:46-50", so2, [a], [b], e, None))
+    k.append(("so2_space_test.cpp:54-65", m.so2_space(3, 1, F64), [1, 2, 3], [1, 0, -1], 0.0 + 2.0 + 2 * PI - 4, None))
+    k.append(("so3_space_test.cpp:39-56", m.so3_space(F64), angle_axis(-1.0, AXIS), angle_axis(2.0, AXIS), 3.0 / 2, 1e-10))
+    for so3w, l2w in ((1, 1), (5, 2), (11, 1), (1, 13)):
+        a = angle_axis(-1.0, AXIS) + [1, 2, 3]
+        b = angle_axis(2.0, AXIS) + [1, 0, -1]
+        k.append((f"se3_space_test.cpp:45-90 ({so3w},{l2w})", m.se3_space(so3w, l2w, F64), a, b, 3.0 / 2 * so3w + SQRT20 * l2w, 1e-9))
+        k.append((f"se2_space_test.cpp:45-84 ({so3w},{l2w})", m.se2_space(so3w, l2w, F64), [2, 3, -1.0], [0, -1, 2.0],
+                  3.0 * so3w + SQRT20 * l2w, None))
+    return k
+
+
+def interpolate_kats():
+    """-> list of (name, space, a, b, t, checker(result) -> bool)"""
+    k = []
+    k.append(("lp_space_test.cpp:53-66", m.lp_space(3, 2, F64), [1, 2, 3], [1, 0, -1], 0.1,
+              lambda c: c[0] == 1.0 and c[1] == 1.8 and c[2] == 2.6))
+    so2 = m.so2_space(1, 1, F64)
+    for a, b, t, e in (
+        (1.0, 1.0, 0.0, 1.0), (1.0, 1.0, 3.0, 1.0), (1.0, 2.0, 0.5, 1.5), (1.0, 2.0, -3.0, -2.0),
+        (-1.0, 2.0, 4.0, 11.0 - 4 * PI), (5 * PI / 6, -5 * PI / 6, 1.0, -5 * PI / 6),
+        (5 * PI / 6, -5 * PI / 6, 2.0, -3 * PI / 6), (-5 * PI / 6, 5 * PI / 6, 2.0, 3 * PI / 6),
+    ):
+        k.append(("so2_space_test.cpp:67-84", so2, [a], [b], t, (lambda e: lambda c: c[0] == e)(e)))
+
+    def slerp_ok(c):
+        ang, ax = to_angle_axis(c[:4])
+        return sum((x - y) ** 2 for x, y in zip(ax, AXIS)) < 1e-15 and abs(ang - (0.5 + 2 * 0.1)) < 1e-10
+
+    k.append(("so3_space_test.cpp:58-79", m.so3_space(F64), angle_axis(0.5, AXIS), angle_axis(2.5, AXIS), 0.1, slerp_ok))
+    k.append(("se3_space_test.cpp:92-118", m.se3_space(1, 1, F64), angle_axis(0.5, AXIS) + [1, 2, 3],
+              angle_axis(2.5, AXIS) + [1, 0, -1], 0.1,
+              lambda c: slerp_ok(c) and c[4] == 1.0 and c[5] == 1.8 and c[6] == 2.6))
+    return k
+
+
+def run_distance_kats(distance_fn):
+    """distance_fn(space, a[1,D], b[1,D]) -> array[1].  Returns list of failure strings."""
+    bad = []
+    for name, sp, a, b, exp, tol in distance_kats():
+        got = float(distance_fn(sp, np.asarray([a], dtype=np.float64), np.asarray([b], dtype=np.float64))[0])
+        ok = got == exp if tol is None else abs(got - exp) < tol
+        if not ok:
+            bad.append(f"{name}: got {got!r}, expected {exp!r}")
+    return bad
+
+
+def run_interpolate_kats(interp_fn):
+    bad = []
+    for name, sp, a, b, t, chk in interpolate_kats():
+        got = interp_fn(sp, np.asarray([a], dtype=np.float64), np.asarray([b], dtype=np.float64), t)[0]
+        if not chk([float(x) for x in got]):
+            bad.append(f"{name}: got {got!r}")
+    return bad

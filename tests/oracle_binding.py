@@ -1,0 +1,199 @@
+"""ctypes binding of oracle/_build/liboracle.so -- the CPU restatement of the reference path.
+
+TEST INFRASTRUCTURE: used by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ODIR = ROOT / "oracle"
+LIB = ODIR / "_build" / "liboracle.so"
+
+F32, F64 = 4, 8
+_P = C.c_void_p
+
+
+def build(force: bool = False):
+    if force or not LIB.exists() or any(
+        p.stat().st_mtime > LIB.stat().st_mtime
+        for p in list(ODIR.glob("*.cpp")) + list(ODIR.glob("*.hpp")) + list((ROOT / "include" / "mptg").glob("*.h"))
+    ):
+        subprocess.run(["make", "-C", str(ODIR), "-j4"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.orc_num_threads.restype = C.c_int
+        lib.orc_tree_create.restype = _P
+        lib.orc_tree_create.argtypes = [_P, _P, C.c_uint32]
+        lib.orc_tree_destroy.argtypes = [_P]
+        lib.orc_tree_knn.argtypes = [_P, _P, C.c_uint32, C.c_uint32, C.c_double, _P, _P, _P, _P]
+        for f in ("orc_grid_create", "orc_shapes_create", "orc_linkarm_create", "orc_mesh_pair_create"):
+            getattr(lib, f).restype = _P
+        lib.orc_grid_create.argtypes = [C.c_int, C.c_int, C.c_int, _P]
+        lib.orc_shapes_create.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]
+        lib.orc_linkarm_create.argtypes = [C.c_int, C.c_int, _P, C.c_double, C.c_int, _P]
+        lib.orc_mesh_pair_create.argtypes = [C.c_int, C.c_uint32, _P, C.c_uint32, _P]
+        lib.orc_geom_destroy.argtypes = [_P]
+        lib.orc_valid_batch.argtypes = [_P, _P, C.c_uint32, _P, _P]
+        lib.orc_link_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, C.c_double, _P, _P, C.c_double, _P]
+        lib.orc_geom_counters.argtypes = [_P, _P]
+        lib.orc_distance_batch.argtypes = [_P, _P, _P, C.c_uint32, _P]
+        lib.orc_interpolate_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, _P]
+        lib.orc_steer_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, C.c_double, _P, _P]
+        lib.orc_knn.argtypes = [_P, _P, C.c_uint32, _P, C.c_uint32, C.c_uint32, C.c_double, _P, _P, _P]
+        lib.orc_acos01f.restype = C.c_double
+        lib.orc_acos01f.argtypes = [C.c_float]
+        lib.orc_acos01d.restype = C.c_double
+        lib.orc_acos01d.argtypes = [C.c_double]
+
+    @property
+    def threads(self) -> int:
+        return self.lib.orc_num_threads()
+
+    def set_threads(self, n: int):
+        self.lib.orc_set_num_threads(int(n))
+
+    # space: mpt_b200.Space (only its ctypes desc is used -- same struct layout as include/mptg/mptg.h)
+    def distance(self, space, a, b):
+        a = np.ascontiguousarray(a, dtype=space.dtype).reshape(-1, space.scalars)
+        b = np.ascontiguousarray(b, dtype=space.dtype).reshape(-1, space.scalars)
+        out = np.empty(a.shape[0], dtype=space.dtype)
+        self.lib.orc_distance_batch(space.ref, _ptr(a), _ptr(b), a.shape[0], _ptr(out))
+        return out
+
+    def interpolate(self, space, a, b, t):
+        a = np.ascontiguousarray(a, dtype=space.dtype).reshape(-1, space.scalars)
+        b = np.ascontiguousarray(b, dtype=space.dtype).reshape(-1, space.scalars)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=space.dtype), (a.shape[0],)))
+        out = np.empty_like(a)
+        self.lib.orc_interpolate_batch(space.ref, _ptr(a), _ptr(b), _ptr(t), a.shape[0], _ptr(out))
+        return out
+
+    def steer(self, space, near, sample, d, rng, with_distance=False):
+        near = np.ascontiguousarray(near, dtype=space.dtype).reshape(-1, space.scalars)
+        sample = np.ascontiguousarray(sample, dtype=space.dtype).reshape(-1, space.scalars)
+        d = np.ascontiguousarray(d, dtype=space.dtype)
+        out = np.empty_like(near)
+        dist = np.empty(near.shape[0], dtype=space.dtype) if with_distance else None
+        self.lib.orc_steer_batch(space.ref, _ptr(near), _ptr(sample), _ptr(d), near.shape[0], float(rng), _ptr(out), _ptr(dist))
+        return (out, dist) if with_distance else out
+
+    def knn(self, space, pts, queries, k, radius=-1.0):
+        pts = np.ascontiguousarray(pts, dtype=space.dtype).reshape(-1, space.scalars)
+        q = np.ascontiguousarray(queries, dtype=space.dtype).reshape(-1, space.scalars)
+        Q = q.shape[0]
+        idx = np.empty((Q, k), dtype=np.uint32)
+        dist = np.empty((Q, k), dtype=space.dtype)
+        cnt = np.empty(Q, dtype=np.uint32)
+        self.lib.orc_knn(space.ref, _ptr(pts), pts.shape[0], _ptr(q), Q, k, float(radius), _ptr(idx), _ptr(dist), _ptr(cnt))
+        return idx, dist, cnt
+
+    def tree(self, space, pts):
+        return OracleTree(self, space, pts)
+
+    def grid(self, occupancy, scalar=F64):
+        occ = np.ascontiguousarray(occupancy, dtype=np.uint8)
+        return OracleGeom(self, self.lib.orc_grid_create(scalar, occ.shape[1], occ.shape[0], _ptr(occ)), scalar, 2)
+
+    def shapes(self, dim, centres, radii, rects=(), scalar=F64):
+        c = np.ascontiguousarray(centres, dtype=np.float64).reshape(-1, dim) if len(radii) else np.zeros((0, dim))
+        r = np.ascontiguousarray(radii, dtype=np.float64)
+        rc = np.ascontiguousarray(rects, dtype=np.float64).reshape(-1, 4) if len(rects) else np.zeros((0, 4))
+        return OracleGeom(self, self.lib.orc_shapes_create(scalar, dim, r.shape[0], _ptr(c), _ptr(r), rc.shape[0], _ptr(rc)), scalar, dim)
+
+    def link_arm(self, lengths, link_radius, circles, scalar=F64):
+        ln = np.ascontiguousarray(lengths, dtype=np.float64)
+        cc = np.ascontiguousarray(circles, dtype=np.float64).reshape(-1, 3)
+        return OracleGeom(self, self.lib.orc_linkarm_create(scalar, ln.shape[0], _ptr(ln), float(link_radius), cc.shape[0], _ptr(cc)), scalar, ln.shape[0])
+
+    def mesh_pair(self, robot_tris, env_tris, space, step):
+        rt = np.ascontiguousarray(robot_tris, dtype=np.float32).reshape(-1, 9)
+        et = np.ascontiguousarray(env_tris, dtype=np.float32).reshape(-1, 9)
+        g = OracleGeom(self, self.lib.orc_mesh_pair_create(space.scalar, rt.shape[0], _ptr(rt), et.shape[0], _ptr(et)), space.scalar, 7)
+        g.space, g.step = space, step
+        return g
+
+
+class OracleTree:
+    def __init__(self, orc, space, pts):
+        self.orc, self.space = orc, space
+        pts = np.ascontiguousarray(pts, dtype=space.dtype).reshape(-1, space.scalars)
+        self.h = orc.lib.orc_tree_create(space.ref, _ptr(pts), pts.shape[0])
+        if not self.h:
+            raise RuntimeError("oracle tree supports float32 spaces only")
+
+    def knn(self, queries, k, radius=-1.0):
+        q = np.ascontiguousarray(queries, dtype=self.space.dtype).reshape(-1, self.space.scalars)
+        Q = q.shape[0]
+        idx = np.empty((Q, k), dtype=np.uint32)
+        dist = np.empty((Q, k), dtype=self.space.dtype)
+        cnt = np.empty(Q, dtype=np.uint32)
+        ev = C.c_uint64()
+        self.orc.lib.orc_tree_knn(self.h, _ptr(q), Q, k, float(radius), _ptr(idx), _ptr(dist), _ptr(cnt), C.byref(ev))
+        self.last_evals = ev.value
+        return idx, dist, cnt
+
+    def __del__(self):
+        try:
+            self.orc.lib.orc_tree_destroy(self.h)
+        except Exception:
+            pass
+
+
+class OracleGeom:
+    def __init__(self, orc, h, scalar, D):
+        self.orc, self.h, self.scalar, self.D = orc, h, scalar, D
+        self.dtype = np.float32 if scalar == F32 else np.float64
+        self.space, self.step = None, 0.0
+
+    def valid(self, states, with_margin=False):
+        s = np.ascontiguousarray(states, dtype=self.dtype).reshape(-1, self.D)
+        ok = np.empty(s.shape[0], dtype=np.uint8)
+        margin = np.empty(s.shape[0], dtype=np.float64) if with_margin else None
+        self.orc.lib.orc_valid_batch(self.h, _ptr(s), s.shape[0], _ptr(ok), _ptr(margin))
+        return (ok, margin) if with_margin else ok
+
+    def link(self, a, b, with_near_contact=False, tol_rel=1e-6):
+        a = np.ascontiguousarray(a, dtype=self.dtype).reshape(-1, self.D)
+        b = np.ascontiguousarray(b, dtype=self.dtype).reshape(-1, self.D)
+        ok = np.empty(a.shape[0], dtype=np.uint8)
+        nc = np.empty(a.shape[0], dtype=np.uint8) if with_near_contact else None
+        states = C.c_uint64()
+        sp = self.space.ref if self.space is not None else None
+        self.orc.lib.orc_link_batch(self.h, sp, _ptr(a), _ptr(b), a.shape[0], float(self.step), _ptr(ok), _ptr(nc), float(tol_rel), C.byref(states))
+        self.last_states = states.value
+        return (ok, nc) if with_near_contact else ok
+
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        self.orc.lib.orc_geom_counters(self.h, out)
+        return {"states": out[0], "bv_tests": out[1], "tri_tests": out[2], "items": out[3]}
+
+    def __del__(self):
+        try:
+            self.orc.lib.orc_geom_destroy(self.h)
+        except Exception:
+            pass
+
+
+_oracle = None
+
+
+def load() -> Oracle:
+    global _oracle
+    if _oracle is None:
+        build()
+        _oracle = Oracle(C.CDLL(str(LIB)))
+    return _oracle

@@ -1,0 +1,308 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmptg.so), against the CPU oracle on
+the same seeded inputs, against the committed golden fixtures and against the reference's KATs.
+
+Bars: kNN indices AND distances bit-identical; grid / shapes / link-arm decisions bit-identical;
+mesh decisions identical except states the oracle flags as within 1e-6 (relative to the scene
+diagonal) of contact, which are counted and reported, never silently dropped."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import mpt_b200 as m
+from mpt_b200 import _lib as L
+from mpt_b200 import workloads as W
+from tests import kats
+from tests.test_oracle import SPACES, random_states
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def assert_knn_equal(got, want):
+    gi, gd, gc = got
+    wi, wd, wc = want
+    assert np.array_equal(gc, wc), "neighbour counts differ"
+    bad = np.nonzero((gi != wi).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} queries differ, first {bad[0]}: {gi[bad[0]]} vs {wi[bad[0]]}; d {gd[bad[0]]} vs {wd[bad[0]]}"
+    assert np.array_equal(gd, wd), "distances not bit-identical"
+
+
+# ------------------------------------------------------------------ metric
+def test_reference_kats_on_device(ctx):
+    """The reference's metric / interpolation known-answer tests, evaluated by the CUDA kernels (f64)."""
+    assert kats.run_distance_kats(ctx.distance) == []
+    assert kats.run_interpolate_kats(ctx.interpolate) == []
+
+
+@pytest.mark.parametrize("name", sorted(SPACES))
+@pytest.mark.parametrize("scalar", [m.F32, m.F64])
+def test_distance_interpolate_bit_exact(ctx, oracle, name, scalar):
+    sp0 = SPACES[name]()
+    parts = [(("lp", "so2", "so3")[sp0.desc.part[i].kind - 1], sp0.desc.part[i].p, sp0.desc.part[i].dim, sp0.desc.part[i].weight)
+             for i in range(sp0.desc.n_parts)]
+    sp = m.Space(parts, scalar)
+    a, b = random_states(sp, 4096, 11), random_states(sp, 4096, 12)
+    b[:16] = a[:16]          # zero distance
+    if name.startswith("se3") or name == "so3":
+        b[16:32, :4] = -a[16:32, :4]  # antipodal quaternions: same rotation (so3_space.hpp:61 quirk path)
+    assert np.array_equal(ctx.distance(sp, a, b), oracle.distance(sp, a, b))
+    t = np.random.default_rng(5).random(4096).astype(sp.dtype)
+    t[:4] = [0, 1, 0.5, 0.25]
+    gi, oi = ctx.interpolate(sp, a, b, t), oracle.interpolate(sp, a, b, t)
+    assert np.array_equal(gi, oi, equal_nan=True)
+    d = oracle.distance(sp, a, b)
+    gs, gd = ctx.steer(sp, a, b, d, 2.5, with_distance=True)
+    os_, od = oracle.steer(sp, a, b, d, 2.5, with_distance=True)
+    assert np.array_equal(gs, os_, equal_nan=True) and np.array_equal(gd, od, equal_nan=True)
+
+
+# ------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("name", sorted(SPACES))
+def test_knn_brute_matches_oracle(ctx, oracle, name):
+    sp = SPACES[name]()
+    pts = random_states(sp, 5000, 1)
+    pts[100] = pts[7]
+    pts[200] = pts[7]
+    q = random_states(sp, 300, 2)
+    q[0] = pts[7]
+    nn = m.Nearest(ctx, sp, 8192, m.KNN_BRUTE)
+    assert nn.insert(pts[:1000]) == 0 and nn.insert(pts[1000:]) == 1000 and nn.size() == 5000
+    assert np.array_equal(nn.states(990, 20), pts[990:1010])
+    for k, radius in ((1, -1.0), (16, -1.0), (33, -1.0), (100, -1.0), (16, 3.0)):
+        assert_knn_equal(nn.nearest(q, k, radius), oracle.knn(sp, pts, q, k, radius))
+    idx, dist, cnt = nn.nearest(q[:1], 3)
+    assert list(idx[0]) == [7, 100, 200] and (dist[0] == 0).all()
+    nn.close()
+
+
+def test_knn_edge_cases(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    nn = m.Nearest(ctx, sp, 64, m.KNN_BRUTE)
+    pts = W.se3_states(5, 3)
+    nn.insert(pts)
+    q = W.se3_states(3, 4)
+    idx, dist, cnt = nn.nearest(q, 8)          # k > n: padded rows
+    assert (cnt == 5).all() and (idx[:, 5:] == L.NO_INDEX).all() and np.isinf(dist[:, 5:]).all()
+    assert_knn_equal((idx, dist, cnt), oracle.knn(sp, pts, q, 8))
+    idx, dist, cnt = nn.nearest(q, 4, radius=1e-3)  # nothing within the radius
+    assert (cnt == 0).all() and (idx == L.NO_INDEX).all()
+    idx, dist, cnt = nn.nearest(np.zeros((0, 7), np.float32), 4)  # empty query batch
+    assert idx.shape == (0, 4)
+    with pytest.raises(m.MptgError):
+        nn.nearest(q, 129)
+    with pytest.raises(m.MptgError):
+        nn.insert(W.se3_states(100, 5))  # over capacity
+    nn.close()
+
+
+def test_knn_few_queries_split_scan(ctx, oracle):
+    """Few queries over many points: the scan is split over CTAs and merged."""
+    sp = m.se3_space(50, 1)
+    pts = W.se3_states(200_000, 7)
+    q = W.se3_states(24, 8)
+    nn = m.Nearest(ctx, sp, 200_000, m.KNN_BRUTE)
+    nn.insert(pts)
+    for k in (1, 16, 49):
+        assert_knn_equal(nn.nearest(q, k), oracle.tree(sp, pts).knn(q, k))
+    nn.close()
+
+
+def test_knn_golden(ctx):
+    g = np.load(ROOT / "tests" / "golden" / "golden.npz")
+    sp = m.se3_space(50, 1)
+    nn = m.Nearest(ctx, sp, 4096)
+    nn.insert(g["se3_pts"])
+    idx, dist, _ = nn.nearest(g["se3_q"], 16)
+    assert np.array_equal(idx, g["se3_knn_idx"]) and np.array_equal(dist, g["se3_knn_dist"])
+    l1 = m.lp_space(8, 1)
+    nn2 = m.Nearest(ctx, l1, 1024)
+    nn2.insert(g["l1_pts"])
+    idx, dist, _ = nn2.nearest(g["l1_q"], 5)
+    assert np.array_equal(idx, g["l1_knn_idx"]) and np.array_equal(dist, g["l1_knn_dist"])
+    assert np.array_equal(ctx.interpolate(sp, g["se3_q"][:32], g["se3_pts"][:32], g["interp_t"]), g["se3_interp"])
+
+
+def test_knn_double_precision(ctx, oracle):
+    sp = m.se3_space(50, 1, m.F64)
+    pts = W.se3_states(3000, 1, dtype=np.float64)
+    q = W.se3_states(100, 2, dtype=np.float64)
+    nn = m.Nearest(ctx, sp, 4096, m.KNN_BRUTE)
+    nn.insert(pts)
+    assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
+
+
+def test_knn_incremental_like_a_planner(ctx, oracle):
+    """Insert in waves, query between waves (the planner's access pattern)."""
+    sp = m.lp_space(2, 2)
+    allpts = W.box_states(6000, 2, 3, 0.0, 1000.0, np.float32)
+    nn = m.Nearest(ctx, sp, 8192)
+    n = 0
+    for wave in (1, 31, 480, 2000, 3488):
+        nn.insert(allpts[n:n + wave])
+        n += wave
+        q = W.box_states(257, 2, 100 + n, 0.0, 1000.0, np.float32)
+        k = min(int(np.ceil(1.1 * np.e * 1.5 * np.log(n + 1))), 128)
+        assert_knn_equal(nn.nearest(q, 1), oracle.knn(sp, allpts[:n], q, 1))
+        assert_knn_equal(nn.nearest(q, k), oracle.knn(sp, allpts[:n], q, k))
+
+
+def test_knn_merge_sharded_equals_single(ctx, oracle):
+    """Tree points dealt round-robin to 4 shards (as on 4 GPUs): per-shard top-k with global indices,
+    then mptg_knn_merge_dev == the single-structure answer."""
+    import torch
+
+    sp = m.se3_space(50, 1)
+    pts = W.se3_states(20_000, 5)
+    q = W.se3_states(512, 6)
+    G, k = 4, 16
+    shards = []
+    for r in range(G):
+        nn = m.Nearest(ctx, sp, 8192, m.KNN_BRUTE)
+        nn.set_index_map(G, r)
+        nn.insert(pts[r::G])
+        shards.append(nn)
+    dq = torch.from_numpy(q).cuda()
+    idx_parts = torch.empty((G, 512, k), dtype=torch.int32, device="cuda")
+    dist_parts = torch.empty((G, 512, k), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for r, nn in enumerate(shards):
+        nn.nearest_dev(dq.data_ptr(), 512, k, -1.0, idx_parts[r].data_ptr(), dist_parts[r].data_ptr())
+    idx = torch.empty((512, k), dtype=torch.int32, device="cuda")
+    dist = torch.empty((512, k), dtype=torch.float32, device="cuda")
+    cnt = torch.empty(512, dtype=torch.int32, device="cuda")
+    m.knn_merge_dev(ctx, m.F32, G, 512, k, idx_parts.data_ptr(), dist_parts.data_ptr(), idx.data_ptr(), dist.data_ptr(), cnt.data_ptr())
+    ctx.sync()
+    got = (idx.cpu().numpy().view(np.uint32), dist.cpu().numpy(), cnt.cpu().numpy().view(np.uint32))
+    assert_knn_equal(got, oracle.tree(sp, pts).knn(q, k))
+
+
+# ------------------------------------------------------------------ grid / shapes / link arm
+@pytest.mark.parametrize("scalar", [m.F64, m.F32])
+def test_grid_matches_oracle(ctx, oracle, scalar):
+    occ = W.synthetic_grid(1000, 700, seed=4, n_blobs=125)
+    dt = np.float64 if scalar == m.F64 else np.float32
+    sc = m.Scenario.grid(ctx, occ, scalar)
+    og = oracle.grid(occ, scalar)
+    st = W.box_states(20000, 2, 8, 0.0, [1000, 700], dt)
+    st[:4] = [[999.6, 10], [10, 699.6], [999.6, 699.6], [0, 0]]  # x == width wrap, out of range
+    assert np.array_equal(sc.valid(st), og.valid(st))
+    for max_len in (None, 64.0, 5.0, 0.5):
+        a, b = W.grid_edges(8192, 1000, 700, 9, max_len, dt)
+        got, want = sc.link(a, b), og.link(a, b)
+        assert np.array_equal(got, want), f"max_len={max_len}: {(got != want).sum()} differ"
+        if max_len == 5.0:
+            assert 0.2 < want.mean() < 0.8
+
+
+def test_grid_golden_and_empty(ctx):
+    g = np.load(ROOT / "tests" / "golden" / "golden.npz")
+    sc = m.Scenario.grid(ctx, g["grid_occ"])
+    assert np.array_equal(sc.link(g["grid_a"], g["grid_b"]), g["grid_link"])
+    assert sc.link(np.zeros((0, 2)), np.zeros((0, 2))).shape == (0,)
+    assert sc.valid(np.zeros((0, 2))).shape == (0,)
+
+
+@pytest.mark.parametrize("scalar", [m.F64, m.F32])
+def test_shapes_match_oracle(ctx, oracle, scalar):
+    dt = np.float64 if scalar == m.F64 else np.float32
+    # the holonomic demo scene (demo/holonomic_2d_point_planning.cpp:67-79)
+    centres, radii = [[170, 140], [800, 70], [900, 380]], [80, 50, 70]
+    rects = [[375, 140, 520, 220], [200, 320, 390, 390], [600, 200, 680, 450]]
+    sc = m.Scenario.shapes(ctx, 2, centres, radii, rects, scalar)
+    og = oracle.shapes(2, centres, radii, rects, scalar)
+    st = W.box_states(20000, 2, 3, 0.0, [1024, 512], dt)
+    assert np.array_equal(sc.valid(st), og.valid(st))
+    for max_len in (None, 100.0, 8.0):
+        a, b = W.grid_edges(8192, 1024, 512, 5, max_len, dt)
+        assert np.array_equal(sc.link(a, b), og.link(a, b))
+    # the 3-D sphere scenario of test/planner_integration_test.hpp:128-150
+    r = float(np.sqrt(2.0) * 0.95)
+    sc3 = m.Scenario.shapes(ctx, 3, [[0, 0, 0]], [r], (), scalar)
+    og3 = oracle.shapes(3, [[0, 0, 0]], [r], (), scalar)
+    a, b = W.box_states(8192, 3, 1, -1.0, 1.0, dt), W.box_states(8192, 3, 2, -1.0, 1.0, dt)
+    assert np.array_equal(sc3.valid(a), og3.valid(a))
+    got = sc3.link(a, b)
+    assert np.array_equal(got, og3.link(a, b)) and 0.05 < got.mean() < 0.95
+
+
+@pytest.mark.parametrize("n_links", [5, 8, 16, 32])
+@pytest.mark.parametrize("scalar", [m.F64, m.F32])
+def test_linkarm_matches_oracle(ctx, oracle, n_links, scalar):
+    dt = np.float64 if scalar == m.F64 else np.float32
+    if n_links == 5:  # the shipped demo (demo/link_manipulator_planning.cpp:62-76)
+        lengths, radius = [10.0, 12.0, 8.0, 6.0, 4.0], 0.5
+        circles = [[20, -20, 8], [-20, -30, 5], [0, 25, 10], [30, 10, 10], [-30, 10, 8]]
+    else:
+        lengths, radius, circles = W.link_arm_scene(n_links)
+    sc = m.Scenario.link_arm(ctx, lengths, radius, circles, scalar)
+    og = oracle.link_arm(lengths, radius, circles, scalar)
+    st = W.box_states(8192, n_links, 3, -np.pi, np.pi, dt)
+    gv = sc.valid(st)
+    assert np.array_equal(gv, og.valid(st))
+    for delta in (0.5, 0.05, 3.0):
+        a, b = W.arm_edges(4096, n_links, 7, delta, dt)
+        got, want = sc.link(a, b), og.link(a, b)
+        assert np.array_equal(got, want), f"delta={delta}: {(got != want).sum()} differ"
+
+
+def test_linkarm_golden(ctx):
+    g = np.load(ROOT / "tests" / "golden" / "golden.npz")
+    sc = m.Scenario.link_arm(ctx, g["arm_lengths"], float(g["arm_radius"]), g["arm_circles"])
+    assert np.array_equal(sc.link(g["arm_a"], g["arm_b"]), g["arm_link"])
+
+
+# ------------------------------------------------------------------ mesh
+def _mesh_scene(env_t=1200, robot_t=400):
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=env_t, robot_tris_target=robot_t)
+    return robot, env, W.se3_step_size(vmin, vmax)
+
+
+def test_mesh_valid_matches_oracle(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    robot, env, step = _mesh_scene()
+    sc = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    og = oracle.mesh_pair(robot, env, sp, step)
+    st = W.se3_states(6000, 21, -45.0, 45.0)
+    got = sc.valid(st)
+    want, margin = og.valid(st, with_margin=True)
+    near = np.abs(margin) < 1e-6 * float(np.linalg.norm(env.reshape(-1, 3).max(0) - env.reshape(-1, 3).min(0)))
+    diff = got != want
+    print(f"mesh valid: {want.mean():.3f} free, {int(near.sum())} states within the contact band, {int(diff.sum())} differ")
+    assert not (diff & ~near).any(), f"{int((diff & ~near).sum())} decisions differ outside the near-contact band"
+    assert 0.3 < want.mean() < 0.97
+    stats = sc.last_stats()
+    assert stats["states"] == 6000 and stats["bv_tests"] > 0 and stats["prim_tests"] > 0
+
+
+def test_mesh_link_matches_oracle(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    robot, env, step = _mesh_scene()
+    sc = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    og = oracle.mesh_pair(robot, env, sp, step)
+    for max_trans, max_angle in ((12.0, 0.5), (40.0, 2.0), (0.5, 0.01)):
+        a, b = W.se3_edges(1500, 23, -45.0, 45.0, max_trans, max_angle)
+        got = sc.link(a, b)
+        want, near = og.link(a, b, with_near_contact=True)
+        diff = got != want
+        print(f"mesh link {max_trans}/{max_angle}: {want.mean():.3f} valid, {int(near.sum())} near-contact edges, {int(diff.sum())} differ")
+        assert not (diff & (near == 0)).any()
+        # the reference's early exit: same number of states checked as the sequential validator
+        if not diff.any():
+            assert sc.last_stats()["states"] == og.last_states
+
+
+def test_mesh_golden_and_degenerate(ctx):
+    g = np.load(ROOT / "tests" / "golden" / "golden.npz")
+    sp = m.se3_space(50, 1)
+    sc = m.Scenario.mesh_pair(ctx, g["mesh_robot"], g["mesh_env"], sp, float(g["mesh_step"]))
+    assert np.array_equal(sc.valid(g["mesh_states"]), g["mesh_valid"])
+    assert np.array_equal(sc.link(g["mesh_a"], g["mesh_b"]), g["mesh_link"])
+    # zero-length edge and an empty batch
+    a = g["mesh_a"][:8]
+    assert np.array_equal(sc.link(a, a), sc.valid(a))
+    assert sc.link(a[:0], a[:0]).shape == (0,)
+    # single triangles
+    tri = m.Scenario.mesh_pair(ctx, [[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], [[[0.2, 0.2, -0.5], [0.2, 0.2, 0.5], [0.8, 0.8, 0.5]]], sp, 0.5)
+    st = np.array([[0, 0, 0, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0, 2.0]], dtype=np.float32)
+    assert list(tri.valid(st)) == [0, 1]
