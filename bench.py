@@ -1,0 +1,419 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the planning hot path on B200 (BASELINE.json: "batched kNN queries/s and
+edge-validity checks/s at 1/2/4/8 B200").
+
+One "step" = one sample wave of the planner's hot path on synthetic input (BASELINE.json configs[4],
+the only configuration the metric is quoted on that needs a GPU):
+    * batched SE(3) kNN: Q = 65,536 queries, k = 16, against a tree of N = 1,048,576 nodes
+      (SO(3) weight 50, L2 weight 1, float32)            -> `value` = queries/s
+    * batched edge validity: E = 65,536 SE(3) edges through DiscreteMotionValidator against a synthetic
+      rigid-body mesh pair (~1k robot / ~4k environment triangles) -> `edges_per_s`
+Multi-GPU (torchrun, one rank per GPU): the path shards by independent units -- every rank owns its
+own query wave and edge wave; the tree (28 MB) and the meshes are replicated, so there is no
+data-path collective (weak scaling).  The tree-sharded variant with its NCCL all-gather + merge is
+measured separately and reported under "sharded_tree" (it is what a tree too large for one HBM needs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_TREE = 1_048_576
+Q_WAVE = 65_536
+E_WAVE = 65_536
+K_NN = 16
+SO3_W, L2_W = 50.0, 1.0
+MESH_LO, MESH_HI = -45.0, 45.0
+EDGE_TRANS, EDGE_ANGLE = 12.0, 0.5  # a steered sample: <= 12 units and <= 0.5 rad from the tree node
+ALGO_BYTES_KNN = N_TREE * 7 * 4 + Q_WAVE * 7 * 4 + Q_WAVE * K_NN * (4 + 4)  # 39,583,744
+F_BV, F_TRI = 45.0, 170.0  # flop per box-pair test (rotated-AABB vs AABB as implemented) / per SAT
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def workload(rank: int):
+    """Synthetic inputs of one rank (host, numpy)."""
+    from mpt_b200 import workloads as W
+
+    tree = W.se3_states(N_TREE, W.TREE_SEED)
+    queries = W.se3_states(Q_WAVE, W.QUERY_SEED + 1000 * rank)
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=4000, robot_tris_target=1000)
+    step = W.se3_step_size(vmin, vmax, SO3_W)
+    ea, eb = W.se3_edges(E_WAVE, W.EDGE_SEED + 1000 * rank, MESH_LO, MESH_HI, EDGE_TRANS, EDGE_ANGLE)
+    return tree, queries, robot, env, step, ea, eb
+
+
+CONFIG = {
+    "workload": "synthetic SE(3) kNN + edge-check sweep (BASELINE.json configs[4])",
+    "tree_nodes": N_TREE, "queries_per_wave": Q_WAVE, "k": K_NN, "edges_per_wave": E_WAVE,
+    "space": "SE3 (SO3 weight 50, L2 weight 1), float32",
+    "mesh_pair": "synthetic bent-tube robot (~1k tris) vs environment (~4k tris), DiscreteMotionValidator resolution 0.01",
+    "edge_length": f"<= {EDGE_TRANS} units, <= {EDGE_ANGLE} rad",
+    "l2": "256 MiB memset between steps (L2 flush), outside the per-step event intervals",
+    "parallelism": "one rank per GPU; queries and edges sharded, tree + meshes replicated, no data-path collective",
+}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle (a port of the reference path; the reference itself cannot be built here --
+    Eigen/Nigh/FCL absent) on all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mpt_b200 as m
+    from tests import oracle_binding
+
+    orc = oracle_binding.load()
+    tree, queries, robot, env, step, ea, eb = workload(0)
+    sp = m.se3_space(SO3_W, L2_W)
+    t0 = time.perf_counter()
+    otree = orc.tree(sp, tree)
+    build_s = time.perf_counter() - t0
+    omesh = orc.mesh_pair(robot, env, sp, step)
+    qs, es = args.cpu_queries, args.cpu_edges
+    knn_t, edge_t = [], []
+    for it in range(args.warmup + args.steps):
+        sel = slice((it * qs) % (Q_WAVE - qs + 1), (it * qs) % (Q_WAVE - qs + 1) + qs)
+        t0 = time.perf_counter()
+        otree.knn(queries[sel], K_NN)
+        t1 = time.perf_counter()
+        esel = slice((it * es) % (E_WAVE - es + 1), (it * es) % (E_WAVE - es + 1) + es)
+        omesh.link(ea[esel], eb[esel])
+        t2 = time.perf_counter()
+        if it >= args.warmup:
+            knn_t.append(t1 - t0)
+            edge_t.append(t2 - t1)
+    qps = qs / float(np.mean(knn_t))
+    eps = es / float(np.mean(edge_t))
+    sample = f"{qs} of {Q_WAVE} queries and {es} of {E_WAVE} edges per step (tree build {build_s:.1f}s untimed)"
+    line = {
+        "impl": "reference", "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(knn_t) + np.mean(edge_t)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": CONFIG, "edges_per_s": eps,
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "edges_per_s": eps, "cores": orc.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mpt_b200 as m
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    tree, queries, robot, env, step, ea, eb = workload(rank)
+    ctx = m.Context(local)
+    sp = m.se3_space(SO3_W, L2_W)
+    nn = m.Nearest(ctx, sp, N_TREE)
+    nn.insert(tree)
+    nn.build_index()
+    mesh = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # device-resident inputs / outputs for `value`
+    d_q = torch.from_numpy(queries).to(dev)
+    d_idx = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
+    d_dist = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty(Q_WAVE, dtype=torch.int32, device=dev)
+    d_ea, d_eb = torch.from_numpy(ea).to(dev), torch.from_numpy(eb).to(dev)
+    d_ok = torch.empty(E_WAVE, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # pinned host buffers for `e2e` (the reference-facing host-pointer C-ABI calls)
+    h_q = torch.from_numpy(queries).pin_memory()
+    h_idx = torch.empty((Q_WAVE, K_NN), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((Q_WAVE, K_NN), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty(Q_WAVE, dtype=torch.int32).pin_memory()
+    h_ea, h_eb = torch.from_numpy(ea).pin_memory(), torch.from_numpy(eb).pin_memory()
+    h_ok = torch.empty(E_WAVE, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step_device(record):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record(stream)
+            nn.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, d_idx.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr())
+            e1.record(stream)
+            mesh.link_dev(d_ea.data_ptr(), d_eb.data_ptr(), E_WAVE, d_ok.data_ptr())
+            e2.record(stream)
+        if record is not None:
+            record.append((e0, e1, e2))
+
+    def step_e2e(record):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record(stream)
+        nn.nearest_host_into(h_q.data_ptr(), Q_WAVE, K_NN, -1.0, h_idx.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
+        e1.record(stream)
+        mesh.link_host_into(h_ea.data_ptr(), h_eb.data_ptr(), E_WAVE, h_ok.data_ptr())
+        e2.record(stream)
+        if record is not None:
+            record.append((e0, e1, e2))
+
+    def timed(step_fn):
+        for _ in range(args.warmup):
+            step_fn(None)
+        barrier()
+        launches0 = ctx.launches
+        rec = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_fn(rec)
+        ctx.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+        knn_ms = sum(a.elapsed_time(b) for a, b, _ in rec) / len(rec)
+        edge_ms = sum(b.elapsed_time(c) for _, b, c in rec) / len(rec)
+        t = torch.tensor([knn_ms, edge_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), wall, ctx.launches - launches0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    knn_ms, edge_ms, wall, launches = timed(step_device)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_knn_ms, e2e_edge_ms, _, _ = timed(step_e2e)
+
+    knn_stats = nn.last_stats()
+    mesh_stats = mesh.last_stats()
+    # parity spot check of the timed outputs against the host-pointer path (same library, both paths)
+    ok_dev = d_ok.cpu().numpy()
+    assert np.array_equal(ok_dev, h_ok.numpy()), "device-pointer and host-pointer edge results differ"
+    assert np.array_equal(d_idx.cpu().numpy(), h_idx.numpy()), "device-pointer and host-pointer kNN results differ"
+
+    extra = {}
+    if world > 1:
+        extra["sharded_tree"] = bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = peaks()
+    qps = world * Q_WAVE / (knn_ms * 1e-3)
+    eps = world * E_WAVE / (edge_ms * 1e-3)
+    achieved = ALGO_BYTES_KNN / (knn_ms * 1e-3) / 1e9
+    edge_flops = mesh_stats["bv_tests"] * F_BV + mesh_stats["prim_tests"] * F_TRI
+    fp32_peak = fp32_probe(torch, dev)
+    line = {
+        "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": knn_ms + edge_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "knn_ms": knn_ms, "edge_ms": edge_ms, "edges_per_s": eps,
+        "edge_states_per_s": world * mesh_stats["states"] / (edge_ms * 1e-3),
+        "roofline": {
+            "kernel": "knnBvhKernel<float,SE3,1>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ALGO_BYTES_KNN,
+            "note": "exact kNN is bound by box tests and distance evaluations, not by compulsory HBM bytes (DESIGN.md)",
+            "distance_evals_per_query": knn_stats["distance_evals"] / Q_WAVE,
+            "nodes_visited_per_query": knn_stats["nodes_visited"] / Q_WAVE,
+        },
+        "roofline_edges": {
+            "kernel": "meshLinkKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,
+            "unit": "TFLOP/s", "frac": edge_flops / (edge_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
+            "peak_source": "cuBLAS SGEMM 8192^3 (TF32 off) on this GPU, same run",
+            "algorithmic_flops_per_launch": edge_flops, "bv_tests": mesh_stats["bv_tests"], "tri_tests": mesh_stats["prim_tests"],
+            "states": mesh_stats["states"], "flop_per_bv_test": F_BV, "flop_per_tri_test": F_TRI,
+        },
+        "e2e": {
+            "value": world * Q_WAVE / (e2e_knn_ms * 1e-3), "unit": "queries/s", "edges_per_s": world * E_WAVE / (e2e_edge_ms * 1e-3),
+            "ms_per_step": e2e_knn_ms + e2e_edge_ms,
+            "h2d_bytes_per_step": int(h_q.numel() * 4 + h_ea.numel() * 4 + h_eb.numel() * 4),
+            "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dist.numel() * 4 + h_cnt.numel() * 4 + h_ok.numel()),
+            "api": "mptg_knn_query + mptg_link_batch with pinned host buffers",
+        },
+        "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall, "edge_valid_fraction": float(ok_dev.mean()),
+        **extra,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def fp32_probe(torch, dev):
+    """FP32 CUDA-core yardstick: cuBLAS SGEMM with TF32 off (library used as a ruler only)."""
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        torch.backends.cuda.matmul.allow_tf32 = old
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb):
+    from tests import oracle_binding
+
+    orc = oracle_binding.load()
+    otree = orc.tree(sp, tree)
+    omesh = orc.mesh_pair(robot, env, sp, step)
+    qs, es = args.cpu_queries, args.cpu_edges
+    otree.knn(queries[:256], K_NN)
+    t0 = time.perf_counter()
+    otree.knn(queries[:qs], K_NN)
+    t1 = time.perf_counter()
+    omesh.link(ea[:es], eb[:es])
+    t2 = time.perf_counter()
+    return {"value": qs / (t1 - t0), "unit": "queries/s", "edges_per_s": es / (t2 - t1), "cores": orc.threads, "kind": "port",
+            "sample": f"first {qs} of {Q_WAVE} queries (k={K_NN}, N={N_TREE}, box-tree search) and first {es} of {E_WAVE} edges, "
+                      f"OpenMP over all host threads"}
+
+
+def bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank):
+    """north_star variant: tree points dealt round-robin to the ranks, every rank answers the same query
+    wave on its shard, NCCL all-gather of the [Q,k] candidates, merge by (distance, global index)."""
+    import torch
+    import torch.distributed as dist
+
+    import mpt_b200 as m
+    from mpt_b200 import workloads as W
+
+    q_all = W.se3_states(Q_WAVE, W.QUERY_SEED)  # identical on all ranks
+    shard = m.Nearest(ctx, sp, N_TREE // world + 1)
+    shard.set_index_map(world, rank)
+    shard.insert(tree[rank::world])
+    shard.build_index()
+    d_q = torch.from_numpy(q_all).to(dev)
+    loc_i = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
+    loc_d = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+    all_i = torch.empty((world, Q_WAVE, K_NN), dtype=torch.int32, device=dev)
+    all_d = torch.empty((world, Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+    out_i = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
+    out_d = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+    times = []
+    for it in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            shard.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, loc_i.data_ptr(), loc_d.data_ptr())
+            dist.all_gather_into_tensor(all_i, loc_i)
+            dist.all_gather_into_tensor(all_d, loc_d)
+            m.knn_merge_dev(ctx, m.F32, world, Q_WAVE, K_NN, all_i.data_ptr(), all_d.data_ptr(), out_i.data_ptr(), out_d.data_ptr())
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(e0.elapsed_time(e1))
+    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    return {"queries_per_s": Q_WAVE / (ms * 1e-3), "ms_per_wave": ms, "collective": "nccl all_gather of [Q,k] (idx,dist) + merge kernel",
+            "tree_nodes_per_gpu": N_TREE // world}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-queries", type=int, default=8192, help="CPU-baseline sample: queries per step")
+    ap.add_argument("--cpu-edges", type=int, default=4096, help="CPU-baseline sample: edges per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,66 @@ def test_knn_brute_matches_oracle(ctx, oracle, name):
     nn.close()
 
 
+@pytest.mark.parametrize("name", sorted(SPACES))
+def test_knn_bvh_matches_oracle(ctx, oracle, name):
+    """The 32-ary box tree returns exactly what the scan returns (indices, distances, ties)."""
+    sp = SPACES[name]()
+    pts = random_states(sp, 40_000, 1)
+    pts[100] = pts[7]
+    pts[200] = pts[7]
+    q = random_states(sp, 400, 2)
+    q[0] = pts[7]
+    nn = m.Nearest(ctx, sp, 65536, m.KNN_BVH)
+    nn.insert(pts)
+    tree = oracle.tree(sp, pts)
+    for k, radius in ((1, -1.0), (16, -1.0), (49, -1.0), (100, -1.0), (16, 2.0)):
+        assert_knn_equal(nn.nearest(q, k, radius), tree.knn(q, k, radius))
+    st = nn.last_stats()
+    assert st["strategy"] == m.KNN_BVH and st["indexed"] == 40_000 and 0 < st["distance_evals"] < 400 * 40_000
+    idx, dist, cnt = nn.nearest(q[:1], 3)
+    assert list(idx[0]) == [7, 100, 200] and (dist[0] == 0).all()
+    nn.close()
+
+
+def test_knn_bvh_with_unindexed_tail(ctx, oracle):
+    """Points inserted after the build are scanned and merged until the index is refreshed."""
+    sp = m.se3_space(50, 1)
+    pts = W.se3_states(60_000, 9)
+    q = W.se3_states(500, 10)
+    nn = m.Nearest(ctx, sp, 65536, m.KNN_BVH)
+    nn.insert(pts[:40_000])
+    tree = oracle.tree(sp, pts[:40_000])
+    assert_knn_equal(nn.nearest(q, 16), tree.knn(q, 16))
+    nn.insert(pts[40_000:45_000])       # tail of 5000 < count/4: index kept, tail scanned
+    assert_knn_equal(nn.nearest(q, 16), oracle.tree(sp, pts[:45_000]).knn(q, 16))
+    assert nn.last_stats()["indexed"] == 40_000
+    nn.insert(pts[45_000:])             # tail of 20000 > count/4: rebuilt
+    assert_knn_equal(nn.nearest(q, 16), oracle.tree(sp, pts).knn(q, 16))
+    assert nn.last_stats()["indexed"] == 60_000
+    nn.close()
+
+
+def test_knn_auto_strategy_and_ragged_sizes(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    for n in (1, 31, 32, 33, 1023, 1025, 16384, 33_000):
+        pts = W.se3_states(n, 100 + n)
+        q = W.se3_states(65, 7)
+        for strat in (m.KNN_AUTO, m.KNN_BVH):
+            nn = m.Nearest(ctx, sp, max(n, 64), strat)
+            nn.insert(pts)
+            assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
+            nn.close()
+
+
+def test_knn_bvh_double(ctx, oracle):
+    sp = m.se3_space(50, 1, m.F64)
+    pts = W.se3_states(20_000, 1, dtype=np.float64)
+    q = W.se3_states(100, 2, dtype=np.float64)
+    nn = m.Nearest(ctx, sp, 32768, m.KNN_BVH)
+    nn.insert(pts)
+    assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
+
+
 def test_knn_edge_cases(ctx, oracle):
     sp = m.se3_space(50, 1)
     nn = m.Nearest(ctx, sp, 64, m.KNN_BRUTE)
@@ -222,8 +282,11 @@ def test_shapes_match_oracle(ctx, oracle, scalar):
     og3 = oracle.shapes(3, [[0, 0, 0]], [r], (), scalar)
     a, b = W.box_states(8192, 3, 1, -1.0, 1.0, dt), W.box_states(8192, 3, 2, -1.0, 1.0, dt)
     assert np.array_equal(sc3.valid(a), og3.valid(a))
-    got = sc3.link(a, b)
-    assert np.array_equal(got, og3.link(a, b)) and 0.05 < got.mean() < 0.95
+    assert np.array_equal(sc3.link(a, b), og3.link(a, b))
+    sc3b = m.Scenario.shapes(ctx, 3, [[0, 0, 0], [0.5, 0.5, 0.5]], [0.5, 0.2], (), scalar)
+    og3b = oracle.shapes(3, [[0, 0, 0], [0.5, 0.5, 0.5]], [0.5, 0.2], (), scalar)
+    got = sc3b.link(a, b)
+    assert np.array_equal(got, og3b.link(a, b)) and 0.05 < got.mean() < 0.95
 
 
 @pytest.mark.parametrize("n_links", [5, 8, 16, 32])
