@@ -1,4 +1,4 @@
-// space.cuh -- device-side metric spaces: distance (a4) and interpolate (a5).
+// mptg_space.h -- metric spaces for device and host code: distance (a4) and interpolate (a5).
 //
 // Operation order is part of the contract (bit-exact against the CPU oracle, DESIGN.md "arithmetic"):
 //   LP p=2   sqrt(fma chain of squared differences, coordinate 0 first)      [test/lp_space_test.cpp:49]
@@ -10,8 +10,8 @@
 // Compile with --fmad=false: only the explicit fma_ calls may fuse.
 #pragma once
 
-#include "../../include/mptg/mptg.h"
-#include "../../include/mptg/mptg_fpmath.h"
+#include "mptg.h"
+#include "mptg_fpmath.h"
 
 namespace mptg {
 

@@ -2,7 +2,7 @@
 #pragma once
 
 #include "common.cuh"
-#include "space.cuh"
+#include "../../include/mptg/mptg_space.h"
 
 struct MeshData;  // mesh.cu
 

@@ -16,7 +16,7 @@
 //     warp-cooperative traversal.  Used for large trees.
 #include "common.cuh"
 #include "knn_bvh.cuh"
-#include "space.cuh"
+#include "../../include/mptg/mptg_space.h"
 #include "topk.cuh"
 
 namespace mptg {

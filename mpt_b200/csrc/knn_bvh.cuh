@@ -24,7 +24,7 @@
 #include <numeric>
 
 #include "common.cuh"
-#include "space.cuh"
+#include "../../include/mptg/mptg_space.h"
 #include "topk.cuh"
 
 namespace mptg {

@@ -2,7 +2,7 @@
 // the steer stage of Appendix C).  One thread per item; these are memory-light helper stages, the
 // arithmetic itself is in space.cuh and is shared with the kNN and edge kernels.
 #include "common.cuh"
-#include "space.cuh"
+#include "../../include/mptg/mptg_space.h"
 
 namespace mptg {
 
