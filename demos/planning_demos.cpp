@@ -1,0 +1,301 @@
+// planning_demos.cpp -- the four planning configurations of BASELINE.json (configs[0..3]) on the
+// wave planners, mirroring the reference's demo mains:
+//   holonomic_2d_point  demo/holonomic_2d_point_planning.cpp:57-102   (PRRT, circles + rectangles)
+//   png_2d              demo/png_2d_planning.cpp:60-105               (PRRT*, occupancy grid)
+//   se3_rigid_body      demo/se3_rigid_body_planning.cpp:155-233      (PRRT*, mesh vs mesh, DiscreteMotionValidator)
+//   link_manipulator    demo/link_manipulator_planning.cpp:59-90      (PPRM, N-link planar arm)
+// Usage: planning_demos [--all | --demo NAME] [--time-ms T] [--check] [--map file.pgm] [--seed S]
+// Prints, per demo, time to first solution, node count and path cost ("solve time" of BASELINE.json).
+// The reference's PNG and OMPL meshes are not redistributable inputs of this repository: the map is
+// a synthetic one of the same size unless --map gives a binary PGM (tools/png_to_pgm.py converts the
+// reference image with the reference's colour filters), the meshes are procedural bent tubes.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <random>
+#include <string>
+
+#include "mptg/planner.hpp"
+#include "mptg/scenarios.hpp"
+
+using namespace mptg;
+using Clock = std::chrono::steady_clock;
+
+struct Options {
+    double timeMs = 5000;
+    bool check = false;
+    std::string map;
+    std::uint64_t seed = 2026;
+};
+
+static int failures = 0;
+
+template <typename Planner, typename Scenario>
+void report(const char* name, const char* algo, Planner& planner, const Scenario& scenario, double firstSolutionS, double totalS,
+            const Options& opt) {
+    using State = typename Scenario::State;
+    std::vector<State> path = planner.solution();
+    double cost = 0;
+    for (std::size_t i = 1; i < path.size(); ++i) cost += scenario.space().distance(path[i - 1], path[i]);
+    planner.printStats();
+    bool ok = planner.solved() && path.size() >= 2;
+    if (opt.check && ok) {
+        Context ctx;
+        Geometry g = scenario.makeGeometry(ctx);
+        std::vector<State> from(path.begin(), path.end() - 1), to(path.begin() + 1, path.end());
+        std::vector<std::uint8_t> v(from.size());
+        auto desc = scenario.space().desc();
+        double step = 0;
+        if constexpr (impl::has_link_step<Scenario>::value) step = scenario.linkStep();
+        g.link(&desc, from.data(), to.data(), (std::uint32_t)from.size(), step, v.data());
+        for (auto x : v) ok = ok && x == 1;
+    }
+    std::printf("%s %s [%s]: solved=%d first solution after %.4f s (ran %.3f s), %zu nodes, %zu waypoints, path cost %.4f\n", ok ? "OK" : "FAILED",
+                name, algo, (int)planner.solved(), firstSolutionS, totalS, planner.size(), path.size(), cost);
+    if (!ok) ++failures;
+}
+
+// scenario.valid(q) / scenario.link(a,b) for single states through the batched back-end
+template <typename Scenario>
+struct Probe {
+    const Scenario& sc;
+    Context ctx;
+    Geometry g;
+    explicit Probe(const Scenario& s) : sc(s), g(s.makeGeometry(ctx)) {}
+    bool valid(const typename Scenario::State& q) {
+        std::uint8_t ok = 0;
+        g.valid(&q, 1, &ok);
+        return ok != 0;
+    }
+    bool link(const typename Scenario::State& a, const typename Scenario::State& b) {
+        std::uint8_t ok = 0;
+        auto desc = sc.space().desc();
+        double step = 0;
+        if constexpr (impl::has_link_step<Scenario>::value) step = sc.linkStep();
+        g.link(&desc, &a, &b, 1, step, &ok);
+        return ok != 0;
+    }
+};
+
+template <typename Planner>
+std::pair<double, double> runUntilSolved(Planner& planner, double timeMs) {
+    const auto t0 = Clock::now();
+    double first = -1;
+    planner.solveFor(
+        [&] {
+            if (first < 0 && planner.solved()) first = std::chrono::duration<double>(Clock::now() - t0).count();
+            return planner.solved();
+        },
+        std::chrono::duration<double, std::milli>(timeMs));
+    if (first < 0 && planner.solved()) first = std::chrono::duration<double>(Clock::now() - t0).count();
+    return {first, std::chrono::duration<double>(Clock::now() - t0).count()};
+}
+
+// ------------------------------------------------------------------ C1
+void holonomic(const Options& opt) {
+    using Scalar = double;
+    using Scenario = demo::Holonomic2DPointScenario<Scalar>;
+    using State = Scenario::State;
+    const int width = 1024, height = 512;
+    std::vector<shape::Circle<Scalar>> circles{{170.0, 140.0, 80.0}, {800.0, 70.0, 50.0}, {900.0, 380.0, 70.0}};
+    std::vector<shape::Rect<Scalar>> rects{{375, 140, 520, 220}, {200, 320, 390, 390}, {600, 200, 680, 450}};
+    State start = makeState<Scalar, 2>({30, 30}), goal = makeState<Scalar, 2>({width - 30.0, height - 30.0});
+    Scenario scenario(width, height, circles, rects, goal);
+    Planner<Scenario, PRRT<report_stats<true>, wave_size<512>>> planner(scenario, opt.seed);
+    planner.addStart(start);
+    auto [first, total] = runUntilSolved(planner, opt.timeMs);
+    report("holonomic_2d_point", "PRRT", planner, scenario, first, total, opt);
+}
+
+// ------------------------------------------------------------------ C2
+static std::vector<std::uint8_t> syntheticMap(int w, int h, std::uint64_t seed) {
+    std::vector<std::uint8_t> occ((std::size_t)w * h, 0);
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> u(0, 1);
+    for (int b = 0; b < 125; ++b) {
+        const double cx = u(rng) * w, cy = u(rng) * h;
+        if (u(rng) < 0.5) {
+            const double r = 30 + u(rng) * 170;
+            for (int y = std::max(0, (int)(cy - r)); y < std::min(h, (int)(cy + r)); ++y)
+                for (int x = std::max(0, (int)(cx - r)); x < std::min(w, (int)(cx + r)); ++x)
+                    if ((x - cx) * (x - cx) + (y - cy) * (y - cy) <= r * r) occ[(std::size_t)y * w + x] = 1;
+        } else {
+            const double bw = 40 + u(rng) * 400, bh = 20 + u(rng) * 200;
+            for (int y = std::max(0, (int)(cy - bh / 2)); y < std::min(h, (int)(cy + bh / 2)); ++y)
+                for (int x = std::max(0, (int)(cx - bw / 2)); x < std::min(w, (int)(cx + bw / 2)); ++x) occ[(std::size_t)y * w + x] = 1;
+        }
+    }
+    return occ;
+}
+
+static bool readPgm(const std::string& path, int& w, int& h, std::vector<std::uint8_t>& occ) {
+    std::ifstream f(path, std::ios::binary);
+    std::string magic;
+    int maxv;
+    if (!(f >> magic >> w >> h >> maxv) || magic != "P5") return false;
+    f.get();
+    occ.resize((std::size_t)w * h);
+    f.read((char*)occ.data(), (std::streamsize)occ.size());
+    for (auto& c : occ) c = c ? 1 : 0;  // non-zero = obstacle
+    return (bool)f;
+}
+
+void png2d(const Options& opt) {
+    using Scalar = double;
+    using Scenario = demo::PNG2dScenario<Scalar>;
+    using State = Scenario::State;
+    int width = 3976, height = 2603;  // size of demo/png_planning_input.png
+    std::vector<std::uint8_t> occ;
+    State start = makeState<Scalar, 2>({430, 1300}), goal = makeState<Scalar, 2>({3150, 950});  // png_2d_planning.cpp:84-86
+    if (opt.map.empty() || !readPgm(opt.map, width, height, occ)) {
+        occ = syntheticMap(width, height, 11);
+        auto clear = [&](const State& q) {  // keep the shipped start / goal usable on the synthetic map
+            for (int y = (int)q[1] - 40; y <= (int)q[1] + 40; ++y)
+                for (int x = (int)q[0] - 40; x <= (int)q[0] + 40; ++x)
+                    if (x >= 0 && y >= 0 && x < width && y < height) occ[(std::size_t)y * width + x] = 0;
+        };
+        clear(start);
+        clear(goal);
+    }
+    Scenario scenario(width, height, goal, occ);
+    Planner<Scenario, PRRTStar<report_stats<true>, wave_size<2048>>> planner(scenario, opt.seed);
+    planner.addStart(start);
+    planner.setRange(200);
+    auto [first, total] = runUntilSolved(planner, opt.timeMs);
+    report("png_2d", "PRRT*", planner, scenario, first, total, opt);
+}
+
+// ------------------------------------------------------------------ C3
+static void tube(std::vector<float>& tris, double scale, double wobble, int nseg, double phase, double radius, int sides) {
+    std::vector<std::array<double, 3>> p(nseg), t(nseg);
+    for (int i = 0; i < nseg; ++i) {
+        const double s = 1.6 * 3.14159265358979 * i / (nseg - 1);
+        p[i] = {scale * std::cos(s), scale * std::sin(s) * (1 + 0.2 * std::sin(3 * s + phase)), wobble * scale * std::sin(2 * s + phase)};
+    }
+    auto sub = [](auto a, auto b) { return std::array<double, 3>{a[0] - b[0], a[1] - b[1], a[2] - b[2]}; };
+    auto norm = [](std::array<double, 3> v) {
+        const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        return std::array<double, 3>{v[0] / n, v[1] / n, v[2] / n};
+    };
+    auto cross = [](auto a, auto b) { return std::array<double, 3>{a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]}; };
+    for (int i = 0; i < nseg; ++i) t[i] = norm(sub(p[std::min(i + 1, nseg - 1)], p[std::max(i - 1, 0)]));
+    std::array<double, 3> nrm = norm(cross(t[0], std::array<double, 3>{0, 0, 1}));
+    std::vector<std::vector<std::array<double, 3>>> rings(nseg, std::vector<std::array<double, 3>>(sides));
+    for (int i = 0; i < nseg; ++i) {
+        const double d = nrm[0] * t[i][0] + nrm[1] * t[i][1] + nrm[2] * t[i][2];
+        nrm = norm({nrm[0] - d * t[i][0], nrm[1] - d * t[i][1], nrm[2] - d * t[i][2]});
+        const auto b = cross(t[i], nrm);
+        for (int j = 0; j < sides; ++j) {
+            const double a = 2 * 3.14159265358979 * j / sides;
+            for (int c = 0; c < 3; ++c) rings[i][j][c] = p[i][c] + radius * (std::cos(a) * nrm[c] + std::sin(a) * b[c]);
+        }
+    }
+    auto push = [&](const std::array<double, 3>& a, const std::array<double, 3>& b, const std::array<double, 3>& c) {
+        for (auto* v : {&a, &b, &c})
+            for (int k = 0; k < 3; ++k) tris.push_back((float)(*v)[k]);
+    };
+    for (int i = 0; i + 1 < nseg; ++i)
+        for (int j = 0; j < sides; ++j) {
+            push(rings[i][j], rings[i][(j + 1) % sides], rings[i + 1][j]);
+            push(rings[i][(j + 1) % sides], rings[i + 1][(j + 1) % sides], rings[i + 1][j]);
+        }
+    for (int j = 0; j < sides; ++j) {
+        push(p[0], rings[0][(j + 1) % sides], rings[0][j]);
+        push(p[nseg - 1], rings[nseg - 1][j], rings[nseg - 1][(j + 1) % sides]);
+    }
+}
+
+void se3RigidBody(const Options& opt) {
+    using Scalar = float;
+    using Scenario = demo::SE3RigidBodyScenario<Scalar>;
+    using State = Scenario::State;
+    std::vector<float> env, robot;
+    tube(env, 30.0, 0.35, 125, 0.3, 4.0, 16);    // ~4k triangles
+    tube(robot, 14.0, 0.45, 50, 1.7, 2.0, 10);   // ~1k triangles
+    State start = State::identityAt(-52, -50, 0), goal = State::identityAt(52, 50, 5);
+    Scenario scenario(env, robot, goal, makeState<Scalar, 3>({-60, -60, -40}), makeState<Scalar, 3>({60, 60, 40}), 0.01f);
+    {
+        Probe<Scenario> probe(scenario);
+        if (!probe.valid(start) || !probe.valid(goal)) throw std::runtime_error("se3_rigid_body: start or goal in collision");
+        std::printf("se3_rigid_body: direct start->goal edge %s\n", probe.link(start, goal) ? "valid" : "blocked");
+    }
+    Planner<Scenario, PRRTStar<report_stats<true>, wave_size<1024>>> planner(scenario, opt.seed);
+    planner.addStart(start);
+    planner.setRange(40);
+    auto [first, total] = runUntilSolved(planner, opt.timeMs);
+    report("se3_rigid_body", "PRRT*", planner, scenario, first, total, opt);
+}
+
+// ------------------------------------------------------------------ C4
+template <int N>
+void linkManipulator(const Options& opt) {
+    using Scalar = double;
+    using Scenario = demo::LinkManipulatorScenario<Scalar, N>;
+    using State = typename Scenario::State;
+    std::vector<Scalar> lengths(N, 4.0);
+    const Scalar reach = 4.0 * N;
+    std::vector<shape::Circle<Scalar>> circles;
+    std::mt19937_64 rng(5);
+    std::uniform_real_distribution<double> u(0, 1);
+    while (circles.size() < 8) {
+        const double r = reach * (0.35 + 0.6 * u(rng)), a = (0.15 + 0.7 * u(rng)) * 2 * 3.14159265358979;
+        circles.push_back({r * std::cos(a), r * std::sin(a), 3.0});
+    }
+    // straight arm along +x (the angular gap above keeps it free) to the first swung-round pose that is
+    // free but not directly connectable, so the roadmap has to go around the circles
+    State start = State::Zero(), goal = State::Zero();
+    {
+        Scenario trial(goal, circles, lengths, 0.5);
+        Probe<Scenario> probe(trial);
+        if (!probe.valid(start)) throw std::runtime_error("link_manipulator: start in collision");
+        bool found = false;
+        for (double base = 3.0; base > 0.5 && !found; base -= 0.1) {
+            State cand = State::Zero();
+            cand[0] = base;
+            for (int i = 1; i < N; ++i) cand[i] = (i % 2 ? 0.05 : -0.05);
+            if (probe.valid(cand) && !probe.link(start, cand)) goal = cand, found = true;
+        }
+        if (!found) throw std::runtime_error("link_manipulator: no blocked goal pose found");
+    }
+    Scenario scenario(goal, circles, lengths, 0.5);
+    Planner<Scenario, PPRM<report_stats<true>, wave_size<1024>>> planner(scenario, opt.seed);
+    planner.addStart(start);
+    planner.addGoal(goal);
+    auto [first, total] = runUntilSolved(planner, opt.timeMs);
+    char name[64];
+    std::snprintf(name, sizeof name, "link_manipulator N=%d", N);
+    report(name, "PPRM", planner, scenario, first, total, opt);
+}
+
+int main(int argc, char** argv) {
+    Options opt;
+    std::string which = "all";
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a == "--all") which = "all";
+        else if (a == "--demo" && i + 1 < argc) which = argv[++i];
+        else if (a == "--time-ms" && i + 1 < argc) opt.timeMs = std::atof(argv[++i]);
+        else if (a == "--check") opt.check = true;
+        else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
+        else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
+        else {
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--check] [--map file.pgm] [--seed S]\n", argv[0]);
+            return 2;
+        }
+    }
+    try {
+        if (which == "all" || which == "holonomic_2d_point") holonomic(opt);
+        if (which == "all" || which == "png_2d") png2d(opt);
+        if (which == "all" || which == "se3_rigid_body") se3RigidBody(opt);
+        if (which == "all" || which == "link_manipulator") {
+            linkManipulator<8>(opt);
+            linkManipulator<16>(opt);
+            linkManipulator<32>(opt);
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return failures ? 1 : 0;
+}

@@ -1,0 +1,884 @@
+// planner.hpp -- Planner<Scenario, Algorithm> with the reference's public API, driven in SAMPLE WAVES
+// so the GPU sees large batches (BASELINE.json north_star item 3).
+//
+// Reference counterparts (paths relative to the reference root):
+//   Planner<Scenario,Algorithm>   src/mpt/planner.hpp:41-47 (PlannerResolver)
+//   PRRT<Opts...>                 src/mpt/prrt.hpp:81-82,       loop src/mpt/impl/prrt/prrt.hpp:358-452
+//   PRRTStar<Opts...>             src/mpt/prrt_star.hpp:95-96,  loop src/mpt/impl/prrt_star/prrt_star.hpp:447-657
+//   PPRM<Opts...>                 src/mpt/pprm.hpp:80-81,       loop src/mpt/impl/pprm/pprm.hpp:298-378
+//   option tags                   src/mpt/planner_tags.hpp:45-64; nearest tag recognition impl/pack_nearest.hpp:43-83
+//   solveFor / solveUntil         src/mpt/impl/planner_base.hpp:58-80
+//   k / r rewiring                src/mpt/impl/rrg_rewire_neighbors.hpp:53-61,102-122
+// What changes: one host thread draws `wave_size` samples, then runs ONE batched 1-NN, steer, state
+// check, edge check (and for PRRT*/PPRM one batched k-NN and one or two batched edge checks) per wave
+// through the C ABI, instead of one sample at a time per worker thread.  Samples of one wave do
+// not see each other as neighbours -- the same effect as the reference's concurrent workers racing
+// on insert.  max_threads<> is accepted and ignored (the wave replaces the worker pool).
+//
+// Scenario concept (duck typed, as in the reference; impl/scenario_*.hpp):
+//   using Space;  const Space& space() const;   const Bounds& bounds() const;
+//   goal() -> callable (space, q) -> pair<bool,Distance>  with .state()     [GoalState]   or
+//   isGoal(q) -> pair<bool,Distance>  and  sampleGoal(rng) -> State
+//   mptg::Geometry makeGeometry(mptg::Context&) const;   // registers the obstacles on the device
+//   optional: double linkStep() const;                   // DiscreteMotionValidator step (mesh scenarios)
+#pragma once
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <queue>
+#include <random>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "host.hpp"
+#include "spaces.hpp"
+
+namespace mptg {
+
+// ------------------------------------------------------------------ option tags (planner_tags.hpp:45-64)
+template <bool report>
+struct report_stats : std::bool_constant<report> {};
+struct rewire_k_nearest {};
+struct rewire_r_nearest {};
+template <int threadCount>
+struct max_threads {};
+using single_threaded = max_threads<1>;
+using hardware_concurrency = max_threads<0>;
+template <int n>
+struct wave_size {};
+// the nearest-neighbour strategy tag of this library (the analogue of nigh::KDTreeBatch<> etc.)
+struct GpuBatch {};
+
+template <typename... Options>
+struct PRRT {};
+template <typename... Options>
+struct PRRTStar {};
+template <typename... Options>
+struct PPRM {};
+
+namespace impl {
+
+template <typename T, typename... Pack>
+constexpr bool pack_contains_v = (std::is_same_v<T, Pack> || ...);
+
+template <template <bool> class Tag, bool def, typename... Pack>
+struct pack_bool_tag : std::bool_constant<def> {};
+template <template <bool> class Tag, bool def, bool v, typename... Rest>
+struct pack_bool_tag<Tag, def, Tag<v>, Rest...> : std::bool_constant<v> {};
+template <template <bool> class Tag, bool def, typename U, typename... Rest>
+struct pack_bool_tag<Tag, def, U, Rest...> : pack_bool_tag<Tag, def, Rest...> {};
+template <template <bool> class Tag, bool def, typename... Pack>
+constexpr bool pack_bool_tag_v = pack_bool_tag<Tag, def, Pack...>::value;
+
+template <template <int> class Tag, int def, typename... Pack>
+struct pack_int_tag : std::integral_constant<int, def> {};
+template <template <int> class Tag, int def, int v, typename... Rest>
+struct pack_int_tag<Tag, def, Tag<v>, Rest...> : std::integral_constant<int, v> {};
+template <template <int> class Tag, int def, typename U, typename... Rest>
+struct pack_int_tag<Tag, def, U, Rest...> : pack_int_tag<Tag, def, Rest...> {};
+template <template <int> class Tag, int def, typename... Pack>
+constexpr int pack_int_tag_v = pack_int_tag<Tag, def, Pack...>::value;
+
+// impl/pack_nearest.hpp:43-83: the nearest strategy named in an option pack, or void
+template <typename... Pack>
+struct pack_nearest {
+    using type = void;
+};
+template <typename First, typename... Rest>
+struct pack_nearest<First, Rest...> : pack_nearest<Rest...> {};
+template <typename... Rest>
+struct pack_nearest<GpuBatch, Rest...> {
+    using type = GpuBatch;
+    static_assert(std::is_void_v<typename pack_nearest<Rest...>::type>, "multiple nearest neighbor strategies");
+};
+template <typename... Pack>
+using pack_nearest_t = typename pack_nearest<Pack...>::type;
+
+// ---- scenario trait resolvers (impl/scenario_goal.hpp:46-88, scenario_goal_sampler.hpp)
+template <typename Scenario, typename = void>
+struct has_goal_fn : std::false_type {};
+template <typename Scenario>
+struct has_goal_fn<Scenario, std::void_t<decltype(std::declval<const Scenario&>().goal())>> : std::true_type {};
+
+template <typename Scenario, typename = void>
+struct has_link_step : std::false_type {};
+template <typename Scenario>
+struct has_link_step<Scenario, std::void_t<decltype(std::declval<const Scenario&>().linkStep())>> : std::true_type {};
+
+template <typename Scenario, typename State>
+auto checkGoal(const Scenario& s, const State& q) {
+    if constexpr (has_goal_fn<Scenario>::value) return s.goal()(s.space(), q);
+    else return s.isGoal(q);
+}
+template <typename Scenario, typename RNG>
+auto sampleGoalState(const Scenario& s, RNG& rng) {
+    if constexpr (has_goal_fn<Scenario>::value) {
+        (void)rng;
+        return s.goal().state();
+    } else {
+        return s.sampleGoal(rng);
+    }
+}
+template <typename Scenario>
+double linkStepOf(const Scenario& s) {
+    if constexpr (has_link_step<Scenario>::value) return (double)s.linkStep();
+    else return 0.0;
+}
+
+template <typename S>
+constexpr S E = S(2.71828182845904523536028747135266249775724709369995L);
+template <typename S>
+constexpr S PI = S(3.14159265358979323846264338327950288419716939937510L);
+
+struct StageTimer {
+    double seconds = 0;
+    std::uint64_t calls = 0, items = 0;
+    struct Scope {
+        StageTimer& t;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Scope() { t.seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    };
+    Scope time(std::uint64_t n) {
+        ++calls;
+        items += n;
+        return Scope{*this};
+    }
+};
+
+// ------------------------------------------------------------------ shared wave machinery
+template <typename Derived, typename Scenario>
+class WavePlannerBase {
+protected:
+    using Space = typename Scenario::Space;
+    using State = typename Space::Type;
+    using Distance = typename Space::Distance;
+    using Bounds = std::decay_t<decltype(std::declval<const Scenario&>().bounds())>;
+    using Sampler = UniformSampler<Space, Bounds>;
+    using RNG = std::mt19937_64;
+
+    Scenario scenario_;
+    Context ctx_;
+    Geometry geom_;
+    mptg_space_desc desc_;
+    std::uint32_t capacity_;
+    std::unique_ptr<Nearest<std::uint32_t, Space>> nn_;
+    std::vector<State> states_;  // host copy of every node's state, index = node id
+    RNG rng_;
+    Sampler sampler_;
+    std::uint32_t wave_;
+    double linkStep_;
+    StageTimer tNearest1_, tNearestK_, tValid_, tLink_, tSteer_;
+    std::uint64_t iterations_ = 0, biasedSamples_ = 0, waves_ = 0;
+
+    WavePlannerBase(const Scenario& scenario, std::uint64_t seed, std::uint32_t wave, int device)
+        : scenario_(scenario), ctx_(device), geom_(scenario_.makeGeometry(ctx_)), desc_(scenario_.space().desc()), capacity_(1u << 16),
+          nn_(new Nearest<std::uint32_t, Space>(ctx_, scenario_.space(), capacity_)), rng_(seed),
+          sampler_(scenario_.space(), scenario_.bounds()), wave_(wave), linkStep_(linkStepOf(scenario_)) {}
+
+    // grow the device structure (capacity doubles; states are re-inserted from the host copy)
+    void reserve(std::size_t need) {
+        if (need <= capacity_) return;
+        while (capacity_ < need) capacity_ *= 2;
+        nn_.reset(new Nearest<std::uint32_t, Space>(ctx_, scenario_.space(), capacity_));
+        std::vector<std::uint32_t> ids(states_.size());
+        for (std::uint32_t i = 0; i < ids.size(); ++i) ids[i] = i;
+        if (!states_.empty()) nn_->insert(states_.data(), ids.data(), (std::uint32_t)states_.size());
+    }
+    std::uint32_t addNode(const State& q) {
+        reserve(states_.size() + 1);
+        const std::uint32_t id = (std::uint32_t)states_.size();
+        states_.push_back(q);
+        nn_->insert(q, id);
+        return id;
+    }
+    void addNodes(const std::vector<State>& qs) {
+        if (qs.empty()) return;
+        reserve(states_.size() + qs.size());
+        std::vector<std::uint32_t> ids(qs.size());
+        for (std::size_t i = 0; i < qs.size(); ++i) ids[i] = (std::uint32_t)(states_.size() + i);
+        states_.insert(states_.end(), qs.begin(), qs.end());
+        nn_->insert(qs.data(), ids.data(), (std::uint32_t)qs.size());
+    }
+    void validBatch(const std::vector<State>& qs, std::vector<std::uint8_t>& ok) {
+        ok.resize(qs.size());
+        if (qs.empty()) return;
+        auto scope = tValid_.time(qs.size());
+        geom_.valid(qs.data(), (std::uint32_t)qs.size(), ok.data());
+    }
+    void linkBatch(const std::vector<State>& from, const std::vector<State>& to, std::vector<std::uint8_t>& ok) {
+        ok.resize(from.size());
+        if (from.empty()) return;
+        auto scope = tLink_.time(from.size());
+        geom_.link(&desc_, from.data(), to.data(), (std::uint32_t)from.size(), linkStep_, ok.data());
+    }
+    void steerBatch(const std::vector<State>& near, const std::vector<State>& sample, const std::vector<Distance>& d, Distance range,
+                    std::vector<State>& out, std::vector<Distance>* distOut) {
+        out.resize(near.size());
+        if (distOut) distOut->resize(near.size());
+        if (near.empty()) return;
+        auto scope = tSteer_.time(near.size());
+        check(mptg_steer_batch(ctx_.get(), &desc_, near.data(), sample.data(), d.data(), (std::uint32_t)near.size(), (double)range, out.data(),
+                               distOut ? distOut->data() : nullptr),
+              ctx_.get(), "mptg_steer_batch");
+    }
+    void printStageStats() const {
+        auto line = [](const char* name, const StageTimer& t) {
+            if (t.calls)
+                std::clog << "  " << name << ": " << t.calls << " batched calls, " << t.items << " items, " << t.seconds * 1e3 << " ms total, "
+                          << (t.items ? t.seconds * 1e6 / t.items : 0.0) << " us/item\n";
+        };
+        std::clog << "  waves: " << waves_ << " of " << wave_ << " samples, iterations: " << iterations_ << ", biased samples: " << biasedSamples_
+                  << ", kernel launches: " << ctx_.launches() << "\n";
+        line("nearest1", tNearest1_);
+        line("nearestK", tNearestK_);
+        line("steer", tSteer_);
+        line("valid", tValid_);
+        line("validMotion", tLink_);
+    }
+
+public:
+    // impl/planner_base.hpp:58-80 (the deadline is checked between waves instead of by a timer thread)
+    template <typename Rep, typename Period>
+    void solveFor(const std::chrono::duration<Rep, Period>& duration) {
+        solveUntil(std::chrono::steady_clock::now() + duration);
+    }
+    template <class Clock, class Duration>
+    void solveUntil(const std::chrono::time_point<Clock, Duration>& endTime) {
+        static_cast<Derived*>(this)->solve([&] { return Clock::now() >= endTime; });
+    }
+    template <typename DoneFn, typename Rep, typename Period>
+    void solveFor(DoneFn doneFn, const std::chrono::duration<Rep, Period>& duration) {
+        solveUntil(doneFn, std::chrono::steady_clock::now() + duration);
+    }
+    template <typename DoneFn, class Clock, class Duration>
+    void solveUntil(DoneFn doneFn, const std::chrono::time_point<Clock, Duration>& endTime) {
+        static_cast<Derived*>(this)->solve([&] { return doneFn() || Clock::now() >= endTime; });
+    }
+    std::size_t size() const { return states_.size(); }
+    void setWaveSize(std::uint32_t w) { wave_ = w ? w : 1; }
+    std::uint32_t getWaveSize() const { return wave_; }
+    const Scenario& scenario() const { return scenario_; }
+    Context& context() { return ctx_; }
+};
+
+// ------------------------------------------------------------------ PRRT (impl/prrt/prrt.hpp:103-459)
+template <typename Scenario, int waveSize, bool reportStats>
+class WavePRRT : public WavePlannerBase<WavePRRT<Scenario, waveSize, reportStats>, Scenario> {
+    using Base = WavePlannerBase<WavePRRT, Scenario>;
+    using typename Base::Distance;
+    using typename Base::State;
+    static constexpr std::uint32_t NONE = 0xFFFFFFFFu;
+    Distance maxDistance_{std::numeric_limits<Distance>::infinity()};
+    Distance goalBias_{0.01};
+    std::vector<std::uint32_t> parent_;
+    std::vector<std::uint32_t> goals_;
+
+public:
+    explicit WavePRRT(const Scenario& scenario = Scenario(), std::uint64_t seed = std::random_device{}(), int device = -1)
+        : Base(scenario, seed, waveSize, device) {}
+
+    void setGoalBias(Distance bias) { goalBias_ = bias; }
+    Distance getGoalBias() const { return goalBias_; }
+    void setRange(Distance range) { maxDistance_ = range; }
+    Distance getRange() const { return maxDistance_; }
+
+    template <typename... Args>
+    void addStart(Args&&... args) {  // :179-187
+        this->addNode(State(std::forward<Args>(args)...));
+        parent_.push_back(NONE);
+    }
+
+    template <typename DoneFn>
+    std::enable_if_t<std::is_same_v<bool, std::invoke_result_t<DoneFn>>> solve(DoneFn doneFn) {  // :193-201
+        if (this->size() == 0) throw std::runtime_error("there are no valid initial states");
+        while (!doneFn()) wave();
+    }
+
+    bool solved() const { return !goals_.empty(); }
+
+    std::vector<State> solution() const {  // :252-264
+        std::vector<State> path;
+        const std::uint32_t g = bestGoal();
+        for (std::uint32_t n = g; n != NONE; n = parent_[n]) path.push_back(this->states_[n]);
+        std::reverse(path.begin(), path.end());
+        return path;
+    }
+    template <typename Fn>
+    void solution(Fn fn) const {  // waypoint callback form (:244-249, 266-276)
+        for (const State& q : solution()) fn(q);
+    }
+    void printStats() const {  // :278-289
+        std::clog << "nodes in graph: " << this->size() << "\nsolutions: " << goals_.size() << "\n";
+        if constexpr (reportStats) this->printStageStats();
+    }
+    template <typename Visitor>
+    void visitGraph(Visitor&& visitor) const {  // :291-308
+        for (std::uint32_t n = 0; n < this->states_.size(); ++n) {
+            visitor.vertex(this->states_[n]);
+            if (parent_[n] != NONE) visitor.edge(this->states_[parent_[n]]);
+        }
+    }
+
+private:
+    std::uint32_t bestGoal() const {  // :203-231 (path cost by summed distances)
+        std::uint32_t best = NONE;
+        Distance bestCost = std::numeric_limits<Distance>::infinity();
+        for (std::uint32_t g : goals_) {
+            Distance c = 0;
+            for (std::uint32_t n = g; parent_[n] != NONE; n = parent_[n]) c += this->scenario_.space().distance(this->states_[n], this->states_[parent_[n]]);
+            if (c < bestCost || best == NONE) bestCost = c, best = g;
+        }
+        return best;
+    }
+
+    // One wave == wave_ iterations of Worker::addSample (:411-452)
+    void wave() {
+        const std::uint32_t W = this->wave_;
+        ++this->waves_;
+        this->iterations_ += W;
+        std::vector<State> samples(W);
+        std::uniform_real_distribution<Distance> uniform01;
+        for (std::uint32_t i = 0; i < W; ++i) {
+            if (goals_.empty() && goalBias_ > 0 && uniform01(this->rng_) < goalBias_) {  // :365-387
+                ++this->biasedSamples_;
+                samples[i] = sampleGoalState(this->scenario_, this->rng_);
+            } else {
+                samples[i] = this->sampler_(this->rng_);
+            }
+        }
+        {
+            auto scope = this->tNearest1_.time(W);
+            this->nn_->nearest(samples.data(), W, 1);  // :416
+        }
+        std::vector<State> near, cand;
+        std::vector<Distance> d;
+        std::vector<std::uint32_t> nearIdx;
+        for (std::uint32_t i = 0; i < W; ++i) {
+            if (this->nn_->counts()[i] == 0) continue;
+            const Distance di = this->nn_->distances()[i];
+            if (di == 0) continue;  // :427-428
+            nearIdx.push_back(this->nn_->indices()[i]);
+            near.push_back(this->states_[nearIdx.back()]);
+            cand.push_back(samples[i]);
+            d.push_back(di);
+        }
+        std::vector<State> steered;
+        this->steerBatch(near, cand, d, maxDistance_, steered, nullptr);  // :430-434 (d is NOT recomputed)
+        std::vector<std::uint8_t> ok;
+        this->validBatch(steered, ok);  // :439
+        std::vector<State> from, to;
+        std::vector<std::uint32_t> fromIdx;
+        for (std::size_t i = 0; i < steered.size(); ++i)
+            if (ok[i]) from.push_back(near[i]), to.push_back(steered[i]), fromIdx.push_back(nearIdx[i]);
+        this->linkBatch(from, to, ok);  // :442
+        std::vector<State> fresh;
+        for (std::size_t i = 0; i < to.size(); ++i)
+            if (ok[i]) {
+                const std::uint32_t id = (std::uint32_t)(this->states_.size() + fresh.size());
+                fresh.push_back(to[i]);
+                parent_.push_back(fromIdx[i]);
+                if (checkGoal(this->scenario_, to[i]).first) goals_.push_back(id);  // :443,449-450
+            }
+        this->addNodes(fresh);  // :446-447
+    }
+};
+
+// ------------------------------------------------------------------ PRRT* (impl/prrt_star/prrt_star.hpp:158-772)
+template <typename Scenario, int waveSize, class Rewire, bool reportStats>
+class WavePRRTStar : public WavePlannerBase<WavePRRTStar<Scenario, waveSize, Rewire, reportStats>, Scenario> {
+    using Base = WavePlannerBase<WavePRRTStar, Scenario>;
+    using typename Base::Distance;
+    using typename Base::State;
+    static constexpr std::uint32_t NONE = 0xFFFFFFFFu;
+    Distance maxDistance_{std::numeric_limits<Distance>::infinity()};
+    Distance goalBias_{0.01};
+    Distance rewireFactor_{1.1};
+    std::vector<std::uint32_t> parent_;
+    std::vector<Distance> cost_;
+    std::vector<std::vector<std::uint32_t>> children_;
+    std::vector<std::uint8_t> isGoal_;
+    std::uint32_t solution_ = NONE;
+    std::size_t goalCount_ = 0;
+    std::uint64_t rewireTests_ = 0, rewireCount_ = 0;
+
+    // rrg_rewire_neighbors.hpp:53-61
+    Distance kRRG() const { return rewireFactor_ * E<Distance> * (1 + 1 / static_cast<Distance>(this->scenario_.space().dimensions())); }
+    unsigned rewireK(std::size_t n) const { return (unsigned)std::ceil(kRRG() * std::log(Distance(n + 1))); }
+    // rrg_rewire_neighbors.hpp:102-122
+    Distance rewireRadius(std::size_t n) const {
+        const unsigned dim = this->scenario_.space().dimensions();
+        const Distance invDim = 1 / Distance(dim);
+        const Distance unitBall = std::pow(std::sqrt(PI<Distance>), Distance(dim)) / std::tgamma(Distance(dim) / 2 + 1);
+        const Distance rRRG = rewireFactor_ * std::pow(2 * (1 + invDim) * this->sampler_.measure() / unitBall, invDim);
+        ++n;
+        return rRRG * std::pow(std::log(Distance(n)) / Distance(n), invDim);
+    }
+
+public:
+    explicit WavePRRTStar(const Scenario& scenario = Scenario(), std::uint64_t seed = std::random_device{}(), int device = -1)
+        : Base(scenario, seed, waveSize, device) {}
+
+    void setRewireFactor(Distance f) { rewireFactor_ = f; }
+    void setGoalBias(Distance bias) { goalBias_ = bias; }
+    Distance getGoalBias() const { return goalBias_; }
+    void setRange(Distance range) { maxDistance_ = range; }
+    Distance getRange() const { return maxDistance_; }
+
+    template <typename... Args>
+    void addStart(Args&&... args) {  // :263-279
+        this->addNode(State(std::forward<Args>(args)...));
+        parent_.push_back(NONE);
+        cost_.push_back(0);
+        children_.emplace_back();
+        isGoal_.push_back(0);
+    }
+
+    template <typename DoneFn>
+    std::enable_if_t<std::is_same_v<bool, std::invoke_result_t<DoneFn>>> solve(DoneFn doneFn) {  // :286-309
+        if (this->size() == 0) throw std::runtime_error("there are no valid initial states");
+        while (!doneFn()) wave();
+    }
+
+    bool solved() const { return solution_ != NONE; }
+    Distance solutionCost() const { return solved() ? cost_[solution_] : std::numeric_limits<Distance>::quiet_NaN(); }  // :317-322
+
+    std::vector<State> solution() const {  // :325-337
+        std::vector<State> path;
+        for (std::uint32_t n = solution_; n != NONE; n = parent_[n]) path.push_back(this->states_[n]);
+        std::reverse(path.begin(), path.end());
+        return path;
+    }
+    template <typename Fn>
+    void solution(Fn fn) const {
+        for (const State& q : solution()) fn(q);
+    }
+    void printStats() const {  // :372-380
+        std::clog << "nodes in graph: " << this->size() << "\n";
+        if constexpr (reportStats) {
+            this->printStageStats();
+            std::clog << "  rewire tests: " << rewireTests_ << ", rewires: " << rewireCount_ << ", goals: " << goalCount_ << "\n";
+        }
+    }
+    template <typename Visitor>
+    void visitGraph(Visitor&& visitor) const {  // :382-401
+        for (std::uint32_t n = 0; n < this->states_.size(); ++n) {
+            visitor.vertex(this->states_[n]);
+            if (parent_[n] != NONE) visitor.edge(this->states_[parent_[n]]);
+        }
+    }
+    // for tests: tree invariants
+    Distance nodeCost(std::uint32_t n) const { return cost_[n]; }
+    std::uint32_t nodeParent(std::uint32_t n) const { return parent_[n]; }
+    const State& nodeState(std::uint32_t n) const { return this->states_[n]; }
+
+private:
+    void noteGoal(std::uint32_t n) {  // foundGoal (:206-219) / setEdge goal branch
+        if (solution_ == NONE || cost_[n] < cost_[solution_]) solution_ = n;
+    }
+    // nonConcurrentPushUpdate (:664-688): subtract delta from the whole subtree
+    void pushUpdate(std::uint32_t n, Distance delta) {
+        ++rewireCount_;
+        std::vector<std::uint32_t> stack{n};
+        while (!stack.empty()) {
+            const std::uint32_t x = stack.back();
+            stack.pop_back();
+            if (isGoal_[x]) noteGoal(x);
+            for (std::uint32_t c : children_[x]) {
+                cost_[c] -= delta;
+                stack.push_back(c);
+            }
+        }
+    }
+    void reparent(std::uint32_t n, std::uint32_t newParent, Distance newCost) {
+        auto& sib = children_[parent_[n]];
+        sib.erase(std::find(sib.begin(), sib.end(), n));
+        parent_[n] = newParent;
+        children_[newParent].push_back(n);
+        const Distance delta = cost_[n] - newCost;
+        cost_[n] = newCost;
+        pushUpdate(n, delta);
+    }
+
+    // One wave == wave_ iterations of Worker::addSample (:510-657)
+    void wave() {
+        const std::uint32_t W = this->wave_;
+        ++this->waves_;
+        this->iterations_ += W;
+        std::vector<State> samples(W);
+        std::uniform_real_distribution<Distance> uniform01;
+        for (std::uint32_t i = 0; i < W; ++i) {
+            if (goalCount_ == 0 && goalBias_ > 0 && uniform01(this->rng_) < goalBias_) {  // :468-481
+                ++this->biasedSamples_;
+                samples[i] = sampleGoalState(this->scenario_, this->rng_);
+            } else {
+                samples[i] = this->sampler_(this->rng_);
+            }
+        }
+        {
+            auto scope = this->tNearest1_.time(W);
+            this->nn_->nearest(samples.data(), W, 1);  // :517
+        }
+        std::vector<State> near, cand;
+        std::vector<Distance> d;
+        std::vector<std::uint32_t> nearIdx;
+        for (std::uint32_t i = 0; i < W; ++i) {
+            if (this->nn_->counts()[i] == 0) continue;
+            const Distance di = this->nn_->distances()[i];
+            if (di == 0) continue;  // :526-527
+            nearIdx.push_back(this->nn_->indices()[i]);
+            near.push_back(this->states_[nearIdx.back()]);
+            cand.push_back(samples[i]);
+            d.push_back(di);
+        }
+        std::vector<State> steered;
+        std::vector<Distance> dNear;
+        this->steerBatch(near, cand, d, maxDistance_, steered, &dNear);  // :529-536 (dNear recomputed after steering)
+        std::vector<std::uint8_t> ok;
+        this->validBatch(steered, ok);  // :539
+        std::vector<State> from, to;
+        std::vector<std::uint32_t> fromIdx;
+        std::vector<Distance> dKeep;
+        for (std::size_t i = 0; i < steered.size(); ++i)
+            if (ok[i]) from.push_back(near[i]), to.push_back(steered[i]), fromIdx.push_back(nearIdx[i]), dKeep.push_back(dNear[i]);
+        this->linkBatch(from, to, ok);  // :545
+        // survivors
+        std::vector<State> fresh;
+        std::vector<std::uint32_t> nearOf;
+        std::vector<Distance> dOf;
+        for (std::size_t i = 0; i < to.size(); ++i)
+            if (ok[i]) fresh.push_back(to[i]), nearOf.push_back(fromIdx[i]), dOf.push_back(dKeep[i]);
+        const std::uint32_t S = (std::uint32_t)fresh.size();
+        if (S == 0) return;
+
+        // neighbourhoods (:559-562)
+        const std::size_t n0 = this->size();
+        std::uint32_t k;
+        Distance radius = std::numeric_limits<Distance>::infinity();
+        if constexpr (std::is_same_v<Rewire, rewire_r_nearest>) {
+            k = MPTG_MAX_K;
+            radius = rewireRadius(n0);
+        } else {
+            k = std::min<unsigned>(std::max(1u, rewireK(n0)), MPTG_MAX_K);
+        }
+        {
+            auto scope = this->tNearestK_.time(S);
+            this->nn_->nearest(fresh.data(), S, k, radius);
+        }
+        const auto& nIdx = this->nn_->indices();
+        const auto& nDist = this->nn_->distances();
+        const auto& nCnt = this->nn_->counts();
+
+        // candidate parents in (cost + distance) order up to the near node (:565-605), checked in ONE batch
+        struct Cand {
+            std::uint32_t s, j;  // survivor, neighbour slot
+        };
+        std::vector<std::vector<std::uint32_t>> order(S);
+        std::vector<Cand> pc;
+        std::vector<State> pFrom, pTo;
+        for (std::uint32_t s = 0; s < S; ++s) {
+            rewireTests_ += nCnt[s];
+            auto& o = order[s];
+            o.resize(nCnt[s]);
+            for (std::uint32_t j = 0; j < nCnt[s]; ++j) o[j] = j;
+            std::stable_sort(o.begin(), o.end(), [&](std::uint32_t a, std::uint32_t b) {
+                return cost_[nIdx[(std::size_t)s * k + a]] + nDist[(std::size_t)s * k + a] < cost_[nIdx[(std::size_t)s * k + b]] + nDist[(std::size_t)s * k + b];
+            });
+            const Distance parentCost = cost_[nearOf[s]] + dOf[s];
+            for (std::uint32_t j : o) {
+                const std::uint32_t nb = nIdx[(std::size_t)s * k + j];
+                const Distance newCost = cost_[nb] + nDist[(std::size_t)s * k + j];
+                if (newCost > parentCost) break;
+                if (nb == nearOf[s]) break;
+                pc.push_back({s, j});
+                pFrom.push_back(this->states_[nb]);
+                pTo.push_back(fresh[s]);
+            }
+        }
+        std::vector<std::uint8_t> pOk;
+        this->linkBatch(pFrom, pTo, pOk);
+        // replay the reference's loop per survivor with the batched answers
+        std::vector<std::uint32_t> parentOf(S);
+        std::vector<Distance> costOf(S);
+        std::vector<std::vector<std::uint8_t>> checked(S);
+        {
+            std::size_t c = 0;
+            for (std::uint32_t s = 0; s < S; ++s) {
+                checked[s].assign(nCnt[s], 0);
+                std::uint32_t parent = nearOf[s];
+                Distance parentCost = cost_[nearOf[s]] + dOf[s];
+                for (std::uint32_t j : order[s]) {
+                    const std::uint32_t nb = nIdx[(std::size_t)s * k + j];
+                    const Distance newCost = cost_[nb] + nDist[(std::size_t)s * k + j];
+                    if (newCost > parentCost) break;
+                    checked[s][j] = 1;
+                    if (nb == nearOf[s]) {
+                        parent = nb;
+                        parentCost = newCost;
+                        break;
+                    }
+                    const bool valid = pOk[c++] != 0;
+                    if (valid) {
+                        parent = nb;
+                        parentCost = newCost;
+                        // the remaining candidates of this survivor were submitted but are not consumed
+                        while (c < pc.size() && pc[c].s == s) ++c;
+                        break;
+                    }
+                }
+                while (c < pc.size() && pc[c].s == s) ++c;
+                parentOf[s] = parent;
+                costOf[s] = parentCost;
+            }
+        }
+        // insert (:607-622)
+        const std::uint32_t first = (std::uint32_t)this->states_.size();
+        for (std::uint32_t s = 0; s < S; ++s) {
+            const std::uint32_t id = first + s;
+            parent_.push_back(parentOf[s]);
+            cost_.push_back(costOf[s]);
+            children_.emplace_back();
+            children_[parentOf[s]].push_back(id);
+            const bool goal = checkGoal(this->scenario_, fresh[s]).first;
+            isGoal_.push_back(goal ? 1 : 0);
+            if (goal) {
+                ++goalCount_;
+                noteGoal(id);
+            }
+        }
+        this->addNodes(fresh);
+        // rewire (:626-656): edges new -> neighbour that would shorten the neighbour's path, one batch
+        std::vector<Cand> rc;
+        std::vector<State> rFrom, rTo;
+        for (std::uint32_t s = 0; s < S; ++s)
+            for (std::uint32_t j = 0; j < nCnt[s]; ++j) {
+                if (checked[s][j]) continue;
+                const std::uint32_t nb = nIdx[(std::size_t)s * k + j];
+                if (cost_[first + s] + nDist[(std::size_t)s * k + j] >= cost_[nb]) continue;
+                rc.push_back({s, j});
+                rFrom.push_back(fresh[s]);
+                rTo.push_back(this->states_[nb]);
+            }
+        std::vector<std::uint8_t> rOk;
+        this->linkBatch(rFrom, rTo, rOk);
+        for (std::size_t c = 0; c < rc.size(); ++c) {
+            if (!rOk[c]) continue;
+            const std::uint32_t id = first + rc[c].s;
+            const std::uint32_t nb = nIdx[(std::size_t)rc[c].s * k + rc[c].j];
+            const Distance newCost = cost_[id] + nDist[(std::size_t)rc[c].s * k + rc[c].j];
+            if (newCost >= cost_[nb]) continue;  // an earlier rewire of this wave already did better
+            reparent(nb, id, newCost);
+        }
+    }
+};
+
+// ------------------------------------------------------------------ PPRM (impl/pprm/pprm.hpp:65-389)
+template <typename Scenario, int waveSize, bool reportStats>
+class WavePPRM : public WavePlannerBase<WavePPRM<Scenario, waveSize, reportStats>, Scenario> {
+    using Base = WavePlannerBase<WavePPRM, Scenario>;
+    using typename Base::Distance;
+    using typename Base::State;
+    enum Flags : std::uint8_t { kNone = 0, kStart = 1, kGoal = 2 };  // impl/pprm/component.hpp
+    struct Edge {
+        std::uint32_t to;
+        Distance d;
+    };
+    std::vector<std::vector<Edge>> adj_;
+    std::vector<std::uint32_t> comp_;  // union-find parent
+    std::vector<std::uint32_t> compSize_;
+    std::vector<std::uint8_t> compFlags_;
+    std::vector<std::uint32_t> startNodes_, goalNodes_;
+    bool solved_ = false;
+    Distance kRRG_;
+
+    std::uint32_t find(std::uint32_t x) {
+        while (comp_[x] != x) x = comp_[x] = comp_[comp_[x]];
+        return x;
+    }
+    void merge(std::uint32_t a, std::uint32_t b) {  // :341-362 (union by size; flags OR-ed)
+        a = find(a), b = find(b);
+        if (a == b) return;
+        if (compSize_[a] > compSize_[b]) std::swap(a, b);
+        comp_[a] = b;
+        compSize_[b] += compSize_[a];
+        compFlags_[b] |= compFlags_[a];
+        if ((compFlags_[b] & (kStart | kGoal)) == (kStart | kGoal)) solved_ = true;  // component.hpp:97-99
+    }
+
+public:
+    explicit WavePPRM(const Scenario& scenario = Scenario(), std::uint64_t seed = std::random_device{}(), int device = -1)
+        : Base(scenario, seed, waveSize, device), kRRG_(E<Distance> + E<Distance> / this->scenario_.space().dimensions()) {}  // :146
+
+    template <typename... Args>
+    void addStart(Args&&... args) {  // :156-164
+        std::vector<State> q{State(std::forward<Args>(args)...)};
+        addSamples(q, kStart);
+    }
+    template <typename... Args>
+    void addGoal(Args&&... args) {  // :166-169
+        std::vector<State> q{State(std::forward<Args>(args)...)};
+        addSamples(q, kGoal);
+    }
+
+    template <typename DoneFn>
+    std::enable_if_t<std::is_same_v<bool, std::invoke_result_t<DoneFn>>> solve(DoneFn doneFn) {  // :171-183
+        if (goalNodes_.empty()) {
+            std::vector<State> q{sampleGoalState(this->scenario_, this->rng_)};
+            addSamples(q, kGoal);
+        }
+        if (goalNodes_.empty() || startNodes_.empty()) throw std::runtime_error("PPRM requires both start and goal configurations");
+        while (!doneFn()) {
+            ++this->waves_;
+            this->iterations_ += this->wave_;
+            std::vector<State> samples(this->wave_);
+            for (auto& q : samples) q = this->sampler_(this->rng_);
+            addSamples(samples, kNone);
+        }
+    }
+    bool solved() const { return solved_; }
+
+    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246)
+    std::vector<State> solution() const {
+        const std::uint32_t NONE = 0xFFFFFFFFu;
+        const std::size_t n = this->states_.size();
+        std::vector<Distance> dist(n, std::numeric_limits<Distance>::infinity());
+        std::vector<std::uint32_t> prev(n, NONE);
+        std::vector<std::uint8_t> isGoal(n, 0);
+        for (std::uint32_t g : goalNodes_) isGoal[g] = 1;
+        using QE = std::pair<Distance, std::uint32_t>;
+        std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+        for (std::uint32_t s : startNodes_) dist[s] = 0, pq.push({0, s});
+        std::uint32_t hit = NONE;
+        while (!pq.empty()) {
+            auto [d, u] = pq.top();
+            pq.pop();
+            if (d > dist[u]) continue;
+            if (isGoal[u]) {
+                hit = u;
+                break;
+            }
+            for (const Edge& e : adj_[u])
+                if (d + e.d < dist[e.to]) dist[e.to] = d + e.d, prev[e.to] = u, pq.push({dist[e.to], e.to});
+        }
+        std::vector<State> path;
+        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(this->states_[x]);
+        std::reverse(path.begin(), path.end());
+        return path;
+    }
+    template <typename Fn>
+    void solution(Fn fn) const {
+        for (const State& q : solution()) fn(q);
+    }
+    void printStats() const {
+        std::clog << "nodes in graph: " << this->size() << "\n";
+        if constexpr (reportStats) this->printStageStats();
+    }
+    template <typename Visitor>
+    void visitGraph(Visitor&& visitor) const {  // :380-387
+        for (std::uint32_t n = 0; n < this->states_.size(); ++n) {
+            visitor.vertex(this->states_[n]);
+            for (const Edge& e : adj_[n]) visitor.edge(this->states_[e.to]);
+        }
+    }
+    std::size_t edgeCount() const {
+        std::size_t c = 0;
+        for (auto& a : adj_) c += a.size();
+        return c / 2;
+    }
+
+private:
+    // Worker::addSample for a batch (:298-339)
+    void addSamples(const std::vector<State>& samples, std::uint8_t flags) {
+        std::vector<std::uint8_t> ok;
+        this->validBatch(samples, ok);  // :299
+        std::vector<State> keep;
+        for (std::size_t i = 0; i < samples.size(); ++i)
+            if (ok[i]) keep.push_back(samples[i]);
+        if (keep.empty()) return;
+        const std::size_t n0 = this->size();
+        std::vector<State> fresh;
+        std::vector<std::uint32_t> slot;  // index into `keep` (for neighbour rows)
+        std::uint32_t k = 0;
+        if (n0 > 0) {
+            k = std::min<unsigned>(std::max(1, (int)std::ceil(kRRG_ * std::log(Distance(n0 + 1)))), MPTG_MAX_K);  // :302-303
+            auto scope = this->tNearestK_.time(keep.size());
+            this->nn_->nearest(keep.data(), (std::uint32_t)keep.size(), k);  // :304
+        }
+        const Distance minDist = std::numeric_limits<Distance>::epsilon();  // :306-308
+        for (std::uint32_t i = 0; i < keep.size(); ++i) {
+            if (n0 > 0 && this->nn_->counts()[i] > 0 && this->nn_->distances()[(std::size_t)i * k] < minDist) continue;
+            fresh.push_back(keep[i]);
+            slot.push_back(i);
+        }
+        // all (sample, neighbour) edges in one batch (:325-326)
+        std::vector<State> from, to;
+        std::vector<std::pair<std::uint32_t, std::uint32_t>> pairs;  // (fresh index, neighbour node)
+        std::vector<Distance> pd;
+        if (n0 > 0)
+            for (std::uint32_t f = 0; f < fresh.size(); ++f) {
+                const std::uint32_t i = slot[f];
+                for (std::uint32_t j = 0; j < this->nn_->counts()[i]; ++j) {
+                    const std::uint32_t nb = this->nn_->indices()[(std::size_t)i * k + j];
+                    from.push_back(fresh[f]);
+                    to.push_back(this->states_[nb]);
+                    pairs.push_back({f, nb});
+                    pd.push_back(this->nn_->distances()[(std::size_t)i * k + j]);
+                }
+            }
+        std::vector<std::uint8_t> eok;
+        this->linkBatch(from, to, eok);
+        const std::uint32_t first = (std::uint32_t)this->states_.size();
+        for (std::uint32_t f = 0; f < fresh.size(); ++f) {
+            const std::uint32_t id = first + f;
+            std::uint8_t fl = flags;
+            if (!(fl & kGoal) && checkGoal(this->scenario_, fresh[f]).first) fl |= kGoal;  // :312-316
+            adj_.emplace_back();
+            comp_.push_back(id);
+            compSize_.push_back(1);
+            compFlags_.push_back(fl);
+            if (fl & kGoal) goalNodes_.push_back(id);
+            if (fl & kStart) startNodes_.push_back(id);
+            if ((fl & (kStart | kGoal)) == (kStart | kGoal)) solved_ = true;
+        }
+        for (std::size_t e = 0; e < pairs.size(); ++e)
+            if (eok[e]) {
+                const std::uint32_t id = first + pairs[e].first, nb = pairs[e].second;
+                adj_[id].push_back({nb, pd[e]});
+                adj_[nb].push_back({id, pd[e]});
+                merge(id, nb);  // :327-334
+            }
+        this->addNodes(fresh);  // :337
+    }
+};
+
+// ------------------------------------------------------------------ resolvers (planner.hpp:41-47)
+template <typename Scenario, typename Algorithm>
+struct PlannerResolver;
+
+template <typename Scenario, typename... Options>
+struct PlannerResolver<Scenario, PRRT<Options...>> {
+    using type = WavePRRT<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>>;
+};
+template <typename Scenario, typename... Options>
+struct PlannerResolver<Scenario, PRRTStar<Options...>> {
+    static constexpr bool kNearest = pack_contains_v<rewire_k_nearest, Options...>;
+    static constexpr bool rNearest = pack_contains_v<rewire_r_nearest, Options...>;
+    static_assert(!(kNearest && rNearest), "RRT* tags cannot include both k_nearest and r_nearest");
+    using Rewire = std::conditional_t<!rNearest, rewire_k_nearest, rewire_r_nearest>;
+    using type = WavePRRTStar<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, Rewire, pack_bool_tag_v<report_stats, false, Options...>>;
+};
+template <typename Scenario, typename... Options>
+struct PlannerResolver<Scenario, PPRM<Options...>> {
+    using type = WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>>;
+};
+
+}  // namespace impl
+
+template <typename Scenario, typename Algorithm>
+using Planner = typename impl::PlannerResolver<Scenario, Algorithm>::type;
+
+}  // namespace mptg

@@ -1,0 +1,129 @@
+// planner_test.cpp -- the reference's planner integration tests (test/planner_integration_test.hpp:219-254,
+// test/{prrt,prrt_star,pprm}_integration_test.cpp, test/pack_nearest_test.cpp:39-69,
+// test/prrt_star_integration_test.cpp:43-57) re-expressed for the wave planners, plus the
+// stronger check of SURVEY.md Appendix B item 4 (every returned edge re-validates).
+// Links against libmptg.so (GPU) or the test-only mock of the same C ABI (CPU, host logic only).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "mptg/planner.hpp"
+#include "mptg/scenarios.hpp"
+
+using namespace mptg;
+using namespace std::literals;
+
+static int failures = 0;
+#define EXPECT(cond)                                                        \
+    do {                                                                    \
+        if (!(cond)) {                                                      \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);     \
+            ++failures;                                                     \
+        }                                                                   \
+    } while (0)
+
+template <typename T, typename Q, typename = void>
+struct has_add_goal : std::false_type {};
+template <typename T, typename Q>
+struct has_add_goal<T, Q, std::void_t<decltype(std::declval<T>().addGoal(std::declval<Q>()))>> : std::true_type {};
+
+template <typename Algorithm>
+void testSolvingBasicScenario(const char* name) {
+    using Scenario = test::BasicScenario<double, 3>;
+    using State = Scenario::State;
+    Planner<Scenario, Algorithm> planner(Scenario(), 12345);
+    planner.addStart(Scenario::startState());
+    if constexpr (has_add_goal<Planner<Scenario, Algorithm>, State>::value) planner.addGoal(Scenario::goalState());
+    auto t0 = std::chrono::steady_clock::now();
+    planner.solveFor([&] { return planner.solved(); }, 10s);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    planner.printStats();
+    EXPECT(planner.solved());
+    std::vector<State> solution = planner.solution();
+    EXPECT(solution.size() > 2);  // start + end + at least one waypoint around the obstacle
+    EXPECT(!solution.empty() && solution[0] == Scenario::startState());
+    EXPECT(!solution.empty() && solution.back() == Scenario::goalState());
+    auto sit = solution.begin();
+    planner.solution([&](const State& a) {
+        EXPECT(sit != solution.end() && *sit == a);
+        ++sit;
+    });
+    EXPECT(sit == solution.end());
+    // every edge of the returned path re-validates on the device (stronger than the reference)
+    if (solution.size() >= 2) {
+        Context ctx;
+        Scenario sc;
+        Geometry g = sc.makeGeometry(ctx);
+        std::vector<State> from(solution.begin(), solution.end() - 1), to(solution.begin() + 1, solution.end());
+        std::vector<std::uint8_t> ok(from.size());
+        auto desc = sc.space().desc();
+        g.link(&desc, from.data(), to.data(), (std::uint32_t)from.size(), 0.0, ok.data());
+        for (auto v : ok) EXPECT(v == 1);
+    }
+    std::size_t verts = 0, edges = 0;
+    struct Visitor {
+        std::size_t &v, &e;
+        void vertex(const State&) { ++v; }
+        void edge(const State&) { ++e; }
+    };
+    planner.visitGraph(Visitor{verts, edges});
+    EXPECT(verts == planner.size());
+    std::printf("%s %s: solved=%d in %.3f s, %zu nodes, %zu graph edges, %zu waypoints\n", failures ? "FAIL" : "PASS", name,
+                (int)planner.solved(), secs, planner.size(), edges, solution.size());
+}
+
+void testPRRTStarInvariants() {
+    // cost(node) == cost(parent) + distance(parent, node) up to rounding, after rewiring
+    using Scenario = test::BasicScenario<double, 3>;
+    Planner<Scenario, PRRTStar<wave_size<256>>> planner(Scenario(), 99);
+    planner.addStart(Scenario::startState());
+    planner.setRange(0.5);
+    planner.solve([&] { return planner.size() > 3000; });
+    Scenario sc;
+    double worst = 0;
+    for (std::uint32_t n = 1; n < planner.size(); ++n) {
+        const std::uint32_t p = planner.nodeParent(n);
+        EXPECT(p < planner.size());
+        const double want = planner.nodeCost(p) + sc.space().distance(planner.nodeState(p), planner.nodeState(n));
+        worst = std::max(worst, std::abs(want - planner.nodeCost(n)));
+    }
+    EXPECT(worst < 1e-9);
+    if (planner.solved()) EXPECT(planner.solutionCost() > 0);
+    std::printf("%s PRRT* invariants: %zu nodes, worst cost residual %.3g, solution cost %.6f\n", failures ? "FAIL" : "PASS", planner.size(),
+                worst, planner.solved() ? planner.solutionCost() : -1.0);
+}
+
+int main() {
+    // test/pack_nearest_test.cpp:39-69 analogue: the strategy tag is recognised, absent -> void
+    static_assert(std::is_same_v<impl::pack_nearest_t<>, void>);
+    static_assert(std::is_same_v<impl::pack_nearest_t<int, report_stats<true>>, void>);
+    static_assert(std::is_same_v<impl::pack_nearest_t<GpuBatch>, GpuBatch>);
+    static_assert(std::is_same_v<impl::pack_nearest_t<report_stats<true>, GpuBatch, single_threaded>, GpuBatch>);
+    // test/prrt_star_integration_test.cpp:43-57: option order does not change the planner type
+    using S = test::BasicScenario<double, 3>;
+    static_assert(std::is_same_v<Planner<S, PRRTStar<report_stats<true>, rewire_r_nearest, GpuBatch>>,
+                                 Planner<S, PRRTStar<GpuBatch, rewire_r_nearest, report_stats<true>>>>);
+    static_assert(!std::is_same_v<Planner<S, PRRTStar<rewire_r_nearest>>, Planner<S, PRRTStar<rewire_k_nearest>>>);
+    static_assert(std::is_same_v<Planner<S, PRRTStar<>>, Planner<S, PRRTStar<rewire_k_nearest>>>);
+
+    testSolvingBasicScenario<PRRT<report_stats<true>>>("PRRT");
+    testSolvingBasicScenario<PRRT<GpuBatch, wave_size<64>>>("PRRT wave 64");
+    testSolvingBasicScenario<PRRTStar<report_stats<true>>>("PRRT* k-nearest");
+    testSolvingBasicScenario<PRRTStar<rewire_r_nearest>>("PRRT* r-nearest");
+    testSolvingBasicScenario<PPRM<report_stats<true>>>("PPRM");
+    testPRRTStarInvariants();
+    // error behaviour (impl/prrt/prrt.hpp:197-198, impl/pprm/pprm.hpp:179-180)
+    {
+        Planner<S, PRRT<>> p(S(), 1);
+        bool threw = false;
+        try {
+            p.solve([] { return true; });
+        } catch (const std::runtime_error&) {
+            threw = true;
+        }
+        EXPECT(threw);
+    }
+    std::printf("%d failures\n", failures);
+    return failures ? 1 : 0;
+}
