@@ -9,6 +9,10 @@
 // The reference's PNG and OMPL meshes are not redistributable inputs of this repository: the map is
 // a synthetic one of the same size unless --map gives a binary PGM (tools/png_to_pgm.py converts the
 // reference image with the reference's colour filters), the meshes are procedural bent tubes.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -82,8 +86,10 @@ template <typename Planner>
 std::pair<double, double> runUntilSolved(Planner& planner, double timeMs) {
     const auto t0 = Clock::now();
     double first = -1;
+    const bool trace = std::getenv("MPTG_DEMO_TRACE") != nullptr;
     planner.solveFor(
         [&] {
+            if (trace) std::fprintf(stderr, "trace: %zu nodes, solved=%d\n", planner.size(), (int)planner.solved());
             if (first < 0 && planner.solved()) first = std::chrono::duration<double>(Clock::now() - t0).count();
             return planner.solved();
         },
@@ -150,13 +156,47 @@ void png2d(const Options& opt) {
     State start = makeState<Scalar, 2>({430, 1300}), goal = makeState<Scalar, 2>({3150, 950});  // png_2d_planning.cpp:84-86
     if (opt.map.empty() || !readPgm(opt.map, width, height, occ)) {
         occ = syntheticMap(width, height, 11);
-        auto clear = [&](const State& q) {  // keep the shipped start / goal usable on the synthetic map
-            for (int y = (int)q[1] - 40; y <= (int)q[1] + 40; ++y)
-                for (int x = (int)q[0] - 40; x <= (int)q[0] + 40; ++x)
-                    if (x >= 0 && y >= 0 && x < width && y < height) occ[(std::size_t)y * width + x] = 0;
-        };
-        clear(start);
-        clear(goal);
+        // keep the shipped start usable on the synthetic map, then move the goal to the reachable free
+        // cell (8 px clearance) closest to the shipped goal
+        for (int y = (int)start[1] - 40; y <= (int)start[1] + 40; ++y)
+            for (int x = (int)start[0] - 40; x <= (int)start[0] + 40; ++x)
+                if (x >= 0 && y >= 0 && x < width && y < height) occ[(std::size_t)y * width + x] = 0;
+        std::vector<std::uint8_t> seen((std::size_t)width * height, 0);
+        std::vector<std::uint32_t> frontier{(std::uint32_t)((int)start[1] * width + (int)start[0])};
+        seen[frontier[0]] = 1;
+        while (!frontier.empty()) {
+            const std::uint32_t c = frontier.back();
+            frontier.pop_back();
+            const int x = (int)(c % width), y = (int)(c / width);
+            const int nx[4] = {x + 1, x - 1, x, x}, ny[4] = {y, y, y + 1, y - 1};
+            for (int i = 0; i < 4; ++i)
+                if (nx[i] >= 0 && ny[i] >= 0 && nx[i] < width && ny[i] < height) {
+                    const std::uint32_t n = (std::uint32_t)(ny[i] * width + nx[i]);
+                    if (!seen[n] && !occ[n]) seen[n] = 1, frontier.push_back(n);
+                }
+        }
+        double best = 1e300;
+        State moved = goal;
+        for (int y = 8; y < height - 8; y += 4)
+            for (int x = 8; x < width - 8; x += 4) {
+                if (!seen[(std::size_t)y * width + x]) continue;
+                const double d = (x - goal[0]) * (x - goal[0]) + (y - goal[1]) * (y - goal[1]);
+                if (d >= best) continue;
+                bool clearAround = true;
+                for (int yy = y - 8; yy <= y + 8 && clearAround; ++yy)
+                    for (int xx = x - 8; xx <= x + 8; ++xx)
+                        if (occ[(std::size_t)yy * width + xx]) {
+                            clearAround = false;
+                            break;
+                        }
+                if (clearAround) best = d, moved = makeState<Scalar, 2>({(Scalar)x, (Scalar)y});
+            }
+        goal = moved;
+    }
+    if (const char* dump = std::getenv("MPTG_DEMO_DUMP_MAP")) {
+        std::ofstream f(dump, std::ios::binary);
+        f << "P5\n" << width << " " << height << "\n255\n";
+        for (auto c : occ) f.put(c ? (char)255 : (char)0);
     }
     Scenario scenario(width, height, goal, occ);
     Planner<Scenario, PRRTStar<report_stats<true>, wave_size<2048>>> planner(scenario, opt.seed);
@@ -268,7 +308,19 @@ void linkManipulator(const Options& opt) {
     report(name, "PPRM", planner, scenario, first, total, opt);
 }
 
+static void onCrash(int sig) {
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "planning_demos: fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char** argv) {
+    signal(SIGSEGV, onCrash);
+    signal(SIGABRT, onCrash);
+    std::setvbuf(stdout, nullptr, _IOLBF, 0);
     Options opt;
     std::string which = "all";
     for (int i = 1; i < argc; ++i) {

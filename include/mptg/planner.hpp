@@ -569,9 +569,10 @@ private:
             auto scope = this->tNearestK_.time(S);
             this->nn_->nearest(fresh.data(), S, k, radius);
         }
-        const auto& nIdx = this->nn_->indices();
-        const auto& nDist = this->nn_->distances();
-        const auto& nCnt = this->nn_->counts();
+        // copies: addNodes() below may grow (re-create) the device structure that owns these vectors
+        const std::vector<std::uint32_t> nIdx = this->nn_->indices();
+        const std::vector<Distance> nDist = this->nn_->distances();
+        const std::vector<std::uint32_t> nCnt = this->nn_->counts();
 
         // candidate parents in (cost + distance) order up to the near node (:565-605), checked in ONE batch
         struct Cand {

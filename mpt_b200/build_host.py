@@ -12,7 +12,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 CXX = "/usr/bin/g++"
-FLAGS = ["-std=c++17", "-O2", "-g", "-ffp-contract=off", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}"]
+FLAGS = ["-std=c++17", "-O2", "-g", "-rdynamic", "-ffp-contract=off", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}"]
 
 
 def _stale(out: Path, deps) -> bool:

@@ -76,6 +76,21 @@ inline int scratch(mptg_ctx* ctx, int slot, size_t bytes, void** out) {
     return MPTG_OK;
 }
 
+// Host -> device upload that is complete when it returns.  cudaMemcpy from pageable memory may return
+// while the DMA is still in flight, and the context stream is non-blocking (not ordered after the
+// legacy default stream), so every upload goes through the context stream and is synchronised.
+inline int uploadSync(mptg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return MPTG_OK;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+inline int memsetSync(mptg_ctx* ctx, void* dst, int value, size_t bytes) {
+    MPTG_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
 inline int spaceScalars(const mptg_space_desc* s) {
     if (!s || s->n_parts < 1 || s->n_parts > MPTG_MAX_PARTS) return -1;
     if (s->scalar != MPTG_F32 && s->scalar != MPTG_F64) return -1;

@@ -323,8 +323,7 @@ int uploadScalars(mptg_ctx* ctx, const double* src, size_t count, void** dst) {
     std::vector<S> tmp(count);
     for (size_t i = 0; i < count; ++i) tmp[i] = (S)src[i];
     MPTG_CUDA(ctx, cudaMalloc(dst, (count ? count : 1) * sizeof(S)));
-    if (count) MPTG_CUDA(ctx, cudaMemcpy(*dst, tmp.data(), count * sizeof(S), cudaMemcpyHostToDevice));
-    return MPTG_OK;
+    return uploadSync(ctx, *dst, tmp.data(), count * sizeof(S));
 }
 
 int newGeom(mptg_ctx* ctx, int kind, int scalar, mptg_geom** out) {
@@ -333,10 +332,10 @@ int newGeom(mptg_ctx* ctx, int kind, int scalar, mptg_geom** out) {
     g->kind = kind;
     g->scalar = scalar;
     cudaError_t e = cudaMalloc(&g->devStats, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(g->devStats, 0, 8 * sizeof(unsigned long long));
-    if (e != cudaSuccess) {
+    if (e != cudaSuccess || memsetSync(ctx, g->devStats, 0, 8 * sizeof(unsigned long long)) != MPTG_OK) {
+        if (e == cudaSuccess) cudaFree(g->devStats);
         delete g;
-        return fail(ctx, MPTG_ERR_CUDA, "geometry create: %s", cudaGetErrorString(e));
+        return fail(ctx, MPTG_ERR_CUDA, "geometry create: %s", e != cudaSuccess ? cudaGetErrorString(e) : "memset failed");
     }
     *out = g;
     return MPTG_OK;
@@ -443,10 +442,14 @@ int mptg_grid_create(mptg_ctx* ctx, int scalar, int32_t width, int32_t height, c
     for (size_t i = 0; i < cells; ++i)
         if (occupancy[i]) bits[i >> 5] |= 1u << (i & 31);
     cudaError_t e = cudaMalloc(&g->gridBits, words * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(g->gridBits, bits.data(), words * 4, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         mptg_geom_destroy(g);
         return fail(ctx, MPTG_ERR_CUDA, "mptg_grid_create: %s", cudaGetErrorString(e));
+    }
+    rc = uploadSync(ctx, g->gridBits, bits.data(), words * 4);
+    if (rc) {
+        mptg_geom_destroy(g);
+        return rc;
     }
     *out = g;
     return MPTG_OK;
@@ -571,7 +574,8 @@ int mptg_link_batch_dev(mptg_geom* g, const mptg_space_desc* space, const void* 
 static int checkDeviceErrors(mptg_geom* g) {
     // called after a synchronise: surface device-side error flags
     unsigned long long host[8];
-    MPTG_CUDA(g->ctx, cudaMemcpy(host, g->devStats, sizeof host, cudaMemcpyDeviceToHost));
+    MPTG_CUDA(g->ctx, cudaMemcpyAsync(host, g->devStats, sizeof host, cudaMemcpyDeviceToHost, g->ctx->stream));
+    MPTG_CUDA(g->ctx, cudaStreamSynchronize(g->ctx->stream));
     for (int i = 0; i < 4; ++i) g->stats[i] = host[i];
     if (host[4] & GEOM_ERR_STACK) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: traversal stack overflow (edge too long / geometry too deep)");
     if (host[4] & GEOM_ERR_STEPS) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: too many interpolation steps on one edge");

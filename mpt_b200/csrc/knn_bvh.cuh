@@ -373,8 +373,9 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     // 1. fetch the points (SoA rows -> AoS on the host), canonicalise rotations
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::vector<S> soa((size_t)D * n);
-    MPTG_CUDA(ctx, cudaMemcpy2D(soa.data(), (size_t)n * sizeof(S), ptsDev, (size_t)stride * sizeof(S), (size_t)n * sizeof(S), D,
-                                cudaMemcpyDeviceToHost));
+    MPTG_CUDA(ctx, cudaMemcpy2DAsync(soa.data(), (size_t)n * sizeof(S), ptsDev, (size_t)stride * sizeof(S), (size_t)n * sizeof(S), D,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     HostBuild<S> hb;
     hb.D = D;
     hb.pts.resize((size_t)n * D);
@@ -473,11 +474,11 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
         memBytes = bytes + bytes / 2;
         MPTG_CUDA(ctx, cudaMalloc(&mem, memBytes));
     }
-    MPTG_CUDA(ctx, cudaMemcpy(mem, host.data(), bytes, cudaMemcpyHostToDevice));
+    if (int rc = uploadSync(ctx, mem, host.data(), bytes)) return rc;
     unsigned long long* stats = ix.devStats;
     if (!stats) {
         MPTG_CUDA(ctx, cudaMalloc(&stats, 4 * sizeof(unsigned long long)));
-        MPTG_CUDA(ctx, cudaMemset(stats, 0, 4 * sizeof(unsigned long long)));
+        if (int rc = memsetSync(ctx, stats, 0, 4 * sizeof(unsigned long long))) return rc;
     }
     nx.mem = mem;
     nx.memBytes = memBytes;
@@ -549,10 +550,11 @@ inline int knnIndexReadStats(mptg_ctx* ctx, KnnIndex& ix, uint64_t* stats) {
     if (!ix.devStats || ix.count == 0 || stats[3] != MPTG_KNN_BVH) return MPTG_OK;
     unsigned long long h[4];
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    MPTG_CUDA(ctx, cudaMemcpy(h, ix.devStats, sizeof h, cudaMemcpyDeviceToHost));
+    MPTG_CUDA(ctx, cudaMemcpyAsync(h, ix.devStats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     stats[0] += h[0] * 32ull;
     stats[1] = h[0] + h[1];
-    MPTG_CUDA(ctx, cudaMemset(ix.devStats, 0, sizeof h));
+    MPTG_CUDA(ctx, cudaMemsetAsync(ix.devStats, 0, sizeof h, ctx->stream));
     return MPTG_OK;
 }
 

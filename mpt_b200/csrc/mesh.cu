@@ -470,9 +470,9 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
     }
     *depth = b.maxDepth;
     MPTG_CUDA(ctx, cudaMalloc(nodesDev, b.nodes.size() * sizeof(BvhNode)));
-    MPTG_CUDA(ctx, cudaMemcpy(*nodesDev, b.nodes.data(), b.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    if (int rc = uploadSync(ctx, *nodesDev, b.nodes.data(), b.nodes.size() * sizeof(BvhNode))) return rc;
     MPTG_CUDA(ctx, cudaMalloc(trisDev, pad.size() * sizeof(TriPad)));
-    MPTG_CUDA(ctx, cudaMemcpy(*trisDev, pad.data(), pad.size() * sizeof(TriPad), cudaMemcpyHostToDevice));
+    if (int rc = uploadSync(ctx, *trisDev, pad.data(), pad.size() * sizeof(TriPad))) return rc;
     return MPTG_OK;
 }
 

@@ -192,6 +192,20 @@ def test_knn_double_precision(ctx, oracle):
     assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
 
 
+@pytest.mark.parametrize("strategy", [m.KNN_BRUTE, m.KNN_BVH])
+def test_knn_f64_planar_like_the_png_demo(ctx, oracle, strategy):
+    """L2 in the plane, double precision (the PNG / holonomic demos), k as PRRT* asks for it."""
+    sp = m.lp_space(2, 2, m.F64)
+    pts = W.box_states(20_000, 2, 3, 0.0, [3976, 2603], np.float64)
+    q = W.box_states(700, 2, 4, 0.0, [3976, 2603], np.float64)
+    q[:50] = pts[:50]
+    nn = m.Nearest(ctx, sp, 32768, strategy)
+    nn.insert(pts)
+    for k, radius in ((1, -1.0), (16, -1.0), (44, -1.0), (100, -1.0), (128, 300.0)):
+        assert_knn_equal(nn.nearest(q, k, radius), oracle.knn(sp, pts, q, k, radius))
+    nn.close()
+
+
 def test_knn_incremental_like_a_planner(ctx, oracle):
     """Insert in waves, query between waves (the planner's access pattern)."""
     sp = m.lp_space(2, 2)
