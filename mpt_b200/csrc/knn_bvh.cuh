@@ -37,13 +37,11 @@ struct KnnIndex {
     uint32_t nPad = 0;     // leaves * 32
     int top = 0;           // top level (0 = leaves)
     uint32_t nNodes[BVH_MAXL] = {0, 0, 0, 0, 0};
-    uint32_t nStride[BVH_MAXL] = {0, 0, 0, 0, 0};  // nodes padded to a multiple of 32
-    void* mem = nullptr;   // one block: sorted points, perm, boxes
+    void* mem = nullptr;   // one block: leaf points, perm, boxes
     size_t memBytes = 0;
-    void* spts = nullptr;  // [D][nPad]
+    void* leafPts = nullptr;  // [leaf][D][32]
     uint32_t* perm = nullptr;
-    void* lo[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [D][nStride[l]]
-    void* hi[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* box[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][2D][32]
     unsigned long long* devStats = nullptr;  // [0] leaves visited, [1] inner nodes visited
     uint64_t builds = 0;
 };
@@ -125,15 +123,15 @@ MPTG_HD S boxLowerBound(const DevSpace<S>& sp, LO lo, HI hi, QF q) {
 }  // namespace dev
 
 // ------------------------------------------------------------------ search kernel
+// Device layouts are blocked so that one address computation serves a whole node visit:
+//   leaves  leafPts[leaf][c][32]            (scalar c of the leaf's 32 points)
+//   boxes   box[l][block][r][32], r < D: lo of scalar r, r >= D: hi of scalar r - D; block = node / 32
 template <typename S>
 struct BvhArgs {
-    const S* spts;
-    uint32_t nPad;
+    const S* leafPts;
     const uint32_t* perm;
-    const S* lo[BVH_MAXL];
-    const S* hi[BVH_MAXL];
+    const S* box[BVH_MAXL];
     uint32_t nNodes[BVH_MAXL];
-    uint32_t nStride[BVH_MAXL];
     int top;
     const S* queries;
     uint32_t Q, k;
@@ -167,7 +165,135 @@ __device__ __forceinline__ float thrAsFloat<double>(double thr) {
     return __double2float_ru(thr);
 }
 
+__device__ __forceinline__ float sqrtApprox(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Cheap SE(3) lower bound from |dot| (or its box maximum) and the squared translation distance
+// (or its box minimum).  Uses acos(x) >= sqrt(2 - 2x) on [0,1], approximate square roots and fused
+// arithmetic; the slack terms (|dot| + 1e-6, result * (1 - 1e-5)) dominate every rounding error of
+// this expression and of the exact distance (a handful of 6e-8 relative errors), so
+// bound <= fl-distance for every point concerned.
+__device__ __forceinline__ float se3CheapBound(float ad, float s, float w0, float w1) {
+    const float t = fmaxf(0.0f, __fmaf_rn(-2.0f, ad + 1e-6f, 2.0f));
+    return __fmaf_rn(w0, sqrtApprox(t), w1 * sqrtApprox(s)) * (1.0f - 1e-5f);
+}
+
 constexpr int BVH_WARPS = 8;
+
+template <typename S, int SHAPE, int KPL>
+struct BvhWalk {
+    const BvhArgs<S>& a;
+    const S* myq;  // query in shared memory (generic path)
+    S qr[7];       // query in registers (SE(3) path)
+    float w0, w1;
+    WarpTopK<S, KPL> top;
+    int lane;
+    unsigned long long leaves = 0, inner = 0;
+
+    __device__ __forceinline__ BvhWalk(const BvhArgs<S>& args, const S* q, int ln) : a(args), myq(q), lane(ln) {}
+
+    __device__ __forceinline__ float threshold() const {
+        const S t = top.kthD < a.radius ? top.kthD : a.radius;
+        return thrAsFloat<S>(t);
+    }
+
+    // key (float bits of a lower bound) of child `lane` of `block` at level L
+    template <int L>
+    __device__ __forceinline__ uint32_t childKey(uint32_t block) const {
+        const uint32_t node = block * 32u + (uint32_t)lane;
+        if (node >= a.nNodes[L]) return BVH_DEAD;
+        const int D = a.sp.D;
+        const S* b = a.box[L] + ((size_t)block * (size_t)(2 * D)) * 32u + lane;
+        if (SHAPE == SHAPE_SE3 && sizeof(S) == 4) {
+            float dotHi, dotLo;
+            {
+                const float l = __ldg((const float*)b), h = __ldg((const float*)b + 7 * 32);
+                const float v = (float)qr[0];
+                dotHi = (v >= 0.0f ? h : l) * v;
+                dotLo = (v >= 0.0f ? l : h) * v;
+            }
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
+                const float v = (float)qr[j];
+                dotHi = __fmaf_rn(v >= 0.0f ? h : l, v, dotHi);
+                dotLo = __fmaf_rn(v >= 0.0f ? l : h, v, dotLo);
+            }
+            const float ad = fminf(1.0f, fmaxf(dotHi, -dotLo));
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 4; j < 7; ++j) {
+                const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
+                const float v = (float)qr[j];
+                const float e = fmaxf(fmaxf(l - v, v - h), 0.0f);
+                acc = __fmaf_rn(e, e, acc);
+            }
+            return __float_as_uint(se3CheapBound(ad, acc, w0, w1) + 0.0f);
+        } else {
+            const S lb = dev::boxLowerBound<S>(
+                a.sp, [&](int c) { return __ldg(b + c * 32); }, [&](int c) { return __ldg(b + (D + c) * 32); },
+                [&](int c) { return myq[c]; });
+            return boundKey<S>(lb);
+        }
+    }
+
+    __device__ __forceinline__ void leaf(uint32_t node) {
+        ++leaves;
+        const int D = a.sp.D;
+        const uint32_t p = node * 32u + (uint32_t)lane;
+        const uint32_t orig = __ldg(a.perm + p);
+        const bool have = orig != MPTG_NO_INDEX;
+        const S* pt = a.leafPts + ((size_t)node * (size_t)D) * 32u + lane;
+        if (SHAPE == SHAPE_SE3 && sizeof(S) == 4) {
+            float pv[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) pv[c] = __ldg((const float*)pt + c * 32);
+            // exact-order pieces shared by the prefilter and the distance (mptg_space.h)
+            float dot = pv[0] * (float)qr[0];
+            dot = __fmaf_rn(pv[1], (float)qr[1], dot);
+            dot = __fmaf_rn(pv[2], (float)qr[2], dot);
+            dot = __fmaf_rn(pv[3], (float)qr[3], dot);
+            const float d0 = pv[4] - (float)qr[4], d1 = pv[5] - (float)qr[5], d2 = pv[6] - (float)qr[6];
+            float s2 = d0 * d0;
+            s2 = __fmaf_rn(d1, d1, s2);
+            s2 = __fmaf_rn(d2, d2, s2);
+            const float ad = fminf(1.0f, fabsf(dot));
+            const bool maybe = have && se3CheapBound(ad, s2, w0, w1) <= threshold();
+            if (!__any_sync(FULL_MASK, maybe)) return;
+            float dr = fp::acos01(ad);
+            if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
+            float dt = fp::sqrt_(s2);
+            if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
+            top.offer(maybe, (S)(dr + dt), orig * a.idxMul + a.idxAdd, a.radius, lane);
+        } else {
+            const S dist = dev::distance<S>(
+                a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
+            top.offer(have, dist, orig * a.idxMul + a.idxAdd, a.radius, lane);
+        }
+    }
+
+    // visit the children (level L nodes) of `block`, nearest bound first
+    template <int L>
+    __device__ __forceinline__ void descend(uint32_t block) {
+        uint32_t key = childKey<L>(block);
+        for (;;) {
+            const uint32_t best = __reduce_min_sync(FULL_MASK, key);
+            if (best == BVH_DEAD || __uint_as_float(best) > threshold()) return;
+            const int src = __ffs(__ballot_sync(FULL_MASK, key == best)) - 1;
+            if (lane == src) key = BVH_DEAD;
+            const uint32_t node = block * 32u + (uint32_t)src;
+            if constexpr (L == 0) {
+                leaf(node);
+            } else {
+                ++inner;
+                descend<L - 1>(node);
+            }
+        }
+    }
+};
 
 template <typename S, int SHAPE, int KPL>
 __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> a) {
@@ -181,135 +307,26 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
     S* myq = qsm + warp * D;
     for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
     __syncwarp();
-    S qr[7];
+    BvhWalk<S, SHAPE, KPL> w(a, myq, lane);
     if (SHAPE == SHAPE_SE3) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) qr[c] = myq[c];
+        for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
+        w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
+        w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
     }
-
-    WarpTopK<S, KPL> top;
-    top.init(a.k);
-    unsigned long long leaves = 0, inner = 0;
-
-    // lower bound of the distance to node `node` of level `lvl`
-    auto bound = [&](int lvl, uint32_t node) -> S {
-        const S* lo = a.lo[lvl];
-        const S* hi = a.hi[lvl];
-        const uint32_t st = a.nStride[lvl];
-        if (SHAPE == SHAPE_SE3) {
-            S dotHi, dotLo;
-            {
-                const S l = __ldg(lo + node), h = __ldg(hi + node);
-                const S v = qr[0];
-                dotHi = (v >= S(0) ? h : l) * v;
-                dotLo = (v >= S(0) ? l : h) * v;
-            }
-#pragma unroll
-            for (int j = 1; j < 4; ++j) {
-                const S l = __ldg(lo + (size_t)j * st + node), h = __ldg(hi + (size_t)j * st + node);
-                const S v = qr[j];
-                dotHi = fp::fma_(v >= S(0) ? h : l, v, dotHi);
-                dotLo = fp::fma_(v >= S(0) ? l : h, v, dotLo);
-            }
-            S ad = dotHi > -dotLo ? dotHi : -dotLo;
-            if (ad > S(1)) ad = S(1);
-            if (!(ad > S(0))) ad = S(0);
-            S dr = fp::acos01(ad) * (S(1) - S(8) * fp::consts<S>::eps());
-            if (a.sp.weighted[0]) dr = dr * a.sp.weight[0];
-            S acc = S(0);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const S l = __ldg(lo + (size_t)(4 + j) * st + node), h = __ldg(hi + (size_t)(4 + j) * st + node);
-                const S v = qr[4 + j];
-                const S e = v < l ? l - v : (v > h ? h - v : S(0));
-                acc = (j == 0) ? e * e : fp::fma_(e, e, acc);
-            }
-            S dt = fp::sqrt_(acc);
-            if (a.sp.weighted[1]) dt = dt * a.sp.weight[1];
-            return dr + dt;
-        } else {
-            return dev::boxLowerBound<S>(
-                a.sp, [&](int c) { return __ldg(lo + (size_t)c * st + node); },
-                [&](int c) { return __ldg(hi + (size_t)c * st + node); }, [&](int c) { return myq[c]; });
-        }
-    };
-
-    uint32_t key[BVH_MAXL];   // per lane: bound of "my" child at each level, BVH_DEAD when consumed/pruned
-    uint32_t base[BVH_MAXL];  // first child index at each level (warp-uniform)
-#pragma unroll
-    for (int l = 0; l < BVH_MAXL; ++l) {
-        key[l] = BVH_DEAD;
-        base[l] = 0;
+    w.top.init(a.k);
+    switch (a.top) {
+        case 0: w.template descend<0>(0); break;
+        case 1: w.template descend<1>(0); break;
+        case 2: w.template descend<2>(0); break;
+        case 3: w.template descend<3>(0); break;
+        default: w.template descend<4>(0); break;
     }
-    int cur = a.top;
-    {
-        const uint32_t node = (uint32_t)lane;
-        uint32_t kx = BVH_DEAD;
-        if (node < a.nNodes[cur]) kx = boundKey<S>(bound(cur, node));
-#pragma unroll
-        for (int l = 0; l < BVH_MAXL; ++l)
-            if (l == cur) key[l] = kx;
-    }
-    for (;;) {
-        uint32_t mine = BVH_DEAD;
-#pragma unroll
-        for (int l = 0; l < BVH_MAXL; ++l)
-            if (l == cur) mine = key[l];
-        const uint32_t best = __reduce_min_sync(FULL_MASK, mine);
-        const S thrS = top.kthD < a.radius ? top.kthD : a.radius;
-        const bool exhausted = best == BVH_DEAD || __uint_as_float(best) > thrAsFloat<S>(thrS);
-        if (exhausted) {
-            if (cur == a.top) break;
-            ++cur;
-            continue;
-        }
-        const int src = __ffs(__ballot_sync(FULL_MASK, mine == best)) - 1;
-        uint32_t b = 0;
-#pragma unroll
-        for (int l = 0; l < BVH_MAXL; ++l)
-            if (l == cur) {
-                if (lane == src) key[l] = BVH_DEAD;
-                b = base[l];
-            }
-        const uint32_t node = b + (uint32_t)src;
-        if (cur == 0) {
-            // leaf: 32 points, one per lane
-            ++leaves;
-            const uint32_t p = node * 32u + (uint32_t)lane;
-            const uint32_t orig = __ldg(a.perm + p);
-            const bool have = orig != MPTG_NO_INDEX;
-            S dist;
-            if (SHAPE == SHAPE_SE3) {
-                S pv[7];
-#pragma unroll
-                for (int c = 0; c < 7; ++c) pv[c] = __ldg(a.spts + (size_t)c * a.nPad + p);
-                dist = dev::se3Distance<S>(a.sp.weight[0], a.sp.weighted[0] != 0, a.sp.weight[1], a.sp.weighted[1] != 0, pv, qr);
-            } else {
-                dist = dev::distance<S>(
-                    a.sp, [&](int c) { return __ldg(a.spts + (size_t)c * a.nPad + p); }, [&](int c) { return myq[c]; });
-            }
-            top.offer(have, dist, orig * a.idxMul + a.idxAdd, a.radius, lane);
-        } else {
-            ++inner;
-            const int child = cur - 1;
-            const uint32_t cb = node * 32u;
-            const uint32_t cn = cb + (uint32_t)lane;
-            uint32_t kx = BVH_DEAD;
-            if (cn < a.nNodes[child]) kx = boundKey<S>(bound(child, cn));
-#pragma unroll
-            for (int l = 0; l < BVH_MAXL; ++l)
-                if (l == child) {
-                    key[l] = kx;
-                    base[l] = cb;
-                }
-            cur = child;
-        }
-    }
-    const uint32_t count = top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
+    const uint32_t count = w.top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
     if (a.countOut && lane == 0) a.countOut[q] = count;
     if (lane == 0 && a.stats) {
-        atomicAdd(a.stats + 0, leaves);
-        atomicAdd(a.stats + 1, inner);
+        atomicAdd(a.stats + 0, w.leaves);
+        atomicAdd(a.stats + 1, w.inner);
     }
 }
 
@@ -396,7 +413,7 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
 #pragma omp parallel
 #pragma omp single
     hb.split(0, n);
-    // 3. levels
+    // 3. levels: SoA boxes per level on the host first
     KnnIndex nx;
     nx.count = n;
     nx.nNodes[0] = (n + 31) / 32;
@@ -407,6 +424,37 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
         nx.nNodes[nx.top + 1] = (nx.nNodes[nx.top] + 31) / 32;
         ++nx.top;
     }
+    const S inf = fp::consts<S>::inf();
+    std::vector<std::vector<S>> lo(nx.top + 1), hi(nx.top + 1);
+    for (int l = 0; l <= nx.top; ++l) {
+        const uint32_t nn = nx.nNodes[l];
+        lo[l].assign((size_t)D * nn, inf);
+        hi[l].assign((size_t)D * nn, -inf);
+        if (l == 0) {
+#pragma omp parallel for schedule(static)
+            for (int64_t j = 0; j < (int64_t)nn; ++j)
+                for (uint32_t i = (uint32_t)j * 32; i < (uint32_t)j * 32 + 32 && i < n; ++i) {
+                    const S* pt = &hb.pts[(size_t)hb.order[i] * D];
+                    for (int c = 0; c < D; ++c) {
+                        lo[0][(size_t)c * nn + j] = pt[c] < lo[0][(size_t)c * nn + j] ? pt[c] : lo[0][(size_t)c * nn + j];
+                        hi[0][(size_t)c * nn + j] = pt[c] > hi[0][(size_t)c * nn + j] ? pt[c] : hi[0][(size_t)c * nn + j];
+                    }
+                }
+        } else {
+            const uint32_t cn = nx.nNodes[l - 1];
+            for (uint32_t j = 0; j < nn; ++j)
+                for (int c = 0; c < D; ++c) {
+                    S mn = inf, mx = -inf;
+                    for (uint32_t i = j * 32; i < j * 32 + 32 && i < cn; ++i) {
+                        mn = lo[l - 1][(size_t)c * cn + i] < mn ? lo[l - 1][(size_t)c * cn + i] : mn;
+                        mx = hi[l - 1][(size_t)c * cn + i] > mx ? hi[l - 1][(size_t)c * cn + i] : mx;
+                    }
+                    lo[l][(size_t)c * nn + j] = mn;
+                    hi[l][(size_t)c * nn + j] = mx;
+                }
+        }
+    }
+    // blocked device image
     size_t bytes = 0;
     auto take = [&](size_t b) {
         const size_t o = bytes;
@@ -415,11 +463,11 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     };
     const size_t oPts = take((size_t)D * nx.nPad * sizeof(S));
     const size_t oPerm = take((size_t)nx.nPad * sizeof(uint32_t));
-    size_t oLo[BVH_MAXL], oHi[BVH_MAXL];
+    size_t oBox[BVH_MAXL] = {0, 0, 0, 0, 0};
+    uint32_t nBlocks[BVH_MAXL] = {0, 0, 0, 0, 0};
     for (int l = 0; l <= nx.top; ++l) {
-        nx.nStride[l] = ((nx.nNodes[l] + 31) / 32) * 32;
-        oLo[l] = take((size_t)D * nx.nStride[l] * sizeof(S));
-        oHi[l] = take((size_t)D * nx.nStride[l] * sizeof(S));
+        nBlocks[l] = (nx.nNodes[l] + 31) / 32;
+        oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(S));
     }
     std::vector<unsigned char> host(bytes, 0);
     S* hp = reinterpret_cast<S*>(host.data() + oPts);
@@ -427,43 +475,20 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     for (uint32_t i = 0; i < nx.nPad; ++i) {
         const uint32_t src = hb.order[i < n ? i : n - 1];  // padding repeats the last point (perm marks it unused)
         hperm[i] = i < n ? src : MPTG_NO_INDEX;
-        for (int c = 0; c < D; ++c) hp[(size_t)c * nx.nPad + i] = hb.pts[(size_t)src * D + c];
+        const uint32_t leaf = i >> 5, ln = i & 31;
+        for (int c = 0; c < D; ++c) hp[((size_t)leaf * D + c) * 32 + ln] = hb.pts[(size_t)src * D + c];
     }
-    const S inf = fp::consts<S>::inf();
     for (int l = 0; l <= nx.top; ++l) {
-        S* lo = reinterpret_cast<S*>(host.data() + oLo[l]);
-        S* hi = reinterpret_cast<S*>(host.data() + oHi[l]);
-        const uint32_t st = nx.nStride[l];
-        for (int c = 0; c < D; ++c)
-            for (uint32_t j = 0; j < st; ++j) lo[(size_t)c * st + j] = inf, hi[(size_t)c * st + j] = -inf;
-        if (l == 0) {
-#pragma omp parallel for schedule(static)
-            for (int64_t j = 0; j < (int64_t)nx.nNodes[0]; ++j)
+        S* bx = reinterpret_cast<S*>(host.data() + oBox[l]);
+        const uint32_t nn = nx.nNodes[l];
+        for (uint32_t b = 0; b < nBlocks[l]; ++b)
+            for (uint32_t ln = 0; ln < 32; ++ln) {
+                const uint32_t j = b * 32 + ln;
                 for (int c = 0; c < D; ++c) {
-                    S mn = inf, mx = -inf;
-                    for (uint32_t i = (uint32_t)j * 32; i < (uint32_t)j * 32 + 32; ++i) {
-                        const S v = hp[(size_t)c * nx.nPad + i];
-                        mn = v < mn ? v : mn;
-                        mx = v > mx ? v : mx;
-                    }
-                    lo[(size_t)c * st + j] = mn;
-                    hi[(size_t)c * st + j] = mx;
+                    bx[((size_t)b * 2 * D + c) * 32 + ln] = j < nn ? lo[l][(size_t)c * nn + j] : inf;
+                    bx[((size_t)b * 2 * D + D + c) * 32 + ln] = j < nn ? hi[l][(size_t)c * nn + j] : -inf;
                 }
-        } else {
-            const S* clo = reinterpret_cast<const S*>(host.data() + oLo[l - 1]);
-            const S* chi = reinterpret_cast<const S*>(host.data() + oHi[l - 1]);
-            const uint32_t cst = nx.nStride[l - 1];
-            for (uint32_t j = 0; j < nx.nNodes[l]; ++j)
-                for (int c = 0; c < D; ++c) {
-                    S mn = inf, mx = -inf;
-                    for (uint32_t i = j * 32; i < j * 32 + 32 && i < nx.nNodes[l - 1]; ++i) {
-                        mn = clo[(size_t)c * cst + i] < mn ? clo[(size_t)c * cst + i] : mn;
-                        mx = chi[(size_t)c * cst + i] > mx ? chi[(size_t)c * cst + i] : mx;
-                    }
-                    lo[(size_t)c * st + j] = mn;
-                    hi[(size_t)c * st + j] = mx;
-                }
-        }
+            }
     }
     // 4. upload (reuse the block when it is large enough)
     void* mem = ix.mem;
@@ -484,12 +509,9 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     nx.memBytes = memBytes;
     nx.devStats = stats;
     nx.builds = ix.builds + 1;
-    nx.spts = (char*)mem + oPts;
+    nx.leafPts = (char*)mem + oPts;
     nx.perm = (uint32_t*)((char*)mem + oPerm);
-    for (int l = 0; l <= nx.top; ++l) {
-        nx.lo[l] = (char*)mem + oLo[l];
-        nx.hi[l] = (char*)mem + oHi[l];
-    }
+    for (int l = 0; l <= nx.top; ++l) nx.box[l] = (char*)mem + oBox[l];
     ix = nx;
     return MPTG_OK;
 }
@@ -518,14 +540,11 @@ int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const
                 double radius, uint32_t idxMul, uint32_t idxAdd, uint32_t* idxOut, S* distOut, uint32_t* countOut,
                 uint64_t* /*hostStats*/) {
     BvhArgs<S> a{};
-    a.spts = (const S*)ix.spts;
-    a.nPad = ix.nPad;
+    a.leafPts = (const S*)ix.leafPts;
     a.perm = ix.perm;
     for (int l = 0; l < BVH_MAXL; ++l) {
-        a.lo[l] = (const S*)ix.lo[l];
-        a.hi[l] = (const S*)ix.hi[l];
+        a.box[l] = (const S*)ix.box[l];
         a.nNodes[l] = ix.nNodes[l];
-        a.nStride[l] = ix.nStride[l];
     }
     a.top = ix.top;
     a.queries = queries;
