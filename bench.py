@@ -121,6 +121,7 @@ def run_reference(args):
     from tests import oracle_binding
 
     orc = oracle_binding.load()
+    orc.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     tree, queries, robot, env, step, ea, eb = workload(0)
     sp = m.se3_space(SO3_W, L2_W)
     t0 = time.perf_counter()
@@ -152,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -310,7 +311,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -342,6 +343,7 @@ def cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb):
     from tests import oracle_binding
 
     orc = oracle_binding.load()
+    orc.set_threads(os.cpu_count() or 1)
     otree = orc.tree(sp, tree)
     omesh = orc.mesh_pair(robot, env, sp, step)
     qs, es = args.cpu_queries, args.cpu_edges
@@ -399,7 +401,21 @@ def bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank):
             "tree_nodes_per_gpu": N_TREE // world}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    # Libraries (NCCL prints its version banner) must not pollute stdout: everything but the JSON line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
