@@ -50,12 +50,13 @@ struct MeshData {
 namespace mptg {
 
 constexpr int MESH_WARPS = 4;
-constexpr int NODE_STACK = 1024;
+constexpr int MESH_MIN_CTAS = 8;  // 32 warps per SM: caps registers at 64
+constexpr int NODE_STACK = 512;
 constexpr int TRI_QUEUE = 64;
 constexpr int DMV_QUEUE = 256;  // fixedBisectQueueSize_, discrete_motion_validator.hpp:54
 
 struct WarpCounters {
-    unsigned long long bv = 0, tri = 0, states = 0;
+    unsigned int bv = 0, tri = 0, states = 0;  // per lane (bv, tri) / per warp (states); summed into 64-bit totals at exit
 };
 
 // Eigen quaternion -> rotation matrix operation order (same as the oracle)
@@ -101,7 +102,7 @@ __device__ __forceinline__ bool project6(const float ax[3], const float p[3][3],
 }
 
 // 17-axis SAT (PQP TriContact / FCL Intersect::intersect_Triangle scheme), coordinates relative to P[0]
-__device__ bool triTriIntersect(const float P[3][3], const float Qt[3][3]) {
+__device__ __noinline__ bool triTriIntersect(const float P[3][3], const float Qt[3][3]) {
     float p[3][3], q[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -159,16 +160,13 @@ __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
 __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3], uint2* stack, uint2* triQ, int lane,
                             WarpCounters& cnt, unsigned long long& err) {
     if (m.nR == 0 || m.nE == 0) return false;
-    float aR[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) aR[i] = fabsf(R[i]);
     int n = 1, nt = 0;
     if (lane == 0) stack[0] = make_uint2(0u, 0u);
     __syncwarp();
     const unsigned ltMask = (1u << lane) - 1u;
     while (n > 0 || nt > 0) {
         if (n > 0) {
-            const int p = (n > NODE_STACK - 128) ? 1 : (n < 32 ? n : 32);
+            const int p = (n > NODE_STACK - 160) ? 1 : (n < 32 ? n : 32);
             const bool mine = lane < p;
             uint2 pr = make_uint2(0u, 0u);
             if (mine) pr = stack[n - 1 - lane];
@@ -189,7 +187,7 @@ __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3]
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     cw[r] = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, t[r])));
-                    hw[r] = __fmaf_rn(aR[3 * r + 2], hz, __fmaf_rn(aR[3 * r + 1], hy, aR[3 * r] * hx));
+                    hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
                     mag += fabsf(cw[r]) + hw[r];
                 }
                 const float pad = 64.0f * 1.1920928955078125e-07f * mag;
@@ -287,20 +285,21 @@ __device__ __forceinline__ uint32_t fetchItem(unsigned int* counter, int lane) {
 }
 
 __device__ __forceinline__ void flushCounters(WarpCounters& c, unsigned long long err, unsigned long long* stats, int lane) {
+    unsigned long long bv = c.bv, tri = c.tri;
     for (int o = 16; o > 0; o >>= 1) {
-        c.bv += __shfl_down_sync(FULL_MASK_, c.bv, o);
-        c.tri += __shfl_down_sync(FULL_MASK_, c.tri, o);
+        bv += __shfl_down_sync(FULL_MASK_, bv, o);
+        tri += __shfl_down_sync(FULL_MASK_, tri, o);
     }
     if (lane == 0) {
-        atomicAdd(stats + 0, c.states);
-        atomicAdd(stats + 1, c.bv);
-        atomicAdd(stats + 2, c.tri);
+        atomicAdd(stats + 0, (unsigned long long)c.states);
+        atomicAdd(stats + 1, bv);
+        atomicAdd(stats + 2, tri);
         if (err) atomicOr(stats + 4, err);
     }
 }
 
 // ------------------------------------------------------------------ valid(q) for a batch of states
-__global__ void __launch_bounds__(MESH_WARPS * 32) meshValidKernel(MeshDev m, const float* __restrict__ states, uint32_t n,
+__global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshValidKernel(MeshDev m, const float* __restrict__ states, uint32_t n,
                                                                    uint8_t* __restrict__ ok, unsigned int* counter,
                                                                    unsigned long long* stats) {
     __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
@@ -324,78 +323,93 @@ __global__ void __launch_bounds__(MESH_WARPS * 32) meshValidKernel(MeshDev m, co
 }
 
 // ------------------------------------------------------------------ link(a,b): DiscreteMotionValidator
-// src/mpt/discrete_motion_validator.hpp:71-130, one warp per edge, states in the reference's order.
-__global__ void __launch_bounds__(MESH_WARPS * 32) meshLinkKernel(MeshDev m, DevSpace<float> sp, const float* __restrict__ from,
+// src/mpt/discrete_motion_validator.hpp:71-130, one warp per edge, states in the reference's order
+// (valid(to) first, then the breadth-first bisection of 1..steps-1 through the 256-entry ring with
+// its sequential fallback), stopping at the first state in collision.  The loop is arranged as a
+// generator of state indices so that the collision routine is expanded once.
+__global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel(MeshDev m, DevSpace<float> sp, const float* __restrict__ from,
                                                                   const float* __restrict__ to, uint32_t n, float invStep,
                                                                   uint8_t* __restrict__ ok, unsigned int* counter,
                                                                   unsigned long long* stats) {
     __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
     __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
     __shared__ uint2 sQueue[MESH_WARPS][DMV_QUEUE];
+    __shared__ float sEnds[MESH_WARPS][16];  // from[7], to[7]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpCounters cnt;
     unsigned long long err = 0;
     uint2* queue = sQueue[warp];
+    float* ends = sEnds[warp];
     for (;;) {
         const uint32_t e = fetchItem(counter, lane);
         if (e >= n) break;
-        float a[7], b[7], q[7], R[9];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            a[c] = __ldg(from + (size_t)e * 7 + c);
-            b[c] = __ldg(to + (size_t)e * 7 + c);
-        }
+        __syncwarp();
+        if (lane < 7) ends[lane] = __ldg(from + (size_t)e * 7 + lane);
+        else if (lane < 14) ends[lane] = __ldg(to + (size_t)e * 7 + (lane - 7));
+        __syncwarp();
         bool good = true;
-        // :75  valid(to)
-        quatToRot(b, R);
-        ++cnt.states;
-        if (warpCollide(m, R, b + 4, sStack[warp], sTri[warp], lane, cnt, err)) good = false;
-        if (good) {
-            // :78  steps = ceil(distance(from,to) * invStepSize)
-            const float dist = dev::distance<float>(sp, [&](int c) { return a[c]; }, [&](int c) { return b[c]; });
-            const float fs = ceilf(dist * invStep);
-            if (!(fs < 2147483648.0f)) {
-                err |= GEOM_ERR_STEPS;
-                good = false;
+        bool first = true;
+        float delta = 0.0f;
+        uint32_t qStart = 0, qEnd = 0, seqCur = 1, seqEnd = 0;
+        for (;;) {
+            float q[7];
+            if (first) {  // :75  valid(to)
+#pragma unroll
+                for (int c = 0; c < 7; ++c) q[c] = ends[7 + c];
             } else {
-                const uint32_t steps = (uint32_t)fs;
-                if (steps >= 2) {
-                    const float delta = fp::div_(1.0f, (float)steps);  // :82
-                    auto check = [&](uint32_t i) {
-                        dev::interpolate<float>(sp, a, b, (float)i * delta, q);
-                        quatToRot(q, R);
-                        ++cnt.states;
-                        return !warpCollide(m, R, q + 4, sStack[warp], sTri[warp], lane, cnt, err);
-                    };
-                    // :102-127  breadth-first bisection with a 256-entry ring, sequential when full
-                    uint32_t qStart = 0, qEnd = 1;
-                    if (lane == 0) queue[0] = make_uint2(1u, steps - 1u);
+                uint32_t i;
+                if (seqCur <= seqEnd) {  // :119-126 sequential fallback in progress
+                    i = seqCur++;
+                } else {
+                    if (qStart == qEnd) break;
+                    const uint2 r = queue[qStart % DMV_QUEUE];
+                    ++qStart;
                     __syncwarp();
-                    while (good && qStart != qEnd) {
-                        const uint2 r = queue[qStart % DMV_QUEUE];
-                        ++qStart;
-                        __syncwarp();
-                        if (r.x == r.y) {
-                            good = check(r.x);
-                        } else if (qEnd + 2 < qStart + DMV_QUEUE) {
-                            const uint32_t mid = (r.x + r.y) / 2;
-                            good = check(mid);
-                            if (good) {
-                                if (r.x < mid) {
-                                    if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(r.x, mid - 1);
-                                    ++qEnd;
-                                }
-                                if (mid < r.y) {
-                                    if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(mid + 1, r.y);
-                                    ++qEnd;
-                                }
-                                __syncwarp();
-                            }
-                        } else {
-                            for (uint32_t i = r.x; good && i <= r.y; ++i) good = check(i);
+                    if (r.x == r.y) {  // :104-106
+                        i = r.x;
+                    } else if (qEnd + 2 < qStart + DMV_QUEUE) {  // :107-114 (children are queued before the
+                        i = (r.x + r.y) / 2;                      //  check; harmless, a failed check ends the edge)
+                        if (r.x < i) {
+                            if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(r.x, i - 1);
+                            ++qEnd;
                         }
+                        if (i < r.y) {
+                            if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(i + 1, r.y);
+                            ++qEnd;
+                        }
+                        __syncwarp();
+                    } else {
+                        seqCur = r.x;
+                        seqEnd = r.y;
+                        continue;
                     }
                 }
+                dev::interpolate<float>(sp, ends, ends + 7, (float)i * delta, q);
+            }
+            float R[9];
+            quatToRot(q, R);
+            ++cnt.states;
+            if (warpCollide(m, R, q + 4, sStack[warp], sTri[warp], lane, cnt, err)) {
+                good = false;
+                break;
+            }
+            if (first) {
+                first = false;
+                // :78  steps = ceil(distance(from,to) * invStepSize)
+                const float dist = dev::distance<float>(sp, [&](int c) { return ends[c]; }, [&](int c) { return ends[7 + c]; });
+                const float fs = ceilf(dist * invStep);
+                if (!(fs < 2147483648.0f)) {
+                    err |= GEOM_ERR_STEPS;
+                    good = false;
+                    break;
+                }
+                const uint32_t steps = (uint32_t)fs;
+                if (steps < 2) break;  // :79
+                delta = fp::div_(1.0f, (float)steps);  // :82
+                if (lane == 0) queue[0] = make_uint2(1u, steps - 1u);
+                qStart = 0;
+                qEnd = 1;
+                __syncwarp();
             }
         }
         if (lane == 0) ok[e] = good ? 1 : 0;
@@ -478,7 +492,7 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
 
 int meshGrid(mptg_ctx* ctx, uint32_t n) {
     const uint32_t want = (n + MESH_WARPS - 1) / MESH_WARPS;
-    const uint32_t cap = (uint32_t)ctx->smCount * 6;  // ~34 KB shared memory per CTA -> 6 CTAs per SM
+    const uint32_t cap = (uint32_t)ctx->smCount * MESH_MIN_CTAS;  // persistent grid: every resident slot gets a CTA
     return (int)(want < cap ? (want ? want : 1) : cap);
 }
 
