@@ -155,28 +155,42 @@ __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
     return n;
 }
 
-// Collision test of one rigid-body state by a full warp.  Returns true on collision.
+// Collision test of up to MESH_SLOTS rigid-body states at once by a full warp.  The states' transforms
+// (R row-major 9 floats, t 3 floats) sit in shared memory, xf[slot][12]; every stack / queue entry
+// carries its slot in the top 4 bits of the robot index, so the 32 lanes always draw from one mixed
+// frontier and stay busy while a single state's frontier is still narrow.  Returns the mask of slots
+// found in collision; with stopAtFirst it returns as soon as any slot collides (edge checks: one
+// invalid state invalidates the edge).
 // err: set to GEOM_ERR_STACK if the pair stack would overflow.
-__device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3], uint2* stack, uint2* triQ, int lane,
-                            WarpCounters& cnt, unsigned long long& err) {
-    if (m.nR == 0 || m.nE == 0) return false;
-    int n = 1, nt = 0;
-    if (lane == 0) stack[0] = make_uint2(0u, 0u);
+constexpr int MESH_SLOTS = 8;
+constexpr unsigned SLOT_SHIFT = 28;
+constexpr unsigned NODE_MASK = (1u << SLOT_SHIFT) - 1u;
+
+__device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (*xf)[12], uint2* stack, uint2* triQ, int lane,
+                                     bool stopAtFirst, WarpCounters& cnt, unsigned long long& err) {
+    if (m.nR == 0 || m.nE == 0 || nSlots == 0) return 0u;
+    const unsigned allMask = (1u << nSlots) - 1u;
+    unsigned hitMask = 0u;
+    int n = nSlots, nt = 0;
+    if (lane < nSlots) stack[lane] = make_uint2((unsigned)lane << SLOT_SHIFT, 0u);
     __syncwarp();
     const unsigned ltMask = (1u << lane) - 1u;
     while (n > 0 || nt > 0) {
         if (n > 0) {
             const int p = (n > NODE_STACK - 160) ? 1 : (n < 32 ? n : 32);
-            const bool mine = lane < p;
+            bool mine = lane < p;
             uint2 pr = make_uint2(0u, 0u);
             if (mine) pr = stack[n - 1 - lane];
             __syncwarp();
             n -= p;
+            const unsigned slot = pr.x >> SLOT_SHIFT;
+            mine = mine && !((hitMask >> slot) & 1u);  // pairs of a state already known to collide are dropped
             int kind = 0;  // 1: triangle pair, 2: expand robot node, 3: expand env node
             int c0 = 0, c1 = 0;
             if (mine) {
-                const BvhNode a = loadNode(m.rNodes, (int)pr.x);
+                const BvhNode a = loadNode(m.rNodes, (int)(pr.x & NODE_MASK));
                 const BvhNode b = loadNode(m.eNodes, (int)pr.y);
+                const float* X = xf[slot];
                 ++cnt.bv;
                 // world AABB of the rotated local box: centre +- |R| h, padded
                 const float cx = 0.5f * (a.lo[0] + a.hi[0]), cy = 0.5f * (a.lo[1] + a.hi[1]), cz = 0.5f * (a.lo[2] + a.hi[2]);
@@ -186,8 +200,9 @@ __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3]
                 float cw[3], hw[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    cw[r] = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, t[r])));
-                    hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
+                    const float r0 = X[3 * r], r1 = X[3 * r + 1], r2 = X[3 * r + 2];
+                    cw[r] = __fmaf_rn(r2, cz, __fmaf_rn(r1, cy, __fmaf_rn(r0, cx, X[9 + r])));
+                    hw[r] = __fmaf_rn(fabsf(r2), hz, __fmaf_rn(fabsf(r1), hy, fabsf(r0) * hx));
                     mag += fabsf(cw[r]) + hw[r];
                 }
                 const float pad = 64.0f * 1.1920928955078125e-07f * mag;
@@ -223,14 +238,15 @@ __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3]
                     }
                 }
             }
+            const unsigned tag = slot << SLOT_SHIFT;
             const unsigned mt = __ballot_sync(FULL_MASK_, kind == 1);
             const unsigned mx = __ballot_sync(FULL_MASK_, kind >= 2);
-            if (kind == 1) triQ[nt + __popc(mt & ltMask)] = make_uint2((unsigned)c0, (unsigned)c1);
+            if (kind == 1) triQ[nt + __popc(mt & ltMask)] = make_uint2((unsigned)c0 | tag, (unsigned)c1);
             if (kind >= 2) {
                 const int o = n + 2 * __popc(mx & ltMask);
                 if (kind == 2) {
-                    stack[o] = make_uint2((unsigned)c0, pr.y);
-                    stack[o + 1] = make_uint2((unsigned)c1, pr.y);
+                    stack[o] = make_uint2((unsigned)c0 | tag, pr.y);
+                    stack[o + 1] = make_uint2((unsigned)c1 | tag, pr.y);
                 } else {
                     stack[o] = make_uint2(pr.x, (unsigned)c0);
                     stack[o + 1] = make_uint2(pr.x, (unsigned)c1);
@@ -240,18 +256,27 @@ __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3]
             n += 2 * __popc(mx);
             if (n > NODE_STACK - 64) {  // cannot happen with the throttle above unless trees are > ~60 deep
                 err |= GEOM_ERR_STACK;
-                return true;
+                return allMask;
             }
             __syncwarp();
         }
         if (nt >= 32 || (n == 0 && nt > 0)) {
             const int p = nt < 32 ? nt : 32;
-            const bool mine = lane < p;
-            bool hit = false;
+            bool mine = lane < p;
+            unsigned hitBit = 0u;
+            uint2 tp = make_uint2(0u, 0u);
+            if (mine) tp = triQ[nt - 1 - lane];
+            const unsigned slot = tp.x >> SLOT_SHIFT;
+            mine = mine && !((hitMask >> slot) & 1u);
             if (mine) {
-                const uint2 tp = triQ[nt - 1 - lane];
                 ++cnt.tri;
-                const float4* rp = reinterpret_cast<const float4*>(m.rTris + tp.x);
+                const float* X = xf[slot];
+                float R[9], t[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = X[k];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) t[k] = X[9 + k];
+                const float4* rp = reinterpret_cast<const float4*>(m.rTris + (tp.x & NODE_MASK));
                 const float4* ep = reinterpret_cast<const float4*>(m.eTris + tp.y);
                 float P[3][3], Q[3][3];
 #pragma unroll
@@ -268,19 +293,20 @@ __device__ bool warpCollide(const MeshDev& m, const float R[9], const float t[3]
                     const float qlo = fminf(Q[0][c], fminf(Q[1][c], Q[2][c])), qhi = fmaxf(Q[0][c], fmaxf(Q[1][c], Q[2][c]));
                     ov = ov && !(plo > qhi || qlo > phi);
                 }
-                hit = ov && triTriIntersect(P, Q);
+                if (ov && triTriIntersect(P, Q)) hitBit = 1u << slot;
             }
             __syncwarp();
             nt -= p;
-            if (__any_sync(FULL_MASK_, hit)) return true;
+            hitMask |= __reduce_or_sync(FULL_MASK_, hitBit);
+            if (hitMask && (stopAtFirst || hitMask == allMask)) return hitMask;
         }
     }
-    return false;
+    return hitMask;
 }
 
-__device__ __forceinline__ uint32_t fetchItem(unsigned int* counter, int lane) {
+__device__ __forceinline__ uint32_t fetchItems(unsigned int* counter, uint32_t count, int lane) {
     uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(counter, 1u);
+    if (lane == 0) i = atomicAdd(counter, count);
     return __shfl_sync(FULL_MASK_, i, 0);
 }
 
@@ -298,35 +324,51 @@ __device__ __forceinline__ void flushCounters(WarpCounters& c, unsigned long lon
     }
 }
 
+// state -> transform in shared memory (lane-private work: one lane per slot)
+__device__ __forceinline__ void storeTransform(const float* q, float* X) {
+    float R[9];
+    quatToRot(q, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) X[k] = R[k];
+    X[9] = q[4], X[10] = q[5], X[11] = q[6];
+}
+
 // ------------------------------------------------------------------ valid(q) for a batch of states
 __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshValidKernel(MeshDev m, const float* __restrict__ states, uint32_t n,
                                                                    uint8_t* __restrict__ ok, unsigned int* counter,
                                                                    unsigned long long* stats) {
     __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
     __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
+    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpCounters cnt;
     unsigned long long err = 0;
     for (;;) {
-        const uint32_t i = fetchItem(counter, lane);
-        if (i >= n) break;
-        float q[7];
+        const uint32_t i0 = fetchItems(counter, MESH_SLOTS, lane);
+        if (i0 >= n) break;
+        const int nb = (int)min((uint32_t)MESH_SLOTS, n - i0);
+        __syncwarp();
+        if (lane < nb) {
+            float q[7];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) q[c] = __ldg(states + (size_t)i * 7 + c);
-        float R[9];
-        quatToRot(q, R);
-        ++cnt.states;
-        const bool hit = warpCollide(m, R, q + 4, sStack[warp], sTri[warp], lane, cnt, err);
-        if (lane == 0) ok[i] = hit ? 0 : 1;
+            for (int c = 0; c < 7; ++c) q[c] = __ldg(states + (size_t)(i0 + lane) * 7 + c);
+            storeTransform(q, sXf[warp][lane]);
+        }
+        __syncwarp();
+        cnt.states += nb;
+        const unsigned hit = warpCollideMulti(m, nb, sXf[warp], sStack[warp], sTri[warp], lane, false, cnt, err);
+        if (lane < nb) ok[i0 + lane] = ((hit >> lane) & 1u) ? 0 : 1;
     }
     flushCounters(cnt, err, stats, lane);
 }
 
 // ------------------------------------------------------------------ link(a,b): DiscreteMotionValidator
-// src/mpt/discrete_motion_validator.hpp:71-130, one warp per edge, states in the reference's order
-// (valid(to) first, then the breadth-first bisection of 1..steps-1 through the 256-entry ring with
-// its sequential fallback), stopping at the first state in collision.  The loop is arranged as a
-// generator of state indices so that the collision routine is expanded once.
+// src/mpt/discrete_motion_validator.hpp:71-130, one warp per edge.  State indices are produced in the
+// reference's order (valid(to) first, then the breadth-first bisection of 1..steps-1 through the
+// 256-entry ring with its sequential fallback; children are queued before the check, which is
+// harmless because a failed check ends the edge) and checked MESH_SLOTS at a time; the edge is
+// invalid as soon as any of them collides.  The decision is the reference's AND over the same set of
+// states; up to MESH_SLOTS-1 more states than the reference's sequential early exit may be touched.
 __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel(MeshDev m, DevSpace<float> sp, const float* __restrict__ from,
                                                                   const float* __restrict__ to, uint32_t n, float invStep,
                                                                   uint8_t* __restrict__ ok, unsigned int* counter,
@@ -335,30 +377,47 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel
     __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
     __shared__ uint2 sQueue[MESH_WARPS][DMV_QUEUE];
     __shared__ float sEnds[MESH_WARPS][16];  // from[7], to[7]
+    __shared__ uint32_t sIdx[MESH_WARPS][MESH_SLOTS];
+    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t IDX_TO = 0xFFFFFFFFu;
     WarpCounters cnt;
     unsigned long long err = 0;
     uint2* queue = sQueue[warp];
     float* ends = sEnds[warp];
     for (;;) {
-        const uint32_t e = fetchItem(counter, lane);
+        const uint32_t e = fetchItems(counter, 1u, lane);
         if (e >= n) break;
         __syncwarp();
         if (lane < 7) ends[lane] = __ldg(from + (size_t)e * 7 + lane);
         else if (lane < 14) ends[lane] = __ldg(to + (size_t)e * 7 + (lane - 7));
         __syncwarp();
+        // :78  steps = ceil(distance(from,to) * invStepSize)
+        const float dist = dev::distance<float>(sp, [&](int c) { return ends[c]; }, [&](int c) { return ends[7 + c]; });
+        const float fs = ceilf(dist * invStep);
         bool good = true;
-        bool first = true;
-        float delta = 0.0f;
+        if (!(fs < 2147483648.0f)) {
+            err |= GEOM_ERR_STEPS;
+            good = false;
+        }
+        const uint32_t steps = good ? (uint32_t)fs : 0u;
+        const float delta = steps >= 2 ? fp::div_(1.0f, (float)steps) : 0.0f;  // :82
         uint32_t qStart = 0, qEnd = 0, seqCur = 1, seqEnd = 0;
-        for (;;) {
-            float q[7];
-            if (first) {  // :75  valid(to)
-#pragma unroll
-                for (int c = 0; c < 7; ++c) q[c] = ends[7 + c];
-            } else {
+        if (steps >= 2) {  // :79,:99-101
+            if (lane == 0) queue[0] = make_uint2(1u, steps - 1u);
+            qEnd = 1;
+        }
+        bool first = true;
+        __syncwarp();
+        while (good) {
+            // next batch of state indices, in the reference's order
+            int nb = 0;
+            while (nb < MESH_SLOTS) {
                 uint32_t i;
-                if (seqCur <= seqEnd) {  // :119-126 sequential fallback in progress
+                if (first) {  // :75  valid(to)
+                    first = false;
+                    i = IDX_TO;
+                } else if (seqCur <= seqEnd) {  // :119-126 sequential fallback in progress
                     i = seqCur++;
                 } else {
                     if (qStart == qEnd) break;
@@ -367,8 +426,8 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel
                     __syncwarp();
                     if (r.x == r.y) {  // :104-106
                         i = r.x;
-                    } else if (qEnd + 2 < qStart + DMV_QUEUE) {  // :107-114 (children are queued before the
-                        i = (r.x + r.y) / 2;                      //  check; harmless, a failed check ends the edge)
+                    } else if (qEnd + 2 < qStart + DMV_QUEUE) {  // :107-114
+                        i = (r.x + r.y) / 2;
                         if (r.x < i) {
                             if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(r.x, i - 1);
                             ++qEnd;
@@ -384,33 +443,25 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel
                         continue;
                     }
                 }
-                dev::interpolate<float>(sp, ends, ends + 7, (float)i * delta, q);
+                if (lane == 0) sIdx[warp][nb] = i;
+                ++nb;
             }
-            float R[9];
-            quatToRot(q, R);
-            ++cnt.states;
-            if (warpCollide(m, R, q + 4, sStack[warp], sTri[warp], lane, cnt, err)) {
-                good = false;
-                break;
-            }
-            if (first) {
-                first = false;
-                // :78  steps = ceil(distance(from,to) * invStepSize)
-                const float dist = dev::distance<float>(sp, [&](int c) { return ends[c]; }, [&](int c) { return ends[7 + c]; });
-                const float fs = ceilf(dist * invStep);
-                if (!(fs < 2147483648.0f)) {
-                    err |= GEOM_ERR_STEPS;
-                    good = false;
-                    break;
+            if (nb == 0) break;
+            __syncwarp();
+            if (lane < nb) {  // one lane per state: interpolate and build its transform
+                const uint32_t i = sIdx[warp][lane];
+                float q[7];
+                if (i == IDX_TO) {
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) q[c] = ends[7 + c];
+                } else {
+                    dev::interpolate<float>(sp, ends, ends + 7, (float)i * delta, q);
                 }
-                const uint32_t steps = (uint32_t)fs;
-                if (steps < 2) break;  // :79
-                delta = fp::div_(1.0f, (float)steps);  // :82
-                if (lane == 0) queue[0] = make_uint2(1u, steps - 1u);
-                qStart = 0;
-                qEnd = 1;
-                __syncwarp();
+                storeTransform(q, sXf[warp][lane]);
             }
+            __syncwarp();
+            cnt.states += nb;
+            if (warpCollideMulti(m, nb, sXf[warp], sStack[warp], sTri[warp], lane, true, cnt, err)) good = false;
         }
         if (lane == 0) ok[e] = good ? 1 : 0;
     }

@@ -364,9 +364,11 @@ def test_mesh_link_matches_oracle(ctx, oracle):
         diff = got != want
         print(f"mesh link {max_trans}/{max_angle}: {want.mean():.3f} valid, {int(near.sum())} near-contact edges, {int(diff.sum())} differ")
         assert not (diff & (near == 0)).any()
-        # the reference's early exit: same number of states checked as the sequential validator
+        # the reference's order and early exit: states are checked eight at a time in the reference's order, so
+        # at most seven more states per invalid edge than the sequential validator, never fewer
         if not diff.any():
-            assert sc.last_stats()["states"] == og.last_states
+            got_states = sc.last_stats()["states"]
+            assert og.last_states <= got_states <= og.last_states + 7 * int((want == 0).sum())
 
 
 def test_mesh_golden_and_degenerate(ctx):
