@@ -264,6 +264,8 @@ def run_ours(args):
     assert np.array_equal(d_idx.cpu().numpy(), h_idx.numpy()), "device-pointer and host-pointer kNN results differ"
 
     extra = {}
+    if rank == 0 and not args.no_secondary:
+        extra["secondary"] = secondary(ctx, torch, dev, stream)
     if world > 1:
         extra["sharded_tree"] = bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank)
 
@@ -314,6 +316,67 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary(ctx, torch, dev, stream):
+    """The other back-ends of the path (C1, C2, C4), device-resident inputs, rank 0 only,
+    outside the main timed region.  Reported for coverage; `value` stays the C5 kNN figure."""
+    import mpt_b200 as m
+    from mpt_b200 import workloads as W
+
+    out = {}
+
+    def time_link(sc, a, b, reps=5):
+        da, db = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+        ok = torch.empty(a.shape[0], dtype=torch.uint8, device=dev)
+        ts = []
+        for it in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                sc.link_dev(da.data_ptr(), db.data_ptr(), a.shape[0], ok.data_ptr())
+                e1.record(stream)
+            ctx.sync()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        st = sc.last_stats()
+        ms = float(np.mean(ts))
+        return {"edges_per_s": a.shape[0] / (ms * 1e-3), "ms": ms, "probes_per_s": st["prim_tests"] / (ms * 1e-3) if st["prim_tests"] else None,
+                "valid_fraction": float(ok.float().mean().item())}
+
+    occ = W.synthetic_grid()  # 3976 x 2603, the shipped PNG's size
+    grid = m.Scenario.grid(ctx, occ, m.F64)
+    for name, max_len in (("grid_edges_range64", 64.0), ("grid_edges_unbounded", None)):
+        a, b = W.grid_edges(E_WAVE, occ.shape[1], occ.shape[0], 31, max_len)
+        out[name] = time_link(grid, a, b)
+    for n_links in (8, 16, 32):
+        lengths, radius, circles = W.link_arm_scene(n_links)
+        arm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
+        a, b = W.arm_edges(E_WAVE, n_links, 41, 0.5)
+        out[f"link_arm_{n_links}_edges"] = time_link(arm, a, b)
+    # planar L2 kNN at a planner-realistic size (tiled scan) and at 1M (tree)
+    for n_pts, label in ((1 << 14, "knn_l2_2d_16k_brute"), (1 << 20, "knn_l2_2d_1m_tree")):
+        sp = m.lp_space(2, 2, m.F32)
+        pts = W.box_states(n_pts, 2, 51, 0.0, [3976, 2603], np.float32)
+        q = W.box_states(Q_WAVE, 2, 52, 0.0, [3976, 2603], np.float32)
+        nn = m.Nearest(ctx, sp, n_pts)
+        nn.insert(pts)
+        dq = torch.from_numpy(q).to(dev)
+        di = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
+        dd = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+        ts = []
+        for it in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                nn.nearest_dev(dq.data_ptr(), Q_WAVE, K_NN, -1.0, di.data_ptr(), dd.data_ptr())
+                e1.record(stream)
+            ctx.sync()
+            if it >= 2:
+                ts.append(e0.elapsed_time(e1))
+        out[label] = {"queries_per_s": Q_WAVE / (float(np.mean(ts)) * 1e-3), "ms": float(np.mean(ts))}
+        nn.close()
+    return out
 
 
 def fp32_probe(torch, dev):
@@ -424,6 +487,7 @@ def main():
     ap.add_argument("--cpu-queries", type=int, default=8192, help="CPU-baseline sample: queries per step")
     ap.add_argument("--cpu-edges", type=int, default=4096, help="CPU-baseline sample: edges per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the grid / link-arm / planar-kNN side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
