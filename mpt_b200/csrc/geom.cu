@@ -5,10 +5,10 @@
 // (demo/png_2d_scenario.hpp:152-165, demo/shape_hierarchy.hpp:191-203,
 // demo/link_manipulator_scenario.hpp:125-138).  The recursion tree depends only on the floating
 // point endpoints (mid = (a+b)/2, stop test on the CURRENT pair), and the answer is the AND over
-// every midpoint in that tree, so visiting order is free.  One warp takes one edge: lane L walks
-// the five top levels along the path given by its bits (re-probing the shared midpoints) and then
-// runs the rest of its subtree depth first with an explicit stack; a warp vote per iteration stops
-// all lanes at the first invalid probe.  All midpoints are produced by the same sequence of
+// every midpoint in that tree, so visiting order is free.  One warp takes one edge: the 31 midpoints
+// of the five top levels are probed one per lane in a single parallel step, then lane L runs subtree
+// L (rooted at depth five) depth first with an explicit stack; a warp vote per iteration stops all
+// lanes at the first invalid probe.  All midpoints are produced by the same sequence of
 // floating point operations as the reference's recursion, so decisions are bit-identical.
 #include "geom.cuh"
 
@@ -137,24 +137,50 @@ __global__ void __launch_bounds__(256) bisectLinkKernel(const V v, const S* __re
             a[i] = from[(size_t)e * D + i];
             b[i] = to[(size_t)e * D + i];
         }
-        // endpoints (all lanes compute the same thing; lane 0's answer is used)
-        bool good = v.endpointsValid(a, b);
-        good = __shfl_sync(FULL_MASK_, good, 0);
-        bool done = !good;
-        // top levels: follow this lane's path
-        if (!done) {
-            for (int level = 0; level < SPLIT_LEVELS; ++level) {
+        // endpoints: lanes 0-15 probe a, lanes 16-31 probe b (one probe latency instead of two)
+        for (int i = 0; i < D; ++i) mid[i] = lane < 16 ? a[i] : b[i];
+        bool good = __all_sync(FULL_MASK_, v.valid(mid));
+        // Phase A -- the 31 midpoints of the five top levels, ONE per lane: lane j owns heap node j+1
+        // (depth floor(log2(j+1))), walks down to it computing midpoints only, and probes just that
+        // node.  A node exists iff none of its ancestors met the stop test.
+        if (good) {
+            const int h = lane + 1;
+            const int d = 31 - __clz(h);  // lane 31 (h = 32) has no node in this phase
+            bool exists = lane < 31;
+            for (int level = 0; level < d && exists; ++level) {
                 if (v.stop(a, b)) {
-                    done = true;  // subtree ends here: nothing below to check
+                    exists = false;
                     break;
                 }
                 for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
+                if ((h >> (d - 1 - level)) & 1) {
+                    for (int i = 0; i < D; ++i) a[i] = mid[i];
+                } else {
+                    for (int i = 0; i < D; ++i) b[i] = mid[i];
+                }
+            }
+            bool mineOk = true;
+            if (exists && !v.stop(a, b)) {
+                for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
                 ++probes;
-                if (!v.valid(mid)) {
-                    good = false;
-                    done = true;
+                mineOk = v.valid(mid);
+            }
+            good = __all_sync(FULL_MASK_, mineOk);
+        }
+        // Phase B -- lane L descends (midpoints only, they were probed in phase A) to the root of
+        // subtree L at depth five and then runs that subtree depth first.
+        bool done = !good;
+        if (!done) {
+            for (int i = 0; i < D; ++i) {
+                a[i] = from[(size_t)e * D + i];
+                b[i] = to[(size_t)e * D + i];
+            }
+            for (int level = 0; level < SPLIT_LEVELS; ++level) {
+                if (v.stop(a, b)) {
+                    done = true;  // the tree ends above depth five on this path: nothing below to check
                     break;
                 }
+                for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
                 if ((lane >> (SPLIT_LEVELS - 1 - level)) & 1) {
                     for (int i = 0; i < D; ++i) a[i] = mid[i];
                 } else {
