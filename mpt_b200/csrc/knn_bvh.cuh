@@ -20,6 +20,8 @@
 // Results are therefore identical to the brute-force scan, including the (distance, index) ties.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <numeric>
 
@@ -42,6 +44,10 @@ struct KnnIndex {
     void* leafPts = nullptr;  // [leaf][D][32]
     uint32_t* perm = nullptr;
     void* box[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][2D][32]
+    // SE(3)/f32 only: half-precision copies that feed the conservative prefilters (half the L2 traffic)
+    uint32_t* leafH = nullptr;                                                 // [leaf][4][32] half2: (qx,qy) (qz,qw) (tx,ty) (tz,0)
+    uint32_t* boxH[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][7][32] half2 (lo rounded down, hi rounded up)
+    float errQ = 0.f, errT = 0.f;  // max |half(v) - v| over the stored quaternion / translation coordinates
     unsigned long long* devStats = nullptr;  // [0] leaves visited, [1] inner nodes visited
     uint64_t builds = 0;
 };
@@ -131,9 +137,16 @@ struct BvhArgs {
     const S* leafPts;
     const uint32_t* perm;
     const S* box[BVH_MAXL];
+    const uint32_t* leafH;  // nullptr when the compressed copies are not available
+    const uint32_t* boxH[BVH_MAXL];
+    float errQ, errT;
     uint32_t nNodes[BVH_MAXL];
     int top;
     const S* queries;
+    const uint32_t* order;  // optional: processing order of the queries (spatially sorted), or nullptr
+    uint32_t* orderKeys;    // key pass only: leaf reached by greedy descent, per query
+    uint32_t* orderHist;    // key pass only: histogram over (leaf >> orderShift)
+    uint32_t orderShift;
     uint32_t Q, k;
     S radius;
     uint32_t idxMul, idxAdd;
@@ -189,6 +202,7 @@ struct BvhWalk {
     const S* myq;  // query in shared memory (generic path)
     S qr[7];       // query in registers (SE(3) path)
     float w0, w1;
+    float qabs;  // sum |q_i| of the query quaternion (error bound of dots against half-precision copies)
     WarpTopK<S, KPL> top;
     int lane;
     unsigned long long leaves = 0, inner = 0;
@@ -208,29 +222,55 @@ struct BvhWalk {
         const int D = a.sp.D;
         const S* b = a.box[L] + ((size_t)block * (size_t)(2 * D)) * 32u + lane;
         if (SHAPE == SHAPE_SE3 && sizeof(S) == 4) {
-            float dotHi, dotLo;
-            {
-                const float l = __ldg((const float*)b), h = __ldg((const float*)b + 7 * 32);
-                const float v = (float)qr[0];
-                dotHi = (v >= 0.0f ? h : l) * v;
-                dotLo = (v >= 0.0f ? l : h) * v;
-            }
+            float dotHi, dotLo, acc = 0.0f;
+            if (a.leafH) {  // boxes as half2 (lo rounded down, hi rounded up): 7 loads instead of 14
+                const uint32_t* bh = a.boxH[L] + ((size_t)block * 7u) * 32u + lane;
+                {
+                    const uint32_t raw = __ldg(bh);
+                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+                    const float v = (float)qr[0];
+                    dotHi = (v >= 0.0f ? lh.y : lh.x) * v;
+                    dotLo = (v >= 0.0f ? lh.x : lh.y) * v;
+                }
 #pragma unroll
-            for (int j = 1; j < 4; ++j) {
-                const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
-                const float v = (float)qr[j];
-                dotHi = __fmaf_rn(v >= 0.0f ? h : l, v, dotHi);
-                dotLo = __fmaf_rn(v >= 0.0f ? l : h, v, dotLo);
+                for (int j = 1; j < 4; ++j) {
+                    const uint32_t raw = __ldg(bh + j * 32);
+                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+                    const float v = (float)qr[j];
+                    dotHi = __fmaf_rn(v >= 0.0f ? lh.y : lh.x, v, dotHi);
+                    dotLo = __fmaf_rn(v >= 0.0f ? lh.x : lh.y, v, dotLo);
+                }
+#pragma unroll
+                for (int j = 4; j < 7; ++j) {
+                    const uint32_t raw = __ldg(bh + j * 32);
+                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+                    const float v = (float)qr[j];
+                    const float e = fmaxf(fmaxf(lh.x - v, v - lh.y), 0.0f);
+                    acc = __fmaf_rn(e, e, acc);
+                }
+            } else {
+                {
+                    const float l = __ldg((const float*)b), h = __ldg((const float*)b + 7 * 32);
+                    const float v = (float)qr[0];
+                    dotHi = (v >= 0.0f ? h : l) * v;
+                    dotLo = (v >= 0.0f ? l : h) * v;
+                }
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
+                    const float v = (float)qr[j];
+                    dotHi = __fmaf_rn(v >= 0.0f ? h : l, v, dotHi);
+                    dotLo = __fmaf_rn(v >= 0.0f ? l : h, v, dotLo);
+                }
+#pragma unroll
+                for (int j = 4; j < 7; ++j) {
+                    const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
+                    const float v = (float)qr[j];
+                    const float e = fmaxf(fmaxf(l - v, v - h), 0.0f);
+                    acc = __fmaf_rn(e, e, acc);
+                }
             }
             const float ad = fminf(1.0f, fmaxf(dotHi, -dotLo));
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 4; j < 7; ++j) {
-                const float l = __ldg((const float*)b + j * 32), h = __ldg((const float*)b + (7 + j) * 32);
-                const float v = (float)qr[j];
-                const float e = fmaxf(fmaxf(l - v, v - h), 0.0f);
-                acc = __fmaf_rn(e, e, acc);
-            }
             return __float_as_uint(se3CheapBound(ad, acc, w0, w1) + 0.0f);
         } else {
             const S lb = dev::boxLowerBound<S>(
@@ -275,25 +315,179 @@ struct BvhWalk {
         }
     }
 
+    // SE(3)/f32 leaf visit split in two so the loads of the NEXT leaf can be in flight while the
+    // current one is evaluated (software pipelining inside the warp hides the L2 latency of the
+    // dependent pick -> load -> evaluate chain).
+    // compressed leaf visit, split in two so the loads of the NEXT leaf are in flight while the current
+    // one is evaluated
+    struct LeafData {
+        uint32_t h[4];  // half2 rows (qx,qy) (qz,qw) (tx,ty) (tz,0)
+    };
+    __device__ __forceinline__ void leafLoad(uint32_t node, LeafData& ld) const {
+        const uint32_t* ph = a.leafH + ((size_t)node * 4u) * 32u + lane;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ld.h[c] = __ldg(ph + c * 32);
+    }
+    // exact distance of this lane's point (operation order of mptg_space.h) and offer
+    __device__ __forceinline__ void leafExact(uint32_t node, bool maybe) {
+        const uint32_t p = node * 32u + (uint32_t)lane;
+        const uint32_t orig = __ldg(a.perm + p);
+        const float* pt = (const float*)a.leafPts + ((size_t)node * 7u) * 32u + lane;
+        float pv[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) pv[c] = __ldg(pt + c * 32);
+        float dot = pv[0] * (float)qr[0];
+        dot = __fmaf_rn(pv[1], (float)qr[1], dot);
+        dot = __fmaf_rn(pv[2], (float)qr[2], dot);
+        dot = __fmaf_rn(pv[3], (float)qr[3], dot);
+        const float d0 = pv[4] - (float)qr[4], d1 = pv[5] - (float)qr[5], d2 = pv[6] - (float)qr[6];
+        float s2 = d0 * d0;
+        s2 = __fmaf_rn(d1, d1, s2);
+        s2 = __fmaf_rn(d2, d2, s2);
+        const float ad = fminf(1.0f, fabsf(dot));
+        float dr = fp::acos01(ad);
+        if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
+        float dt = fp::sqrt_(s2);
+        if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
+        top.offer(maybe && orig != MPTG_NO_INDEX, (S)(dr + dt), orig * a.idxMul + a.idxAdd, a.radius, lane);
+    }
+    __device__ __forceinline__ void leafEval(uint32_t node, const LeafData& ld) {
+        ++leaves;
+        // prefilter on the half-precision copy: |dot error| <= qabs*errQ, |coordinate error| <= errT
+        const float2 xy = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[0]));
+        const float2 zw = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[1]));
+        const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[2]));
+        const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[3]));
+        float dot = xy.x * (float)qr[0];
+        dot = __fmaf_rn(xy.y, (float)qr[1], dot);
+        dot = __fmaf_rn(zw.x, (float)qr[2], dot);
+        dot = __fmaf_rn(zw.y, (float)qr[3], dot);
+        const float e0 = fmaxf(fabsf(t01.x - (float)qr[4]) - a.errT, 0.0f);
+        const float e1 = fmaxf(fabsf(t01.y - (float)qr[5]) - a.errT, 0.0f);
+        const float e2 = fmaxf(fabsf(t2.x - (float)qr[6]) - a.errT, 0.0f);
+        const float s2 = __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0));
+        const float ad = fminf(1.0f, __fmaf_rn(qabs, a.errQ, fabsf(dot)));
+        const bool maybe = se3CheapBound(ad, s2, w0, w1) <= threshold();
+        if (!__any_sync(FULL_MASK, maybe)) return;
+        leafExact(node, maybe);  // rare: fetch the exact points and evaluate the true distance
+    }
+
+    // take the child with the smallest remaining bound; false when none is left within the threshold
+    __device__ __forceinline__ bool pick(uint32_t& key, uint32_t block, uint32_t& node) const {
+        const uint32_t best = __reduce_min_sync(FULL_MASK, key);
+        if (best == BVH_DEAD || __uint_as_float(best) > threshold()) return false;
+        const int src = __ffs(__ballot_sync(FULL_MASK, key == best)) - 1;
+        if (lane == src) key = BVH_DEAD;
+        node = block * 32u + (uint32_t)src;
+        return true;
+    }
+
     // visit the children (level L nodes) of `block`, nearest bound first
     template <int L>
     __device__ __forceinline__ void descend(uint32_t block) {
         uint32_t key = childKey<L>(block);
-        for (;;) {
-            const uint32_t best = __reduce_min_sync(FULL_MASK, key);
-            if (best == BVH_DEAD || __uint_as_float(best) > threshold()) return;
-            const int src = __ffs(__ballot_sync(FULL_MASK, key == best)) - 1;
-            if (lane == src) key = BVH_DEAD;
-            const uint32_t node = block * 32u + (uint32_t)src;
-            if constexpr (L == 0) {
-                leaf(node);
-            } else {
-                ++inner;
-                descend<L - 1>(node);
+        uint32_t node;
+        if (L == 0 && SHAPE == SHAPE_SE3 && sizeof(S) == 4 && a.leafH != nullptr) {
+            LeafData cur, nxt;
+            if (!pick(key, block, node)) return;
+            leafLoad(node, cur);
+            for (;;) {
+                // the next leaf is chosen (and its loads issued) against the threshold BEFORE the current
+                // leaf is evaluated; if that evaluation tightens the threshold past it, it is dropped below
+                const uint32_t keyBefore = key;
+                uint32_t nextNode;
+                const bool haveNext = pick(key, block, nextNode);
+                if (haveNext) leafLoad(nextNode, nxt);
+                leafEval(node, cur);
+                if (!haveNext) return;
+                // re-check the picked leaf's bound against the (possibly smaller) threshold
+                const uint32_t nb = __reduce_min_sync(FULL_MASK, keyBefore);
+                if (__uint_as_float(nb) > threshold()) return;  // every remaining bound is >= nb
+                cur = nxt;
+                node = nextNode;
+            }
+        } else {
+            while (pick(key, block, node)) {
+                if constexpr (L == 0) {
+                    leaf(node);
+                } else {
+                    ++inner;
+                    descend<L - 1>(node);
+                }
             }
         }
     }
 };
+
+// ---- query ordering: queries that end up in the same region of the tree are processed by
+// neighbouring warps, so the node and leaf lines they touch are shared through L1.
+// Key = the leaf reached by always following the smallest child bound (three node visits at 1M).
+template <typename S, int SHAPE>
+__global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKeyKernel(const BvhArgs<S> a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* qsm = reinterpret_cast<S*>(smemRaw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q = blockIdx.x * BVH_WARPS + warp;
+    if (q >= a.Q) return;
+    S* myq = qsm + warp * D;
+    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+    __syncwarp();
+    BvhWalk<S, SHAPE, 1> w(a, myq, lane);
+    if (SHAPE == SHAPE_SE3) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
+        w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
+        w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
+        w.qabs = fabsf((float)myq[0]) + fabsf((float)myq[1]) + fabsf((float)myq[2]) + fabsf((float)myq[3]);
+    }
+    uint32_t node = 0;
+    auto step = [&](uint32_t key) {
+        const uint32_t best = __reduce_min_sync(FULL_MASK, key);
+        const int src = __ffs(__ballot_sync(FULL_MASK, key == best)) - 1;
+        node = node * 32u + (uint32_t)(src < 0 ? 0 : src);
+    };
+    switch (a.top) {  // fall through from the top level down to the leaves
+        case 4: step(w.template childKey<4>(node));
+        case 3: step(w.template childKey<3>(node));
+        case 2: step(w.template childKey<2>(node));
+        case 1: step(w.template childKey<1>(node));
+        default: step(w.template childKey<0>(node));
+    }
+    if (lane == 0) {
+        a.orderKeys[q] = node;
+        atomicAdd(a.orderHist + (node >> a.orderShift), 1u);
+    }
+}
+
+// exclusive scan of up to 65536 bins by one CTA
+__global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint32_t bins) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (bins + 1023u) / 1024u;
+    const uint32_t b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint32_t i = b0; i < b0 + per && i < bins; ++i) sum += hist[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        const uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = b0; i < b0 + per && i < bins; ++i) {
+        const uint32_t c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+
+__global__ void knnOrderScatterKernel(const uint32_t* keys, uint32_t* cursor, uint32_t shift, uint32_t Q, uint32_t* order) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    order[atomicAdd(cursor + (keys[q] >> shift), 1u)] = q;
+}
 
 template <typename S, int SHAPE, int KPL>
 __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> a) {
@@ -301,8 +495,9 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
     S* qsm = reinterpret_cast<S*>(smemRaw);  // [BVH_WARPS][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = a.sp.D;
-    const uint32_t q = blockIdx.x * BVH_WARPS + warp;
-    if (q >= a.Q) return;  // warp-uniform; no block-wide barriers below
+    const uint32_t slot = blockIdx.x * BVH_WARPS + warp;
+    if (slot >= a.Q) return;  // warp-uniform; no block-wide barriers below
+    const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
 
     S* myq = qsm + warp * D;
     for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
@@ -313,6 +508,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
         for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
         w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
         w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
+        w.qabs = fabsf((float)myq[0]) + fabsf((float)myq[1]) + fabsf((float)myq[2]) + fabsf((float)myq[3]);
     }
     w.top.init(a.k);
     switch (a.top) {
@@ -332,6 +528,59 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
 
 // ------------------------------------------------------------------ host: build
 namespace {
+
+// IEEE binary16 helpers on the host (bit exact, no dependence on host support in cuda_fp16.h)
+inline float halfBitsToFloat(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {
+            int e = -1;
+            do {
+                ++e;
+                man <<= 1;
+            } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+// nearest half (ties to even); |v| beyond the half range becomes +-inf
+inline uint16_t floatToHalfBitsRn(float v) {
+    uint32_t x;
+    memcpy(&x, &v, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);  // rounds to >= 65520 -> inf
+    if (x < 0x33000001u) return sign;                          // < 2^-25 -> 0
+    int exp = (int)(x >> 23) - 127;
+    uint32_t man = (x & 0x7fffffu) | 0x800000u;
+    int shift = exp < -14 ? (13 + (-14 - exp)) : 13;
+    uint32_t hman = man >> shift;
+    const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (hman & 1u))) ++hman;
+    uint32_t hbits = exp < -14 ? hman : (((uint32_t)(exp + 15) << 10) + (hman - 0x400u));
+    return (uint16_t)(sign | hbits);
+}
+// largest half <= v  /  smallest half >= v
+inline uint16_t floatToHalfBitsDown(float v) {
+    uint16_t h = floatToHalfBitsRn(v);
+    if (halfBitsToFloat(h) > v) h = (h & 0x8000u) ? (uint16_t)(h + 1) : (h == 0 ? (uint16_t)0x8001u : (uint16_t)(h - 1));
+    return h;
+}
+inline uint16_t floatToHalfBitsUp(float v) {
+    uint16_t h = floatToHalfBitsRn(v);
+    if (halfBitsToFloat(h) < v) h = (h & 0x8000u) ? (h == 0x8000u ? (uint16_t)0x0001u : (uint16_t)(h - 1)) : (uint16_t)(h + 1);
+    return h;
+}
 
 template <typename S>
 struct HostBuild {
@@ -469,6 +718,16 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
         nBlocks[l] = (nx.nNodes[l] + 31) / 32;
         oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(S));
     }
+    // SE(3)/f32: half-precision copies for the prefilters (only when every coordinate fits a half)
+    bool compressed = sizeof(S) == 4 && classifySpace(space) == SHAPE_SE3;
+    if (compressed)
+        for (uint32_t i = 0; i < n && compressed; ++i)
+            for (int c = 4; c < 7; ++c) compressed = compressed && std::fabs((double)hb.pts[(size_t)i * D + c]) < 60000.0;
+    size_t oLeafH = 0, oBoxH[BVH_MAXL] = {0, 0, 0, 0, 0};
+    if (compressed) {
+        oLeafH = take((size_t)nx.nNodes[0] * 4 * 32 * sizeof(uint32_t));
+        for (int l = 0; l <= nx.top; ++l) oBoxH[l] = take((size_t)nBlocks[l] * 7 * 32 * sizeof(uint32_t));
+    }
     std::vector<unsigned char> host(bytes, 0);
     S* hp = reinterpret_cast<S*>(host.data() + oPts);
     uint32_t* hperm = reinterpret_cast<uint32_t*>(host.data() + oPerm);
@@ -489,6 +748,35 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
                     bx[((size_t)b * 2 * D + D + c) * 32 + ln] = j < nn ? hi[l][(size_t)c * nn + j] : -inf;
                 }
             }
+    }
+    float errQ = 0.f, errT = 0.f;
+    if (compressed) {
+        uint32_t* lh = reinterpret_cast<uint32_t*>(host.data() + oLeafH);
+        for (uint32_t i = 0; i < nx.nPad; ++i) {
+            const uint32_t leaf = i >> 5, ln = i & 31;
+            uint16_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < 7; ++c) {
+                const float v = (float)hp[((size_t)leaf * D + c) * 32 + ln];
+                h[c] = floatToHalfBitsRn(v);
+                const float e = std::fabs(halfBitsToFloat(h[c]) - v);
+                if (c < 4) errQ = e > errQ ? e : errQ;
+                else errT = e > errT ? e : errT;
+            }
+            for (int r = 0; r < 4; ++r) lh[((size_t)leaf * 4 + r) * 32 + ln] = (uint32_t)h[2 * r] | ((uint32_t)h[2 * r + 1] << 16);
+        }
+        for (int l = 0; l <= nx.top; ++l) {
+            uint32_t* bh = reinterpret_cast<uint32_t*>(host.data() + oBoxH[l]);
+            const uint32_t nn = nx.nNodes[l];
+            for (uint32_t b = 0; b < nBlocks[l]; ++b)
+                for (uint32_t ln = 0; ln < 32; ++ln) {
+                    const uint32_t j = b * 32 + ln;
+                    for (int c = 0; c < 7; ++c) {
+                        const uint16_t hl = j < nn ? floatToHalfBitsDown((float)lo[l][(size_t)c * nn + j]) : (uint16_t)0x7c00u;
+                        const uint16_t hh = j < nn ? floatToHalfBitsUp((float)hi[l][(size_t)c * nn + j]) : (uint16_t)0xfc00u;
+                        bh[((size_t)b * 7 + c) * 32 + ln] = (uint32_t)hl | ((uint32_t)hh << 16);
+                    }
+                }
+        }
     }
     // 4. upload (reuse the block when it is large enough)
     void* mem = ix.mem;
@@ -512,6 +800,12 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     nx.leafPts = (char*)mem + oPts;
     nx.perm = (uint32_t*)((char*)mem + oPerm);
     for (int l = 0; l <= nx.top; ++l) nx.box[l] = (char*)mem + oBox[l];
+    if (compressed) {
+        nx.leafH = (uint32_t*)((char*)mem + oLeafH);
+        for (int l = 0; l <= nx.top; ++l) nx.boxH[l] = (uint32_t*)((char*)mem + oBoxH[l]);
+        nx.errQ = errQ * 1.0001f + 1e-30f;
+        nx.errT = errT * 1.0001f + 1e-30f;
+    }
     ix = nx;
     return MPTG_OK;
 }
@@ -525,9 +819,30 @@ int knnEnsureIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& sp, const
 }
 
 template <typename S, int SHAPE>
-int launchBvhShape(mptg_ctx* ctx, const BvhArgs<S>& a) {
+int launchBvhShape(mptg_ctx* ctx, BvhArgs<S>& a) {
     const dim3 grid((a.Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
     const size_t smem = (size_t)BVH_WARPS * a.sp.D * sizeof(S);
+    // spatial processing order for large waves (skipped for small ones: three extra launches)
+    if (a.Q >= 4096 && a.top >= 1) {
+        uint32_t shift = 0;
+        while ((a.nNodes[0] >> shift) > 65536u) ++shift;
+        const uint32_t bins = (a.nNodes[0] >> shift) + 1u;
+        void* buf;
+        int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
+        if (rc) return rc;
+        uint32_t* order = (uint32_t*)buf;
+        a.orderKeys = order + a.Q;
+        a.orderHist = order + 2 * (size_t)a.Q;
+        a.orderShift = shift;
+        MPTG_CUDA(ctx, cudaMemsetAsync(a.orderHist, 0, bins * sizeof(uint32_t), ctx->stream));
+        knnBvhKeyKernel<S, SHAPE><<<grid, block, smem, ctx->stream>>>(a);
+        MPTG_LAUNCHED(ctx);
+        knnOrderScanKernel<<<1, 1024, 0, ctx->stream>>>(a.orderHist, bins);
+        MPTG_LAUNCHED(ctx);
+        knnOrderScatterKernel<<<(a.Q + 255) / 256, 256, 0, ctx->stream>>>(a.orderKeys, a.orderHist, shift, a.Q, order);
+        MPTG_LAUNCHED(ctx);
+        a.order = order;
+    }
     if (a.k <= 32) knnBvhKernel<S, SHAPE, 1><<<grid, block, smem, ctx->stream>>>(a);
     else if (a.k <= 64) knnBvhKernel<S, SHAPE, 2><<<grid, block, smem, ctx->stream>>>(a);
     else knnBvhKernel<S, SHAPE, 4><<<grid, block, smem, ctx->stream>>>(a);
@@ -542,6 +857,10 @@ int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const
     BvhArgs<S> a{};
     a.leafPts = (const S*)ix.leafPts;
     a.perm = ix.perm;
+    a.leafH = ix.leafH;
+    a.errQ = ix.errQ;
+    a.errT = ix.errT;
+    for (int l = 0; l < BVH_MAXL; ++l) a.boxH[l] = ix.boxH[l];
     for (int l = 0; l < BVH_MAXL; ++l) {
         a.box[l] = (const S*)ix.box[l];
         a.nNodes[l] = ix.nNodes[l];
