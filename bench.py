@@ -42,6 +42,15 @@ ALGO_BYTES_KNN = N_TREE * 7 * 4 + Q_WAVE * 7 * 4 + Q_WAVE * K_NN * (4 + 4)  # SU
 F_BV, F_TRI = 45.0, 170.0  # flop per box-pair test (rotated-AABB vs AABB as implemented) / per SAT
 
 
+def measured_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    try:
+        return float(json.loads(p.read_text())[kernel]["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -288,7 +297,7 @@ def run_ours(args):
         "edge_states_per_s": world * mesh_stats["states"] / (edge_ms * 1e-3),
         "roofline": {
             "kernel": "knnBvhKernel<float,SE3,1>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / hbm_peak, "traffic": measured_traffic("knnBvhKernel<float,SE3,1>"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ALGO_BYTES_KNN,
             "note": "exact kNN is bound by box tests and distance evaluations, not by compulsory HBM bytes (DESIGN.md)",
             "distance_evals_per_query": knn_stats["distance_evals"] / Q_WAVE,
