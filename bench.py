@@ -302,6 +302,11 @@ def run_ours(args):
             "note": "exact kNN is bound by box tests and distance evaluations, not by compulsory HBM bytes (DESIGN.md)",
             "distance_evals_per_query": knn_stats["distance_evals"] / Q_WAVE,
             "nodes_visited_per_query": knn_stats["nodes_visited"] / Q_WAVE,
+            # SURVEY.md 8(d) honesty check: which roofline binds.  F_pair = 21 flop per SE(3) distance evaluation.
+            "fp32": {"achieved": knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": (knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
+                     "flop_per_distance_eval": 21.0,
+                     "binds": "FP32/issue (ncu: smsp__issue_active 83%, dram throughput 0.2% -- profiles/r1_ncu_knn_bvh_c.txt)"},
         },
         "roofline_edges": {
             "kernel": "meshLinkKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,

@@ -24,7 +24,7 @@ NVCC = os.environ.get("MPTG_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-std=c++17", "-O3", "-lineinfo", "--fmad=false",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-fopenmp",
     "-ccbin", "/usr/bin/g++",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xptxas", "-warn-spills",
@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building libmptg.so")
-    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-ccbin", "/usr/bin/g++", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-ccbin", "/usr/bin/g++", "-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lgomp"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         print(r.stdout)

@@ -198,6 +198,7 @@ void knnBrute(const mptg_space_desc& sp, const S* pts, uint32_t n, const S* quer
         const S* q = queries + (size_t)qi * D;
         for (uint32_t i = 0; i < n; ++i) {
             S d = distance(sp, pts + (size_t)i * D, q);
+            if (d != d) continue;  // NaN (e.g. a NaN query) is never a neighbour
             if (bounded && !(d <= r)) continue;
             if (best.size() == k && !(d < best.back().first)) continue;  // index ascending: ties keep older
             auto it = std::upper_bound(best.begin(), best.end(), std::make_pair(d, i));

@@ -179,6 +179,7 @@ struct BoxTree {
                 for (uint32_t i = n.begin; i < n.end; ++i) {
                     S d = distance(sp, &pts[(size_t)i * D], q);
                     ++evals;
+                    if (d != d) continue;
                     if (bounded && !(d <= r)) continue;
                     E e{d, ids[i]};
                     if (heap.size() < k) heap.push(e);

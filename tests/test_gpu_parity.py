@@ -136,6 +136,54 @@ def test_knn_bvh_double(ctx, oracle):
     assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
 
 
+def test_knn_degenerate_point_sets(ctx, oracle):
+    """All points identical / on a line / two clusters: zero-extent boxes, massive ties (index order decides)."""
+    sp = m.se3_space(50, 1)
+    base = W.se3_states(1, 3)
+    same = np.repeat(base, 20_000, axis=0)
+    line = np.repeat(base, 20_000, axis=0)
+    line[:, 4] = np.linspace(-50, 50, 20_000, dtype=np.float32)
+    two = np.concatenate([np.repeat(W.se3_states(1, 4), 10_000, axis=0), np.repeat(W.se3_states(1, 5), 10_000, axis=0)])
+    q = np.concatenate([base, W.se3_states(63, 6)])
+    for pts in (same, line, two):
+        for strat in (m.KNN_BRUTE, m.KNN_BVH):
+            nn = m.Nearest(ctx, sp, 32768, strat)
+            nn.insert(pts)
+            for k in (1, 16, 40):
+                assert_knn_equal(nn.nearest(q, k), oracle.knn(sp, pts, q, k))
+            nn.close()
+
+
+def test_knn_nan_and_far_queries(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    pts = W.se3_states(30_000, 1)
+    q = W.se3_states(16, 2)
+    q[0, 4] = np.nan          # NaN query: no distance compares true, no neighbours
+    q[1, 4:] = 1e6            # far away: still exact
+    q[2, :4] = 0              # zero quaternion: |dot| = 0, rotation term pi/2 * w everywhere
+    for strat in (m.KNN_BRUTE, m.KNN_BVH):
+        nn = m.Nearest(ctx, sp, 32768, strat)
+        nn.insert(pts)
+        got, want = nn.nearest(q, 8), oracle.knn(sp, pts, q, 8)
+        assert got[2][0] == 0 and want[2][0] == 0
+        assert_knn_equal(got, want)
+        nn.close()
+
+
+def test_mesh_empty_and_far(ctx, oracle):
+    sp = m.se3_space(50, 1)
+    tri = [[[0, 0, 0], [1, 0, 0], [0, 1, 0]]]
+    none = np.zeros((0, 3, 3), np.float32)
+    st = W.se3_states(100, 1, -5, 5)
+    for robot, env in ((tri, none), (none, tri), (none, none)):
+        sc = m.Scenario.mesh_pair(ctx, robot, env, sp, 0.5)
+        assert sc.valid(st).all() and sc.link(st[:50], st[50:]).all()
+    far = st.copy()
+    far[:, 4:] += 1e4
+    sc = m.Scenario.mesh_pair(ctx, tri, tri, sp, 0.5)
+    assert sc.valid(far).all()
+
+
 def test_knn_edge_cases(ctx, oracle):
     sp = m.se3_space(50, 1)
     nn = m.Nearest(ctx, sp, 64, m.KNN_BRUTE)
