@@ -237,10 +237,10 @@ public:
     GoalState(Distance radius, const State_& goal) : radius_(radius), goal_(goal) {}
     const State_& state() const { return goal_; }
     Distance radius() const { return radius_; }
-    // goal_state.hpp:64-69: (distance <= radius, distance)
+    // goal_state.hpp:64-69: (true, 0) inside the radius, otherwise (false, distance - radius)
     std::pair<bool, Distance> operator()(const Space& space, const State_& q) const {
-        const Distance d = space.distance(goal_, q);
-        return {d <= radius_, d};
+        const Distance d = space.distance(q, goal_);
+        return d <= radius_ ? std::make_pair(true, Distance(0)) : std::make_pair(false, d - radius_);
     }
 };
 
