@@ -1,0 +1,437 @@
+// knn_build.cu -- device-side construction of the kNN index (float32 spaces).
+//
+// Same structure as the host build in knn_bvh.cuh (kd-style median splits on the widest weighted
+// coordinate, split positions aligned to powers of 32, 32 points per leaf, 32 children per node),
+// built without leaving the GPU: one pass per binary level
+//     segment extents (block-reduced min/max, then atomics)  ->  split axis per segment
+//     ->  64-bit keys (segment, ordered coordinate)  ->  radix sort of (key, point id)
+// followed by kernels that emit the blocked leaf / box arrays, the half-precision copies and their
+// error bounds.  The radix sort is cub::DeviceRadixSort (library code, build path only -- the search
+// kernels are hand written).  Any permutation gives a correct index (the search is exact for any
+// boxes that contain their members); the ordering only decides how well it prunes.
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+#include "../../include/mptg/mptg_space.h"
+#include "knn_index.cuh"
+
+namespace mptg {
+namespace {
+
+__device__ __forceinline__ int orderedInt(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float fromOrderedInt(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ uint32_t orderedUint(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SegLevel {        // one binary level: segments in position order
+    const uint32_t* begin;   // [nSeg]
+    const uint32_t* mid;     // [nSeg]  (== end when the segment is not split any further)
+    const uint32_t* end;     // [nSeg]
+    const uint32_t* childBase;  // [nSeg] index of the first child segment in the next level
+    uint32_t nSeg;
+};
+
+// canonical AoS copy: SO(3) parts flipped to w >= 0
+__global__ void canonKernel(DevSpace<float> sp, const float* __restrict__ pts, uint32_t stride, uint32_t n, float* __restrict__ canon) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int p = 0; p < sp.nParts; ++p) {
+        const int off = sp.off[p];
+        bool flip = false;
+        if (sp.kind[p] == MPTG_PART_SO3) flip = pts[(size_t)(off + 3) * stride + i] < 0.0f;
+        for (int j = 0; j < sp.dim[p]; ++j) {
+            const float v = pts[(size_t)(off + j) * stride + i];
+            canon[(size_t)i * sp.D + off + j] = flip ? -v : v;
+        }
+    }
+}
+
+__global__ void iotaKernel(uint32_t* ids, uint32_t* segOf, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ids[i] = i, segOf[i] = 0;
+}
+
+__global__ void resetExtentKernel(int* segMin, int* segMax, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) segMin[i] = 0x7fffffff, segMax[i] = (int)0x80000000;
+}
+
+// per-segment min / max of every coordinate; a block whose positions all lie in one segment reduces first
+constexpr int EXT_THREADS = 256;
+__global__ void __launch_bounds__(EXT_THREADS) segExtentKernel(const float* __restrict__ canon, const uint32_t* __restrict__ ids,
+                                                               const uint32_t* __restrict__ segOf, uint32_t n, int D, int* segMin,
+                                                               int* segMax) {
+    __shared__ int sMin[EXT_THREADS / 32], sMax[EXT_THREADS / 32];
+    const uint32_t i = blockIdx.x * EXT_THREADS + threadIdx.x;
+    const uint32_t first = blockIdx.x * EXT_THREADS, last = min(n, first + EXT_THREADS) - 1;
+    const bool uniform = segOf[first] == segOf[last];  // segments are contiguous position ranges
+    const bool have = i < n;
+    const uint32_t seg = have ? segOf[i] : 0;
+    const float* pt = have ? canon + (size_t)ids[i] * D : canon;
+    for (int c = 0; c < D; ++c) {
+        const int v = have ? orderedInt(pt[c]) : 0;
+        if (uniform) {
+            int mn = have ? v : 0x7fffffff, mx = have ? v : (int)0x80000000;
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if ((threadIdx.x & 31) == 0) sMin[threadIdx.x >> 5] = mn, sMax[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < EXT_THREADS / 32; ++w) mn = min(mn, sMin[w]), mx = max(mx, sMax[w]);
+                const uint32_t s0 = segOf[first];
+                atomicMin(segMin + (size_t)s0 * D + c, mn);
+                atomicMax(segMax + (size_t)s0 * D + c, mx);
+            }
+            __syncthreads();
+        } else if (have) {
+            atomicMin(segMin + (size_t)seg * D + c, v);
+            atomicMax(segMax + (size_t)seg * D + c, v);
+        }
+    }
+}
+
+__global__ void axisKernel(DevSpace<float> sp, const int* __restrict__ segMin, const int* __restrict__ segMax, uint32_t nSeg,
+                           uint32_t* __restrict__ axis) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSeg) return;
+    int best = 0;
+    float bestExt = -1.0f;
+    for (int p = 0; p < sp.nParts; ++p)
+        for (int j = 0; j < sp.dim[p]; ++j) {
+            const int c = sp.off[p] + j;
+            const float ext = (fromOrderedInt(segMax[(size_t)s * sp.D + c]) - fromOrderedInt(segMin[(size_t)s * sp.D + c])) * sp.weight[p];
+            if (ext > bestExt) bestExt = ext, best = c;
+        }
+    axis[s] = (uint32_t)best;
+}
+
+__global__ void keyKernel(const float* __restrict__ canon, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ segOf,
+                          const uint32_t* __restrict__ axis, uint32_t n, int D, unsigned long long* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t seg = segOf[i];
+    keys[i] = ((unsigned long long)seg << 32) | orderedUint(canon[(size_t)ids[i] * D + axis[seg]]);
+}
+
+__global__ void splitKernel(SegLevel lv, uint32_t* __restrict__ segOf, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = segOf[i];
+    segOf[i] = lv.childBase[s] + (i >= lv.mid[s] ? 1u : 0u);
+}
+
+// ---- emit the device image
+// one warp per leaf: blocked points, perm, leaf box (SoA per level: lo[c][nNodes], hi[c][nNodes])
+__global__ void __launch_bounds__(256) leafEmitKernel(const float* __restrict__ canon, const uint32_t* __restrict__ ids, uint32_t n, int D,
+                                                      uint32_t nLeaves, float* __restrict__ leafPts, uint32_t* __restrict__ perm,
+                                                      float* __restrict__ lo, float* __restrict__ hi) {
+    const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (leaf >= nLeaves) return;
+    const uint32_t p = leaf * 32u + lane;
+    const bool real = p < n;
+    const uint32_t src = ids[real ? p : n - 1];  // padding repeats the last point (perm marks it unused)
+    perm[p] = real ? src : MPTG_NO_INDEX;
+    for (int c = 0; c < D; ++c) {
+        const float v = canon[(size_t)src * D + c];
+        leafPts[((size_t)leaf * D + c) * 32u + lane] = v;
+        float mn = v, mx = v;
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) lo[(size_t)c * nLeaves + leaf] = mn, hi[(size_t)c * nLeaves + leaf] = mx;
+    }
+}
+
+// one warp per parent: box of its (up to) 32 children
+__global__ void __launch_bounds__(256) parentBoxKernel(const float* __restrict__ clo, const float* __restrict__ chi, uint32_t nChild, int D,
+                                                       uint32_t nParent, float* __restrict__ lo, float* __restrict__ hi) {
+    const uint32_t parent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (parent >= nParent) return;
+    const uint32_t child = parent * 32u + lane;
+    for (int c = 0; c < D; ++c) {
+        float mn = child < nChild ? clo[(size_t)c * nChild + child] : INFINITY;
+        float mx = child < nChild ? chi[(size_t)c * nChild + child] : -INFINITY;
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (lane == 0) lo[(size_t)c * nParent + parent] = mn, hi[(size_t)c * nParent + parent] = mx;
+    }
+}
+
+// SoA boxes -> blocked [block][2D][32]; and for SE(3) the half2 (lo down, hi up) copies
+__global__ void boxBlockKernel(const float* __restrict__ lo, const float* __restrict__ hi, uint32_t nNodes, int D, float* __restrict__ box,
+                               uint32_t* __restrict__ boxH) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // node slot, padded to a multiple of 32
+    const uint32_t nSlots = ((nNodes + 31u) / 32u) * 32u;
+    if (j >= nSlots) return;
+    const uint32_t b = j >> 5, ln = j & 31;
+    for (int c = 0; c < D; ++c) {
+        const float l = j < nNodes ? lo[(size_t)c * nNodes + j] : INFINITY;
+        const float h = j < nNodes ? hi[(size_t)c * nNodes + j] : -INFINITY;
+        box[((size_t)b * 2 * D + c) * 32u + ln] = l;
+        box[((size_t)b * 2 * D + D + c) * 32u + ln] = h;
+        if (boxH) {
+            const __half hl = __float2half_rd(l), hh = __float2half_ru(h);
+            boxH[((size_t)b * 7 + c) * 32u + ln] = (uint32_t)__half_as_ushort(hl) | ((uint32_t)__half_as_ushort(hh) << 16);
+        }
+    }
+}
+
+// SE(3): half2 rows of the leaf points + max conversion error of quaternion / translation coordinates
+__global__ void leafHalfKernel(const float* __restrict__ leafPts, uint32_t nPad, uint32_t* __restrict__ leafH, unsigned int* __restrict__ err) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    float eq = 0.0f, et = 0.0f;
+    if (p < nPad) {
+        const uint32_t leaf = p >> 5, ln = p & 31;
+        unsigned short h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < 7; ++c) {
+            const float v = leafPts[((size_t)leaf * 7 + c) * 32u + ln];
+            const __half hv = __float2half_rn(v);
+            h[c] = __half_as_ushort(hv);
+            const float e = fabsf(__half2float(hv) - v);
+            if (c < 4) eq = fmaxf(eq, e);
+            else et = fmaxf(et, e);
+        }
+        for (int r = 0; r < 4; ++r) leafH[((size_t)leaf * 4 + r) * 32u + ln] = (uint32_t)h[2 * r] | ((uint32_t)h[2 * r + 1] << 16);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        eq = fmaxf(eq, __shfl_xor_sync(0xffffffffu, eq, o));
+        et = fmaxf(et, __shfl_xor_sync(0xffffffffu, et, o));
+    }
+    if ((threadIdx.x & 31) == 0) {  // non-negative floats order like unsigned ints
+        atomicMax(err + 0, __float_as_uint(eq));
+        atomicMax(err + 1, __float_as_uint(et));
+    }
+}
+
+struct Levels {
+    std::vector<uint32_t> begin, mid, end, childBase;  // concatenated over levels
+    std::vector<uint32_t> levelOffset, levelCount;
+};
+
+// segment lists per binary level, same split rule as HostBuild::split (knn_bvh.cuh)
+Levels makeLevels(uint32_t n) {
+    Levels L;
+    std::vector<std::pair<uint32_t, uint32_t>> cur{{0u, n}};
+    for (;;) {
+        bool any = false;
+        std::vector<std::pair<uint32_t, uint32_t>> next;
+        L.levelOffset.push_back((uint32_t)L.begin.size());
+        L.levelCount.push_back((uint32_t)cur.size());
+        for (auto [b, e] : cur) {
+            const uint32_t len = e - b;
+            L.begin.push_back(b);
+            L.end.push_back(e);
+            L.childBase.push_back((uint32_t)next.size());
+            if (len <= 32) {
+                L.mid.push_back(e);
+                next.push_back({b, e});
+            } else {
+                uint32_t blk = 32;
+                while ((uint64_t)blk * 32 < len) blk *= 32;
+                const uint32_t nblk = (len + blk - 1) / blk;
+                const uint32_t mid = b + ((nblk + 1) / 2) * blk;
+                L.mid.push_back(mid);
+                next.push_back({b, mid});
+                next.push_back({mid, e});
+                any = true;
+            }
+        }
+        if (!any) break;
+        cur.swap(next);
+    }
+    return L;
+}
+
+}  // namespace
+
+int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t n) {
+    if (n == 0) {
+        ix.count = 0;
+        return MPTG_OK;
+    }
+    const DevSpace<float> sp = makeDevSpace<float>(space);
+    const int D = sp.D;
+    cudaStream_t st = ctx->stream;
+    const bool compressed = classifySpace(space) == SHAPE_SE3;  // half copies; coordinates beyond the half range fall back below
+
+    // ---- geometry of the image
+    KnnIndex nx;
+    nx.count = n;
+    nx.nNodes[0] = (n + 31) / 32;
+    nx.nPad = nx.nNodes[0] * 32;
+    nx.top = 0;
+    while (nx.nNodes[nx.top] > 32) {
+        if (nx.top + 1 >= BVH_MAXL) return fail(ctx, MPTG_ERR_CAPACITY, "kNN index: too many points for %d levels", BVH_MAXL);
+        nx.nNodes[nx.top + 1] = (nx.nNodes[nx.top] + 31) / 32;
+        ++nx.top;
+    }
+    size_t bytes = 0;
+    auto take = [&](size_t b) {
+        const size_t o = bytes;
+        bytes += (b + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t oPts = take((size_t)D * nx.nPad * sizeof(float));
+    const size_t oPerm = take((size_t)nx.nPad * sizeof(uint32_t));
+    size_t oBox[BVH_MAXL] = {0, 0, 0, 0, 0}, oBoxH[BVH_MAXL] = {0, 0, 0, 0, 0}, oLeafH = 0;
+    uint32_t nBlocks[BVH_MAXL] = {0, 0, 0, 0, 0};
+    for (int l = 0; l <= nx.top; ++l) {
+        nBlocks[l] = (nx.nNodes[l] + 31) / 32;
+        oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(float));
+    }
+    if (compressed) {
+        oLeafH = take((size_t)nx.nNodes[0] * 4 * 32 * sizeof(uint32_t));
+        for (int l = 0; l <= nx.top; ++l) oBoxH[l] = take((size_t)nBlocks[l] * 7 * 32 * sizeof(uint32_t));
+    }
+    void* mem = ix.mem;
+    size_t memBytes = ix.memBytes;
+    if (memBytes < bytes) {
+        MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+        if (mem) MPTG_CUDA(ctx, cudaFree(mem));
+        mem = nullptr;
+        memBytes = bytes + bytes / 2;
+        MPTG_CUDA(ctx, cudaMalloc(&mem, memBytes));
+    }
+    unsigned long long* stats = ix.devStats;
+    if (!stats) {
+        MPTG_CUDA(ctx, cudaMalloc(&stats, 4 * sizeof(unsigned long long)));
+        if (int rc = memsetSync(ctx, stats, 0, 4 * sizeof(unsigned long long))) return rc;
+    }
+
+    // ---- work space (context scratch slot 7): canon, keys x2, ids x2, segOf, extents, axis, level tables, SoA boxes, cub temp
+    const Levels L = makeLevels(n);
+    const uint32_t maxSeg = nx.nNodes[0] + 1;
+    const size_t nTab = L.begin.size();
+    size_t cubBytes = 0;
+    cub::DoubleBuffer<unsigned long long> kb(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> vb(nullptr, nullptr);
+    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, kb, vb, (int)n, 0, 64, st));
+    size_t wbytes = 0;
+    auto wtake = [&](size_t b) {
+        const size_t o = wbytes;
+        wbytes += (b + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t wCanon = wtake((size_t)n * D * 4), wKey0 = wtake((size_t)n * 8), wKey1 = wtake((size_t)n * 8), wId0 = wtake((size_t)n * 4),
+                 wId1 = wtake((size_t)n * 4), wSeg = wtake((size_t)n * 4), wMin = wtake((size_t)maxSeg * D * 4),
+                 wMax = wtake((size_t)maxSeg * D * 4), wAxis = wtake((size_t)maxSeg * 4), wTab = wtake(nTab * 4 * 4), wCub = wtake(cubBytes),
+                 wErr = wtake(16);
+    size_t wLo[BVH_MAXL], wHi[BVH_MAXL];
+    for (int l = 0; l <= nx.top; ++l) wLo[l] = wtake((size_t)D * nx.nNodes[l] * 4), wHi[l] = wtake((size_t)D * nx.nNodes[l] * 4);
+    void* wbase;
+    if (int rc = scratch(ctx, 7, wbytes, &wbase)) return rc;
+    char* W = (char*)wbase;
+    float* canon = (float*)(W + wCanon);
+    unsigned long long* keys[2] = {(unsigned long long*)(W + wKey0), (unsigned long long*)(W + wKey1)};
+    uint32_t* ids[2] = {(uint32_t*)(W + wId0), (uint32_t*)(W + wId1)};
+    uint32_t* segOf = (uint32_t*)(W + wSeg);
+    int* segMin = (int*)(W + wMin);
+    int* segMax = (int*)(W + wMax);
+    uint32_t* axis = (uint32_t*)(W + wAxis);
+    uint32_t* tab = (uint32_t*)(W + wTab);
+    unsigned int* err = (unsigned int*)(W + wErr);
+    {  // level tables: begin | mid | end | childBase, each nTab entries
+        std::vector<uint32_t> host(nTab * 4);
+        std::copy(L.begin.begin(), L.begin.end(), host.begin());
+        std::copy(L.mid.begin(), L.mid.end(), host.begin() + nTab);
+        std::copy(L.end.begin(), L.end.end(), host.begin() + 2 * nTab);
+        std::copy(L.childBase.begin(), L.childBase.end(), host.begin() + 3 * nTab);
+        if (int rc = uploadSync(ctx, tab, host.data(), host.size() * 4)) return rc;
+    }
+
+    // ---- 1. canonical copy, 2. one sort per binary level
+    const uint32_t g256 = (n + 255) / 256;
+    canonKernel<<<g256, 256, 0, st>>>(sp, ptsDev, stride, n, canon);
+    MPTG_LAUNCHED(ctx);
+    iotaKernel<<<g256, 256, 0, st>>>(ids[0], segOf, n);
+    MPTG_LAUNCHED(ctx);
+    int cur = 0;
+    const size_t nLevels = L.levelCount.size();
+    for (size_t lev = 0; lev + 1 < nLevels; ++lev) {  // the last level has nothing left to split
+        const uint32_t nSeg = L.levelCount[lev], off = L.levelOffset[lev];
+        SegLevel lv{tab + off, tab + nTab + off, tab + 2 * nTab + off, tab + 3 * nTab + off, nSeg};
+        resetExtentKernel<<<(nSeg * D + 255) / 256, 256, 0, st>>>(segMin, segMax, nSeg * D);
+        MPTG_LAUNCHED(ctx);
+        segExtentKernel<<<(n + EXT_THREADS - 1) / EXT_THREADS, EXT_THREADS, 0, st>>>(canon, ids[cur], segOf, n, D, segMin, segMax);
+        MPTG_LAUNCHED(ctx);
+        axisKernel<<<(nSeg + 255) / 256, 256, 0, st>>>(sp, segMin, segMax, nSeg, axis);
+        MPTG_LAUNCHED(ctx);
+        keyKernel<<<g256, 256, 0, st>>>(canon, ids[cur], segOf, axis, n, D, keys[cur]);
+        MPTG_LAUNCHED(ctx);
+        cub::DoubleBuffer<unsigned long long> dk(keys[cur], keys[cur ^ 1]);
+        cub::DoubleBuffer<uint32_t> dv(ids[cur], ids[cur ^ 1]);
+        int segBits = 1;
+        while ((1u << segBits) < nSeg) ++segBits;
+        MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(W + wCub, cubBytes, dk, dv, (int)n, 0, 32 + segBits, st));
+        ++ctx->launches;
+        cur = dv.Current() == ids[0] ? 0 : 1;  // the key buffers are scratch: fresh keys are written every level
+        splitKernel<<<g256, 256, 0, st>>>(lv, segOf, n);
+        MPTG_LAUNCHED(ctx);
+    }
+
+    // ---- 3. device image
+    char* M = (char*)mem;
+    float* lo0 = (float*)(W + wLo[0]);
+    float* hi0 = (float*)(W + wHi[0]);
+    leafEmitKernel<<<(nx.nNodes[0] * 32 + 255) / 256, 256, 0, st>>>(canon, ids[cur], n, D, nx.nNodes[0], (float*)(M + oPts),
+                                                                   (uint32_t*)(M + oPerm), lo0, hi0);
+    MPTG_LAUNCHED(ctx);
+    for (int l = 1; l <= nx.top; ++l) {
+        parentBoxKernel<<<(nx.nNodes[l] * 32 + 255) / 256, 256, 0, st>>>((const float*)(W + wLo[l - 1]), (const float*)(W + wHi[l - 1]),
+                                                                        nx.nNodes[l - 1], D, nx.nNodes[l], (float*)(W + wLo[l]),
+                                                                        (float*)(W + wHi[l]));
+        MPTG_LAUNCHED(ctx);
+    }
+    for (int l = 0; l <= nx.top; ++l) {
+        boxBlockKernel<<<(nBlocks[l] * 32 + 255) / 256, 256, 0, st>>>((const float*)(W + wLo[l]), (const float*)(W + wHi[l]), nx.nNodes[l], D,
+                                                                     (float*)(M + oBox[l]), compressed ? (uint32_t*)(M + oBoxH[l]) : nullptr);
+        MPTG_LAUNCHED(ctx);
+    }
+    float errQ = 0.f, errT = 0.f;
+    bool useHalf = compressed;
+    if (compressed) {
+        MPTG_CUDA(ctx, cudaMemsetAsync(err, 0, 16, st));
+        leafHalfKernel<<<(nx.nPad + 255) / 256, 256, 0, st>>>((const float*)(M + oPts), nx.nPad, (uint32_t*)(M + oLeafH), err);
+        MPTG_LAUNCHED(ctx);
+        unsigned int herr[2];
+        MPTG_CUDA(ctx, cudaMemcpyAsync(herr, err, 8, cudaMemcpyDeviceToHost, st));
+        MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+        memcpy(&errQ, &herr[0], 4);
+        memcpy(&errT, &herr[1], 4);
+        if (!(errT < 1e30f) || !(errQ < 1e30f)) useHalf = false;  // a coordinate overflowed the half range: keep the float path
+    }
+
+    nx.mem = mem;
+    nx.memBytes = memBytes;
+    nx.devStats = stats;
+    nx.builds = ix.builds + 1;
+    nx.leafPts = M + oPts;
+    nx.perm = (uint32_t*)(M + oPerm);
+    for (int l = 0; l <= nx.top; ++l) nx.box[l] = M + oBox[l];
+    if (useHalf) {
+        nx.leafH = (uint32_t*)(M + oLeafH);
+        for (int l = 0; l <= nx.top; ++l) nx.boxH[l] = (uint32_t*)(M + oBoxH[l]);
+        nx.errQ = errQ * 1.0001f + 1e-30f;
+        nx.errT = errT * 1.0001f + 1e-30f;
+    }
+    ix = nx;
+    return MPTG_OK;
+}
+
+}  // namespace mptg

@@ -23,40 +23,15 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "common.cuh"
+#include "knn_index.cuh"
 #include "../../include/mptg/mptg_space.h"
 #include "topk.cuh"
 
 namespace mptg {
-
-constexpr int BVH_MAXL = 5;  // 32^5 leaves -> up to 2^30 points
-constexpr uint32_t BVH_DEAD = 0xFFFFFFFFu;
-
-struct KnnIndex {
-    uint32_t count = 0;    // points covered (a prefix of the store)
-    uint32_t nPad = 0;     // leaves * 32
-    int top = 0;           // top level (0 = leaves)
-    uint32_t nNodes[BVH_MAXL] = {0, 0, 0, 0, 0};
-    void* mem = nullptr;   // one block: leaf points, perm, boxes
-    size_t memBytes = 0;
-    void* leafPts = nullptr;  // [leaf][D][32]
-    uint32_t* perm = nullptr;
-    void* box[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][2D][32]
-    // SE(3)/f32 only: half-precision copies that feed the conservative prefilters (half the L2 traffic)
-    uint32_t* leafH = nullptr;                                                 // [leaf][4][32] half2: (qx,qy) (qz,qw) (tx,ty) (tz,0)
-    uint32_t* boxH[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][7][32] half2 (lo rounded down, hi rounded up)
-    float errQ = 0.f, errT = 0.f;  // max |half(v) - v| over the stored quaternion / translation coordinates
-    unsigned long long* devStats = nullptr;  // [0] leaves visited, [1] inner nodes visited
-    uint64_t builds = 0;
-};
-
-inline void knnIndexFree(KnnIndex& ix) {
-    if (ix.mem) cudaFree(ix.mem);
-    if (ix.devStats) cudaFree(ix.devStats);
-    ix = KnnIndex();
-}
 
 // AUTO policy: the tree pays off once a scan of the whole set costs more than a handful of node
 // visits per query; below that the tiled scan wins and needs no build.
@@ -633,6 +608,12 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     if (n == 0) {
         ix.count = 0;
         return MPTG_OK;
+    }
+    // float32 spaces are built on the device (knn_build.cu); MPTG_KNN_HOST_BUILD=1 keeps the host path
+    // below (the double-precision path) for comparison.
+    if constexpr (sizeof(S) == 4) {
+        const char* env = getenv("MPTG_KNN_HOST_BUILD");
+        if (!(env && env[0] == '1')) return knnBuildIndexGpu(ctx, ix, space, (const float*)ptsDev, stride, n);
     }
     const DevSpace<S> sp = makeDevSpace<S>(space);
     const int D = sp.D;
