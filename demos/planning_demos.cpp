@@ -27,6 +27,7 @@ using namespace mptg;
 using Clock = std::chrono::steady_clock;
 
 struct Options {
+    std::size_t nodes = 0;  // > 0: run until the graph has this many nodes (the reference's -n flag, se3_rigid_body_planning.cpp:80-153)
     double timeMs = 5000;
     bool check = false;
     std::string map;
@@ -55,8 +56,8 @@ void report(const char* name, const char* algo, Planner& planner, const Scenario
         g.link(&desc, from.data(), to.data(), (std::uint32_t)from.size(), step, v.data());
         for (auto x : v) ok = ok && x == 1;
     }
-    std::printf("%s %s [%s]: solved=%d first solution after %.4f s (ran %.3f s), %zu nodes, %zu waypoints, path cost %.4f\n", ok ? "OK" : "FAILED",
-                name, algo, (int)planner.solved(), firstSolutionS, totalS, planner.size(), path.size(), cost);
+    std::printf("%s %s [%s]: solved=%d first solution after %.4f s (ran %.3f s, %.0f nodes/s), %zu nodes, %zu waypoints, path cost %.4f\n",
+                ok ? "OK" : "FAILED", name, algo, (int)planner.solved(), firstSolutionS, totalS, planner.size() / totalS, planner.size(), path.size(), cost);
     if (!ok) ++failures;
 }
 
@@ -82,6 +83,8 @@ struct Probe {
     }
 };
 
+static std::size_t g_targetNodes = 0;
+
 template <typename Planner>
 std::pair<double, double> runUntilSolved(Planner& planner, double timeMs) {
     const auto t0 = Clock::now();
@@ -91,7 +94,7 @@ std::pair<double, double> runUntilSolved(Planner& planner, double timeMs) {
         [&] {
             if (trace) std::fprintf(stderr, "trace: %zu nodes, solved=%d\n", planner.size(), (int)planner.solved());
             if (first < 0 && planner.solved()) first = std::chrono::duration<double>(Clock::now() - t0).count();
-            return planner.solved();
+            return g_targetNodes ? planner.size() >= g_targetNodes : planner.solved();
         },
         std::chrono::duration<double, std::milli>(timeMs));
     if (first < 0 && planner.solved()) first = std::chrono::duration<double>(Clock::now() - t0).count();
@@ -329,10 +332,11 @@ int main(int argc, char** argv) {
         else if (a == "--demo" && i + 1 < argc) which = argv[++i];
         else if (a == "--time-ms" && i + 1 < argc) opt.timeMs = std::atof(argv[++i]);
         else if (a == "--check") opt.check = true;
+        else if (a == "--nodes" && i + 1 < argc) opt.nodes = g_targetNodes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
         else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
         else {
-            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--check] [--map file.pgm] [--seed S]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--map file.pgm] [--seed S]\n", argv[0]);
             return 2;
         }
     }

@@ -791,11 +791,17 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     return MPTG_OK;
 }
 
-// (Re)build when there is no index yet or the unindexed tail has grown past a quarter of the
-// indexed prefix; the tail is scanned by brute force in between (knn.cu).
+// (Re)build when there is no index yet or the unindexed tail has grown past min(count/4, 65536) points;
+// in between the tail is scanned by brute force (knn.cu) and merged.  A device rebuild costs a few
+// milliseconds at a million points, a tail scan a few microseconds per thousand tail points and wave.
 template <typename S>
 int knnEnsureIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& sp, const S* pts, uint32_t stride, uint32_t n) {
-    if (ix.count != 0 && ix.count <= n && (n - ix.count) <= ix.count / 4) return MPTG_OK;
+    if (ix.count != 0 && ix.count <= n) {
+        const uint32_t tail = n - ix.count;
+        uint32_t limit = ix.count / 4;
+        if (limit > 65536u) limit = 65536u;
+        if (tail <= limit) return MPTG_OK;
+    }
     return knnBuildIndex<S>(ctx, ix, sp, pts, stride, n);
 }
 
