@@ -5,11 +5,15 @@
 // mpt_b200/) never includes or calls it.
 //
 // Parity status:
-//   * metric distance / interpolate: PINNED by the reference's own known-answer tests
+//   * metric distance: PINNED by the reference's own known-answer tests
 //     (test/{lp,scaled,so2,so3,se2,se3}_space_test.cpp), re-run in oracle/kat_main.cpp.
-//   * interpolate, DiscreteMotionValidator, grid / shapes / link-arm checks: arithmetic follows the
-//     in-tree reference sources line by line (cited per function).  No reference test touches them;
-//     the reference itself cannot be built here (Eigen, Nigh, FCL, libpng absent).
+//   * interpolate, DiscreteMotionValidator, grid / shapes / link-arm checks, GoalState: arithmetic follows
+//     the in-tree reference sources line by line (cited per function) and is PINNED against the
+//     reference's own code: those headers are compiled from /root/reference against stand-in
+//     Eigen/Nigh headers (oracle/ref_driver.cpp -> oracle/_ref/libref.so) and their outputs on seeded
+//     inputs are committed as tests/golden/reference_golden.npz (tests/test_reference_parity.py).
+//     Decisions are identical; interpolated quaternions agree to libm tolerance (the reference calls
+//     libm, we call mptg_fpmath.h).
 //   * kNN result order and mesh-mesh collision: PARITY UNPINNED -- the arithmetic lives in Nigh and
 //     FCL, which are not in /root/reference and not on this machine.  The oracle defines them:
 //     kNN = exact total order by (distance, insertion index); mesh = AABB-overlap && 17-axis
