@@ -177,17 +177,30 @@ struct BvhWalk {
     const S* myq;  // query in shared memory (generic path)
     S qr[7];       // query in registers (SE(3) path)
     float w0, w1;
-    float qabs;  // sum |q_i| of the query quaternion (error bound of dots against half-precision copies)
+    float qabs = 0.0f;  // sum |q_i| of the query quaternion (error bound of dots against half-precision copies)
     WarpTopK<S, KPL> top;
     int lane;
     unsigned long long leaves = 0, inner = 0;
 
     __device__ __forceinline__ BvhWalk(const BvhArgs<S>& args, const S* q, int ln) : a(args), myq(q), lane(ln) {}
 
-    __device__ __forceinline__ float threshold() const {
+    // Pruning threshold min(k-th distance, radius), cached as a float (rounded up) and refreshed after
+    // every offer; thrS is the same value divided by the slack factor of the leaf prefilter.
+    float thrF, thrS;
+    float dotC;  // 2 - slack - 2*qabs*errQ: prefilter term so that t = dotC - 2|dot_h| <= 2 - 2|dot|
+    float eT;    // sqrt(3)*errT (rounded up): |t_h - q| - eT <= |t - q|
+    __device__ __forceinline__ void refreshThr() {
         const S t = top.kthD < a.radius ? top.kthD : a.radius;
-        return thrAsFloat<S>(t);
+        thrF = thrAsFloat<S>(t);
+        thrS = thrF * (1.0f + 3e-5f);
     }
+    __device__ __forceinline__ void start() {
+        top.init(a.k);
+        refreshThr();
+        dotC = __fmaf_rn(-2.0f * qabs, a.errQ, 2.0f - 3e-6f);
+        eT = a.errT * 1.73206f;  // sqrt(3) * (1 + 5e-6)
+    }
+    __device__ __forceinline__ float threshold() const { return thrF; }
 
     // key (float bits of a lower bound) of child `lane` of `block` at level L
     template <int L>
@@ -288,6 +301,7 @@ struct BvhWalk {
                 a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
             top.offer(have, dist, orig * a.idxMul + a.idxAdd, a.radius, lane);
         }
+        refreshThr();
     }
 
     // SE(3)/f32 leaf visit split in two so the loads of the NEXT leaf can be in flight while the
@@ -325,10 +339,16 @@ struct BvhWalk {
         float dt = fp::sqrt_(s2);
         if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
         top.offer(maybe && orig != MPTG_NO_INDEX, (S)(dr + dt), orig * a.idxMul + a.idxAdd, a.radius, lane);
+        refreshThr();
     }
+    // Prefilter on the half-precision copy.  With h = the stored copy: |dot - dot_h| <= qabs*errQ and
+    // ||t - q|| >= ||t_h - q|| - sqrt(3)*errT, so
+    //   w0*sqrt(2 - 2(|dot_h| + qabs*errQ + slack)) + w1*max(||t_h - q|| - eT, 0)
+    // is a lower bound of the exact distance up to rounding; the rounding (approximate square roots
+    // 2.4e-7 relative, a few 6e-8 in the sums, and the exact distance's own) is covered by the 3e-6
+    // absolute slack inside dotC, the 1e-6 relative inflation of eT and the 3e-5 relative slack in thrS.
     __device__ __forceinline__ void leafEval(uint32_t node, const LeafData& ld) {
         ++leaves;
-        // prefilter on the half-precision copy: |dot error| <= qabs*errQ, |coordinate error| <= errT
         const float2 xy = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[0]));
         const float2 zw = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[1]));
         const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[2]));
@@ -337,24 +357,27 @@ struct BvhWalk {
         dot = __fmaf_rn(xy.y, (float)qr[1], dot);
         dot = __fmaf_rn(zw.x, (float)qr[2], dot);
         dot = __fmaf_rn(zw.y, (float)qr[3], dot);
-        const float e0 = fmaxf(fabsf(t01.x - (float)qr[4]) - a.errT, 0.0f);
-        const float e1 = fmaxf(fabsf(t01.y - (float)qr[5]) - a.errT, 0.0f);
-        const float e2 = fmaxf(fabsf(t2.x - (float)qr[6]) - a.errT, 0.0f);
-        const float s2 = __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0));
-        const float ad = fminf(1.0f, __fmaf_rn(qabs, a.errQ, fabsf(dot)));
-        const bool maybe = se3CheapBound(ad, s2, w0, w1) <= threshold();
+        const float d0 = t01.x - (float)qr[4], d1 = t01.y - (float)qr[5], d2 = t2.x - (float)qr[6];
+        const float s2 = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, d0 * d0));
+        const float sT = fmaxf(sqrtApprox(s2) - eT, 0.0f);
+        const float t = fmaxf(__fmaf_rn(-2.0f, fabsf(dot), dotC), 0.0f);
+        const bool maybe = __fmaf_rn(w0, sqrtApprox(t), w1 * sT) <= thrS;
         if (!__any_sync(FULL_MASK, maybe)) return;
         leafExact(node, maybe);  // rare: fetch the exact points and evaluate the true distance
     }
 
     // take the child with the smallest remaining bound; false when none is left within the threshold
-    __device__ __forceinline__ bool pick(uint32_t& key, uint32_t block, uint32_t& node) const {
-        const uint32_t best = __reduce_min_sync(FULL_MASK, key);
-        if (best == BVH_DEAD || __uint_as_float(best) > threshold()) return false;
+    __device__ __forceinline__ bool pick(uint32_t& key, uint32_t block, uint32_t& node, uint32_t& best) const {
+        best = __reduce_min_sync(FULL_MASK, key);
+        if (best == BVH_DEAD || __uint_as_float(best) > thrF) return false;
         const int src = __ffs(__ballot_sync(FULL_MASK, key == best)) - 1;
         if (lane == src) key = BVH_DEAD;
         node = block * 32u + (uint32_t)src;
         return true;
+    }
+    __device__ __forceinline__ bool pick(uint32_t& key, uint32_t block, uint32_t& node) const {
+        uint32_t best;
+        return pick(key, block, node, best);
     }
 
     // visit the children (level L nodes) of `block`, nearest bound first
@@ -363,23 +386,22 @@ struct BvhWalk {
         uint32_t key = childKey<L>(block);
         uint32_t node;
         if (L == 0 && SHAPE == SHAPE_SE3 && sizeof(S) == 4 && a.leafH != nullptr) {
-            LeafData cur, nxt;
-            if (!pick(key, block, node)) return;
-            leafLoad(node, cur);
+            // Software pipeline over two register sets: the next leaf is chosen (and its loads issued)
+            // against the threshold BEFORE the current leaf is evaluated; if that evaluation tightens the
+            // threshold past the chosen leaf's bound, it and every remaining child (bounds >= its) are dropped.
+            LeafData da, db;
+            uint32_t nodeB, ka, kb;
+            if (!pick(key, block, node, ka)) return;
+            leafLoad(node, da);
             for (;;) {
-                // the next leaf is chosen (and its loads issued) against the threshold BEFORE the current
-                // leaf is evaluated; if that evaluation tightens the threshold past it, it is dropped below
-                const uint32_t keyBefore = key;
-                uint32_t nextNode;
-                const bool haveNext = pick(key, block, nextNode);
-                if (haveNext) leafLoad(nextNode, nxt);
-                leafEval(node, cur);
-                if (!haveNext) return;
-                // re-check the picked leaf's bound against the (possibly smaller) threshold
-                const uint32_t nb = __reduce_min_sync(FULL_MASK, keyBefore);
-                if (__uint_as_float(nb) > threshold()) return;  // every remaining bound is >= nb
-                cur = nxt;
-                node = nextNode;
+                bool more = pick(key, block, nodeB, kb);
+                if (more) leafLoad(nodeB, db);
+                leafEval(node, da);
+                if (!more || __uint_as_float(kb) > thrF) return;
+                more = pick(key, block, node, ka);
+                if (more) leafLoad(node, da);
+                leafEval(nodeB, db);
+                if (!more || __uint_as_float(ka) > thrF) return;
             }
         } else {
             while (pick(key, block, node)) {
@@ -485,7 +507,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
         w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
         w.qabs = fabsf((float)myq[0]) + fabsf((float)myq[1]) + fabsf((float)myq[2]) + fabsf((float)myq[3]);
     }
-    w.top.init(a.k);
+    w.start();
     switch (a.top) {
         case 0: w.template descend<0>(0); break;
         case 1: w.template descend<1>(0); break;
