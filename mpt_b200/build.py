@@ -28,7 +28,7 @@ FLAGS = [
     "-ccbin", "/usr/bin/g++",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-Xptxas", "-warn-spills",
-]
+] + os.environ.get("MPTG_NVCC_EXTRA", "").split()  # kernel experiments: extra -D flags
 
 
 def sources():

@@ -10,6 +10,9 @@
 // L (rooted at depth five) depth first with an explicit stack; a warp vote per iteration stops all
 // lanes at the first invalid probe.  All midpoints are produced by the same sequence of
 // floating point operations as the reference's recursion, so decisions are bit-identical.
+#include <cstdio>
+#include <cstdlib>
+
 #include "geom.cuh"
 
 namespace mptg {
@@ -539,7 +542,7 @@ int mptg_linkarm_create(mptg_ctx* ctx, int scalar, int32_t nLinks, const double*
 int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris,
                           mptg_geom** out) {
     if (!ctx || !out || (nr && !robotTris) || (ne && !envTris)) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_mesh_pair_create: bad argument");
-    if (scalar != MPTG_F32) return fail(ctx, MPTG_ERR_UNSUPPORTED, "mptg_mesh_pair_create: only MPTG_F32 meshes are supported");
+    if (scalar != MPTG_F32 && scalar != MPTG_F64) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_mesh_pair_create: scalar must be MPTG_F32 or MPTG_F64");
     MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
     mptg_geom* g;
     int rc = newGeom(ctx, MPTG_GEOM_MESH, scalar, &g);
@@ -603,6 +606,9 @@ static int checkDeviceErrors(mptg_geom* g) {
     MPTG_CUDA(g->ctx, cudaMemcpyAsync(host, g->devStats, sizeof host, cudaMemcpyDeviceToHost, g->ctx->stream));
     MPTG_CUDA(g->ctx, cudaStreamSynchronize(g->ctx->stream));
     for (int i = 0; i < 4; ++i) g->stats[i] = host[i];
+    if (getenv("MPTG_DEBUG_STATS"))
+        fprintf(stderr, "[mptg] geom stats: states %llu bv %llu prim %llu items %llu | dbg %llu %llu %llu\n", host[0], host[1], host[2],
+                host[3], host[5], host[6], host[7]);
     if (host[4] & GEOM_ERR_STACK) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: traversal stack overflow (edge too long / geometry too deep)");
     if (host[4] & GEOM_ERR_STEPS) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: too many interpolation steps on one edge");
     return MPTG_OK;

@@ -10,12 +10,18 @@
 // the hierarchy.  Vertex transform and the SAT use plain, unfused arithmetic in a fixed order; the
 // box tests use fused arithmetic freely.
 //
-// Execution: one warp per work item (a state, or an edge whose states are visited in the
-// reference's bisection order with its early exit).  Warps pull items from a global counter, so
-// long and short items balance.  The simultaneous descent of the two binary AABB trees is
-// breadth-limited: the warp keeps a stack of node pairs in shared memory, each round the 32 lanes
-// test up to 32 pairs from the top and push the surviving children; leaf-leaf survivors go to a
-// triangle-pair queue that is drained 32 at a time so the SAT runs without divergence.
+// Execution: persistent warps over a flat list of states (see "flat work list" below): every warp keeps
+// up to 32 states of any items in flight and its 32 lanes test node pairs from one mixed frontier held
+// in shared memory; leaf-leaf survivors go to a triangle-pair queue that is drained 32 at a time so the
+// SAT runs without divergence.  States arrive as float or double (the edge discretisation runs in the
+// state's scalar type); the collision test itself is always float, on the pose rounded to float.
+// #define MESH_DEBUG_STATS 1
+#include <cub/device/device_scan.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+
 #include "geom.cuh"
 
 namespace mptg {
@@ -40,20 +46,34 @@ struct MeshDev {
 
 }  // namespace mptg
 
+namespace mptg {
+struct DonBlock;
+}
 struct MeshData {
     mptg::MeshDev dev{};
     void* mem[4] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned int* workCounter = nullptr;
+    unsigned long long* workCounter = nullptr;  // [0] pass 1 / states, [1] pass 2; followed by the donation control words
+    mptg::DonBlock* poolBlocks = nullptr;
     int depthR = 0, depthE = 0;
+    // per-edge work buffers of link batches (grow-only)
+    uint32_t* steps = nullptr;
+    unsigned long long* counts = nullptr;
+    unsigned long long* offs = nullptr;
+    void* scanTemp = nullptr;
+    size_t scanBytes = 0;
+    uint32_t workEdges = 0;
 };
 
 namespace mptg {
 
 constexpr int MESH_WARPS = 4;
-constexpr int MESH_MIN_CTAS = 8;  // 32 warps per SM: caps registers at 64
+#ifndef MESH_CTAS
+#define MESH_CTAS 6
+#endif
+constexpr int MESH_MIN_CTAS = MESH_CTAS;  // resident CTAs per SM (caps registers per thread)
 constexpr int NODE_STACK = 512;
+constexpr int STACK_SOFT = NODE_STACK - 64 - 60;  // see the pop rule in meshFlatKernel
 constexpr int TRI_QUEUE = 64;
-constexpr int DMV_QUEUE = 256;  // fixedBisectQueueSize_, discrete_motion_validator.hpp:54
 
 struct WarpCounters {
     unsigned int bv = 0, tri = 0, states = 0;  // per lane (bv, tri) / per warp (states); summed into 64-bit totals at exit
@@ -155,36 +175,369 @@ __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
     return n;
 }
 
-// Collision test of up to MESH_SLOTS rigid-body states at once by a full warp.  The states' transforms
-// (R row-major 9 floats, t 3 floats) sit in shared memory, xf[slot][12]; every stack / queue entry
-// carries its slot in the top 4 bits of the robot index, so the 32 lanes always draw from one mixed
-// frontier and stay busy while a single state's frontier is still narrow.  Returns the mask of slots
-// found in collision; with stopAtFirst it returns as soon as any slot collides (edge checks: one
-// invalid state invalidates the edge).
-// err: set to GEOM_ERR_STACK if the pair stack would overflow.
-constexpr int MESH_SLOTS = 8;
-constexpr unsigned SLOT_SHIFT = 28;
+// ------------------------------------------------------------------ flat work list + mixed frontier
+// Work is a flat list of rigid-body states, each belonging to an ITEM (a state of a valid() batch, or an
+// edge of a link() batch).  A warp keeps up to MESH_SLOTS states in flight: their transforms sit in
+// shared memory (R row-major, t), and every stack / queue entry carries its slot in the top 5 bits of the
+// robot index, so the 32 lanes draw BV pair tests from ONE mixed frontier.  Whenever the frontier gets
+// narrow (<= REFILL_AT pairs) the warp pulls more work ids from a global counter into the slots that
+// have nothing pending, so lanes stay busy across states and across edges.  The first collision found
+// for an item clears ok[item]; its remaining pairs are dropped, and states of an edge already known to
+// be invalid are skipped when they are pulled.
+//
+// Edges (DiscreteMotionValidator::operator(), src/mpt/discrete_motion_validator.hpp:71-130): the
+// reference's decision is  valid(to) && AND_{i=1..steps-1} valid(interpolate(from, to, i * (1/steps)))
+// with steps = ceil(distance * (1/stepSize)) (:64,:78,:82); its bisection queue (:99-126) only fixes the
+// ORDER in which that set is visited, i.e. how early an invalid edge is abandoned.  The decision is
+// order-independent, so the same set is enumerated here coarse-to-fine over ALL edges in one list:
+//   first 8 ids per edge -- `to`, then the multiples of P/8 inside 1..steps-1 in bisection order
+//         (P = max(8, steps rounded up to a power of two)),
+//   then, for the edges with steps > 8, their other interior indices (located through a prefix sum of
+//         the per-edge counts); by the time these are pulled the coarse states of the edge have been
+//         checked, and an edge already found invalid is skipped.
+constexpr int MESH_SLOTS = 32;
+constexpr unsigned SLOT_SHIFT = 27;
 constexpr unsigned NODE_MASK = (1u << SLOT_SHIFT) - 1u;
+constexpr int XF_STRIDE = 13;   // odd stride: lanes reading different slots hit different banks
+constexpr int REFILL_AT = 16;   // refill when at most this many node pairs are pending
+constexpr int REFILL_MAX = 16;  // states started per refill
+constexpr int COARSE_IDS = 8;   // work ids per edge in pass 1
 
-__device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (*xf)[12], uint2* stack, uint2* triQ, int lane,
-                                     bool stopAtFirst, WarpCounters& cnt, unsigned long long& err) {
-    if (m.nR == 0 || m.nE == 0 || nSlots == 0) return 0u;
-    const unsigned allMask = (1u << nSlots) - 1u;
-    unsigned hitMask = 0u;
-    int n = nSlots, nt = 0;
-    if (lane < nSlots) stack[lane] = make_uint2((unsigned)lane << SLOT_SHIFT, 0u);
-    __syncwarp();
+enum { WORK_STATES = 0, WORK_EDGES = 1 };
+
+template <typename S>
+struct MeshWork {
+    const S* a;     // states (WORK_STATES) / edge starts
+    const S* b;     // edge ends
+    uint32_t n;     // states / edges
+    const uint32_t* steps;           // per edge
+    const unsigned long long* offs;  // exclusive prefix sums of the per-edge counts of non-coarse states, n+1 entries
+    uint8_t* ok;                     // per item, preset to 1
+    DevSpace<S> sp;
+};
+
+// ---- work donation between warps.  A few states (deep contact, long grazing passes) need thousands of
+// pair tests; left to the warp that pulled them they become the tail of the launch.  Once the work list
+// is exhausted, warps with nothing left register as idle, and a warp whose stack is deep hands the
+// OLDEST half of it (the largest subtrees) to an idle one through a ring of blocks in global memory.  A
+// block carries the donor's whole slot table (transforms + items), so the receiver -- which is empty --
+// adopts it as is.  Both sides may then work on the same state; a hit by either clears ok[item], which
+// the other notices at its next periodic look at ok[] (also how warps learn that ANOTHER warp has
+// already invalidated an edge).
+// tuned on the C5 edge wave (B200): see profiles/r1_mesh_donation_tuning.txt
+#ifndef MESH_DON_MAX
+#define MESH_DON_MAX 128
+#define MESH_DON_MIN 64
+#define MESH_DON_KEEP 32
+#define MESH_DON_EVERY 3u
+#define MESH_MAX_POLLERS 128
+#endif
+constexpr int DON_MAX = MESH_DON_MAX;        // pairs per block
+constexpr int DON_MIN_STACK = MESH_DON_MIN;  // only stacks at least this deep are split
+constexpr int DON_KEEP = MESH_DON_KEEP;       // pairs the donor keeps (the newest: its next round)
+constexpr unsigned POOL_BLOCKS = 8192;  // ring size: more than the waiters plus one block per warp that can donate at once
+enum { CTL_HEAD = 0, CTL_TAIL = 1, CTL_IDLE = 2, CTL_STARTED = 3, CTL_WORDS = 32 };  // one 128-byte line per pass
+constexpr unsigned MAX_POLLERS = MESH_MAX_POLLERS;  // idle warps that queue for donated work; the others leave
+
+struct DonBlock {
+    float xf[MESH_SLOTS * 12];
+    uint32_t items[MESH_SLOTS];
+    uint2 pairs[DON_MAX];
+    uint32_t count, dead, pad0, pad1;
+};
+
+struct MeshPool {
+    DonBlock* blocks;
+    unsigned int* ctl;    // CTL_WORDS
+    unsigned int* ready;  // POOL_BLOCKS sequence numbers (0 = empty)
+};
+
+// control block: the two work counters (u64) on lines of their own, then per pass CTL_WORDS control words and
+// POOL_BLOCKS ready flags
+constexpr size_t CTL_COUNTER_STRIDE = 16;  // u64 units: 128 bytes between the counters
+constexpr size_t CTL_PASS_WORDS = CTL_WORDS + POOL_BLOCKS;
+constexpr size_t CTL_BYTES = 2 * CTL_COUNTER_STRIDE * sizeof(unsigned long long) + 2 * CTL_PASS_WORDS * sizeof(unsigned int);
+
+__device__ __forceinline__ unsigned int volLoad(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+
+__device__ __forceinline__ uint32_t pow2AtLeast8(uint32_t steps) {  // steps <= 2^31
+    return steps <= 8u ? 8u : (1u << (32 - __clz(steps - 1u)));
+}
+
+// state -> transform in shared memory (lane-private work: one lane per slot)
+__device__ __forceinline__ void storeTransform(const float* q, float* X) {
+    float R[9];
+    quatToRot(q, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) X[k] = R[k];
+    X[9] = q[4], X[10] = q[5], X[11] = q[6];
+}
+
+// Decode one work id into (item, transform).  false: nothing to check (a hole of the enumeration, or an
+// edge already known to be invalid).
+template <typename S, int MODE>
+__device__ __forceinline__ bool decodeWork(const MeshWork<S>& w, unsigned long long id, uint32_t& item, float* X) {
+    S q[7];
+    if (MODE == WORK_STATES) {
+        item = (uint32_t)id;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) q[c] = __ldg(w.a + (size_t)item * 7 + c);
+    } else {
+        uint32_t e, i = 0;
+        const unsigned long long nCoarse = (unsigned long long)w.n * COARSE_IDS;
+        if (id < nCoarse) {
+            e = (uint32_t)(id / COARSE_IDS);
+            const uint32_t j = (uint32_t)(id % COARSE_IDS);
+            const uint32_t steps = __ldg(w.steps + e);
+            if (j != 0) {
+                if (steps < 2u) return false;
+                const int l = 31 - __clz(j);  // bisection level 0..2, k-th node of the level
+                const uint32_t k = j - (1u << l);
+                i = (2u * k + 1u) * (pow2AtLeast8(steps) >> (l + 1));
+                if (i > steps - 1u) return false;
+            }
+        } else {
+            const unsigned long long r = id - nCoarse;
+            uint32_t lo = 0, hi = w.n;  // largest e with offs[e] <= r (offs[n] = total > r)
+            while (hi - lo > 1u) {
+                const uint32_t mid = lo + (hi - lo) / 2u;
+                if (__ldg(w.offs + mid) <= r) lo = mid;
+                else hi = mid;
+            }
+            e = lo;
+            i = (uint32_t)(r - __ldg(w.offs + e)) + 1u;
+            if (i % (pow2AtLeast8(__ldg(w.steps + e)) >> 3) == 0u) return false;  // one of the coarse states
+        }
+        if (__ldcg(w.ok + e) == 0) return false;
+        item = e;
+        if (i == 0) {  // :75 valid(to)
+#pragma unroll
+            for (int c = 0; c < 7; ++c) q[c] = __ldg(w.b + (size_t)e * 7 + c);
+        } else {  // :82,:110 interpolate(from, to, i * delta), delta = 1 / steps
+            S a[7], b[7];
+#pragma unroll
+            for (int c = 0; c < 7; ++c) a[c] = __ldg(w.a + (size_t)e * 7 + c), b[c] = __ldg(w.b + (size_t)e * 7 + c);
+            const S delta = fp::div_(S(1), (S)__ldg(w.steps + e));
+            dev::interpolate<S>(w.sp, a, b, (S)i * delta, q);
+        }
+    }
+    float qf[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) qf[c] = (float)q[c];
+    storeTransform(qf, X);
+    return true;
+}
+
+__device__ __forceinline__ void flushCounters(WarpCounters& c, unsigned long long err, unsigned long long* stats, int lane) {
+    unsigned long long bv = c.bv, tri = c.tri;
+    for (int o = 16; o > 0; o >>= 1) {
+        bv += __shfl_down_sync(FULL_MASK_, bv, o);
+        tri += __shfl_down_sync(FULL_MASK_, tri, o);
+    }
+    if (lane == 0) {
+        atomicAdd(stats + 0, (unsigned long long)c.states);
+        atomicAdd(stats + 1, bv);
+        atomicAdd(stats + 2, tri);
+        if (err) atomicOr(stats + 4, err);
+    }
+}
+
+#ifdef MESH_DEBUG_STATS
+__device__ unsigned long long gDbgT[3][8192][8];  // per mode, per warp: start, end, rounds, bv, tri, states, tri rounds
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+template <typename S, int MODE>
+__global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel(MeshDev m, MeshWork<S> w, unsigned long long* counter,
+                                                                                MeshPool pool, unsigned long long* stats) {
+    __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
+    __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
+    __shared__ float sXf[MESH_WARPS][MESH_SLOTS][XF_STRIDE];
+    __shared__ uint32_t sItem[MESH_WARPS][MESH_SLOTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    while (n > 0 || nt > 0) {
+    uint2* stack = sStack[warp];
+    uint2* triQ = sTri[warp];
+    float(*xf)[XF_STRIDE] = sXf[warp];
+    uint32_t* items = sItem[warp];
+    const unsigned long long total =
+        MODE == WORK_STATES ? (unsigned long long)w.n : (unsigned long long)w.n * COARSE_IDS + __ldg(w.offs + w.n);
+    const unsigned long long nWarps = (unsigned long long)gridDim.x * MESH_WARPS;
+    WarpCounters cnt;
+    unsigned long long err = 0;
+    unsigned dead = 0u;  // slots whose item is already decided: their pending pairs are dropped
+    int n = 0, nt = 0;
+    bool exhausted = total == 0;
+    unsigned roundNo = 0;
+    unsigned fresh = 0xffffffffu;  // slots (re)filled since ok[] was last requested
+    unsigned ctlSeen = 0u;
+    uint8_t okSeen = 1;
+    items[lane] = 0;
+    if (lane == 0) atomicAdd(pool.ctl + CTL_STARTED, 1u);
+    __syncwarp();
+#ifdef MESH_DEBUG_STATS
+    unsigned long long dbgRounds = 0, dbgThrottled = 0, dbgTriRounds = 0, dbgAdopted = 0, dbgDonated = 0;
+    int dbgMaxN = 0;
+    const unsigned long long dbgT0 = gtimer();
+    unsigned long long dbgIdleT = 0, dbgSpin = 0, dbgPoll = 0;
+#endif
+    for (;;) {
+        if (!exhausted && n <= REFILL_AT) {
+            // slots with nothing pending in the stack or the triangle queue are free
+            unsigned bits = 0u;
+            if (lane < n) bits |= 1u << (stack[lane].x >> SLOT_SHIFT);
+            if (lane < nt) bits |= 1u << (triQ[lane].x >> SLOT_SHIFT);
+            if (lane + 32 < nt) bits |= 1u << (triQ[lane + 32].x >> SLOT_SHIFT);
+            const unsigned freeSlots = ~__reduce_or_sync(FULL_MASK_, bits);
+            // near the end of the list take smaller bites so that the warps finish together
+            unsigned long long base = 0;
+            int cap = 0;
+            if (lane == 0) {
+                const unsigned long long cur = *(volatile unsigned long long*)counter;
+                const unsigned long long share = cur < total ? (total - cur) / nWarps + 1ull : 1ull;
+                cap = (int)(share < 4ull ? 4ull : (share > (unsigned long long)REFILL_MAX ? (unsigned long long)REFILL_MAX : share));
+                const int avail = __popc(freeSlots);
+                cap = cap < avail ? cap : avail;
+                if (cap > 0) base = atomicAdd(counter, (unsigned long long)cap);
+            }
+            cap = __shfl_sync(FULL_MASK_, cap, 0);
+            base = __shfl_sync(FULL_MASK_, base, 0);
+            if (cap > 0) {
+                const int rank = __popc(freeSlots & ltMask);
+                const bool take = ((freeSlots >> lane) & 1u) && rank < cap && base + (unsigned long long)rank < total;
+                bool push = false;
+                if (take) {
+                    uint32_t item;
+                    push = decodeWork<S, MODE>(w, base + (unsigned long long)rank, item, xf[lane]);
+                    if (push) items[lane] = item;
+                }
+                const unsigned mp = __ballot_sync(FULL_MASK_, push);
+                dead &= ~mp;
+                fresh |= mp;
+                if (push) stack[n + __popc(mp & ltMask)] = make_uint2((unsigned)lane << SLOT_SHIFT, 0u);
+                n += __popc(mp);
+                cnt.states += __popc(mp);
+                if (base + (unsigned long long)cap >= total) exhausted = true;
+                __syncwarp();
+            }
+        }
+        if (n == 0 && nt == 0) {
+            if (!exhausted) continue;
+            // Nothing left here: queue for donated work (ticket = position in the ring), unless enough warps
+            // are queueing already.  CTL_IDLE counts the idle warps MINUS the blocks handed out and not yet
+            // picked up (the donor subtracts one per block), so IDLE >= STARTED means: every warp is idle and
+            // no block is pending -- nothing can arrive any more.  Each waiter spins on its own ready flag.
+            unsigned got = 0xffffffffu;
+#ifdef MESH_DEBUG_STATS
+            if (dbgIdleT == 0) dbgIdleT = gtimer();
+#endif
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(pool.ctl + CTL_IDLE, 1u);
+                const int waiting = (int)(volLoad(pool.ctl + CTL_TAIL) - volLoad(pool.ctl + CTL_HEAD));  // < 0: blocks pending
+                if (waiting < (int)MAX_POLLERS) {
+                    const unsigned my = atomicAdd(pool.ctl + CTL_TAIL, 1u);
+                    const unsigned* flag = pool.ready + my % POOL_BLOCKS;
+                    for (unsigned it = 0;; ++it) {
+                        if (volLoad(flag) == my + 1u) {
+                            got = my;
+                            break;
+                        }
+                        if ((it & 3u) == 3u && (int)volLoad(pool.ctl + CTL_IDLE) >= (int)volLoad(pool.ctl + CTL_STARTED)) break;  // signed: IDLE dips below zero while blocks outnumber idle warps
+                        __nanosleep(500);
+#ifdef MESH_DEBUG_STATS
+                        ++dbgPoll;
+#endif
+                    }
+                }
+            }
+            got = __shfl_sync(FULL_MASK_, got, 0);
+            if (got == 0xffffffffu) break;
+            const unsigned bi = got % POOL_BLOCKS;
+            __syncwarp();
+            __threadfence();
+            const DonBlock* blk = pool.blocks + bi;
+            for (int i = lane; i < MESH_SLOTS * 12; i += 32) xf[i / 12][i % 12] = __ldcg(blk->xf + i);
+            items[lane] = __ldcg(blk->items + lane);
+            n = (int)__ldcg(&blk->count);
+            dead = __ldcg(&blk->dead);
+            for (int i = lane; i < n; i += 32) stack[i] = __ldcg(blk->pairs + i);
+            fresh = 0xffffffffu;
+            __syncwarp();
+#ifdef MESH_DEBUG_STATS
+            ++dbgAdopted;
+#endif
+            continue;
+        }
+        if ((++roundNo & MESH_DON_EVERY) == 0u) {
+            // Every 8th round: a look at ok[] (items invalidated by another warp are finished here too) and at
+            // the donation ring.  The values used are the ones requested at the PREVIOUS look, so the loads
+            // never stall the traversal; slots refilled since then are skipped.
+            dead |= __ballot_sync(FULL_MASK_, okSeen == 0) & ~fresh;
+            fresh = 0u;
+            okSeen = __ldcg(w.ok + items[lane]);
+            const int waiting = (int)(__shfl_sync(FULL_MASK_, ctlSeen, 0) - __shfl_sync(FULL_MASK_, ctlSeen, 1));  // TAIL - HEAD
+            if (lane < 2 && n >= DON_MIN_STACK / 2 + 8) ctlSeen = volLoad(pool.ctl + (lane == 0 ? CTL_TAIL : CTL_HEAD));
+            bool donate = n >= DON_MIN_STACK && waiting > 0;
+            if (donate) {  // confirm on fresh values (rare path); a few warps may overshoot, those blocks wait for the next idle warp
+                unsigned v = 0u;
+                if (lane < 2) v = volLoad(pool.ctl + (lane == 0 ? CTL_TAIL : CTL_HEAD));
+                donate = (int)(__shfl_sync(FULL_MASK_, v, 0) - __shfl_sync(FULL_MASK_, v, 1)) > 0;
+            }
+            {
+                if (donate) {
+                    const int d = n - DON_KEEP < DON_MAX ? n - DON_KEEP : DON_MAX;
+                    unsigned idx = 0;
+                    if (lane == 0) {
+                        idx = atomicAdd(pool.ctl + CTL_HEAD, 1u);
+                        atomicSub(pool.ctl + CTL_IDLE, 1u);  // on behalf of the warp that will pick the block up
+                    }
+                    idx = __shfl_sync(FULL_MASK_, idx, 0);
+                    DonBlock* blk = pool.blocks + idx % POOL_BLOCKS;
+                    for (int i = lane; i < d; i += 32) blk->pairs[i] = stack[i];
+                    for (int i = lane; i < MESH_SLOTS * 12; i += 32) blk->xf[i] = xf[i / 12][i % 12];
+                    blk->items[lane] = items[lane];
+                    if (lane == 0) blk->count = (uint32_t)d, blk->dead = dead;
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) *(volatile unsigned int*)(pool.ready + idx % POOL_BLOCKS) = idx + 1u;
+                    for (int base = 0; base < n - d; base += 32) {  // close the gap
+                        uint2 e = make_uint2(0u, 0u);
+                        if (base + lane < n - d) e = stack[d + base + lane];
+                        __syncwarp();
+                        if (base + lane < n - d) stack[base + lane] = e;
+                        __syncwarp();
+                    }
+                    n -= d;
+#ifdef MESH_DEBUG_STATS
+                    ++dbgDonated;
+#endif
+                }
+            }
+        }
         if (n > 0) {
-            const int p = (n > NODE_STACK - 160) ? 1 : (n < 32 ? n : 32);
+            // Pop up to 32 pairs, fewer as the stack nears STACK_SOFT (each pop pushes at most two); from
+            // STACK_SOFT on it is one pair per round, a depth-first descent that can add at most
+            // depthR + depthE <= 56 more entries (checked at creation), which stays below the hard limit.
+            int p = STACK_SOFT - n;
+            p = p < 1 ? 1 : (p > 32 ? 32 : p);
+            p = p < n ? p : n;
+#ifdef MESH_DEBUG_STATS
+            ++dbgRounds;
+            if (p < 32 && p < n) ++dbgThrottled;
+            if (n > dbgMaxN) dbgMaxN = n;
+#endif
             bool mine = lane < p;
             uint2 pr = make_uint2(0u, 0u);
             if (mine) pr = stack[n - 1 - lane];
             __syncwarp();
             n -= p;
             const unsigned slot = pr.x >> SLOT_SHIFT;
-            mine = mine && !((hitMask >> slot) & 1u);  // pairs of a state already known to collide are dropped
+            mine = mine && !((dead >> slot) & 1u);
             int kind = 0;  // 1: triangle pair, 2: expand robot node, 3: expand env node
             int c0 = 0, c1 = 0;
             if (mine) {
@@ -192,24 +545,36 @@ __device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (
                 const BvhNode b = loadNode(m.eNodes, (int)pr.y);
                 const float* X = xf[slot];
                 ++cnt.bv;
-                // world AABB of the rotated local box: centre +- |R| h, padded
+                // robot box (centre c, half extents h in the robot frame) against the env box, separating
+                // axes = the three world axes and the three robot-frame axes; all bounds padded
                 const float cx = 0.5f * (a.lo[0] + a.hi[0]), cy = 0.5f * (a.lo[1] + a.hi[1]), cz = 0.5f * (a.lo[2] + a.hi[2]);
                 const float hx = 0.5f * (a.hi[0] - a.lo[0]), hy = 0.5f * (a.hi[1] - a.lo[1]), hz = 0.5f * (a.hi[2] - a.lo[2]);
-                bool ov = true;
+                float R[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = X[k];
+                float d[3], hb[3], hw[3];
                 float mag = 0.0f;
-                float cw[3], hw[3];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float r0 = X[3 * r], r1 = X[3 * r + 1], r2 = X[3 * r + 2];
-                    cw[r] = __fmaf_rn(r2, cz, __fmaf_rn(r1, cy, __fmaf_rn(r0, cx, X[9 + r])));
-                    hw[r] = __fmaf_rn(fabsf(r2), hz, __fmaf_rn(fabsf(r1), hy, fabsf(r0) * hx));
-                    mag += fabsf(cw[r]) + hw[r];
+                    const float cw = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, X[9 + r])));
+                    hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
+                    const float cb = 0.5f * (b.lo[r] + b.hi[r]);
+                    hb[r] = 0.5f * (b.hi[r] - b.lo[r]);
+                    d[r] = cb - cw;
+                    mag += (fabsf(cw) + hw[r]) + (fabsf(cb) + hb[r]);
                 }
                 const float pad = 64.0f * 1.1920928955078125e-07f * mag;
+                bool ov = true;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float lo = cw[r] - hw[r] - pad, hi = cw[r] + hw[r] + pad;
-                    ov = ov && !(lo > b.hi[r] || b.lo[r] > hi);
+                for (int r = 0; r < 3; ++r) ov = ov && !(fabsf(d[r]) > hw[r] + hb[r] + pad);
+                if (ov) {
+                    const float ha[3] = {hx, hy, hz};
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {  // robot-frame axis j = column j of R
+                        const float dl = __fmaf_rn(R[6 + j], d[2], __fmaf_rn(R[3 + j], d[1], R[j] * d[0]));
+                        const float el = __fmaf_rn(fabsf(R[6 + j]), hb[2], __fmaf_rn(fabsf(R[3 + j]), hb[1], fabsf(R[j]) * hb[0]));
+                        ov = ov && !(fabsf(dl) > ha[j] + el + pad);
+                    }
                 }
                 if (ov) {
                     const bool leafA = a.left < 0, leafB = b.left < 0;
@@ -221,11 +586,7 @@ __device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (
                         bool descendRobot;
                         if (leafA) descendRobot = false;
                         else if (leafB) descendRobot = true;
-                        else {
-                            const float ea = 2.0f * fmaxf(hx, fmaxf(hy, hz));
-                            const float eb = fmaxf(b.hi[0] - b.lo[0], fmaxf(b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]));
-                            descendRobot = ea > eb;
-                        }
+                        else descendRobot = fmaxf(hx, fmaxf(hy, hz)) > fmaxf(hb[0], fmaxf(hb[1], hb[2]));
                         if (descendRobot) {
                             kind = 2;
                             c0 = a.left;
@@ -256,18 +617,22 @@ __device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (
             n += 2 * __popc(mx);
             if (n > NODE_STACK - 64) {  // cannot happen with the throttle above unless trees are > ~60 deep
                 err |= GEOM_ERR_STACK;
-                return allMask;
+                if (lane == 0) atomicAdd(pool.ctl + CTL_IDLE, 1u);  // leaving: keep the termination count right
+                break;
             }
             __syncwarp();
         }
-        if (nt >= 32 || (n == 0 && nt > 0)) {
+        if (nt >= 32 || (n == 0 && nt > 0 && exhausted)) {
             const int p = nt < 32 ? nt : 32;
+#ifdef MESH_DEBUG_STATS
+            ++dbgTriRounds;
+#endif
             bool mine = lane < p;
             unsigned hitBit = 0u;
             uint2 tp = make_uint2(0u, 0u);
             if (mine) tp = triQ[nt - 1 - lane];
             const unsigned slot = tp.x >> SLOT_SHIFT;
-            mine = mine && !((hitMask >> slot) & 1u);
+            mine = mine && !((dead >> slot) & 1u);
             if (mine) {
                 ++cnt.tri;
                 const float* X = xf[slot];
@@ -297,175 +662,59 @@ __device__ unsigned warpCollideMulti(const MeshDev& m, int nSlots, const float (
             }
             __syncwarp();
             nt -= p;
-            hitMask |= __reduce_or_sync(FULL_MASK_, hitBit);
-            if (hitMask && (stopAtFirst || hitMask == allMask)) return hitMask;
+            const unsigned hits = __reduce_or_sync(FULL_MASK_, hitBit) & ~dead;
+            if (hits) {
+                if ((hits >> lane) & 1u) w.ok[items[lane]] = 0;  // lane s reports slot s
+                // every slot working on the same item is finished too (stale items of free slots may match: harmless)
+                const unsigned same = __match_any_sync(FULL_MASK_, items[lane]);
+                dead |= __ballot_sync(FULL_MASK_, (same & hits) != 0u);
+            }
         }
     }
-    return hitMask;
-}
-
-__device__ __forceinline__ uint32_t fetchItems(unsigned int* counter, uint32_t count, int lane) {
-    uint32_t i = 0;
-    if (lane == 0) i = atomicAdd(counter, count);
-    return __shfl_sync(FULL_MASK_, i, 0);
-}
-
-__device__ __forceinline__ void flushCounters(WarpCounters& c, unsigned long long err, unsigned long long* stats, int lane) {
-    unsigned long long bv = c.bv, tri = c.tri;
-    for (int o = 16; o > 0; o >>= 1) {
-        bv += __shfl_down_sync(FULL_MASK_, bv, o);
-        tri += __shfl_down_sync(FULL_MASK_, tri, o);
+#ifdef MESH_DEBUG_STATS
+    {
+        unsigned bvw = cnt.bv, triw = cnt.tri;
+        for (int o = 16; o > 0; o >>= 1) bvw += __shfl_down_sync(FULL_MASK_, bvw, o), triw += __shfl_down_sync(FULL_MASK_, triw, o);
+        const unsigned gw = blockIdx.x * MESH_WARPS + warp;
+        if (lane == 0 && gw < 8192) gDbgT[MODE][gw][3] = bvw, gDbgT[MODE][gw][4] = triw;
     }
+#endif
+    flushCounters(cnt, err, stats, lane);
+#ifdef MESH_DEBUG_STATS
     if (lane == 0) {
-        atomicAdd(stats + 0, (unsigned long long)c.states);
-        atomicAdd(stats + 1, bv);
-        atomicAdd(stats + 2, tri);
-        if (err) atomicOr(stats + 4, err);
+        atomicAdd(stats + 5, dbgRounds);
+        atomicAdd(stats + 6, dbgThrottled);
+        atomicMax(stats + 7, (unsigned long long)dbgRounds);
+        const unsigned gw = blockIdx.x * MESH_WARPS + warp;
+        if (gw < 8192) gDbgT[MODE][gw][0] = dbgT0, gDbgT[MODE][gw][1] = gtimer(), gDbgT[MODE][gw][2] = dbgRounds, gDbgT[MODE][gw][5] = (dbgSpin << 32) | dbgPoll, gDbgT[MODE][gw][6] = dbgIdleT, gDbgT[MODE][gw][7] = (dbgAdopted << 32) | dbgDonated;
+        atomicMax(stats + 3, (unsigned long long)cnt.states);
     }
+#endif
 }
 
-// state -> transform in shared memory (lane-private work: one lane per slot)
-__device__ __forceinline__ void storeTransform(const float* q, float* X) {
-    float R[9];
-    quatToRot(q, R);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) X[k] = R[k];
-    X[9] = q[4], X[10] = q[5], X[11] = q[6];
-}
-
-// ------------------------------------------------------------------ valid(q) for a batch of states
-__global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshValidKernel(MeshDev m, const float* __restrict__ states, uint32_t n,
-                                                                   uint8_t* __restrict__ ok, unsigned int* counter,
-                                                                   unsigned long long* stats) {
-    __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
-    __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
-    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][12];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpCounters cnt;
-    unsigned long long err = 0;
-    for (;;) {
-        const uint32_t i0 = fetchItems(counter, MESH_SLOTS, lane);
-        if (i0 >= n) break;
-        const int nb = (int)min((uint32_t)MESH_SLOTS, n - i0);
-        __syncwarp();
-        if (lane < nb) {
-            float q[7];
-#pragma unroll
-            for (int c = 0; c < 7; ++c) q[c] = __ldg(states + (size_t)(i0 + lane) * 7 + c);
-            storeTransform(q, sXf[warp][lane]);
-        }
-        __syncwarp();
-        cnt.states += nb;
-        const unsigned hit = warpCollideMulti(m, nb, sXf[warp], sStack[warp], sTri[warp], lane, false, cnt, err);
-        if (lane < nb) ok[i0 + lane] = ((hit >> lane) & 1u) ? 0 : 1;
+// per edge: steps = ceil(distance(from,to) * (1/stepSize)) (:64,:78), the number of its states outside the
+// coarse set, and ok preset to 1
+template <typename S>
+__global__ void meshStepsKernel(DevSpace<S> sp, const S* __restrict__ from, const S* __restrict__ to, uint32_t n, S invStep,
+                                uint32_t* __restrict__ steps, unsigned long long* __restrict__ counts, uint8_t* __restrict__ ok,
+                                unsigned long long* stats) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (e == 0) counts[n] = 0;
+    const S* a = from + (size_t)e * 7;
+    const S* b = to + (size_t)e * 7;
+    const S dist = dev::distance<S>(sp, [&](int c) { return __ldg(a + c); }, [&](int c) { return __ldg(b + c); });
+    const S fs = ceil(dist * invStep);
+    uint32_t s = 0;
+    if (!(fs < S(2147483648.0))) {
+        atomicOr(stats + 4, (unsigned long long)GEOM_ERR_STEPS);
+        ok[e] = 0;
+    } else {
+        s = (uint32_t)fs;
+        ok[e] = 1;
     }
-    flushCounters(cnt, err, stats, lane);
-}
-
-// ------------------------------------------------------------------ link(a,b): DiscreteMotionValidator
-// src/mpt/discrete_motion_validator.hpp:71-130, one warp per edge.  State indices are produced in the
-// reference's order (valid(to) first, then the breadth-first bisection of 1..steps-1 through the
-// 256-entry ring with its sequential fallback; children are queued before the check, which is
-// harmless because a failed check ends the edge) and checked MESH_SLOTS at a time; the edge is
-// invalid as soon as any of them collides.  The decision is the reference's AND over the same set of
-// states; up to MESH_SLOTS-1 more states than the reference's sequential early exit may be touched.
-__global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshLinkKernel(MeshDev m, DevSpace<float> sp, const float* __restrict__ from,
-                                                                  const float* __restrict__ to, uint32_t n, float invStep,
-                                                                  uint8_t* __restrict__ ok, unsigned int* counter,
-                                                                  unsigned long long* stats) {
-    __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
-    __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
-    __shared__ uint2 sQueue[MESH_WARPS][DMV_QUEUE];
-    __shared__ float sEnds[MESH_WARPS][16];  // from[7], to[7]
-    __shared__ uint32_t sIdx[MESH_WARPS][MESH_SLOTS];
-    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][12];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr uint32_t IDX_TO = 0xFFFFFFFFu;
-    WarpCounters cnt;
-    unsigned long long err = 0;
-    uint2* queue = sQueue[warp];
-    float* ends = sEnds[warp];
-    for (;;) {
-        const uint32_t e = fetchItems(counter, 1u, lane);
-        if (e >= n) break;
-        __syncwarp();
-        if (lane < 7) ends[lane] = __ldg(from + (size_t)e * 7 + lane);
-        else if (lane < 14) ends[lane] = __ldg(to + (size_t)e * 7 + (lane - 7));
-        __syncwarp();
-        // :78  steps = ceil(distance(from,to) * invStepSize)
-        const float dist = dev::distance<float>(sp, [&](int c) { return ends[c]; }, [&](int c) { return ends[7 + c]; });
-        const float fs = ceilf(dist * invStep);
-        bool good = true;
-        if (!(fs < 2147483648.0f)) {
-            err |= GEOM_ERR_STEPS;
-            good = false;
-        }
-        const uint32_t steps = good ? (uint32_t)fs : 0u;
-        const float delta = steps >= 2 ? fp::div_(1.0f, (float)steps) : 0.0f;  // :82
-        uint32_t qStart = 0, qEnd = 0, seqCur = 1, seqEnd = 0;
-        if (steps >= 2) {  // :79,:99-101
-            if (lane == 0) queue[0] = make_uint2(1u, steps - 1u);
-            qEnd = 1;
-        }
-        bool first = true;
-        __syncwarp();
-        while (good) {
-            // next batch of state indices, in the reference's order
-            int nb = 0;
-            while (nb < MESH_SLOTS) {
-                uint32_t i;
-                if (first) {  // :75  valid(to)
-                    first = false;
-                    i = IDX_TO;
-                } else if (seqCur <= seqEnd) {  // :119-126 sequential fallback in progress
-                    i = seqCur++;
-                } else {
-                    if (qStart == qEnd) break;
-                    const uint2 r = queue[qStart % DMV_QUEUE];
-                    ++qStart;
-                    __syncwarp();
-                    if (r.x == r.y) {  // :104-106
-                        i = r.x;
-                    } else if (qEnd + 2 < qStart + DMV_QUEUE) {  // :107-114
-                        i = (r.x + r.y) / 2;
-                        if (r.x < i) {
-                            if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(r.x, i - 1);
-                            ++qEnd;
-                        }
-                        if (i < r.y) {
-                            if (lane == 0) queue[qEnd % DMV_QUEUE] = make_uint2(i + 1, r.y);
-                            ++qEnd;
-                        }
-                        __syncwarp();
-                    } else {
-                        seqCur = r.x;
-                        seqEnd = r.y;
-                        continue;
-                    }
-                }
-                if (lane == 0) sIdx[warp][nb] = i;
-                ++nb;
-            }
-            if (nb == 0) break;
-            __syncwarp();
-            if (lane < nb) {  // one lane per state: interpolate and build its transform
-                const uint32_t i = sIdx[warp][lane];
-                float q[7];
-                if (i == IDX_TO) {
-#pragma unroll
-                    for (int c = 0; c < 7; ++c) q[c] = ends[7 + c];
-                } else {
-                    dev::interpolate<float>(sp, ends, ends + 7, (float)i * delta, q);
-                }
-                storeTransform(q, sXf[warp][lane]);
-            }
-            __syncwarp();
-            cnt.states += nb;
-            if (warpCollideMulti(m, nb, sXf[warp], sStack[warp], sTri[warp], lane, true, cnt, err)) good = false;
-        }
-        if (lane == 0) ok[e] = good ? 1 : 0;
-    }
-    flushCounters(cnt, err, stats, lane);
+    steps[e] = s;
+    counts[e] = s > (uint32_t)COARSE_IDS ? s - 1u : 0u;
 }
 
 // ------------------------------------------------------------------ host: BVH build
@@ -541,12 +790,6 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
     return MPTG_OK;
 }
 
-int meshGrid(mptg_ctx* ctx, uint32_t n) {
-    const uint32_t want = (n + MESH_WARPS - 1) / MESH_WARPS;
-    const uint32_t cap = (uint32_t)ctx->smCount * MESH_MIN_CTAS;  // persistent grid: every resident slot gets a CTA
-    return (int)(want < cap ? (want ? want : 1) : cap);
-}
-
 }  // namespace
 
 int meshCreate(mptg_ctx* ctx, int /*scalar*/, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris,
@@ -555,9 +798,12 @@ int meshCreate(mptg_ctx* ctx, int /*scalar*/, uint32_t nr, const float* robotTri
     int rc = uploadMesh(ctx, robotTris, nr, &m->mem[0], &m->mem[1], &m->depthR);
     if (!rc) rc = uploadMesh(ctx, envTris, ne, &m->mem[2], &m->mem[3], &m->depthE);
     if (!rc) {
-        cudaError_t e = cudaMalloc(&m->workCounter, sizeof(unsigned int));
+        cudaError_t e = cudaMalloc(&m->workCounter, CTL_BYTES);
+        if (e == cudaSuccess) e = cudaMalloc(&m->poolBlocks, (size_t)POOL_BLOCKS * sizeof(DonBlock));
         if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_CUDA, "meshCreate: %s", cudaGetErrorString(e));
     }
+    if (!rc && (unsigned)(ctx->smCount * MESH_MIN_CTAS * MESH_WARPS) + 2u * MAX_POLLERS > POOL_BLOCKS)
+        rc = fail(ctx, MPTG_ERR_CAPACITY, "meshCreate: device has more resident warps than the donation ring allows");
     if (!rc && m->depthR + m->depthE > 56)
         rc = fail(ctx, MPTG_ERR_CAPACITY, "meshCreate: BVH depth %d + %d exceeds the traversal stack budget", m->depthR, m->depthE);
     if (rc) {
@@ -578,28 +824,127 @@ void meshDestroy(MeshData* m) {
     if (!m) return;
     for (void* p : m->mem) cudaFree(p);
     cudaFree(m->workCounter);
+    cudaFree(m->poolBlocks);
+    cudaFree(m->steps), cudaFree(m->counts), cudaFree(m->offs), cudaFree(m->scanTemp);
     delete m;
 }
 
-int meshValidDev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+namespace {
+
+template <int MODE, typename S>
+void launchFlat(mptg_ctx* ctx, MeshData* md, const MeshWork<S>& w, unsigned long long units, int pass, unsigned long long* stats) {
+    unsigned long long* counter = md->workCounter + (size_t)pass * CTL_COUNTER_STRIDE;
+    unsigned int* ctl = reinterpret_cast<unsigned int*>(md->workCounter + 2 * CTL_COUNTER_STRIDE) + (size_t)pass * CTL_PASS_WORDS;
+    const MeshPool pool{md->poolBlocks, ctl, ctl + CTL_WORDS};
+    // persistent grid; a warp starts up to REFILL_MAX states at a time
+    const unsigned long long want = units / (MESH_WARPS * REFILL_MAX) + 1ull;
+    const unsigned long long cap = (unsigned long long)ctx->smCount * MESH_MIN_CTAS;
+    const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+    meshFlatKernel<S, MODE><<<grid, MESH_WARPS * 32, 0, ctx->stream>>>(md->dev, w, counter, pool, stats);
+}
+
+int ensureEdgeWork(mptg_ctx* ctx, MeshData* md, uint32_t n) {
+    size_t scanBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)(n + 1u));
+    if (md->workEdges >= n && md->scanBytes >= scanBytes) return MPTG_OK;
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(md->steps), cudaFree(md->counts), cudaFree(md->offs), cudaFree(md->scanTemp);
+    md->steps = nullptr, md->counts = md->offs = nullptr, md->scanTemp = nullptr, md->workEdges = 0, md->scanBytes = 0;
+    const size_t cap = (size_t)n + (size_t)n / 4 + 1024;
+    cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)(cap + 1));
+    MPTG_CUDA(ctx, cudaMalloc(&md->steps, cap * sizeof(uint32_t)));
+    MPTG_CUDA(ctx, cudaMalloc(&md->counts, (cap + 1) * sizeof(unsigned long long)));
+    MPTG_CUDA(ctx, cudaMalloc(&md->offs, (cap + 1) * sizeof(unsigned long long)));
+    MPTG_CUDA(ctx, cudaMalloc(&md->scanTemp, scanBytes ? scanBytes : 16));
+    md->workEdges = (uint32_t)(cap > 0xffffffffull ? 0xffffffffull : cap);
+    md->scanBytes = scanBytes;
+    return MPTG_OK;
+}
+
+template <typename S>
+int meshValidT(mptg_geom* g, const S* states, uint32_t n, uint8_t* ok) {
     mptg_ctx* ctx = g->ctx;
-    MPTG_CUDA(ctx, cudaMemsetAsync(g->mesh->workCounter, 0, sizeof(unsigned int), ctx->stream));
-    meshValidKernel<<<meshGrid(ctx, n), MESH_WARPS * 32, 0, ctx->stream>>>(g->mesh->dev, (const float*)states, n, ok,
-                                                                          g->mesh->workCounter, g->devStats);
+    MeshData* md = g->mesh;
+    MPTG_CUDA(ctx, cudaMemsetAsync(ok, 1, n, ctx->stream));
+    if (md->dev.nR == 0 || md->dev.nE == 0) return MPTG_OK;  // nothing can collide
+    MPTG_CUDA(ctx, cudaMemsetAsync(md->workCounter, 0, CTL_BYTES, ctx->stream));
+    MeshWork<S> w{};
+    w.a = states, w.n = n, w.ok = ok;
+    launchFlat<WORK_STATES>(ctx, md, w, n, 0, g->devStats);
     MPTG_LAUNCHED(ctx);
     return MPTG_OK;
+}
+
+template <typename S>
+int meshLinkT(mptg_geom* g, const mptg_space_desc* space, const S* from, const S* to, uint32_t n, double step, uint8_t* ok) {
+    mptg_ctx* ctx = g->ctx;
+    MeshData* md = g->mesh;
+    if ((unsigned long long)n * COARSE_IDS > 0xffffffffull) return fail(ctx, MPTG_ERR_CAPACITY, "mptg_link_batch: at most 2^29 mesh edges per call");
+    if (int rc = ensureEdgeWork(ctx, md, n)) return rc;
+    MPTG_CUDA(ctx, cudaMemsetAsync(md->workCounter, 0, CTL_BYTES, ctx->stream));
+    const DevSpace<S> sp = makeDevSpace<S>(*space);
+    const S invStep = S(1) / (S)step;  // discrete_motion_validator.hpp:64
+    meshStepsKernel<S><<<(n + 255) / 256, 256, 0, ctx->stream>>>(sp, from, to, n, invStep, md->steps, md->counts, ok, g->devStats);
+    MPTG_LAUNCHED(ctx);
+    if (md->dev.nR == 0 || md->dev.nE == 0) return MPTG_OK;
+    size_t scanBytes = md->scanBytes;
+    MPTG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(md->scanTemp, scanBytes, md->counts, md->offs, (int)(n + 1u), ctx->stream));
+    MPTG_LAUNCHED(ctx);
+    MeshWork<S> w{};
+    w.a = from, w.b = to, w.n = n, w.steps = md->steps, w.offs = md->offs, w.ok = ok, w.sp = sp;
+    // the length of the list is only known on the device; at least the coarse ids are there
+    launchFlat<WORK_EDGES>(ctx, md, w, (unsigned long long)n * COARSE_IDS, 0, g->devStats);
+    MPTG_LAUNCHED(ctx);
+#ifdef MESH_DEBUG_STATS
+    if (getenv("MPTG_DEBUG_TIMELINE")) {
+        cudaStreamSynchronize(ctx->stream);
+        static unsigned long long h[3][8192][8];
+        cudaMemcpyFromSymbol(h, gDbgT, sizeof h);
+        for (int mode = 1; mode <= 1; ++mode) {
+            const int nw = ctx->smCount * MESH_MIN_CTAS * MESH_WARPS;
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < nw; ++i) t0 = h[mode][i][0] < t0 ? h[mode][i][0] : t0;
+            std::vector<double> endv, rounds;
+            for (int i = 0; i < nw; ++i) endv.push_back((h[mode][i][1] - t0) * 1e-3), rounds.push_back((double)h[mode][i][2]);
+            unsigned long long totA = 0, totD = 0, nAd = 0;
+            for (int i = 0; i < nw; ++i) totA += h[mode][i][7] >> 32, totD += h[mode][i][7] & 0xffffffffull, nAd += (h[mode][i][7] >> 32) ? 1 : 0;
+            unsigned long long nSpin = 0, nPoll = 0, totSpin = 0, totPoll = 0;
+            for (int i = 0; i < nw; ++i) {
+                const unsigned long long sp = h[mode][i][5] >> 32, po = h[mode][i][5] & 0xffffffffull;
+                nSpin += sp ? 1 : 0, nPoll += po ? 1 : 0, totSpin += sp, totPoll += po;
+            }
+            fprintf(stderr, "[mptg] mode %d donations %llu adoptions %llu by %llu warps; %llu warps spun (%llu iterations), %llu warps polled (%llu iterations)\n", mode, totD, totA, nAd, nSpin, totSpin, nPoll, totPoll);
+            std::vector<double> st, si;
+            for (int i = 0; i < nw; ++i) st.push_back((h[mode][i][0] - t0) * 1e-3), si.push_back(h[mode][i][6] ? (h[mode][i][6] - t0) * 1e-3 : -1.0);
+            std::sort(st.begin(), st.end()), std::sort(si.begin(), si.end());
+            fprintf(stderr, "[mptg] mode %d start us p50 %.0f p99 %.0f max %.0f | first idle us p10 %.0f p50 %.0f p90 %.0f max %.0f\n", mode, st[nw / 2], st[nw * 99 / 100], st[nw - 1], si[nw / 10], si[nw / 2], si[nw * 9 / 10], si[nw - 1]);
+            std::vector<double> se = endv, sr = rounds;
+            std::sort(se.begin(), se.end()), std::sort(sr.begin(), sr.end());
+            fprintf(stderr, "[mptg] mode %d warp end us: p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f | rounds p50 %.0f p90 %.0f p99 %.0f max %.0f\n", mode,
+                    se[nw / 10], se[nw / 2], se[nw * 9 / 10], se[nw * 99 / 100], se[nw - 1], sr[nw / 2], sr[nw * 9 / 10], sr[nw * 99 / 100], sr[nw - 1]);
+            // the last 5 warps
+            for (int k = 0; k < 5; ++k) {
+                int best = 0;
+                for (int i = 0; i < nw; ++i) if (endv[i] > endv[best]) best = i;
+                fprintf(stderr, "   late warp %d (cta %d): end %.0f us rounds %.0f bv %llu tri %llu states %llu triRounds %llu adopted %llu donated %llu\n", best, best / MESH_WARPS, endv[best], rounds[best], h[mode][best][3], h[mode][best][4], h[mode][best][5], h[mode][best][6], h[mode][best][7] >> 32, h[mode][best][7] & 0xffffffffull);
+                endv[best] = -1;
+            }
+        }
+    }
+#endif
+    return MPTG_OK;
+}
+
+}  // namespace
+
+int meshValidDev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+    return g->scalar == MPTG_F32 ? meshValidT<float>(g, (const float*)states, n, ok) : meshValidT<double>(g, (const double*)states, n, ok);
 }
 
 int meshLinkDev(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
                 uint8_t* ok) {
-    mptg_ctx* ctx = g->ctx;
-    MPTG_CUDA(ctx, cudaMemsetAsync(g->mesh->workCounter, 0, sizeof(unsigned int), ctx->stream));
-    const float invStep = 1.0f / (float)step;  // discrete_motion_validator.hpp:64
-    meshLinkKernel<<<meshGrid(ctx, n), MESH_WARPS * 32, 0, ctx->stream>>>(g->mesh->dev, makeDevSpace<float>(*space),
-                                                                         (const float*)from, (const float*)to, n, invStep, ok,
-                                                                         g->mesh->workCounter, g->devStats);
-    MPTG_LAUNCHED(ctx);
-    return MPTG_OK;
+    return g->scalar == MPTG_F32 ? meshLinkT<float>(g, space, (const float*)from, (const float*)to, n, step, ok)
+                                 : meshLinkT<double>(g, space, (const double*)from, (const double*)to, n, step, ok);
 }
 
 }  // namespace mptg

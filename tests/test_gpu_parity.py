@@ -412,11 +412,19 @@ def test_mesh_link_matches_oracle(ctx, oracle):
         diff = got != want
         print(f"mesh link {max_trans}/{max_angle}: {want.mean():.3f} valid, {int(near.sum())} near-contact edges, {int(diff.sum())} differ")
         assert not (diff & (near == 0)).any()
-        # the reference's order and early exit: states are checked eight at a time in the reference's order, so
-        # at most seven more states per invalid edge than the sequential validator, never fewer
+        # valid edges touch exactly the reference's set of states (`to` + steps-1 interior ones); an invalid edge
+        # touches between one state and its whole set (the visiting order is coarse-to-fine, not the reference's)
         if not diff.any():
             got_states = sc.last_stats()["states"]
-            assert og.last_states <= got_states <= og.last_states + 7 * int((want == 0).sum())
+            full = _dmv_state_counts(ctx, sp, a, b, step)
+            assert int(full[want == 1].sum()) + int((want == 0).sum()) <= got_states <= int(full.sum())
+
+
+def _dmv_state_counts(ctx, sp, a, b, step):
+    """states of each edge under discrete_motion_validator.hpp:78 -- max(1, ceil(distance * (1/stepSize)))"""
+    dist = ctx.distance(sp, a, b).astype(np.float32)
+    steps = np.ceil(dist * (np.float32(1.0) / np.float32(step))).astype(np.int64)
+    return np.maximum(steps, 1)
 
 
 def test_mesh_golden_and_degenerate(ctx):

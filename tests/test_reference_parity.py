@@ -109,6 +109,11 @@ def test_device_dmv_matches_reference(ctx):
     sc = m.Scenario.mesh_pair(ctx, G["dmv_robot"], G["dmv_env"], sp, float(G["dmv_step"]))
     ok = sc.link(G["dmv_a"], G["dmv_b"])
     assert np.array_equal(ok, G["dmv_ok"])
+    # valid edges touch exactly the states the reference's validator touched; an invalid edge touches between one
+    # state and its whole set (coarse-to-fine order over all edges instead of the reference's per-edge queue)
     states = sc.last_stats()["states"]
-    total = int(G["dmv_states"].sum())
-    assert total <= states <= total + 7 * int((G["dmv_ok"] == 0).sum())
+    okm = G["dmv_ok"] == 1
+    dist = ctx.distance(sp, G["dmv_a"], G["dmv_b"]).astype(np.float32)
+    full = np.maximum(np.ceil(dist * (np.float32(1.0) / np.float32(G["dmv_step"]))).astype(np.int64), 1)
+    assert np.array_equal(full[okm], G["dmv_states"][okm])
+    assert int(full[okm].sum()) + int((~okm).sum()) <= states <= int(full.sum())
