@@ -39,7 +39,8 @@ SO3_W, L2_W = 50.0, 1.0
 MESH_LO, MESH_HI = -45.0, 45.0
 EDGE_TRANS, EDGE_ANGLE = 12.0, 0.5  # a steered sample: <= 12 units and <= 0.5 rad from the tree node
 ALGO_BYTES_KNN = N_TREE * 7 * 4 + Q_WAVE * 7 * 4 + Q_WAVE * K_NN * (4 + 4)  # 39,583,744
-F_BV, F_TRI = 45.0, 170.0  # flop per box-pair test (rotated-AABB vs AABB as implemented) / per SAT
+F_BV, F_TRI = 82.0, 170.0  # flop per box-pair test (box transform + world-axis stage as implemented; the robot-frame
+# stage adds 39 more when it is reached -- not counted) / per 17-axis SAT
 
 
 def measured_traffic(kernel: str):
@@ -306,14 +307,15 @@ def run_ours(args):
             "fp32": {"achieved": knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": (knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
                      "flop_per_distance_eval": 21.0,
-                     "binds": "FP32/issue (ncu: smsp__issue_active 83%, dram throughput 0.2% -- profiles/r1_ncu_knn_bvh_c.txt)"},
+                     "binds": "FP32/issue (ncu: smsp__issue_active 78%, dram throughput 0.3% -- profiles/r1_ncu_knn_bvh_d.txt)"},
         },
         "roofline_edges": {
-            "kernel": "meshLinkKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,
+            "kernel": "meshFlatKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,
             "unit": "TFLOP/s", "frac": edge_flops / (edge_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
             "peak_source": "cuBLAS SGEMM 8192^3 (TF32 off) on this GPU, same run",
             "algorithmic_flops_per_launch": edge_flops, "bv_tests": mesh_stats["bv_tests"], "tri_tests": mesh_stats["prim_tests"],
             "states": mesh_stats["states"], "flop_per_bv_test": F_BV, "flop_per_tri_test": F_TRI,
+            "traffic": measured_traffic("meshFlatKernel"),
         },
         "e2e": {
             "value": world * Q_WAVE / (e2e_knn_ms * 1e-3), "unit": "queries/s", "edges_per_s": world * E_WAVE / (e2e_edge_ms * 1e-3),

@@ -427,6 +427,33 @@ def _dmv_state_counts(ctx, sp, a, b, step):
     return np.maximum(steps, 1)
 
 
+def test_mesh_float64_states_match_oracle(ctx, oracle):
+    """SE3RigidBodyScenario<double> (the demos build both scalar types, demo/CMakeLists.txt:39): the edge
+    discretisation runs in double (steps, interpolation parameters, slerp), the collision test in float on the
+    rounded pose; the double-precision oracle may only disagree inside its near-contact band."""
+    sp = m.se3_space(50, 1, m.F64)
+    robot, env, step = _mesh_scene()
+    sc = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    og = oracle.mesh_pair(robot, env, sp, step)
+    st = W.se3_states(4000, 27, -45.0, 45.0, dtype=np.float64)
+    got = sc.valid(st)
+    want, margin = og.valid(st, with_margin=True)
+    near = np.abs(margin) < 1e-6 * float(np.linalg.norm(env.reshape(-1, 3).max(0) - env.reshape(-1, 3).min(0)))
+    assert not ((got != want) & ~near).any()
+    assert 0.3 < want.mean() < 0.97
+    for max_trans, max_angle in ((12.0, 0.5), (40.0, 2.0)):
+        a, b = W.se3_edges(1200, 29, -45.0, 45.0, max_trans, max_angle, dtype=np.float64)
+        got = sc.link(a, b)
+        want, nearc = og.link(a, b, with_near_contact=True)
+        diff = got != want
+        print(f"mesh link f64 {max_trans}/{max_angle}: {want.mean():.3f} valid, {int(nearc.sum())} near-contact edges, {int(diff.sum())} differ")
+        assert not (diff & (nearc == 0)).any()
+        assert 0.05 < want.mean() < 0.98
+        if not diff.any():  # valid edges touch exactly ceil(distance / step) states, computed in double
+            full = np.maximum(np.ceil(ctx.distance(sp, a, b) * (1.0 / step)).astype(np.int64), 1)
+            assert int(full[want == 1].sum()) + int((want == 0).sum()) <= sc.last_stats()["states"] <= int(full.sum())
+
+
 def test_mesh_golden_and_degenerate(ctx):
     g = np.load(ROOT / "tests" / "golden" / "golden.npz")
     sp = m.se3_space(50, 1)
