@@ -299,6 +299,82 @@ def test_knn_merge_sharded_equals_single(ctx, oracle):
     assert_knn_equal(got, oracle.tree(sp, pts).knn(q, k))
 
 
+# ------------------------------------------------------------------ BASELINE.json configs[4] at full size
+def test_c5_full_size_knn_properties(ctx, oracle):
+    """N = 1,048,576 tree points, Q = 65,536 queries, k = 16 (the bench workload).  Too large for the oracle
+    as a whole, so: size-independent properties on the full wave, the two device strategies against each other
+    on 2,048 queries, and the oracle on 128 queries."""
+    sp = m.se3_space(50, 1)
+    N, Q, k = 1 << 20, 1 << 16, 16
+    pts, q = W.se3_states(N, W.TREE_SEED), W.se3_states(Q, W.QUERY_SEED)
+    nn = m.Nearest(ctx, sp, N, m.KNN_BVH)
+    nn.insert(pts)
+    idx, dist, cnt = nn.nearest(q, k)
+    # every query gets k neighbours, sorted by (distance, index), all indices valid and distinct per query
+    assert (cnt == k).all() and (idx < N).all()
+    assert (np.diff(dist, axis=1) >= 0).all()
+    ties = np.diff(dist, axis=1) == 0
+    assert (np.diff(idx.astype(np.int64), axis=1)[ties] > 0).all()
+    assert (np.sort(idx, axis=1)[:, 1:] != np.sort(idx, axis=1)[:, :-1]).all()
+    # the reported distances ARE the metric: recompute them with the batched distance entry point
+    sel = np.arange(0, Q, 97)
+    for j in (0, 7, 15):
+        assert np.array_equal(ctx.distance(sp, q[sel], pts[idx[sel, j]]), dist[sel, j])
+    # idempotence, and independence from the rest of the wave (query ordering pass, split scans)
+    idx2, dist2, _ = nn.nearest(q, k)
+    assert np.array_equal(idx, idx2) and np.array_equal(dist, dist2)
+    sub = np.arange(5, Q, 211)
+    si, sd, _ = nn.nearest(q[sub], k)
+    assert np.array_equal(si, idx[sub]) and np.array_equal(sd, dist[sub])
+    # a tree point queried against the tree finds itself first (distance 0 up to the rounding of |q.q| vs 1)
+    self_i, self_d, _ = nn.nearest(pts[:4096], 1)
+    own = ctx.distance(sp, pts[:4096], pts[:4096])
+    assert (self_d[:, 0] <= own).all() and (self_i[:, 0] == np.arange(4096)).mean() > 0.99
+    # exhaustive scan of all 1M points (the other device strategy) on 2,048 queries: bit-identical
+    brute = m.Nearest(ctx, sp, N, m.KNN_BRUTE)
+    brute.insert(pts)
+    bsel = np.arange(0, Q, 32)
+    assert_knn_equal(brute.nearest(q[bsel], k), (idx[bsel], dist[bsel], cnt[bsel]))
+    # and the CPU oracle's exhaustive scan on 128 queries
+    osel = np.arange(3, Q, 512)
+    assert_knn_equal((idx[osel], dist[osel], cnt[osel]), oracle.knn(sp, pts, q[osel], k))
+    # radius form: exactly the neighbours within r, same order
+    r = float(np.median(dist[:, 7]))
+    ri, rd, rc = nn.nearest(q[bsel], k, r)
+    inside = dist[bsel] <= np.float32(r)
+    assert np.array_equal(rc, inside.sum(axis=1).astype(np.uint32))
+    assert np.array_equal(ri[inside], idx[bsel][inside]) and (ri[~inside] == m.NO_INDEX).all()
+
+
+def test_c5_full_size_edge_properties(ctx, oracle):
+    """E = 65,536 SE(3) edges against the bench mesh pair (~1k vs ~4k triangles)."""
+    sp = m.se3_space(50, 1)
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=4000, robot_tris_target=1000)
+    step = W.se3_step_size(vmin, vmax, 50.0)
+    sc = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    E = 1 << 16
+    a, b = W.se3_edges(E, W.EDGE_SEED, -45.0, 45.0, 12.0, 0.5)
+    ok = sc.link(a, b)
+    states = sc.last_stats()["states"]
+    assert 0.3 < ok.mean() < 0.95
+    # the schedule (work pulling, donation between warps) must not leak into the answer
+    for _ in range(3):
+        assert np.array_equal(sc.link(a, b), ok)
+    sub = np.arange(11, E, 37)
+    assert np.array_equal(sc.link(a[sub], b[sub]), ok[sub])
+    # an edge is valid only if its end state is (discrete_motion_validator.hpp:75); a zero-length edge is valid(to)
+    vb = sc.valid(b)
+    assert not (ok.astype(bool) & ~vb.astype(bool)).any()
+    assert np.array_equal(sc.link(b[:4096], b[:4096]), vb[:4096])
+    # number of states touched: all of a valid edge's, at least one of an invalid edge's
+    full = _dmv_state_counts(ctx, sp, a, b, step)
+    assert int(full[ok == 1].sum()) + int((ok == 0).sum()) <= states <= int(full.sum())
+    # the oracle on 2,048 of the edges
+    osel = np.arange(0, E, 32)
+    want, near = oracle.mesh_pair(robot, env, sp, step).link(a[osel], b[osel], with_near_contact=True)
+    assert not ((ok[osel] != want) & (near == 0)).any()
+
+
 # ------------------------------------------------------------------ grid / shapes / link arm
 @pytest.mark.parametrize("scalar", [m.F64, m.F32])
 def test_grid_matches_oracle(ctx, oracle, scalar):
