@@ -195,6 +195,59 @@ int mptg_geom_last_stats(mptg_geom* geom, uint64_t stats_out[4]);
 int mptg_steer_batch(mptg_ctx* ctx, const mptg_space_desc* space, const void* near, const void* sample,
                      const void* d, uint32_t n, double range, void* out, void* dist_out);
 
+/* --------------------------------------------------------- sampling
+ * Uniform samples of a space: LP coordinates uniform in [lo,hi) (src/mpt/uniform_box_sampler.hpp:60-68), SO2
+ * coordinates uniform in [-pi,pi) (impl/uniform_sampler_so2.hpp:58-64), SO3 by the reference's three-uniform
+ * formula (impl/uniform_sampler_so3.hpp:55-68), compound spaces part by part
+ * (impl/uniform_sampler_cartesian.hpp:75-78).  lo / hi hold one double per scalar of the state (entries of SO2 /
+ * SO3 parts are ignored).  Sample number g = first + i is a pure function of (seed, g): Philox4x32-10 counter
+ * stream, see csrc/plan.cu -- the reference seeds one mt19937_64 per worker from std::random_device, so there is
+ * no reference sequence, only the distributions.  Uniform 0 of every sample is reserved for the goal-bias draw. */
+int mptg_space_uniforms(const mptg_space_desc* space); /* uniforms consumed per state (SO3: 3, else 1 per scalar) */
+int mptg_sample_batch(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi,
+                      uint64_t seed, uint64_t first, uint32_t n, void* states_out);
+int mptg_sample_batch_dev(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi,
+                          uint64_t seed, uint64_t first, uint32_t n, void* states_out_dev);
+/* The deterministic half alone: n * mptg_space_uniforms() uniforms in [0,1) (the space's scalar type) -> n
+ * states.  With all-zero uniforms this reproduces the reference's sampler tests, which drive the samplers with
+ * a generator that always returns its minimum (test/scenario_sampler_test.cpp:198-270). */
+int mptg_sample_transform_batch(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi,
+                                const void* uniforms, uint32_t n, void* states_out);
+
+/* --------------------------------------------------------- device-resident PRRT
+ * The tree (node states, parent indices), its nearest-neighbour structure and every stage of
+ * Worker::addSample (src/mpt/impl/prrt/prrt.hpp:411-452) stay on the GPU.  One wave = n_samples iterations of
+ * the reference's loop run as a batch: sample (goal-biased until the first goal node, :365-387) -> nearest (:416)
+ * -> drop d == 0 (:427) -> steer to `range` (:430-434) -> scenario.valid (:439) -> scenario.link (:441) ->
+ * append the survivors in sample order with parent = nearest node (:444-447) -> goal test (:442, GoalState
+ * semantics of src/mpt/goal_state.hpp:64-69).  Samples of one wave do not see each other's nodes. */
+typedef struct mptg_prrt mptg_prrt;
+typedef struct mptg_prrt_params {
+    const mptg_space_desc* space;
+    const double* lo;       /* sampling bounds, one double per scalar (see mptg_sample_batch) */
+    const double* hi;
+    double range;           /* Planner::setRange(); use HUGE_VAL for none */
+    double goal_bias;       /* Planner::setGoalBias(), default of the reference 0.01 */
+    const void* goal_state; /* GoalState: state (space scalar type) or NULL for no goal */
+    double goal_radius;
+    double link_step;       /* DiscreteMotionValidator step size (mesh geometries) */
+    uint64_t seed;
+    uint32_t capacity;      /* maximum number of nodes */
+    uint32_t max_wave;      /* maximum samples per wave */
+} mptg_prrt_params;
+int mptg_prrt_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params* params, mptg_prrt** out);
+int mptg_prrt_destroy(mptg_prrt* prrt);
+/* Planner::addStart(state) (prrt.hpp:176-190) */
+int mptg_prrt_add_start(mptg_prrt* prrt, const void* state);
+/* One wave.  size_out: nodes in the tree afterwards (Planner::size()); goal_node_out: index of the first node
+ * that reached the goal, MPTG_NO_INDEX while unsolved (Planner::solved()). */
+int mptg_prrt_wave(mptg_prrt* prrt, uint32_t n_samples, uint32_t* size_out, uint32_t* goal_node_out);
+uint32_t mptg_prrt_size(const mptg_prrt* prrt);
+uint64_t mptg_prrt_samples_drawn(const mptg_prrt* prrt);
+/* Node states (AoS, host) and parent indices (MPTG_NO_INDEX for a start) of nodes first .. first+count-1:
+ * what Planner::solution() and visitGraph() walk (prrt.hpp:232-262). */
+int mptg_prrt_get_tree(mptg_prrt* prrt, uint32_t first, uint32_t count, void* states_out, uint32_t* parents_out);
+
 #ifdef __cplusplus
 }
 #endif

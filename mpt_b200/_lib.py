@@ -31,6 +31,12 @@ class SpaceDesc(C.Structure):
     _fields_ = [("n_parts", C.c_int32), ("scalar", C.c_int32), ("part", SpacePart * MAX_PARTS)]
 
 
+class PrrtParams(C.Structure):
+    _fields_ = [("space", C.POINTER(SpaceDesc)), ("lo", C.c_void_p), ("hi", C.c_void_p), ("range", C.c_double),
+                ("goal_bias", C.c_double), ("goal_state", C.c_void_p), ("goal_radius", C.c_double), ("link_step", C.c_double),
+                ("seed", C.c_uint64), ("capacity", C.c_uint32), ("max_wave", C.c_uint32)]
+
+
 class MptgError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmptg error {code}: {msg}")
@@ -80,6 +86,17 @@ SYMBOLS = {
     "mptg_link_batch_dev": (C.c_int, [_P, _SD, _P, _P, _U32, C.c_double, _P]),
     "mptg_geom_last_stats": (C.c_int, [_P, _U64P]),
     "mptg_steer_batch": (C.c_int, [_P, _SD, _P, _P, _P, _U32, C.c_double, _P, _P]),
+    "mptg_space_uniforms": (C.c_int, [_SD]),
+    "mptg_sample_batch": (C.c_int, [_P, _SD, _P, _P, C.c_uint64, C.c_uint64, _U32, _P]),
+    "mptg_sample_batch_dev": (C.c_int, [_P, _SD, _P, _P, C.c_uint64, C.c_uint64, _U32, _P]),
+    "mptg_sample_transform_batch": (C.c_int, [_P, _SD, _P, _P, _P, _U32, _P]),
+    "mptg_prrt_create": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
+    "mptg_prrt_destroy": (C.c_int, [_P]),
+    "mptg_prrt_add_start": (C.c_int, [_P, _P]),
+    "mptg_prrt_wave": (C.c_int, [_P, _U32, _U32P, _U32P]),
+    "mptg_prrt_size": (_U32, [_P]),
+    "mptg_prrt_samples_drawn": (C.c_uint64, [_P]),
+    "mptg_prrt_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P]),
 }
 
 _lib = None

@@ -214,6 +214,98 @@ class Nearest:
         return {"distance_evals": out[0], "nodes_visited": out[1], "indexed": out[2], "strategy": out[3]}
 
 
+def _bounds(space: Space, lo, hi):
+    lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (space.scalars,)))
+    hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (space.scalars,)))
+    return lo, hi
+
+
+def sample(ctx: Context, space: Space, lo, hi, seed: int, first: int, n: int) -> np.ndarray:
+    """n uniform samples of `space` (sample numbers first .. first+n-1 of the stream `seed`); lo / hi: one bound per
+    scalar of the state (ignored for SO2 / SO3 parts).  UniformSampler of the reference, counter-based generator."""
+    lo, hi = _bounds(space, lo, hi)
+    out = np.empty((n, space.scalars), dtype=space.dtype)
+    L.check(ctx.lib.mptg_sample_batch(ctx.h, space.ref, _ptr(lo), _ptr(hi), seed, first, n, _ptr(out)), ctx.h)
+    return out
+
+
+def sample_from_uniforms(ctx: Context, space: Space, lo, hi, uniforms) -> np.ndarray:
+    """The deterministic half of the sampler: rows of uniforms in [0,1) -> states."""
+    lo, hi = _bounds(space, lo, hi)
+    per = ctx.lib.mptg_space_uniforms(space.ref)
+    u = np.ascontiguousarray(uniforms, dtype=space.dtype).reshape(-1, per)
+    out = np.empty((u.shape[0], space.scalars), dtype=space.dtype)
+    L.check(ctx.lib.mptg_sample_transform_batch(ctx.h, space.ref, _ptr(lo), _ptr(hi), _ptr(u), u.shape[0], _ptr(out)), ctx.h)
+    return out
+
+
+class DevicePRRT:
+    """Device-resident PRRT (mptg_prrt_*): Planner<Scenario, PRRT> with the tree kept on the GPU."""
+
+    def __init__(self, scenario: "Scenario", space: Space, lo, hi, *, range: float = float("inf"), goal=None, goal_radius: float = 0.0,
+                 goal_bias: float = 0.01, seed: int = 1, capacity: int = 1 << 20, max_wave: int = 1 << 16):
+        self.ctx, self.scenario, self.space = scenario.ctx, scenario, space
+        self._lo, self._hi = _bounds(space, lo, hi)
+        self._goal = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
+        prm = L.PrrtParams(C.pointer(space.desc), self._lo.ctypes.data, self._hi.ctypes.data, min(float(range), 1.7e308), float(goal_bias),
+                           None if self._goal is None else self._goal.ctypes.data, float(goal_radius), float(scenario.step or 0.0),
+                           int(seed), int(capacity), int(max_wave))
+        self.h = C.c_void_p()
+        L.check(self.ctx.lib.mptg_prrt_create(self.ctx.h, scenario.h, C.byref(prm), C.byref(self.h)), self.ctx.h)
+        self.goal_node = L.NO_INDEX
+
+    def add_start(self, state):
+        s = np.ascontiguousarray(state, dtype=self.space.dtype).reshape(self.space.scalars)
+        L.check(self.ctx.lib.mptg_prrt_add_start(self.h, _ptr(s)), self.ctx.h)
+
+    def wave(self, n_samples: int) -> int:
+        size, goal = C.c_uint32(), C.c_uint32()
+        L.check(self.ctx.lib.mptg_prrt_wave(self.h, n_samples, C.byref(size), C.byref(goal)), self.ctx.h)
+        self.goal_node = goal.value
+        return size.value
+
+    @property
+    def size(self) -> int:
+        return self.ctx.lib.mptg_prrt_size(self.h)
+
+    @property
+    def samples_drawn(self) -> int:
+        return self.ctx.lib.mptg_prrt_samples_drawn(self.h)
+
+    def solved(self) -> bool:
+        return self.goal_node != L.NO_INDEX
+
+    def tree(self, first: int = 0, count: int | None = None):
+        """-> (states [n, D], parents [n] uint32; NO_INDEX for a start node)"""
+        count = self.size - first if count is None else count
+        st = np.empty((count, self.space.scalars), dtype=self.space.dtype)
+        pa = np.empty(count, dtype=np.uint32)
+        L.check(self.ctx.lib.mptg_prrt_get_tree(self.h, first, count, _ptr(st), _ptr(pa)), self.ctx.h)
+        return st, pa
+
+    def solution(self) -> np.ndarray:
+        """Planner::solution(): states from the start to the first goal node (prrt.hpp:232-249)."""
+        if not self.solved():
+            return np.empty((0, self.space.scalars), dtype=self.space.dtype)
+        st, pa = self.tree()
+        path, n = [], self.goal_node
+        while n != L.NO_INDEX:
+            path.append(st[n])
+            n = int(pa[n])
+        return np.stack(path[::-1])
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mptg_prrt_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def knn_merge_dev(ctx: Context, scalar: int, parts: int, Q: int, k: int, idx_in: int, dist_in: int, idx_out: int,
                   dist_out: int, cnt_out: int = 0):
     L.check(ctx.lib.mptg_knn_merge_dev(ctx.h, scalar, parts, Q, k, C.c_void_p(idx_in), C.c_void_p(dist_in),

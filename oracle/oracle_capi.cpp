@@ -7,6 +7,7 @@
 #include <memory>
 
 #include "oracle.hpp"
+#include "oracle_sample.hpp"
 #include "oracle_tree.hpp"
 
 using namespace oracle;
@@ -297,6 +298,37 @@ int orc_geom_counters(void* geom, uint64_t out[4]) {
 }
 
 // Exhaustive / sampled accuracy figures of mptg_fpmath.h against libm (see fpmath_check.cpp)
+// one Philox4x32-10 block with the counter layout of the sample streams: (g_lo, g_hi, blk, 0), key = seed
+void orc_philox_block(uint64_t seed, uint64_t g, uint32_t blk, uint32_t out[4]) { Philox::block(seed, g, blk, out); }
+
+// samples first .. first+n-1 of stream `seed`; goal (or NULL) with its bias
+int orc_sample_batch(const mptg_space_desc* sp, const double* lo, const double* hi, uint64_t seed, uint64_t first, uint32_t n,
+                     const void* goal, double goalBias, void* out) {
+    int D = 0;
+    for (int i = 0; i < sp->n_parts; ++i) D += sp->part[i].kind == MPTG_PART_SO3 ? 4 : sp->part[i].dim;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (sp->scalar == MPTG_F32) sampleState<float>(*sp, lo, hi, seed, first + i, (const float*)goal, goalBias, (float*)out + (size_t)i * D);
+        else sampleState<double>(*sp, lo, hi, seed, first + i, (const double*)goal, goalBias, (double*)out + (size_t)i * D);
+    }
+    return 0;
+}
+int orc_sample_from_uniforms(const mptg_space_desc* sp, const double* lo, const double* hi, const void* uniforms, int perState, uint32_t n,
+                             void* out) {
+    int D = 0;
+    for (int i = 0; i < sp->n_parts; ++i) D += sp->part[i].kind == MPTG_PART_SO3 ? 4 : sp->part[i].dim;
+    for (uint32_t i = 0; i < n; ++i) {
+        int j = 0;
+        if (sp->scalar == MPTG_F32) {
+            const float* u = (const float*)uniforms + (size_t)i * perState;
+            sampleFromUniforms<float>(*sp, lo, hi, [&]() { return u[j++]; }, (float*)out + (size_t)i * D);
+        } else {
+            const double* u = (const double*)uniforms + (size_t)i * perState;
+            sampleFromUniforms<double>(*sp, lo, hi, [&]() { return u[j++]; }, (double*)out + (size_t)i * D);
+        }
+    }
+    return 0;
+}
+
 double orc_acos01f(float x) { return fp::acos01(x); }
 double orc_acos01d(double x) { return fp::acos01(x); }
 void orc_sincosd(double x, double* s, double* c) { fp::sincos_(x, s, c); }

@@ -81,6 +81,22 @@ class Oracle:
         self.lib.orc_interpolate_batch(space.ref, _ptr(a), _ptr(b), _ptr(t), a.shape[0], _ptr(out))
         return out
 
+    def sample(self, space, lo, hi, seed, first, n, goal=None, goal_bias=0.0):
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (space.scalars,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (space.scalars,)))
+        g = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
+        out = np.empty((n, space.scalars), dtype=space.dtype)
+        self.lib.orc_sample_batch(space.ref, _ptr(lo), _ptr(hi), C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), _ptr(g), C.c_double(goal_bias), _ptr(out))
+        return out
+
+    def sample_from_uniforms(self, space, lo, hi, uniforms, per_state):
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (space.scalars,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (space.scalars,)))
+        u = np.ascontiguousarray(uniforms, dtype=space.dtype).reshape(-1, per_state)
+        out = np.empty((u.shape[0], space.scalars), dtype=space.dtype)
+        self.lib.orc_sample_from_uniforms(space.ref, _ptr(lo), _ptr(hi), _ptr(u), C.c_int(per_state), C.c_uint32(u.shape[0]), _ptr(out))
+        return out
+
     def steer(self, space, near, sample, d, rng, with_distance=False):
         near = np.ascontiguousarray(near, dtype=space.dtype).reshape(-1, space.scalars)
         sample = np.ascontiguousarray(sample, dtype=space.dtype).reshape(-1, space.scalars)

@@ -375,6 +375,110 @@ def test_c5_full_size_edge_properties(ctx, oracle):
     assert not ((ok[osel] != want) & (near == 0)).any()
 
 
+# ------------------------------------------------------------------ sampling and the device-resident PRRT
+def test_device_sampler_matches_oracle_and_reference_kats(ctx, oracle):
+    from tests.test_oracle import sampler_kats
+
+    assert sampler_kats(lambda sp, lo, hi, u: m.sample_from_uniforms(ctx, sp, lo, hi, u)) == []
+    cases = [
+        (m.se3_space(50, 1, m.F32), [0, 0, 0, 0, -100, -100, -100], [0, 0, 0, 0, 100, 100, 100]),
+        (m.se3_space(50, 1, m.F64), [0, 0, 0, 0, -45, -45, -45], [0, 0, 0, 0, 45, 45, 45]),
+        (m.lp_space(2, 2, m.F64), [0, 0], [3976, 2603]),
+        (m.lp_space(8, 1, m.F64), -np.pi, np.pi),
+        (m.so2_space(5, 1, m.F32), 0, 0),
+        (m.se2_space(1, 1, m.F32), [-5, -5, 0], [5, 5, 0]),
+        (m.so3_space(m.F64), 0, 0),
+    ]
+    for sp, lo, hi in cases:
+        for first, n in ((0, 4097), (123456789012, 1000)):
+            got = m.sample(ctx, sp, lo, hi, 20261017, first, n)
+            want = oracle.sample(sp, lo, hi, 20261017, first, n)
+            assert np.array_equal(got, want), f"sampler differs for {sp.parts} scalar {sp.scalar}"
+
+
+def _replay_prrt(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, seed, waves, W):
+    """Worker::addSample (src/mpt/impl/prrt/prrt.hpp:411-452) on the oracle, one wave at a time, on the same samples."""
+    nodes = [np.asarray(start, dtype=sp.dtype).reshape(1, -1)]
+    parents = [np.array([m.NO_INDEX], dtype=np.uint32)]
+    goal_node, drawn = m.NO_INDEX, 0
+    for _ in range(waves):
+        tree = np.concatenate(nodes)
+        biased = goal is not None and goal_bias > 0 and goal_node == m.NO_INDEX
+        smp = oracle.sample(sp, lo, hi, seed, drawn, W, goal if biased else None, goal_bias)
+        drawn += W
+        idx, dist, cnt = oracle.knn(sp, tree, smp, 1)
+        near, d = tree[idx[:, 0]], dist[:, 0]
+        to = oracle.steer(sp, near, smp, d, rng)
+        keep = (cnt > 0) & (d != 0) & (og.valid(to) != 0) & (og.link(near, to) != 0)
+        fresh = to[keep]
+        if goal is not None and goal_node == m.NO_INDEX and len(fresh):
+            hit = np.nonzero(oracle.distance(sp, fresh, np.broadcast_to(np.asarray(goal, dtype=sp.dtype), fresh.shape)) <= sp.dtype(goal_radius))[0]
+            if hit.size:
+                goal_node = tree.shape[0] + int(hit[0])
+        nodes.append(fresh)
+        parents.append(idx[keep, 0].astype(np.uint32))
+    return np.concatenate(nodes), np.concatenate(parents), goal_node
+
+
+def test_device_prrt_replays_the_reference_loop_on_a_grid(ctx, oracle):
+    """PNG-style occupancy grid, planar L2 double states (png_2d_scenario.hpp): the device-resident tree must be
+    the tree the reference's addSample loop builds from the same samples -- states bit-identical, same parents,
+    same goal node."""
+    occ = W.synthetic_grid(500, 400, seed=2)
+    sp = m.lp_space(2, 2, m.F64)
+    sc, og = m.Scenario.grid(ctx, occ, m.F64), oracle.grid(occ)
+    free = np.argwhere(occ == 0)
+    start = free[len(free) // 7][::-1].astype(np.float64)
+    goal = free[-len(free) // 9][::-1].astype(np.float64)
+    lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
+    for rng, waves, W_ in ((25.0, 6, 512), (float("inf"), 3, 300)):
+        pl = m.DevicePRRT(sc, sp, lo, hi, range=rng, goal=goal, goal_radius=12.0, goal_bias=0.05, seed=99, capacity=8192, max_wave=512)
+        pl.add_start(start)
+        for _ in range(waves):
+            pl.wave(W_)
+        states, parents = pl.tree()
+        want_states, want_parents, want_goal = _replay_prrt(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 99, waves, W_)
+        assert pl.samples_drawn == waves * W_
+        assert states.shape == want_states.shape and states.shape[0] > 50
+        assert np.array_equal(states, want_states) and np.array_equal(parents, want_parents)
+        assert pl.goal_node == want_goal
+        if pl.solved():
+            path = pl.solution()
+            assert np.array_equal(path[0], start) and np.linalg.norm(path[-1] - goal) <= 12.0
+            assert og.link(path[:-1], path[1:]).all()
+        pl.close()
+
+
+def test_device_prrt_on_meshes_builds_a_valid_tree(ctx, oracle):
+    """SE(3) rigid body among meshes (se3_rigid_body_scenario.hpp): every node valid, every tree edge a valid motion
+    within `range` of its parent (oracle; near-contact items excepted and counted), parents precede children, and
+    the run is reproducible."""
+    sp = m.se3_space(50, 1)
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=1200, robot_tris_target=400)
+    step = W.se3_step_size(vmin, vmax)
+    sc, og = m.Scenario.mesh_pair(ctx, robot, env, sp, step), oracle.mesh_pair(robot, env, sp, step)
+    lo, hi = [0, 0, 0, 0, -45, -45, -45], [0, 0, 0, 0, 45, 45, 45]
+    cand = W.se3_states(64, 5, -45.0, 45.0)
+    start = cand[np.nonzero(og.valid(cand))[0][0]]
+    trees = []
+    for _ in range(2):
+        pl = m.DevicePRRT(sc, sp, lo, hi, range=30.0, seed=7, capacity=1 << 15, max_wave=2048)
+        pl.add_start(start)
+        for _ in range(6):
+            pl.wave(2048)
+        trees.append(pl.tree())
+        pl.close()
+    (states, parents), (s2, p2) = trees
+    assert np.array_equal(states, s2) and np.array_equal(parents, p2)
+    n = states.shape[0]
+    assert n > 2000 and parents[0] == m.NO_INDEX and (parents[1:] < np.arange(1, n)).all()
+    child, par = states[1:], states[parents[1:]]
+    ok, near = og.link(par, child, with_near_contact=True)
+    assert not ((ok == 0) & (near == 0)).any()
+    edge = oracle.distance(sp, par, child).astype(np.float64)
+    assert edge.max() <= 30.0 * (1 + 1e-4), f"longest tree edge {edge.max()}"
+
+
 # ------------------------------------------------------------------ grid / shapes / link arm
 @pytest.mark.parametrize("scalar", [m.F64, m.F32])
 def test_grid_matches_oracle(ctx, oracle, scalar):

@@ -91,6 +91,85 @@ def test_knn_order_and_padding(oracle):
     assert cnt[0] == 3 and list(idx[0][:3]) == [0, 1, 2]
 
 
+# ------------------------------------------------------------------ samplers
+def test_philox_known_answers(oracle):
+    """Philox4x32-10 against the published Random123 known-answer vectors that fit the sample streams' counter
+    layout (c3 = 0 only for the first), and against an independent restatement for the rest."""
+    def philox(c, k):
+        c, k = list(c), list(k)
+        for _ in range(10):
+            a, b = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(b >> 32) ^ c[1] ^ k[0], b & 0xFFFFFFFF, (a >> 32) ^ c[3] ^ k[1], a & 0xFFFFFFFF]
+            k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+        return c
+    # Random123 kat_vectors: philox4x32 10
+    assert philox([0] * 4, [0] * 2) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert philox([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    import ctypes as C
+    out = (C.c_uint32 * 4)()
+    oracle.lib.orc_philox_block(C.c_uint64(0), C.c_uint64(0), C.c_uint32(0), out)
+    assert list(out) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        seed, g, blk = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**63)), int(rng.integers(0, 2**31))
+        oracle.lib.orc_philox_block(C.c_uint64(seed), C.c_uint64(g), C.c_uint32(blk), out)
+        assert list(out) == philox([g & 0xFFFFFFFF, g >> 32, blk, 0], [seed & 0xFFFFFFFF, seed >> 32])
+
+
+def sampler_kats(sample_from_uniforms):
+    """test/scenario_sampler_test.cpp:198-270 drives the uniform samplers with a generator that always returns its
+    minimum (all uniforms 0): SO(3) -> coeffs (1,0,0,0), box -> its minimum corner, SE(3) -> both."""
+    bad = []
+    for scalar in (m.F32, m.F64):
+        so3 = m.so3_space(scalar)
+        if not np.array_equal(sample_from_uniforms(so3, 0, 0, np.zeros((1, 3)))[0], [1, 0, 0, 0]):
+            bad.append(("so3", scalar))
+        lp2 = m.lp_space(2, 2, scalar)
+        if not np.array_equal(sample_from_uniforms(lp2, [1, 2], [3, 5], np.zeros((1, 2)))[0], [1, 2]):
+            bad.append(("lp2", scalar))
+        se3 = m.se3_space(50, 1, scalar)
+        lo, hi = [0, 0, 0, 0, 1, 2, 3], [0, 0, 0, 0, 4, 5, 6]
+        if not np.array_equal(sample_from_uniforms(se3, lo, hi, np.zeros((1, 6)))[0], [1, 0, 0, 0, 1, 2, 3]):
+            bad.append(("se3", scalar))
+        so2 = m.so2_space(3, 1, scalar)
+        got = sample_from_uniforms(so2, 0, 0, np.zeros((1, 3)))[0]
+        if not np.array_equal(got, np.full(3, -np.pi, dtype=got.dtype)):
+            bad.append(("so2", scalar))
+    return bad
+
+
+def test_sampler_reference_kats(oracle):
+    assert sampler_kats(lambda sp, lo, hi, u: oracle.sample_from_uniforms(sp, lo, hi, u, u.shape[1])) == []
+
+
+def test_sampler_distributions(oracle):
+    """Uniform on the box; unit quaternions uniform on S^3 (each coefficient mean 0, variance 1/4; the rotation
+    angle theta = 2 acos|w| has density (1 - cos theta)/pi, i.e. P(theta < t) = (t - sin t)/pi)."""
+    n = 200_000
+    for scalar in (m.F32, m.F64):
+        se3 = m.se3_space(50, 1, scalar)
+        lo, hi = [0, 0, 0, 0, -10, 0, 5], [0, 0, 0, 0, 10, 1, 7]
+        s = oracle.sample(se3, lo, hi, seed=12345, first=0, n=n).astype(np.float64)
+        q, t = s[:, :4], s[:, 4:]
+        assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < (2e-6 if scalar == m.F32 else 1e-14)
+        assert np.abs(q.mean(axis=0)).max() < 0.005 and np.abs(q.var(axis=0) - 0.25).max() < 0.005
+        theta = 2 * np.arccos(np.minimum(1.0, np.abs(q[:, 3])))
+        for tt in (0.5, 1.0, 2.0, 3.0):
+            assert abs((theta < tt).mean() - (tt - np.sin(tt)) / np.pi) < 0.005
+        assert (t >= np.array(lo[4:])).all() and (t < np.array(hi[4:])).all()
+        assert np.abs(t.mean(axis=0) - np.array([0, 0.5, 6])).max() < 0.03
+        assert np.abs(t.var(axis=0) - np.array([400, 1, 4]) / 12).max() < 0.5
+        # streams: disjoint sample numbers are the same samples whatever the batching; other seeds differ
+        again = np.concatenate([oracle.sample(se3, lo, hi, 12345, 0, 1000), oracle.sample(se3, lo, hi, 12345, 1000, 500)])
+        assert np.array_equal(again, oracle.sample(se3, lo, hi, 12345, 0, 1500))
+        assert not np.array_equal(oracle.sample(se3, lo, hi, 12346, 0, 100), again[:100])
+    # goal bias: the goal state replaces about goal_bias of the samples
+    lp = m.lp_space(2, 2, m.F64)
+    g = oracle.sample(lp, [0, 0], [1, 1], 7, 0, 100_000, goal=[5.0, 5.0], goal_bias=0.05)
+    assert abs((g[:, 0] == 5.0).mean() - 0.05) < 0.003
+
+
 def test_grid_semantics(oracle):
     """demo/png_2d_scenario.hpp:104-117: round-half-up indexing, row wrap at x == width, out of range -> obstacle."""
     occ = np.zeros((4, 6), dtype=np.uint8)
