@@ -392,6 +392,23 @@ def secondary(ctx, torch, dev, stream):
                 ts.append(e0.elapsed_time(e1))
         out[label] = {"queries_per_s": Q_WAVE / (float(np.mean(ts)) * 1e-3), "ms": float(np.mean(ts))}
         nn.close()
+    # device-resident PRRT: tree, sampling and every stage of the loop on the GPU; wall clock
+    # around whole waves, two words read back per wave
+    import time
+
+    free = np.argwhere(occ == 0)
+    start = free[len(free) // 7][::-1].astype(np.float64)
+    pl = m.DevicePRRT(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], range=200.0, seed=17,
+                      capacity=1 << 20, max_wave=16384)
+    pl.add_start(start)
+    pl.wave(16384)
+    ctx.sync()
+    t0, n0 = time.perf_counter(), pl.size
+    while pl.size < 500_000:
+        pl.wave(16384)
+    dt = time.perf_counter() - t0
+    out["device_prrt_grid"] = {"nodes_per_s": (pl.size - n0) / dt, "samples_per_s": (pl.samples_drawn - 16384) / dt, "nodes": pl.size, "s": dt}
+    pl.close()
     return out
 
 

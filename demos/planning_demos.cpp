@@ -32,6 +32,7 @@ struct Options {
     bool check = false;
     std::string map;
     std::uint64_t seed = 2026;
+    bool devicePrrt = false;  // also run Planner<Scenario, PRRT<device_resident>>: tree and sampling on the GPU
 };
 
 static int failures = 0;
@@ -207,6 +208,13 @@ void png2d(const Options& opt) {
     planner.setRange(200);
     auto [first, total] = runUntilSolved(planner, opt.timeMs);
     report("png_2d", "PRRT*", planner, scenario, first, total, opt);
+    if (opt.devicePrrt) {
+        Planner<Scenario, PRRT<device_resident, report_stats<true>, wave_size<16384>, max_nodes<(1 << 22)>>> dev(scenario, opt.seed);
+        dev.addStart(start);
+        dev.setRange(200);
+        auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
+        report("png_2d", "PRRT, device-resident", dev, scenario, dFirst, dTotal, opt);
+    }
 }
 
 // ------------------------------------------------------------------ C3
@@ -268,6 +276,13 @@ void se3RigidBody(const Options& opt) {
     planner.setRange(40);
     auto [first, total] = runUntilSolved(planner, opt.timeMs);
     report("se3_rigid_body", "PRRT*", planner, scenario, first, total, opt);
+    if (opt.devicePrrt) {
+        Planner<Scenario, PRRT<device_resident, report_stats<true>, wave_size<16384>, max_nodes<(1 << 22)>>> dev(scenario, opt.seed);
+        dev.addStart(start);
+        dev.setRange(40);
+        auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
+        report("se3_rigid_body", "PRRT, device-resident", dev, scenario, dFirst, dTotal, opt);
+    }
 }
 
 // ------------------------------------------------------------------ C4
@@ -332,11 +347,12 @@ int main(int argc, char** argv) {
         else if (a == "--demo" && i + 1 < argc) which = argv[++i];
         else if (a == "--time-ms" && i + 1 < argc) opt.timeMs = std::atof(argv[++i]);
         else if (a == "--check") opt.check = true;
+        else if (a == "--device-prrt") opt.devicePrrt = true;
         else if (a == "--nodes" && i + 1 < argc) opt.nodes = g_targetNodes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
         else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
         else {
-            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--map file.pgm] [--seed S]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--device-prrt] [--map file.pgm] [--seed S]\n", argv[0]);
             return 2;
         }
     }
