@@ -19,12 +19,12 @@ def _stale(out: Path, deps) -> bool:
     return not out.exists() or any(Path(d).stat().st_mtime > out.stat().st_mtime for d in deps)
 
 
-def build_program(src: Path, out: Path, lib_dir: Path, lib: str) -> Path:
+def build_program(src: Path, out: Path, lib_dir: Path, lib: str, defines=()) -> Path:
     deps = [src, *sorted((ROOT / "include" / "mptg").glob("*"))]
     if _stale(out, deps):
         out.parent.mkdir(parents=True, exist_ok=True)
         rpath = "$ORIGIN/" + str(Path(*[".."] * len(out.parent.relative_to(ROOT).parts)) / lib_dir.relative_to(ROOT))
-        cmd = [CXX, *FLAGS, str(src), "-o", str(out), f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{rpath}", "-lpthread"]
+        cmd = [CXX, *FLAGS, *[f"-D{d}" for d in defines], str(src), "-o", str(out), f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{rpath}", "-lpthread"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}")
@@ -52,7 +52,7 @@ def build_mock() -> Path:
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for the mock:\n{r.stdout}")
-    return build_program(ROOT / "tests" / "cpp" / "planner_test.cpp", bdir / "planner_test_mock", bdir, "mptg_mock")
+    return build_program(ROOT / "tests" / "cpp" / "planner_test.cpp", bdir / "planner_test_mock", bdir, "mptg_mock", defines=("MPTG_TEST_MOCK_BACKEND",))
 
 
 if __name__ == "__main__":

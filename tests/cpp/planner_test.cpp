@@ -112,6 +112,11 @@ int main() {
     testSolvingBasicScenario<PRRTStar<report_stats<true>>>("PRRT* k-nearest");
     testSolvingBasicScenario<PRRTStar<rewire_r_nearest>>("PRRT* r-nearest");
     testSolvingBasicScenario<PPRM<report_stats<true>>>("PPRM");
+#ifndef MPTG_TEST_MOCK_BACKEND  // the mock backs the batched calls only; the device-resident planner needs the GPU library
+    static_assert(!std::is_same_v<Planner<S, PRRT<device_resident>>, Planner<S, PRRT<>>>);
+    static_assert(std::is_same_v<Planner<S, PRRT<device_resident, wave_size<4096>>>, Planner<S, PRRT<wave_size<4096>, device_resident>>>);
+    testSolvingBasicScenario<PRRT<device_resident, report_stats<true>, wave_size<4096>, max_nodes<(1 << 18)>>>("PRRT device-resident");
+#endif
     testPRRTStarInvariants();
     // error behaviour (impl/prrt/prrt.hpp:197-198, impl/pprm/pprm.hpp:179-180)
     {

@@ -46,7 +46,7 @@ def test_wave_planners_on_gpu():
     if not prog.exists():
         build_host.build()
     out = _run(prog)
-    for name in ("PRRT:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
+    for name in ("PRRT:", "PRRT device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
         assert f"PASS {name}" in out
 
 
@@ -58,9 +58,10 @@ def test_demo_scenarios_on_gpu():
     prog = ROOT / "demos" / "_build" / "planning_demos"
     if not prog.exists():
         build_host.build()
-    r = subprocess.run([str(prog), "--all", "--check"], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([str(prog), "--all", "--check", "--device-prrt"], capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0
     for name in ("holonomic_2d_point", "png_2d", "link_manipulator", "se3_rigid_body"):
         assert f"OK {name}" in r.stdout
+    assert r.stdout.count("[PRRT, device-resident]") == 2 and "FAILED" not in r.stdout
