@@ -22,8 +22,8 @@ struct mptg_ctx {
     void* pinned = nullptr;
     size_t pinnedBytes = 0;
     // device scratch reused by the host-pointer entry points (grown on demand)
-    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratchBytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* scratch[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratchBytes[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace mptg {

@@ -52,8 +52,8 @@ int mptg_ctx_destroy(mptg_ctx* ctx) {
     if (!ctx) return MPTG_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; ++i)
-        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (void* p : ctx->scratch)
+        if (p) cudaFree(p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -611,6 +611,7 @@ static int checkDeviceErrors(mptg_geom* g) {
                 host[3], host[5], host[6], host[7]);
     if (host[4] & GEOM_ERR_STACK) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: traversal stack overflow (edge too long / geometry too deep)");
     if (host[4] & GEOM_ERR_STEPS) return fail(g->ctx, MPTG_ERR_CAPACITY, "edge check: too many interpolation steps on one edge");
+    if (host[4] & GEOM_ERR_SCHED) return fail(g->ctx, MPTG_ERR_CUDA, "mesh check: a warp waited for donated work for seconds (scheduling fault); results are not valid");
     return MPTG_OK;
 }
 

@@ -32,7 +32,7 @@ struct mptg_geom {
 
 namespace mptg {
 constexpr unsigned FULL_MASK_ = 0xffffffffu;
-enum GeomError : unsigned long long { GEOM_ERR_STACK = 1ull, GEOM_ERR_STEPS = 2ull };
+enum GeomError : unsigned long long { GEOM_ERR_STACK = 1ull, GEOM_ERR_STEPS = 2ull, GEOM_ERR_SCHED = 4ull };
 
 // implemented in mesh.cu
 int meshCreate(mptg_ctx* ctx, int scalar, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris, MeshData** out);

@@ -27,9 +27,9 @@
 namespace mptg {
 
 struct __align__(16) BvhNode {
-    float lo[3];
-    int left;  // >= 0: internal (children left,right); < 0: leaf holding triangle (-1 - left)
-    float hi[3];
+    float lo[3];  // host build: box minimum; device image: box CENTRE
+    int left;     // >= 0: internal (children left,right); < 0: leaf holding triangle (-1 - left)
+    float hi[3];  // host build: box maximum; device image: HALF EXTENT (rounded outwards)
     int right;
 };
 struct __align__(16) TriPad {
@@ -198,7 +198,7 @@ __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
 constexpr int MESH_SLOTS = 32;
 constexpr unsigned SLOT_SHIFT = 27;
 constexpr unsigned NODE_MASK = (1u << SLOT_SHIFT) - 1u;
-constexpr int XF_STRIDE = 13;   // odd stride: lanes reading different slots hit different banks
+constexpr int XF_STRIDE = 12;   // 48-byte rows: three 128-bit loads per box test, conflict-free for 8 consecutive slots
 constexpr int REFILL_AT = 16;   // refill when at most this many node pairs are pending
 constexpr int REFILL_MAX = 16;  // states started per refill
 constexpr int COARSE_IDS = 8;   // work ids per edge in pass 1
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                                                                                 MeshPool pool, unsigned long long* stats) {
     __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
     __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
-    __shared__ float sXf[MESH_WARPS][MESH_SLOTS][XF_STRIDE];
+    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][XF_STRIDE];
     __shared__ uint32_t sItem[MESH_WARPS][MESH_SLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             // picked up (the donor subtracts one per block), so IDLE >= STARTED means: every warp is idle and
             // no block is pending -- nothing can arrive any more.  Each waiter spins on its own ready flag.
             unsigned got = 0xffffffffu;
+            bool watchdog = false;
 #ifdef MESH_DEBUG_STATS
             if (dbgIdleT == 0) dbgIdleT = gtimer();
 #endif
@@ -448,6 +449,10 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                             break;
                         }
                         if ((it & 3u) == 3u && (int)volLoad(pool.ctl + CTL_IDLE) >= (int)volLoad(pool.ctl + CTL_STARTED)) break;  // signed: IDLE dips below zero while blocks outnumber idle warps
+                        if (it > (1u << 22)) {  // seconds of waiting: never hang the device, report instead
+                            watchdog = true;
+                            break;
+                        }
                         __nanosleep(500);
 #ifdef MESH_DEBUG_STATS
                         ++dbgPoll;
@@ -455,6 +460,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                     }
                 }
             }
+            if (watchdog) err |= GEOM_ERR_SCHED;
             got = __shfl_sync(FULL_MASK_, got, 0);
             if (got == 0xffffffffu) break;
             const unsigned bi = got % POOL_BLOCKS;
@@ -547,19 +553,20 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                 ++cnt.bv;
                 // robot box (centre c, half extents h in the robot frame) against the env box, separating
                 // axes = the three world axes and the three robot-frame axes; all bounds padded
-                const float cx = 0.5f * (a.lo[0] + a.hi[0]), cy = 0.5f * (a.lo[1] + a.hi[1]), cz = 0.5f * (a.lo[2] + a.hi[2]);
-                const float hx = 0.5f * (a.hi[0] - a.lo[0]), hy = 0.5f * (a.hi[1] - a.lo[1]), hz = 0.5f * (a.hi[2] - a.lo[2]);
-                float R[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) R[k] = X[k];
+                const float cx = a.lo[0], cy = a.lo[1], cz = a.lo[2];  // device image: lo = centre, hi = half extent
+                const float hx = a.hi[0], hy = a.hi[1], hz = a.hi[2];
+                const float4 x0 = *reinterpret_cast<const float4*>(X), x1 = *reinterpret_cast<const float4*>(X + 4),
+                             x2 = *reinterpret_cast<const float4*>(X + 8);
+                const float R[9] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x};
+                const float T[3] = {x2.y, x2.z, x2.w};
                 float d[3], hb[3], hw[3];
                 float mag = 0.0f;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float cw = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, X[9 + r])));
+                    const float cw = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, T[r])));
                     hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
-                    const float cb = 0.5f * (b.lo[r] + b.hi[r]);
-                    hb[r] = 0.5f * (b.hi[r] - b.lo[r]);
+                    const float cb = b.lo[r];
+                    hb[r] = b.hi[r];
                     d[r] = cb - cw;
                     mag += (fabsf(cw) + hw[r]) + (fabsf(cb) + hb[r]);
                 }
@@ -783,6 +790,17 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
         b.nodes.push_back(BvhNode{});
     }
     *depth = b.maxDepth;
+    // device image: centre / half-extent form (what the box test needs), half extents rounded outwards so that
+    // [c - h, c + h] contains [lo, hi]
+    for (BvhNode& n : b.nodes)
+        for (int c = 0; c < 3; ++c) {
+            const float lo = n.lo[c], hi = n.hi[c];
+            const float ctr = 0.5f * (lo + hi);
+            float h = std::fmax(hi - ctr, ctr - lo);
+            h = std::nextafter(h, INFINITY);
+            n.lo[c] = ctr;  // device meaning: centre
+            n.hi[c] = h;    // device meaning: half extent
+        }
     MPTG_CUDA(ctx, cudaMalloc(nodesDev, b.nodes.size() * sizeof(BvhNode)));
     if (int rc = uploadSync(ctx, *nodesDev, b.nodes.data(), b.nodes.size() * sizeof(BvhNode))) return rc;
     MPTG_CUDA(ctx, cudaMalloc(trisDev, pad.size() * sizeof(TriPad)));

@@ -194,11 +194,10 @@ int spaceUniforms(const mptg_space_desc* sp) {
     return n;
 }
 
-// bounds (doubles, one per scalar; SO2 / SO3 entries ignored) -> device arrays of the space's scalar type: lo then hi
-int uploadBounds(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi, void** out) {
+// bounds (doubles, one per scalar; SO2 / SO3 entries ignored) as lo then hi in the space's scalar type
+std::vector<unsigned char> packBounds(const mptg_space_desc* space, const double* lo, const double* hi) {
     const int D = spaceScalars(space);
-    const size_t s = (size_t)space->scalar;
-    std::vector<unsigned char> host(2 * (size_t)D * s);
+    std::vector<unsigned char> host(2 * (size_t)D * (size_t)space->scalar);
     for (int c = 0; c < D; ++c) {
         const double l = lo ? lo[c] : 0.0, h = hi ? hi[c] : 0.0;
         if (space->scalar == MPTG_F32) {
@@ -209,8 +208,20 @@ int uploadBounds(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, 
             ((double*)host.data())[D + c] = h;
         }
     }
+    return host;
+}
+// persistent copy (planner handles)
+int uploadBounds(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi, void** out) {
+    const std::vector<unsigned char> host = packBounds(space, lo, hi);
     MPTG_CUDA(ctx, cudaMalloc(out, host.size()));
     return uploadSync(ctx, *out, host.data(), host.size());
+}
+// per-call copy in scratch slot 8, stream-ordered (the pageable source is staged before the call returns)
+int stageBounds(mptg_ctx* ctx, const mptg_space_desc* space, const double* lo, const double* hi, void** out) {
+    const std::vector<unsigned char> host = packBounds(space, lo, hi);
+    if (int rc = scratch(ctx, 8, host.size(), out)) return rc;
+    MPTG_CUDA(ctx, cudaMemcpyAsync(*out, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return MPTG_OK;
 }
 
 bool spaceOk(const mptg_space_desc* space) {
@@ -238,12 +249,10 @@ int mptg_sample_batch_dev(mptg_ctx* ctx, const mptg_space_desc* space, const dou
     if (n == 0) return MPTG_OK;
     MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
     void* bounds = nullptr;
-    if (int rc = uploadBounds(ctx, space, lo, hi, &bounds)) return rc;
+    if (int rc = stageBounds(ctx, space, lo, hi, &bounds)) return rc;
     if (space->scalar == MPTG_F32) launchSample<float>(ctx, space, bounds, seed, first, n, nullptr, 0.0, out_dev);
     else launchSample<double>(ctx, space, bounds, seed, first, n, nullptr, 0.0, out_dev);
     MPTG_LAUNCHED(ctx);
-    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the bounds buffer is released below
-    cudaFree(bounds);
     return MPTG_OK;
 }
 
@@ -271,7 +280,7 @@ int mptg_sample_transform_batch(mptg_ctx* ctx, const mptg_space_desc* space, con
     void *dU, *dOut, *bounds = nullptr;
     if (int rc = scratch(ctx, 0, ub, &dU)) return rc;
     if (int rc = scratch(ctx, 1, ob, &dOut)) return rc;
-    if (int rc = uploadBounds(ctx, space, lo, hi, &bounds)) return rc;
+    if (int rc = stageBounds(ctx, space, lo, hi, &bounds)) return rc;
     MPTG_CUDA(ctx, cudaMemcpyAsync(dU, uniforms, ub, cudaMemcpyHostToDevice, ctx->stream));
     if (space->scalar == MPTG_F32)
         transformKernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>(makeDevSpace<float>(*space), (const float*)bounds, (const float*)bounds + D,
@@ -282,7 +291,6 @@ int mptg_sample_transform_batch(mptg_ctx* ctx, const mptg_space_desc* space, con
     MPTG_LAUNCHED(ctx);
     MPTG_CUDA(ctx, cudaMemcpyAsync(out, dOut, ob, cudaMemcpyDeviceToHost, ctx->stream));
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(bounds);
     return MPTG_OK;
 }
 
