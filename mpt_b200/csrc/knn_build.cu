@@ -40,17 +40,23 @@ struct SegLevel {        // one binary level: segments in position order
     uint32_t nSeg;
 };
 
-// canonical AoS copy: SO(3) parts flipped to w >= 0
-__global__ void canonKernel(DevSpace<float> sp, const float* __restrict__ pts, uint32_t stride, uint32_t n, float* __restrict__ canon) {
+// canonical AoS copy: SO(3) parts flipped to w >= 0.  `canon` (float) drives the partition (extents, sort keys);
+// double-precision sets also keep the exact values in `exact` for the emitted leaves and boxes -- rounding to
+// float is monotone, so any partition of the rounded values is a valid partition of the exact ones.
+template <typename S>
+__global__ void canonKernel(DevSpace<float> sp, const S* __restrict__ pts, uint32_t stride, uint32_t n, float* __restrict__ canon,
+                            S* __restrict__ exact) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int p = 0; p < sp.nParts; ++p) {
         const int off = sp.off[p];
         bool flip = false;
-        if (sp.kind[p] == MPTG_PART_SO3) flip = pts[(size_t)(off + 3) * stride + i] < 0.0f;
+        if (sp.kind[p] == MPTG_PART_SO3) flip = pts[(size_t)(off + 3) * stride + i] < S(0);
         for (int j = 0; j < sp.dim[p]; ++j) {
-            const float v = pts[(size_t)(off + j) * stride + i];
-            canon[(size_t)i * sp.D + off + j] = flip ? -v : v;
+            const S v = pts[(size_t)(off + j) * stride + i];
+            const S w = flip ? -v : v;
+            canon[(size_t)i * sp.D + off + j] = (float)w;
+            if (sizeof(S) == 8) exact[(size_t)i * sp.D + off + j] = w;
         }
     }
 }
@@ -133,9 +139,10 @@ __global__ void splitKernel(SegLevel lv, uint32_t* __restrict__ segOf, uint32_t 
 
 // ---- emit the device image
 // one warp per leaf: blocked points, perm, leaf box (SoA per level: lo[c][nNodes], hi[c][nNodes])
-__global__ void __launch_bounds__(256) leafEmitKernel(const float* __restrict__ canon, const uint32_t* __restrict__ ids, uint32_t n, int D,
-                                                      uint32_t nLeaves, float* __restrict__ leafPts, uint32_t* __restrict__ perm,
-                                                      float* __restrict__ lo, float* __restrict__ hi) {
+template <typename S>
+__global__ void __launch_bounds__(256) leafEmitKernel(const S* __restrict__ canon, const uint32_t* __restrict__ ids, uint32_t n, int D,
+                                                      uint32_t nLeaves, S* __restrict__ leafPts, uint32_t* __restrict__ perm,
+                                                      S* __restrict__ lo, S* __restrict__ hi) {
     const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (leaf >= nLeaves) return;
@@ -144,49 +151,53 @@ __global__ void __launch_bounds__(256) leafEmitKernel(const float* __restrict__ 
     const uint32_t src = ids[real ? p : n - 1];  // padding repeats the last point (perm marks it unused)
     perm[p] = real ? src : MPTG_NO_INDEX;
     for (int c = 0; c < D; ++c) {
-        const float v = canon[(size_t)src * D + c];
+        const S v = canon[(size_t)src * D + c];
         leafPts[((size_t)leaf * D + c) * 32u + lane] = v;
-        float mn = v, mx = v;
+        S mn = v, mx = v;
         for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const S a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
         }
         if (lane == 0) lo[(size_t)c * nLeaves + leaf] = mn, hi[(size_t)c * nLeaves + leaf] = mx;
     }
 }
 
 // one warp per parent: box of its (up to) 32 children
-__global__ void __launch_bounds__(256) parentBoxKernel(const float* __restrict__ clo, const float* __restrict__ chi, uint32_t nChild, int D,
-                                                       uint32_t nParent, float* __restrict__ lo, float* __restrict__ hi) {
+template <typename S>
+__global__ void __launch_bounds__(256) parentBoxKernel(const S* __restrict__ clo, const S* __restrict__ chi, uint32_t nChild, int D,
+                                                       uint32_t nParent, S* __restrict__ lo, S* __restrict__ hi) {
     const uint32_t parent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (parent >= nParent) return;
     const uint32_t child = parent * 32u + lane;
     for (int c = 0; c < D; ++c) {
-        float mn = child < nChild ? clo[(size_t)c * nChild + child] : INFINITY;
-        float mx = child < nChild ? chi[(size_t)c * nChild + child] : -INFINITY;
+        S mn = child < nChild ? clo[(size_t)c * nChild + child] : (S)INFINITY;
+        S mx = child < nChild ? chi[(size_t)c * nChild + child] : (S)-INFINITY;
         for (int o = 16; o > 0; o >>= 1) {
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const S a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
         }
         if (lane == 0) lo[(size_t)c * nParent + parent] = mn, hi[(size_t)c * nParent + parent] = mx;
     }
 }
 
 // SoA boxes -> blocked [block][2D][32]; and for SE(3) the half2 (lo down, hi up) copies
-__global__ void boxBlockKernel(const float* __restrict__ lo, const float* __restrict__ hi, uint32_t nNodes, int D, float* __restrict__ box,
+template <typename S>
+__global__ void boxBlockKernel(const S* __restrict__ lo, const S* __restrict__ hi, uint32_t nNodes, int D, S* __restrict__ box,
                                uint32_t* __restrict__ boxH) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // node slot, padded to a multiple of 32
     const uint32_t nSlots = ((nNodes + 31u) / 32u) * 32u;
     if (j >= nSlots) return;
     const uint32_t b = j >> 5, ln = j & 31;
     for (int c = 0; c < D; ++c) {
-        const float l = j < nNodes ? lo[(size_t)c * nNodes + j] : INFINITY;
-        const float h = j < nNodes ? hi[(size_t)c * nNodes + j] : -INFINITY;
+        const S l = j < nNodes ? lo[(size_t)c * nNodes + j] : (S)INFINITY;
+        const S h = j < nNodes ? hi[(size_t)c * nNodes + j] : (S)-INFINITY;
         box[((size_t)b * 2 * D + c) * 32u + ln] = l;
         box[((size_t)b * 2 * D + D + c) * 32u + ln] = h;
-        if (boxH) {
-            const __half hl = __float2half_rd(l), hh = __float2half_ru(h);
+        if (boxH) {  // float sets only
+            const __half hl = __float2half_rd((float)l), hh = __float2half_ru((float)h);
             boxH[((size_t)b * 7 + c) * 32u + ln] = (uint32_t)__half_as_ushort(hl) | ((uint32_t)__half_as_ushort(hh) << 16);
         }
     }
@@ -260,7 +271,8 @@ Levels makeLevels(uint32_t n) {
 
 }  // namespace
 
-int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t n) {
+template <typename S>
+int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const S* ptsDev, uint32_t stride, uint32_t n) {
     if (n == 0) {
         ix.count = 0;
         return MPTG_OK;
@@ -268,7 +280,7 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
     const DevSpace<float> sp = makeDevSpace<float>(space);
     const int D = sp.D;
     cudaStream_t st = ctx->stream;
-    const bool compressed = classifySpace(space) == SHAPE_SE3;  // half copies; coordinates beyond the half range fall back below
+    const bool compressed = sizeof(S) == 4 && classifySpace(space) == SHAPE_SE3;  // half copies; coordinates beyond the half range fall back below
 
     // ---- geometry of the image
     KnnIndex nx;
@@ -287,13 +299,13 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
         bytes += (b + 255) & ~(size_t)255;
         return o;
     };
-    const size_t oPts = take((size_t)D * nx.nPad * sizeof(float));
+    const size_t oPts = take((size_t)D * nx.nPad * sizeof(S));
     const size_t oPerm = take((size_t)nx.nPad * sizeof(uint32_t));
     size_t oBox[BVH_MAXL] = {0, 0, 0, 0, 0}, oBoxH[BVH_MAXL] = {0, 0, 0, 0, 0}, oLeafH = 0;
     uint32_t nBlocks[BVH_MAXL] = {0, 0, 0, 0, 0};
     for (int l = 0; l <= nx.top; ++l) {
         nBlocks[l] = (nx.nNodes[l] + 31) / 32;
-        oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(float));
+        oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(S));
     }
     if (compressed) {
         oLeafH = take((size_t)nx.nNodes[0] * 4 * 32 * sizeof(uint32_t));
@@ -328,16 +340,17 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
         wbytes += (b + 255) & ~(size_t)255;
         return o;
     };
-    const size_t wCanon = wtake((size_t)n * D * 4), wKey0 = wtake((size_t)n * 8), wKey1 = wtake((size_t)n * 8), wId0 = wtake((size_t)n * 4),
+    const size_t wCanon = wtake((size_t)n * D * 4), wExact = wtake(sizeof(S) == 8 ? (size_t)n * D * 8 : 0), wKey0 = wtake((size_t)n * 8), wKey1 = wtake((size_t)n * 8), wId0 = wtake((size_t)n * 4),
                  wId1 = wtake((size_t)n * 4), wSeg = wtake((size_t)n * 4), wMin = wtake((size_t)maxSeg * D * 4),
                  wMax = wtake((size_t)maxSeg * D * 4), wAxis = wtake((size_t)maxSeg * 4), wTab = wtake(nTab * 4 * 4), wCub = wtake(cubBytes),
                  wErr = wtake(16);
     size_t wLo[BVH_MAXL], wHi[BVH_MAXL];
-    for (int l = 0; l <= nx.top; ++l) wLo[l] = wtake((size_t)D * nx.nNodes[l] * 4), wHi[l] = wtake((size_t)D * nx.nNodes[l] * 4);
+    for (int l = 0; l <= nx.top; ++l) wLo[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S)), wHi[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S));
     void* wbase;
     if (int rc = scratch(ctx, 7, wbytes, &wbase)) return rc;
     char* W = (char*)wbase;
     float* canon = (float*)(W + wCanon);
+    S* exact = sizeof(S) == 8 ? (S*)(W + wExact) : (S*)canon;  // what the emitted leaves and boxes are made of
     unsigned long long* keys[2] = {(unsigned long long*)(W + wKey0), (unsigned long long*)(W + wKey1)};
     uint32_t* ids[2] = {(uint32_t*)(W + wId0), (uint32_t*)(W + wId1)};
     uint32_t* segOf = (uint32_t*)(W + wSeg);
@@ -357,7 +370,7 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
 
     // ---- 1. canonical copy, 2. one sort per binary level
     const uint32_t g256 = (n + 255) / 256;
-    canonKernel<<<g256, 256, 0, st>>>(sp, ptsDev, stride, n, canon);
+    canonKernel<S><<<g256, 256, 0, st>>>(sp, ptsDev, stride, n, canon, exact);
     MPTG_LAUNCHED(ctx);
     iotaKernel<<<g256, 256, 0, st>>>(ids[0], segOf, n);
     MPTG_LAUNCHED(ctx);
@@ -387,20 +400,19 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
 
     // ---- 3. device image
     char* M = (char*)mem;
-    float* lo0 = (float*)(W + wLo[0]);
-    float* hi0 = (float*)(W + wHi[0]);
-    leafEmitKernel<<<(nx.nNodes[0] * 32 + 255) / 256, 256, 0, st>>>(canon, ids[cur], n, D, nx.nNodes[0], (float*)(M + oPts),
-                                                                   (uint32_t*)(M + oPerm), lo0, hi0);
+    S* lo0 = (S*)(W + wLo[0]);
+    S* hi0 = (S*)(W + wHi[0]);
+    leafEmitKernel<S><<<(nx.nNodes[0] * 32 + 255) / 256, 256, 0, st>>>(exact, ids[cur], n, D, nx.nNodes[0], (S*)(M + oPts),
+                                                                      (uint32_t*)(M + oPerm), lo0, hi0);
     MPTG_LAUNCHED(ctx);
     for (int l = 1; l <= nx.top; ++l) {
-        parentBoxKernel<<<(nx.nNodes[l] * 32 + 255) / 256, 256, 0, st>>>((const float*)(W + wLo[l - 1]), (const float*)(W + wHi[l - 1]),
-                                                                        nx.nNodes[l - 1], D, nx.nNodes[l], (float*)(W + wLo[l]),
-                                                                        (float*)(W + wHi[l]));
+        parentBoxKernel<S><<<(nx.nNodes[l] * 32 + 255) / 256, 256, 0, st>>>((const S*)(W + wLo[l - 1]), (const S*)(W + wHi[l - 1]),
+                                                                           nx.nNodes[l - 1], D, nx.nNodes[l], (S*)(W + wLo[l]), (S*)(W + wHi[l]));
         MPTG_LAUNCHED(ctx);
     }
     for (int l = 0; l <= nx.top; ++l) {
-        boxBlockKernel<<<(nBlocks[l] * 32 + 255) / 256, 256, 0, st>>>((const float*)(W + wLo[l]), (const float*)(W + wHi[l]), nx.nNodes[l], D,
-                                                                     (float*)(M + oBox[l]), compressed ? (uint32_t*)(M + oBoxH[l]) : nullptr);
+        boxBlockKernel<S><<<(nBlocks[l] * 32 + 255) / 256, 256, 0, st>>>((const S*)(W + wLo[l]), (const S*)(W + wHi[l]), nx.nNodes[l], D,
+                                                                        (S*)(M + oBox[l]), compressed ? (uint32_t*)(M + oBoxH[l]) : nullptr);
         MPTG_LAUNCHED(ctx);
     }
     float errQ = 0.f, errT = 0.f;
@@ -432,6 +444,13 @@ int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, 
     }
     ix = nx;
     return MPTG_OK;
+}
+
+int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t n) {
+    return knnBuildIndexGpuT<float>(ctx, ix, space, ptsDev, stride, n);
+}
+int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const double* ptsDev, uint32_t stride, uint32_t n) {
+    return knnBuildIndexGpuT<double>(ctx, ix, space, ptsDev, stride, n);
 }
 
 }  // namespace mptg

@@ -635,11 +635,10 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
         ix.count = 0;
         return MPTG_OK;
     }
-    // float32 spaces are built on the device (knn_build.cu); MPTG_KNN_HOST_BUILD=1 keeps the host path
-    // below (the double-precision path) for comparison.
-    if constexpr (sizeof(S) == 4) {
+    // the index is built on the device (knn_build.cu); MPTG_KNN_HOST_BUILD=1 keeps the host path below for comparison
+    {
         const char* env = getenv("MPTG_KNN_HOST_BUILD");
-        if (!(env && env[0] == '1')) return knnBuildIndexGpu(ctx, ix, space, (const float*)ptsDev, stride, n);
+        if (!(env && env[0] == '1')) return knnBuildIndexGpu(ctx, ix, space, ptsDev, stride, n);
     }
     const DevSpace<S> sp = makeDevSpace<S>(space);
     const int D = sp.D;

@@ -36,5 +36,6 @@ inline void knnIndexFree(KnnIndex& ix) {
 
 // Device build of the index for float32 spaces (knn_build.cu).  Fills `ix` like the host build does.
 int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t n);
+int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const double* ptsDev, uint32_t stride, uint32_t n);
 
 }  // namespace mptg

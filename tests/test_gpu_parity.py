@@ -136,6 +136,29 @@ def test_knn_bvh_double(ctx, oracle):
     assert_knn_equal(nn.nearest(q, 16), oracle.knn(sp, pts, q, 16))
 
 
+@pytest.mark.parametrize("scalar", [m.F32, m.F64])
+def test_knn_index_device_build_equals_host_build(ctx, oracle, scalar, monkeypatch):
+    """The index built on the device (knn_build.cu; double-precision sets are partitioned by their float roundings
+    and emitted exactly) and the host build of the same tree give the same, exact, answers."""
+    dt = np.float32 if scalar == m.F32 else np.float64
+    for sp, pts, q in (
+        (m.se3_space(50, 1, scalar), W.se3_states(70_000, 11, dtype=dt), W.se3_states(300, 12, dtype=dt)),
+        (m.lp_space(2, 2, scalar), W.box_states(50_000, 2, 13, 0.0, [3976, 2603], dt), W.box_states(300, 2, 14, 0.0, [3976, 2603], dt)),
+        (m.lp_space(8, 1, scalar), W.box_states(40_000, 8, 15, -np.pi, np.pi, dt), W.box_states(200, 8, 16, -np.pi, np.pi, dt)),
+    ):
+        want = oracle.knn(sp, pts, q, 20)
+        results = []
+        for host in ("0", "1"):
+            monkeypatch.setenv("MPTG_KNN_HOST_BUILD", host)
+            nn = m.Nearest(ctx, sp, 1 << 17, m.KNN_BVH)
+            nn.insert(pts)
+            nn.build_index()
+            results.append(nn.nearest(q, 20))
+            nn.close()
+        assert_knn_equal(results[0], want)
+        assert_knn_equal(results[1], want)
+
+
 def test_knn_degenerate_point_sets(ctx, oracle):
     """All points identical / on a line / two clusters: zero-extent boxes, massive ties (index order decides)."""
     sp = m.se3_space(50, 1)
