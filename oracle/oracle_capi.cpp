@@ -312,6 +312,20 @@ int orc_sample_batch(const mptg_space_desc* sp, const double* lo, const double* 
     }
     return 0;
 }
+// the raw uniforms of samples first .. first+n-1: positions 0 .. perState-1 of each sample's stream (position 0 is the
+// goal-bias draw); float or double per `scalar`
+int orc_sample_uniforms(int scalar, uint64_t seed, uint64_t first, uint32_t n, int perState, void* out) {
+    for (uint32_t i = 0; i < n; ++i) {
+        if (scalar == MPTG_F32) {
+            SampleStream<float> st(seed, first + i);
+            for (int j = 0; j < perState; ++j) ((float*)out)[(size_t)i * perState + j] = st.next();
+        } else {
+            SampleStream<double> st(seed, first + i);
+            for (int j = 0; j < perState; ++j) ((double*)out)[(size_t)i * perState + j] = st.next();
+        }
+    }
+    return 0;
+}
 int orc_sample_from_uniforms(const mptg_space_desc* sp, const double* lo, const double* hi, const void* uniforms, int perState, uint32_t n,
                              void* out) {
     int D = 0;

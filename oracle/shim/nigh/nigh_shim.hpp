@@ -42,6 +42,7 @@ template <class T, class M> struct Space;
 template <class S, int N, int p>
 struct Space<Eigen::Matrix<S, N, 1>, LP<p>> {
     using Type = Eigen::Matrix<S, N, 1>; using Distance = S; using Metric = LP<p>;
+    static constexpr int kDimensions = N;
     constexpr unsigned dimensions() const { return N; }
     static S& coeff(Type& q, std::size_t i) { return q[(int)i]; }
     static const S& coeff(const Type& q, std::size_t i) { return q[(int)i]; }

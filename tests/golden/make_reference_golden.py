@@ -66,6 +66,14 @@ def main():
     gq[0] = [0.25, 0.25, 0.25]
     out["goal_q"] = gq
     out["goal_is"], out["goal_dist"] = ref.goal_l2_3([0.25, 0.25, 0.25], 1e-6, gq)
+    # the reference's own PRRT planner (oracle/ref_planner.cpp) on a synthetic occupancy grid, replayed sample stream
+    from tests.kats import PRRT_CASES, prrt_scene
+    occ, lo, hi, start, goal = prrt_scene()
+    for i, (rng_, n, goal_radius, goal_bias, seed) in enumerate(PRRT_CASES):
+        u = orc.sample_uniforms(m.F64, seed, 0, n, 3)
+        st, par, gn = ref.prrt_grid(occ, lo, hi, start, goal, goal_radius, goal_bias, rng_, u)
+        out[f"prrt{i}_states"], out[f"prrt{i}_parents"], out[f"prrt{i}_goal"] = st, par, np.uint32(gn)
+        print(f"prrt case {i}: {n} samples -> {st.shape[0]} nodes, goal node {gn}")
     path = Path(__file__).with_name("reference_golden.npz")
     np.savez_compressed(path, **out)
     print(path, "grid link", out["grid_link"].mean(), "holo link", out["holo_link"].mean(), "arm5 link", out["arm5_link"].mean(),

@@ -97,3 +97,45 @@ def run_interpolate_kats(interp_fn):
         if not chk([float(x) for x in got]):
             bad.append(f"{name}: got {got!r}")
     return bad
+
+
+NO_INDEX = 0xFFFFFFFF
+
+
+def replay_prrt(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, seed, waves, W):
+    """Worker::addSample (src/mpt/impl/prrt/prrt.hpp:411-452) on the oracle, one wave at a time, on the same samples."""
+    nodes = [np.asarray(start, dtype=sp.dtype).reshape(1, -1)]
+    parents = [np.array([NO_INDEX], dtype=np.uint32)]
+    goal_node, drawn = NO_INDEX, 0
+    for _ in range(waves):
+        tree = np.concatenate(nodes)
+        biased = goal is not None and goal_bias > 0 and goal_node == NO_INDEX
+        smp = oracle.sample(sp, lo, hi, seed, drawn, W, goal if biased else None, goal_bias)
+        drawn += W
+        idx, dist, cnt = oracle.knn(sp, tree, smp, 1)
+        near, d = tree[idx[:, 0]], dist[:, 0]
+        to = oracle.steer(sp, near, smp, d, rng)
+        keep = (cnt > 0) & (d != 0) & (og.valid(to) != 0) & (og.link(near, to) != 0)
+        fresh = to[keep]
+        if goal is not None and goal_node == NO_INDEX and len(fresh):
+            hit = np.nonzero(oracle.distance(sp, fresh, np.broadcast_to(np.asarray(goal, dtype=sp.dtype), fresh.shape)) <= sp.dtype(goal_radius))[0]
+            if hit.size:
+                goal_node = tree.shape[0] + int(hit[0])
+        nodes.append(fresh)
+        parents.append(idx[keep, 0].astype(np.uint32))
+    return np.concatenate(nodes), np.concatenate(parents), goal_node
+
+
+# The reference's own PRRT (oracle/ref_planner.cpp) vs the planner-loop restatement above vs the device-resident PRRT:
+# (range, samples, goal radius, goal bias, seed) on prrt_scene(); results in tests/golden/reference_golden.npz.
+PRRT_CASES = [(25.0, 3000, 12.0, 0.05, 99), (float("inf"), 800, 12.0, 0.05, 99), (40.0, 2000, 1e-6, 0.0, 7), (60.0, 2500, 5.0, 0.2, 2026)]
+
+
+def prrt_scene():
+    from mpt_b200 import workloads as W
+
+    occ = W.synthetic_grid(500, 400, seed=2)
+    free = np.argwhere(occ == 0)
+    start = free[len(free) // 7][::-1].astype(np.float64)
+    goal = free[-len(free) // 9][::-1].astype(np.float64)
+    return occ, [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], start, goal

@@ -89,6 +89,12 @@ class Oracle:
         self.lib.orc_sample_batch(space.ref, _ptr(lo), _ptr(hi), C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), _ptr(g), C.c_double(goal_bias), _ptr(out))
         return out
 
+    def sample_uniforms(self, scalar, seed, first, n, per_state):
+        """Raw uniforms of the sample streams: [n, per_state], column 0 = the goal-bias draw."""
+        out = np.empty((n, per_state), dtype=np.float32 if scalar == 4 else np.float64)
+        self.lib.orc_sample_uniforms(C.c_int(scalar), C.c_uint64(seed), C.c_uint64(first), C.c_uint32(n), C.c_int(per_state), _ptr(out))
+        return out
+
     def sample_from_uniforms(self, space, lo, hi, uniforms, per_state):
         lo = np.ascontiguousarray(np.broadcast_to(np.asarray(lo, dtype=np.float64), (space.scalars,)))
         hi = np.ascontiguousarray(np.broadcast_to(np.asarray(hi, dtype=np.float64), (space.scalars,)))

@@ -12,6 +12,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "oracle" / "_ref" / "libref.so"
+LIB_PLANNER = ROOT / "oracle" / "_ref" / "libref_planner.so"
 REFERENCE = Path("/root/reference")
 _P = C.c_void_p
 VALID_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_void_p)
@@ -24,7 +25,7 @@ def available() -> bool:
 def load():
     if REFERENCE.exists():
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    return Ref(C.CDLL(str(LIB)))
+    return Ref(C.CDLL(str(LIB)), C.CDLL(str(LIB_PLANNER)))
 
 
 def _p(a):
@@ -32,8 +33,24 @@ def _p(a):
 
 
 class Ref:
-    def __init__(self, lib):
+    def __init__(self, lib, planner_lib=None):
         self.lib = lib
+        self.planner_lib = planner_lib
+
+    def prrt_grid(self, occ, lo, hi, start, goal, goal_radius, goal_bias, rng, uniforms, capacity=1 << 16):
+        """The reference's Planner<Scenario, PRRT<single_threaded>> (oracle/ref_planner.cpp) on an occupancy grid, one
+        iteration per row of `uniforms` ([n, 3]: goal-bias draw, x, y).  Returns (states, parents, goal_node)."""
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        lo, hi, start, goal = (np.ascontiguousarray(x, dtype=np.float64) for x in (lo, hi, start, goal))
+        u = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1, 3)
+        states = np.empty((capacity, 2), np.float64)
+        parents = np.empty(capacity, np.uint32)
+        n, goal_node, used = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        rc = self.planner_lib.ref_prrt_grid(occ.shape[1], occ.shape[0], _p(occ), _p(lo), _p(hi), _p(start), _p(goal), C.c_double(goal_radius),
+                                            C.c_double(goal_bias), C.c_double(rng), _p(u), C.c_uint32(u.shape[0]), _p(states), _p(parents),
+                                            C.c_uint32(capacity), C.byref(n), C.byref(goal_node), C.byref(used))
+        assert rc == 0 and used.value == u.shape[0], f"ref_prrt_grid rc={rc}, used {used.value} of {u.shape[0]}"
+        return states[: n.value].copy(), parents[: n.value].copy(), goal_node.value
 
     def interpolate(self, kind, a, b, t):
         dt = np.float32 if kind == "se3_f32" else np.float64

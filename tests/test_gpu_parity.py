@@ -419,30 +419,6 @@ def test_device_sampler_matches_oracle_and_reference_kats(ctx, oracle):
             assert np.array_equal(got, want), f"sampler differs for {sp.parts} scalar {sp.scalar}"
 
 
-def _replay_prrt(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, seed, waves, W):
-    """Worker::addSample (src/mpt/impl/prrt/prrt.hpp:411-452) on the oracle, one wave at a time, on the same samples."""
-    nodes = [np.asarray(start, dtype=sp.dtype).reshape(1, -1)]
-    parents = [np.array([m.NO_INDEX], dtype=np.uint32)]
-    goal_node, drawn = m.NO_INDEX, 0
-    for _ in range(waves):
-        tree = np.concatenate(nodes)
-        biased = goal is not None and goal_bias > 0 and goal_node == m.NO_INDEX
-        smp = oracle.sample(sp, lo, hi, seed, drawn, W, goal if biased else None, goal_bias)
-        drawn += W
-        idx, dist, cnt = oracle.knn(sp, tree, smp, 1)
-        near, d = tree[idx[:, 0]], dist[:, 0]
-        to = oracle.steer(sp, near, smp, d, rng)
-        keep = (cnt > 0) & (d != 0) & (og.valid(to) != 0) & (og.link(near, to) != 0)
-        fresh = to[keep]
-        if goal is not None and goal_node == m.NO_INDEX and len(fresh):
-            hit = np.nonzero(oracle.distance(sp, fresh, np.broadcast_to(np.asarray(goal, dtype=sp.dtype), fresh.shape)) <= sp.dtype(goal_radius))[0]
-            if hit.size:
-                goal_node = tree.shape[0] + int(hit[0])
-        nodes.append(fresh)
-        parents.append(idx[keep, 0].astype(np.uint32))
-    return np.concatenate(nodes), np.concatenate(parents), goal_node
-
-
 def test_device_prrt_replays_the_reference_loop_on_a_grid(ctx, oracle):
     """PNG-style occupancy grid, planar L2 double states (png_2d_scenario.hpp): the device-resident tree must be
     the tree the reference's addSample loop builds from the same samples -- states bit-identical, same parents,
@@ -460,7 +436,7 @@ def test_device_prrt_replays_the_reference_loop_on_a_grid(ctx, oracle):
         for _ in range(waves):
             pl.wave(W_)
         states, parents = pl.tree()
-        want_states, want_parents, want_goal = _replay_prrt(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 99, waves, W_)
+        want_states, want_parents, want_goal = kats.replay_prrt(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 99, waves, W_)
         assert pl.samples_drawn == waves * W_
         assert states.shape == want_states.shape and states.shape[0] > 50
         assert np.array_equal(states, want_states) and np.array_equal(parents, want_parents)

@@ -11,7 +11,7 @@ import pytest
 
 import mpt_b200 as m
 from mpt_b200 import workloads as W
-from tests import reference_binding
+from tests import kats, reference_binding
 
 ROOT = Path(__file__).resolve().parent.parent
 G = np.load(ROOT / "tests" / "golden" / "reference_golden.npz")
@@ -77,6 +77,31 @@ def test_goal_state_semantics():
     assert np.allclose(G["goal_dist"], np.where(d <= 1e-6, 0.0, d - 1e-6), rtol=0, atol=1e-15)
 
 
+def test_planner_loop_restatement_builds_the_reference_planners_tree(oracle):
+    """Row a11.  The reference's own Planner<Scenario, PRRT<single_threaded>> -- its Worker::solve / addSample loop,
+    UniformBoxSampler, goal-biased sampling, GoalState, interpolate, PNG2dScenario::valid / link, compiled from
+    /root/reference (oracle/ref_planner.cpp), fed with the product's sample stream -- and the oracle's restatement of
+    that loop (one sample per wave) build the same tree: states bit-identical, same parents, same first goal node."""
+    occ, lo, hi, start, goal = kats.prrt_scene()
+    sp, og = m.lp_space(2, 2, m.F64), oracle.grid(occ)
+    for i, (rng, n, goal_radius, goal_bias, seed) in enumerate(kats.PRRT_CASES):
+        states, parents, goal_node = kats.replay_prrt(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, seed, n, 1)
+        assert states.shape[0] > 200
+        assert np.array_equal(states, G[f"prrt{i}_states"]) and np.array_equal(parents, G[f"prrt{i}_parents"]), i
+        assert goal_node == int(G[f"prrt{i}_goal"]), i
+    assert int(G["prrt0_goal"]) != kats.NO_INDEX and int(G["prrt2_goal"]) == kats.NO_INDEX  # both outcomes are covered
+
+
+@pytest.mark.skipif(not reference_binding.REFERENCE.exists(), reason="/root/reference not present (GPU box)")
+def test_reference_planner_live_reproduces_committed_tree(oracle):
+    ref = reference_binding.load()
+    occ, lo, hi, start, goal = kats.prrt_scene()
+    rng, n, goal_radius, goal_bias, seed = kats.PRRT_CASES[3]
+    u = oracle.sample_uniforms(m.F64, seed, 0, n, 3)
+    states, parents, goal_node = ref.prrt_grid(occ, lo, hi, start, goal, goal_radius, goal_bias, rng, u)
+    assert np.array_equal(states, G["prrt3_states"]) and np.array_equal(parents, G["prrt3_parents"]) and goal_node == int(G["prrt3_goal"])
+
+
 @pytest.mark.skipif(not reference_binding.REFERENCE.exists(), reason="/root/reference not present (GPU box)")
 def test_reference_live_reproduces_committed_vectors():
     """Where the reference tree exists, rebuild oracle/_ref from its sources and re-run it: the committed
@@ -117,3 +142,21 @@ def test_device_dmv_matches_reference(ctx):
     full = np.maximum(np.ceil(dist * (np.float32(1.0) / np.float32(G["dmv_step"]))).astype(np.int64), 1)
     assert np.array_equal(full[okm], G["dmv_states"][okm])
     assert int(full[okm].sum()) + int((~okm).sum()) <= states <= int(full.sum())
+
+
+@pytest.mark.gpu
+def test_device_prrt_builds_the_reference_planners_tree(ctx):
+    """Row a11 on the device: the device-resident PRRT, one sample per wave, builds the tree the reference's own PRRT
+    class built from the same sample stream (committed vectors) -- node for node, bit for bit."""
+    occ, lo, hi, start, goal = kats.prrt_scene()
+    sp, sc = m.lp_space(2, 2, m.F64), m.Scenario.grid(ctx, occ, m.F64)
+    for i in (1, 3):
+        rng, n, goal_radius, goal_bias, seed = kats.PRRT_CASES[i]
+        pl = m.DevicePRRT(sc, sp, lo, hi, range=rng, goal=goal, goal_radius=goal_radius, goal_bias=goal_bias, seed=seed, capacity=8192, max_wave=64)
+        pl.add_start(start)
+        for _ in range(n):
+            pl.wave(1)
+        states, parents = pl.tree()
+        assert np.array_equal(states, G[f"prrt{i}_states"]) and np.array_equal(parents, G[f"prrt{i}_parents"]), i
+        assert pl.goal_node == int(G[f"prrt{i}_goal"]), i
+        pl.close()
