@@ -7,9 +7,11 @@ loudly when there is no sm_100a device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libmptg.so"
+# MPTG_LIB: another build of the same library (kernel experiments, tools/build_variant.sh)
+LIB_PATH = Path(os.environ.get("MPTG_LIB") or Path(__file__).resolve().parent / "_lib" / "libmptg.so")
 
 MAX_PARTS = 8
 MAX_SCALARS = 64

@@ -55,6 +55,40 @@ def build_mock() -> Path:
     return build_program(ROOT / "tests" / "cpp" / "planner_test.cpp", bdir / "planner_test_mock", bdir, "mptg_mock", defines=("MPTG_TEST_MOCK_BACKEND",))
 
 
+REFERENCE = Path("/root/reference")
+
+
+def build_reference_parity(mock: bool = True) -> Path | None:
+    """TEST ONLY: tests/cpp/reference_planner_parity.cpp -- the reference's own planner classes (compiled from
+    /root/reference against the stand-in headers under oracle/shim) next to the wave planners, in one program.
+    Linked against the CPU mock of the C ABI (mock=True) or against libmptg.so.  Needs /root/reference; where it is
+    absent (GPU box) the binary built here is used if it travelled with the snapshot, else None."""
+    bdir = ROOT / "tests" / "cpp" / "_build"
+    out = bdir / ("reference_planner_parity_mock" if mock else "reference_planner_parity")
+    if not REFERENCE.exists():
+        return out if out.exists() else None
+    src = ROOT / "tests" / "cpp" / "reference_planner_parity.cpp"
+    if mock:
+        build_mock()
+        lib_dir, lib, defines = bdir, "mptg_mock", ["-DMPTG_TEST_MOCK_BACKEND"]
+    else:
+        from . import build as b
+
+        b.build()
+        lib_dir, lib, defines = b.LIBDIR, "mptg", []
+    deps = [src, *sorted((ROOT / "include" / "mptg").glob("*")), *sorted((ROOT / "oracle" / "shim").rglob("*.hpp"))]
+    if _stale(out, deps):
+        rpath = "$ORIGIN/" + str(Path(*[".."] * len(out.parent.relative_to(ROOT).parts)) / lib_dir.relative_to(ROOT))
+        cmd = [CXX, "-std=c++17", "-O2", "-g", "-DNDEBUG", "-ffp-contract=off", "-Wno-unused-function", "-Wno-deprecated-declarations", *defines,
+               f"-I{ROOT / 'oracle' / 'shim'}", f"-I{REFERENCE / 'src'}", f"-I{REFERENCE / 'demo'}", f"-I{ROOT / 'include'}", str(src), "-o", str(out),
+               f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{rpath}", "-lpthread"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}")
+    return out
+
+
 if __name__ == "__main__":
     for p in build():
         print(p)
+    print(build_reference_parity(mock=False))

@@ -185,6 +185,9 @@ struct BvhWalk {
     WarpTopK<S, KPL> top;
     int lane;
     unsigned long long leaves = 0, inner = 0;
+#ifdef MPTG_KNN_PROBE
+    unsigned long long useful = 0, cand = 0;  // experiment: leaf visits with a surviving lane, surviving lanes
+#endif
 
     __device__ __forceinline__ BvhWalk(const BvhArgs<S>& args, const S* q, int ln) : a(args), myq(q), lane(ln) {}
 
@@ -366,6 +369,13 @@ struct BvhWalk {
         const float sT = fmaxf(sqrtApprox(s2) - eT, 0.0f);
         const float t = fmaxf(__fmaf_rn(-2.0f, fabsf(dot), dotC), 0.0f);
         const bool maybe = __fmaf_rn(w0, sqrtApprox(t), w1 * sT) <= thrS;
+#ifdef MPTG_KNN_PROBE
+        {
+            const unsigned pb = __ballot_sync(FULL_MASK, maybe);
+            useful += pb != 0u;
+            cand += __popc(pb);
+        }
+#endif
         if (!__any_sync(FULL_MASK, maybe)) return;
         leafExact(node, maybe);  // rare: fetch the exact points and evaluate the true distance
     }
@@ -524,6 +534,10 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
     if (lane == 0 && a.stats) {
         atomicAdd(a.stats + 0, w.leaves);
         atomicAdd(a.stats + 1, w.inner);
+#ifdef MPTG_KNN_PROBE
+        atomicAdd(a.stats + 2, w.useful);
+        atomicAdd(a.stats + 3, w.cand);
+#endif
     }
 }
 
@@ -902,6 +916,9 @@ inline int knnIndexReadStats(mptg_ctx* ctx, KnnIndex& ix, uint64_t* stats) {
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MPTG_CUDA(ctx, cudaMemcpyAsync(h, ix.devStats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+#ifdef MPTG_KNN_PROBE
+    fprintf(stderr, "[knn probe] leaf visits %llu, inner %llu, leaf visits with a candidate %llu, candidate lanes %llu\n", h[0], h[1], h[2], h[3]);
+#endif
     stats[0] += h[0] * 32ull;
     stats[1] = h[0] + h[1];
     MPTG_CUDA(ctx, cudaMemsetAsync(ix.devStats, 0, sizeof h, ctx->stream));

@@ -29,6 +29,11 @@ public:
     BoxBounds() {}
     BoxBounds(const Eigen::Matrix<S, dim, 1>& mn, const Eigen::Matrix<S, dim, 1>& mx) : min_(mn), max_(mx) {}
     unsigned size() const { return dim; }
+    S measure() const {  // box_bounds.hpp:88-90: (max - min).prod()
+        S m = max_[0] - min_[0];
+        for (int i = 1; i < dim; ++i) m = m * (max_[i] - min_[i]);
+        return m;
+    }
     const Eigen::Matrix<S, dim, 1>& min() const { return min_; }
     const Eigen::Matrix<S, dim, 1>& max() const { return max_; }
 };

@@ -1,0 +1,212 @@
+// reference_planner_parity.cpp -- row a11: the wave planners of include/mptg/planner.hpp against THE
+// REFERENCE'S OWN planner classes, in one process, on the same scenario and the same random stream.
+//
+// Reference side: src/mpt/impl/{prrt,prrt_star,pprm} compiled from /root/reference (never copied) against the
+// stand-in Eigen / Nigh headers under oracle/shim (exhaustive-scan Nigh with the (distance, insertion order) tie
+// rule), single_threaded, scenario = the reference's PNG2dScenario::valid / link on a synthetic occupancy grid,
+// RNG = std::mt19937_64 (the Scenario's `using RNG`, impl/scenario_rng.hpp:46-54) seeded with a plain integer.
+// Our side: Planner<Scenario, Algorithm<wave_size<1>>> over the TEST-ONLY CPU mock of the C ABI
+// (tests/cpp/mock_mptg.cpp), same seed.  With one sample per wave the wave planners must consume the generator
+// exactly like the reference's worker loop and build the SAME graph: same vertices (bit-identical states), same
+// edges, same solution path -- for PRRT, PRRT* (k-nearest and r-nearest rewiring) and PPRM.
+// TEST INFRASTRUCTURE: only buildable where /root/reference exists (tests/test_host_cpp.py skips it elsewhere).
+#include <algorithm>
+#include <array>
+#include <cassert>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <random>
+#include <utility>
+#include <vector>
+
+// ---- the reference
+#include "mpt_stubs.hpp"
+#include "nigh/nigh_linear.hpp"
+
+#include <mpt/goal_state.hpp>
+#include <mpt/lp_space.hpp>
+#include <mpt/planner.hpp>
+#include <mpt/pprm.hpp>
+#include <mpt/prrt.hpp>
+#include <mpt/prrt_star.hpp>
+
+#include <png_2d_scenario.hpp>
+
+// ---- ours
+#include "mptg/planner.hpp"
+#include "mptg/scenarios.hpp"
+
+namespace ref = unc::robotics::mpt;
+
+static int failures = 0;
+#define EXPECT(cond)                                                    \
+    do {                                                                \
+        if (!(cond)) {                                                  \
+            std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            ++failures;                                                 \
+        }                                                               \
+    } while (0)
+
+// synthetic occupancy grid: random rectangles and discs
+struct Grid {
+    int w, h;
+    std::vector<std::uint8_t> occ;
+    double start[2], goal[2];
+};
+static Grid makeGrid(int w, int h, unsigned seed) {
+    Grid g{w, h, std::vector<std::uint8_t>((size_t)w * h, 0), {0, 0}, {0, 0}};
+    std::mt19937 r(seed);
+    auto uni = [&](int n) { return (int)(r() % (unsigned)n); };
+    for (int k = 0; k < 40; ++k) {
+        const int cx = uni(w), cy = uni(h), rx = 4 + uni(w / 12), ry = 4 + uni(h / 12);
+        const bool disc = (k & 1) != 0;
+        for (int y = std::max(0, cy - ry); y < std::min(h, cy + ry); ++y)
+            for (int x = std::max(0, cx - rx); x < std::min(w, cx + rx); ++x)
+                if (!disc || (double)(x - cx) * (x - cx) / ((double)rx * rx) + (double)(y - cy) * (y - cy) / ((double)ry * ry) <= 1.0)
+                    g.occ[(size_t)w * y + x] = 1;
+    }
+    auto freeCell = [&](int x0, int y0, double* out) {
+        for (int d = 0;; ++d)
+            for (int y = std::max(0, y0 - d); y <= std::min(h - 1, y0 + d); ++y)
+                for (int x = std::max(0, x0 - d); x <= std::min(w - 1, x0 + d); ++x)
+                    if (!g.occ[(size_t)w * y + x]) {
+                        out[0] = x, out[1] = y;
+                        return;
+                    }
+    };
+    freeCell(w / 8, h / 8, g.start);
+    freeCell(w - w / 8, h - h / 8, g.goal);
+    return g;
+}
+
+// the reference's PNG scenario with bounds that keep x + 0.5 < width (beyond, the reference indexes its bitmap out of
+// range) and a caller-chosen goal radius (it hard-wires 1e-6, demo/png_2d_scenario.hpp:99)
+struct RefGrid {
+    using Base = mpt_demo::PNG2dScenario<double>;
+    using Space = Base::Space;
+    using Bounds = Base::Bounds;
+    using State = Base::State;
+    using Distance = Base::Distance;
+    using Goal = ref::GoalState<Space>;
+    using RNG = std::mt19937_64;
+    std::shared_ptr<Base> base;
+    Bounds bounds_;
+    Goal goal_;
+    RefGrid(const Grid& g, double radius)
+        : bounds_(State(0, 0), State(g.w - 1, g.h - 1)), goal_(radius, State(g.goal[0], g.goal[1])) {
+        std::vector<bool> obst(g.occ.size());
+        for (size_t i = 0; i < obst.size(); ++i) obst[i] = g.occ[i] != 0;
+        base = std::make_shared<Base>(g.w, g.h, State(g.goal[0], g.goal[1]), obst);
+    }
+    bool valid(const State& q) const { return base->valid(q); }
+    bool link(const State& a, const State& b) const { return base->link(a, b); }
+    const Space& space() const { return base->space(); }
+    const Bounds& bounds() const { return bounds_; }
+    const Goal& goal() const { return goal_; }
+};
+
+struct OurGrid {
+    using Space = mptg::L2Space<double, 2>;
+    using Bounds = mptg::BoxBounds<double, 2>;
+    using State = Space::Type;
+    using Distance = Space::Distance;
+    using Goal = mptg::GoalState<Space>;
+    int w, h;
+    Space space_;
+    Bounds bounds_;
+    Goal goal_;
+    std::shared_ptr<const std::vector<std::uint8_t>> occ;
+    OurGrid(const Grid& g, double radius)
+        : w(g.w), h(g.h), bounds_(State::Zero(), mptg::makeState<double, 2>({double(g.w - 1), double(g.h - 1)})),
+          goal_(radius, mptg::makeState<double, 2>({g.goal[0], g.goal[1]})), occ(std::make_shared<const std::vector<std::uint8_t>>(g.occ)) {}
+    const Space& space() const { return space_; }
+    const Bounds& bounds() const { return bounds_; }
+    const Goal& goal() const { return goal_; }
+    mptg::Geometry makeGeometry(mptg::Context& ctx) const {
+        return mptg::Geometry::grid(ctx, mptg::detail::scalarTag<double>(), w, h, occ->data());
+    }
+};
+
+template <typename T, typename = void>
+struct has_solution_cost : std::false_type {};
+template <typename T>
+struct has_solution_cost<T, std::void_t<decltype(std::declval<const T&>().solutionCost())>> : std::true_type {};
+
+using P2 = std::array<double, 2>;
+using Edge = std::pair<P2, P2>;
+struct GraphDump {
+    std::vector<P2> vertices;  // visiting order
+    std::vector<Edge> edges;   // (vertex, edge target)
+    template <class Q>
+    void vertex(const Q& q) { vertices.push_back({q[0], q[1]}); }
+    template <class Q>
+    void edge(const Q& to) { edges.push_back({vertices.back(), {to[0], to[1]}}); }
+};
+
+template <class RefAlgo, class OurAlgo>
+void compare(const char* name, const Grid& g, double goalRadius, double goalBias, double range, std::uint64_t seed, std::size_t nodes,
+             bool orderedVertices, bool addGoal) {
+    using RefState = RefGrid::State;
+    using OurState = OurGrid::State;
+    const int before = failures;
+    ref::Planner<RefGrid, RefAlgo> rp(RefGrid(g, goalRadius), seed);
+    mptg::Planner<OurGrid, OurAlgo> op(OurGrid(g, goalRadius), seed);
+    if constexpr (!std::is_same_v<RefAlgo, ref::PPRM<ref::single_threaded>>) {
+        rp.setGoalBias(goalBias), op.setGoalBias(goalBias);
+        if (std::isfinite(range)) rp.setRange(range), op.setRange(range);
+    }
+    rp.addStart(RefState(g.start[0], g.start[1]));
+    op.addStart(mptg::makeState<double, 2>({g.start[0], g.start[1]}));
+    if constexpr (std::is_same_v<RefAlgo, ref::PPRM<ref::single_threaded>>) {
+        if (addGoal) {
+            rp.addGoal(RefState(g.goal[0], g.goal[1]));
+            op.addGoal(mptg::makeState<double, 2>({g.goal[0], g.goal[1]}));
+        }
+    }
+    rp.solve([&] { return rp.size() >= nodes; });
+    op.solve([&] { return op.size() >= nodes; });
+
+    GraphDump rg, og;
+    rp.visitGraph(rg);
+    op.visitGraph(og);
+    EXPECT(rp.size() == op.size());
+    EXPECT(rg.vertices.size() == og.vertices.size());
+    if (!orderedVertices) {
+        std::sort(rg.vertices.begin(), rg.vertices.end());
+        std::sort(og.vertices.begin(), og.vertices.end());
+    }
+    EXPECT(rg.vertices == og.vertices);
+    std::sort(rg.edges.begin(), rg.edges.end());
+    std::sort(og.edges.begin(), og.edges.end());
+    EXPECT(rg.edges.size() == og.edges.size());
+    EXPECT(rg.edges == og.edges);
+    EXPECT(rp.solved() == op.solved());
+    std::vector<RefState> rs = rp.solution();
+    std::vector<OurState> os = op.solution();
+    EXPECT(rs.size() == os.size());
+    for (std::size_t i = 0; i < rs.size() && i < os.size(); ++i) EXPECT(rs[i][0] == os[i][0] && rs[i][1] == os[i][1]);
+    if constexpr (has_solution_cost<ref::Planner<RefGrid, RefAlgo>>::value && has_solution_cost<mptg::Planner<OurGrid, OurAlgo>>::value) {
+        if (rp.solved() && op.solved()) EXPECT(rp.solutionCost() == op.solutionCost());  // PRRT*: cost after rewiring, bit for bit
+    }
+    std::printf("%s %s: %zu / %zu vertices, %zu / %zu edges, solved %d / %d, %zu / %zu waypoints (reference / ours)\n",
+                failures == before ? "PASS" : "FAIL", name, rg.vertices.size(), og.vertices.size(), rg.edges.size(), og.edges.size(),
+                (int)rp.solved(), (int)op.solved(), rs.size(), os.size());
+}
+
+int main() {
+    const Grid g = makeGrid(400, 300, 5);
+    const double inf = std::numeric_limits<double>::infinity();
+    compare<ref::PRRT<ref::single_threaded>, mptg::PRRT<mptg::wave_size<1>>>("PRRT range 20", g, 8.0, 0.05, 20.0, 11, 1500, true, false);
+    compare<ref::PRRT<ref::single_threaded>, mptg::PRRT<mptg::wave_size<1>>>("PRRT unbounded", g, 1e-6, 0.1, inf, 12, 400, true, false);
+    compare<ref::PRRTStar<ref::single_threaded>, mptg::PRRTStar<mptg::wave_size<1>>>("PRRT* k-nearest", g, 8.0, 0.05, 25.0, 13, 1200, true, false);
+    compare<ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest>, mptg::PRRTStar<mptg::wave_size<1>, mptg::rewire_r_nearest>>(
+        "PRRT* r-nearest", g, 8.0, 0.05, 25.0, 14, 1200, true, false);
+    compare<ref::PPRM<ref::single_threaded>, mptg::PPRM<mptg::wave_size<1>>>("PPRM", g, 1e-6, 0.0, inf, 15, 600, false, true);
+    std::printf("%d failures\n", failures);
+    return failures ? 1 : 0;
+}

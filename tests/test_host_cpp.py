@@ -30,6 +30,23 @@ def test_wave_planners_host_logic_with_mock_backend():
         assert f"PASS {name}" in out
 
 
+PARITY_CASES = ("PRRT range 20:", "PRRT unbounded:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:")
+
+
+def test_wave_planners_build_the_reference_planners_graphs():
+    """Row a11: Planner<Scenario, PRRT / PRRTStar / PPRM <wave_size<1>>> over the CPU mock of the ABI against the
+    reference's own planner classes in the same process (tests/cpp/reference_planner_parity.cpp): identical vertices,
+    edges, solution paths and PRRT* solution costs.  Needs /root/reference to compile the reference side."""
+    from mpt_b200 import build_host
+
+    prog = build_host.build_reference_parity(mock=True)
+    if prog is None:
+        pytest.skip("/root/reference not present and no prebuilt parity program")
+    out = _run(prog)
+    for name in PARITY_CASES:
+        assert f"PASS {name}" in out
+
+
 def test_demo_programs_compile():
     """The demo mains and the GPU test program build against include/mptg and libmptg.so."""
     from mpt_b200 import build_host
@@ -47,6 +64,21 @@ def test_wave_planners_on_gpu():
         build_host.build()
     out = _run(prog)
     for name in ("PRRT:", "PRRT device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
+        assert f"PASS {name}" in out
+
+
+@pytest.mark.gpu
+def test_wave_planners_on_gpu_build_the_reference_planners_graphs():
+    """The same comparison with the wave planners running on the device (libmptg.so): the reference's planner classes
+    run on the host in the same process; graphs must be identical.  The program is built where /root/reference
+    exists and travels with the snapshot."""
+    from mpt_b200 import build_host
+
+    prog = build_host.build_reference_parity(mock=False)
+    if prog is None:
+        pytest.skip("reference parity program was not built (no /root/reference here and none shipped)")
+    out = _run(prog)
+    for name in PARITY_CASES:
         assert f"PASS {name}" in out
 
 
