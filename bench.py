@@ -154,6 +154,13 @@ def run_reference(args):
     qps = qs / float(np.mean(knn_t))
     eps = es / float(np.mean(edge_t))
     sample = f"{qs} of {Q_WAVE} queries and {es} of {E_WAVE} edges per step (tree build {build_s:.1f}s untimed)"
+    # solve time: the reference's own multi-threaded planner classes on the occupancy-grid scenario (same map as the
+    # GPU arm's secondary.device_prrt_grid)
+    from mpt_b200 import workloads as W
+
+    occ = W.synthetic_grid()
+    free = np.argwhere(occ == 0)
+    planner = reference_planner_cpu(occ, free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64), 12.0, 200.0)
     line = {
         "impl": "reference", "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(knn_t) + np.mean(edge_t)),
@@ -163,6 +170,8 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if planner:
+        line["reference_planner_cpu_grid"] = planner
     emit(line)
 
 
@@ -409,6 +418,42 @@ def secondary(ctx, torch, dev, stream):
     dt = time.perf_counter() - t0
     out["device_prrt_grid"] = {"nodes_per_s": (pl.size - n0) / dt, "samples_per_s": (pl.samples_drawn - 16384) / dt, "nodes": pl.size, "s": dt}
     pl.close()
+    # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
+    goal = free[-len(free) // 9][::-1].astype(np.float64)
+    ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)
+    if ref:
+        out["reference_planner_cpu_grid"] = ref
+    return out
+
+
+def reference_planner_cpu(occ, start, goal, goal_radius, prrt_range, nodes=200_000, time_ms=8000):
+    """The reference's OWN multi-threaded planner classes (src/mpt PRRT / PRRT*, OpenMP worker pool, one worker per host
+    thread) on the occupancy-grid scenario, timed on this box's host cores: oracle/_ref/ref_planner_bench, compiled where
+    /root/reference exists (oracle/Makefile, target ref) and shipped with the snapshot.  Nigh is absent, so the nearest-
+    neighbour structure is a stand-in concurrent kd-tree (oracle/shim/nigh/nigh_kdtree.hpp); everything else -- worker
+    loop, sampling, steering, rewiring, PNG2dScenario::valid / link -- is the reference's code.  Returns {} when the
+    program was not shipped."""
+    import json
+    import subprocess
+    import tempfile
+
+    prog = ROOT / "oracle" / "_ref" / "ref_planner_bench"
+    if not prog.exists():
+        return {}
+    out = {}
+    with tempfile.NamedTemporaryFile(suffix=".pgm") as f:
+        f.write(b"P5\n%d %d\n255\n" % (occ.shape[1], occ.shape[0]) + (np.asarray(occ) != 0).astype(np.uint8).tobytes())
+        f.flush()
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+        for algo in ("prrt", "prrtstar"):
+            cmd = [str(prog), "--map", f.name, "--start", str(start[0]), str(start[1]), "--goal", str(goal[0]), str(goal[1]), "--goal-radius",
+                   str(goal_radius), "--range", str(prrt_range), "--algo", algo, "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "17"]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=time_ms / 1e3 + 60, env=env)
+                out[algo] = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:  # a baseline, never fatal
+                out[algo] = {"error": str(e)[:200]}
     return out
 
 
