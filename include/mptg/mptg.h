@@ -248,6 +248,47 @@ uint64_t mptg_prrt_samples_drawn(const mptg_prrt* prrt);
  * what Planner::solution() and visitGraph() walk (prrt.hpp:232-262). */
 int mptg_prrt_get_tree(mptg_prrt* prrt, uint32_t first, uint32_t count, void* states_out, uint32_t* parents_out);
 
+/* --------------------------------------------------------- device-resident PPRM
+ * The roadmap (node states, per-node edge rows, union-find components, start / goal marks), its nearest-neighbour
+ * structure and every stage of PPRM's Worker::addSample (src/mpt/impl/pprm/pprm.hpp:298-339) stay on the GPU.
+ * One wave = n_samples iterations of the reference's loop (:368-378) run as a batch: sample -> scenario.valid (:299)
+ * -> k nearest, k = ceil(kRRG * ln(size + 1)), kRRG = e + e / dimensions (:146,:302-304) -> drop samples closer than
+ * epsilon to a node (:306-308) -> scenario.link(sample, neighbour) for every neighbour (:325-326) -> append the nodes
+ * in sample order, record the valid edges, merge components (:327-334,:341-362), goal test (:312-316) -> solved when a
+ * component holds a start and a goal (impl/pprm/component.hpp).  Samples of one wave do not see each other's nodes.
+ * Edge rows: node i keeps the edges found when it was added (to older nodes), `row_stride` slots, unused slots
+ * MPTG_NO_INDEX; the roadmap is the undirected union of the rows. */
+typedef struct mptg_pprm mptg_pprm;
+typedef struct mptg_pprm_params {
+    const mptg_space_desc* space;
+    const double* lo;       /* sampling bounds, one double per scalar (see mptg_sample_batch) */
+    const double* hi;
+    const void* goal_state; /* GoalState: state (space scalar type) or NULL: only mptg_pprm_add_state marks goals */
+    double goal_radius;
+    double link_step;       /* DiscreteMotionValidator step size (mesh geometries) */
+    uint64_t seed;
+    uint32_t capacity;      /* maximum number of nodes */
+    uint32_t max_wave;      /* maximum samples per wave */
+    uint32_t max_k;         /* cap on k (0: min(MPTG_MAX_K, k at `capacity` nodes)) = row stride */
+} mptg_pprm_params;
+#define MPTG_PPRM_START 1u
+#define MPTG_PPRM_GOAL 2u
+int mptg_pprm_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_pprm_params* params, mptg_pprm** out);
+int mptg_pprm_destroy(mptg_pprm* pprm);
+/* Planner::addStart(state) / addGoal(state) (pprm.hpp:156-169): addSample with the start / goal mark.
+ * node_out: the new node, MPTG_NO_INDEX when the state is invalid or closer than epsilon to a node. */
+int mptg_pprm_add_state(mptg_pprm* pprm, const void* state, uint32_t marks, uint32_t* node_out);
+/* One wave.  size_out: nodes afterwards (Planner::size()); solved_out: 1 once a start and a goal are connected. */
+int mptg_pprm_wave(mptg_pprm* pprm, uint32_t n_samples, uint32_t* size_out, uint32_t* solved_out);
+uint32_t mptg_pprm_size(const mptg_pprm* pprm);
+uint64_t mptg_pprm_samples_drawn(const mptg_pprm* pprm);
+uint32_t mptg_pprm_row_stride(const mptg_pprm* pprm);
+/* Nodes first .. first+count-1: states (AoS), edge rows (neighbour index / distance, count * row_stride each), marks
+ * (MPTG_PPRM_START | MPTG_PPRM_GOAL) and component representative: what Planner::solution() (Dijkstra over the
+ * roadmap, pprm.hpp:218-246) and visitGraph() (:380-387) walk.  Any output may be NULL. */
+int mptg_pprm_get_graph(mptg_pprm* pprm, uint32_t first, uint32_t count, void* states_out, uint32_t* edge_idx_out, void* edge_dist_out,
+                        uint8_t* marks_out, uint32_t* component_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,11 @@ class PrrtParams(C.Structure):
                 ("seed", C.c_uint64), ("capacity", C.c_uint32), ("max_wave", C.c_uint32)]
 
 
+class PprmParams(C.Structure):
+    _fields_ = [("space", C.POINTER(SpaceDesc)), ("lo", C.c_void_p), ("hi", C.c_void_p), ("goal_state", C.c_void_p), ("goal_radius", C.c_double),
+                ("link_step", C.c_double), ("seed", C.c_uint64), ("capacity", C.c_uint32), ("max_wave", C.c_uint32), ("max_k", C.c_uint32)]
+
+
 class MptgError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libmptg error {code}: {msg}")
@@ -99,6 +104,14 @@ SYMBOLS = {
     "mptg_prrt_size": (_U32, [_P]),
     "mptg_prrt_samples_drawn": (C.c_uint64, [_P]),
     "mptg_prrt_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P]),
+    "mptg_pprm_create": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
+    "mptg_pprm_destroy": (C.c_int, [_P]),
+    "mptg_pprm_add_state": (C.c_int, [_P, _P, _U32, _U32P]),
+    "mptg_pprm_wave": (C.c_int, [_P, _U32, _U32P, _U32P]),
+    "mptg_pprm_size": (_U32, [_P]),
+    "mptg_pprm_samples_drawn": (C.c_uint64, [_P]),
+    "mptg_pprm_row_stride": (_U32, [_P]),
+    "mptg_pprm_get_graph": (C.c_int, [_P, _U32, _U32, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -306,6 +306,115 @@ class DevicePRRT:
             pass
 
 
+class DevicePPRM:
+    """Device-resident PPRM (mptg_pprm_*): Planner<Scenario, PPRM> with the roadmap kept on the GPU."""
+
+    START, GOAL = 1, 2
+
+    def __init__(self, scenario: "Scenario", space: Space, lo, hi, *, goal=None, goal_radius: float = 0.0, seed: int = 1,
+                 capacity: int = 1 << 20, max_wave: int = 1 << 14, max_k: int = 0):
+        self.ctx, self.scenario, self.space = scenario.ctx, scenario, space
+        self._lo, self._hi = _bounds(space, lo, hi)
+        self._goal = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
+        prm = L.PprmParams(C.pointer(space.desc), self._lo.ctypes.data, self._hi.ctypes.data, None if self._goal is None else self._goal.ctypes.data,
+                           float(goal_radius), float(scenario.step or 0.0), int(seed), int(capacity), int(max_wave), int(max_k))
+        self.h = C.c_void_p()
+        L.check(self.ctx.lib.mptg_pprm_create(self.ctx.h, scenario.h, C.byref(prm), C.byref(self.h)), self.ctx.h)
+        self._solved = False
+
+    def add_state(self, state, marks: int) -> int:
+        """addStart / addGoal (pprm.hpp:156-169); returns the node or NO_INDEX when the state was rejected."""
+        s = np.ascontiguousarray(state, dtype=self.space.dtype).reshape(self.space.scalars)
+        node = C.c_uint32()
+        L.check(self.ctx.lib.mptg_pprm_add_state(self.h, _ptr(s), marks, C.byref(node)), self.ctx.h)
+        return node.value
+
+    def add_start(self, state) -> int:
+        return self.add_state(state, self.START)
+
+    def add_goal(self, state) -> int:
+        return self.add_state(state, self.GOAL)
+
+    def wave(self, n_samples: int) -> int:
+        size, solved = C.c_uint32(), C.c_uint32()
+        L.check(self.ctx.lib.mptg_pprm_wave(self.h, n_samples, C.byref(size), C.byref(solved)), self.ctx.h)
+        self._solved = bool(solved.value)
+        return size.value
+
+    @property
+    def size(self) -> int:
+        return self.ctx.lib.mptg_pprm_size(self.h)
+
+    @property
+    def samples_drawn(self) -> int:
+        return self.ctx.lib.mptg_pprm_samples_drawn(self.h)
+
+    @property
+    def row_stride(self) -> int:
+        return self.ctx.lib.mptg_pprm_row_stride(self.h)
+
+    def solved(self) -> bool:
+        return self._solved
+
+    def graph(self, first: int = 0, count: int | None = None):
+        """-> (states [n, D], edge_idx [n, stride] (NO_INDEX = unused), edge_dist [n, stride], marks [n], component [n])"""
+        count = self.size - first if count is None else count
+        K = self.row_stride
+        st = np.empty((count, self.space.scalars), dtype=self.space.dtype)
+        ei = np.empty((count, K), dtype=np.uint32)
+        ed = np.empty((count, K), dtype=self.space.dtype)
+        mk = np.empty(count, dtype=np.uint8)
+        cp = np.empty(count, dtype=np.uint32)
+        L.check(self.ctx.lib.mptg_pprm_get_graph(self.h, first, count, _ptr(st), _ptr(ei), _ptr(ed), _ptr(mk), _ptr(cp)), self.ctx.h)
+        return st, ei, ed, mk, cp
+
+    def solution(self) -> np.ndarray:
+        """Planner::solution(): shortest roadmap path from a start to a goal (Dijkstra, pprm.hpp:218-246)."""
+        import heapq
+
+        st, ei, ed, mk, _ = self.graph()
+        n = st.shape[0]
+        adj = [[] for _ in range(n)]
+        rows, cols = np.nonzero(ei != L.NO_INDEX)
+        for r, c in zip(rows.tolist(), cols.tolist()):
+            nb, d = int(ei[r, c]), float(ed[r, c])
+            adj[r].append((nb, d))
+            adj[nb].append((r, d))
+        dist, prev = np.full(n, np.inf), np.full(n, -1, dtype=np.int64)
+        pq = []
+        for s in np.nonzero(mk & self.START)[0].tolist():
+            dist[s] = 0.0
+            heapq.heappush(pq, (0.0, s))
+        hit = -1
+        while pq:
+            d, u = heapq.heappop(pq)
+            if d > dist[u]:
+                continue
+            if mk[u] & self.GOAL:
+                hit = u
+                break
+            for v, w in adj[u]:
+                if d + w < dist[v]:
+                    dist[v], prev[v] = d + w, u
+                    heapq.heappush(pq, (d + w, v))
+        path = []
+        while hit >= 0:
+            path.append(st[hit])
+            hit = int(prev[hit])
+        return np.stack(path[::-1]) if path else np.empty((0, self.space.scalars), dtype=self.space.dtype)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mptg_pprm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def knn_merge_dev(ctx: Context, scalar: int, parts: int, Q: int, k: int, idx_in: int, dist_in: int, idx_out: int,
                   dist_out: int, cnt_out: int = 0):
     L.check(ctx.lib.mptg_knn_merge_dev(ctx.h, scalar, parts, Q, k, C.c_void_p(idx_in), C.c_void_p(dist_in),

@@ -477,3 +477,382 @@ int mptg_prrt_get_tree(mptg_prrt* p, uint32_t first, uint32_t count, void* state
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// device-resident PPRM (src/mpt/impl/pprm/pprm.hpp:298-362)
+// ---------------------------------------------------------------------------------------------
+namespace mptg {
+
+template <typename S>
+__global__ void pprmGatherKernel(const uint32_t* __restrict__ sel, uint32_t n, int D, const S* __restrict__ src, S* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const S* ps = src + (size_t)sel[i] * D;
+    S* pd = dst + (size_t)i * D;
+    for (int c = 0; c < D; ++c) pd[c] = ps[c];
+}
+
+// pprm.hpp:306-308: a sample closer than epsilon to its nearest node is dropped
+template <typename S>
+__global__ void pprmKeepKernel(const S* __restrict__ dist, const uint32_t* __restrict__ cnt, uint32_t k, uint32_t n, S minDist,
+                               uint8_t* __restrict__ keep) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keep[i] = (cnt != nullptr && cnt[i] > 0 && dist[(size_t)i * k] < minDist) ? 0 : 1;
+}
+
+// edges (kept sample sel[s]) -> (its neighbour j), pprm.hpp:325; slots beyond the neighbour count become zero-length
+// edges at the sample and are ignored later
+template <typename S>
+__global__ void pprmEdgeKernel(const uint32_t* __restrict__ sel, uint32_t nSel, uint32_t k, int D, const S* __restrict__ samples,
+                               const S* __restrict__ nodes, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ cnt,
+                               S* __restrict__ from, S* __restrict__ to) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)nSel * k) return;
+    const uint32_t s = (uint32_t)(e / k), j = (uint32_t)(e % k);
+    const uint32_t i = sel[s];
+    const S* ps = samples + (size_t)i * D;
+    const S* pn = j < cnt[i] ? nodes + (size_t)idx[(size_t)i * k + j] * D : ps;
+    S* pf = from + e * D;
+    S* pt = to + e * D;
+    for (int c = 0; c < D; ++c) pf[c] = ps[c], pt[c] = pn[c];
+}
+
+// append the kept samples in sample order: state, marks (goal test, pprm.hpp:312-316), own component, edge row
+template <typename S>
+__global__ void pprmAppendKernel(DevSpace<S> sp, const uint32_t* __restrict__ sel, uint32_t nSel, uint32_t k, uint32_t stride,
+                                 const S* __restrict__ samples, const uint32_t* __restrict__ idx, const S* __restrict__ dist,
+                                 const uint32_t* __restrict__ cnt, const uint8_t* __restrict__ okEdge, uint32_t size, const S* __restrict__ goal,
+                                 S goalRadius, uint32_t forcedMarks, S* __restrict__ nodes, S* __restrict__ fresh, uint32_t* __restrict__ edgeIdx,
+                                 S* __restrict__ edgeDist, uint8_t* __restrict__ marks, uint32_t* __restrict__ comp, uint32_t* __restrict__ lists) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSel) return;
+    const int D = sp.D;
+    const uint32_t i = sel[s], id = size + s;
+    const S* ps = samples + (size_t)i * D;
+    S* pn = nodes + (size_t)id * D;
+    S* pf = fresh + (size_t)s * D;
+    for (int c = 0; c < D; ++c) pn[c] = pf[c] = ps[c];
+    uint32_t m = forcedMarks;
+    if (!(m & MPTG_PPRM_GOAL) && goal != nullptr) {
+        const S d = dev::distance<S>(sp, [&](int c) { return ps[c]; }, [&](int c) { return goal[c]; });
+        if (d <= goalRadius) m |= MPTG_PPRM_GOAL;
+    }
+    marks[id] = (uint8_t)m;
+    comp[id] = id;
+    // lists: [0] start count, [1] goal count, [2 .. 2+PPRM_STARTS) starts, then goals
+    if (m & MPTG_PPRM_START) {
+        const uint32_t slot = atomicAdd(lists + 0, 1u);
+        if (slot < 64u) lists[2 + slot] = id;
+    }
+    if (m & MPTG_PPRM_GOAL) {
+        const uint32_t slot = atomicAdd(lists + 1, 1u);
+        if (slot < 4096u) lists[2 + 64 + slot] = id;
+    }
+    const uint32_t have = cnt ? cnt[i] : 0u;
+    for (uint32_t j = 0; j < stride; ++j) {
+        const bool live = j < k && j < have && okEdge[(size_t)s * k + j] != 0;
+        edgeIdx[(size_t)id * stride + j] = live ? idx[(size_t)i * k + j] : MPTG_NO_INDEX;
+        edgeDist[(size_t)id * stride + j] = live ? dist[(size_t)i * k + j] : S(0);
+    }
+}
+
+// lock-free union-find: roots point to themselves, a root is only ever hooked under a smaller index (no cycles),
+// path halving writes are benign (they replace a parent by one of its ancestors)
+__device__ __forceinline__ uint32_t pprmFind(uint32_t* comp, uint32_t x) {
+    for (;;) {
+        const uint32_t p = ((volatile uint32_t*)comp)[x];
+        if (p == x) return x;
+        const uint32_t gp = ((volatile uint32_t*)comp)[p];
+        if (gp != p) ((volatile uint32_t*)comp)[x] = gp;
+        x = p;
+    }
+}
+__device__ __forceinline__ void pprmUnite(uint32_t* comp, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = pprmFind(comp, a);
+        b = pprmFind(comp, b);
+        if (a == b) return;
+        if (a < b) {
+            const uint32_t t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS(comp + a, a, b) == a) return;
+    }
+}
+// merge the components along the new edges (pprm.hpp:327-334, 341-362)
+__global__ void pprmUniteKernel(uint32_t nSel, uint32_t stride, uint32_t size, const uint32_t* __restrict__ edgeIdx, uint32_t* comp) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)nSel * stride) return;
+    const uint32_t id = size + (uint32_t)(e / stride);
+    const uint32_t nb = edgeIdx[(size_t)id * stride + (e % stride)];
+    if (nb != MPTG_NO_INDEX) pprmUnite(comp, id, nb);
+}
+// component.hpp:97-99: solved when one component holds a start and a goal
+__global__ void pprmSolvedKernel(uint32_t* comp, const uint32_t* __restrict__ lists, uint32_t* __restrict__ result) {
+    const uint32_t nStart = min(lists[0], 64u), nGoal = min(lists[1], 4096u);
+    for (uint32_t p = threadIdx.x; p < nStart * nGoal; p += blockDim.x) {
+        const uint32_t s = lists[2 + p / nGoal], g = lists[2 + 64 + p % nGoal];
+        if (pprmFind(comp, s) == pprmFind(comp, g)) result[0] = 1u;
+    }
+}
+// representatives for mptg_pprm_get_graph
+__global__ void pprmRootKernel(uint32_t* comp, uint32_t first, uint32_t count, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = pprmFind(comp, first + i);
+}
+
+}  // namespace mptg
+
+struct mptg_pprm {
+    mptg_ctx* ctx = nullptr;
+    mptg_geom* geom = nullptr;
+    mptg_knn* knn = nullptr;  // owned
+    mptg_space_desc space{};
+    int D = 0, scalar = MPTG_F32, dims = 0;
+    double goalRadius = 0, linkStep = 0;
+    bool hasGoal = false, solved = false;
+    uint64_t seed = 0, drawn = 0, waves = 0;
+    uint32_t capacity = 0, size = 0, maxWave = 0, stride = 0;
+    // device
+    void *bounds = nullptr, *goal = nullptr, *nodes = nullptr, *edgeDist = nullptr;
+    uint32_t *edgeIdx = nullptr, *comp = nullptr, *lists = nullptr;
+    uint8_t* marks = nullptr;
+    void *samples = nullptr, *cand = nullptr, *fresh = nullptr, *nnDist = nullptr, *from = nullptr, *to = nullptr;
+    uint32_t *nnIdx = nullptr, *nnCnt = nullptr, *sel = nullptr, *sel2 = nullptr, *nSel = nullptr, *result = nullptr;
+    uint8_t *okValid = nullptr, *keep = nullptr, *okEdge = nullptr;
+    void* selTemp = nullptr;
+    size_t selBytes = 0;
+    uint32_t* host = nullptr;  // pinned: [0] selected count, [1] solved
+};
+
+namespace {
+
+void pprmFree(mptg_pprm* p) {
+    if (!p) return;
+    if (p->knn) mptg_knn_destroy(p->knn);
+    for (void* q : {p->bounds, p->goal, p->nodes, p->edgeDist, (void*)p->edgeIdx, (void*)p->comp, (void*)p->lists, (void*)p->marks, p->samples,
+                    p->cand, p->fresh, p->nnDist, p->from, p->to, (void*)p->nnIdx, (void*)p->nnCnt, (void*)p->sel, (void*)p->sel2, (void*)p->nSel,
+                    (void*)p->result, (void*)p->okValid, (void*)p->keep, (void*)p->okEdge, p->selTemp})
+        cudaFree(q);
+    if (p->host) cudaFreeHost(p->host);
+    delete p;
+}
+
+int spaceDimensions(const mptg_space_desc& sp) {  // Space::dimensions(): SO(3) counts 3
+    int d = 0;
+    for (int i = 0; i < sp.n_parts; ++i) d += sp.part[i].kind == MPTG_PART_SO3 ? 3 : sp.part[i].dim;
+    return d;
+}
+
+// k = ceil(kRRG * ln(n + 1)) in the space's scalar type (pprm.hpp:146,302-303)
+template <typename S>
+uint32_t pprmK(int dims, uint32_t n) {
+    const S e = (S)2.718281828459045235360287471352662498L;
+    const S kRRG = e + e / (S)dims;
+    const S logSizePlus1 = (S)std::log((double)n + 1.0);
+    const int k = (int)std::ceil(kRRG * logSizePlus1);
+    return (uint32_t)(k < 1 ? 1 : k);
+}
+
+template <typename T>
+int selectFlagged(mptg_pprm* p, const uint8_t* flags, uint32_t n, T* out, uint32_t* countHost) {
+    mptg_ctx* ctx = p->ctx;
+    size_t bytes = p->selBytes;
+    MPTG_CUDA(ctx, cub::DeviceSelect::Flagged(p->selTemp, bytes, thrust::counting_iterator<uint32_t>(0), flags, out, p->nSel, (int)n, ctx->stream));
+    MPTG_LAUNCHED(ctx);
+    MPTG_CUDA(ctx, cudaMemcpyAsync(p->host, p->nSel, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *countHost = p->host[0];
+    return MPTG_OK;
+}
+
+// Worker::addSample for the W states in p->samples (pprm.hpp:298-339); marks: start / goal marks forced on them
+template <typename S>
+int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, uint32_t* addedOut) {
+    mptg_ctx* ctx = p->ctx;
+    const DevSpace<S> sp = makeDevSpace<S>(p->space);
+    const int D = p->D;
+    cudaStream_t st = ctx->stream;
+    *firstOut = p->size, *addedOut = 0;
+    // valid (:299), keep the valid samples in sample order
+    if (int rc = mptg_valid_batch_dev(p->geom, p->samples, W, p->okValid)) return rc;
+    uint32_t V = 0;
+    if (int rc = selectFlagged(p, p->okValid, W, p->sel, &V)) return rc;
+    if (V == 0) return MPTG_OK;
+    pprmGatherKernel<S><<<(V + 127) / 128, 128, 0, st>>>(p->sel, V, D, (const S*)p->samples, (S*)p->cand);
+    MPTG_LAUNCHED(ctx);
+    // k nearest (:302-304) and the epsilon test (:306-308)
+    const uint32_t n = p->size;
+    uint32_t k = 1;
+    uint32_t nSel = V;
+    if (n > 0) {
+        k = pprmK<S>(p->dims, n);
+        if (k > p->stride) k = p->stride;
+        if (int rc = mptg_knn_query_dev(p->knn, p->cand, V, k, -1.0, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
+        pprmKeepKernel<S><<<(V + 127) / 128, 128, 0, st>>>((const S*)p->nnDist, p->nnCnt, k, V, std::numeric_limits<S>::epsilon(), p->keep);
+        MPTG_LAUNCHED(ctx);
+        if (int rc = selectFlagged(p, p->keep, V, p->sel2, &nSel)) return rc;
+    } else {
+        // empty roadmap: nothing to be near to; the samples of this call do not see each other
+        std::vector<uint32_t> iota(V);
+        for (uint32_t i = 0; i < V; ++i) iota[i] = i;
+        MPTG_CUDA(ctx, cudaMemcpyAsync(p->sel2, iota.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st));
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->nnCnt, 0, (size_t)V * 4, st));
+        MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (nSel > p->capacity - p->size) nSel = p->capacity - p->size;
+    if (nSel == 0) return MPTG_OK;
+    // every (sample, neighbour) edge in one batch (:325)
+    if (n > 0) {
+        const size_t E = (size_t)nSel * k;
+        pprmEdgeKernel<S><<<(unsigned)((E + 127) / 128), 128, 0, st>>>(p->sel2, nSel, k, D, (const S*)p->cand, (const S*)p->nodes, p->nnIdx, p->nnCnt,
+                                                                         (S*)p->from, (S*)p->to);
+        MPTG_LAUNCHED(ctx);
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, (uint32_t)E, p->linkStep, p->okEdge)) return rc;
+    }
+    pprmAppendKernel<S><<<(nSel + 127) / 128, 128, 0, st>>>(sp, p->sel2, nSel, k, p->stride, (const S*)p->cand, p->nnIdx, (const S*)p->nnDist, p->nnCnt,
+                                                          p->okEdge, p->size, p->hasGoal ? (const S*)p->goal : nullptr, (S)p->goalRadius, marks,
+                                                          (S*)p->nodes, (S*)p->fresh, p->edgeIdx, (S*)p->edgeDist, p->marks, p->comp, p->lists);
+    MPTG_LAUNCHED(ctx);
+    if (n > 0) {
+        const size_t E = (size_t)nSel * p->stride;
+        pprmUniteKernel<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(nSel, p->stride, p->size, p->edgeIdx, p->comp);
+        MPTG_LAUNCHED(ctx);
+    }
+    pprmSolvedKernel<<<1, 256, 0, st>>>(p->comp, p->lists, p->result);
+    MPTG_LAUNCHED(ctx);
+    MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 1, p->result, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t first = 0;
+    if (int rc = mptg_knn_insert_dev(p->knn, p->fresh, nSel, &first)) return rc;  // :337
+    if (first != p->size) return fail(ctx, MPTG_ERR_CUDA, "mptg_pprm: node numbering out of step");
+    MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (p->host[1]) p->solved = true;
+    p->size += nSel;
+    *addedOut = nSel;
+    return MPTG_OK;
+}
+
+int pprmProcess(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* first, uint32_t* added) {
+    return p->scalar == MPTG_F32 ? pprmProcessT<float>(p, W, marks, first, added) : pprmProcessT<double>(p, W, marks, first, added);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptg_pprm_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_pprm_params* prm, mptg_pprm** out) {
+    if (!ctx || !geom || !prm || !out || !spaceOk(prm->space) || prm->capacity == 0 || prm->max_wave == 0 || prm->max_k > MPTG_MAX_K)
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_pprm_create: bad argument");
+    if (geom->ctx != ctx || geom->scalar != prm->space->scalar || geom->D != spaceScalars(prm->space))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_pprm_create: the geometry's states are not states of this space");
+    if (geom->kind == MPTG_GEOM_MESH && !(prm->link_step > 0)) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_pprm_create: mesh geometries need link_step > 0");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto* p = new mptg_pprm();
+    p->ctx = ctx, p->geom = geom, p->space = *prm->space;
+    p->D = spaceScalars(prm->space), p->scalar = prm->space->scalar, p->dims = spaceDimensions(*prm->space);
+    p->goalRadius = prm->goal_radius, p->linkStep = prm->link_step, p->hasGoal = prm->goal_state != nullptr;
+    p->seed = prm->seed, p->capacity = prm->capacity, p->maxWave = prm->max_wave;
+    const uint32_t kFull = p->scalar == MPTG_F32 ? pprmK<float>(p->dims, p->capacity) : pprmK<double>(p->dims, p->capacity);
+    p->stride = prm->max_k ? prm->max_k : (kFull < MPTG_MAX_K ? kFull : MPTG_MAX_K);
+    const size_t sb = (size_t)p->D * p->scalar, W = p->maxWave, K = p->stride;
+    int rc = mptg_knn_create(ctx, prm->space, p->capacity, &p->knn);
+    if (!rc) rc = uploadBounds(ctx, prm->space, prm->lo, prm->hi, &p->bounds);
+    auto alloc = [&](auto** q, size_t bytes) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc((void**)q, bytes ? bytes : 16);
+        if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_create: %s", cudaGetErrorString(e));
+    };
+    alloc(&p->nodes, (size_t)p->capacity * sb);
+    alloc(&p->edgeIdx, (size_t)p->capacity * K * 4), alloc(&p->edgeDist, (size_t)p->capacity * K * p->scalar);
+    alloc(&p->comp, (size_t)p->capacity * 4), alloc(&p->marks, p->capacity), alloc(&p->lists, (2 + 64 + 4096) * 4);
+    alloc(&p->samples, W * sb), alloc(&p->cand, W * sb), alloc(&p->fresh, W * sb);
+    alloc(&p->nnIdx, W * K * 4), alloc(&p->nnDist, W * K * p->scalar), alloc(&p->nnCnt, W * 4);
+    alloc(&p->from, W * K * sb), alloc(&p->to, W * K * sb), alloc(&p->okEdge, W * K);
+    alloc(&p->sel, W * 4), alloc(&p->sel2, W * 4), alloc(&p->nSel, 4), alloc(&p->result, 4), alloc(&p->okValid, W), alloc(&p->keep, W);
+    if (!rc) {
+        cub::DeviceSelect::Flagged(nullptr, p->selBytes, thrust::counting_iterator<uint32_t>(0), p->keep, p->sel, p->nSel, (int)W);
+        alloc(&p->selTemp, p->selBytes);
+    }
+    if (!rc && p->hasGoal) {
+        alloc(&p->goal, sb);
+        if (!rc) rc = uploadSync(ctx, p->goal, prm->goal_state, sb);
+    }
+    if (!rc) rc = memsetSync(ctx, p->lists, 0, (2 + 64 + 4096) * 4);
+    if (!rc) rc = memsetSync(ctx, p->result, 0, 4);
+    if (!rc && cudaMallocHost((void**)&p->host, 2 * sizeof(uint32_t)) != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_create: pinned allocation failed");
+    if (rc) {
+        pprmFree(p);
+        return rc;
+    }
+    *out = p;
+    return MPTG_OK;
+}
+
+int mptg_pprm_destroy(mptg_pprm* p) {
+    if (!p) return MPTG_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    pprmFree(p);
+    return MPTG_OK;
+}
+
+int mptg_pprm_add_state(mptg_pprm* p, const void* state, uint32_t marks, uint32_t* node_out) {
+    if (!p || !state || (marks & ~(MPTG_PPRM_START | MPTG_PPRM_GOAL))) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_pprm_add_state: bad argument");
+    if (p->size >= p->capacity) return fail(p->ctx, MPTG_ERR_CAPACITY, "mptg_pprm_add_state: roadmap is full");
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int rc = uploadSync(ctx, p->samples, state, (size_t)p->D * p->scalar)) return rc;
+    uint32_t first = 0, added = 0;
+    if (int rc = pprmProcess(p, 1, marks, &first, &added)) return rc;
+    if (node_out) *node_out = added ? first : MPTG_NO_INDEX;
+    return MPTG_OK;
+}
+
+int mptg_pprm_wave(mptg_pprm* p, uint32_t n_samples, uint32_t* size_out, uint32_t* solved_out) {
+    if (!p || n_samples == 0 || n_samples > p->maxWave) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_pprm_wave: bad argument");
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // sample (pprm.hpp:372-374: no goal bias in PPRM); uniform 0 of every sample's stream stays the unused bias draw
+    if (p->scalar == MPTG_F32) launchSample<float>(ctx, &p->space, p->bounds, p->seed, p->drawn, n_samples, nullptr, 0.0, p->samples);
+    else launchSample<double>(ctx, &p->space, p->bounds, p->seed, p->drawn, n_samples, nullptr, 0.0, p->samples);
+    MPTG_LAUNCHED(ctx);
+    p->drawn += n_samples;
+    uint32_t first = 0, added = 0;
+    const int rc = pprmProcess(p, n_samples, 0u, &first, &added);
+    ++p->waves;
+    if (size_out) *size_out = p->size;
+    if (solved_out) *solved_out = p->solved ? 1u : 0u;
+    return rc;
+}
+
+uint32_t mptg_pprm_size(const mptg_pprm* p) { return p ? p->size : 0; }
+uint64_t mptg_pprm_samples_drawn(const mptg_pprm* p) { return p ? p->drawn : 0; }
+uint32_t mptg_pprm_row_stride(const mptg_pprm* p) { return p ? p->stride : 0; }
+
+int mptg_pprm_get_graph(mptg_pprm* p, uint32_t first, uint32_t count, void* states_out, uint32_t* edge_idx_out, void* edge_dist_out,
+                        uint8_t* marks_out, uint32_t* component_out) {
+    if (!p || (uint64_t)first + count > p->size) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_pprm_get_graph: bad range");
+    if (count == 0) return MPTG_OK;
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t sb = (size_t)p->D * p->scalar, K = p->stride;
+    if (states_out) MPTG_CUDA(ctx, cudaMemcpyAsync(states_out, (char*)p->nodes + first * sb, count * sb, cudaMemcpyDeviceToHost, st));
+    if (edge_idx_out) MPTG_CUDA(ctx, cudaMemcpyAsync(edge_idx_out, p->edgeIdx + (size_t)first * K, (size_t)count * K * 4, cudaMemcpyDeviceToHost, st));
+    if (edge_dist_out)
+        MPTG_CUDA(ctx, cudaMemcpyAsync(edge_dist_out, (char*)p->edgeDist + (size_t)first * K * p->scalar, (size_t)count * K * p->scalar,
+                                       cudaMemcpyDeviceToHost, st));
+    if (marks_out) MPTG_CUDA(ctx, cudaMemcpyAsync(marks_out, p->marks + first, count, cudaMemcpyDeviceToHost, st));
+    if (component_out) {
+        void* tmp;
+        if (int rc = scratch(ctx, 1, (size_t)count * 4, &tmp)) return rc;
+        pprmRootKernel<<<(count + 255) / 256, 256, 0, st>>>(p->comp, first, count, (uint32_t*)tmp);
+        MPTG_LAUNCHED(ctx);
+        MPTG_CUDA(ctx, cudaMemcpyAsync(component_out, tmp, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+    }
+    MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    return MPTG_OK;
+}
+
+}  // extern "C"

@@ -139,3 +139,73 @@ def prrt_scene():
     start = free[len(free) // 7][::-1].astype(np.float64)
     goal = free[-len(free) // 9][::-1].astype(np.float64)
     return occ, [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], start, goal
+
+
+def pprm_k(space, n):
+    """k = ceil(kRRG * ln(n + 1)), kRRG = e + e / dimensions, in the space's scalar type (src/mpt/impl/pprm/pprm.hpp:146,302-303)."""
+    dt = space.dtype
+    e = dt(math.e)
+    return max(1, int(np.ceil((e + e / dt(space.dimensions)) * dt(math.log(n + 1.0)))))
+
+
+def replay_pprm(oracle, og, sp, lo, hi, starts, goals, goal, goal_radius, seed, waves, W, stride):
+    """PPRM's Worker::addSample (src/mpt/impl/pprm/pprm.hpp:298-339) on the oracle, one wave at a time, on the same
+    samples: -> (states, edge rows [n, stride] of neighbour indices, edge distances, marks)."""
+    D = sp.scalars
+    states = np.empty((0, D), dtype=sp.dtype)
+    rows_i, rows_d, marks = [], [], []
+
+    def process(samples, forced):
+        nonlocal states
+        samples = np.asarray(samples, dtype=sp.dtype).reshape(-1, D)
+        cand = samples[og.valid(samples) != 0]
+        if cand.shape[0] == 0:
+            return
+        n = states.shape[0]
+        if n > 0:
+            k = min(pprm_k(sp, n), stride)
+            idx, dist, cnt = oracle.knn(sp, states, cand, k)
+            keep = ~((cnt > 0) & (dist[:, 0] < np.finfo(sp.dtype).eps))
+            cand, idx, dist, cnt = cand[keep], idx[keep], dist[keep], cnt[keep]
+        for s in range(cand.shape[0]):
+            ri = np.full(stride, NO_INDEX, dtype=np.uint32)
+            rd = np.zeros(stride, dtype=sp.dtype)
+            if n > 0 and cnt[s] > 0:
+                c = int(cnt[s])
+                ok = og.link(np.repeat(cand[s:s + 1], c, axis=0), states[idx[s, :c]]) != 0
+                ri[:c][ok] = idx[s, :c][ok]
+                rd[:c][ok] = dist[s, :c][ok]
+            mk = forced
+            if goal is not None and not (mk & 2):
+                if oracle.distance(sp, cand[s:s + 1], np.asarray(goal, dtype=sp.dtype).reshape(1, D))[0] <= sp.dtype(goal_radius):
+                    mk |= 2
+            rows_i.append(ri), rows_d.append(rd), marks.append(mk)
+        states = np.concatenate([states, cand])
+
+    for q in starts:
+        process([q], 1)
+    for q in goals:
+        process([q], 2)
+    drawn = 0
+    for _ in range(waves):
+        process(oracle.sample(sp, lo, hi, seed, drawn, W), 0)
+        drawn += W
+    return states, np.stack(rows_i), np.stack(rows_d), np.asarray(marks, dtype=np.uint8)
+
+
+def components(edge_idx):
+    """Connected-component label (smallest node index) per node of the undirected union of the edge rows."""
+    n = edge_idx.shape[0]
+    comp = np.arange(n)
+
+    def find(x):
+        while comp[x] != x:
+            comp[x] = comp[comp[x]]
+            x = comp[x]
+        return x
+
+    for r, c in zip(*np.nonzero(edge_idx != NO_INDEX)):
+        a, b = find(int(r)), find(int(edge_idx[r, c]))
+        if a != b:
+            comp[max(a, b)] = min(a, b)
+    return np.array([find(i) for i in range(n)])

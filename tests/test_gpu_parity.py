@@ -478,6 +478,50 @@ def test_device_prrt_on_meshes_builds_a_valid_tree(ctx, oracle):
     assert edge.max() <= 30.0 * (1 + 1e-4), f"longest tree edge {edge.max()}"
 
 
+def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W):
+    pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W)
+    assert pl.add_start(start) == 0 and pl.add_goal(goal) == 1
+    assert pl.add_goal(goal) == m.NO_INDEX  # closer than epsilon to a node: rejected (pprm.hpp:306-308)
+    for _ in range(waves):
+        pl.wave(W)
+    st, ei, ed, mk, cp = pl.graph()
+    ws, wi, wd, wm = kats.replay_pprm(oracle, og, sp, lo, hi, [start], [goal], goal, goal_radius, seed, waves, W, pl.row_stride)
+    assert pl.samples_drawn == waves * W and st.shape[0] > 100
+    assert np.array_equal(st, ws) and np.array_equal(ei, wi) and np.array_equal(ed, wd) and np.array_equal(mk, wm)
+    # components: same partition as a host union-find over the same edges; solved() <=> start and goal connected
+    want = kats.components(wi)
+    assert np.array_equal(cp == cp[:, None], want == want[:, None]) if st.shape[0] <= 2048 else np.array_equal(cp, want)
+    starts, goals = np.nonzero(mk & 1)[0], np.nonzero(mk & 2)[0]
+    assert pl.solved() == bool(np.isin(want[goals], want[starts]).any())
+    if pl.solved():
+        path = pl.solution()
+        assert np.array_equal(path[0], np.asarray(start, dtype=sp.dtype)) and (mk[np.nonzero((st == path[-1]).all(axis=1))[0][0]] & 2)
+        assert og.link(path[:-1], path[1:]).all()
+    n_edges = int((ei != m.NO_INDEX).sum())
+    pl.close()
+    return st.shape[0], n_edges
+
+
+def test_device_pprm_replays_the_reference_loop(ctx, oracle):
+    """Device-resident PPRM (mptg_pprm_*): the roadmap after every wave equals the one PPRM's addSample loop builds on the
+    oracle from the same samples -- states, edge rows (neighbour, distance), marks, components, solved()."""
+    # occupancy grid, planar L2 doubles (BASELINE configs[1] geometry)
+    occ = W.synthetic_grid(500, 400, seed=2)
+    sp = m.lp_space(2, 2, m.F64)
+    free = np.argwhere(occ == 0)
+    start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
+    n, e = _check_device_pprm(ctx, oracle, sp, m.Scenario.grid(ctx, occ, m.F64), oracle.grid(occ), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1],
+                              start, goal, 1e-6, 5, 5, 256)
+    assert e > 3 * n
+    # 8-link arm, L1 over [-pi, pi]^8 (BASELINE configs[3]: PPRM for the link manipulator)
+    lengths, radius, circles = W.link_arm_scene(8)
+    sp8 = m.lp_space(8, 1, m.F64)
+    arm, oarm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64), oracle.link_arm(lengths, radius, circles)
+    cand = W.box_states(256, 8, 3, -np.pi, np.pi)
+    free8 = cand[oarm.valid(cand) != 0]
+    _check_device_pprm(ctx, oracle, sp8, arm, oarm, -np.pi, np.pi, free8[0], free8[1], 1e-6, 11, 4, 200)
+
+
 # ------------------------------------------------------------------ grid / shapes / link arm
 @pytest.mark.parametrize("scalar", [m.F64, m.F32])
 def test_grid_matches_oracle(ctx, oracle, scalar):
