@@ -418,6 +418,26 @@ def secondary(ctx, torch, dev, stream):
     dt = time.perf_counter() - t0
     out["device_prrt_grid"] = {"nodes_per_s": (pl.size - n0) / dt, "samples_per_s": (pl.samples_drawn - 16384) / dt, "nodes": pl.size, "s": dt}
     pl.close()
+    # device-resident PPRM (BASELINE configs[3]: PPRM for the N-link arm): roadmap, components and every stage on the GPU
+    for n_links in (8, 16):
+        lengths, radius, circles = W.link_arm_scene(n_links)
+        spn = m.lp_space(n_links, 1, m.F64)
+        arm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
+        cand = W.box_states(512, n_links, 3, -np.pi, np.pi)
+        ok = arm.valid(cand) != 0
+        pp = m.DevicePPRM(arm, spn, -np.pi, np.pi, seed=23, capacity=1 << 18, max_wave=4096)
+        pp.add_start(cand[ok][0])
+        pp.add_goal(cand[ok][1])
+        pp.wave(4096)
+        ctx.sync()
+        t0, n0 = time.perf_counter(), pp.size
+        while pp.size < 150_000:
+            pp.wave(4096)
+        dt = time.perf_counter() - t0
+        ei = pp.graph(n0, pp.size - n0)[1]
+        out[f"device_pprm_arm{n_links}"] = {"nodes_per_s": (pp.size - n0) / dt, "edges_checked_per_s": float((pp.size - n0) * pp.row_stride) / dt,
+                                            "roadmap_edges": int((ei != m.NO_INDEX).sum()), "nodes": pp.size, "solved": pp.solved(), "s": dt}
+        pp.close()
     # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
     goal = free[-len(free) // 9][::-1].astype(np.float64)
     ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)

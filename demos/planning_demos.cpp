@@ -324,6 +324,13 @@ void linkManipulator(const Options& opt) {
     char name[64];
     std::snprintf(name, sizeof name, "link_manipulator N=%d", N);
     report(name, "PPRM", planner, scenario, first, total, opt);
+    if (opt.devicePrrt) {  // the same roadmap planner with the roadmap kept on the GPU (mptg_pprm_*)
+        Planner<Scenario, PPRM<device_resident, report_stats<true>, wave_size<4096>, max_nodes<(1 << 19)>>> dev(scenario, opt.seed);
+        dev.addStart(start);
+        dev.addGoal(goal);
+        auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
+        report(name, "PPRM, device-resident", dev, scenario, dFirst, dTotal, opt);
+    }
 }
 
 static void onCrash(int sig) {
@@ -352,7 +359,7 @@ int main(int argc, char** argv) {
         else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
         else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
         else {
-            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--device-prrt] [--map file.pgm] [--seed S]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--device-prrt (also run the device-resident PRRT / PPRM)] [--map file.pgm] [--seed S]\n", argv[0]);
             return 2;
         }
     }

@@ -53,7 +53,7 @@ template <int n>
 struct wave_size {};
 // the nearest-neighbour strategy tag of this library (the analogue of nigh::KDTreeBatch<> etc.)
 struct GpuBatch {};
-// PRRT<device_resident, ...>: keep the tree on the GPU (mptg_prrt_*), sample on the device
+// PRRT<device_resident, ...> / PPRM<device_resident, ...>: keep the tree / roadmap on the GPU (mptg_prrt_*, mptg_pprm_*), sample on the device
 struct device_resident {};
 template <int n>
 struct max_nodes {};
@@ -997,6 +997,173 @@ public:
     Context& context() { return ctx_; }
 };
 
+// ------------------------------------------------------------------ device-resident PPRM
+// Planner<Scenario, PPRM<device_resident, ...>>: the roadmap, its components and every stage of PPRM's addSample
+// (impl/pprm/pprm.hpp:298-339) stay on the GPU (mptg_pprm_*); two words come back per wave.  solution() runs the
+// reference's Dijkstra (pprm.hpp:218-246) over a host mirror fetched on demand.
+template <typename Scenario, int waveSize, int maxNodes, bool reportStats>
+class DevicePPRM {
+    using Space = typename Scenario::Space;
+    using State = typename Space::Type;
+    using Distance = typename Space::Distance;
+    static constexpr std::uint32_t NONE = 0xFFFFFFFFu;
+    Scenario scenario_;
+    Context ctx_;
+    Geometry geom_;
+    mptg_space_desc desc_;
+    mptg_pprm* pprm_ = nullptr;
+    std::uint32_t wave_ = waveSize, size_ = 0, solved_ = 0, stride_ = 0;
+    std::size_t starts_ = 0, goals_ = 0;
+    std::uint64_t waves_ = 0;
+    double seconds_ = 0;
+    mutable std::vector<State> states_;  // host mirror, refreshed on demand
+    mutable std::vector<std::uint32_t> edgeIdx_;
+    mutable std::vector<Distance> edgeDist_;
+    mutable std::vector<std::uint8_t> marks_;
+
+    void mirror() const {
+        if (states_.size() == size_) return;
+        states_.resize(size_), marks_.resize(size_);
+        edgeIdx_.resize((std::size_t)size_ * stride_), edgeDist_.resize((std::size_t)size_ * stride_);
+        check(mptg_pprm_get_graph(pprm_, 0, size_, states_.data(), edgeIdx_.data(), edgeDist_.data(), marks_.data(), nullptr), ctx_.get(),
+              "mptg_pprm_get_graph");
+    }
+    std::uint32_t add(const State& q, std::uint32_t marks) {
+        std::uint32_t node = NONE;
+        check(mptg_pprm_add_state(pprm_, q.data(), marks, &node), ctx_.get(), "mptg_pprm_add_state");
+        size_ = mptg_pprm_size(pprm_);
+        return node;
+    }
+
+public:
+    explicit DevicePPRM(const Scenario& scenario = Scenario(), std::uint64_t seed = std::random_device{}(), int device = -1)
+        : scenario_(scenario), ctx_(device), geom_(scenario_.makeGeometry(ctx_)), desc_(scenario_.space().desc()) {
+        double lo[MPTG_MAX_SCALARS] = {0}, hi[MPTG_MAX_SCALARS] = {0};
+        detail::fillBounds(scenario_.bounds(), 0, lo, hi);
+        mptg_pprm_params prm{};
+        prm.space = &desc_, prm.lo = lo, prm.hi = hi;
+        State g{};
+        if constexpr (impl::has_goal_fn<Scenario>::value) {  // GoalState: goal test on the device
+            g = scenario_.goal().state();
+            prm.goal_state = g.data(), prm.goal_radius = (double)scenario_.goal().radius();
+        }
+        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
+        check(mptg_pprm_create(ctx_.get(), geom_.get(), &prm, &pprm_), ctx_.get(), "mptg_pprm_create");
+        stride_ = mptg_pprm_row_stride(pprm_);
+    }
+    DevicePPRM(const DevicePPRM&) = delete;
+    DevicePPRM& operator=(const DevicePPRM&) = delete;
+    ~DevicePPRM() {
+        if (pprm_) mptg_pprm_destroy(pprm_);
+    }
+    void setWaveSize(std::uint32_t w) { wave_ = w ? std::min<std::uint32_t>(w, waveSize) : 1; }
+
+    template <typename... Args>
+    void addStart(Args&&... args) {  // pprm.hpp:156-164
+        if (add(State(std::forward<Args>(args)...), MPTG_PPRM_START) != NONE) ++starts_;
+    }
+    template <typename... Args>
+    void addGoal(Args&&... args) {  // :166-169
+        if (add(State(std::forward<Args>(args)...), MPTG_PPRM_GOAL) != NONE) ++goals_;
+    }
+    template <typename DoneFn>
+    std::enable_if_t<std::is_same_v<bool, std::invoke_result_t<DoneFn>>> solve(DoneFn doneFn) {  // :171-183
+        if (goals_ == 0) {
+            std::mt19937_64 unused;
+            addGoal(impl::sampleGoalState(scenario_, unused));
+        }
+        if (goals_ == 0 || starts_ == 0) throw std::runtime_error("PPRM requires both start and goal configurations");
+        const auto t0 = std::chrono::steady_clock::now();
+        while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
+            check(mptg_pprm_wave(pprm_, wave_, &size_, &solved_), ctx_.get(), "mptg_pprm_wave");
+            ++waves_;
+        }
+        seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    template <typename Rep, typename Period>
+    void solveFor(const std::chrono::duration<Rep, Period>& duration) {
+        solveUntil(std::chrono::steady_clock::now() + duration);
+    }
+    template <class Clock, class Duration>
+    void solveUntil(const std::chrono::time_point<Clock, Duration>& endTime) {
+        solve([&] { return Clock::now() >= endTime; });
+    }
+    template <typename DoneFn, typename Rep, typename Period>
+    void solveFor(DoneFn doneFn, const std::chrono::duration<Rep, Period>& duration) {
+        const auto endTime = std::chrono::steady_clock::now() + duration;
+        solve([&] { return doneFn() || std::chrono::steady_clock::now() >= endTime; });
+    }
+    bool solved() const { return solved_ != 0; }
+    std::size_t size() const { return size_; }
+    std::size_t edgeCount() const {
+        mirror();
+        std::size_t c = 0;
+        for (std::uint32_t e : edgeIdx_) c += e != NONE;
+        return c;
+    }
+    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246)
+    std::vector<State> solution() const {
+        mirror();
+        const std::size_t n = states_.size();
+        std::vector<std::vector<std::pair<std::uint32_t, Distance>>> adj(n);
+        for (std::uint32_t i = 0; i < n; ++i)
+            for (std::uint32_t j = 0; j < stride_; ++j) {
+                const std::uint32_t nb = edgeIdx_[(std::size_t)i * stride_ + j];
+                if (nb == NONE) continue;
+                const Distance d = edgeDist_[(std::size_t)i * stride_ + j];
+                adj[i].push_back({nb, d}), adj[nb].push_back({i, d});
+            }
+        std::vector<Distance> dist(n, std::numeric_limits<Distance>::infinity());
+        std::vector<std::uint32_t> prev(n, NONE);
+        using QE = std::pair<Distance, std::uint32_t>;
+        std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+        for (std::uint32_t s = 0; s < n; ++s)
+            if (marks_[s] & MPTG_PPRM_START) dist[s] = 0, pq.push({0, s});
+        std::uint32_t hit = NONE;
+        while (!pq.empty()) {
+            auto [d, u] = pq.top();
+            pq.pop();
+            if (d > dist[u]) continue;
+            if (marks_[u] & MPTG_PPRM_GOAL) {
+                hit = u;
+                break;
+            }
+            for (auto [v, w] : adj[u])
+                if (d + w < dist[v]) dist[v] = d + w, prev[v] = u, pq.push({dist[v], v});
+        }
+        std::vector<State> path;
+        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(states_[x]);
+        std::reverse(path.begin(), path.end());
+        return path;
+    }
+    template <typename Fn>
+    void solution(Fn fn) const {
+        for (const State& q : solution()) fn(q);
+    }
+    template <typename Visitor>
+    void visitGraph(Visitor&& visitor) const {  // :380-387 (each edge from both of its ends)
+        mirror();
+        std::vector<std::vector<std::uint32_t>> back(states_.size());
+        for (std::uint32_t i = 0; i < states_.size(); ++i)
+            for (std::uint32_t j = 0; j < stride_; ++j)
+                if (edgeIdx_[(std::size_t)i * stride_ + j] != NONE) back[edgeIdx_[(std::size_t)i * stride_ + j]].push_back(i);
+        for (std::uint32_t i = 0; i < states_.size(); ++i) {
+            visitor.vertex(states_[i]);
+            for (std::uint32_t j = 0; j < stride_; ++j)
+                if (edgeIdx_[(std::size_t)i * stride_ + j] != NONE) visitor.edge(states_[edgeIdx_[(std::size_t)i * stride_ + j]]);
+            for (std::uint32_t b : back[i]) visitor.edge(states_[b]);
+        }
+    }
+    void printStats() const {
+        std::clog << "nodes in graph: " << size() << "\n";
+        if constexpr (reportStats)
+            std::clog << "  device-resident waves: " << waves_ << " of " << wave_ << " samples, " << mptg_pprm_samples_drawn(pprm_) << " samples drawn, "
+                      << seconds_ * 1e3 << " ms in solve(), kernel launches: " << ctx_.launches() << "\n";
+    }
+    const Scenario& scenario() const { return scenario_; }
+    Context& context() { return ctx_; }
+};
+
 // ------------------------------------------------------------------ resolvers (planner.hpp:41-47)
 template <typename Scenario, typename Algorithm>
 struct PlannerResolver;
@@ -1018,7 +1185,10 @@ struct PlannerResolver<Scenario, PRRTStar<Options...>> {
 };
 template <typename Scenario, typename... Options>
 struct PlannerResolver<Scenario, PPRM<Options...>> {
-    using type = WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>>;
+    using type = std::conditional_t<pack_contains_v<device_resident, Options...>,
+                                    DevicePPRM<Scenario, pack_int_tag_v<wave_size, 4096, Options...>, pack_int_tag_v<max_nodes, 1 << 20, Options...>,
+                                               pack_bool_tag_v<report_stats, false, Options...>>,
+                                    WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>>>;
 };
 
 }  // namespace impl

@@ -116,6 +116,8 @@ int main() {
     static_assert(!std::is_same_v<Planner<S, PRRT<device_resident>>, Planner<S, PRRT<>>>);
     static_assert(std::is_same_v<Planner<S, PRRT<device_resident, wave_size<4096>>>, Planner<S, PRRT<wave_size<4096>, device_resident>>>);
     testSolvingBasicScenario<PRRT<device_resident, report_stats<true>, wave_size<4096>, max_nodes<(1 << 18)>>>("PRRT device-resident");
+    static_assert(!std::is_same_v<Planner<S, PPRM<device_resident>>, Planner<S, PPRM<>>>);
+    testSolvingBasicScenario<PPRM<device_resident, report_stats<true>, wave_size<512>, max_nodes<(1 << 16)>>>("PPRM device-resident");
 #endif
     testPRRTStarInvariants();
     // error behaviour (impl/prrt/prrt.hpp:197-198, impl/pprm/pprm.hpp:179-180)
