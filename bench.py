@@ -418,6 +418,23 @@ def secondary(ctx, torch, dev, stream):
     dt = time.perf_counter() - t0
     out["device_prrt_grid"] = {"nodes_per_s": (pl.size - n0) / dt, "samples_per_s": (pl.samples_drawn - 16384) / dt, "nodes": pl.size, "s": dt}
     pl.close()
+    # device-resident PRRT* (BASELINE configs[1]: PRRT* on the occupancy grid): same map, start and range
+    goal = free[-len(free) // 9][::-1].astype(np.float64)
+    ps = m.DevicePRRTStar(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], range=200.0, goal=goal, goal_radius=12.0,
+                          seed=17, capacity=1 << 20, max_wave=8192)
+    ps.add_start(start)
+    t0 = time.perf_counter()
+    first_solution = None
+    while ps.size < 200_000:
+        ps.wave(8192)
+        if first_solution is None and ps.solved():
+            first_solution = (time.perf_counter() - t0, ps.size)
+    dt = time.perf_counter() - t0
+    out["device_prrtstar_grid"] = {"nodes_per_s": ps.size / dt, "nodes": ps.size, "s": dt, "rewires": ps.rewires, "solved": ps.solved(),
+                                   "first_solution_s": first_solution[0] if first_solution else None,
+                                   "first_solution_nodes": first_solution[1] if first_solution else None,
+                                   "solution_cost": ps.solution_cost() if ps.solved() else None}
+    ps.close()
     # device-resident PPRM (BASELINE configs[3]: PPRM for the N-link arm): roadmap, components and every stage on the GPU
     for n_links in (8, 16):
         lengths, radius, circles = W.link_arm_scene(n_links)
@@ -439,7 +456,6 @@ def secondary(ctx, torch, dev, stream):
                                             "roadmap_edges": int((ei != m.NO_INDEX).sum()), "nodes": pp.size, "solved": pp.solved(), "s": dt}
         pp.close()
     # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
-    goal = free[-len(free) // 9][::-1].astype(np.float64)
     ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)
     if ref:
         out["reference_planner_cpu_grid"] = ref

@@ -214,6 +214,11 @@ void png2d(const Options& opt) {
         dev.setRange(200);
         auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
         report("png_2d", "PRRT, device-resident", dev, scenario, dFirst, dTotal, opt);
+        Planner<Scenario, PRRTStar<device_resident, report_stats<true>, wave_size<8192>, max_nodes<(1 << 21)>>> star(scenario, opt.seed);
+        star.addStart(start);
+        star.setRange(200);
+        auto [sFirst, sTotal] = runUntilSolved(star, opt.timeMs);
+        report("png_2d", "PRRT*, device-resident", star, scenario, sFirst, sTotal, opt);
     }
 }
 
@@ -282,6 +287,11 @@ void se3RigidBody(const Options& opt) {
         dev.setRange(40);
         auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
         report("se3_rigid_body", "PRRT, device-resident", dev, scenario, dFirst, dTotal, opt);
+        Planner<Scenario, PRRTStar<device_resident, report_stats<true>, wave_size<8192>, max_nodes<(1 << 21)>>> star(scenario, opt.seed);
+        star.addStart(start);
+        star.setRange(40);
+        auto [sFirst, sTotal] = runUntilSolved(star, opt.timeMs);
+        report("se3_rigid_body", "PRRT*, device-resident", star, scenario, sFirst, sTotal, opt);
     }
 }
 

@@ -289,6 +289,29 @@ uint32_t mptg_pprm_row_stride(const mptg_pprm* pprm);
 int mptg_pprm_get_graph(mptg_pprm* pprm, uint32_t first, uint32_t count, void* states_out, uint32_t* edge_idx_out, void* edge_dist_out,
                         uint8_t* marks_out, uint32_t* component_out);
 
+/* --------------------------------------------------------- device-resident PRRT* 
+ * Tree (states, parents, costs), nearest-neighbour structure and every stage of PRRT*'s Worker::addSample
+ * (src/mpt/impl/prrt_star/prrt_star.hpp:510-657) on the GPU, one wave = n_samples iterations run as a batch against the
+ * tree as it stood when the wave began: sample -> nearest -> steer (distance recomputed, :526-537) -> valid -> link ->
+ * k nearest (k = ceil(kRRG ln(size+1)), kRRG = rewire_factor e (1 + 1/d), rrg_rewire_neighbors.hpp:53-67) -> parent =
+ * first valid neighbour in cost + distance order, up to the near node or the cost cut-off (:565-605) -> append ->
+ * rewire every unchecked neighbour whose cost would drop (:626-656).  Inside a wave rewiring offers are evaluated on
+ * the costs before the wave's rewiring step, each node takes its best valid offer (smallest cost, then smallest
+ * (sample, slot)), all are applied at once (this cannot close a cycle) and the decreases are pushed to the subtrees
+ * (:664-688).  Parameters as for mptg_prrt_create plus Planner::setRewireFactor() (default of the reference 1.1). */
+typedef struct mptg_prrtstar mptg_prrtstar;
+int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params* params, double rewire_factor, mptg_prrtstar** out);
+int mptg_prrtstar_destroy(mptg_prrtstar* star);
+int mptg_prrtstar_add_start(mptg_prrtstar* star, const void* state);
+/* goal_node_out: the goal node of smallest cost so far (Planner::solution() / solutionCost(), :317-337), MPTG_NO_INDEX
+ * while unsolved. */
+int mptg_prrtstar_wave(mptg_prrtstar* star, uint32_t n_samples, uint32_t* size_out, uint32_t* goal_node_out);
+uint32_t mptg_prrtstar_size(const mptg_prrtstar* star);
+uint64_t mptg_prrtstar_samples_drawn(const mptg_prrtstar* star);
+uint64_t mptg_prrtstar_rewires(const mptg_prrtstar* star);
+/* states, parents (MPTG_NO_INDEX for a start) and path costs (space scalar type) of nodes first .. first+count-1 */
+int mptg_prrtstar_get_tree(mptg_prrtstar* star, uint32_t first, uint32_t count, void* states_out, uint32_t* parents_out, void* costs_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -997,6 +997,147 @@ public:
     Context& context() { return ctx_; }
 };
 
+// ------------------------------------------------------------------ device-resident PRRT* 
+// Planner<Scenario, PRRTStar<device_resident, ...>>: tree, costs, parent choice and rewiring on the GPU (mptg_prrtstar_*,
+// wave-parallel semantics stated in mptg.h); the k-nearest rewiring variant.
+template <typename Scenario, int waveSize, int maxNodes, bool reportStats>
+class DevicePRRTStar {
+    using Space = typename Scenario::Space;
+    using State = typename Space::Type;
+    using Distance = typename Space::Distance;
+    static constexpr std::uint32_t NONE = 0xFFFFFFFFu;
+    Scenario scenario_;
+    Context ctx_;
+    Geometry geom_;
+    mptg_space_desc desc_;
+    std::uint64_t seed_;
+    mptg_prrtstar* prrt_ = nullptr;
+    Distance rewireFactor_{1.1};
+    Distance maxDistance_{std::numeric_limits<Distance>::infinity()};
+    Distance goalBias_{0.01};
+    std::vector<State> starts_;
+    std::uint32_t wave_ = waveSize, size_ = 0, goalNode_ = NONE;
+    std::uint64_t waves_ = 0;
+    mutable std::uint64_t mirroredWaves_ = ~0ull;
+    double seconds_ = 0;
+    mutable std::vector<State> states_;  // host mirror, refreshed on demand
+    mutable std::vector<std::uint32_t> parent_;
+    mutable std::vector<Distance> cost_;
+
+    void create() {  // deferred to the first solve() so that setRange / setGoalBias apply
+        if (prrt_) return;
+        double lo[MPTG_MAX_SCALARS] = {0}, hi[MPTG_MAX_SCALARS] = {0};
+        detail::fillBounds(scenario_.bounds(), 0, lo, hi);
+        const auto& goal = scenario_.goal();
+        const State g = goal.state();
+        mptg_prrt_params prm{};
+        prm.space = &desc_, prm.lo = lo, prm.hi = hi;
+        prm.range = std::isfinite((double)maxDistance_) ? (double)maxDistance_ : 1.7e308;
+        prm.goal_bias = (double)goalBias_, prm.goal_state = g.data(), prm.goal_radius = (double)goal.radius();
+        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
+        check(mptg_prrtstar_create(ctx_.get(), geom_.get(), &prm, (double)rewireFactor_, &prrt_), ctx_.get(), "mptg_prrtstar_create");
+        for (const State& q : starts_) check(mptg_prrtstar_add_start(prrt_, q.data()), ctx_.get(), "mptg_prrtstar_add_start");
+        size_ = (std::uint32_t)starts_.size();
+    }
+    void mirror() const {
+        if (!prrt_ || (states_.size() == size_ && mirroredWaves_ == waves_)) return;  // rewiring changes old nodes too
+        mirroredWaves_ = waves_;
+        states_.resize(size_);
+        parent_.resize(size_);
+        cost_.resize(size_);
+        check(mptg_prrtstar_get_tree(prrt_, 0, size_, states_.data(), parent_.data(), cost_.data()), ctx_.get(), "mptg_prrtstar_get_tree");
+    }
+
+public:
+    explicit DevicePRRTStar(const Scenario& scenario = Scenario(), std::uint64_t seed = std::random_device{}(), int device = -1)
+        : scenario_(scenario), ctx_(device), geom_(scenario_.makeGeometry(ctx_)), desc_(scenario_.space().desc()), seed_(seed) {}
+    DevicePRRTStar(const DevicePRRTStar&) = delete;
+    DevicePRRTStar& operator=(const DevicePRRTStar&) = delete;
+    ~DevicePRRTStar() {
+        if (prrt_) mptg_prrtstar_destroy(prrt_);
+    }
+
+    void setRewireFactor(Distance f) { rewireFactor_ = f; }
+    void setGoalBias(Distance bias) { goalBias_ = bias; }
+    Distance getGoalBias() const { return goalBias_; }
+    void setRange(Distance range) { maxDistance_ = range; }
+    Distance getRange() const { return maxDistance_; }
+    void setWaveSize(std::uint32_t w) { wave_ = w ? std::min<std::uint32_t>(w, waveSize) : 1; }
+
+    template <typename... Args>
+    void addStart(Args&&... args) {
+        starts_.emplace_back(std::forward<Args>(args)...);
+        if (prrt_) {
+            check(mptg_prrtstar_add_start(prrt_, starts_.back().data()), ctx_.get(), "mptg_prrtstar_add_start");
+            ++size_;
+        }
+    }
+    template <typename DoneFn>
+    std::enable_if_t<std::is_same_v<bool, std::invoke_result_t<DoneFn>>> solve(DoneFn doneFn) {
+        if (starts_.empty()) throw std::runtime_error("there are no valid initial states");  // prrt.hpp:197-198
+        create();
+        const auto t0 = std::chrono::steady_clock::now();
+        while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
+            check(mptg_prrtstar_wave(prrt_, wave_, &size_, &goalNode_), ctx_.get(), "mptg_prrtstar_wave");
+            ++waves_;
+        }
+        seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    template <typename Rep, typename Period>
+    void solveFor(const std::chrono::duration<Rep, Period>& duration) {
+        solveUntil(std::chrono::steady_clock::now() + duration);
+    }
+    template <class Clock, class Duration>
+    void solveUntil(const std::chrono::time_point<Clock, Duration>& endTime) {
+        solve([&] { return Clock::now() >= endTime; });
+    }
+    template <typename DoneFn, typename Rep, typename Period>
+    void solveFor(DoneFn doneFn, const std::chrono::duration<Rep, Period>& duration) {
+        const auto endTime = std::chrono::steady_clock::now() + duration;
+        solve([&] { return doneFn() || std::chrono::steady_clock::now() >= endTime; });
+    }
+    bool solved() const { return goalNode_ != NONE; }
+    Distance solutionCost() const {  // prrt_star.hpp:317-322
+        if (!solved()) return std::numeric_limits<Distance>::quiet_NaN();
+        mirror();
+        return cost_[goalNode_];
+    }
+    // for tests: tree invariants
+    Distance nodeCost(std::uint32_t n) const { return mirror(), cost_[n]; }
+    std::uint32_t nodeParent(std::uint32_t n) const { return mirror(), parent_[n]; }
+    const State& nodeState(std::uint32_t n) const { return mirror(), states_[n]; }
+    std::uint64_t rewires() const { return prrt_ ? mptg_prrtstar_rewires(prrt_) : 0; }
+    std::size_t size() const { return prrt_ ? size_ : starts_.size(); }
+    std::vector<State> solution() const {
+        std::vector<State> path;
+        if (!solved()) return path;
+        mirror();
+        for (std::uint32_t n = goalNode_; n != NONE; n = parent_[n]) path.push_back(states_[n]);
+        std::reverse(path.begin(), path.end());
+        return path;
+    }
+    template <typename Fn>
+    void solution(Fn fn) const {
+        for (const State& q : solution()) fn(q);
+    }
+    template <typename Visitor>
+    void visitGraph(Visitor&& visitor) const {
+        mirror();
+        for (std::uint32_t n = 0; n < states_.size(); ++n) {
+            visitor.vertex(states_[n]);
+            if (parent_[n] != NONE) visitor.edge(states_[parent_[n]]);
+        }
+    }
+    void printStats() const {
+        std::clog << "nodes in graph: " << size() << "\nsolutions: " << (solved() ? 1 : 0) << "\n";
+        if constexpr (reportStats)
+            std::clog << "  device-resident waves: " << waves_ << " of " << wave_ << " samples, " << (prrt_ ? mptg_prrtstar_samples_drawn(prrt_) : 0)
+                      << " samples drawn, " << rewires() << " rewires, " << seconds_ * 1e3 << " ms in solve(), kernel launches: " << ctx_.launches() << "\n";
+    }
+    const Scenario& scenario() const { return scenario_; }
+    Context& context() { return ctx_; }
+};
+
 // ------------------------------------------------------------------ device-resident PPRM
 // Planner<Scenario, PPRM<device_resident, ...>>: the roadmap, its components and every stage of PPRM's addSample
 // (impl/pprm/pprm.hpp:298-339) stay on the GPU (mptg_pprm_*); two words come back per wave.  solution() runs the
@@ -1181,7 +1322,11 @@ struct PlannerResolver<Scenario, PRRTStar<Options...>> {
     static constexpr bool rNearest = pack_contains_v<rewire_r_nearest, Options...>;
     static_assert(!(kNearest && rNearest), "RRT* tags cannot include both k_nearest and r_nearest");
     using Rewire = std::conditional_t<!rNearest, rewire_k_nearest, rewire_r_nearest>;
-    using type = WavePRRTStar<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, Rewire, pack_bool_tag_v<report_stats, false, Options...>>;
+    static_assert(!(pack_contains_v<device_resident, Options...> && rNearest), "the device-resident PRRT* implements k-nearest rewiring");
+    using type = std::conditional_t<pack_contains_v<device_resident, Options...>,
+                                    DevicePRRTStar<Scenario, pack_int_tag_v<wave_size, 16384, Options...>, pack_int_tag_v<max_nodes, 1 << 21, Options...>,
+                                                   pack_bool_tag_v<report_stats, false, Options...>>,
+                                    WavePRRTStar<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, Rewire, pack_bool_tag_v<report_stats, false, Options...>>>;
 };
 template <typename Scenario, typename... Options>
 struct PlannerResolver<Scenario, PPRM<Options...>> {

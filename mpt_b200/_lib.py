@@ -104,6 +104,14 @@ SYMBOLS = {
     "mptg_prrt_size": (_U32, [_P]),
     "mptg_prrt_samples_drawn": (C.c_uint64, [_P]),
     "mptg_prrt_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P]),
+    "mptg_prrtstar_create": (C.c_int, [_P, _P, _P, C.c_double, C.POINTER(_P)]),
+    "mptg_prrtstar_destroy": (C.c_int, [_P]),
+    "mptg_prrtstar_add_start": (C.c_int, [_P, _P]),
+    "mptg_prrtstar_wave": (C.c_int, [_P, _U32, _U32P, _U32P]),
+    "mptg_prrtstar_size": (_U32, [_P]),
+    "mptg_prrtstar_samples_drawn": (C.c_uint64, [_P]),
+    "mptg_prrtstar_rewires": (C.c_uint64, [_P]),
+    "mptg_prrtstar_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P, _P]),
     "mptg_pprm_create": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
     "mptg_pprm_destroy": (C.c_int, [_P]),
     "mptg_pprm_add_state": (C.c_int, [_P, _P, _U32, _U32P]),

@@ -306,6 +306,61 @@ class DevicePRRT:
             pass
 
 
+class DevicePRRTStar(DevicePRRT):
+    """Device-resident PRRT* (mptg_prrtstar_*): Planner<Scenario, PRRTStar> with tree, costs and rewiring on the GPU."""
+
+    def __init__(self, scenario: "Scenario", space: Space, lo, hi, *, range: float = float("inf"), goal=None, goal_radius: float = 0.0,
+                 goal_bias: float = 0.01, rewire_factor: float = 1.1, seed: int = 1, capacity: int = 1 << 20, max_wave: int = 1 << 14):
+        self.ctx, self.scenario, self.space = scenario.ctx, scenario, space
+        self._lo, self._hi = _bounds(space, lo, hi)
+        self._goal = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
+        prm = L.PrrtParams(C.pointer(space.desc), self._lo.ctypes.data, self._hi.ctypes.data, min(float(range), 1.7e308), float(goal_bias),
+                           None if self._goal is None else self._goal.ctypes.data, float(goal_radius), float(scenario.step or 0.0),
+                           int(seed), int(capacity), int(max_wave))
+        self.h = C.c_void_p()
+        L.check(self.ctx.lib.mptg_prrtstar_create(self.ctx.h, scenario.h, C.byref(prm), float(rewire_factor), C.byref(self.h)), self.ctx.h)
+        self.goal_node = L.NO_INDEX
+
+    def add_start(self, state):
+        s = np.ascontiguousarray(state, dtype=self.space.dtype).reshape(self.space.scalars)
+        L.check(self.ctx.lib.mptg_prrtstar_add_start(self.h, _ptr(s)), self.ctx.h)
+
+    def wave(self, n_samples: int) -> int:
+        size, goal = C.c_uint32(), C.c_uint32()
+        L.check(self.ctx.lib.mptg_prrtstar_wave(self.h, n_samples, C.byref(size), C.byref(goal)), self.ctx.h)
+        self.goal_node = goal.value
+        return size.value
+
+    @property
+    def size(self) -> int:
+        return self.ctx.lib.mptg_prrtstar_size(self.h)
+
+    @property
+    def samples_drawn(self) -> int:
+        return self.ctx.lib.mptg_prrtstar_samples_drawn(self.h)
+
+    @property
+    def rewires(self) -> int:
+        return self.ctx.lib.mptg_prrtstar_rewires(self.h)
+
+    def tree(self, first: int = 0, count: int | None = None, with_costs: bool = False):
+        """-> (states [n, D], parents [n] uint32[, costs [n]]); the goal node of smallest cost is `goal_node`"""
+        count = self.size - first if count is None else count
+        st = np.empty((count, self.space.scalars), dtype=self.space.dtype)
+        pa = np.empty(count, dtype=np.uint32)
+        co = np.empty(count, dtype=self.space.dtype)
+        L.check(self.ctx.lib.mptg_prrtstar_get_tree(self.h, first, count, _ptr(st), _ptr(pa), _ptr(co)), self.ctx.h)
+        return (st, pa, co) if with_costs else (st, pa)
+
+    def solution_cost(self) -> float:
+        return float("nan") if not self.solved() else float(self.tree(self.goal_node, 1, with_costs=True)[2][0])
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mptg_prrtstar_destroy(self.h)
+        self.h = None
+
+
 class DevicePPRM:
     """Device-resident PPRM (mptg_pprm_*): Planner<Scenario, PPRM> with the roadmap kept on the GPU."""
 

@@ -856,3 +856,526 @@ int mptg_pprm_get_graph(mptg_pprm* p, uint32_t first, uint32_t count, void* stat
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// device-resident PRRT* (src/mpt/impl/prrt_star/prrt_star.hpp:510-657), wave-parallel
+// ---------------------------------------------------------------------------------------------
+// One wave = n_samples iterations of Worker::addSample run as a batch against the tree as it stood when the wave
+// began (samples of one wave do not see each other, like the reference's concurrent workers):
+//   sample -> nearest -> d == 0 drops -> steer to `range`, distance recomputed (:526-537) -> valid -> link(near, new)
+//   -> k nearest, k = ceil(kRRG ln(n+1)) (rrg_rewire_neighbors.hpp:53-67) -> neighbours ranked by cost + distance,
+//   tested in that order up to the near node or the cost cut-off, first valid one becomes the parent (:565-605)
+//   -> append (:607-622) -> rewire: every unchecked neighbour whose cost would drop is tested (:626-656).
+// Rewiring inside a wave is evaluated against the costs at the start of the wave's rewiring step: each old node takes
+// the best valid offer (smallest new cost, then smallest (sample, neighbour slot)); all offers are applied at once.
+// This cannot close a cycle: afterwards every node's parent has a strictly smaller pre-rewire cost than the node
+// itself.  The cost decrease of a re-parented node is then pushed to its whole subtree (nonConcurrentPushUpdate,
+// :664-688) by one pass in which every node walks its new ancestor chain and subtracts the decreases it meets,
+// nearest ancestor first.
+namespace mptg {
+
+template <typename S>
+__global__ void starSteerKernel(DevSpace<S> sp, const S* __restrict__ nodes, const S* __restrict__ samples, const uint32_t* __restrict__ nearIdx,
+                                const S* __restrict__ nearDist, const uint32_t* __restrict__ nearCnt, uint32_t n, S range, S* __restrict__ from,
+                                S* __restrict__ to, S* __restrict__ dNew, uint8_t* __restrict__ alive) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int D = sp.D;
+    const S* ps = samples + (size_t)i * D;
+    S* pf = from + (size_t)i * D;
+    S* pt = to + (size_t)i * D;
+    const S d = nearDist[i];
+    const bool live = nearCnt[i] != 0 && !(d == S(0));
+    alive[i] = live ? 1 : 0;
+    dNew[i] = d;
+    if (!live) {
+        for (int c = 0; c < D; ++c) pf[c] = pt[c] = ps[c];
+        return;
+    }
+    const S* pn = nodes + (size_t)nearIdx[i] * D;
+    S a[MPTG_MAX_SCALARS];
+    for (int c = 0; c < D; ++c) a[c] = pf[c] = pn[c];
+    if (d > range) {
+        S b[MPTG_MAX_SCALARS], q[MPTG_MAX_SCALARS];
+        for (int c = 0; c < D; ++c) b[c] = ps[c];
+        dev::interpolate<S>(sp, a, b, fp::div_(range, d), q);
+        for (int c = 0; c < D; ++c) pt[c] = q[c];
+        dNew[i] = dev::distance<S>(sp, [&](int c) { return a[c]; }, [&](int c) { return q[c]; });  // :535
+    } else {
+        for (int c = 0; c < D; ++c) pt[c] = ps[c];
+    }
+}
+
+template <typename S>
+__global__ void starGatherKernel(const uint32_t* __restrict__ sel, uint32_t n, int D, const S* __restrict__ to, const uint32_t* __restrict__ nearIdx,
+                                 const S* __restrict__ dNew, S* __restrict__ fresh, uint32_t* __restrict__ nearOf, S* __restrict__ dOf) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = sel[s];
+    for (int c = 0; c < D; ++c) fresh[(size_t)s * D + c] = to[(size_t)i * D + c];
+    nearOf[s] = nearIdx[i];
+    dOf[s] = dNew[i];
+}
+
+// one warp per survivor: rank the neighbours by cost + distance (stable), mark the ones the reference's loop could
+// test before it stops (cost cut-off or the near node), :565-605
+template <typename S>
+__global__ void __launch_bounds__(128) starRankKernel(uint32_t nS, uint32_t k, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+                                                      const uint32_t* __restrict__ nnCnt, const uint32_t* __restrict__ nearOf,
+                                                      const S* __restrict__ dOf, const S* __restrict__ cost, uint8_t* __restrict__ order,
+                                                      uint8_t* __restrict__ candFlag, uint8_t* __restrict__ checked, uint32_t* __restrict__ limit,
+                                                      uint32_t* __restrict__ nearRank, S* __restrict__ defCost) {
+    __shared__ S sc[4][MPTG_MAX_K];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * 4 + warp;
+    if (s >= nS) return;
+    const uint32_t cnt = nnCnt[s], near = nearOf[s];
+    const S parentCost = cost[near] + dOf[s];
+    for (uint32_t j = lane; j < cnt; j += 32) sc[warp][j] = cost[nnIdx[(size_t)s * k + j]] + nnDist[(size_t)s * k + j];
+    __syncwarp();
+    uint32_t cutLocal = 0, nearRankLocal = 0xFFFFFFFFu;
+    uint32_t myRank[MPTG_MAX_K / 32];
+#pragma unroll
+    for (int r = 0; r < MPTG_MAX_K / 32; ++r) {
+        const uint32_t j = (uint32_t)r * 32 + lane;
+        myRank[r] = 0xFFFFFFFFu;
+        if (j < cnt) {
+            const S c = sc[warp][j];
+            uint32_t rank = 0;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const S o = sc[warp][i];
+                rank += (o < c || (o == c && i < j)) ? 1u : 0u;
+            }
+            myRank[r] = rank;
+            order[(size_t)s * k + rank] = (uint8_t)j;
+            if (!(c > parentCost)) ++cutLocal;
+            if (nnIdx[(size_t)s * k + j] == near) nearRankLocal = rank;
+        }
+    }
+    uint32_t rCut = cutLocal, rNear = nearRankLocal;
+    for (int o = 16; o > 0; o >>= 1) {
+        rCut += __shfl_xor_sync(0xffffffffu, rCut, o);
+        rNear = min(rNear, __shfl_xor_sync(0xffffffffu, rNear, o));
+    }
+    // costs are sorted by rank, so "newCost > parentCost" holds exactly for ranks >= rCut
+    const uint32_t lim = min(rCut, rNear);
+    const bool nearReached = rNear < rCut;
+#pragma unroll
+    for (int r = 0; r < MPTG_MAX_K / 32; ++r) {
+        const uint32_t j = (uint32_t)r * 32 + lane;
+        if (j < k) {
+            const bool test = j < cnt && myRank[r] < lim;
+            candFlag[(size_t)s * k + j] = test ? 1 : 0;
+            checked[(size_t)s * k + j] = 0;  // set by starAppendKernel: the loop marks what it visited before it stopped
+        }
+    }
+    if (lane == 0) {
+        limit[s] = lim;
+        nearRank[s] = nearReached ? rNear : 0xFFFFFFFFu;
+        S dc = parentCost;
+        if (nearReached) dc = sc[warp][order[(size_t)s * k + rNear]];  // parent stays the near node, cost from the neighbour list (:588-592)
+        defCost[s] = dc;
+    }
+}
+
+// edges for the flagged (survivor, slot) pairs; fromNode: neighbour -> new state (parent candidates) or new state -> neighbour (rewiring)
+template <typename S>
+__global__ void starEdgeKernel(const uint32_t* __restrict__ ids, uint32_t nE, uint32_t k, int D, bool towardsFresh, const S* __restrict__ fresh,
+                               const S* __restrict__ nodes, const uint32_t* __restrict__ nnIdx, S* __restrict__ from, S* __restrict__ to,
+                               uint32_t* __restrict__ inv) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    const uint32_t id = ids[e], s = id / k;
+    if (inv) inv[id] = e;
+    const S* pf = fresh + (size_t)s * D;
+    const S* pn = nodes + (size_t)nnIdx[id] * D;
+    const S* a = towardsFresh ? pn : pf;
+    const S* b = towardsFresh ? pf : pn;
+    for (int c = 0; c < D; ++c) from[(size_t)e * D + c] = a[c], to[(size_t)e * D + c] = b[c];
+}
+
+// first valid candidate in rank order becomes the parent; append node, parent, cost; goal test (:607-622)
+template <typename S>
+__global__ void starAppendKernel(DevSpace<S> sp, uint32_t nS, uint32_t k, const S* __restrict__ fresh, const uint32_t* __restrict__ nnIdx,
+                                 const S* __restrict__ nnDist, const uint8_t* __restrict__ order, const uint32_t* __restrict__ limit,
+                                 const uint32_t* __restrict__ nearRank, uint8_t* __restrict__ checked, const uint32_t* __restrict__ inv,
+                                 const uint8_t* __restrict__ okCand, const uint32_t* __restrict__ nearOf, const S* __restrict__ defCost, uint32_t size, const S* __restrict__ goal, S goalRadius, S* __restrict__ nodes,
+                                 uint32_t* __restrict__ parent, S* __restrict__ cost, uint32_t* __restrict__ goalList) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nS) return;
+    const int D = sp.D;
+    uint32_t par = nearOf[s];
+    S c = defCost[s];
+    const uint32_t lim = limit[s];
+    bool found = false;
+    for (uint32_t r = 0; r < lim && !found; ++r) {
+        const uint32_t j = order[(size_t)s * k + r];
+        checked[(size_t)s * k + j] = 1;  // :586 "mark as checked"
+        if (okCand[inv[(size_t)s * k + j]]) {
+            par = nnIdx[(size_t)s * k + j];
+            c = cost[par] + nnDist[(size_t)s * k + j];
+            found = true;
+        }
+    }
+    if (!found && nearRank[s] != 0xFFFFFFFFu) checked[(size_t)s * k + order[(size_t)s * k + nearRank[s]]] = 1;  // the loop reached the near node
+    const uint32_t id = size + s;
+    const S* pf = fresh + (size_t)s * D;
+    for (int d = 0; d < D; ++d) nodes[(size_t)id * D + d] = pf[d];
+    parent[id] = par;
+    cost[id] = c;
+    if (goal != nullptr) {
+        const S dg = dev::distance<S>(sp, [&](int d) { return pf[d]; }, [&](int d) { return goal[d]; });
+        if (dg <= goalRadius) {
+            const uint32_t slot = atomicAdd(goalList, 1u);
+            if (slot < 65535u) goalList[1 + slot] = id;
+        }
+    }
+}
+
+// rewiring offers: unchecked neighbours whose cost would drop (:626-637)
+template <typename S>
+__global__ void starRewireFlagKernel(uint32_t nS, uint32_t k, uint32_t size, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+                                     const uint32_t* __restrict__ nnCnt, const uint8_t* __restrict__ checked, const S* __restrict__ cost,
+                                     uint8_t* __restrict__ flag) {
+    const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (size_t)nS * k) return;
+    const uint32_t s = (uint32_t)(id / k), j = (uint32_t)(id % k);
+    bool f = false;
+    if (j < nnCnt[s] && !checked[id]) f = cost[size + s] + nnDist[id] < cost[nnIdx[id]];
+    flag[id] = f ? 1 : 0;
+}
+
+__device__ __forceinline__ unsigned long long starCostKey(double c) {  // costs are non-negative: the bit pattern orders them
+    return (unsigned long long)__double_as_longlong(c + 0.0);
+}
+template <typename S>
+__global__ void starRewireMinKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+                                    const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
+                                    unsigned long long* __restrict__ bestKey) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nR || !ok[e]) return;
+    const uint32_t id = ids[e];
+    atomicMin(bestKey + nnIdx[id], starCostKey((double)(cost[size + id / k] + nnDist[id])));
+}
+template <typename S>
+__global__ void starRewirePickKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+                                     const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
+                                     const unsigned long long* __restrict__ bestKey, uint32_t* __restrict__ bestCand) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nR || !ok[e]) return;
+    const uint32_t id = ids[e], nb = nnIdx[id];
+    if (starCostKey((double)(cost[size + id / k] + nnDist[id])) == bestKey[nb]) atomicMin(bestCand + nb, e);
+}
+template <typename S>
+__global__ void starRewireApplyKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+                                      const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
+                                      const uint32_t* __restrict__ bestCand, uint32_t* __restrict__ parent, S* __restrict__ delta,
+                                      uint32_t* __restrict__ counters) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nR || !ok[e]) return;
+    const uint32_t id = ids[e], nb = nnIdx[id];
+    if (bestCand[nb] != e) return;
+    const uint32_t from = size + id / k;
+    parent[nb] = from;
+    delta[nb] = cost[nb] - (cost[from] + nnDist[id]);  // :647 (cost[] itself is updated by the push pass below)
+    atomicAdd(counters, 1u);
+}
+// nonConcurrentPushUpdate (:664-688) for all re-parented nodes at once
+template <typename S>
+__global__ void starPushKernel(uint32_t n, const uint32_t* __restrict__ parent, const S* __restrict__ delta, S* __restrict__ cost) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    S c = cost[i];
+    bool changed = false;
+    uint32_t steps = 0;  // a path has fewer than n nodes; the bound keeps a corrupted tree from hanging the device
+    for (uint32_t a = i; a != MPTG_NO_INDEX && steps < n; a = parent[a], ++steps) {
+        const S d = delta[a];
+        if (d > S(0)) c = c - d, changed = true;
+    }
+    if (changed) cost[i] = c;
+}
+// best goal node: smallest cost, then smallest index
+template <typename S>
+__global__ void starGoalKernel(const uint32_t* __restrict__ goalList, const S* __restrict__ cost, uint32_t* __restrict__ result) {
+    __shared__ unsigned long long best;
+    if (threadIdx.x == 0) best = ~0ull;
+    __syncthreads();
+    const uint32_t n = min(goalList[0], 65535u);
+    unsigned long long mine = ~0ull;
+    uint32_t mineIdx = MPTG_NO_INDEX;
+    for (uint32_t g = threadIdx.x; g < n; g += blockDim.x) {
+        const uint32_t id = goalList[1 + g];
+        const unsigned long long key = starCostKey((double)cost[id]);
+        if (key < mine || (key == mine && id < mineIdx)) mine = key, mineIdx = id;
+    }
+    atomicMin(&best, mine);
+    __syncthreads();
+    if (mineIdx != MPTG_NO_INDEX && mine == best) atomicMin(result, mineIdx);
+}
+
+}  // namespace mptg
+
+struct mptg_prrtstar {
+    mptg_ctx* ctx = nullptr;
+    mptg_geom* geom = nullptr;
+    mptg_knn* knn = nullptr;  // owned
+    mptg_space_desc space{};
+    int D = 0, scalar = MPTG_F32, dims = 0;
+    double range = 0, goalBias = 0, goalRadius = 0, linkStep = 0, rewireFactor = 1.1;
+    bool hasGoal = false;
+    uint64_t seed = 0, drawn = 0, waves = 0, rewires = 0;
+    uint32_t capacity = 0, size = 0, maxWave = 0, stride = 0, goalNode = MPTG_NO_INDEX;
+    // tree
+    void *bounds = nullptr, *goal = nullptr, *nodes = nullptr, *cost = nullptr, *delta = nullptr;
+    uint32_t *parent = nullptr, *bestCand = nullptr, *goalList = nullptr;
+    unsigned long long* bestKey = nullptr;
+    // wave
+    void *samples = nullptr, *from = nullptr, *to = nullptr, *fresh = nullptr, *nearDist = nullptr, *dNew = nullptr, *dOf = nullptr, *defCost = nullptr;
+    void *nnDist = nullptr, *eFrom = nullptr, *eTo = nullptr;
+    uint32_t *nearIdx = nullptr, *nearCnt = nullptr, *sel = nullptr, *nSel = nullptr, *nearOf = nullptr, *nnIdx = nullptr, *nnCnt = nullptr,
+             *limit = nullptr, *nearRank = nullptr, *ids = nullptr, *inv = nullptr, *result = nullptr;
+    uint8_t *alive = nullptr, *okValid = nullptr, *okLink = nullptr, *keep = nullptr, *order = nullptr, *flag = nullptr, *checked = nullptr, *okEdge = nullptr;
+    void* selTemp = nullptr;
+    size_t selBytes = 0;
+    uint32_t* host = nullptr;  // pinned: [0] select count, [1] best goal node, [2] rewires applied
+};
+
+namespace {
+
+void starFree(mptg_prrtstar* p) {
+    if (!p) return;
+    if (p->knn) mptg_knn_destroy(p->knn);
+    for (void* q : {p->bounds, p->goal, p->nodes, p->cost, p->delta, (void*)p->parent, (void*)p->bestCand, (void*)p->goalList, (void*)p->bestKey,
+                    p->samples, p->from, p->to, p->fresh, p->nearDist, p->dNew, p->dOf, p->defCost, p->nnDist, p->eFrom, p->eTo, (void*)p->nearIdx,
+                    (void*)p->nearCnt, (void*)p->sel, (void*)p->nSel, (void*)p->nearOf, (void*)p->nnIdx, (void*)p->nnCnt, (void*)p->limit, (void*)p->nearRank,
+                    (void*)p->ids, (void*)p->inv, (void*)p->result, (void*)p->alive, (void*)p->okValid, (void*)p->okLink, (void*)p->keep,
+                    (void*)p->order, (void*)p->flag, (void*)p->checked, (void*)p->okEdge, p->selTemp})
+        cudaFree(q);
+    if (p->host) cudaFreeHost(p->host);
+    delete p;
+}
+
+// k = ceil(kRRG ln(n + 1)), kRRG = rewireFactor e (1 + 1/d) (rrg_rewire_neighbors.hpp:53-61), in the space's scalar type
+template <typename S>
+uint32_t starK(double rewireFactor, int dims, uint32_t n) {
+    const S e = (S)2.718281828459045235360287471352662498L;
+    const S kRRG = (S)rewireFactor * e * (S(1) + S(1) / (S)dims);
+    const int k = (int)std::ceil(kRRG * std::log((S)(n + 1.0)));
+    return (uint32_t)(k < 1 ? 1 : k);
+}
+
+int starSelect(mptg_prrtstar* p, const uint8_t* flags, size_t n, uint32_t* out, uint32_t* countHost) {
+    mptg_ctx* ctx = p->ctx;
+    size_t bytes = p->selBytes;
+    MPTG_CUDA(ctx, cub::DeviceSelect::Flagged(p->selTemp, bytes, thrust::counting_iterator<uint32_t>(0), flags, out, p->nSel, (int)n, ctx->stream));
+    MPTG_LAUNCHED(ctx);
+    MPTG_CUDA(ctx, cudaMemcpyAsync(p->host, p->nSel, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *countHost = p->host[0];
+    return MPTG_OK;
+}
+
+template <typename S>
+int starWaveT(mptg_prrtstar* p, uint32_t W) {
+    mptg_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const DevSpace<S> sp = makeDevSpace<S>(p->space);
+    const int D = p->D;
+    const uint32_t grid = (W + 127) / 128;
+    const bool biased = p->hasGoal && p->goalBias > 0 && p->goalNode == MPTG_NO_INDEX;  // :468-481
+    sampleKernel<S><<<grid, 128, 0, st>>>(sp, (const S*)p->bounds, (const S*)p->bounds + D, p->seed, p->drawn, W, biased ? (const S*)p->goal : nullptr,
+                                          (S)p->goalBias, (S*)p->samples);
+    MPTG_LAUNCHED(ctx);
+    p->drawn += W;
+    if (int rc = mptg_knn_query_dev(p->knn, p->samples, W, 1, -1.0, p->nearIdx, p->nearDist, p->nearCnt)) return rc;  // :517
+    starSteerKernel<S><<<grid, 128, 0, st>>>(sp, (const S*)p->nodes, (const S*)p->samples, p->nearIdx, (const S*)p->nearDist, p->nearCnt, W,
+                                             (S)p->range, (S*)p->from, (S*)p->to, (S*)p->dNew, p->alive);
+    MPTG_LAUNCHED(ctx);
+    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid)) return rc;                              // :539
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink)) return rc;  // :545
+    prrtFlagKernel<<<grid, 128, 0, st>>>(p->alive, p->okValid, p->okLink, W, p->keep);
+    MPTG_LAUNCHED(ctx);
+    uint32_t nS = 0;
+    if (int rc = starSelect(p, p->keep, W, p->sel, &nS)) return rc;
+    if (nS > p->capacity - p->size) nS = p->capacity - p->size;
+    ++p->waves;
+    if (nS == 0) return MPTG_OK;
+    starGatherKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(p->sel, nS, D, (const S*)p->to, p->nearIdx, (const S*)p->dNew, (S*)p->fresh, p->nearOf,
+                                                         (S*)p->dOf);
+    MPTG_LAUNCHED(ctx);
+    // neighbourhoods (:559-562)
+    uint32_t k = starK<S>(p->rewireFactor, p->dims, p->size);
+    if (k > p->stride) k = p->stride;
+    if (int rc = mptg_knn_query_dev(p->knn, p->fresh, nS, k, -1.0, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
+    starRankKernel<S><<<(nS + 3) / 4, 128, 0, st>>>(nS, k, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->nearOf, (const S*)p->dOf, (const S*)p->cost,
+                                                   p->order, p->flag, p->checked, p->limit, p->nearRank, (S*)p->defCost);
+    MPTG_LAUNCHED(ctx);
+    // candidate parents, one link batch (:580-605)
+    uint32_t nE = 0;
+    if (int rc = starSelect(p, p->flag, (size_t)nS * k, p->ids, &nE)) return rc;
+    if (nE) {
+        starEdgeKernel<S><<<(nE + 127) / 128, 128, 0, st>>>(p->ids, nE, k, D, true, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
+                                                           (S*)p->eTo, p->inv);
+        MPTG_LAUNCHED(ctx);
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nE, p->linkStep, p->okEdge)) return rc;
+    }
+    starAppendKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(sp, nS, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank,
+                                                         p->checked, p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
+                                                         (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList);
+    MPTG_LAUNCHED(ctx);
+    // rewire (:626-656)
+    const size_t nSK = (size_t)nS * k;
+    starRewireFlagKernel<S><<<(unsigned)((nSK + 127) / 128), 128, 0, st>>>(nS, k, p->size, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->checked,
+                                                                          (const S*)p->cost, p->flag);
+    MPTG_LAUNCHED(ctx);
+    uint32_t nR = 0;
+    if (int rc = starSelect(p, p->flag, nSK, p->ids, &nR)) return rc;
+    const uint32_t total = p->size + nS;
+    if (nR) {
+        starEdgeKernel<S><<<(nR + 127) / 128, 128, 0, st>>>(p->ids, nR, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
+                                                           (S*)p->eTo, nullptr);
+        MPTG_LAUNCHED(ctx);
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nR, p->linkStep, p->okEdge)) return rc;
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->bestKey, 0xFF, (size_t)p->size * 8, st));
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->bestCand, 0xFF, (size_t)p->size * 4, st));
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->delta, 0, (size_t)total * sizeof(S), st));
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
+        const uint32_t gr = (nR + 127) / 128;
+        starRewireMinKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey);
+        MPTG_LAUNCHED(ctx);
+        starRewirePickKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey,
+                                                    p->bestCand);
+        MPTG_LAUNCHED(ctx);
+        starRewireApplyKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestCand,
+                                                     p->parent, (S*)p->delta, p->result + 1);
+        MPTG_LAUNCHED(ctx);
+        starPushKernel<S><<<(total + 127) / 128, 128, 0, st>>>(total, p->parent, (const S*)p->delta, (S*)p->cost);
+        MPTG_LAUNCHED(ctx);
+    } else {
+        MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
+    }
+    MPTG_CUDA(ctx, cudaMemsetAsync(p->result, 0xFF, 4, st));
+    if (p->hasGoal) {
+        starGoalKernel<S><<<1, 256, 0, st>>>(p->goalList, (const S*)p->cost, p->result);
+        MPTG_LAUNCHED(ctx);
+    }
+    MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 1, p->result, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t first = 0;
+    if (int rc = mptg_knn_insert_dev(p->knn, p->fresh, nS, &first)) return rc;  // :619
+    if (first != p->size) return fail(ctx, MPTG_ERR_CUDA, "mptg_prrtstar_wave: node numbering out of step");
+    MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    p->goalNode = p->host[1];
+    p->rewires += p->host[2];
+    p->size += nS;
+    return MPTG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params* prm, double rewire_factor, mptg_prrtstar** out) {
+    if (!ctx || !geom || !prm || !out || !spaceOk(prm->space) || prm->capacity == 0 || prm->max_wave == 0 || !(prm->range > 0) || !(rewire_factor > 0))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_prrtstar_create: bad argument");
+    if (geom->ctx != ctx || geom->scalar != prm->space->scalar || geom->D != spaceScalars(prm->space))
+        return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_prrtstar_create: the geometry's states are not states of this space");
+    if (geom->kind == MPTG_GEOM_MESH && !(prm->link_step > 0)) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_prrtstar_create: mesh geometries need link_step > 0");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto* p = new mptg_prrtstar();
+    p->ctx = ctx, p->geom = geom, p->space = *prm->space;
+    p->D = spaceScalars(prm->space), p->scalar = prm->space->scalar, p->dims = spaceDimensions(*prm->space);
+    p->range = prm->range, p->goalBias = prm->goal_bias, p->goalRadius = prm->goal_radius, p->linkStep = prm->link_step, p->rewireFactor = rewire_factor;
+    p->seed = prm->seed, p->capacity = prm->capacity, p->maxWave = prm->max_wave, p->hasGoal = prm->goal_state != nullptr;
+    const uint32_t kFull = p->scalar == MPTG_F32 ? starK<float>(rewire_factor, p->dims, p->capacity) : starK<double>(rewire_factor, p->dims, p->capacity);
+    p->stride = kFull < MPTG_MAX_K ? kFull : MPTG_MAX_K;
+    const size_t sb = (size_t)p->D * p->scalar, W = p->maxWave, K = p->stride, sc = p->scalar;
+    int rc = mptg_knn_create(ctx, prm->space, p->capacity, &p->knn);
+    if (!rc) rc = uploadBounds(ctx, prm->space, prm->lo, prm->hi, &p->bounds);
+    auto alloc = [&](auto** q, size_t bytes) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc((void**)q, bytes ? bytes : 16);
+        if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_prrtstar_create: %s", cudaGetErrorString(e));
+    };
+    alloc(&p->nodes, (size_t)p->capacity * sb), alloc(&p->parent, (size_t)p->capacity * 4), alloc(&p->cost, (size_t)p->capacity * sc);
+    alloc(&p->delta, (size_t)p->capacity * sc), alloc(&p->bestKey, (size_t)p->capacity * 8), alloc(&p->bestCand, (size_t)p->capacity * 4);
+    alloc(&p->goalList, 65536 * 4);
+    alloc(&p->samples, W * sb), alloc(&p->from, W * sb), alloc(&p->to, W * sb), alloc(&p->fresh, W * sb);
+    alloc(&p->nearDist, W * sc), alloc(&p->dNew, W * sc), alloc(&p->dOf, W * sc), alloc(&p->defCost, W * sc);
+    alloc(&p->nearIdx, W * 4), alloc(&p->nearCnt, W * 4), alloc(&p->sel, W * 4), alloc(&p->nearOf, W * 4), alloc(&p->limit, W * 4), alloc(&p->nearRank, W * 4);
+    alloc(&p->nSel, 4), alloc(&p->result, 8);
+    alloc(&p->alive, W), alloc(&p->okValid, W), alloc(&p->okLink, W), alloc(&p->keep, W);
+    alloc(&p->nnIdx, W * K * 4), alloc(&p->nnDist, W * K * sc), alloc(&p->nnCnt, W * 4);
+    alloc(&p->order, W * K), alloc(&p->flag, W * K), alloc(&p->checked, W * K), alloc(&p->okEdge, W * K);
+    alloc(&p->ids, W * K * 4), alloc(&p->inv, W * K * 4), alloc(&p->eFrom, W * K * sb), alloc(&p->eTo, W * K * sb);
+    if (!rc) {
+        cub::DeviceSelect::Flagged(nullptr, p->selBytes, thrust::counting_iterator<uint32_t>(0), p->flag, p->ids, p->nSel, (int)(W * K));
+        alloc(&p->selTemp, p->selBytes);
+    }
+    if (!rc && p->hasGoal) {
+        alloc(&p->goal, sb);
+        if (!rc) rc = uploadSync(ctx, p->goal, prm->goal_state, sb);
+    }
+    if (!rc) rc = memsetSync(ctx, p->goalList, 0, 65536 * 4);
+    if (!rc && cudaMallocHost((void**)&p->host, 4 * sizeof(uint32_t)) != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_prrtstar_create: pinned allocation failed");
+    if (rc) {
+        starFree(p);
+        return rc;
+    }
+    *out = p;
+    return MPTG_OK;
+}
+
+int mptg_prrtstar_destroy(mptg_prrtstar* p) {
+    if (!p) return MPTG_OK;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    starFree(p);
+    return MPTG_OK;
+}
+
+int mptg_prrtstar_add_start(mptg_prrtstar* p, const void* state) {
+    if (!p || !state) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_prrtstar_add_start: bad argument");
+    if (p->size >= p->capacity) return fail(p->ctx, MPTG_ERR_CAPACITY, "mptg_prrtstar_add_start: tree is full");
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)p->D * p->scalar;
+    const uint32_t none = MPTG_NO_INDEX;
+    const double zero = 0.0;  // all-zero bits in either scalar type
+    if (int rc = uploadSync(ctx, (char*)p->nodes + (size_t)p->size * sb, state, sb)) return rc;
+    if (int rc = uploadSync(ctx, p->parent + p->size, &none, sizeof none)) return rc;
+    if (int rc = uploadSync(ctx, (char*)p->cost + (size_t)p->size * p->scalar, &zero, p->scalar)) return rc;
+    uint32_t first = 0;
+    if (int rc = mptg_knn_insert(p->knn, state, 1, &first)) return rc;
+    ++p->size;
+    return MPTG_OK;
+}
+
+int mptg_prrtstar_wave(mptg_prrtstar* p, uint32_t n_samples, uint32_t* size_out, uint32_t* goal_node_out) {
+    if (!p || n_samples == 0 || n_samples > p->maxWave) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_prrtstar_wave: bad argument");
+    if (p->size == 0) return fail(p->ctx, MPTG_ERR_BAD_ARG, "mptg_prrtstar_wave: there are no valid initial states");
+    MPTG_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    const int rc = p->scalar == MPTG_F32 ? starWaveT<float>(p, n_samples) : starWaveT<double>(p, n_samples);
+    if (size_out) *size_out = p->size;
+    if (goal_node_out) *goal_node_out = p->goalNode;
+    return rc;
+}
+
+uint32_t mptg_prrtstar_size(const mptg_prrtstar* p) { return p ? p->size : 0; }
+uint64_t mptg_prrtstar_samples_drawn(const mptg_prrtstar* p) { return p ? p->drawn : 0; }
+uint64_t mptg_prrtstar_rewires(const mptg_prrtstar* p) { return p ? p->rewires : 0; }
+
+int mptg_prrtstar_get_tree(mptg_prrtstar* p, uint32_t first, uint32_t count, void* states_out, uint32_t* parents_out, void* costs_out) {
+    if (!p || (uint64_t)first + count > p->size) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_prrtstar_get_tree: bad range");
+    if (count == 0) return MPTG_OK;
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t sb = (size_t)p->D * p->scalar;
+    if (states_out) MPTG_CUDA(ctx, cudaMemcpyAsync(states_out, (char*)p->nodes + first * sb, count * sb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (parents_out) MPTG_CUDA(ctx, cudaMemcpyAsync(parents_out, p->parent + first, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (costs_out)
+        MPTG_CUDA(ctx, cudaMemcpyAsync(costs_out, (char*)p->cost + (size_t)first * p->scalar, (size_t)count * p->scalar, cudaMemcpyDeviceToHost, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
+}  // extern "C"

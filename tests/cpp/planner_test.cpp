@@ -116,6 +116,27 @@ int main() {
     static_assert(!std::is_same_v<Planner<S, PRRT<device_resident>>, Planner<S, PRRT<>>>);
     static_assert(std::is_same_v<Planner<S, PRRT<device_resident, wave_size<4096>>>, Planner<S, PRRT<wave_size<4096>, device_resident>>>);
     testSolvingBasicScenario<PRRT<device_resident, report_stats<true>, wave_size<4096>, max_nodes<(1 << 18)>>>("PRRT device-resident");
+    static_assert(!std::is_same_v<Planner<S, PRRTStar<device_resident>>, Planner<S, PRRTStar<>>>);
+    testSolvingBasicScenario<PRRTStar<device_resident, report_stats<true>, wave_size<2048>, max_nodes<(1 << 17)>>>("PRRT* device-resident");
+    {   // cost(node) == cost(parent) + distance(parent, node) up to rounding after wave-parallel rewiring; rewiring happened
+        using Scenario = test::BasicScenario<double, 3>;
+        Planner<Scenario, PRRTStar<device_resident, wave_size<1024>, max_nodes<(1 << 16)>>> planner(Scenario(), 99);
+        planner.addStart(Scenario::startState());
+        planner.setRange(0.5);
+        planner.solve([&] { return planner.size() > 20000; });
+        Scenario sc;
+        double worst = 0;
+        for (std::uint32_t n = 1; n < planner.size(); ++n) {
+            const std::uint32_t p = planner.nodeParent(n);
+            EXPECT(p < planner.size());
+            if (p >= planner.size()) break;
+            worst = std::max(worst, std::abs(planner.nodeCost(p) + sc.space().distance(planner.nodeState(p), planner.nodeState(n)) - planner.nodeCost(n)));
+        }
+        EXPECT(worst < 1e-9);
+        EXPECT(planner.rewires() > 0);
+        std::printf("%s PRRT* device-resident invariants: %zu nodes, %llu rewires, worst cost residual %.3g, solution cost %.6f\n",
+                    failures ? "FAIL" : "PASS", planner.size(), (unsigned long long)planner.rewires(), worst, planner.solved() ? (double)planner.solutionCost() : -1.0);
+    }
     static_assert(!std::is_same_v<Planner<S, PPRM<device_resident>>, Planner<S, PPRM<>>>);
     testSolvingBasicScenario<PPRM<device_resident, report_stats<true>, wave_size<512>, max_nodes<(1 << 16)>>>("PPRM device-resident");
 #endif

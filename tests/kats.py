@@ -209,3 +209,104 @@ def components(edge_idx):
         if a != b:
             comp[max(a, b)] = min(a, b)
     return np.array([find(i) for i in range(n)])
+
+
+def prrtstar_k(space, rewire_factor, n):
+    """k = ceil(kRRG ln(n + 1)), kRRG = rewireFactor e (1 + 1/d) (src/mpt/impl/rrg_rewire_neighbors.hpp:53-61)."""
+    dt = space.dtype
+    k_rrg = dt(rewire_factor) * dt(math.e) * (dt(1) + dt(1) / dt(space.dimensions))
+    return max(1, int(np.ceil(k_rrg * np.log(dt(n + 1.0)))))
+
+
+def replay_prrtstar(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, rewire_factor, seed, waves, W, stride):
+    """The wave-parallel PRRT* of include/mptg/mptg.h (mptg_prrtstar_*) restated on the oracle: Worker::addSample of
+    src/mpt/impl/prrt_star/prrt_star.hpp:510-657 per sample against the tree at the start of the wave; rewiring offers
+    evaluated on the costs before the wave's rewiring step, best valid offer per node, applied at once, decreases
+    pushed down the new ancestor chains.  -> (states, parents, costs, best goal node, rewires applied)"""
+    dt = sp.dtype
+    D = sp.scalars
+    states = np.asarray(start, dtype=dt).reshape(1, D)
+    parent = [NO_INDEX]
+    cost = [dt(0)]
+    goals, best_goal, drawn, rewires = [], NO_INDEX, 0, 0
+    for _ in range(waves):
+        tree = states
+        biased = goal is not None and goal_bias > 0 and best_goal == NO_INDEX
+        smp = oracle.sample(sp, lo, hi, seed, drawn, W, goal if biased else None, goal_bias)
+        drawn += W
+        idx, dist, cnt = oracle.knn(sp, tree, smp, 1)
+        near, d = tree[idx[:, 0]], dist[:, 0]
+        to, dre = oracle.steer(sp, near, smp, d, rng, with_distance=True)
+        dnew = np.where(d > dt(rng), dre, d)
+        keep = (cnt > 0) & (d != 0) & (og.valid(to) != 0) & (og.link(near, to) != 0)
+        fresh, near_of, d_of = to[keep], idx[keep, 0], dnew[keep]
+        S = fresh.shape[0]
+        if S == 0:
+            continue
+        n0 = tree.shape[0]
+        k = min(prrtstar_k(sp, rewire_factor, n0), stride)
+        nidx, ndist, ncnt = oracle.knn(sp, tree, fresh, k)
+        c0 = np.asarray(cost, dtype=dt)
+        # candidate parents in cost + distance order up to the near node or the cut-off, one link batch
+        orders, cands = [], []
+        for s in range(S):
+            c = c0[nidx[s, :ncnt[s]]] + ndist[s, :ncnt[s]]
+            order = np.argsort(c, kind="stable")
+            orders.append((order, c))
+            parent_cost = c0[near_of[s]] + d_of[s]
+            for j in order:
+                if c[j] > parent_cost or nidx[s, j] == near_of[s]:
+                    break
+                cands.append((s, int(j)))
+        ok = og.link(tree[[nidx[s, j] for s, j in cands]], fresh[[s for s, _ in cands]]) if cands else np.zeros(0, np.uint8)
+        ok_of = {c: bool(o) for c, o in zip(cands, ok)}
+        checked = np.zeros((S, k), dtype=bool)
+        for s in range(S):
+            order, c = orders[s]
+            par, pc = int(near_of[s]), c0[near_of[s]] + d_of[s]
+            parent_cost = pc
+            for j in order:
+                if c[j] > parent_cost:
+                    break
+                checked[s, j] = True
+                if nidx[s, j] == near_of[s]:
+                    pc = c[j]
+                    break
+                if ok_of[(s, int(j))]:
+                    par, pc = int(nidx[s, j]), c[j]
+                    break
+            parent.append(par)
+            cost.append(dt(pc))
+            if goal is not None and oracle.distance(sp, fresh[s:s + 1], np.asarray(goal, dtype=dt).reshape(1, D))[0] <= dt(goal_radius):
+                goals.append(n0 + s)
+        states = np.concatenate([states, fresh])
+        # rewiring offers on the costs as they are now
+        c1 = np.asarray(cost, dtype=dt)
+        offers = [(s, j) for s in range(S) for j in range(int(ncnt[s])) if not checked[s, j] and c1[n0 + s] + ndist[s, j] < c1[nidx[s, j]]]
+        if offers:
+            okr = og.link(fresh[[s for s, _ in offers]], tree[[nidx[s, j] for s, j in offers]])
+            best = {}
+            for e, ((s, j), o) in enumerate(zip(offers, okr)):
+                if not o:
+                    continue
+                nb, new_cost = int(nidx[s, j]), c1[n0 + s] + ndist[s, j]
+                key = (float(new_cost), e)
+                if nb not in best or key < best[nb][0]:
+                    best[nb] = (key, n0 + s, new_cost)
+            delta = np.zeros(len(cost), dtype=dt)
+            for nb, (_key, frm, new_cost) in best.items():
+                parent[nb] = frm
+                delta[nb] = c1[nb] - new_cost
+            rewires += len(best)
+            if best:
+                for i in range(len(cost)):
+                    c, a = c1[i], i
+                    while a != NO_INDEX:
+                        if delta[a] > 0:
+                            c = dt(c - delta[a])
+                        a = parent[a]
+                    cost[i] = c
+        if goals:
+            cg = np.asarray(cost, dtype=dt)[goals]
+            best_goal = goals[int(np.lexsort((goals, cg))[0])]
+    return states, np.asarray(parent, dtype=np.uint32), np.asarray(cost, dtype=dt), best_goal, rewires

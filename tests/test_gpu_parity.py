@@ -478,6 +478,48 @@ def test_device_prrt_on_meshes_builds_a_valid_tree(ctx, oracle):
     assert edge.max() <= 30.0 * (1 + 1e-4), f"longest tree edge {edge.max()}"
 
 
+def test_device_prrtstar_replays_its_wave_semantics_on_the_oracle(ctx, oracle):
+    """Device-resident PRRT* (mptg_prrtstar_*) against the same wave-parallel loop restated on the oracle: states
+    bit-identical, same parents, same costs, same best goal node, same number of rewires -- and the tree invariants:
+    parents precede or were re-parented to later nodes without cycles, every edge is a valid motion, cost(node) =
+    cost(parent) + distance up to rounding."""
+    occ = W.synthetic_grid(500, 400, seed=2)
+    sp = m.lp_space(2, 2, m.F64)
+    sc, og = m.Scenario.grid(ctx, occ, m.F64), oracle.grid(occ)
+    free = np.argwhere(occ == 0)
+    start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
+    lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
+    for rng, waves, W_ in ((30.0, 8, 256), (float("inf"), 4, 200), (40.0, 300, 1)):
+        pl = m.DevicePRRTStar(sc, sp, lo, hi, range=rng, goal=goal, goal_radius=12.0, goal_bias=0.05, seed=31, capacity=8192, max_wave=256)
+        pl.add_start(start)
+        for _ in range(waves):
+            pl.wave(W_)
+        st, pa, co = pl.tree(with_costs=True)
+        ws, wp, wc, wg, wr = kats.replay_prrtstar(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 1.1, 31, waves, W_, 128)
+        assert st.shape[0] > 50 and np.array_equal(st, ws), (rng, st.shape, ws.shape)
+        assert np.array_equal(pa, wp), f"{(pa != wp).sum()} parents differ"
+        assert np.array_equal(co, wc), f"{(co != wc).sum()} costs differ, max {np.abs(co - wc).max()}"
+        assert pl.goal_node == wg and pl.rewires == wr and (W_ == 1 or wr > 0)
+        # invariants
+        n = st.shape[0]
+        assert pa[0] == m.NO_INDEX and co[0] == 0 and (pa[1:] < n).all()
+        depth = np.zeros(n, dtype=np.int64)
+        for i in range(1, n):  # no cycles: every node reaches the root
+            a, steps = i, 0
+            while a != 0:
+                a, steps = int(pa[a]), steps + 1
+                assert steps <= n
+            depth[i] = steps
+        edge = oracle.distance(sp, st[pa[1:]], st[1:])
+        assert np.abs(co[pa[1:]] + edge - co[1:]).max() < 1e-9 * max(1.0, co.max())
+        assert og.link(st[pa[1:]], st[1:]).all()
+        if pl.solved():
+            path = pl.solution()
+            assert np.array_equal(path[0], start) and np.linalg.norm(path[-1] - goal) <= 12.0
+            assert abs(np.linalg.norm(np.diff(path, axis=0), axis=1).sum() - pl.solution_cost()) < 1e-6
+        pl.close()
+
+
 def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W):
     pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W)
     assert pl.add_start(start) == 0 and pl.add_goal(goal) == 1
