@@ -520,6 +520,87 @@ def test_device_prrtstar_replays_its_wave_semantics_on_the_oracle(ctx, oracle):
         pl.close()
 
 
+def test_device_prrtstar_and_pprm_on_meshes_se3_f32(ctx, oracle):
+    """SE(3) rigid body among meshes, float32 states (BASELINE configs[2]): the device-resident PRRT* and PPRM build
+    graphs whose every node is valid and every edge a valid motion on the oracle (near-contact items excepted and
+    counted), PRRT* costs are consistent and runs are reproducible."""
+    sp = m.se3_space(50, 1)
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=1200, robot_tris_target=400)
+    step = W.se3_step_size(vmin, vmax)
+    sc, og = m.Scenario.mesh_pair(ctx, robot, env, sp, step), oracle.mesh_pair(robot, env, sp, step)
+    lo, hi = [0, 0, 0, 0, -45, -45, -45], [0, 0, 0, 0, 45, 45, 45]
+    cand = W.se3_states(64, 5, -45.0, 45.0)
+    free = cand[np.nonzero(og.valid(cand))[0]]
+    start, goal = free[0], free[1]
+    runs = []
+    for _ in range(2):
+        pl = m.DevicePRRTStar(sc, sp, lo, hi, range=30.0, goal=goal, goal_radius=8.0, goal_bias=0.05, seed=7, capacity=1 << 14, max_wave=1024)
+        pl.add_start(start)
+        for _ in range(5):
+            pl.wave(1024)
+        runs.append(pl.tree(with_costs=True) + (pl.rewires, pl.goal_node))
+        pl.close()
+    (st, pa, co, rew, gn), second = runs
+    assert all(np.array_equal(a, b) for a, b in zip((st, pa, co), second[:3])) and (rew, gn) == second[3:]
+    n = st.shape[0]
+    assert n > 1000 and rew > 0 and pa[0] == m.NO_INDEX and (pa[1:] < n).all()
+    ok, near = og.link(st[pa[1:]], st[1:], with_near_contact=True)
+    assert not ((ok == 0) & (near == 0)).any()
+    edge = oracle.distance(sp, st[pa[1:]], st[1:]).astype(np.float64)
+    # (tree edges may be longer than `range`: parents and rewiring come from the k nearest, prrt_star.hpp:553-556)
+    assert np.abs(co[pa[1:]].astype(np.float64) + edge - co[1:]).max() < 2e-4 * max(1.0, float(co.max()))  # float32 costs
+    for i in range(1, n, 7):  # no cycles
+        a, steps = i, 0
+        while a != 0:
+            a, steps = int(pa[a]), steps + 1
+            assert steps <= n
+    # PPRM on the same scene
+    pp = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=8.0, seed=9, capacity=1 << 13, max_wave=512)
+    assert pp.add_start(start) == 0 and pp.add_goal(goal) == 1
+    for _ in range(4):
+        pp.wave(512)
+    gs, ei, ed, mk, cp = pp.graph()
+    assert gs.shape[0] > 300 and og.valid(gs).all()
+    rows, cols = np.nonzero(ei != m.NO_INDEX)
+    ok, near = og.link(gs[rows], gs[ei[rows, cols]], with_near_contact=True)
+    assert rows.size > 1000 and not ((ok == 0) & (near == 0)).any()
+    assert np.array_equal(ed[rows, cols], oracle.distance(sp, gs[rows], gs[ei[rows, cols]]))
+    want = kats.components(ei)
+    assert np.array_equal(cp, want)
+    pp.close()
+
+
+def test_device_planner_argument_errors(ctx):
+    """Misuse is an error, never a silent fallback: waves before a start, waves larger than max_wave, a full tree."""
+    occ = W.synthetic_grid(200, 150, seed=3)
+    sp = m.lp_space(2, 2, m.F64)
+    sc = m.Scenario.grid(ctx, occ, m.F64)
+    free = np.argwhere(occ == 0)[0][::-1].astype(np.float64)
+    for cls in (m.DevicePRRT, m.DevicePRRTStar):
+        pl = cls(sc, sp, [0, 0], [199, 149], range=20.0, seed=1, capacity=64, max_wave=128)
+        with pytest.raises(m.MptgError):
+            pl.wave(16)  # "there are no valid initial states" (prrt.hpp:197-198)
+        pl.add_start(free)
+        with pytest.raises(m.MptgError):
+            pl.wave(129)
+        for _ in range(6):
+            pl.wave(128)
+        assert pl.size == 64  # capacity: the tree stops growing, no overrun
+        st, pa = pl.tree()
+        assert (pa[1:] < 64).all()
+        pl.close()
+    pp = m.DevicePPRM(sc, sp, [0, 0], [199, 149], seed=1, capacity=64, max_wave=128)
+    with pytest.raises(m.MptgError):
+        pp.wave(129)
+    obstacle = np.argwhere(occ != 0)[0][::-1].astype(np.float64)
+    assert pp.add_start(obstacle) == m.NO_INDEX  # invalid state: rejected (pprm.hpp:299-300)
+    assert pp.add_start(free) == 0
+    for _ in range(4):
+        pp.wave(128)
+    assert pp.size == 64
+    pp.close()
+
+
 def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W):
     pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W)
     assert pl.add_start(start) == 0 and pl.add_goal(goal) == 1
