@@ -4,7 +4,7 @@
 //   png_2d              demo/png_2d_planning.cpp:60-105               (PRRT*, occupancy grid)
 //   se3_rigid_body      demo/se3_rigid_body_planning.cpp:155-233      (PRRT*, mesh vs mesh, DiscreteMotionValidator)
 //   link_manipulator    demo/link_manipulator_planning.cpp:59-90      (PPRM, N-link planar arm)
-// Usage: planning_demos [--all | --demo NAME] [--time-ms T] [--check] [--map file.pgm] [--seed S]
+// Usage: planning_demos [--all | --demo NAME] [--time-ms T] [--check] [--map file.png|file.pgm] [--seed S]
 // Prints, per demo, time to first solution, node count and path cost ("solve time" of BASELINE.json).
 // The reference's PNG and OMPL meshes are not redistributable inputs of this repository: the map is
 // a synthetic one of the same size unless --map gives a binary PGM (tools/png_to_pgm.py converts the
@@ -20,6 +20,7 @@
 #include <random>
 #include <string>
 
+#include "mptg/formats.hpp"
 #include "mptg/planner.hpp"
 #include "mptg/scenarios.hpp"
 
@@ -158,7 +159,17 @@ void png2d(const Options& opt) {
     int width = 3976, height = 2603;  // size of demo/png_planning_input.png
     std::vector<std::uint8_t> occ;
     State start = makeState<Scalar, 2>({430, 1300}), goal = makeState<Scalar, 2>({3150, 950});  // png_2d_planning.cpp:84-86
-    if (opt.map.empty() || !readPgm(opt.map, width, height, occ)) {
+    bool haveMap = false;
+    if (opt.map.size() > 4 && opt.map.substr(opt.map.size() - 4) == ".png") {
+        // the reference's own input: decode the PNG and apply its obstacle colour filters (png_2d_planning.cpp:69-72,
+        // png_2d_scenario.hpp:192-265)
+        const formats::Image img = formats::readPngRgb(opt.map);
+        occ = formats::filterObstacles(img, {{126, 106, 61, 15}, {61, 53, 6, 15}, {255, 255, 255, 5}});
+        width = img.width, height = img.height, haveMap = true;
+    } else if (!opt.map.empty()) {
+        haveMap = readPgm(opt.map, width, height, occ);
+    }
+    if (!haveMap) {
         occ = syntheticMap(width, height, 11);
         // keep the shipped start usable on the synthetic map, then move the goal to the reachable free
         // cell (8 px clearance) closest to the shipped goal
@@ -369,7 +380,7 @@ int main(int argc, char** argv) {
         else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
         else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
         else {
-            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--device-prrt (also run the device-resident PRRT / PPRM)] [--map file.pgm] [--seed S]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator] [--time-ms T] [--nodes N] [--check] [--device-prrt (also run the device-resident PRRT / PPRM)] [--map file.png|file.pgm] [--seed S]\n", argv[0]);
             return 2;
         }
     }

@@ -24,7 +24,7 @@ def build_program(src: Path, out: Path, lib_dir: Path, lib: str, defines=()) -> 
     if _stale(out, deps):
         out.parent.mkdir(parents=True, exist_ok=True)
         rpath = "$ORIGIN/" + str(Path(*[".."] * len(out.parent.relative_to(ROOT).parts)) / lib_dir.relative_to(ROOT))
-        cmd = [CXX, *FLAGS, *[f"-D{d}" for d in defines], str(src), "-o", str(out), f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{rpath}", "-lpthread"]
+        cmd = [CXX, *FLAGS, *[f"-D{d}" for d in defines], str(src), "-o", str(out), f"-L{lib_dir}", f"-l{lib}", f"-Wl,-rpath,{rpath}", "-lpthread", "-lz"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}")

@@ -1,0 +1,50 @@
+"""Where does a device-resident planner wave spend its time?  Grow a tree to --nodes nodes on the 3976x2603 synthetic map,
+then run two waves between cudaProfilerStart/Stop:
+    ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file out.csv \
+        python tools/planner_wave_profile.py --algo prrtstar
+and summarise with tools/summarize_launches.py.  Without ncu it prints wall-clock per wave."""
+import argparse
+import sys
+import time
+
+sys.path.insert(0, ".")
+import numpy as np
+import torch
+
+import mpt_b200 as m
+from mpt_b200 import workloads as W
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--algo", default="prrtstar", choices=["prrt", "prrtstar", "pprm"])
+ap.add_argument("--nodes", type=int, default=150_000)
+ap.add_argument("--wave", type=int, default=8192)
+args = ap.parse_args()
+
+ctx = m.Context(0)
+occ = W.synthetic_grid()
+sp = m.lp_space(2, 2, m.F64)
+grid = m.Scenario.grid(ctx, occ, m.F64)
+free = np.argwhere(occ == 0)
+start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
+lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
+if args.algo == "prrt":
+    pl = m.DevicePRRT(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl.add_start(start)
+elif args.algo == "prrtstar":
+    pl = m.DevicePRRTStar(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl.add_start(start)
+else:
+    pl = m.DevicePPRM(grid, sp, lo, hi, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl.add_start(start)
+    pl.add_goal(goal)
+while pl.size < args.nodes:
+    pl.wave(args.wave)
+ctx.sync()
+torch.cuda.profiler.start()
+t0, n0 = time.perf_counter(), pl.size
+for _ in range(2):
+    pl.wave(args.wave)
+ctx.sync()
+dt = time.perf_counter() - t0
+torch.cuda.profiler.stop()
+print(f"{args.algo}: 2 waves of {args.wave} samples at {n0} nodes: {dt * 1e3 / 2:.3f} ms per wave, {(pl.size - n0) / 2:.0f} nodes added per wave")
