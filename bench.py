@@ -455,6 +455,9 @@ def secondary(ctx, torch, dev, stream):
         out[f"device_pprm_arm{n_links}"] = {"nodes_per_s": (pp.size - n0) / dt, "edges_checked_per_s": float((pp.size - n0) * pp.row_stride) / dt,
                                             "roadmap_edges": int((ei != m.NO_INDEX).sum()), "nodes": pp.size, "solved": pp.solved(), "s": dt}
         pp.close()
+        ref_arm = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1])
+        if ref_arm:
+            out[f"reference_planner_cpu_arm{n_links}"] = ref_arm
     # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
     ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)
     if ref:
@@ -491,6 +494,33 @@ def reference_planner_cpu(occ, start, goal, goal_radius, prrt_range, nodes=200_0
             except Exception as e:  # a baseline, never fatal
                 out[algo] = {"error": str(e)[:200]}
     return out
+
+
+def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_000, time_ms=6000):
+    """The reference's own multi-threaded PPRM (BASELINE configs[3]) on the reference's LinkManipulatorScenario<double, N>
+    (demo/link_manipulator_scenario.hpp), N = 8 or 16, on this box's host cores.  Same program and caveats as
+    reference_planner_cpu."""
+    import json
+    import subprocess
+    import tempfile
+
+    prog = ROOT / "oracle" / "_ref" / "ref_planner_bench"
+    if not prog.exists() or len(lengths) not in (8, 16):
+        return {}
+    with tempfile.NamedTemporaryFile("w", suffix=".txt") as f:
+        f.write(f"{len(lengths)} {radius!r}\n" + " ".join(repr(float(x)) for x in lengths) + f"\n{len(circles)}\n")
+        for c in circles:
+            f.write(" ".join(repr(float(x)) for x in c) + "\n")
+        f.write(" ".join(repr(float(x)) for x in start) + "\n" + " ".join(repr(float(x)) for x in goal) + "\n")
+        f.flush()
+        env = dict(os.environ)
+        env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        try:
+            r = subprocess.run([str(prog), "--arm", f.name, "--algo", "pprm", "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "23"],
+                               capture_output=True, text=True, timeout=time_ms / 1e3 + 60, env=env)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            return {"error": str(e)[:200]}
 
 
 def fp32_probe(torch, dev):

@@ -9,6 +9,9 @@
 //
 // usage: ref_planner_bench --map file.pgm --start X Y --goal X Y [--goal-radius R] [--range R] [--algo prrt|prrtstar]
 //                          [--threads N] [--nodes N] [--time-ms T] [--seed S]
+//        ref_planner_bench --arm scene.txt --algo pprm|prrtstar [--threads N] [--nodes N] [--time-ms T] [--seed S]
+//            (the reference's LinkManipulatorScenario<double, N>, N = 8 or 16; scene.txt: N radius / N lengths /
+//             C / C lines "cx cy r" / start (N angles) / goal (N angles))
 // Phase 1 runs until the first solution (or the node / time limit); phase 2 continues to the node / time limit.
 #include <omp.h>
 
@@ -36,8 +39,10 @@
 #include <mpt/lp_space.hpp>
 #include <mpt/planner.hpp>
 #include <mpt/prrt.hpp>
+#include <mpt/pprm.hpp>
 #include <mpt/prrt_star.hpp>
 
+#include <link_manipulator_scenario.hpp>
 #include <png_2d_scenario.hpp>
 
 namespace mpt = unc::robotics::mpt;
@@ -63,7 +68,7 @@ struct GridScenario {
 };
 
 struct Options {
-    std::string map, algo = "prrtstar";
+    std::string map, arm, algo = "prrtstar";
     double start[2] = {0, 0}, goal[2] = {0, 0}, goalRadius = 1e-6, range = INFINITY;
     int threads = 0;
     std::size_t nodes = 200000;
@@ -117,12 +122,57 @@ int run(const Options& o, int w, int h, std::vector<bool>& obst) {
     return 0;
 }
 
+// the reference's N-link arm scenario (demo/link_manipulator_scenario.hpp) under its PPRM / PRRT*
+template <int N, template <class...> class AlgoT>
+int runArm(const Options& o, const char* algoName) {
+    using Scenario = mpt_demo::LinkManipulatorScenario<double, N>;
+    using State = typename Scenario::State;
+    using Clock = std::chrono::steady_clock;
+    std::ifstream f(o.arm);
+    int n = 0, nc = 0;
+    double radius = 0;
+    f >> n >> radius;
+    if (!f || n != N) return 2;
+    std::vector<double> lengths(N);
+    for (double& l : lengths) f >> l;
+    f >> nc;
+    std::vector<shape::Circle<double>> circles;
+    for (int i = 0; i < nc; ++i) {
+        double x, y, r;
+        f >> x >> y >> r;
+        circles.emplace_back(x, y, r);
+    }
+    State start, goal;
+    for (int i = 0; i < N; ++i) f >> start[i];
+    for (int i = 0; i < N; ++i) f >> goal[i];
+    if (!f) return 2;
+    Scenario scenario(goal, circles, lengths, radius);
+    mpt::Planner<Scenario, AlgoT<>> planner(scenario, o.seed);
+    planner.addStart(start);
+    if constexpr (std::is_same_v<AlgoT<>, mpt::PPRM<>>) planner.addGoal(goal);
+    const auto t0 = Clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(Clock::now() - t0).count(); };
+    planner.solve([&] { return planner.solved() || planner.size() >= o.nodes || elapsed() * 1e3 >= o.timeMs; });
+    const double first = elapsed();
+    const std::size_t firstNodes = planner.size();
+    const bool solvedFirst = planner.solved();
+    planner.solve([&] { return planner.size() >= o.nodes || elapsed() * 1e3 >= o.timeMs; });
+    const double total = elapsed();
+    std::printf("{\"impl\": \"reference planner classes (src/mpt, OpenMP worker pool) on the reference's LinkManipulatorScenario<double, %d>\", "
+                "\"nn\": \"stand-in concurrent kd-tree (Nigh absent)\", \"algo\": \"%s\", \"threads\": %d, \"solved\": %s, "
+                "\"first_solution_s\": %.6f, \"first_solution_nodes\": %zu, \"nodes\": %zu, \"seconds\": %.6f, \"nodes_per_s\": %.1f}\n",
+                N, algoName, omp_get_max_threads(), planner.solved() ? "true" : "false", solvedFirst ? first : -1.0, firstNodes, planner.size(), total,
+                planner.size() / total);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     Options o;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&] { return i + 1 < argc ? argv[++i] : (char*)"0"; };
         if (a == "--map") o.map = next();
+        else if (a == "--arm") o.arm = next();
         else if (a == "--start") o.start[0] = atof(next()), o.start[1] = atof(next());
         else if (a == "--goal") o.goal[0] = atof(next()), o.goal[1] = atof(next());
         else if (a == "--goal-radius") o.goalRadius = atof(next());
@@ -136,6 +186,17 @@ int main(int argc, char** argv) {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return 2;
         }
+    }
+    if (o.threads > 0) omp_set_num_threads(o.threads);
+    if (!o.arm.empty()) {
+        std::ifstream f(o.arm);
+        int n = 0;
+        f >> n;
+        int rc = 2;
+        if (o.algo == "pprm") rc = n == 8 ? runArm<8, mpt::PPRM>(o, "pprm") : n == 16 ? runArm<16, mpt::PPRM>(o, "pprm") : 2;
+        else if (o.algo == "prrtstar") rc = n == 8 ? runArm<8, mpt::PRRTStar>(o, "prrtstar") : n == 16 ? runArm<16, mpt::PRRTStar>(o, "prrtstar") : 2;
+        if (rc == 2) std::fprintf(stderr, "cannot run the arm scene %s (N = 8 or 16; algo pprm or prrtstar)\n", o.arm.c_str());
+        return rc;
     }
     int w = 0, h = 0;
     std::vector<bool> obst;
