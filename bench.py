@@ -420,9 +420,16 @@ def secondary(ctx, torch, dev, stream):
     pl.close()
     # device-resident PRRT* (BASELINE configs[1]: PRRT* on the occupancy grid): same map, start and range
     goal = free[-len(free) // 9][::-1].astype(np.float64)
+    warm = m.DevicePRRTStar(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], range=200.0, goal=goal, goal_radius=12.0,
+                            seed=3, capacity=1 << 16, max_wave=8192)  # untimed: loads every kernel of the wave (wall-clock timing below)
+    warm.add_start(start)
+    for _ in range(6):
+        warm.wave(8192)
+    warm.close()
     ps = m.DevicePRRTStar(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], range=200.0, goal=goal, goal_radius=12.0,
                           seed=17, capacity=1 << 20, max_wave=8192)
     ps.add_start(start)
+    ctx.sync()
     t0 = time.perf_counter()
     first_solution = None
     while ps.size < 200_000:

@@ -166,6 +166,74 @@ __global__ void __launch_bounds__(256) knnMergeKernel(uint32_t parts, uint32_t Q
     if (countOut && lane == 0) countOut[q] = count;
 }
 
+// ---------------------------------------------------------------------------------------------
+// search of the tail's Morton-sorted leaves (KnnTail, knn_index.cuh): one warp per query walks the flat list of leaf
+// boxes 32 at a time and visits the leaves whose lower bound is within the threshold.  `cap` (optional, [Q][k]
+// distances of the tree search of the same queries) bounds the search from the start: a tail point farther than the
+// tree's k-th neighbour cannot be among the k nearest of the union.
+// ---------------------------------------------------------------------------------------------
+template <typename S>
+struct TailArgs {
+    const S* leafPts;
+    const uint32_t* perm;
+    const S* box;
+    uint32_t nLeaves;
+    const S* queries;
+    const S* cap;
+    uint32_t Q, k;
+    S radius;
+    uint32_t idxMul, idxAdd;
+    uint32_t* idxOut;
+    S* distOut;
+    DevSpace<S> sp;
+};
+
+template <typename S, int KPL>
+__global__ void __launch_bounds__(256) knnTailKernel(const TailArgs<S> a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* qsm = reinterpret_cast<S*>(smemRaw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q = blockIdx.x * 8 + warp;
+    if (q >= a.Q) return;
+    S* myq = qsm + warp * D;
+    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+    __syncwarp();
+    S radius = a.radius;
+    if (a.cap) {
+        const S c = a.cap[(size_t)q * a.k + (a.k - 1)];  // +inf when the tree returned fewer than k
+        radius = c < radius ? c : radius;
+    }
+    WarpTopK<S, KPL> top;
+    top.init(a.k);
+    const uint32_t nBlocks = (a.nLeaves + 31u) / 32u;
+    for (uint32_t b = 0; b < nBlocks; ++b) {
+        const uint32_t leaf = b * 32u + (uint32_t)lane;
+        uint32_t key = BVH_DEAD;
+        if (leaf < a.nLeaves) {
+            const S* bx = a.box + ((size_t)b * (size_t)(2 * D)) * 32u + lane;
+            key = boundKey<S>(dev::boxLowerBound<S>(
+                a.sp, [&](int c) { return __ldg(bx + c * 32); }, [&](int c) { return __ldg(bx + (D + c) * 32); }, [&](int c) { return myq[c]; }));
+        }
+        S thr = top.kthD < radius ? top.kthD : radius;
+        unsigned m = __ballot_sync(FULL_MASK, __uint_as_float(key) <= thrAsFloat<S>(thr));
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1u;
+            const uint32_t lkey = __shfl_sync(FULL_MASK, key, src);
+            if (__uint_as_float(lkey) > thrAsFloat<S>(thr)) continue;  // the threshold has shrunk since the vote
+            const uint32_t node = b * 32u + (uint32_t)src;
+            const uint32_t orig = __ldg(a.perm + (size_t)node * 32u + lane);
+            const S* pt = a.leafPts + ((size_t)node * (size_t)D) * 32u + lane;
+            const S dist = dev::distance<S>(
+                a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
+            top.offer(orig != MPTG_NO_INDEX, dist, orig * a.idxMul + a.idxAdd, radius, lane);
+            thr = top.kthD < radius ? top.kthD : radius;
+        }
+    }
+    top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
+}
+
 // AoS -> SoA append
 template <typename S>
 __global__ void knnScatterKernel(const S* aos, uint32_t count, int D, S* pts, uint32_t stride, uint32_t first) {
@@ -201,6 +269,7 @@ struct mptg_knn {
     uint32_t idxMul = 1, idxAdd = 0;
     uint64_t stats[4] = {0, 0, 0, 0};
     KnnIndex index;  // knn_bvh.cuh
+    KnnTail tail;    // knn_index.cuh: Morton-sorted leaves over the points inserted since the tree was built
 };
 
 namespace {
@@ -325,28 +394,60 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
     knn->stats[3] = (uint64_t)strategy;
     if (indexed == 0) return bruteScan<S>(knn, 0, knn->size, queries, Q, k, radius, idxOut, distOut, countOut);
 
-    // indexed prefix via the tree, unindexed tail by brute force, then merge the two lists
-    const bool tail = indexed < knn->size;
+    // indexed prefix via the tree; the tail through its Morton-sorted leaves (bounded by the tree's k-th distances)
+    // and, for what has arrived since, by brute force; then merge the lists
+    KnnTail& tl = knn->tail;
+    if (tl.forBuild != knn->index.builds || tl.base != indexed) {  // the tree was rebuilt: start a new tail
+        tl.forBuild = knn->index.builds;
+        tl.base = indexed;
+        tl.covered = 0;
+        tl.nLeaves = 0;
+    }
+    const uint32_t rawBegin = indexed + tl.covered;
+    if (knn->size - rawBegin >= TAIL_MIN_CHUNK) {
+        if (int rc = knnTailAppend(ctx, tl, knn->space, (const S*)knn->pts, knn->stride, rawBegin, knn->size - rawBegin)) return rc;
+    }
+    const bool useLeaves = tl.nLeaves > 0;
+    const bool raw = indexed + tl.covered < knn->size;
+    const uint32_t parts = 1u + (useLeaves ? 1u : 0u) + (raw ? 1u : 0u);
     uint32_t* i0 = idxOut;
     S* d0 = distOut;
-    if (tail) {
+    if (parts > 1) {
         void* p0;
         void* p1;
-        int rc = scratch(ctx, 4, (size_t)2 * Q * k * sizeof(uint32_t), &p0);
+        int rc = scratch(ctx, 4, (size_t)3 * Q * k * sizeof(uint32_t), &p0);
         if (rc) return rc;
-        rc = scratch(ctx, 5, (size_t)2 * Q * k * sizeof(S), &p1);
+        rc = scratch(ctx, 5, (size_t)3 * Q * k * sizeof(S), &p1);
         if (rc) return rc;
         i0 = (uint32_t*)p0;
         d0 = (S*)p1;
     }
     int rc = knnBvhQuery<S>(ctx, knn->index, knn->space, queries, Q, k, radius, knn->idxMul, knn->idxAdd, i0, d0,
-                            tail ? nullptr : countOut, knn->stats);
+                            parts > 1 ? nullptr : countOut, knn->stats);
     if (rc) return rc;
-    if (tail) {
-        rc = bruteScan<S>(knn, indexed, knn->size, queries, Q, k, radius, i0 + (size_t)Q * k, d0 + (size_t)Q * k, nullptr);
-        if (rc) return rc;
-        rc = launchMerge<S>(ctx, 2, Q, k, i0, d0, idxOut, distOut, countOut);
+    uint32_t slot = 1;
+    if (useLeaves) {
+        TailArgs<S> a{};
+        a.leafPts = (const S*)tl.leafPts, a.perm = tl.perm, a.box = (const S*)tl.box, a.nLeaves = tl.nLeaves;
+        a.queries = queries, a.cap = d0, a.Q = Q, a.k = k;
+        a.radius = (radius >= 0 && radius == radius) ? (S)radius : fp::consts<S>::inf();
+        a.idxMul = knn->idxMul, a.idxAdd = knn->idxAdd;
+        a.idxOut = i0 + (size_t)slot * Q * k, a.distOut = d0 + (size_t)slot * Q * k;
+        a.sp = makeDevSpace<S>(knn->space);
+        const dim3 grid((Q + 7) / 8), block(256);
+        const size_t smem = (size_t)8 * knn->D * sizeof(S);
+        if (k <= 32) knnTailKernel<S, 1><<<grid, block, smem, ctx->stream>>>(a);
+        else if (k <= 64) knnTailKernel<S, 2><<<grid, block, smem, ctx->stream>>>(a);
+        else knnTailKernel<S, 4><<<grid, block, smem, ctx->stream>>>(a);
+        MPTG_LAUNCHED(ctx);
+        knn->stats[0] += (uint64_t)tl.nLeaves * Q;  // box tests (an upper bound of the work; leaf visits are not counted)
+        ++slot;
     }
+    if (raw) {
+        rc = bruteScan<S>(knn, indexed + tl.covered, knn->size, queries, Q, k, radius, i0 + (size_t)slot * Q * k, d0 + (size_t)slot * Q * k, nullptr);
+        if (rc) return rc;
+    }
+    if (parts > 1) rc = launchMerge<S>(ctx, parts, Q, k, i0, d0, idxOut, distOut, countOut);
     return rc;
 }
 
@@ -394,6 +495,7 @@ int mptg_knn_destroy(mptg_knn* knn) {
     cudaSetDevice(knn->ctx->device);
     cudaStreamSynchronize(knn->ctx->stream);
     knnIndexFree(knn->index);
+    if (knn->tail.mem) cudaFree(knn->tail.mem);
     cudaFree(knn->pts);
     delete knn;
     return MPTG_OK;

@@ -142,14 +142,14 @@ __global__ void splitKernel(SegLevel lv, uint32_t* __restrict__ segOf, uint32_t 
 template <typename S>
 __global__ void __launch_bounds__(256) leafEmitKernel(const S* __restrict__ canon, const uint32_t* __restrict__ ids, uint32_t n, int D,
                                                       uint32_t nLeaves, S* __restrict__ leafPts, uint32_t* __restrict__ perm,
-                                                      S* __restrict__ lo, S* __restrict__ hi) {
+                                                      S* __restrict__ lo, S* __restrict__ hi, uint32_t idBase = 0) {
     const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (leaf >= nLeaves) return;
     const uint32_t p = leaf * 32u + lane;
     const bool real = p < n;
     const uint32_t src = ids[real ? p : n - 1];  // padding repeats the last point (perm marks it unused)
-    perm[p] = real ? src : MPTG_NO_INDEX;
+    perm[p] = real ? src + idBase : MPTG_NO_INDEX;
     for (int c = 0; c < D; ++c) {
         const S v = canon[(size_t)src * D + c];
         leafPts[((size_t)leaf * D + c) * 32u + lane] = v;
@@ -269,6 +269,142 @@ Levels makeLevels(uint32_t n) {
     return L;
 }
 
+
+// ---- tail chunks (KnnTail): Morton order of one batch of new points, 32-point leaves with boxes
+// the (up to) three coordinates of largest weighted extent, with offset and scale to 10 bits each
+__global__ void mortonAxesKernel(DevSpace<float> sp, const int* __restrict__ segMin, const int* __restrict__ segMax, int* __restrict__ axes,
+                                 float* __restrict__ offScale) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float best[3] = {-1.0f, -1.0f, -1.0f};
+    int ax[3] = {-1, -1, -1};
+    for (int p = 0; p < sp.nParts; ++p)
+        for (int j = 0; j < sp.dim[p]; ++j) {
+            const int c = sp.off[p] + j;
+            const float ext = (fromOrderedInt(segMax[c]) - fromOrderedInt(segMin[c])) * sp.weight[p];
+            for (int r = 0; r < 3; ++r)
+                if (ext > best[r]) {
+                    for (int t = 2; t > r; --t) best[t] = best[t - 1], ax[t] = ax[t - 1];
+                    best[r] = ext, ax[r] = c;
+                    break;
+                }
+        }
+    for (int r = 0; r < 3; ++r) {
+        axes[r] = ax[r];
+        const float mn = ax[r] >= 0 ? fromOrderedInt(segMin[ax[r]]) : 0.0f, mx = ax[r] >= 0 ? fromOrderedInt(segMax[ax[r]]) : 0.0f;
+        offScale[2 * r] = mn;
+        offScale[2 * r + 1] = mx > mn ? 1023.0f / (mx - mn) : 0.0f;
+    }
+}
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void mortonKeyKernel(const float* __restrict__ canon, uint32_t n, int D, const int* __restrict__ axes, const float* __restrict__ offScale,
+                                uint32_t* __restrict__ keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t key = 0;
+    for (int r = 0; r < 3; ++r) {
+        const int c = axes[r];
+        if (c < 0) continue;
+        float q = (canon[(size_t)i * D + c] - offScale[2 * r]) * offScale[2 * r + 1];
+        q = fminf(fmaxf(q, 0.0f), 1023.0f);
+        key |= spread3((uint32_t)q) << r;
+    }
+    keys[i] = key;
+}
+// SoA leaf boxes of a chunk -> the tail's blocked box array at leaf offset `leaf0`
+template <typename S>
+__global__ void tailBoxKernel(const S* __restrict__ lo, const S* __restrict__ hi, uint32_t nNew, int D, uint32_t leaf0, S* __restrict__ box) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nNew) return;
+    const uint32_t leaf = leaf0 + j, b = leaf >> 5, ln = leaf & 31;
+    for (int c = 0; c < D; ++c) {
+        box[((size_t)b * 2 * D + c) * 32u + ln] = lo[(size_t)c * nNew + j];
+        box[((size_t)b * 2 * D + D + c) * 32u + ln] = hi[(size_t)c * nNew + j];
+    }
+}
+
+}  // namespace
+
+template <typename S>
+int knnTailAppendT(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, const S* ptsDev, uint32_t stride, uint32_t first, uint32_t count) {
+    if (count == 0) return MPTG_OK;
+    const DevSpace<float> sp = makeDevSpace<float>(space);
+    const int D = sp.D;
+    cudaStream_t st = ctx->stream;
+    const uint32_t nNew = (count + 31) / 32;
+    if (((size_t)tail.nLeaves + nNew) * 32 > TAIL_MAX_POINTS) return MPTG_OK;  // full: the caller scans what is not covered
+    if (!tail.mem) {
+        const size_t maxLeaves = TAIL_MAX_POINTS / 32, maxBlocks = (maxLeaves + 31) / 32;
+        const size_t bPts = ((size_t)TAIL_MAX_POINTS * D * sizeof(S) + 255) & ~(size_t)255, bPerm = ((size_t)TAIL_MAX_POINTS * 4 + 255) & ~(size_t)255,
+                     bBox = maxBlocks * 2 * D * 32 * sizeof(S);
+        MPTG_CUDA(ctx, cudaMalloc(&tail.mem, bPts + bPerm + bBox));
+        tail.leafPts = tail.mem;
+        tail.perm = (uint32_t*)((char*)tail.mem + bPts);
+        tail.box = (char*)tail.mem + bPts + bPerm;
+    }
+    size_t cubBytes = 0;
+    cub::DoubleBuffer<uint32_t> kb(nullptr, nullptr), vb(nullptr, nullptr);
+    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, kb, vb, (int)count, 0, 30, st));
+    size_t wbytes = 0;
+    auto wtake = [&](size_t b) {
+        const size_t o = wbytes;
+        wbytes += (b + 255) & ~(size_t)255;
+        return o;
+    };
+    const size_t wCanon = wtake((size_t)count * D * 4), wExact = wtake(sizeof(S) == 8 ? (size_t)count * D * 8 : 0), wKey0 = wtake((size_t)count * 4),
+                 wKey1 = wtake((size_t)count * 4), wId0 = wtake((size_t)count * 4), wId1 = wtake((size_t)count * 4), wSeg = wtake((size_t)count * 4),
+                 wMin = wtake((size_t)D * 4), wMax = wtake((size_t)D * 4), wAxes = wtake(16), wOff = wtake(32), wCub = wtake(cubBytes),
+                 wLo = wtake((size_t)D * nNew * sizeof(S)), wHi = wtake((size_t)D * nNew * sizeof(S));
+    void* wbase;
+    if (int rc = scratch(ctx, 7, wbytes, &wbase)) return rc;
+    char* W = (char*)wbase;
+    float* canon = (float*)(W + wCanon);
+    S* exact = sizeof(S) == 8 ? (S*)(W + wExact) : (S*)canon;
+    uint32_t* keys[2] = {(uint32_t*)(W + wKey0), (uint32_t*)(W + wKey1)};
+    uint32_t* ids[2] = {(uint32_t*)(W + wId0), (uint32_t*)(W + wId1)};
+    uint32_t* segOf = (uint32_t*)(W + wSeg);
+    int* segMin = (int*)(W + wMin);
+    int* segMax = (int*)(W + wMax);
+    const uint32_t g256 = (count + 255) / 256;
+    canonKernel<S><<<g256, 256, 0, st>>>(sp, ptsDev + first, stride, count, canon, exact);
+    MPTG_LAUNCHED(ctx);
+    iotaKernel<<<g256, 256, 0, st>>>(ids[0], segOf, count);
+    MPTG_LAUNCHED(ctx);
+    resetExtentKernel<<<1, 256, 0, st>>>(segMin, segMax, (uint32_t)D);
+    MPTG_LAUNCHED(ctx);
+    segExtentKernel<<<(count + EXT_THREADS - 1) / EXT_THREADS, EXT_THREADS, 0, st>>>(canon, ids[0], segOf, count, D, segMin, segMax);
+    MPTG_LAUNCHED(ctx);
+    mortonAxesKernel<<<1, 32, 0, st>>>(sp, segMin, segMax, (int*)(W + wAxes), (float*)(W + wOff));
+    MPTG_LAUNCHED(ctx);
+    mortonKeyKernel<<<g256, 256, 0, st>>>(canon, count, D, (const int*)(W + wAxes), (const float*)(W + wOff), keys[0]);
+    MPTG_LAUNCHED(ctx);
+    cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(ids[0], ids[1]);
+    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(W + wCub, cubBytes, dk, dv, (int)count, 0, 30, st));
+    ++ctx->launches;
+    leafEmitKernel<S><<<(nNew * 32 + 255) / 256, 256, 0, st>>>(exact, dv.Current(), count, D, nNew, (S*)tail.leafPts + (size_t)tail.nLeaves * D * 32,
+                                                              tail.perm + (size_t)tail.nLeaves * 32, (S*)(W + wLo), (S*)(W + wHi), first);
+    MPTG_LAUNCHED(ctx);
+    tailBoxKernel<S><<<(nNew + 127) / 128, 128, 0, st>>>((const S*)(W + wLo), (const S*)(W + wHi), nNew, D, tail.nLeaves, (S*)tail.box);
+    MPTG_LAUNCHED(ctx);
+    tail.nLeaves += nNew;
+    tail.covered += count;
+    return MPTG_OK;
+}
+
+int knnTailAppend(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t first, uint32_t count) {
+    return knnTailAppendT<float>(ctx, tail, space, ptsDev, stride, first, count);
+}
+int knnTailAppend(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, const double* ptsDev, uint32_t stride, uint32_t first, uint32_t count) {
+    return knnTailAppendT<double>(ctx, tail, space, ptsDev, stride, first, count);
+}
+
+namespace {
 }  // namespace
 
 template <typename S>

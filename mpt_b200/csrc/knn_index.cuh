@@ -27,6 +27,23 @@ struct KnnIndex {
     uint64_t builds = 0;
 };
 
+// Indexed part of the tail (points inserted since the last build of the tree): each batch of points that has arrived
+// between two searches is sorted along a Morton curve and cut into 32-point leaves with boxes -- a flat, one-level
+// index that costs one small sort to extend.  Planner waves insert thousands of points per wave and rebuild the tree
+// only every few waves; without this the exhaustive scan of the tail was half of a device-resident planner wave.
+constexpr uint32_t TAIL_MAX_POINTS = 65536 + 4096;  // the tree is rebuilt before the tail outgrows 65536 points
+constexpr uint32_t TAIL_MIN_CHUNK = 1024;           // fewer new points than this are scanned exhaustively
+struct KnnTail {
+    uint32_t base = 0;      // first point covered (== index.count when valid)
+    uint32_t covered = 0;   // points [base, base + covered) are in the leaves below
+    uint32_t nLeaves = 0;   // 32-point leaves (each chunk padded to a multiple of 32, perm = MPTG_NO_INDEX for padding)
+    uint64_t forBuild = ~0ull;  // KnnIndex::builds this tail belongs to
+    void* mem = nullptr;
+    void* leafPts = nullptr;   // [leaf][D][32]
+    uint32_t* perm = nullptr;  // [leaf * 32] insertion index
+    void* box = nullptr;       // [block][2D][32], block = leaf / 32
+};
+
 inline void knnIndexFree(KnnIndex& ix) {
     if (ix.mem) cudaFree(ix.mem);
     if (ix.devStats) cudaFree(ix.devStats);
@@ -37,5 +54,8 @@ inline void knnIndexFree(KnnIndex& ix) {
 // Device build of the index for float32 spaces (knn_build.cu).  Fills `ix` like the host build does.
 int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t n);
 int knnBuildIndexGpu(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const double* ptsDev, uint32_t stride, uint32_t n);
+// Append points [first, first + count) of the store to the tail's leaves (knn_build.cu).
+int knnTailAppend(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, const float* ptsDev, uint32_t stride, uint32_t first, uint32_t count);
+int knnTailAppend(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, const double* ptsDev, uint32_t stride, uint32_t first, uint32_t count);
 
 }  // namespace mptg

@@ -115,6 +115,45 @@ def test_knn_bvh_with_unindexed_tail(ctx, oracle):
     nn.close()
 
 
+@pytest.mark.parametrize("name", ["se3_f32", "l2_2d_f64", "l1_8d_f64", "so2_3_f32"])
+def test_knn_tail_leaves_and_raw_remainder(ctx, oracle, name):
+    """The planner's access pattern on a tree-indexed set: batches arrive between searches; batches of >= 1024 points
+    become Morton-sorted leaves (several chunks), smaller ones are scanned; everything is merged with the tree's answer.
+    Results stay bit-identical to the exhaustive oracle, for k = 1, a large k, a radius, duplicates of tree points in
+    the tail, and a sharded index map."""
+    sp = {"se3_f32": m.se3_space(50, 1), "l2_2d_f64": m.lp_space(2, 2, m.F64), "l1_8d_f64": m.lp_space(8, 1, m.F64),
+          "so2_3_f32": m.so2_space(3, 1, m.F32)}[name]
+    pts = random_states(sp, 52_000, 21)
+    pts[41_000:41_050] = pts[100:150]      # duplicates of indexed points inside the tail: ties broken by index
+    q = random_states(sp, 300, 22)
+    q[:20] = pts[41_000:41_020]
+    nn = m.Nearest(ctx, sp, 65536, m.KNN_BVH)
+    nn.insert(pts[:40_000])
+    nn.nearest(q[:8], 1)                   # builds the tree over 40,000 points
+    n = 40_000
+    for batch, k, radius in ((1500, 16, None), (300, 1, None), (2500, 48, None), (40, 16, None), (3000, 100, None), (1200, 16, 0.5)):
+        nn.insert(pts[n:n + batch])
+        n += batch
+        if radius is not None:
+            d16 = oracle.knn(sp, pts[:n], q, 16)[1]
+            radius = float(np.median(d16[:, 8]))   # about half of the neighbours fall inside
+        got = nn.nearest(q, k, radius) if radius is not None else nn.nearest(q, k)
+        want = oracle.knn(sp, pts[:n], q, k, radius if radius is not None else -1.0)
+        assert_knn_equal(got, want)
+        assert nn.last_stats()["indexed"] == 40_000   # still the first tree: the tail did the rest
+    nn.close()
+    # sharded index map (global = local * 4 + 1), as on 4 GPUs
+    nn = m.Nearest(ctx, sp, 65536, m.KNN_BVH)
+    nn.set_index_map(4, 1)
+    nn.insert(pts[:40_000])
+    nn.nearest(q[:8], 1)
+    nn.insert(pts[40_000:43_000])
+    gi, gd, gc = nn.nearest(q, 16)
+    wi, wd, wc = oracle.knn(sp, pts[:43_000], q, 16)
+    assert np.array_equal(gi, wi * 4 + 1) and np.array_equal(gd, wd) and np.array_equal(gc, wc)
+    nn.close()
+
+
 def test_knn_auto_strategy_and_ragged_sizes(ctx, oracle):
     sp = m.se3_space(50, 1)
     for n in (1, 31, 32, 33, 1023, 1025, 16384, 33_000):
