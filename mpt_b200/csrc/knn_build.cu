@@ -271,7 +271,8 @@ Levels makeLevels(uint32_t n) {
 
 
 // ---- tail chunks (KnnTail): Morton order of one batch of new points, 32-point leaves with boxes
-// the (up to) three coordinates of largest weighted extent, with offset and scale to 10 bits each
+// the (up to) three coordinates of largest weighted extent, with offset and scale to 8 bits each (24-bit keys: three
+// radix passes; a 256^3 grid is plenty for a tail of at most 65536 points)
 __global__ void mortonAxesKernel(DevSpace<float> sp, const int* __restrict__ segMin, const int* __restrict__ segMax, int* __restrict__ axes,
                                  float* __restrict__ offScale) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -292,7 +293,7 @@ __global__ void mortonAxesKernel(DevSpace<float> sp, const int* __restrict__ seg
         axes[r] = ax[r];
         const float mn = ax[r] >= 0 ? fromOrderedInt(segMin[ax[r]]) : 0.0f, mx = ax[r] >= 0 ? fromOrderedInt(segMax[ax[r]]) : 0.0f;
         offScale[2 * r] = mn;
-        offScale[2 * r + 1] = mx > mn ? 1023.0f / (mx - mn) : 0.0f;
+        offScale[2 * r + 1] = mx > mn ? 255.0f / (mx - mn) : 0.0f;
     }
 }
 __device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
@@ -312,7 +313,7 @@ __global__ void mortonKeyKernel(const float* __restrict__ canon, uint32_t n, int
         const int c = axes[r];
         if (c < 0) continue;
         float q = (canon[(size_t)i * D + c] - offScale[2 * r]) * offScale[2 * r + 1];
-        q = fminf(fmaxf(q, 0.0f), 1023.0f);
+        q = fminf(fmaxf(q, 0.0f), 255.0f);
         key |= spread3((uint32_t)q) << r;
     }
     keys[i] = key;
@@ -350,7 +351,7 @@ int knnTailAppendT(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, c
     }
     size_t cubBytes = 0;
     cub::DoubleBuffer<uint32_t> kb(nullptr, nullptr), vb(nullptr, nullptr);
-    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, kb, vb, (int)count, 0, 30, st));
+    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, cubBytes, kb, vb, (int)count, 0, 24, st));
     size_t wbytes = 0;
     auto wtake = [&](size_t b) {
         const size_t o = wbytes;
@@ -385,7 +386,7 @@ int knnTailAppendT(mptg_ctx* ctx, KnnTail& tail, const mptg_space_desc& space, c
     mortonKeyKernel<<<g256, 256, 0, st>>>(canon, count, D, (const int*)(W + wAxes), (const float*)(W + wOff), keys[0]);
     MPTG_LAUNCHED(ctx);
     cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(ids[0], ids[1]);
-    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(W + wCub, cubBytes, dk, dv, (int)count, 0, 30, st));
+    MPTG_CUDA(ctx, cub::DeviceRadixSort::SortPairs(W + wCub, cubBytes, dk, dv, (int)count, 0, 24, st));
     ++ctx->launches;
     leafEmitKernel<S><<<(nNew * 32 + 255) / 256, 256, 0, st>>>(exact, dv.Current(), count, D, nNew, (S*)tail.leafPts + (size_t)tail.nLeaves * D * 32,
                                                               tail.perm + (size_t)tail.nLeaves * 32, (S*)(W + wLo), (S*)(W + wHi), first);
