@@ -380,11 +380,12 @@ def secondary(ctx, torch, dev, stream):
         a, b = W.arm_edges(E_WAVE, n_links, 41, 0.5)
         out[f"link_arm_{n_links}_edges"] = time_link(arm, a, b)
     # planar L2 kNN at a planner-realistic size (tiled scan) and at 1M (tree)
-    for n_pts, label in ((1 << 14, "knn_l2_2d_16k_brute"), (1 << 20, "knn_l2_2d_1m_tree")):
+    for n_pts, label, strat in ((1 << 14, "knn_l2_2d_16k_brute", m.KNN_BRUTE), (1 << 14, "knn_l2_2d_16k_auto", m.KNN_AUTO),
+                                (1 << 20, "knn_l2_2d_1m_tree", m.KNN_AUTO)):
         sp = m.lp_space(2, 2, m.F32)
         pts = W.box_states(n_pts, 2, 51, 0.0, [3976, 2603], np.float32)
         q = W.box_states(Q_WAVE, 2, 52, 0.0, [3976, 2603], np.float32)
-        nn = m.Nearest(ctx, sp, n_pts)
+        nn = m.Nearest(ctx, sp, n_pts, strat)
         nn.insert(pts)
         dq = torch.from_numpy(q).to(dev)
         di = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)

@@ -383,7 +383,7 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
     mptg_ctx* ctx = knn->ctx;
     knn->stats[0] = knn->stats[1] = 0;
     int strategy = knn->strategy;
-    if (strategy == MPTG_KNN_AUTO) strategy = knnAutoStrategy(knn->size, Q, knn->index);
+    if (strategy == MPTG_KNN_AUTO) strategy = knnAutoStrategy(knn->size, Q, (int)knn->shape, knn->D);
     uint32_t indexed = 0;
     if (strategy == MPTG_KNN_BVH) {
         int rc = knnEnsureIndex<S>(ctx, knn->index, knn->space, (const S*)knn->pts, knn->stride, knn->size);
@@ -404,7 +404,9 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
         tl.nLeaves = 0;
     }
     const uint32_t rawBegin = indexed + tl.covered;
-    if (knn->size - rawBegin >= TAIL_MIN_CHUNK) {
+    // 1-NN waves (PRRT) scan a raw tail faster than they could sort it into leaves: the exhaustive 1-NN scan costs
+    // ~3 us per 1,000 tail points and 8,192 queries, a chunk ~100 us to build; k-NN waves (PRRT*, PPRM) are the other way
+    if (knn->size - rawBegin >= TAIL_MIN_CHUNK && (k > 1 || knn->size - rawBegin >= 32768u)) {
         if (int rc = knnTailAppend(ctx, tl, knn->space, (const S*)knn->pts, knn->stride, rawBegin, knn->size - rawBegin)) return rc;
     }
     const bool useLeaves = tl.nLeaves > 0;

@@ -33,14 +33,27 @@
 
 namespace mptg {
 
-// AUTO policy.  The tiled scan evaluates Q*N pairs at full machine width whatever the queries are; the tree
-// visits far fewer points but each query is a chain of dependent node fetches, which a small wave cannot
-// hide (measured: 1,024 uniform SE(3) samples against a 200K-node planner tree, i.e. queries far from the
-// tree, take 3 ms through the tree and 0.2 ms scanned).  So: scan while the set is small or the wave's
-// pair count fits a fraction of a millisecond, tree otherwise.
-inline int knnAutoStrategy(uint32_t size, uint32_t Q, const KnnIndex& /*ix*/) {
+// AUTO policy.  The tiled scan evaluates Q*N pairs at full machine width whatever the queries are; the tree visits
+// far fewer points but each query is a chain of dependent node fetches, which a small wave cannot hide.  Where the
+// two cross depends on the space (measured on B200 with planner waves, tools/planner_wave_profile.py):
+//   SE(3), float:   1,024 uniform samples against a 200K-node tree (queries far from the tree) take 3 ms through the
+//                   tree and 0.2 ms scanned                                            -> scan up to 2^29 pairs
+//   planar / 3-D L2: PRRT* waves of 256 / 1,024 / 4,096 samples at 60K nodes: 0.60 / 0.90 / 1.89 ms scanned,
+//                   0.41 / 0.40 / 0.49 ms through the tree (boxes prune well in 2-3 dimensions)  -> scan up to 2^23 pairs
+//   8 scalars and more (N-link arms): boxes prune little; 4,096-sample PPRM waves at 100K nodes: 8-D 7.1 ms scanned,
+//                   7.3 ms tree; 16-D 19 ms scanned, 28 ms tree                        -> scan up to 2^36 pairs
+inline int knnAutoStrategy(uint32_t size, uint32_t Q, int shape, int scalars) {
     if (size < 16384u) return MPTG_KNN_BRUTE;
-    return (unsigned long long)size * Q <= (1ull << 29) ? MPTG_KNN_BRUTE : MPTG_KNN_BVH;
+    static const int forced = [] {  // MPTG_KNN_AUTO_LOG2_PAIRS: tuning experiments
+        const char* e = getenv("MPTG_KNN_AUTO_LOG2_PAIRS");
+        const int v = e ? atoi(e) : -1;
+        return v > 62 ? 62 : v;
+    }();
+    int log2Pairs = 29;
+    if (shape == SHAPE_L2_2 || shape == SHAPE_L2_3) log2Pairs = 23;
+    else if (shape == SHAPE_GENERIC && scalars >= 8) log2Pairs = 36;
+    if (forced >= 0) log2Pairs = forced;
+    return (unsigned long long)size * Q <= (1ull << log2Pairs) ? MPTG_KNN_BRUTE : MPTG_KNN_BVH;
 }
 
 // ------------------------------------------------------------------ lower bounds

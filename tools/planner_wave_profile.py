@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--algo", default="prrtstar", choices=["prrt", "prrtstar", "pprm"])
 ap.add_argument("--nodes", type=int, default=150_000)
 ap.add_argument("--wave", type=int, default=8192)
+ap.add_argument("--arm", type=int, default=0, help="N-link arm scene (PPRM) instead of the grid")
 args = ap.parse_args()
 
 ctx = m.Context(0)
@@ -27,6 +28,13 @@ grid = m.Scenario.grid(ctx, occ, m.F64)
 free = np.argwhere(occ == 0)
 start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
 lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
+if args.arm:
+    lengths, radius, circles = W.link_arm_scene(args.arm)
+    sp = m.lp_space(args.arm, 1, m.F64)
+    grid = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
+    cand = W.box_states(512, args.arm, 3, -np.pi, np.pi)
+    okc = grid.valid(cand) != 0
+    start, goal, lo, hi = cand[okc][0], cand[okc][1], -np.pi, np.pi
 if args.algo == "prrt":
     pl = m.DevicePRRT(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
     pl.add_start(start)
@@ -34,7 +42,7 @@ elif args.algo == "prrtstar":
     pl = m.DevicePRRTStar(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
     pl.add_start(start)
 else:
-    pl = m.DevicePPRM(grid, sp, lo, hi, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl = m.DevicePPRM(grid, sp, lo, hi, goal=goal, goal_radius=1e-6 if args.arm else 12.0, seed=17, capacity=1 << 18 if args.arm else 1 << 20, max_wave=args.wave)
     pl.add_start(start)
     pl.add_goal(goal)
 while pl.size < args.nodes:
