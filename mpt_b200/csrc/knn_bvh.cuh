@@ -34,14 +34,18 @@
 namespace mptg {
 
 // AUTO policy.  The tiled scan evaluates Q*N pairs at full machine width whatever the queries are; the tree visits
-// far fewer points but each query is a chain of dependent node fetches, which a small wave cannot hide.  Where the
-// two cross depends on the space (measured on B200 with planner waves, tools/planner_wave_profile.py):
-//   SE(3), float:   1,024 uniform samples against a 200K-node tree (queries far from the tree) take 3 ms through the
-//                   tree and 0.2 ms scanned                                            -> scan up to 2^29 pairs
-//   planar / 3-D L2: PRRT* waves of 256 / 1,024 / 4,096 samples at 60K nodes: 0.60 / 0.90 / 1.89 ms scanned,
-//                   0.41 / 0.40 / 0.49 ms through the tree (boxes prune well in 2-3 dimensions)  -> scan up to 2^23 pairs
+// far fewer points but each query is a chain of dependent node fetches, and the tree has to be rebuilt as the set
+// grows.  Measured on B200 (tools/knn_crossover.py: static sets, k = 16 and 1; tools/planner_wave_profile.py and the
+// demos: planner waves):
+//   planar L2, double: the tree wins from 1,024 points on for every wave size (16,384 points, 2,048 queries: 0.120 ms
+//                   scanned, 0.030 ms tree); PRRT* waves of 256 / 1,024 / 4,096 samples at 60K nodes: 0.60 / 0.90 /
+//                   1.89 ms scanned, 0.41 / 0.40 / 0.49 ms through the tree                 -> scan up to 2^23 pairs
+//   SE(3), float:   the tree wins for waves of >= 2,048 queries at every size, ties at 256 queries (65,536 points,
+//                   2,048 queries: 0.70 ms scanned, 0.24 ms tree); device-resident PRRT / PRRT* to 200K nodes:
+//                   3.4 / 1.3 M nodes/s with the old 2^29-pair rule, 5.1 / 1.9 M with 2^23..2^26 -> scan up to 2^24 pairs
 //   8 scalars and more (N-link arms): boxes prune little; 4,096-sample PPRM waves at 100K nodes: 8-D 7.1 ms scanned,
-//                   7.3 ms tree; 16-D 19 ms scanned, 28 ms tree                        -> scan up to 2^36 pairs
+//                   7.3 ms tree; 16-D 19 ms scanned, 28 ms tree                             -> scan up to 2^36 pairs
+// Below 16,384 points the scan stays: such sets are rebuilt every wave or two while a planner grows them.
 inline int knnAutoStrategy(uint32_t size, uint32_t Q, int shape, int scalars) {
     if (size < 16384u) return MPTG_KNN_BRUTE;
     static const int forced = [] {  // MPTG_KNN_AUTO_LOG2_PAIRS: tuning experiments
@@ -49,8 +53,9 @@ inline int knnAutoStrategy(uint32_t size, uint32_t Q, int shape, int scalars) {
         const int v = e ? atoi(e) : -1;
         return v > 62 ? 62 : v;
     }();
-    int log2Pairs = 29;
+    int log2Pairs = 26;
     if (shape == SHAPE_L2_2 || shape == SHAPE_L2_3) log2Pairs = 23;
+    else if (shape == SHAPE_SE3) log2Pairs = 24;
     else if (shape == SHAPE_GENERIC && scalars >= 8) log2Pairs = 36;
     if (forced >= 0) log2Pairs = forced;
     return (unsigned long long)size * Q <= (1ull << log2Pairs) ? MPTG_KNN_BRUTE : MPTG_KNN_BVH;
