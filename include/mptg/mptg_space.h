@@ -46,7 +46,7 @@ inline DevSpace<S> makeDevSpace(const mptg_space_desc& s) {
 }
 
 // compile-time shapes with a dedicated code path; everything else interprets DevSpace at run time
-enum SpaceShape { SHAPE_GENERIC = 0, SHAPE_SE3 = 1, SHAPE_L2_2 = 2, SHAPE_L2_3 = 3 };
+enum SpaceShape { SHAPE_GENERIC = 0, SHAPE_SE3 = 1, SHAPE_L2_2 = 2, SHAPE_L2_3 = 3, SHAPE_L1 = 4 };  // L1: one unweighted L1 part of any dimension (N-link arms)
 
 inline SpaceShape classifySpace(const mptg_space_desc& s) {
     if (s.n_parts == 2 && s.part[0].kind == MPTG_PART_SO3 && s.part[1].kind == MPTG_PART_LP && s.part[1].p == 2 &&
@@ -56,6 +56,7 @@ inline SpaceShape classifySpace(const mptg_space_desc& s) {
         if (s.part[0].dim == 2) return SHAPE_L2_2;
         if (s.part[0].dim == 3) return SHAPE_L2_3;
     }
+    if (s.n_parts == 1 && s.part[0].kind == MPTG_PART_LP && s.part[0].p == 1 && s.part[0].weight == 1.0) return SHAPE_L1;
     return SHAPE_GENERIC;
 }
 

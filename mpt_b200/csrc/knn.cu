@@ -71,9 +71,10 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteKernel(const BruteAr
     top.init(a.k);
 
     // prefilter threshold on the squared translation distance (fast paths): skip when surely d > thr
-    S thr2 = fp::consts<S>::inf();
+    S thr2 = fp::consts<S>::inf(), thr1 = fp::consts<S>::inf();
     auto refreshThr = [&]() {
         S thr = top.kthD < a.radius ? top.kthD : a.radius;
+        thr1 = thr;
         if (SHAPE == SHAPE_SE3 && a.sp.weighted[1]) thr = fp::div_(thr, a.sp.weight[1]) * (S(1) + S(8) * fp::consts<S>::eps());
         S t2 = thr * thr;
         thr2 = t2 + t2 * (S(16) * fp::consts<S>::eps());  // generous slack: sqrt/round can only shrink d by < 1 ulp
@@ -124,6 +125,15 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteKernel(const BruteAr
                 cand = cand && s <= thr2;
                 if (!__any_sync(FULL_MASK, cand)) continue;
                 dist = fp::sqrt_(s);
+            } else if (SHAPE == SHAPE_L1) {
+                // one L1 part of any dimension (the N-link arm's space): the sum in the order of mptg_space.h
+                // (partDistance, p == 1), and the sum itself is the prefilter
+                S acc = fp::abs_(tile[pp] - myq[0]);
+#pragma unroll 4
+                for (int c = 1; c < D; ++c) acc = acc + fp::abs_(tile[(size_t)c * a.tile + pp] - myq[c]);
+                cand = cand && acc <= thr1;
+                if (!__any_sync(FULL_MASK, cand)) continue;
+                dist = acc;
             } else {
                 dist = dev::distance<S>(
                     a.sp, [&](int c) { return tile[(size_t)c * a.tile + pp]; }, [&](int c) { return myq[c]; });
@@ -369,6 +379,7 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
         case SHAPE_SE3: rc = launchBruteShape<S, SHAPE_SE3>(ctx, a, grid, smem); break;
         case SHAPE_L2_2: rc = launchBruteShape<S, SHAPE_L2_2>(ctx, a, grid, smem); break;
         case SHAPE_L2_3: rc = launchBruteShape<S, SHAPE_L2_3>(ctx, a, grid, smem); break;
+        case SHAPE_L1: rc = launchBruteShape<S, SHAPE_L1>(ctx, a, grid, smem); break;
         default: rc = launchBruteShape<S, SHAPE_GENERIC>(ctx, a, grid, smem); break;
     }
     if (rc) return rc;

@@ -56,7 +56,7 @@ inline int knnAutoStrategy(uint32_t size, uint32_t Q, int shape, int scalars) {
     int log2Pairs = 26;
     if (shape == SHAPE_L2_2 || shape == SHAPE_L2_3) log2Pairs = 23;
     else if (shape == SHAPE_SE3) log2Pairs = 24;
-    else if (shape == SHAPE_GENERIC && scalars >= 8) log2Pairs = 36;
+    else if ((shape == SHAPE_GENERIC || shape == SHAPE_L1) && scalars >= 8) log2Pairs = 36;
     if (forced >= 0) log2Pairs = forced;
     return (unsigned long long)size * Q <= (1ull << log2Pairs) ? MPTG_KNN_BRUTE : MPTG_KNN_BVH;
 }
