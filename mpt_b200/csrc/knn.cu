@@ -280,6 +280,7 @@ struct mptg_knn {
     uint64_t stats[4] = {0, 0, 0, 0};
     KnnIndex index;  // knn_bvh.cuh
     KnnTail tail;    // knn_index.cuh: Morton-sorted leaves over the points inserted since the tree was built
+    bool sawKnn = false;  // a search with k > 1 has been made on this set (PRRT*, PPRM: every wave will make another)
 };
 
 namespace {
@@ -417,7 +418,9 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
     const uint32_t rawBegin = indexed + tl.covered;
     // 1-NN waves (PRRT) scan a raw tail faster than they could sort it into leaves: the exhaustive 1-NN scan costs
     // ~3 us per 1,000 tail points and 8,192 queries, a chunk ~100 us to build; k-NN waves (PRRT*, PPRM) are the other way
-    if (knn->size - rawBegin >= TAIL_MIN_CHUNK && (k > 1 || knn->size - rawBegin >= 32768u)) {
+    // A set that is also searched with k > 1 (PRRT*: 1-NN then k-NN in every wave) sorts its new points at the first search.
+    if (k > 1) knn->sawKnn = true;
+    if (knn->size - rawBegin >= TAIL_MIN_CHUNK && (knn->sawKnn || knn->size - rawBegin >= 32768u)) {
         if (int rc = knnTailAppend(ctx, tl, knn->space, (const S*)knn->pts, knn->stride, rawBegin, knn->size - rawBegin)) return rc;
     }
     const bool useLeaves = tl.nLeaves > 0;

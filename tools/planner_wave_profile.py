@@ -19,6 +19,7 @@ ap.add_argument("--algo", default="prrtstar", choices=["prrt", "prrtstar", "pprm
 ap.add_argument("--nodes", type=int, default=150_000)
 ap.add_argument("--wave", type=int, default=8192)
 ap.add_argument("--arm", type=int, default=0, help="N-link arm scene (PPRM) instead of the grid")
+ap.add_argument("--se3", action="store_true", help="SE(3) rigid body among meshes (float32) instead of the grid")
 args = ap.parse_args()
 
 ctx = m.Context(0)
@@ -35,11 +36,20 @@ if args.arm:
     cand = W.box_states(512, args.arm, 3, -np.pi, np.pi)
     okc = grid.valid(cand) != 0
     start, goal, lo, hi = cand[okc][0], cand[okc][1], -np.pi, np.pi
+rng_ = 200.0
+if args.se3:
+    sp = m.se3_space(50, 1)
+    robot, env, vmin, vmax = W.alpha_puzzle_like()
+    grid = m.Scenario.mesh_pair(ctx, robot, env, sp, W.se3_step_size(vmin, vmax))
+    cand = W.se3_states(256, 5, -45.0, 45.0)
+    okc = grid.valid(cand) != 0
+    start, goal = cand[okc][0], cand[okc][1]
+    lo, hi, rng_ = [0, 0, 0, 0, -45, -45, -45], [0, 0, 0, 0, 45, 45, 45], 40.0
 if args.algo == "prrt":
-    pl = m.DevicePRRT(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl = m.DevicePRRT(grid, sp, lo, hi, range=rng_, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
     pl.add_start(start)
 elif args.algo == "prrtstar":
-    pl = m.DevicePRRTStar(grid, sp, lo, hi, range=200.0, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
+    pl = m.DevicePRRTStar(grid, sp, lo, hi, range=rng_, goal=goal, goal_radius=12.0, seed=17, capacity=1 << 20, max_wave=args.wave)
     pl.add_start(start)
 else:
     pl = m.DevicePPRM(grid, sp, lo, hi, goal=goal, goal_radius=1e-6 if args.arm else 12.0, seed=17, capacity=1 << 18 if args.arm else 1 << 20, max_wave=args.wave)
