@@ -14,6 +14,10 @@
 //     inputs are committed as tests/golden/reference_golden.npz (tests/test_reference_parity.py).
 //     Decisions are identical; interpolated quaternions agree to libm tolerance (the reference calls
 //     libm, we call mptg_fpmath.h).
+//   * planner loops (PRRT, PRRT*, PPRM -- src/mpt/impl/{prrt,prrt_star,pprm}): PINNED against the reference's own
+//     planner classes, compiled from /root/reference against the same stand-ins plus an exhaustive-scan Nigh
+//     (oracle/ref_planner.cpp, tests/cpp/reference_planner_parity.cpp): same random stream in, identical trees /
+//     roadmaps / solution paths / PRRT* costs out at one sample per wave (golden trees in reference_golden.npz).
 //   * kNN result order and mesh-mesh collision: PARITY UNPINNED -- the arithmetic lives in Nigh and
 //     FCL, which are not in /root/reference and not on this machine.  The oracle defines them:
 //     kNN = exact total order by (distance, insertion index); mesh = AABB-overlap && 17-axis
