@@ -301,6 +301,11 @@ int mptg_pprm_get_graph(mptg_pprm* pprm, uint32_t first, uint32_t count, void* s
  * (:664-688).  Parameters as for mptg_prrt_create plus Planner::setRewireFactor() (default of the reference 1.1). */
 typedef struct mptg_prrtstar mptg_prrtstar;
 int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params* params, double rewire_factor, mptg_prrtstar** out);
+/* rewire_r_nearest (rrg_rewire_neighbors.hpp:102-128): the neighbourhood of a new node is everything within
+ * r(n) = r_rrg (ln(n+1) / (n+1))^(1/d), at most MPTG_MAX_K nodes, instead of the k nearest.  r_rrg = rewire_factor
+ * (2 (1 + 1/d) measure / unit_ball_d)^(1/d) is computed by the caller, who knows the measure of the sampled region.
+ * Before the first wave only. */
+int mptg_prrtstar_set_rewire_radius(mptg_prrtstar* star, double r_rrg);
 int mptg_prrtstar_destroy(mptg_prrtstar* star);
 int mptg_prrtstar_add_start(mptg_prrtstar* star, const void* state);
 /* goal_node_out: the goal node of smallest cost so far (Planner::solution() / solutionCost(), :317-337), MPTG_NO_INDEX

@@ -999,8 +999,8 @@ public:
 
 // ------------------------------------------------------------------ device-resident PRRT* 
 // Planner<Scenario, PRRTStar<device_resident, ...>>: tree, costs, parent choice and rewiring on the GPU (mptg_prrtstar_*,
-// wave-parallel semantics stated in mptg.h); the k-nearest rewiring variant.
-template <typename Scenario, int waveSize, int maxNodes, bool reportStats>
+// wave-parallel semantics stated in mptg.h); k-nearest rewiring, or radius rewiring with rewire_r_nearest.
+template <typename Scenario, int waveSize, int maxNodes, bool reportStats, bool rNearest = false>
 class DevicePRRTStar {
     using Space = typename Scenario::Space;
     using State = typename Space::Type;
@@ -1036,6 +1036,14 @@ class DevicePRRTStar {
         prm.goal_bias = (double)goalBias_, prm.goal_state = g.data(), prm.goal_radius = (double)goal.radius();
         prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
         check(mptg_prrtstar_create(ctx_.get(), geom_.get(), &prm, (double)rewireFactor_, &prrt_), ctx_.get(), "mptg_prrtstar_create");
+        if constexpr (rNearest) {  // rrg_rewire_neighbors.hpp:102-122
+            const unsigned dim = scenario_.space().dimensions();
+            const Distance invDim = 1 / Distance(dim);
+            const Distance unitBall = std::pow(std::sqrt(impl::PI<Distance>), Distance(dim)) / std::tgamma(Distance(dim) / 2 + 1);
+            const UniformSampler<Space, std::decay_t<decltype(scenario_.bounds())>> sampler(scenario_.space(), scenario_.bounds());
+            const Distance rRRG = rewireFactor_ * std::pow(2 * (1 + invDim) * sampler.measure() / unitBall, invDim);
+            check(mptg_prrtstar_set_rewire_radius(prrt_, (double)rRRG), ctx_.get(), "mptg_prrtstar_set_rewire_radius");
+        }
         for (const State& q : starts_) check(mptg_prrtstar_add_start(prrt_, q.data()), ctx_.get(), "mptg_prrtstar_add_start");
         size_ = (std::uint32_t)starts_.size();
     }
@@ -1322,10 +1330,9 @@ struct PlannerResolver<Scenario, PRRTStar<Options...>> {
     static constexpr bool rNearest = pack_contains_v<rewire_r_nearest, Options...>;
     static_assert(!(kNearest && rNearest), "RRT* tags cannot include both k_nearest and r_nearest");
     using Rewire = std::conditional_t<!rNearest, rewire_k_nearest, rewire_r_nearest>;
-    static_assert(!(pack_contains_v<device_resident, Options...> && rNearest), "the device-resident PRRT* implements k-nearest rewiring");
     using type = std::conditional_t<pack_contains_v<device_resident, Options...>,
                                     DevicePRRTStar<Scenario, pack_int_tag_v<wave_size, 16384, Options...>, pack_int_tag_v<max_nodes, 1 << 21, Options...>,
-                                                   pack_bool_tag_v<report_stats, false, Options...>>,
+                                                   pack_bool_tag_v<report_stats, false, Options...>, rNearest>,
                                     WavePRRTStar<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, Rewire, pack_bool_tag_v<report_stats, false, Options...>>>;
 };
 template <typename Scenario, typename... Options>

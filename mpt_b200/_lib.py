@@ -106,6 +106,7 @@ SYMBOLS = {
     "mptg_prrt_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P]),
     "mptg_prrtstar_create": (C.c_int, [_P, _P, _P, C.c_double, C.POINTER(_P)]),
     "mptg_prrtstar_destroy": (C.c_int, [_P]),
+    "mptg_prrtstar_set_rewire_radius": (C.c_int, [_P, C.c_double]),
     "mptg_prrtstar_add_start": (C.c_int, [_P, _P]),
     "mptg_prrtstar_wave": (C.c_int, [_P, _U32, _U32P, _U32P]),
     "mptg_prrtstar_size": (_U32, [_P]),

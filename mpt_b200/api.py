@@ -310,7 +310,9 @@ class DevicePRRTStar(DevicePRRT):
     """Device-resident PRRT* (mptg_prrtstar_*): Planner<Scenario, PRRTStar> with tree, costs and rewiring on the GPU."""
 
     def __init__(self, scenario: "Scenario", space: Space, lo, hi, *, range: float = float("inf"), goal=None, goal_radius: float = 0.0,
-                 goal_bias: float = 0.01, rewire_factor: float = 1.1, seed: int = 1, capacity: int = 1 << 20, max_wave: int = 1 << 14):
+                 goal_bias: float = 0.01, rewire_factor: float = 1.1, rewire_radius: float | None = None, seed: int = 1, capacity: int = 1 << 20,
+                 max_wave: int = 1 << 14):
+        """rewire_radius: r_rrg of rewire_r_nearest (mptg_prrtstar_set_rewire_radius); None = k-nearest rewiring."""
         self.ctx, self.scenario, self.space = scenario.ctx, scenario, space
         self._lo, self._hi = _bounds(space, lo, hi)
         self._goal = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
@@ -319,6 +321,8 @@ class DevicePRRTStar(DevicePRRT):
                            int(seed), int(capacity), int(max_wave))
         self.h = C.c_void_p()
         L.check(self.ctx.lib.mptg_prrtstar_create(self.ctx.h, scenario.h, C.byref(prm), float(rewire_factor), C.byref(self.h)), self.ctx.h)
+        if rewire_radius is not None:
+            L.check(self.ctx.lib.mptg_prrtstar_set_rewire_radius(self.h, float(rewire_radius)), self.ctx.h)
         self.goal_node = L.NO_INDEX
 
     def add_start(self, state):

@@ -1121,7 +1121,7 @@ struct mptg_prrtstar {
     mptg_knn* knn = nullptr;  // owned
     mptg_space_desc space{};
     int D = 0, scalar = MPTG_F32, dims = 0;
-    double range = 0, goalBias = 0, goalRadius = 0, linkStep = 0, rewireFactor = 1.1;
+    double range = 0, goalBias = 0, goalRadius = 0, linkStep = 0, rewireFactor = 1.1, rRRG = 0;  // rRRG > 0: radius rewiring
     bool hasGoal = false;
     uint64_t seed = 0, drawn = 0, waves = 0, rewires = 0;
     uint32_t capacity = 0, size = 0, maxWave = 0, stride = 0, goalNode = MPTG_NO_INDEX;
@@ -1175,6 +1175,31 @@ int starSelect(mptg_prrtstar* p, const uint8_t* flags, size_t n, uint32_t* out, 
     return MPTG_OK;
 }
 
+// the buffers whose size depends on the neighbour-row stride (k-nearest: k at capacity; radius rewiring: MPTG_MAX_K)
+int starAllocNeighbourBuffers(mptg_prrtstar* p) {
+    mptg_ctx* ctx = p->ctx;
+    for (void** q : {&p->nnDist, &p->eFrom, &p->eTo, (void**)&p->nnIdx, (void**)&p->ids, (void**)&p->inv, (void**)&p->order, (void**)&p->flag,
+                     (void**)&p->checked, (void**)&p->okEdge, &p->selTemp}) {
+        if (*q) cudaFree(*q);
+        *q = nullptr;
+    }
+    const size_t sb = (size_t)p->D * p->scalar, W = p->maxWave, K = p->stride, sc = p->scalar;
+    int rc = MPTG_OK;
+    auto alloc = [&](auto** q, size_t bytes) {
+        if (rc) return;
+        cudaError_t e = cudaMalloc((void**)q, bytes ? bytes : 16);
+        if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_prrtstar: %s", cudaGetErrorString(e));
+    };
+    alloc(&p->nnIdx, W * K * 4), alloc(&p->nnDist, W * K * sc);
+    alloc(&p->order, W * K), alloc(&p->flag, W * K), alloc(&p->checked, W * K), alloc(&p->okEdge, W * K);
+    alloc(&p->ids, W * K * 4), alloc(&p->inv, W * K * 4), alloc(&p->eFrom, W * K * sb), alloc(&p->eTo, W * K * sb);
+    if (!rc) {
+        cub::DeviceSelect::Flagged(nullptr, p->selBytes, thrust::counting_iterator<uint32_t>(0), p->flag, p->ids, p->nSel, (int)(W * K));
+        alloc(&p->selTemp, p->selBytes);
+    }
+    return rc;
+}
+
 template <typename S>
 int starWaveT(mptg_prrtstar* p, uint32_t W) {
     mptg_ctx* ctx = p->ctx;
@@ -1205,8 +1230,14 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
     MPTG_LAUNCHED(ctx);
     // neighbourhoods (:559-562)
     uint32_t k = starK<S>(p->rewireFactor, p->dims, p->size);
+    double radius = -1.0;
+    if (p->rRRG > 0) {  // rewire_r_nearest (rrg_rewire_neighbors.hpp:102-128): everything within r(n), at most MPTG_MAX_K
+        const S n1 = (S)(p->size + 1.0);
+        radius = (double)((S)p->rRRG * std::pow(std::log(n1) / n1, S(1) / (S)p->dims));
+        k = p->stride;
+    }
     if (k > p->stride) k = p->stride;
-    if (int rc = mptg_knn_query_dev(p->knn, p->fresh, nS, k, -1.0, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
+    if (int rc = mptg_knn_query_dev(p->knn, p->fresh, nS, k, radius, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
     starRankKernel<S><<<(nS + 3) / 4, 128, 0, st>>>(nS, k, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->nearOf, (const S*)p->dOf, (const S*)p->cost,
                                                    p->order, p->flag, p->checked, p->limit, p->nearRank, (S*)p->defCost);
     MPTG_LAUNCHED(ctx);
@@ -1288,7 +1319,7 @@ int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params*
     p->seed = prm->seed, p->capacity = prm->capacity, p->maxWave = prm->max_wave, p->hasGoal = prm->goal_state != nullptr;
     const uint32_t kFull = p->scalar == MPTG_F32 ? starK<float>(rewire_factor, p->dims, p->capacity) : starK<double>(rewire_factor, p->dims, p->capacity);
     p->stride = kFull < MPTG_MAX_K ? kFull : MPTG_MAX_K;
-    const size_t sb = (size_t)p->D * p->scalar, W = p->maxWave, K = p->stride, sc = p->scalar;
+    const size_t sb = (size_t)p->D * p->scalar, W = p->maxWave, sc = p->scalar;
     int rc = mptg_knn_create(ctx, prm->space, p->capacity, &p->knn);
     if (!rc) rc = uploadBounds(ctx, prm->space, prm->lo, prm->hi, &p->bounds);
     auto alloc = [&](auto** q, size_t bytes) {
@@ -1304,13 +1335,8 @@ int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params*
     alloc(&p->nearIdx, W * 4), alloc(&p->nearCnt, W * 4), alloc(&p->sel, W * 4), alloc(&p->nearOf, W * 4), alloc(&p->limit, W * 4), alloc(&p->nearRank, W * 4);
     alloc(&p->nSel, 4), alloc(&p->result, 8);
     alloc(&p->alive, W), alloc(&p->okValid, W), alloc(&p->okLink, W), alloc(&p->keep, W);
-    alloc(&p->nnIdx, W * K * 4), alloc(&p->nnDist, W * K * sc), alloc(&p->nnCnt, W * 4);
-    alloc(&p->order, W * K), alloc(&p->flag, W * K), alloc(&p->checked, W * K), alloc(&p->okEdge, W * K);
-    alloc(&p->ids, W * K * 4), alloc(&p->inv, W * K * 4), alloc(&p->eFrom, W * K * sb), alloc(&p->eTo, W * K * sb);
-    if (!rc) {
-        cub::DeviceSelect::Flagged(nullptr, p->selBytes, thrust::counting_iterator<uint32_t>(0), p->flag, p->ids, p->nSel, (int)(W * K));
-        alloc(&p->selTemp, p->selBytes);
-    }
+    alloc(&p->nnCnt, W * 4);
+    if (!rc) rc = starAllocNeighbourBuffers(p);
     if (!rc && p->hasGoal) {
         alloc(&p->goal, sb);
         if (!rc) rc = uploadSync(ctx, p->goal, prm->goal_state, sb);
@@ -1322,6 +1348,18 @@ int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params*
         return rc;
     }
     *out = p;
+    return MPTG_OK;
+}
+
+int mptg_prrtstar_set_rewire_radius(mptg_prrtstar* p, double r_rrg) {
+    if (!p || !(r_rrg > 0)) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_prrtstar_set_rewire_radius: bad argument");
+    if (p->waves != 0) return fail(p->ctx, MPTG_ERR_BAD_ARG, "mptg_prrtstar_set_rewire_radius: must be called before the first wave");
+    MPTG_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
+    p->rRRG = r_rrg;
+    if (p->stride != MPTG_MAX_K) {
+        p->stride = MPTG_MAX_K;
+        return starAllocNeighbourBuffers(p);
+    }
     return MPTG_OK;
 }
 

@@ -118,6 +118,8 @@ int main() {
     testSolvingBasicScenario<PRRT<device_resident, report_stats<true>, wave_size<4096>, max_nodes<(1 << 18)>>>("PRRT device-resident");
     static_assert(!std::is_same_v<Planner<S, PRRTStar<device_resident>>, Planner<S, PRRTStar<>>>);
     testSolvingBasicScenario<PRRTStar<device_resident, report_stats<true>, wave_size<2048>, max_nodes<(1 << 17)>>>("PRRT* device-resident");
+    static_assert(!std::is_same_v<Planner<S, PRRTStar<device_resident, rewire_r_nearest>>, Planner<S, PRRTStar<device_resident>>>);
+    testSolvingBasicScenario<PRRTStar<device_resident, rewire_r_nearest, wave_size<2048>, max_nodes<(1 << 17)>>>("PRRT* device-resident r-nearest");
     {   // cost(node) == cost(parent) + distance(parent, node) up to rounding after wave-parallel rewiring; rewiring happened
         using Scenario = test::BasicScenario<double, 3>;
         Planner<Scenario, PRRTStar<device_resident, wave_size<1024>, max_nodes<(1 << 16)>>> planner(Scenario(), 99);

@@ -218,7 +218,7 @@ def prrtstar_k(space, rewire_factor, n):
     return max(1, int(np.ceil(k_rrg * np.log(dt(n + 1.0)))))
 
 
-def replay_prrtstar(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, rewire_factor, seed, waves, W, stride):
+def replay_prrtstar(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias, rng, rewire_factor, seed, waves, W, stride, r_rrg=None):
     """The wave-parallel PRRT* of include/mptg/mptg.h (mptg_prrtstar_*) restated on the oracle: Worker::addSample of
     src/mpt/impl/prrt_star/prrt_star.hpp:510-657 per sample against the tree at the start of the wave; rewiring offers
     evaluated on the costs before the wave's rewiring step, best valid offer per node, applied at once, decreases
@@ -245,7 +245,12 @@ def replay_prrtstar(oracle, og, sp, lo, hi, start, goal, goal_radius, goal_bias,
             continue
         n0 = tree.shape[0]
         k = min(prrtstar_k(sp, rewire_factor, n0), stride)
-        nidx, ndist, ncnt = oracle.knn(sp, tree, fresh, k)
+        radius = -1.0
+        if r_rrg is not None:  # rewire_r_nearest (src/mpt/impl/rrg_rewire_neighbors.hpp:102-128)
+            n1 = dt(n0 + 1.0)
+            radius = float(dt(r_rrg) * np.power(np.log(n1) / n1, dt(1) / dt(sp.dimensions)))
+            k = stride
+        nidx, ndist, ncnt = oracle.knn(sp, tree, fresh, k, radius)
         c0 = np.asarray(cost, dtype=dt)
         # candidate parents in cost + distance order up to the near node or the cut-off, one link batch
         orders, cands = [], []

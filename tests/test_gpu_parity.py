@@ -528,13 +528,16 @@ def test_device_prrtstar_replays_its_wave_semantics_on_the_oracle(ctx, oracle):
     free = np.argwhere(occ == 0)
     start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
     lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
-    for rng, waves, W_ in ((30.0, 8, 256), (float("inf"), 4, 200), (40.0, 300, 1)):
-        pl = m.DevicePRRTStar(sc, sp, lo, hi, range=rng, goal=goal, goal_radius=12.0, goal_bias=0.05, seed=31, capacity=8192, max_wave=256)
+    # radius rewiring: r_rrg = rewireFactor (2 (1 + 1/d) measure / unit_ball)^(1/d) (rrg_rewire_neighbors.hpp:102-122), d = 2
+    r_rrg = 1.1 * (2 * 1.5 * (occ.shape[1] - 1) * (occ.shape[0] - 1) / np.pi) ** 0.5
+    for rng, waves, W_, rr in ((30.0, 8, 256, None), (float("inf"), 4, 200, None), (40.0, 300, 1, None), (30.0, 8, 256, r_rrg)):
+        pl = m.DevicePRRTStar(sc, sp, lo, hi, range=rng, goal=goal, goal_radius=12.0, goal_bias=0.05, rewire_radius=rr, seed=31, capacity=8192,
+                              max_wave=256)
         pl.add_start(start)
         for _ in range(waves):
             pl.wave(W_)
         st, pa, co = pl.tree(with_costs=True)
-        ws, wp, wc, wg, wr = kats.replay_prrtstar(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 1.1, 31, waves, W_, 128)
+        ws, wp, wc, wg, wr = kats.replay_prrtstar(oracle, og, sp, lo, hi, start, goal, 12.0, 0.05, rng, 1.1, 31, waves, W_, 128, rr)
         assert st.shape[0] > 50 and np.array_equal(st, ws), (rng, st.shape, ws.shape)
         assert np.array_equal(pa, wp), f"{(pa != wp).sum()} parents differ"
         assert np.array_equal(co, wc), f"{(co != wc).sum()} costs differ, max {np.abs(co - wc).max()}"

@@ -63,7 +63,7 @@ def test_wave_planners_on_gpu():
     if not prog.exists():
         build_host.build()
     out = _run(prog)
-    for name in ("PRRT:", "PRRT device-resident:", "PRRT* device-resident:", "PRRT* device-resident invariants:", "PPRM device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
+    for name in ("PRRT:", "PRRT device-resident:", "PRRT* device-resident:", "PRRT* device-resident r-nearest:", "PRRT* device-resident invariants:", "PPRM device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
         assert f"PASS {name}" in out
 
 
