@@ -176,74 +176,6 @@ __global__ void __launch_bounds__(256) knnMergeKernel(uint32_t parts, uint32_t Q
     if (countOut && lane == 0) countOut[q] = count;
 }
 
-// ---------------------------------------------------------------------------------------------
-// search of the tail's Morton-sorted leaves (KnnTail, knn_index.cuh): one warp per query walks the flat list of leaf
-// boxes 32 at a time and visits the leaves whose lower bound is within the threshold.  `cap` (optional, [Q][k]
-// distances of the tree search of the same queries) bounds the search from the start: a tail point farther than the
-// tree's k-th neighbour cannot be among the k nearest of the union.
-// ---------------------------------------------------------------------------------------------
-template <typename S>
-struct TailArgs {
-    const S* leafPts;
-    const uint32_t* perm;
-    const S* box;
-    uint32_t nLeaves;
-    const S* queries;
-    const S* cap;
-    uint32_t Q, k;
-    S radius;
-    uint32_t idxMul, idxAdd;
-    uint32_t* idxOut;
-    S* distOut;
-    DevSpace<S> sp;
-};
-
-template <typename S, int KPL>
-__global__ void __launch_bounds__(256) knnTailKernel(const TailArgs<S> a) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    S* qsm = reinterpret_cast<S*>(smemRaw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int D = a.sp.D;
-    const uint32_t q = blockIdx.x * 8 + warp;
-    if (q >= a.Q) return;
-    S* myq = qsm + warp * D;
-    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
-    __syncwarp();
-    S radius = a.radius;
-    if (a.cap) {
-        const S c = a.cap[(size_t)q * a.k + (a.k - 1)];  // +inf when the tree returned fewer than k
-        radius = c < radius ? c : radius;
-    }
-    WarpTopK<S, KPL> top;
-    top.init(a.k);
-    const uint32_t nBlocks = (a.nLeaves + 31u) / 32u;
-    for (uint32_t b = 0; b < nBlocks; ++b) {
-        const uint32_t leaf = b * 32u + (uint32_t)lane;
-        uint32_t key = BVH_DEAD;
-        if (leaf < a.nLeaves) {
-            const S* bx = a.box + ((size_t)b * (size_t)(2 * D)) * 32u + lane;
-            key = boundKey<S>(dev::boxLowerBound<S>(
-                a.sp, [&](int c) { return __ldg(bx + c * 32); }, [&](int c) { return __ldg(bx + (D + c) * 32); }, [&](int c) { return myq[c]; }));
-        }
-        S thr = top.kthD < radius ? top.kthD : radius;
-        unsigned m = __ballot_sync(FULL_MASK, __uint_as_float(key) <= thrAsFloat<S>(thr));
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1u;
-            const uint32_t lkey = __shfl_sync(FULL_MASK, key, src);
-            if (__uint_as_float(lkey) > thrAsFloat<S>(thr)) continue;  // the threshold has shrunk since the vote
-            const uint32_t node = b * 32u + (uint32_t)src;
-            const uint32_t orig = __ldg(a.perm + (size_t)node * 32u + lane);
-            const S* pt = a.leafPts + ((size_t)node * (size_t)D) * 32u + lane;
-            const S dist = dev::distance<S>(
-                a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
-            top.offer(orig != MPTG_NO_INDEX, dist, orig * a.idxMul + a.idxAdd, radius, lane);
-            thr = top.kthD < radius ? top.kthD : radius;
-        }
-    }
-    top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
-}
-
 // AoS -> SoA append
 template <typename S>
 __global__ void knnScatterKernel(const S* aos, uint32_t count, int D, S* pts, uint32_t stride, uint32_t first) {
@@ -397,11 +329,15 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
     int strategy = knn->strategy;
     if (strategy == MPTG_KNN_AUTO) strategy = knnAutoStrategy(knn->size, Q, (int)knn->shape, knn->D);
     uint32_t indexed = 0;
+    static const bool debug = getenv("MPTG_DEBUG_KNN") != nullptr;
     if (strategy == MPTG_KNN_BVH) {
+        const uint64_t before = knn->index.builds;
         int rc = knnEnsureIndex<S>(ctx, knn->index, knn->space, (const S*)knn->pts, knn->stride, knn->size);
         if (rc) return rc;
         indexed = knn->index.count;
+        if (debug && knn->index.builds != before) fprintf(stderr, "[knn] rebuilt the tree over %u points (build %llu)\n", indexed, (unsigned long long)knn->index.builds);
     }
+    if (debug) fprintf(stderr, "[knn] query Q=%u k=%u size=%u strategy=%d indexed=%u tail leaves=%u covered=%u\n", Q, k, knn->size, strategy, indexed, knn->tail.nLeaves, knn->tail.covered);
     knn->stats[2] = indexed;
     knn->stats[3] = (uint64_t)strategy;
     if (indexed == 0) return bruteScan<S>(knn, 0, knn->size, queries, Q, k, radius, idxOut, distOut, countOut);
@@ -443,18 +379,25 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
     if (rc) return rc;
     uint32_t slot = 1;
     if (useLeaves) {
-        TailArgs<S> a{};
-        a.leafPts = (const S*)tl.leafPts, a.perm = tl.perm, a.box = (const S*)tl.box, a.nLeaves = tl.nLeaves;
-        a.queries = queries, a.cap = d0, a.Q = Q, a.k = k;
+        BvhArgs<S> a{};
+        a.leafPts = (const S*)tl.leafPts, a.perm = tl.perm, a.box[0] = (const S*)tl.box, a.nNodes[0] = tl.nLeaves, a.top = 0;
+        a.queries = queries, a.Q = Q, a.k = k;
         a.radius = (radius >= 0 && radius == radius) ? (S)radius : fp::consts<S>::inf();
         a.idxMul = knn->idxMul, a.idxAdd = knn->idxAdd;
         a.idxOut = i0 + (size_t)slot * Q * k, a.distOut = d0 + (size_t)slot * Q * k;
         a.sp = makeDevSpace<S>(knn->space);
-        const dim3 grid((Q + 7) / 8), block(256);
-        const size_t smem = (size_t)8 * knn->D * sizeof(S);
-        if (k <= 32) knnTailKernel<S, 1><<<grid, block, smem, ctx->stream>>>(a);
-        else if (k <= 64) knnTailKernel<S, 2><<<grid, block, smem, ctx->stream>>>(a);
-        else knnTailKernel<S, 4><<<grid, block, smem, ctx->stream>>>(a);
+        const dim3 grid((Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
+        const size_t smem = (size_t)BVH_WARPS * knn->D * sizeof(S);
+        const bool se3 = knn->shape == SHAPE_SE3;
+#define MPTG_TAIL(KPL)                                                                                      \
+    do {                                                                                                    \
+        if (se3) knnTailKernel<S, SHAPE_SE3, KPL><<<grid, block, smem, ctx->stream>>>(a, d0);               \
+        else knnTailKernel<S, SHAPE_GENERIC, KPL><<<grid, block, smem, ctx->stream>>>(a, d0);               \
+    } while (0)
+        if (k <= 32) MPTG_TAIL(1);
+        else if (k <= 64) MPTG_TAIL(2);
+        else MPTG_TAIL(4);
+#undef MPTG_TAIL
         MPTG_LAUNCHED(ctx);
         knn->stats[0] += (uint64_t)tl.nLeaves * Q;  // box tests (an upper bound of the work; leaf visits are not counted)
         ++slot;

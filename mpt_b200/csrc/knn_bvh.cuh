@@ -212,15 +212,17 @@ struct BvhWalk {
     // Pruning threshold min(k-th distance, radius), cached as a float (rounded up) and refreshed after
     // every offer; thrS is the same value divided by the slack factor of the leaf prefilter.
     float thrF, thrS;
+    S rad;  // search radius of this query: a.radius, or tighter (tail search bounded by the tree's k-th distance)
     float dotC;  // 2 - slack - 2*qabs*errQ: prefilter term so that t = dotC - 2|dot_h| <= 2 - 2|dot|
     float eT;    // sqrt(3)*errT (rounded up): |t_h - q| - eT <= |t - q|
     __device__ __forceinline__ void refreshThr() {
-        const S t = top.kthD < a.radius ? top.kthD : a.radius;
+        const S t = top.kthD < rad ? top.kthD : rad;
         thrF = thrAsFloat<S>(t);
         thrS = thrF * (1.0f + 3e-5f);
     }
     __device__ __forceinline__ void start() {
         top.init(a.k);
+        rad = a.radius;
         refreshThr();
         dotC = __fmaf_rn(-2.0f * qabs, a.errQ, 2.0f - 3e-6f);
         eT = a.errT * 1.73206f;  // sqrt(3) * (1 + 5e-6)
@@ -320,11 +322,11 @@ struct BvhWalk {
             if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
             float dt = fp::sqrt_(s2);
             if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
-            top.offer(maybe, (S)(dr + dt), orig * a.idxMul + a.idxAdd, a.radius, lane);
+            top.offer(maybe, (S)(dr + dt), orig * a.idxMul + a.idxAdd, rad, lane);
         } else {
             const S dist = dev::distance<S>(
                 a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
-            top.offer(have, dist, orig * a.idxMul + a.idxAdd, a.radius, lane);
+            top.offer(have, dist, orig * a.idxMul + a.idxAdd, rad, lane);
         }
         refreshThr();
     }
@@ -363,7 +365,7 @@ struct BvhWalk {
         if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
         float dt = fp::sqrt_(s2);
         if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
-        top.offer(maybe && orig != MPTG_NO_INDEX, (S)(dr + dt), orig * a.idxMul + a.idxAdd, a.radius, lane);
+        top.offer(maybe && orig != MPTG_NO_INDEX, (S)(dr + dt), orig * a.idxMul + a.idxAdd, rad, lane);
         refreshThr();
     }
     // Prefilter on the half-precision copy.  With h = the stored copy: |dot - dot_h| <= qabs*errQ and
@@ -557,6 +559,50 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> 
         atomicAdd(a.stats + 3, w.cand);
 #endif
     }
+}
+
+// ---- search of the tail's Morton-sorted leaves (KnnTail, knn_index.cuh) with the same walker: args.box[0] / leafPts /
+// perm describe the flat list of 32-point leaves (args.nNodes[0] of them, no half-precision copies).  One warp per query
+// tests the leaf boxes 32 at a time and visits the leaves whose bound is within the threshold.  `cap` ([Q][k] distances
+// of the tree search of the same queries) bounds the search from the start: a tail point farther than the tree's k-th
+// neighbour cannot be among the k nearest of the union.
+template <typename S, int SHAPE, int KPL>
+__global__ void __launch_bounds__(BVH_WARPS * 32) knnTailKernel(const BvhArgs<S> a, const S* __restrict__ cap) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* qsm = reinterpret_cast<S*>(smemRaw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q = blockIdx.x * BVH_WARPS + warp;
+    if (q >= a.Q) return;
+    S* myq = qsm + warp * D;
+    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+    __syncwarp();
+    BvhWalk<S, SHAPE, KPL> w(a, myq, lane);
+    if (SHAPE == SHAPE_SE3) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
+        w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
+        w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
+    }
+    w.start();
+    if (cap) {
+        const S c = cap[(size_t)q * a.k + (a.k - 1)];  // +inf when the tree returned fewer than k
+        if (c < w.rad) w.rad = c;
+        w.refreshThr();
+    }
+    const uint32_t nBlocks = (a.nNodes[0] + 31u) / 32u;
+    for (uint32_t b = 0; b < nBlocks; ++b) {
+        const uint32_t key = w.template childKey<0>(b);
+        unsigned m = __ballot_sync(FULL_MASK, __uint_as_float(key) <= w.thrF);  // BVH_DEAD is a NaN pattern
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1u;
+            const uint32_t lkey = __shfl_sync(FULL_MASK, key, src);
+            if (__uint_as_float(lkey) > w.thrF) continue;  // the threshold has shrunk since the vote
+            w.leaf(b * 32u + (uint32_t)src);
+        }
+    }
+    w.top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
 }
 
 // ------------------------------------------------------------------ host: build
@@ -848,15 +894,18 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     return MPTG_OK;
 }
 
-// (Re)build when there is no index yet or the unindexed tail has grown past min(count/4, 65536) points;
-// in between the tail is scanned by brute force (knn.cu) and merged.  A device rebuild costs a few
-// milliseconds at a million points, a tail scan a few microseconds per thousand tail points and wave.
+// (Re)build when there is no index yet or the tail (points inserted since the build) has grown past
+// min(count/2, 131072) points.  In between the tail is searched through its Morton-sorted leaves (KnnTail) and, for the
+// newest points, by brute force (knn.cu), and merged.  Measured on planner waves (8,192 samples, 150K-node planar
+// roadmap): a wave costs 0.6 ms, a rebuild ~6 ms (sorts, allocation growth, one synchronisation) -- with the earlier
+// limit of min(count/4, 65536) a rebuild every seven waves cost more than the searches themselves, while the tail
+// search grows by only ~2 us per 1,000 tail points.
 template <typename S>
 int knnEnsureIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& sp, const S* pts, uint32_t stride, uint32_t n) {
     if (ix.count != 0 && ix.count <= n) {
         const uint32_t tail = n - ix.count;
-        uint32_t limit = ix.count / 4;
-        if (limit > 65536u) limit = 65536u;
+        uint32_t limit = ix.count / 2;
+        if (limit > TAIL_REBUILD_LIMIT) limit = TAIL_REBUILD_LIMIT;
         if (tail <= limit) return MPTG_OK;
     }
     return knnBuildIndex<S>(ctx, ix, sp, pts, stride, n);

@@ -31,7 +31,8 @@ struct KnnIndex {
 // between two searches is sorted along a Morton curve and cut into 32-point leaves with boxes -- a flat, one-level
 // index that costs one small sort to extend.  Planner waves insert thousands of points per wave and rebuild the tree
 // only every few waves; without this the exhaustive scan of the tail was half of a device-resident planner wave.
-constexpr uint32_t TAIL_MAX_POINTS = 65536 + 4096;  // the tree is rebuilt before the tail outgrows 65536 points
+constexpr uint32_t TAIL_REBUILD_LIMIT = 131072;                   // the tree is rebuilt before the tail outgrows this (knnEnsureIndex)
+constexpr uint32_t TAIL_MAX_POINTS = TAIL_REBUILD_LIMIT + 8192;  // room for the 32-point padding of every chunk
 constexpr uint32_t TAIL_MIN_CHUNK = 1024;           // fewer new points than this are scanned exhaustively
 struct KnnTail {
     uint32_t base = 0;      // first point covered (== index.count when valid)

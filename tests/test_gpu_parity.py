@@ -103,13 +103,13 @@ def test_knn_bvh_with_unindexed_tail(ctx, oracle):
     pts = W.se3_states(60_000, 9)
     q = W.se3_states(500, 10)
     nn = m.Nearest(ctx, sp, 65536, m.KNN_BVH)
-    nn.insert(pts[:40_000])
-    tree = oracle.tree(sp, pts[:40_000])
+    nn.insert(pts[:36_000])
+    tree = oracle.tree(sp, pts[:36_000])
     assert_knn_equal(nn.nearest(q, 16), tree.knn(q, 16))
-    nn.insert(pts[40_000:45_000])       # tail of 5000 < count/4: index kept, tail scanned
-    assert_knn_equal(nn.nearest(q, 16), oracle.tree(sp, pts[:45_000]).knn(q, 16))
-    assert nn.last_stats()["indexed"] == 40_000
-    nn.insert(pts[45_000:])             # tail of 20000 > count/4: rebuilt
+    nn.insert(pts[36_000:41_000])       # tail of 5000 <= count/2: index kept, tail searched separately
+    assert_knn_equal(nn.nearest(q, 16), oracle.tree(sp, pts[:41_000]).knn(q, 16))
+    assert nn.last_stats()["indexed"] == 36_000
+    nn.insert(pts[41_000:])             # tail of 24000 > count/2: rebuilt
     assert_knn_equal(nn.nearest(q, 16), oracle.tree(sp, pts).knn(q, 16))
     assert nn.last_stats()["indexed"] == 60_000
     nn.close()
