@@ -439,6 +439,7 @@ int mptg_knn_create(mptg_ctx* ctx, const mptg_space_desc* space, uint32_t capaci
     k->shape = classifySpace(*space);
     k->capacity = capacity;
     k->stride = ((capacity + 255u) / 256u) * 256u;
+    k->index.capacityHint = capacity;
     cudaError_t e = cudaMalloc(&k->pts, (size_t)D * k->stride * space->scalar);
     if (e != cudaSuccess) {
         delete k;

@@ -455,6 +455,12 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
         if (mem) MPTG_CUDA(ctx, cudaFree(mem));
         mem = nullptr;
         memBytes = bytes + bytes / 2;
+        if (ix.capacityHint > n) {  // every term of `bytes` is linear in n up to padding
+            double grow = (double)ix.capacityHint / (double)n;
+            if (grow > 8.0) grow = 8.0;  // a nearly empty store of huge capacity grows in a few steps instead
+            const size_t atCapacity = (size_t)((double)bytes * grow * 1.02) + (1u << 20);
+            if (atCapacity > memBytes) memBytes = atCapacity;
+        }
         MPTG_CUDA(ctx, cudaMalloc(&mem, memBytes));
     }
     unsigned long long* stats = ix.devStats;
@@ -484,7 +490,16 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     size_t wLo[BVH_MAXL], wHi[BVH_MAXL];
     for (int l = 0; l <= nx.top; ++l) wLo[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S)), wHi[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S));
     void* wbase;
-    if (int rc = scratch(ctx, 7, wbytes, &wbase)) return rc;
+    {
+        size_t want = wbytes;  // sized for the store's capacity the first time (see KnnIndex::capacityHint)
+        if (ix.capacityHint > n) {
+            double grow = (double)ix.capacityHint / (double)n;
+            if (grow > 8.0) grow = 8.0;
+            want = (size_t)((double)wbytes * grow * 1.02) + (1u << 20);
+        }
+        if (ctx->scratchBytes[7] >= wbytes) want = wbytes;
+        if (int rc = scratch(ctx, 7, want, &wbase)) return rc;
+    }
     char* W = (char*)wbase;
     float* canon = (float*)(W + wCanon);
     S* exact = sizeof(S) == 8 ? (S*)(W + wExact) : (S*)canon;  // what the emitted leaves and boxes are made of
@@ -570,6 +585,7 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     nx.memBytes = memBytes;
     nx.devStats = stats;
     nx.builds = ix.builds + 1;
+    nx.capacityHint = ix.capacityHint;
     nx.leafPts = M + oPts;
     nx.perm = (uint32_t*)(M + oPerm);
     for (int l = 0; l <= nx.top; ++l) nx.box[l] = M + oBox[l];

@@ -881,6 +881,7 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     nx.memBytes = memBytes;
     nx.devStats = stats;
     nx.builds = ix.builds + 1;
+    nx.capacityHint = ix.capacityHint;
     nx.leafPts = (char*)mem + oPts;
     nx.perm = (uint32_t*)((char*)mem + oPerm);
     for (int l = 0; l <= nx.top; ++l) nx.box[l] = (char*)mem + oBox[l];

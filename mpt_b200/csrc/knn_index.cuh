@@ -25,6 +25,9 @@ struct KnnIndex {
     float errQ = 0.f, errT = 0.f;  // max |half(v) - v| over the stored quaternion / translation coordinates
     unsigned long long* devStats = nullptr;  // [0] leaves visited, [1] inner nodes visited
     uint64_t builds = 0;
+    uint32_t capacityHint = 0;  // capacity of the store: the image and the build's work space are sized for it once, so that
+                                // rebuilding a growing set does not go through cudaFree / cudaMalloc (they stall for
+                                // milliseconds to hundreds of milliseconds on a busy host)
 };
 
 // Indexed part of the tail (points inserted since the last build of the tree): each batch of points that has arrived
