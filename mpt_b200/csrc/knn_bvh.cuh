@@ -191,7 +191,10 @@ __device__ __forceinline__ float se3CheapBound(float ad, float s, float w0, floa
     return __fmaf_rn(w0, sqrtApprox(t), w1 * sqrtApprox(s)) * (1.0f - 1e-5f);
 }
 
-constexpr int BVH_WARPS = 8;
+#ifndef MPTG_BVH_WARPS
+#define MPTG_BVH_WARPS 8
+#endif
+constexpr int BVH_WARPS = MPTG_BVH_WARPS;  // warps (queries) per CTA; 4 and 16 measured no faster than 8
 
 template <typename S, int SHAPE, int KPL>
 struct BvhWalk {
