@@ -298,7 +298,9 @@ def run_ours(args):
     eps = world * E_WAVE / (edge_ms * 1e-3)
     achieved = ALGO_BYTES_KNN / (knn_ms * 1e-3) / 1e9
     edge_flops = mesh_stats["bv_tests"] * F_BV + mesh_stats["prim_tests"] * F_TRI
-    fp32_peak = fp32_probe(torch, dev)
+    launches_before_probe = ctx.launches
+    fp32_peak = fp32_probe(ctx)
+    assert ctx.launches == launches_before_probe + 4
     line = {
         "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": knn_ms + edge_ms, "higher_is_better": True, "scaling": "weak",
@@ -321,7 +323,7 @@ def run_ours(args):
         "roofline_edges": {
             "kernel": "meshFlatKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,
             "unit": "TFLOP/s", "frac": edge_flops / (edge_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
-            "peak_source": "cuBLAS SGEMM 8192^3 (TF32 off) on this GPU, same run",
+            "peak_source": "FFMA microbenchmark of this library on this GPU, same run (mptg_probe_fp32_tflops)",
             "algorithmic_flops_per_launch": edge_flops, "bv_tests": mesh_stats["bv_tests"], "tri_tests": mesh_stats["prim_tests"],
             "states": mesh_stats["states"], "flop_per_bv_test": F_BV, "flop_per_tri_test": F_TRI,
             "traffic": measured_traffic("meshFlatKernel"),
@@ -379,29 +381,54 @@ def secondary(ctx, torch, dev, stream):
         arm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
         a, b = W.arm_edges(E_WAVE, n_links, 41, 0.5)
         out[f"link_arm_{n_links}_edges"] = time_link(arm, a, b)
-    # planar L2 kNN at a planner-realistic size (tiled scan) and at 1M (tree)
-    for n_pts, label, strat in ((1 << 14, "knn_l2_2d_16k_brute", m.KNN_BRUTE), (1 << 14, "knn_l2_2d_16k_auto", m.KNN_AUTO),
-                                (1 << 20, "knn_l2_2d_1m_tree", m.KNN_AUTO)):
-        sp = m.lp_space(2, 2, m.F32)
-        pts = W.box_states(n_pts, 2, 51, 0.0, [3976, 2603], np.float32)
-        q = W.box_states(Q_WAVE, 2, 52, 0.0, [3976, 2603], np.float32)
-        nn = m.Nearest(ctx, sp, n_pts, strat)
+    def time_knn(sp, pts, q, strat, np_dtype=np.float32):
+        nn = m.Nearest(ctx, sp, pts.shape[0], strat)
         nn.insert(pts)
         dq = torch.from_numpy(q).to(dev)
-        di = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
-        dd = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
+        di = torch.empty((q.shape[0], K_NN), dtype=torch.int32, device=dev)
+        dd = torch.empty((q.shape[0], K_NN), dtype=torch.float32 if np_dtype == np.float32 else torch.float64, device=dev)
         ts = []
         for it in range(7):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
                 e0.record(stream)
-                nn.nearest_dev(dq.data_ptr(), Q_WAVE, K_NN, -1.0, di.data_ptr(), dd.data_ptr())
+                nn.nearest_dev(dq.data_ptr(), q.shape[0], K_NN, -1.0, di.data_ptr(), dd.data_ptr())
                 e1.record(stream)
             ctx.sync()
             if it >= 2:
                 ts.append(e0.elapsed_time(e1))
-        out[label] = {"queries_per_s": Q_WAVE / (float(np.mean(ts)) * 1e-3), "ms": float(np.mean(ts))}
         nn.close()
+        return {"queries_per_s": q.shape[0] / (float(np.mean(ts)) * 1e-3), "ms": float(np.mean(ts))}
+
+    # planar L2 kNN at a planner-realistic size (tiled scan) and at 1M (tree)
+    for n_pts, label, strat in ((1 << 14, "knn_l2_2d_16k_brute", m.KNN_BRUTE), (1 << 14, "knn_l2_2d_16k_auto", m.KNN_AUTO),
+                                (1 << 20, "knn_l2_2d_1m_tree", m.KNN_AUTO)):
+        pts = W.box_states(n_pts, 2, 51, 0.0, [3976, 2603], np.float32)
+        q = W.box_states(Q_WAVE, 2, 52, 0.0, [3976, 2603], np.float32)
+        out[label] = time_knn(m.lp_space(2, 2, m.F32), pts, q, strat)
+    # SURVEY.md 8(d) sweep: the C5 space at planner-realistic set sizes (2^20 is the headline line), strategy AUTO
+    q = W.se3_states(Q_WAVE, W.QUERY_SEED)
+    for lg in (10, 14, 17):
+        out[f"knn_se3_2^{lg}"] = time_knn(m.se3_space(SO3_W, L2_W), W.se3_states(1 << lg, W.TREE_SEED), q, m.KNN_AUTO)
+    # ... and the N-link arm's space (L1 over [-pi, pi)^N, float64 as the reference's main builds it), 2^17 points
+    for n_links in (8, 16, 32):
+        pts = W.box_states(1 << 17, n_links, 61, -np.pi, np.pi)
+        q = W.box_states(Q_WAVE, n_links, 62, -np.pi, np.pi)
+        out[f"knn_l1_{n_links}d_128k"] = time_knn(m.lp_space(n_links, 1, m.F64), pts, q, m.KNN_AUTO, np.float64)
+    # mesh edges steered to a range of 5 % / 20 % of the scenario's diagonal (|max - min| + 50 pi / 2, the quantity the
+    # reference's step-size rule uses, se3_rigid_body_scenario.hpp:333), half of it spent on translation, half on rotation
+    robot, env, vmin, vmax = W.alpha_puzzle_like(env_tris_target=4000, robot_tris_target=1000)
+    sp3 = m.se3_space(SO3_W, L2_W)
+    mesh = m.Scenario.mesh_pair(ctx, robot, env, sp3, W.se3_step_size(vmin, vmax, SO3_W))
+    diag = float(np.linalg.norm(np.asarray(vmax, dtype=np.float64) - np.asarray(vmin, dtype=np.float64))) + SO3_W * np.pi / 2
+    for pct in (5, 20):
+        rho = diag * pct / 100.0
+        a, b = W.se3_edges(E_WAVE, W.EDGE_SEED + pct, MESH_LO, MESH_HI, rho / 2, rho / 2 / SO3_W)
+        r = time_link(mesh, a, b)
+        r["states_per_s"] = mesh.last_stats()["states"] / (r["ms"] * 1e-3)
+        r["range"] = rho
+        out[f"mesh_edges_range{pct}pct"] = r
+    mesh.close()
     # device-resident PRRT: tree, sampling and every stage of the loop on the GPU; wall clock
     # around whole waves, two words read back per wave
     import time
@@ -538,27 +565,9 @@ def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_00
             return {"error": str(e)[:200]}
 
 
-def fp32_probe(torch, dev):
-    """FP32 CUDA-core yardstick: cuBLAS SGEMM with TF32 off (library used as a ruler only)."""
-    try:
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
-        torch.matmul(a, b)
-        torch.cuda.synchronize()
-        best = 1e9
-        for _ in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(a, b)
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        torch.backends.cuda.matmul.allow_tf32 = old
-        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
-    except Exception:
-        return None
+def fp32_probe(ctx):
+    """FP32 CUDA-core yardstick: the library's register-only FFMA kernel (mptg_probe_fp32_tflops), as SURVEY.md 8(d) asks."""
+    return ctx.probe_fp32_tflops()
 
 
 def cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb):

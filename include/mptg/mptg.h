@@ -84,6 +84,10 @@ const char* mptg_last_error(const mptg_ctx* ctx);
 void* mptg_ctx_stream(mptg_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t mptg_ctx_launch_count(const mptg_ctx* ctx);
+/* Measured FP32 rate of this GPU: a register-only FFMA kernel (8 independent chains per thread, every SM full),
+ * best of three timed launches, in TFLOP/s (2 flop per FFMA).  The yardstick bench.py's fp32 rooflines use
+ * ("FP32 peak is not in MEASURED_PEAKS.json; measure it with an FFMA microbenchmark"). */
+int mptg_probe_fp32_tflops(mptg_ctx* ctx, double* tflops_out);
 /* Scalars per state for a space (sum of part sizes); < 0 on a malformed descriptor. */
 int mptg_space_scalars(const mptg_space_desc* space);
 /* space.dimensions() of the reference (LP: dim, SO2: dim, SO3: 3, sum over parts) used by

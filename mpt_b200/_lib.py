@@ -64,6 +64,7 @@ SYMBOLS = {
     "mptg_last_error": (C.c_char_p, [_P]),
     "mptg_ctx_stream": (_P, [_P]),
     "mptg_ctx_launch_count": (C.c_uint64, [_P]),
+    "mptg_probe_fp32_tflops": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mptg_space_scalars": (C.c_int, [_SD]),
     "mptg_space_dimensions": (C.c_int, [_SD]),
     "mptg_distance_batch": (C.c_int, [_P, _SD, _P, _P, _U32, _P]),

@@ -106,6 +106,12 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.mptg_ctx_launch_count(self.h))
 
+    def probe_fp32_tflops(self) -> float:
+        """FFMA rate of this GPU in TFLOP/s (mptg_probe_fp32_tflops)."""
+        out = C.c_double(0.0)
+        L.check(self.lib.mptg_probe_fp32_tflops(self.h, C.byref(out)), self.h)
+        return float(out.value)
+
     # ---- metric helpers (a4, a5, steer)
     def _arr(self, space: Space, a, cols=None):
         a = np.ascontiguousarray(a, dtype=space.dtype)

@@ -6,6 +6,21 @@ thread_local std::string g_lastError;
 }
 using namespace mptg;
 
+// FP32 yardstick: 8 independent FFMA chains per thread, nothing else in the loop
+__global__ void __launch_bounds__(256) ffmaProbeKernel(float* sink, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fmaf(x0, a, b), x1 = fmaf(x1, a, b), x2 = fmaf(x2, a, b), x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b), x5 = fmaf(x5, a, b), x6 = fmaf(x6, a, b), x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678f) sink[0] = s;  // keeps the chains alive; practically never taken
+}
+
 extern "C" {
 
 int mptg_abi_version(void) { return MPTG_ABI_VERSION; }
@@ -63,6 +78,33 @@ int mptg_ctx_destroy(mptg_ctx* ctx) {
 int mptg_sync(mptg_ctx* ctx) {
     if (!ctx) return fail(nullptr, MPTG_ERR_BAD_ARG, "mptg_sync: null context");
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
+int mptg_probe_fp32_tflops(mptg_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_probe_fp32_tflops: null argument");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* sink = nullptr;
+    if (int rc = scratch(ctx, 0, 256, &sink)) return rc;
+    cudaEvent_t e0, e1;
+    MPTG_CUDA(ctx, cudaEventCreate(&e0));
+    MPTG_CUDA(ctx, cudaEventCreate(&e1));
+    const int iters = 4096, ctas = ctx->smCount * 8 * 4, threads = 256;  // 8 CTAs of 256 threads per SM, four waves
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {  // first launch warms up
+        cudaEventRecord(e0, ctx->stream);
+        ffmaProbeKernel<<<ctas, threads, 0, ctx->stream>>>((float*)sink, iters, 0.999f, 0.001f);
+        MPTG_LAUNCHED(ctx);
+        cudaEventRecord(e1, ctx->stream);
+        MPTG_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8 * 16 * double(iters) * threads * ctas / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
     return MPTG_OK;
 }
 
