@@ -151,6 +151,164 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteKernel(const BruteAr
 }
 
 // ---------------------------------------------------------------------------------------------
+// scan, one unweighted L1 part (the N-link arm's space): R queries x P points per lane
+// ---------------------------------------------------------------------------------------------
+// knnBruteKernel<S, SHAPE_L1> is bound by shared-memory wavefronts, not arithmetic: per coordinate and 32 pairs it
+// issues one tile load and one broadcast load of the query's coordinate for two adds, and a broadcast load costs as
+// many wavefronts as a strided one of the same width (measured: doubles, one query per warp 65 clk per SM
+// sub-partition for 4 x 32 coordinate pairs; four queries per warp 40; model 4 wavefronts per 128-bit load: 64 / 40).
+// Here a lane owns P consecutive-by-vector points and a warp owns R queries: per coordinate, P / V 128-bit tile
+// loads (V = 16 / sizeof(S) points each) and R / V 128-bit broadcast loads of the [D][R] query block feed 2 R P adds
+// per lane, which brings the load wavefronts down to the cost of the adds.  Sums run in the order of mptg_space.h
+// (partDistance, p == 1), so distances are the same bits as everywhere else; candidates may be offered in any
+// order because the list order is the total order (distance, index).
+template <typename S, int N>
+struct alignas(sizeof(S) * N > 16 ? 16 : sizeof(S) * N) ScalarVec {
+    S v[N];
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cpAsync(void* smemDst, const void* src, int srcBytes) {  // the rest of BYTES is zero-filled
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(d), "l"(src), "n"(BYTES), "r"(srcBytes) : "memory");
+}
+
+constexpr int L1_R = 4;    // queries per warp
+constexpr int L1_PTS = 4;  // points per lane and step: a step covers 128 points
+
+template <typename S, int KPL>
+__global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteL1Kernel(const BruteArgs<S> a) {
+    constexpr int R = L1_R, P = L1_PTS;
+    constexpr int V = 16 / (int)sizeof(S) < P ? 16 / (int)sizeof(S) : P;  // points per 128-bit load
+    constexpr int G = P / V;                                              // loads per coordinate
+    constexpr int STEP = 32 * P;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* tiles = reinterpret_cast<S*>(smemRaw);          // [2][D][a.tile], a.tile a multiple of STEP
+    S* qsm = tiles + 2 * (size_t)a.sp.D * a.tile;      // [BRUTE_WARPS][D][R]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q0 = (blockIdx.x * BRUTE_WARPS + warp) * R;
+    const bool active = q0 < a.Q;
+
+    S* myq = qsm + (size_t)warp * D * R;
+    for (int e = lane; e < D * R; e += 32) {
+        const int c = e / R, r = e % R;
+        myq[e] = q0 + r < a.Q ? a.queries[(size_t)(q0 + r) * D + c] : S(0);
+    }
+    __syncwarp();
+    const ScalarVec<S, R>* qv = reinterpret_cast<const ScalarVec<S, R>*>(myq);
+
+    WarpTopK<S, KPL> top[R];
+    S thr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        top[r].init(a.k);
+        thr[r] = a.radius;
+    }
+
+    const uint32_t splitBegin = a.begin + blockIdx.y * a.chunk;
+    const uint32_t splitEnd = min(a.end, splitBegin + a.chunk);
+
+    // Tiles are filled with cp.async into two buffers, the next one while the current one is scanned (filled
+    // synchronously the fill was 40-50 % of the kernel).  16-byte copies when every row of the tile starts on a
+    // 16-byte boundary, element copies otherwise; the rest of the last 128-point step is zero-filled and masked below.
+    constexpr int E = 16 / (int)sizeof(S);
+    const bool rows16 = (a.stride % E) == 0 && (splitBegin % E) == 0 && (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;
+    auto fill = [&](S* buf, uint32_t t0) {
+        const uint32_t cnt = min(a.tile, splitEnd - t0);
+        const uint32_t cntPad = (cnt + STEP - 1) / STEP * STEP;
+        if (rows16) {
+            const uint32_t chunks = cntPad / E, total = chunks * (uint32_t)D;
+            for (uint32_t x = threadIdx.x; x < total; x += blockDim.x) {
+                const uint32_t c = x / chunks, j = (x - c * chunks) * E;
+                const int bytes = j + E <= cnt ? 16 : j < cnt ? (int)((cnt - j) * sizeof(S)) : 0;
+                cpAsync<16>(buf + (size_t)c * a.tile + j, bytes ? a.pts + (size_t)c * a.stride + t0 + j : a.pts, bytes);
+            }
+        } else {
+            const uint32_t total = cntPad * (uint32_t)D;
+            for (uint32_t x = threadIdx.x; x < total; x += blockDim.x) {
+                const uint32_t c = x / cntPad, j = x - c * cntPad;
+                cpAsync<(int)sizeof(S)>(buf + (size_t)c * a.tile + j, j < cnt ? a.pts + (size_t)c * a.stride + t0 + j : a.pts,
+                                        j < cnt ? (int)sizeof(S) : 0);
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    if (splitBegin < splitEnd) fill(tiles, splitBegin);
+    uint32_t which = 0;
+    for (uint32_t t0 = splitBegin; t0 < splitEnd; t0 += a.tile, which ^= 1) {
+        const uint32_t cnt = min(a.tile, splitEnd - t0);
+        const S* tile = tiles + (size_t)which * D * a.tile;
+        if (t0 + a.tile < splitEnd) {  // the other buffer was released by the barrier that ended the previous iteration
+            fill(tiles + (size_t)(which ^ 1) * D * a.tile, t0 + a.tile);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        }
+        __syncthreads();  // every thread's copies of this tile have landed
+        if (active)
+        for (uint32_t base = 0; base < cnt; base += STEP) {
+            S acc[R][P];
+            {
+                const ScalarVec<S, R> qc = qv[0];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const ScalarVec<S, V> t = *reinterpret_cast<const ScalarVec<S, V>*>(tile + base + g * 32 * V + lane * V);
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r][g * V + j] = fp::abs_(t.v[j] - qc.v[r]);
+                }
+            }
+#pragma unroll 2
+            for (int c = 1; c < D; ++c) {
+                const ScalarVec<S, R> qc = qv[c];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const ScalarVec<S, V> t =
+                        *reinterpret_cast<const ScalarVec<S, V>*>(tile + (size_t)c * a.tile + base + g * 32 * V + lane * V);
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+#pragma unroll
+                        for (int r = 0; r < R; ++r) acc[r][g * V + j] = acc[r][g * V + j] + fp::abs_(t.v[j] - qc.v[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const bool qok = q0 + r < a.Q;
+                // no candidate in the whole step: the common case once the list is full
+                bool some = false;
+#pragma unroll
+                for (int x = 0; x < P; ++x) some = some || acc[r][x] <= thr[r];
+                if (!__any_sync(FULL_MASK, qok && some)) continue;
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const uint32_t p = base + g * 32 * V + lane * V + j;
+                        const bool cand = qok && p < cnt && acc[r][g * V + j] <= thr[r];
+                        if (__any_sync(FULL_MASK, cand)) {
+                            top[r].offer(cand, acc[r][g * V + j], (t0 + p) * a.idxMul + a.idxAdd, a.radius, lane);
+                            thr[r] = top[r].kthD < a.radius ? top[r].kthD : a.radius;
+                        }
+                    }
+            }
+        }
+        __syncthreads();  // this tile fully consumed: its buffer is refilled in the next iteration
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t q = q0 + r;
+        if (q < a.Q) {
+            const size_t row = ((size_t)blockIdx.y * a.Q + q) * a.k;
+            const uint32_t count = top[r].store(a.k, a.idxOut + row, a.distOut + row, lane);
+            if (gridDim.y == 1 && a.countOut && lane == 0) a.countOut[q] = count;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // merge of `parts` sorted candidate lists per query (split-N brute force, tail + index, multi-GPU)
 // ---------------------------------------------------------------------------------------------
 template <typename S, int KPL>
@@ -247,6 +405,23 @@ int launchBruteShape(mptg_ctx* ctx, const BruteArgs<S>& a, dim3 grid, size_t sme
     return MPTG_OK;
 }
 
+template <typename S>
+int launchBruteL1(mptg_ctx* ctx, const BruteArgs<S>& a, dim3 grid, size_t smem) {
+    const dim3 block(BRUTE_WARPS * 32);
+#define MPTG_BRUTE_L1(KPL)                                                                                           \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            MPTG_CUDA(ctx, cudaFuncSetAttribute(knnBruteL1Kernel<S, KPL>,                                      \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        knnBruteL1Kernel<S, KPL><<<grid, block, smem, ctx->stream>>>(a);                                       \
+    } while (0)
+    if (a.k <= 32) MPTG_BRUTE_L1(1);
+    else MPTG_BRUTE_L1(2);  // k <= 64 (the caller keeps larger k on the one-query kernel: four lists of 128 slots spill)
+#undef MPTG_BRUTE_L1
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+
 // Scan points [begin,end) for all queries; results (k per query) to idxOut/distOut/countOut (device).
 template <typename S>
 int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uint32_t Q, uint32_t k, double radius,
@@ -258,7 +433,14 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
     tile = tile > 1024 ? 1024 : (tile / 32) * 32;
     if (tile < 32) tile = 32;
     const uint32_t n = end - begin;
-    const uint32_t qBlocks = (Q + BRUTE_WARPS - 1) / BRUTE_WARPS;
+    // the L1 kernel with several queries per warp and points per lane, once a wave is large enough to fill the machine
+    // with it; its tiles are multiples of a 128-point step
+    constexpr uint32_t l1Step = 32 * L1_PTS;
+    const bool multiQuery = knn->shape == SHAPE_L1 && k <= 64 && Q >= (uint32_t)(BRUTE_WARPS * L1_R) * 16 &&
+                            2 * (size_t)D * l1Step * sizeof(S) <= 160 * 1024;  // two tile buffers
+    if (multiQuery) tile = tile < l1Step ? l1Step : (tile / l1Step) * l1Step;
+    const uint32_t queriesPerCta = multiQuery ? BRUTE_WARPS * L1_R : BRUTE_WARPS;
+    const uint32_t qBlocks = (Q + queriesPerCta - 1) / queriesPerCta;
     // split the scan so that the grid fills the machine (~4 CTAs per SM) when there are few queries
     uint32_t splits = 1;
     const uint32_t wantCtas = (uint32_t)ctx->smCount * 4;
@@ -305,14 +487,14 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
         a.idxOut = idxOut;
         a.distOut = distOut;
     }
-    const size_t smem = ((size_t)D * tile + (size_t)BRUTE_WARPS * D) * sizeof(S);
+    const size_t smem = ((multiQuery ? 2 : 1) * (size_t)D * tile + (size_t)queriesPerCta * D) * sizeof(S);
     const dim3 grid(qBlocks, splits);
     int rc;
     switch (knn->shape) {
         case SHAPE_SE3: rc = launchBruteShape<S, SHAPE_SE3>(ctx, a, grid, smem); break;
         case SHAPE_L2_2: rc = launchBruteShape<S, SHAPE_L2_2>(ctx, a, grid, smem); break;
         case SHAPE_L2_3: rc = launchBruteShape<S, SHAPE_L2_3>(ctx, a, grid, smem); break;
-        case SHAPE_L1: rc = launchBruteShape<S, SHAPE_L1>(ctx, a, grid, smem); break;
+        case SHAPE_L1: rc = multiQuery ? launchBruteL1<S>(ctx, a, grid, smem) : launchBruteShape<S, SHAPE_L1>(ctx, a, grid, smem); break;
         default: rc = launchBruteShape<S, SHAPE_GENERIC>(ctx, a, grid, smem); break;
     }
     if (rc) return rc;

@@ -198,6 +198,31 @@ def test_knn_index_device_build_equals_host_build(ctx, oracle, scalar, monkeypat
         assert_knn_equal(results[1], want)
 
 
+@pytest.mark.parametrize("scalar", [m.F32, m.F64])
+def test_knn_l1_scan_several_queries_per_warp(ctx, oracle, scalar):
+    """Arm-space scan with several queries per warp (knnBruteL1Kernel; waves of >= 512 queries, k <= 64): bit-exact
+    indices and distances against the oracle and against the one-query-per-warp kernel, over dimensions that are not
+    multiples of anything, ragged wave sizes, k in both register layouts, radius searches, duplicates, a NaN query, and the
+    split scan (few query blocks -> several partial lists per query merged)."""
+    dt = np.float32 if scalar == m.F32 else np.float64
+    for dim, n_pts, n_q in ((5, 3000, 515), (8, 9000, 1000), (16, 2500, 512), (32, 1100, 777), (7, 33, 600)):
+        sp = m.lp_space(dim, 1, scalar)
+        pts = W.box_states(n_pts, dim, 100 + dim, -np.pi, np.pi, dt)
+        pts[n_pts // 2:n_pts // 2 + 40] = pts[3]  # ties: index order decides
+        q = W.box_states(n_q, dim, 200 + dim, -np.pi, np.pi, dt)
+        q[5] = pts[3]
+        q[7, dim - 1] = np.nan
+        nn = m.Nearest(ctx, sp, 16384, m.KNN_BRUTE)
+        nn.insert(pts)
+        for k, radius in ((1, -1.0), (16, -1.0), (37, -1.0), (64, -1.0), (20, 0.35 * dim), (100, -1.0)):
+            got, want = nn.nearest(q, k, radius), oracle.knn(sp, pts, q, k, radius)
+            assert got[2][7] == 0
+            assert_knn_equal(got, want)
+            small = nn.nearest(q[:100], k, radius)  # below the threshold: the one-query-per-warp kernel
+            assert np.array_equal(small[0], got[0][:100]) and np.array_equal(small[1].view(np.uint8), got[1][:100].view(np.uint8))
+        nn.close()
+
+
 def test_knn_degenerate_point_sets(ctx, oracle):
     """All points identical / on a line / two clusters: zero-extent boxes, massive ties (index order decides)."""
     sp = m.se3_space(50, 1)
