@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteL1Kernel(const Brute
     const uint32_t splitEnd = min(a.end, splitBegin + a.chunk);
 
     // Tiles are filled with cp.async into two buffers, the next one while the current one is scanned (filled
-    // synchronously the fill was 40-50 % of the kernel).  16-byte copies when every row of the tile starts on a
+    // synchronously the fill was 40-50 % of the kernel; the one-query-per-warp kernel above was tried with the same
+    // scheme and gained nothing on SE(3) / planar sets -- its fills are 2-7 rows against a full distance per pair).  16-byte copies when every row of the tile starts on a
     // 16-byte boundary, element copies otherwise; the rest of the last 128-point step is zero-filled and masked below.
     constexpr int E = 16 / (int)sizeof(S);
     const bool rows16 = (a.stride % E) == 0 && (splitBegin % E) == 0 && (reinterpret_cast<uintptr_t>(a.pts) & 15) == 0;
