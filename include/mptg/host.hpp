@@ -34,6 +34,12 @@ public:
     mptg_ctx* get() const { return h_; }
     void sync() { check(mptg_sync(h_), h_, "mptg_sync"); }
     std::uint64_t launches() const { return mptg_ctx_launch_count(h_); }
+    // FFMA rate of the device in TFLOP/s (the FP32 yardstick of the bench's rooflines)
+    double fp32Tflops() {
+        double t = 0;
+        check(mptg_probe_fp32_tflops(h_, &t), h_, "mptg_probe_fp32_tflops");
+        return t;
+    }
 };
 
 // Scenario geometry registered on the device (mptg_geom).  Move only.
