@@ -101,8 +101,20 @@ struct ArmValidator {
             const S len = lengths[i];
             to[0] = from[0] + len * cs;
             to[1] = from[1] + len * sn;
+            // Far circles are passed without the exact test.  With w = centre - from, v = to - from as computed:
+            // the distance from w to the segment [0, v] is >= |w| - |v|, and the value the exact test computes
+            // is within a few eps * |w| of it (case c1 <= 0 returns this very |w|^2; the far-end case is |w - v|
+            // up to one rounding per coordinate; the projection adds v * f with |v f| <= |v| < |w| to -w, which is
+            // exact).  So |w|^2 > ((|v| + rr) * (1 + 1024 eps))^2, all in relative terms, implies the exact
+            // test's "distance^2 > rr^2": same decision, about a third of the arithmetic.  NaNs fail the
+            // comparison and take the exact test.
+            const S vx = to[0] - from[0], vy = to[1] - from[1];
+            const S reach = fp::sqrt_(vx * vx + vy * vy) * (S(1) + S(1024) * fp::consts<S>::eps());
             for (int c = 0; c < nCircles; ++c) {
                 const S rr = circles[3 * c + 2] + linkRadius;
+                const S wx = circles[3 * c] - from[0], wy = circles[3 * c + 1] - from[1];
+                const S far = reach + rr;
+                if (wx * wx + wy * wy > far * far) continue;
                 if (!(distPointSegmentSquared2<S>(circles + 3 * c, from, to) > rr * rr)) return false;
             }
             from[0] = to[0];
