@@ -300,7 +300,7 @@ def run_ours(args):
     edge_flops = mesh_stats["bv_tests"] * F_BV + mesh_stats["prim_tests"] * F_TRI
     launches_before_probe = ctx.launches
     fp32_peak = fp32_probe(ctx)
-    assert ctx.launches == launches_before_probe + 4
+    assert ctx.launches == launches_before_probe + 3
     line = {
         "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": knn_ms + edge_ms, "higher_is_better": True, "scaling": "weak",

@@ -85,7 +85,7 @@ void* mptg_ctx_stream(mptg_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t mptg_ctx_launch_count(const mptg_ctx* ctx);
 /* Measured FP32 rate of this GPU: a register-only FFMA kernel (8 independent chains per thread, every SM full),
- * best of three timed launches, in TFLOP/s (2 flop per FFMA).  The yardstick bench.py's fp32 rooflines use
+ * best of two timed launches of ~4 ms, in TFLOP/s (2 flop per FFMA).  The yardstick bench.py's fp32 rooflines use
  * ("FP32 peak is not in MEASURED_PEAKS.json; measure it with an FFMA microbenchmark"). */
 int mptg_probe_fp32_tflops(mptg_ctx* ctx, double* tflops_out);
 /* Scalars per state for a space (sum of part sizes); < 0 on a malformed descriptor. */

@@ -89,9 +89,9 @@ int mptg_probe_fp32_tflops(mptg_ctx* ctx, double* tflops_out) {
     cudaEvent_t e0, e1;
     MPTG_CUDA(ctx, cudaEventCreate(&e0));
     MPTG_CUDA(ctx, cudaEventCreate(&e1));
-    const int iters = 4096, ctas = ctx->smCount * 8 * 4, threads = 256;  // 8 CTAs of 256 threads per SM, four waves
+    const int iters = 1024, ctas = ctx->smCount * 8 * 4, threads = 256;  // 8 CTAs of 256 threads per SM, four waves: ~4.4 ms (at 1 ms, launch and tail cost 3.5 %)
     double best = 0;
-    for (int rep = 0; rep < 4; ++rep) {  // first launch warms up
+    for (int rep = 0; rep < 3; ++rep) {  // first launch warms up
         cudaEventRecord(e0, ctx->stream);
         ffmaProbeKernel<<<ctas, threads, 0, ctx->stream>>>((float*)sink, iters, 0.999f, 0.001f);
         MPTG_LAUNCHED(ctx);
