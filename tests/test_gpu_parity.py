@@ -784,6 +784,55 @@ def test_linkarm_matches_oracle(ctx, oracle, n_links, scalar):
         assert np.array_equal(got, want), f"delta={delta}: {(got != want).sum()} differ"
 
 
+def _reach_boundary_scenes(dt):
+    """Arm scenes with ONE circle each, its centre at (reach + radius) * (1 + delta) from a joint: delta from -1e-3 to +1e-3
+    through 0 and a few ulps, along, against and across the link or in a random direction; every sixth arm is 100 times
+    longer, so that the coordinates' rounding errors are large against the margins."""
+    eps = np.finfo(dt).eps
+    rng = np.random.default_rng(77)
+    for scene in range(20):
+        n_links = int(rng.integers(1, 6))
+        lengths = rng.uniform(0.5, 6.0, n_links) * (100.0 if scene % 6 == 5 else 1.0)
+        radius = float(rng.uniform(0.05, 0.8))
+        pose = rng.uniform(-np.pi, np.pi, n_links)
+        ang = np.cumsum(pose)
+        joints = np.concatenate([[[0.0, 0.0]], np.cumsum(np.stack([lengths * np.cos(ang), lengths * np.sin(ang)], axis=1), axis=0)])
+        for d in (-1e-3, -64 * eps, -eps, 0.0, eps, 64 * eps, 1024 * eps, 4096 * eps, 1e-3):
+            i = int(rng.integers(0, n_links))
+            r = float(rng.uniform(0.1, 2.0))
+            along = (joints[i + 1] - joints[i]) / lengths[i]
+            direction = [along, -along, np.array([-along[1], along[0]]), rng.normal(size=2)][int(rng.integers(0, 4))]
+            direction = direction / np.linalg.norm(direction)
+            c = joints[i] + direction * (lengths[i] + r + radius) * (1.0 + d)
+            st = np.concatenate([pose[None, :], pose[None, :] + rng.normal(scale=1e-7, size=(63, n_links)),
+                                 pose[None, :] + rng.normal(scale=1e-3, size=(64, n_links)),
+                                 pose[None, :] + rng.normal(scale=0.2, size=(128, n_links))]).astype(dt)
+            yield lengths, radius, [[c[0], c[1], r]], st
+
+
+@pytest.mark.parametrize("scalar", [m.F64, m.F32])
+def test_linkarm_circles_at_the_reach_boundary(ctx, oracle, scalar):
+    """The arm validator passes circles farther from a link's start than the link's reach without the exact segment test;
+    on scenes that sit on that boundary its decisions must still equal the oracle's (states and edges)."""
+    dt = np.float64 if scalar == m.F64 else np.float32
+    seen = set()
+    for n, (lengths, radius, circles, st) in enumerate(_reach_boundary_scenes(dt)):
+        sc = m.Scenario.link_arm(ctx, lengths, radius, circles, scalar)
+        og = oracle.link_arm(lengths, radius, circles, scalar)
+        want = og.valid(st)
+        seen.update(int(x) for x in want[:128])
+        assert np.array_equal(sc.valid(st), want), f"scene {n}"
+        assert np.array_equal(sc.link(st[:128], st[128:]), og.link(st[:128], st[128:])), f"scene {n} (edges)"
+        sc.close()
+    assert seen == {0, 1}
+
+
+def test_fp32_probe(ctx):
+    """mptg_probe_fp32_tflops: the FFMA yardstick of bench.py's fp32 rooflines lands near the nominal 74.4 TFLOP/s of a B200."""
+    t = ctx.probe_fp32_tflops()
+    assert 40.0 < t < 80.0, t
+
+
 def test_linkarm_golden(ctx):
     g = np.load(ROOT / "tests" / "golden" / "golden.npz")
     sc = m.Scenario.link_arm(ctx, g["arm_lengths"], float(g["arm_radius"]), g["arm_circles"])
