@@ -38,6 +38,7 @@ struct BruteArgs {
     uint32_t* idxOut;  // [split][Q][k]
     S* distOut;
     uint32_t* countOut;  // [Q], only written when gridDim.y == 1
+    unsigned long long* bound;  // [Q] or null: k-th distances published by the splits of a query (knnBruteL1Kernel)
     DevSpace<S> sp;
 };
 
@@ -173,6 +174,21 @@ __device__ __forceinline__ void cpAsync(void* smemDst, const void* src, int srcB
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(d), "l"(src), "n"(BYTES), "r"(srcBytes) : "memory");
 }
 
+template <typename S> __device__ __forceinline__ S loadBound(const unsigned long long* p);
+template <> __device__ __forceinline__ double loadBound<double>(const unsigned long long* p) {
+    return __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(p));  // all ones (unset) = NaN: compares false
+}
+template <> __device__ __forceinline__ float loadBound<float>(const unsigned long long* p) {
+    return __uint_as_float(*reinterpret_cast<const volatile unsigned int*>(p));
+}
+template <typename S> __device__ __forceinline__ void publishBound(unsigned long long* p, S d);
+template <> __device__ __forceinline__ void publishBound<double>(unsigned long long* p, double d) {
+    atomicMin(p, (unsigned long long)__double_as_longlong(d));
+}
+template <> __device__ __forceinline__ void publishBound<float>(unsigned long long* p, float d) {
+    atomicMin(reinterpret_cast<unsigned int*>(p), __float_as_uint(d));
+}
+
 constexpr int L1_R = 4;    // queries per warp
 constexpr int L1_PTS = 4;  // points per lane and step: a step covers 128 points
 
@@ -248,6 +264,17 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteL1Kernel(const Brute
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         __syncthreads();  // every thread's copies of this tile have landed
+        if (active && a.bound) {
+            // split scans: the k-th distance of any split's full list bounds the k-th distance of the union, so the
+            // splits of a query publish theirs (bit patterns of non-negative numbers order like unsigned integers) and
+            // prune with the smallest one seen; "<=" keeps ties, which the index order decides in the merge
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (q0 + r < a.Q) {
+                    const S g = loadBound<S>(a.bound + q0 + r);
+                    thr[r] = g < thr[r] ? g : thr[r];
+                }
+        }
         if (active)
         for (uint32_t base = 0; base < cnt; base += STEP) {
             S acc[R][P];
@@ -291,7 +318,9 @@ __global__ void __launch_bounds__(BRUTE_WARPS * 32) knnBruteL1Kernel(const Brute
                         const bool cand = qok && p < cnt && acc[r][g * V + j] <= thr[r];
                         if (__any_sync(FULL_MASK, cand)) {
                             top[r].offer(cand, acc[r][g * V + j], (t0 + p) * a.idxMul + a.idxAdd, a.radius, lane);
-                            thr[r] = top[r].kthD < a.radius ? top[r].kthD : a.radius;
+                            const S mine = top[r].kthD < a.radius ? top[r].kthD : a.radius;
+                            if (a.bound && lane == 0 && top[r].kthD < fp::consts<S>::inf()) publishBound<S>(a.bound + q0 + r, top[r].kthD);
+                            thr[r] = mine < thr[r] ? mine : thr[r];
                         }
                     }
             }
@@ -473,6 +502,13 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
     a.countOut = countOut;
     uint32_t* scrIdx = nullptr;
     S* scrDist = nullptr;
+    if (multiQuery && splits > 1) {
+        void* pb;
+        int rcb = scratch(ctx, 9, (size_t)Q * sizeof(unsigned long long), &pb);
+        if (rcb) return rcb;
+        MPTG_CUDA(ctx, cudaMemsetAsync(pb, 0xFF, (size_t)Q * sizeof(unsigned long long), ctx->stream));
+        a.bound = (unsigned long long*)pb;
+    }
     if (splits > 1) {
         void* p0;
         void* p1;
