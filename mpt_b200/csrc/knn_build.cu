@@ -107,8 +107,11 @@ __global__ void __launch_bounds__(EXT_THREADS) segExtentKernel(const float* __re
     }
 }
 
+// rotSplit: extents of SO(3) coefficients count rotSplit times their weight when the split axis is chosen.  With the
+// cap bound a finer rotation partition prunes better than equal weighted extents (tools/knn_tree_shape_experiment.py:
+// floor of the leaves a C5 query must visit 125 -> 104 at 1.4, 101 at 2.0).
 __global__ void axisKernel(DevSpace<float> sp, const int* __restrict__ segMin, const int* __restrict__ segMax, uint32_t nSeg,
-                           uint32_t* __restrict__ axis) {
+                           uint32_t* __restrict__ axis, float rotSplit) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nSeg) return;
     int best = 0;
@@ -116,7 +119,8 @@ __global__ void axisKernel(DevSpace<float> sp, const int* __restrict__ segMin, c
     for (int p = 0; p < sp.nParts; ++p)
         for (int j = 0; j < sp.dim[p]; ++j) {
             const int c = sp.off[p] + j;
-            const float ext = (fromOrderedInt(segMax[(size_t)s * sp.D + c]) - fromOrderedInt(segMin[(size_t)s * sp.D + c])) * sp.weight[p];
+            float ext = (fromOrderedInt(segMax[(size_t)s * sp.D + c]) - fromOrderedInt(segMin[(size_t)s * sp.D + c])) * sp.weight[p];
+            if (sp.kind[p] == MPTG_PART_SO3) ext *= rotSplit;
             if (ext > bestExt) bestExt = ext, best = c;
         }
     axis[s] = (uint32_t)best;
@@ -183,10 +187,9 @@ __global__ void __launch_bounds__(256) parentBoxKernel(const S* __restrict__ clo
     }
 }
 
-// SoA boxes -> blocked [block][2D][32]; and for SE(3) the half2 (lo down, hi up) copies
+// SoA boxes -> blocked [block][2D][32]
 template <typename S>
-__global__ void boxBlockKernel(const S* __restrict__ lo, const S* __restrict__ hi, uint32_t nNodes, int D, S* __restrict__ box,
-                               uint32_t* __restrict__ boxH) {
+__global__ void boxBlockKernel(const S* __restrict__ lo, const S* __restrict__ hi, uint32_t nNodes, int D, S* __restrict__ box) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;  // node slot, padded to a multiple of 32
     const uint32_t nSlots = ((nNodes + 31u) / 32u) * 32u;
     if (j >= nSlots) return;
@@ -196,29 +199,138 @@ __global__ void boxBlockKernel(const S* __restrict__ lo, const S* __restrict__ h
         const S h = j < nNodes ? hi[(size_t)c * nNodes + j] : (S)-INFINITY;
         box[((size_t)b * 2 * D + c) * 32u + ln] = l;
         box[((size_t)b * 2 * D + D + c) * 32u + ln] = h;
-        if (boxH) {  // float sets only
-            const __half hl = __float2half_rd((float)l), hh = __float2half_ru((float)h);
-            boxH[((size_t)b * 7 + c) * 32u + ln] = (uint32_t)__half_as_ushort(hl) | ((uint32_t)__half_as_ushort(hh) << 16);
-        }
     }
 }
 
-// SE(3): half2 rows of the leaf points + max conversion error of quaternion / translation coordinates
+// ---- SE(3)/f32: rotation caps.  Any centre gives a valid cap (the radius is measured against the centre as stored);
+// the centre only decides how small the radius is.  q and -q are the same rotation, so members are sign-aligned to a
+// reference before they are averaged.
+// one warp per leaf: centre = normalised sum of the leaf's quaternions aligned to its first point
+__global__ void __launch_bounds__(256) leafCapCentreKernel(const float* __restrict__ leafPts, uint32_t nLeaves, float4* __restrict__ centre) {
+    const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (leaf >= nLeaves) return;
+    const float* pt = leafPts + ((size_t)leaf * 7u) * 32u + lane;
+    float q[4];
+    for (int c = 0; c < 4; ++c) q[c] = pt[c * 32];
+    float d = 0.0f;
+    for (int c = 0; c < 4; ++c) d += q[c] * __shfl_sync(0xffffffffu, q[c], 0);
+    const float sg = d < 0.0f ? -1.0f : 1.0f;
+    for (int c = 0; c < 4; ++c) {
+        q[c] *= sg;
+        for (int o = 16; o > 0; o >>= 1) q[c] += __shfl_xor_sync(0xffffffffu, q[c], o);
+    }
+    if (lane == 0) {
+        const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        centre[leaf] = n > 0.0f && n < INFINITY ? make_float4(q[0] / n, q[1] / n, q[2] / n, q[3] / n) : make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+}
+// one warp per parent: centre = normalised sum of the children's centres aligned to the first child's
+__global__ void __launch_bounds__(256) parentCapCentreKernel(const float4* __restrict__ child, uint32_t nChild, uint32_t nParent,
+                                                             float4* __restrict__ centre) {
+    const uint32_t parent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (parent >= nParent) return;
+    const uint32_t ch = parent * 32u + lane;
+    const float4 v = ch < nChild ? child[ch] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float q[4] = {v.x, v.y, v.z, v.w};
+    float d = 0.0f;
+    for (int c = 0; c < 4; ++c) d += q[c] * __shfl_sync(0xffffffffu, q[c], 0);
+    const float sg = d < 0.0f ? -1.0f : 1.0f;
+    for (int c = 0; c < 4; ++c) {
+        q[c] *= sg;
+        for (int o = 16; o > 0; o >>= 1) q[c] += __shfl_xor_sync(0xffffffffu, q[c], o);
+    }
+    if (lane == 0) {
+        const float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        centre[parent] = n > 0.0f && n < INFINITY ? make_float4(q[0] / n, q[1] / n, q[2] / n, q[3] / n) : make_float4(0.f, 0.f, 0.f, 1.f);
+    }
+}
+// one thread per stored point (padding repeats a real point): cosine of its angle to the centre of its level-l node, in
+// double (exact to 1e-15 of the real geometry of the stored floats), rounded down to float; minimum per node through
+// the bit pattern (non-negative floats order like unsigned integers).  Level 0 also takes the largest quaternion norm.
+__global__ void __launch_bounds__(256) capRadiusKernel(const float* __restrict__ leafPts, uint32_t nPad, int shift, const float4* __restrict__ centre,
+                                                       unsigned int* __restrict__ minCos, unsigned int* __restrict__ normMax) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPad) return;  // nPad is a multiple of 32: whole warps leave together
+    const uint32_t leaf = p >> 5, ln = p & 31;
+    const float* pt = leafPts + ((size_t)leaf * 7u) * 32u + ln;
+    const float4 c = centre[p >> shift];
+    const double q0 = pt[0], q1 = pt[32], q2 = pt[64], q3 = pt[96];
+    const double dot = fabs(q0 * c.x + q1 * c.y + q2 * c.z + q3 * c.w);
+    const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3, c2 = (double)c.x * c.x + (double)c.y * c.y + (double)c.z * c.z + (double)c.w * c.w;
+    double cs = dot / sqrt(n2 * c2);
+    if (!(cs >= 0.0)) cs = 0.0;  // zero norm or NaN: no rotation pruning for this node
+    if (cs > 1.0) cs = 1.0;
+    float cf = __double2float_rd(cs);
+    float nf = __double2float_ru(sqrt(n2));
+    if (!(nf >= 0.0f)) nf = INFINITY;  // NaN coordinates: the caller falls back to the box path
+    for (int o = 16; o > 0; o >>= 1) {
+        cf = fminf(cf, __shfl_xor_sync(0xffffffffu, cf, o));
+        nf = fmaxf(nf, __shfl_xor_sync(0xffffffffu, nf, o));
+    }
+    if (ln == 0) {
+        atomicMin(minCos + (p >> shift), __float_as_uint(cf));
+        if (normMax) atomicMax(normMax, __float_as_uint(nf));
+    }
+}
+__global__ void fillKernel(unsigned int* a, unsigned int v, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+// blocked cap image of one level: [block][3][32] float4
+__global__ void capPackKernel(const float4* __restrict__ centre, const unsigned int* __restrict__ minCos, const float* __restrict__ lo,
+                              const float* __restrict__ hi, uint32_t nNodes, float4* __restrict__ cap) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nSlots = ((nNodes + 31u) / 32u) * 32u;
+    if (j >= nSlots) return;
+    const uint32_t b = j >> 5, ln = j & 31;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 1.f), v1 = make_float4(0.f, 1.f, INFINITY, -INFINITY), v2 = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+    if (j < nNodes) {
+        v0 = centre[j];
+        const double cs = (double)__uint_as_float(minCos[j]);
+        const float sn = fminf(1.0f, __double2float_ru(sqrt(fmax(0.0, 1.0 - cs * cs))));
+        v1 = make_float4((float)cs, sn, lo[(size_t)4 * nNodes + j], hi[(size_t)4 * nNodes + j]);
+        v2 = make_float4(lo[(size_t)5 * nNodes + j], hi[(size_t)5 * nNodes + j], lo[(size_t)6 * nNodes + j], hi[(size_t)6 * nNodes + j]);
+    }
+    cap[((size_t)b * 3 + 0) * 32u + ln] = v0;
+    cap[((size_t)b * 3 + 1) * 32u + ln] = v1;
+    cap[((size_t)b * 3 + 2) * 32u + ln] = v2;
+}
+
+// SE(3): half2 words of the leaf points ([leaf][32] uint4, one 128-bit load per lane) + max conversion error of
+// quaternion / translation coordinates
+// power of two that brings the largest |translation coordinate| of the set into (1024, 2048]: the half copies then
+// keep 11 significant bits whatever the unit of length is, and differences of in-range coordinates cannot overflow
+__global__ void tScaleKernel(const float* __restrict__ lo, const float* __restrict__ hi, uint32_t nTop, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float m = 0.0f;
+    for (int c = 4; c < 7; ++c)
+        for (uint32_t j = 0; j < nTop; ++j) m = fmaxf(m, fmaxf(fabsf(lo[(size_t)c * nTop + j]), fabsf(hi[(size_t)c * nTop + j])));
+    float sc = 1.0f;
+    if (m > 0.0f && m < 1e30f) {
+        int e;
+        frexpf(m, &e);  // m = f 2^e, f in [0.5, 1)
+        sc = ldexpf(1.0f, 11 - e);
+    }
+    *out = sc;
+}
 __global__ void leafHalfKernel(const float* __restrict__ leafPts, uint32_t nPad, uint32_t* __restrict__ leafH, unsigned int* __restrict__ err) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     float eq = 0.0f, et = 0.0f;
+    const float sc = __uint_as_float(err[3]);
     if (p < nPad) {
         const uint32_t leaf = p >> 5, ln = p & 31;
         unsigned short h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < 7; ++c) {
-            const float v = leafPts[((size_t)leaf * 7 + c) * 32u + ln];
+            const float v = leafPts[((size_t)leaf * 7 + c) * 32u + ln] * (c < 4 ? 1.0f : sc);  // exact: sc is a power of two
             const __half hv = __float2half_rn(v);
             h[c] = __half_as_ushort(hv);
             const float e = fabsf(__half2float(hv) - v);
             if (c < 4) eq = fmaxf(eq, e);
             else et = fmaxf(et, e);
         }
-        for (int r = 0; r < 4; ++r) leafH[((size_t)leaf * 4 + r) * 32u + ln] = (uint32_t)h[2 * r] | ((uint32_t)h[2 * r + 1] << 16);
+        for (int r = 0; r < 4; ++r) leafH[(size_t)p * 4u + r] = (uint32_t)h[2 * r] | ((uint32_t)h[2 * r + 1] << 16);
     }
     for (int o = 16; o > 0; o >>= 1) {
         eq = fmaxf(eq, __shfl_xor_sync(0xffffffffu, eq, o));
@@ -417,7 +529,12 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     const DevSpace<float> sp = makeDevSpace<float>(space);
     const int D = sp.D;
     cudaStream_t st = ctx->stream;
-    const bool compressed = sizeof(S) == 4 && classifySpace(space) == SHAPE_SE3;  // half copies; coordinates beyond the half range fall back below
+    const bool compressed = sizeof(S) == 4 && classifySpace(space) == SHAPE_SE3;  // half copies + caps; coordinates beyond the half range fall back below
+    static const float rotSplit = [] {  // MPTG_KNN_ROT_SPLIT: tuning experiments
+        const char* e = getenv("MPTG_KNN_ROT_SPLIT");
+        const float v = e ? (float)atof(e) : 0.0f;
+        return v > 0.0f ? v : 0.75f;
+    }();
 
     // ---- geometry of the image
     KnnIndex nx;
@@ -438,7 +555,7 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     };
     const size_t oPts = take((size_t)D * nx.nPad * sizeof(S));
     const size_t oPerm = take((size_t)nx.nPad * sizeof(uint32_t));
-    size_t oBox[BVH_MAXL] = {0, 0, 0, 0, 0}, oBoxH[BVH_MAXL] = {0, 0, 0, 0, 0}, oLeafH = 0;
+    size_t oBox[BVH_MAXL] = {0, 0, 0, 0, 0}, oCap[BVH_MAXL] = {0, 0, 0, 0, 0}, oLeafH = 0;
     uint32_t nBlocks[BVH_MAXL] = {0, 0, 0, 0, 0};
     for (int l = 0; l <= nx.top; ++l) {
         nBlocks[l] = (nx.nNodes[l] + 31) / 32;
@@ -446,7 +563,7 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     }
     if (compressed) {
         oLeafH = take((size_t)nx.nNodes[0] * 4 * 32 * sizeof(uint32_t));
-        for (int l = 0; l <= nx.top; ++l) oBoxH[l] = take((size_t)nBlocks[l] * 7 * 32 * sizeof(uint32_t));
+        for (int l = 0; l <= nx.top; ++l) oCap[l] = take((size_t)nBlocks[l] * 3 * 32 * sizeof(float4));
     }
     void* mem = ix.mem;
     size_t memBytes = ix.memBytes;
@@ -465,8 +582,8 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     }
     unsigned long long* stats = ix.devStats;
     if (!stats) {
-        MPTG_CUDA(ctx, cudaMalloc(&stats, 4 * sizeof(unsigned long long)));
-        if (int rc = memsetSync(ctx, stats, 0, 4 * sizeof(unsigned long long))) return rc;
+        MPTG_CUDA(ctx, cudaMalloc(&stats, 8 * sizeof(unsigned long long)));
+        if (int rc = memsetSync(ctx, stats, 0, 8 * sizeof(unsigned long long))) return rc;
     }
 
     // ---- work space (context scratch slot 7): canon, keys x2, ids x2, segOf, extents, axis, level tables, SoA boxes, cub temp
@@ -487,8 +604,10 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
                  wId1 = wtake((size_t)n * 4), wSeg = wtake((size_t)n * 4), wMin = wtake((size_t)maxSeg * D * 4),
                  wMax = wtake((size_t)maxSeg * D * 4), wAxis = wtake((size_t)maxSeg * 4), wTab = wtake(nTab * 4 * 4), wCub = wtake(cubBytes),
                  wErr = wtake(16);
-    size_t wLo[BVH_MAXL], wHi[BVH_MAXL];
+    size_t wLo[BVH_MAXL], wHi[BVH_MAXL], wCentre[BVH_MAXL] = {0, 0, 0, 0, 0}, wMinCos[BVH_MAXL] = {0, 0, 0, 0, 0};
     for (int l = 0; l <= nx.top; ++l) wLo[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S)), wHi[l] = wtake((size_t)D * nx.nNodes[l] * sizeof(S));
+    if (compressed)
+        for (int l = 0; l <= nx.top; ++l) wCentre[l] = wtake((size_t)nx.nNodes[l] * sizeof(float4)), wMinCos[l] = wtake((size_t)nx.nNodes[l] * 4);
     void* wbase;
     {
         size_t want = wbytes;  // sized for the store's capacity the first time (see KnnIndex::capacityHint)
@@ -535,7 +654,7 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
         MPTG_LAUNCHED(ctx);
         segExtentKernel<<<(n + EXT_THREADS - 1) / EXT_THREADS, EXT_THREADS, 0, st>>>(canon, ids[cur], segOf, n, D, segMin, segMax);
         MPTG_LAUNCHED(ctx);
-        axisKernel<<<(nSeg + 255) / 256, 256, 0, st>>>(sp, segMin, segMax, nSeg, axis);
+        axisKernel<<<(nSeg + 255) / 256, 256, 0, st>>>(sp, segMin, segMax, nSeg, axis, rotSplit);
         MPTG_LAUNCHED(ctx);
         keyKernel<<<g256, 256, 0, st>>>(canon, ids[cur], segOf, axis, n, D, keys[cur]);
         MPTG_LAUNCHED(ctx);
@@ -564,21 +683,42 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     }
     for (int l = 0; l <= nx.top; ++l) {
         boxBlockKernel<S><<<(nBlocks[l] * 32 + 255) / 256, 256, 0, st>>>((const S*)(W + wLo[l]), (const S*)(W + wHi[l]), nx.nNodes[l], D,
-                                                                        (S*)(M + oBox[l]), compressed ? (uint32_t*)(M + oBoxH[l]) : nullptr);
+                                                                        (S*)(M + oBox[l]));
         MPTG_LAUNCHED(ctx);
     }
-    float errQ = 0.f, errT = 0.f;
+    float errQ = 0.f, errT = 0.f, normMax = 1.f, tScale = 1.f;
     bool useHalf = compressed;
     if (compressed) {
         MPTG_CUDA(ctx, cudaMemsetAsync(err, 0, 16, st));
+        tScaleKernel<<<1, 32, 0, st>>>((const float*)(W + wLo[nx.top]), (const float*)(W + wHi[nx.top]), nx.nNodes[nx.top], (float*)(err + 3));
+        MPTG_LAUNCHED(ctx);
         leafHalfKernel<<<(nx.nPad + 255) / 256, 256, 0, st>>>((const float*)(M + oPts), nx.nPad, (uint32_t*)(M + oLeafH), err);
         MPTG_LAUNCHED(ctx);
-        unsigned int herr[2];
-        MPTG_CUDA(ctx, cudaMemcpyAsync(herr, err, 8, cudaMemcpyDeviceToHost, st));
+        // rotation caps of every level: centres bottom-up, radii against ALL member points, then the blocked image
+        const float* lp = (const float*)(M + oPts);
+        for (int l = 0; l <= nx.top; ++l) {
+            float4* centre = (float4*)(W + wCentre[l]);
+            unsigned int* minCos = (unsigned int*)(W + wMinCos[l]);
+            if (l == 0) leafCapCentreKernel<<<(nx.nNodes[0] * 32 + 255) / 256, 256, 0, st>>>(lp, nx.nNodes[0], centre);
+            else parentCapCentreKernel<<<(nx.nNodes[l] * 32 + 255) / 256, 256, 0, st>>>((const float4*)(W + wCentre[l - 1]), nx.nNodes[l - 1], nx.nNodes[l], centre);
+            MPTG_LAUNCHED(ctx);
+            fillKernel<<<(nx.nNodes[l] + 255) / 256, 256, 0, st>>>(minCos, 0x3f800000u, nx.nNodes[l]);
+            MPTG_LAUNCHED(ctx);
+            capRadiusKernel<<<(nx.nPad + 255) / 256, 256, 0, st>>>(lp, nx.nPad, 5 * (l + 1), centre, minCos, l == 0 ? err + 2 : nullptr);
+            MPTG_LAUNCHED(ctx);
+            capPackKernel<<<(nBlocks[l] * 32 + 255) / 256, 256, 0, st>>>(centre, minCos, (const float*)(W + wLo[l]), (const float*)(W + wHi[l]), nx.nNodes[l],
+                                                                        (float4*)(M + oCap[l]));
+            MPTG_LAUNCHED(ctx);
+        }
+        unsigned int herr[4];
+        MPTG_CUDA(ctx, cudaMemcpyAsync(herr, err, 16, cudaMemcpyDeviceToHost, st));
         MPTG_CUDA(ctx, cudaStreamSynchronize(st));
         memcpy(&errQ, &herr[0], 4);
         memcpy(&errT, &herr[1], 4);
-        if (!(errT < 1e30f) || !(errQ < 1e30f)) useHalf = false;  // a coordinate overflowed the half range: keep the float path
+        memcpy(&normMax, &herr[2], 4);
+        memcpy(&tScale, &herr[3], 4);
+        // a coordinate overflowed the half range, or a quaternion is not finite: keep the float box path
+        if (!(errT < 1e30f) || !(errQ < 1e30f) || !(normMax < 1e18f)) useHalf = false;
     }
 
     nx.mem = mem;
@@ -591,9 +731,11 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     for (int l = 0; l <= nx.top; ++l) nx.box[l] = M + oBox[l];
     if (useHalf) {
         nx.leafH = (uint32_t*)(M + oLeafH);
-        for (int l = 0; l <= nx.top; ++l) nx.boxH[l] = (uint32_t*)(M + oBoxH[l]);
+        for (int l = 0; l <= nx.top; ++l) nx.cap[l] = M + oCap[l];
         nx.errQ = errQ * 1.0001f + 1e-30f;
         nx.errT = errT * 1.0001f + 1e-30f;
+        nx.normMax = normMax;
+        nx.tScale = tScale;
     }
     ix = nx;
     return MPTG_OK;

@@ -134,9 +134,9 @@ struct BvhArgs {
     const S* leafPts;
     const uint32_t* perm;
     const S* box[BVH_MAXL];
-    const uint32_t* leafH;  // nullptr when the compressed copies are not available
-    const uint32_t* boxH[BVH_MAXL];
-    float errQ, errT;
+    const uint32_t* leafH;  // nullptr when the compressed copies / caps are not available
+    const float4* cap[BVH_MAXL];
+    float errQ, errT, normMax, tScale, tScaleInv;  // cap image (knn_se3.cuh)
     uint32_t nNodes[BVH_MAXL];
     int top;
     const S* queries;
@@ -151,6 +151,7 @@ struct BvhArgs {
     S* distOut;
     uint32_t* countOut;
     unsigned long long* stats;
+    uint32_t* cursor;  // next position of the wave (persistent warps), zeroed before the launch
     DevSpace<S> sp;
 };
 
@@ -202,33 +203,24 @@ struct BvhWalk {
     const S* myq;  // query in shared memory (generic path)
     S qr[7];       // query in registers (SE(3) path)
     float w0, w1;
-    float qabs = 0.0f;  // sum |q_i| of the query quaternion (error bound of dots against half-precision copies)
     WarpTopK<S, KPL> top;
     int lane;
-    unsigned long long leaves = 0, inner = 0;
-#ifdef MPTG_KNN_PROBE
-    unsigned long long useful = 0, cand = 0;  // experiment: leaf visits with a surviving lane, surviving lanes
-#endif
+    uint32_t leaves = 0, inner = 0;
 
     __device__ __forceinline__ BvhWalk(const BvhArgs<S>& args, const S* q, int ln) : a(args), myq(q), lane(ln) {}
 
     // Pruning threshold min(k-th distance, radius), cached as a float (rounded up) and refreshed after
-    // every offer; thrS is the same value divided by the slack factor of the leaf prefilter.
-    float thrF, thrS;
+    // every offer.
+    float thrF;
     S rad;  // search radius of this query: a.radius, or tighter (tail search bounded by the tree's k-th distance)
-    float dotC;  // 2 - slack - 2*qabs*errQ: prefilter term so that t = dotC - 2|dot_h| <= 2 - 2|dot|
-    float eT;    // sqrt(3)*errT (rounded up): |t_h - q| - eT <= |t - q|
     __device__ __forceinline__ void refreshThr() {
         const S t = top.kthD < rad ? top.kthD : rad;
         thrF = thrAsFloat<S>(t);
-        thrS = thrF * (1.0f + 3e-5f);
     }
     __device__ __forceinline__ void start() {
         top.init(a.k);
         rad = a.radius;
         refreshThr();
-        dotC = __fmaf_rn(-2.0f * qabs, a.errQ, 2.0f - 3e-6f);
-        eT = a.errT * 1.73206f;  // sqrt(3) * (1 + 5e-6)
     }
     __device__ __forceinline__ float threshold() const { return thrF; }
 
@@ -241,32 +233,7 @@ struct BvhWalk {
         const S* b = a.box[L] + ((size_t)block * (size_t)(2 * D)) * 32u + lane;
         if (SHAPE == SHAPE_SE3 && sizeof(S) == 4) {
             float dotHi, dotLo, acc = 0.0f;
-            if (a.leafH) {  // boxes as half2 (lo rounded down, hi rounded up): 7 loads instead of 14
-                const uint32_t* bh = a.boxH[L] + ((size_t)block * 7u) * 32u + lane;
-                {
-                    const uint32_t raw = __ldg(bh);
-                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-                    const float v = (float)qr[0];
-                    dotHi = (v >= 0.0f ? lh.y : lh.x) * v;
-                    dotLo = (v >= 0.0f ? lh.x : lh.y) * v;
-                }
-#pragma unroll
-                for (int j = 1; j < 4; ++j) {
-                    const uint32_t raw = __ldg(bh + j * 32);
-                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-                    const float v = (float)qr[j];
-                    dotHi = __fmaf_rn(v >= 0.0f ? lh.y : lh.x, v, dotHi);
-                    dotLo = __fmaf_rn(v >= 0.0f ? lh.x : lh.y, v, dotLo);
-                }
-#pragma unroll
-                for (int j = 4; j < 7; ++j) {
-                    const uint32_t raw = __ldg(bh + j * 32);
-                    const float2 lh = __half22float2(*reinterpret_cast<const __half2*>(&raw));
-                    const float v = (float)qr[j];
-                    const float e = fmaxf(fmaxf(lh.x - v, v - lh.y), 0.0f);
-                    acc = __fmaf_rn(e, e, acc);
-                }
-            } else {
+            {
                 {
                     const float l = __ldg((const float*)b), h = __ldg((const float*)b + 7 * 32);
                     const float v = (float)qr[0];
@@ -334,75 +301,6 @@ struct BvhWalk {
         refreshThr();
     }
 
-    // SE(3)/f32 leaf visit split in two so the loads of the NEXT leaf can be in flight while the
-    // current one is evaluated (software pipelining inside the warp hides the L2 latency of the
-    // dependent pick -> load -> evaluate chain).
-    // compressed leaf visit, split in two so the loads of the NEXT leaf are in flight while the current
-    // one is evaluated
-    struct LeafData {
-        uint32_t h[4];  // half2 rows (qx,qy) (qz,qw) (tx,ty) (tz,0)
-    };
-    __device__ __forceinline__ void leafLoad(uint32_t node, LeafData& ld) const {
-        const uint32_t* ph = a.leafH + ((size_t)node * 4u) * 32u + lane;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ld.h[c] = __ldg(ph + c * 32);
-    }
-    // exact distance of this lane's point (operation order of mptg_space.h) and offer
-    __device__ __forceinline__ void leafExact(uint32_t node, bool maybe) {
-        const uint32_t p = node * 32u + (uint32_t)lane;
-        const uint32_t orig = __ldg(a.perm + p);
-        const float* pt = (const float*)a.leafPts + ((size_t)node * 7u) * 32u + lane;
-        float pv[7];
-#pragma unroll
-        for (int c = 0; c < 7; ++c) pv[c] = __ldg(pt + c * 32);
-        float dot = pv[0] * (float)qr[0];
-        dot = __fmaf_rn(pv[1], (float)qr[1], dot);
-        dot = __fmaf_rn(pv[2], (float)qr[2], dot);
-        dot = __fmaf_rn(pv[3], (float)qr[3], dot);
-        const float d0 = pv[4] - (float)qr[4], d1 = pv[5] - (float)qr[5], d2 = pv[6] - (float)qr[6];
-        float s2 = d0 * d0;
-        s2 = __fmaf_rn(d1, d1, s2);
-        s2 = __fmaf_rn(d2, d2, s2);
-        const float ad = fminf(1.0f, fabsf(dot));
-        float dr = fp::acos01(ad);
-        if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
-        float dt = fp::sqrt_(s2);
-        if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
-        top.offer(maybe && orig != MPTG_NO_INDEX, (S)(dr + dt), orig * a.idxMul + a.idxAdd, rad, lane);
-        refreshThr();
-    }
-    // Prefilter on the half-precision copy.  With h = the stored copy: |dot - dot_h| <= qabs*errQ and
-    // ||t - q|| >= ||t_h - q|| - sqrt(3)*errT, so
-    //   w0*sqrt(2 - 2(|dot_h| + qabs*errQ + slack)) + w1*max(||t_h - q|| - eT, 0)
-    // is a lower bound of the exact distance up to rounding; the rounding (approximate square roots
-    // 2.4e-7 relative, a few 6e-8 in the sums, and the exact distance's own) is covered by the 3e-6
-    // absolute slack inside dotC, the 1e-6 relative inflation of eT and the 3e-5 relative slack in thrS.
-    __device__ __forceinline__ void leafEval(uint32_t node, const LeafData& ld) {
-        ++leaves;
-        const float2 xy = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[0]));
-        const float2 zw = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[1]));
-        const float2 t01 = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[2]));
-        const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&ld.h[3]));
-        float dot = xy.x * (float)qr[0];
-        dot = __fmaf_rn(xy.y, (float)qr[1], dot);
-        dot = __fmaf_rn(zw.x, (float)qr[2], dot);
-        dot = __fmaf_rn(zw.y, (float)qr[3], dot);
-        const float d0 = t01.x - (float)qr[4], d1 = t01.y - (float)qr[5], d2 = t2.x - (float)qr[6];
-        const float s2 = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, d0 * d0));
-        const float sT = fmaxf(sqrtApprox(s2) - eT, 0.0f);
-        const float t = fmaxf(__fmaf_rn(-2.0f, fabsf(dot), dotC), 0.0f);
-        const bool maybe = __fmaf_rn(w0, sqrtApprox(t), w1 * sT) <= thrS;
-#ifdef MPTG_KNN_PROBE
-        {
-            const unsigned pb = __ballot_sync(FULL_MASK, maybe);
-            useful += pb != 0u;
-            cand += __popc(pb);
-        }
-#endif
-        if (!__any_sync(FULL_MASK, maybe)) return;
-        leafExact(node, maybe);  // rare: fetch the exact points and evaluate the true distance
-    }
-
     // take the child with the smallest remaining bound; false when none is left within the threshold
     __device__ __forceinline__ bool pick(uint32_t& key, uint32_t block, uint32_t& node, uint32_t& best) const {
         best = __reduce_min_sync(FULL_MASK, key);
@@ -422,25 +320,7 @@ struct BvhWalk {
     __device__ __forceinline__ void descend(uint32_t block) {
         uint32_t key = childKey<L>(block);
         uint32_t node;
-        if (L == 0 && SHAPE == SHAPE_SE3 && sizeof(S) == 4 && a.leafH != nullptr) {
-            // Software pipeline over two register sets: the next leaf is chosen (and its loads issued)
-            // against the threshold BEFORE the current leaf is evaluated; if that evaluation tightens the
-            // threshold past the chosen leaf's bound, it and every remaining child (bounds >= its) are dropped.
-            LeafData da, db;
-            uint32_t nodeB, ka, kb;
-            if (!pick(key, block, node, ka)) return;
-            leafLoad(node, da);
-            for (;;) {
-                bool more = pick(key, block, nodeB, kb);
-                if (more) leafLoad(nodeB, db);
-                leafEval(node, da);
-                if (!more || __uint_as_float(kb) > thrF) return;
-                more = pick(key, block, node, ka);
-                if (more) leafLoad(node, da);
-                leafEval(nodeB, db);
-                if (!more || __uint_as_float(ka) > thrF) return;
-            }
-        } else {
+        {
             while (pick(key, block, node)) {
                 if constexpr (L == 0) {
                     leaf(node);
@@ -473,7 +353,6 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKeyKernel(const BvhArgs<
         for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
         w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
         w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
-        w.qabs = fabsf((float)myq[0]) + fabsf((float)myq[1]) + fabsf((float)myq[2]) + fabsf((float)myq[3]);
     }
     uint32_t node = 0;
     auto step = [&](uint32_t key) {
@@ -523,44 +402,53 @@ __global__ void knnOrderScatterKernel(const uint32_t* keys, uint32_t* cursor, ui
     order[atomicAdd(cursor + (keys[q] >> shift), 1u)] = q;
 }
 
+#ifndef MPTG_BVH_MIN_CTAS
+#define MPTG_BVH_MIN_CTAS 1
+#endif
+// Persistent warps: the grid is sized to the machine and every warp draws the next position of the (spatially sorted)
+// wave from a counter until the wave is exhausted.  A search takes 0.5x to 3x the mean, and with one query per warp of
+// an 8-warp CTA a slot stayed occupied until its slowest warp was done: ncu showed 23 of the 32 resident warps active
+// and the kernel waiting on loads (long scoreboard 3.3 per issue) rather than issuing.
 template <typename S, int SHAPE, int KPL>
-__global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKernel(const BvhArgs<S> a) {
+__global__ void __launch_bounds__(BVH_WARPS * 32, MPTG_BVH_MIN_CTAS) knnBvhKernel(const BvhArgs<S> a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     S* qsm = reinterpret_cast<S*>(smemRaw);  // [BVH_WARPS][D]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = a.sp.D;
-    const uint32_t slot = blockIdx.x * BVH_WARPS + warp;
-    if (slot >= a.Q) return;  // warp-uniform; no block-wide barriers below
-    const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
-
     S* myq = qsm + warp * D;
-    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
-    __syncwarp();
-    BvhWalk<S, SHAPE, KPL> w(a, myq, lane);
-    if (SHAPE == SHAPE_SE3) {
+    uint32_t leaves = 0, inner = 0;
+    for (;;) {
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(a.cursor, 1u);
+        slot = __shfl_sync(FULL_MASK, slot, 0);
+        if (slot >= a.Q) break;  // warp-uniform; no block-wide barriers in this kernel
+        const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
+        __syncwarp();
+        for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+        __syncwarp();
+        BvhWalk<S, SHAPE, KPL> w(a, myq, lane);
+        if (SHAPE == SHAPE_SE3) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
-        w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
-        w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
-        w.qabs = fabsf((float)myq[0]) + fabsf((float)myq[1]) + fabsf((float)myq[2]) + fabsf((float)myq[3]);
+            for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
+            w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
+            w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
+        }
+        w.start();
+        switch (a.top) {
+            case 0: w.template descend<0>(0); break;
+            case 1: w.template descend<1>(0); break;
+            case 2: w.template descend<2>(0); break;
+            case 3: w.template descend<3>(0); break;
+            default: w.template descend<4>(0); break;
+        }
+        const uint32_t count = w.top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
+        if (a.countOut && lane == 0) a.countOut[q] = count;
+        leaves += w.leaves;
+        inner += w.inner;
     }
-    w.start();
-    switch (a.top) {
-        case 0: w.template descend<0>(0); break;
-        case 1: w.template descend<1>(0); break;
-        case 2: w.template descend<2>(0); break;
-        case 3: w.template descend<3>(0); break;
-        default: w.template descend<4>(0); break;
-    }
-    const uint32_t count = w.top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
-    if (a.countOut && lane == 0) a.countOut[q] = count;
     if (lane == 0 && a.stats) {
-        atomicAdd(a.stats + 0, w.leaves);
-        atomicAdd(a.stats + 1, w.inner);
-#ifdef MPTG_KNN_PROBE
-        atomicAdd(a.stats + 2, w.useful);
-        atomicAdd(a.stats + 3, w.cand);
-#endif
+        atomicAdd(a.stats + 0, (unsigned long long)leaves);
+        atomicAdd(a.stats + 1, (unsigned long long)inner);
     }
 }
 
@@ -608,61 +496,12 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnTailKernel(const BvhArgs<S>
     w.top.store(a.k, a.idxOut + (size_t)q * a.k, a.distOut + (size_t)q * a.k, lane);
 }
 
+}  // namespace mptg
+#include "knn_se3.cuh"
+namespace mptg {
+
 // ------------------------------------------------------------------ host: build
 namespace {
-
-// IEEE binary16 helpers on the host (bit exact, no dependence on host support in cuda_fp16.h)
-inline float halfBitsToFloat(uint16_t h) {
-    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
-    uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu, bits;
-    if (exp == 0) {
-        if (man == 0) bits = sign;
-        else {
-            int e = -1;
-            do {
-                ++e;
-                man <<= 1;
-            } while (!(man & 0x400u));
-            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
-        }
-    } else if (exp == 31) {
-        bits = sign | 0x7f800000u | (man << 13);
-    } else {
-        bits = sign | ((exp + 112u) << 23) | (man << 13);
-    }
-    float f;
-    memcpy(&f, &bits, 4);
-    return f;
-}
-// nearest half (ties to even); |v| beyond the half range becomes +-inf
-inline uint16_t floatToHalfBitsRn(float v) {
-    uint32_t x;
-    memcpy(&x, &v, 4);
-    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
-    x &= 0x7fffffffu;
-    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));
-    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);  // rounds to >= 65520 -> inf
-    if (x < 0x33000001u) return sign;                          // < 2^-25 -> 0
-    int exp = (int)(x >> 23) - 127;
-    uint32_t man = (x & 0x7fffffu) | 0x800000u;
-    int shift = exp < -14 ? (13 + (-14 - exp)) : 13;
-    uint32_t hman = man >> shift;
-    const uint32_t rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
-    if (rem > halfway || (rem == halfway && (hman & 1u))) ++hman;
-    uint32_t hbits = exp < -14 ? hman : (((uint32_t)(exp + 15) << 10) + (hman - 0x400u));
-    return (uint16_t)(sign | hbits);
-}
-// largest half <= v  /  smallest half >= v
-inline uint16_t floatToHalfBitsDown(float v) {
-    uint16_t h = floatToHalfBitsRn(v);
-    if (halfBitsToFloat(h) > v) h = (h & 0x8000u) ? (uint16_t)(h + 1) : (h == 0 ? (uint16_t)0x8001u : (uint16_t)(h - 1));
-    return h;
-}
-inline uint16_t floatToHalfBitsUp(float v) {
-    uint16_t h = floatToHalfBitsRn(v);
-    if (halfBitsToFloat(h) < v) h = (h & 0x8000u) ? (h == 0x8000u ? (uint16_t)0x0001u : (uint16_t)(h - 1)) : (uint16_t)(h + 1);
-    return h;
-}
 
 template <typename S>
 struct HostBuild {
@@ -805,16 +644,6 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
         nBlocks[l] = (nx.nNodes[l] + 31) / 32;
         oBox[l] = take((size_t)nBlocks[l] * 2 * D * 32 * sizeof(S));
     }
-    // SE(3)/f32: half-precision copies for the prefilters (only when every coordinate fits a half)
-    bool compressed = sizeof(S) == 4 && classifySpace(space) == SHAPE_SE3;
-    if (compressed)
-        for (uint32_t i = 0; i < n && compressed; ++i)
-            for (int c = 4; c < 7; ++c) compressed = compressed && std::fabs((double)hb.pts[(size_t)i * D + c]) < 60000.0;
-    size_t oLeafH = 0, oBoxH[BVH_MAXL] = {0, 0, 0, 0, 0};
-    if (compressed) {
-        oLeafH = take((size_t)nx.nNodes[0] * 4 * 32 * sizeof(uint32_t));
-        for (int l = 0; l <= nx.top; ++l) oBoxH[l] = take((size_t)nBlocks[l] * 7 * 32 * sizeof(uint32_t));
-    }
     std::vector<unsigned char> host(bytes, 0);
     S* hp = reinterpret_cast<S*>(host.data() + oPts);
     uint32_t* hperm = reinterpret_cast<uint32_t*>(host.data() + oPerm);
@@ -836,35 +665,6 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
                 }
             }
     }
-    float errQ = 0.f, errT = 0.f;
-    if (compressed) {
-        uint32_t* lh = reinterpret_cast<uint32_t*>(host.data() + oLeafH);
-        for (uint32_t i = 0; i < nx.nPad; ++i) {
-            const uint32_t leaf = i >> 5, ln = i & 31;
-            uint16_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            for (int c = 0; c < 7; ++c) {
-                const float v = (float)hp[((size_t)leaf * D + c) * 32 + ln];
-                h[c] = floatToHalfBitsRn(v);
-                const float e = std::fabs(halfBitsToFloat(h[c]) - v);
-                if (c < 4) errQ = e > errQ ? e : errQ;
-                else errT = e > errT ? e : errT;
-            }
-            for (int r = 0; r < 4; ++r) lh[((size_t)leaf * 4 + r) * 32 + ln] = (uint32_t)h[2 * r] | ((uint32_t)h[2 * r + 1] << 16);
-        }
-        for (int l = 0; l <= nx.top; ++l) {
-            uint32_t* bh = reinterpret_cast<uint32_t*>(host.data() + oBoxH[l]);
-            const uint32_t nn = nx.nNodes[l];
-            for (uint32_t b = 0; b < nBlocks[l]; ++b)
-                for (uint32_t ln = 0; ln < 32; ++ln) {
-                    const uint32_t j = b * 32 + ln;
-                    for (int c = 0; c < 7; ++c) {
-                        const uint16_t hl = j < nn ? floatToHalfBitsDown((float)lo[l][(size_t)c * nn + j]) : (uint16_t)0x7c00u;
-                        const uint16_t hh = j < nn ? floatToHalfBitsUp((float)hi[l][(size_t)c * nn + j]) : (uint16_t)0xfc00u;
-                        bh[((size_t)b * 7 + c) * 32 + ln] = (uint32_t)hl | ((uint32_t)hh << 16);
-                    }
-                }
-        }
-    }
     // 4. upload (reuse the block when it is large enough)
     void* mem = ix.mem;
     size_t memBytes = ix.memBytes;
@@ -877,8 +677,8 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     if (int rc = uploadSync(ctx, mem, host.data(), bytes)) return rc;
     unsigned long long* stats = ix.devStats;
     if (!stats) {
-        MPTG_CUDA(ctx, cudaMalloc(&stats, 4 * sizeof(unsigned long long)));
-        if (int rc = memsetSync(ctx, stats, 0, 4 * sizeof(unsigned long long))) return rc;
+        MPTG_CUDA(ctx, cudaMalloc(&stats, 8 * sizeof(unsigned long long)));
+        if (int rc = memsetSync(ctx, stats, 0, 8 * sizeof(unsigned long long))) return rc;
     }
     nx.mem = mem;
     nx.memBytes = memBytes;
@@ -888,12 +688,6 @@ int knnBuildIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, con
     nx.leafPts = (char*)mem + oPts;
     nx.perm = (uint32_t*)((char*)mem + oPerm);
     for (int l = 0; l <= nx.top; ++l) nx.box[l] = (char*)mem + oBox[l];
-    if (compressed) {
-        nx.leafH = (uint32_t*)((char*)mem + oLeafH);
-        for (int l = 0; l <= nx.top; ++l) nx.boxH[l] = (uint32_t*)((char*)mem + oBoxH[l]);
-        nx.errQ = errQ * 1.0001f + 1e-30f;
-        nx.errT = errT * 1.0001f + 1e-30f;
-    }
     ix = nx;
     return MPTG_OK;
 }
@@ -915,37 +709,63 @@ int knnEnsureIndex(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& sp, const
     return knnBuildIndex<S>(ctx, ix, sp, pts, stride, n);
 }
 
-template <typename S, int SHAPE>
-int launchBvhShape(mptg_ctx* ctx, BvhArgs<S>& a) {
-    const dim3 grid((a.Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
-    const size_t smem = (size_t)BVH_WARPS * a.sp.D * sizeof(S);
-    // spatial processing order for large waves (skipped for small ones: three extra launches)
-    if (a.Q >= 4096 && a.top >= 1) {
-        uint32_t shift = 0;
-        while ((a.nNodes[0] >> shift) > 65536u) ++shift;
-        const uint32_t bins = (a.nNodes[0] >> shift) + 1u;
-        void* buf;
-        int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
-        if (rc) return rc;
-        uint32_t* order = (uint32_t*)buf;
-        a.orderKeys = order + a.Q;
-        a.orderHist = order + 2 * (size_t)a.Q;
-        a.orderShift = shift;
-        MPTG_CUDA(ctx, cudaMemsetAsync(a.orderHist, 0, bins * sizeof(uint32_t), ctx->stream));
-        knnBvhKeyKernel<S, SHAPE><<<grid, block, smem, ctx->stream>>>(a);
-        MPTG_LAUNCHED(ctx);
-        knnOrderScanKernel<<<1, 1024, 0, ctx->stream>>>(a.orderHist, bins);
-        MPTG_LAUNCHED(ctx);
-        knnOrderScatterKernel<<<(a.Q + 255) / 256, 256, 0, ctx->stream>>>(a.orderKeys, a.orderHist, shift, a.Q, order);
-        MPTG_LAUNCHED(ctx);
-        a.order = order;
-    }
-    if (a.k <= 32) knnBvhKernel<S, SHAPE, 1><<<grid, block, smem, ctx->stream>>>(a);
-    else if (a.k <= 64) knnBvhKernel<S, SHAPE, 2><<<grid, block, smem, ctx->stream>>>(a);
-    else knnBvhKernel<S, SHAPE, 4><<<grid, block, smem, ctx->stream>>>(a);
+// persistent grid: as many CTAs as the machine holds at once (occupancy of the instantiation), at most one warp per query
+template <typename K, typename A>
+int launchPersistent(mptg_ctx* ctx, K kernel, const A& a, uint32_t Q, size_t smem) {
+    int perSm = 0;
+    MPTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, BVH_WARPS * 32, smem));
+    uint32_t ctas = (uint32_t)(perSm > 0 ? perSm : 1) * (uint32_t)ctx->smCount;
+    const uint32_t need = (Q + BVH_WARPS - 1) / BVH_WARPS;
+    if (ctas > need) ctas = need;
+    kernel<<<ctas, BVH_WARPS * 32, smem, ctx->stream>>>(a);
     MPTG_LAUNCHED(ctx);
     return MPTG_OK;
 }
+
+// spatial processing order for large waves (skipped for small ones: three extra launches): queries that end up in the
+// same region of the tree are processed by neighbouring warps, so the node and leaf lines they touch are shared in L1
+template <typename S, typename KEYK>
+int orderWave(mptg_ctx* ctx, BvhArgs<S>& a, KEYK keyKernel, size_t smem) {
+    if (!(a.Q >= 4096 && a.top >= 1)) return MPTG_OK;
+    const dim3 grid((a.Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
+    uint32_t shift = 0;
+    while ((a.nNodes[0] >> shift) > 65536u) ++shift;
+    const uint32_t bins = (a.nNodes[0] >> shift) + 1u;
+    void* buf;
+    int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
+    if (rc) return rc;
+    uint32_t* order = (uint32_t*)buf;
+    a.orderKeys = order + a.Q;
+    a.orderHist = order + 2 * (size_t)a.Q;
+    a.orderShift = shift;
+    MPTG_CUDA(ctx, cudaMemsetAsync(a.orderHist, 0, bins * sizeof(uint32_t), ctx->stream));
+    keyKernel<<<grid, block, smem, ctx->stream>>>(a);
+    MPTG_LAUNCHED(ctx);
+    knnOrderScanKernel<<<1, 1024, 0, ctx->stream>>>(a.orderHist, bins);
+    MPTG_LAUNCHED(ctx);
+    knnOrderScatterKernel<<<(a.Q + 255) / 256, 256, 0, ctx->stream>>>(a.orderKeys, a.orderHist, shift, a.Q, order);
+    MPTG_LAUNCHED(ctx);
+    a.order = order;
+    return MPTG_OK;
+}
+
+template <typename S, int SHAPE>
+int launchBvhShape(mptg_ctx* ctx, BvhArgs<S>& a) {
+    const size_t smem = (size_t)BVH_WARPS * a.sp.D * sizeof(S);
+    if (int rc = orderWave<S>(ctx, a, knnBvhKeyKernel<S, SHAPE>, smem)) return rc;
+    if (a.k <= 32) return launchPersistent(ctx, knnBvhKernel<S, SHAPE, 1>, a, a.Q, smem);
+    if (a.k <= 64) return launchPersistent(ctx, knnBvhKernel<S, SHAPE, 2>, a, a.Q, smem);
+    return launchPersistent(ctx, knnBvhKernel<S, SHAPE, 4>, a, a.Q, smem);
+}
+
+// SE(3)/float32 over the cap image (knn_se3.cuh)
+inline int launchSe3(mptg_ctx* ctx, BvhArgs<float>& a) {
+    if (int rc = orderWave<float>(ctx, a, knnSe3KeyKernel, 0)) return rc;
+    if (a.k <= 32) return launchPersistent(ctx, knnSe3Kernel<1>, a, a.Q, 0);
+    if (a.k <= 64) return launchPersistent(ctx, knnSe3Kernel<2>, a, a.Q, 0);
+    return launchPersistent(ctx, knnSe3Kernel<4>, a, a.Q, 0);
+}
+inline int launchSe3(mptg_ctx* ctx, BvhArgs<double>&) { return fail(ctx, MPTG_ERR_UNSUPPORTED, "cap image on a double-precision set"); }
 
 template <typename S>
 int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const S* queries, uint32_t Q, uint32_t k,
@@ -957,7 +777,10 @@ int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const
     a.leafH = ix.leafH;
     a.errQ = ix.errQ;
     a.errT = ix.errT;
-    for (int l = 0; l < BVH_MAXL; ++l) a.boxH[l] = ix.boxH[l];
+    for (int l = 0; l < BVH_MAXL; ++l) a.cap[l] = (const float4*)ix.cap[l];
+    a.normMax = ix.normMax;
+    a.tScale = ix.tScale;
+    a.tScaleInv = 1.0f / ix.tScale;
     for (int l = 0; l < BVH_MAXL; ++l) {
         a.box[l] = (const S*)ix.box[l];
         a.nNodes[l] = ix.nNodes[l];
@@ -973,9 +796,10 @@ int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const
     a.distOut = distOut;
     a.countOut = countOut;
     a.stats = ix.devStats;
+    a.cursor = reinterpret_cast<uint32_t*>(ix.devStats + 4);
     a.sp = makeDevSpace<S>(space);
-    MPTG_CUDA(ctx, cudaMemsetAsync(ix.devStats, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    if (classifySpace(space) == SHAPE_SE3) return launchBvhShape<S, SHAPE_SE3>(ctx, a);
+    MPTG_CUDA(ctx, cudaMemsetAsync(ix.devStats, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    if (classifySpace(space) == SHAPE_SE3) return (sizeof(S) == 4 && ix.leafH) ? launchSe3(ctx, a) : launchBvhShape<S, SHAPE_SE3>(ctx, a);
     return launchBvhShape<S, SHAPE_GENERIC>(ctx, a);
 }
 

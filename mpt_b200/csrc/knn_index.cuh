@@ -19,10 +19,16 @@ struct KnnIndex {
     void* leafPts = nullptr;  // [leaf][D][32]
     uint32_t* perm = nullptr;
     void* box[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][2D][32]
-    // SE(3)/f32 only: half-precision copies that feed the conservative prefilters (half the L2 traffic)
-    uint32_t* leafH = nullptr;                                                 // [leaf][4][32] half2: (qx,qy) (qz,qw) (tx,ty) (tz,0)
-    uint32_t* boxH[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [block][7][32] half2 (lo rounded down, hi rounded up)
+    // SE(3)/f32 only (device build): what the conservative prefilters read, one 128-bit load per lane
+    //   leafH   [leaf][32] uint4 = half2 (qx,qy) (qz,qw) (tx,ty) (tz,0) of the lane's point, translations times tScale
+    //   cap[l]  [block][3][32] float4 per child: (c0 c1 c2 c3) (cos rho, sin rho, tlo.x, thi.x) (tlo.y, thi.y, tlo.z, thi.z)
+    //           rotation part of a node = geodesic cap on RP^3: centre quaternion c and angular radius rho with
+    //           acos(|p.c| / (|p||c|)) <= rho for every member p; translation part = its axis-aligned box
+    uint32_t* leafH = nullptr;
+    void* cap[BVH_MAXL] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float errQ = 0.f, errT = 0.f;  // max |half(v) - v| over the stored quaternion / translation coordinates
+    float normMax = 1.f;           // max |quaternion| over the indexed points (rounded up)
+    float tScale = 1.f;            // power of two: leafH translations are stored times tScale, max |t| tScale in (1024, 2048]
     unsigned long long* devStats = nullptr;  // [0] leaves visited, [1] inner nodes visited
     uint64_t builds = 0;
     uint32_t capacityHint = 0;  // capacity of the store: the image and the build's work space are sized for it once, so that

@@ -22,7 +22,7 @@ struct WarpTopK {
     uint32_t i[KPL];
     S kthD;         // warp-uniform: distance in slot k-1
     uint32_t kthI;  // warp-uniform: index in slot k-1
-    int kr, kl;     // register / lane of slot k-1
+    uint32_t k1;    // k - 1: slot k-1 lives in register k1 / 32 of lane k1 % 32
 
     __device__ __forceinline__ void init(uint32_t k) {
 #pragma unroll
@@ -32,8 +32,7 @@ struct WarpTopK {
         }
         kthD = fp::consts<S>::inf();
         kthI = MPTG_NO_INDEX;
-        kr = (int)((k - 1) >> 5);
-        kl = (int)((k - 1) & 31);
+        k1 = k - 1;
     }
 
     // (nd, ni) < current k-th in the total order
@@ -69,14 +68,15 @@ struct WarpTopK {
         }
         S kd = d[0];
         uint32_t ki = i[0];
+        const int kr = (int)(k1 >> 5);
 #pragma unroll
         for (int r = 1; r < KPL; ++r)
             if (r == kr) {
                 kd = d[r];
                 ki = i[r];
             }
-        kthD = __shfl_sync(FULL_MASK, kd, kl);
-        kthI = __shfl_sync(FULL_MASK, ki, kl);
+        kthD = __shfl_sync(FULL_MASK, kd, (int)(k1 & 31u));
+        kthI = __shfl_sync(FULL_MASK, ki, (int)(k1 & 31u));
     }
 
     // Offer one candidate per lane (cand == false for lanes without one); inserts those that beat the
