@@ -97,13 +97,14 @@ public:
         return Geometry(c.get(), g);
     }
 
-    // scenario.valid(q) for n states (AoS, host)
-    void valid(const void* states, std::uint32_t n, std::uint8_t* ok) const {
-        check(mptg_valid_batch(h_, states, n, ok), ctx_, "mptg_valid_batch");
+    // scenario.valid(q) for n states (AoS, host); near (optional): the near-contact flags of mptg_valid_batch
+    void valid(const void* states, std::uint32_t n, std::uint8_t* ok, std::uint8_t* near = nullptr) const {
+        check(mptg_valid_batch(h_, states, n, ok, near), ctx_, "mptg_valid_batch");
     }
     // scenario.link(a, b) for n edges
-    void link(const mptg_space_desc* space, const void* from, const void* to, std::uint32_t n, double step, std::uint8_t* ok) const {
-        check(mptg_link_batch(h_, space, from, to, n, step, ok), ctx_, "mptg_link_batch");
+    void link(const mptg_space_desc* space, const void* from, const void* to, std::uint32_t n, double step, std::uint8_t* ok,
+              std::uint8_t* near = nullptr) const {
+        check(mptg_link_batch(h_, space, from, to, n, step, ok, near), ctx_, "mptg_link_batch");
     }
 };
 

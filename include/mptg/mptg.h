@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MPTG_ABI_VERSION 1
+#define MPTG_ABI_VERSION 2 /* 2: near_contact_out on mptg_valid_batch / mptg_link_batch; mptg_comm_*, mptg_knn_query_sharded */
 #define MPTG_MAX_PARTS 8
 #define MPTG_MAX_SCALARS 64 /* max scalars per state */
 #define MPTG_MAX_K 128      /* max neighbours per query */
@@ -173,9 +173,18 @@ int mptg_geom_destroy(mptg_geom* geom);
 int mptg_geom_kind(const mptg_geom* geom);
 
 /* scenario.valid(q) for n states -> ok_out[i] in {0,1}.  (impl/prrt/prrt.hpp:439,
- * prrt_star.hpp:539, pprm.hpp:299) */
-int mptg_valid_batch(mptg_geom* geom, const void* states, uint32_t n, uint8_t* ok_out);
-int mptg_valid_batch_dev(mptg_geom* geom, const void* states_dev, uint32_t n, uint8_t* ok_out_dev);
+ * prrt_star.hpp:539, pprm.hpp:299)
+ * near_contact_out (optional, NULL to skip): 1 where the decision of item i rests on a configuration within the
+ * geometry's contact band (mptg_geom_contact_band) of touching -- some triangle pair of a checked state whose largest
+ * normalised separating-axis gap lies in (-band, band].  Decisions equal the exact ones outside the band; inside it they
+ * are reported here instead of being trusted (SURVEY.md 8d "correctness gates").  For an edge the flag covers the
+ * states the call examined: every state of an edge reported valid, the states up to the first collision otherwise.
+ * Always 0 for grids, shapes and link arms, whose decisions are bit-identical to the reference's arithmetic. */
+int mptg_valid_batch(mptg_geom* geom, const void* states, uint32_t n, uint8_t* ok_out, uint8_t* near_contact_out);
+int mptg_valid_batch_dev(mptg_geom* geom, const void* states_dev, uint32_t n, uint8_t* ok_out_dev, uint8_t* near_contact_out_dev);
+/* The contact band of a geometry, as an absolute length: 1e-6 x the diagonal of the environment mesh's bounding box
+ * (0 for the other geometry kinds). */
+int mptg_geom_contact_band(const mptg_geom* geom, double* band_out);
 /* scenario.link(a,b) for n edges -> ok_out[i] in {0,1}.  (impl/prrt/prrt.hpp:454-457,
  * prrt_star.hpp:659-662, pprm.hpp:364-366).  Semantics per geometry kind:
  *   GRID    valid(a) && valid(b) && midpoint bisection until |b-a|^2 < 1   (png_2d_scenario.hpp:112-117,152-165)
@@ -183,11 +192,12 @@ int mptg_valid_batch_dev(mptg_geom* geom, const void* states_dev, uint32_t n, ui
  *   LINKARM valid(a) && valid(b) && bisection until |a-b|_inf < 0.02        (link_manipulator_scenario.hpp:118-138)
  *   MESH    DiscreteMotionValidator with step size `step` over `space`      (discrete_motion_validator.hpp:71-130);
  *           `from` is assumed valid and not checked, exactly as the reference (:72-73).
- * `space` / `step` are only read for MESH (pass NULL / 0 otherwise). */
+ * `space` / `step` are only read for MESH (pass NULL / 0 otherwise).
+ * near_contact_out: see mptg_valid_batch. */
 int mptg_link_batch(mptg_geom* geom, const mptg_space_desc* space, const void* from, const void* to,
-                    uint32_t n, double step, uint8_t* ok_out);
+                    uint32_t n, double step, uint8_t* ok_out, uint8_t* near_contact_out);
 int mptg_link_batch_dev(mptg_geom* geom, const mptg_space_desc* space, const void* from_dev,
-                        const void* to_dev, uint32_t n, double step, uint8_t* ok_out_dev);
+                        const void* to_dev, uint32_t n, double step, uint8_t* ok_out_dev, uint8_t* near_contact_out_dev);
 /* Counters of the last valid/link call on this geometry: [0]=states checked, [1]=BV pair tests,
  * [2]=primitive (triangle-pair / circle / cell) tests, [3]=work items. */
 int mptg_geom_last_stats(mptg_geom* geom, uint64_t stats_out[4]);

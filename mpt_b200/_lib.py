@@ -88,10 +88,11 @@ SYMBOLS = {
     "mptg_mesh_pair_create": (C.c_int, [_P, C.c_int, _U32, _P, _U32, _P, C.POINTER(_P)]),
     "mptg_geom_destroy": (C.c_int, [_P]),
     "mptg_geom_kind": (C.c_int, [_P]),
-    "mptg_valid_batch": (C.c_int, [_P, _P, _U32, _P]),
-    "mptg_valid_batch_dev": (C.c_int, [_P, _P, _U32, _P]),
-    "mptg_link_batch": (C.c_int, [_P, _SD, _P, _P, _U32, C.c_double, _P]),
-    "mptg_link_batch_dev": (C.c_int, [_P, _SD, _P, _P, _U32, C.c_double, _P]),
+    "mptg_valid_batch": (C.c_int, [_P, _P, _U32, _P, _P]),
+    "mptg_valid_batch_dev": (C.c_int, [_P, _P, _U32, _P, _P]),
+    "mptg_link_batch": (C.c_int, [_P, _SD, _P, _P, _U32, C.c_double, _P, _P]),
+    "mptg_link_batch_dev": (C.c_int, [_P, _SD, _P, _P, _U32, C.c_double, _P, _P]),
+    "mptg_geom_contact_band": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mptg_geom_last_stats": (C.c_int, [_P, _U64P]),
     "mptg_steer_batch": (C.c_int, [_P, _SD, _P, _P, _P, _U32, C.c_double, _P, _P]),
     "mptg_space_uniforms": (C.c_int, [_SD]),

@@ -544,32 +544,40 @@ class Scenario:
         except Exception:
             pass
 
-    def valid(self, states) -> np.ndarray:
+    def valid(self, states, with_near_contact=False):
+        """scenario.valid for a batch; with_near_contact also returns the near-contact flags (mptg.h)."""
         s = np.ascontiguousarray(states, dtype=self.dtype).reshape(-1, self.D)
         ok = np.empty(s.shape[0], dtype=np.uint8)
-        L.check(self.ctx.lib.mptg_valid_batch(self.h, _ptr(s), s.shape[0], _ptr(ok)), self.ctx.h)
-        return ok
+        near = np.empty(s.shape[0], dtype=np.uint8) if with_near_contact else None
+        L.check(self.ctx.lib.mptg_valid_batch(self.h, _ptr(s), s.shape[0], _ptr(ok), _ptr(near)), self.ctx.h)
+        return (ok, near) if with_near_contact else ok
 
-    def link(self, a, b) -> np.ndarray:
+    def link(self, a, b, with_near_contact=False):
         a = np.ascontiguousarray(a, dtype=self.dtype).reshape(-1, self.D)
         b = np.ascontiguousarray(b, dtype=self.dtype).reshape(-1, self.D)
         ok = np.empty(a.shape[0], dtype=np.uint8)
+        near = np.empty(a.shape[0], dtype=np.uint8) if with_near_contact else None
         sp = self.space.ref if self.space is not None else None
-        L.check(self.ctx.lib.mptg_link_batch(self.h, sp, _ptr(a), _ptr(b), a.shape[0], float(self.step), _ptr(ok)), self.ctx.h)
-        return ok
+        L.check(self.ctx.lib.mptg_link_batch(self.h, sp, _ptr(a), _ptr(b), a.shape[0], float(self.step), _ptr(ok), _ptr(near)), self.ctx.h)
+        return (ok, near) if with_near_contact else ok
+
+    def contact_band(self) -> float:
+        out = C.c_double()
+        L.check(self.ctx.lib.mptg_geom_contact_band(self.h, C.byref(out)), self.ctx.h)
+        return out.value
 
     def link_host_into(self, a_ptr: int, b_ptr: int, n: int, ok_ptr: int):
         sp = self.space.ref if self.space is not None else None
         L.check(self.ctx.lib.mptg_link_batch(self.h, sp, C.c_void_p(a_ptr), C.c_void_p(b_ptr), n, float(self.step),
-                                             C.c_void_p(ok_ptr)), self.ctx.h)
+                                             C.c_void_p(ok_ptr), None), self.ctx.h)
 
     def valid_dev(self, s_ptr: int, n: int, ok_ptr: int):
-        L.check(self.ctx.lib.mptg_valid_batch_dev(self.h, C.c_void_p(s_ptr), n, C.c_void_p(ok_ptr)), self.ctx.h)
+        L.check(self.ctx.lib.mptg_valid_batch_dev(self.h, C.c_void_p(s_ptr), n, C.c_void_p(ok_ptr), None), self.ctx.h)
 
     def link_dev(self, a_ptr: int, b_ptr: int, n: int, ok_ptr: int):
         sp = self.space.ref if self.space is not None else None
         L.check(self.ctx.lib.mptg_link_batch_dev(self.h, sp, C.c_void_p(a_ptr), C.c_void_p(b_ptr), n, float(self.step),
-                                                 C.c_void_p(ok_ptr)), self.ctx.h)
+                                                 C.c_void_p(ok_ptr), None), self.ctx.h)
 
     def last_stats(self):
         out = (C.c_uint64 * 4)()

@@ -586,18 +586,25 @@ int mptg_geom_destroy(mptg_geom* g) {
 
 int mptg_geom_kind(const mptg_geom* g) { return g ? g->kind : 0; }
 
-int mptg_valid_batch_dev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+int mptg_geom_contact_band(const mptg_geom* g, double* out) {
+    if (!g || !out) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_geom_contact_band: bad argument");
+    *out = g->kind == MPTG_GEOM_MESH ? meshBand(g->mesh) : 0.0;
+    return MPTG_OK;
+}
+
+int mptg_valid_batch_dev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok, uint8_t* nearOut) {
     if (!g || (n && (!states || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_valid_batch: bad argument");
     if (n == 0) return MPTG_OK;
     MPTG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
     int rc = resetStats(g);
     if (rc) return rc;
-    if (g->kind == MPTG_GEOM_MESH) return meshValidDev(g, states, n, ok);
+    if (g->kind == MPTG_GEOM_MESH) return meshValidDev(g, states, n, ok, nearOut);
+    if (nearOut) MPTG_CUDA(g->ctx, cudaMemsetAsync(nearOut, 0, n, g->ctx->stream));  // bit-identical decisions: no band
     return g->scalar == MPTG_F32 ? validDevT<float>(g, (const float*)states, n, ok) : validDevT<double>(g, (const double*)states, n, ok);
 }
 
 int mptg_link_batch_dev(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
-                        uint8_t* ok) {
+                        uint8_t* ok, uint8_t* nearOut) {
     if (!g || (n && (!from || !to || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_link_batch: bad argument");
     if (n == 0) return MPTG_OK;
     MPTG_CUDA(g->ctx, cudaSetDevice(g->ctx->device));
@@ -606,8 +613,9 @@ int mptg_link_batch_dev(mptg_geom* g, const mptg_space_desc* space, const void* 
     if (g->kind == MPTG_GEOM_MESH) {
         if (!space || spaceScalars(space) != 7 || space->scalar != g->scalar || !(step > 0))
             return fail(g->ctx, MPTG_ERR_BAD_ARG, "mptg_link_batch: mesh edges need an SE(3) space of the mesh's scalar type and step > 0");
-        return meshLinkDev(g, space, from, to, n, step, ok);
+        return meshLinkDev(g, space, from, to, n, step, ok, nearOut);
     }
+    if (nearOut) MPTG_CUDA(g->ctx, cudaMemsetAsync(nearOut, 0, n, g->ctx->stream));
     return g->scalar == MPTG_F32 ? linkDevT<float>(g, (const float*)from, (const float*)to, n, ok)
                                  : linkDevT<double>(g, (const double*)from, (const double*)to, n, ok);
 }
@@ -627,7 +635,7 @@ static int checkDeviceErrors(mptg_geom* g) {
     return MPTG_OK;
 }
 
-int mptg_valid_batch(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
+int mptg_valid_batch(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok, uint8_t* nearOut) {
     if (!g || (n && (!states || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_valid_batch: bad argument");
     if (n == 0) return MPTG_OK;
     mptg_ctx* ctx = g->ctx;
@@ -637,18 +645,20 @@ int mptg_valid_batch(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) 
     void* dOut;
     int rc = scratch(ctx, 0, sb, &dIn);
     if (rc) return rc;
-    rc = scratch(ctx, 1, n, &dOut);
+    rc = scratch(ctx, 1, 2 * (size_t)n, &dOut);
     if (rc) return rc;
+    uint8_t* dNear = nearOut ? (uint8_t*)dOut + n : nullptr;
     MPTG_CUDA(ctx, cudaMemcpyAsync(dIn, states, sb, cudaMemcpyHostToDevice, ctx->stream));
-    rc = mptg_valid_batch_dev(g, dIn, n, (uint8_t*)dOut);
+    rc = mptg_valid_batch_dev(g, dIn, n, (uint8_t*)dOut, dNear);
     if (rc) return rc;
     MPTG_CUDA(ctx, cudaMemcpyAsync(ok, dOut, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nearOut) MPTG_CUDA(ctx, cudaMemcpyAsync(nearOut, dNear, n, cudaMemcpyDeviceToHost, ctx->stream));
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return checkDeviceErrors(g);
 }
 
 int mptg_link_batch(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
-                    uint8_t* ok) {
+                    uint8_t* ok, uint8_t* nearOut) {
     if (!g || (n && (!from || !to || !ok))) return fail(g ? g->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_link_batch: bad argument");
     if (n == 0) return MPTG_OK;
     mptg_ctx* ctx = g->ctx;
@@ -658,14 +668,16 @@ int mptg_link_batch(mptg_geom* g, const mptg_space_desc* space, const void* from
     void* dOut;
     int rc = scratch(ctx, 0, 2 * sbp, &dIn);
     if (rc) return rc;
-    rc = scratch(ctx, 1, n, &dOut);
+    rc = scratch(ctx, 1, 2 * (size_t)n, &dOut);
     if (rc) return rc;
     void* dTo = (char*)dIn + sbp;
+    uint8_t* dNear = nearOut ? (uint8_t*)dOut + n : nullptr;
     MPTG_CUDA(ctx, cudaMemcpyAsync(dIn, from, sb, cudaMemcpyHostToDevice, ctx->stream));
     MPTG_CUDA(ctx, cudaMemcpyAsync(dTo, to, sb, cudaMemcpyHostToDevice, ctx->stream));
-    rc = mptg_link_batch_dev(g, space, dIn, dTo, n, step, (uint8_t*)dOut);
+    rc = mptg_link_batch_dev(g, space, dIn, dTo, n, step, (uint8_t*)dOut, dNear);
     if (rc) return rc;
     MPTG_CUDA(ctx, cudaMemcpyAsync(ok, dOut, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nearOut) MPTG_CUDA(ctx, cudaMemcpyAsync(nearOut, dNear, n, cudaMemcpyDeviceToHost, ctx->stream));
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return checkDeviceErrors(g);
 }

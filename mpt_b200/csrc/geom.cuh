@@ -37,7 +37,8 @@ enum GeomError : unsigned long long { GEOM_ERR_STACK = 1ull, GEOM_ERR_STEPS = 2u
 // implemented in mesh.cu
 int meshCreate(mptg_ctx* ctx, int scalar, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris, MeshData** out);
 void meshDestroy(MeshData* m);
-int meshValidDev(mptg_geom* g, const void* statesDev, uint32_t n, uint8_t* okDev);
+int meshValidDev(mptg_geom* g, const void* statesDev, uint32_t n, uint8_t* okDev, uint8_t* nearDev);
 int meshLinkDev(mptg_geom* g, const mptg_space_desc* space, const void* fromDev, const void* toDev, uint32_t n, double step,
-                uint8_t* okDev);
+                uint8_t* okDev, uint8_t* nearDev);
+double meshBand(const MeshData* m);
 }  // namespace mptg

@@ -42,6 +42,7 @@ struct MeshDev {
     const BvhNode* eNodes;
     const TriPad* eTris;
     uint32_t nR, nE;  // triangle counts
+    uint32_t stageR, stageE;  // nodes [0, stage) of each tree are copied into shared memory by every CTA (breadth-first prefix)
 };
 
 }  // namespace mptg
@@ -55,6 +56,7 @@ struct MeshData {
     unsigned long long* workCounter = nullptr;  // [0] pass 1 / states, [1] pass 2; followed by the donation control words
     mptg::DonBlock* poolBlocks = nullptr;
     int depthR = 0, depthE = 0;
+    float band = 0.0f;  // contact band: 1e-6 x the diagonal of the environment's bounding box (absolute length)
     // per-edge work buffers of link batches (grow-only)
     uint32_t* steps = nullptr;
     unsigned long long* counts = nullptr;
@@ -66,12 +68,21 @@ struct MeshData {
 
 namespace mptg {
 
-constexpr int MESH_WARPS = 4;
+// One large CTA per SM: its warps share ONE copy of the hierarchies' upper levels in shared memory (north_star:
+// "obstacle BVHs staged through shared memory/TMA"), brought in by two bulk copies (cp.async.bulk + mbarrier) when the
+// persistent CTA starts.  r1 ran 6 CTAs of 4 warps per SM and fetched every node pair through L1/L2 (ncu: 2.06 warps
+// per issue waiting on the long scoreboard, 19 of 64 warps active).
+#ifndef MESH_WARPS_PER_CTA
+#define MESH_WARPS_PER_CTA 16
+#endif
+constexpr int MESH_WARPS = MESH_WARPS_PER_CTA;
 #ifndef MESH_CTAS
-#define MESH_CTAS 6
+#define MESH_CTAS 1
 #endif
 constexpr int MESH_MIN_CTAS = MESH_CTAS;  // resident CTAs per SM (caps registers per thread)
+constexpr size_t MESH_SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 constexpr int NODE_STACK = 512;
+constexpr size_t MESH_WARP_SMEM = 512 * 8 + 64 * 8 + 32 * 12 * 4 + 32 * 4;  // stack + triangle queue + transforms + items
 constexpr int STACK_SOFT = NODE_STACK - 64 - 60;  // see the pop rule in meshFlatKernel
 constexpr int TRI_QUEUE = 64;
 
@@ -166,6 +177,68 @@ __device__ __noinline__ bool triTriIntersect(const float P[3][3], const float Qt
     return true;
 }
 
+// The same test with the contact band made visible (near_contact_out of the C ABI).  Per axis g = signed gap of the two
+// projections (> 0: separated), compared with +-tol |axis|:
+//   some axis with g > tol |axis|        -> 0: clearly apart
+//   otherwise bit 0: no axis separates (contact), bit 1: some axis has |g| within tol |axis| -- the largest normalised
+//   gap, which is what decides, lies in (-tol, tol]: a perturbation of that size can flip the decision.
+__device__ __noinline__ int triTriNear(const float P[3][3], const float Qt[3][3], float tol) {
+    float p[3][3], q[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            p[i][c] = P[i][c] - P[0][c];
+            q[i][c] = Qt[i][c] - P[0][c];
+        }
+    float e[3][3], f[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        e[0][c] = p[1][c] - p[0][c];
+        e[1][c] = p[2][c] - p[1][c];
+        e[2][c] = p[0][c] - p[2][c];
+        f[0][c] = q[1][c] - q[0][c];
+        f[1][c] = q[2][c] - q[1][c];
+        f[2][c] = q[0][c] - q[2][c];
+    }
+    bool hit = true, within = false, apart = false;
+    auto axis = [&](const float ax[3]) {
+        const float P0 = dot3(ax, p[0]), P1 = dot3(ax, p[1]), P2 = dot3(ax, p[2]);
+        const float Q0 = dot3(ax, q[0]), Q1 = dot3(ax, q[1]), Q2 = dot3(ax, q[2]);
+        const float mx1 = fmaxf(P0, fmaxf(P1, P2)), mn1 = fminf(P0, fminf(P1, P2));
+        const float mx2 = fmaxf(Q0, fmaxf(Q1, Q2)), mn2 = fminf(Q0, fminf(Q1, Q2));
+        if (mn1 > mx2 || mn2 > mx1) hit = false;  // the decision itself: exactly project6
+        const float g = fmaxf(mn1 - mx2, mn2 - mx1);
+        const float tl = tol * sqrtf(dot3(ax, ax));
+        if (g > tl) apart = true;
+        else if (g > -tl) within = true;
+    };
+    float n1[3], m1[3], ax[3];
+    cross3(e[0], e[1], n1);
+    axis(n1);
+    cross3(f[0], f[1], m1);
+    axis(m1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            cross3(e[i], f[j], ax);
+            axis(ax);
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        cross3(e[i], n1, ax);
+        axis(ax);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        cross3(f[i], m1, ax);
+        axis(ax);
+    }
+    if (apart) return 0;
+    return (hit ? 1 : 0) | (within ? 2 : 0);
+}
+
 __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
     const float4* p = reinterpret_cast<const float4*>(nodes + i);
     const float4 a = __ldg(p), b = __ldg(p + 1);
@@ -173,6 +246,47 @@ __device__ __forceinline__ BvhNode loadNode(const BvhNode* nodes, int i) {
     n.lo[0] = a.x, n.lo[1] = a.y, n.lo[2] = a.z, n.left = __float_as_int(a.w);
     n.hi[0] = b.x, n.hi[1] = b.y, n.hi[2] = b.z, n.right = __float_as_int(b.w);
     return n;
+}
+
+// node i of a tree: from the staged prefix in shared memory, or from global memory below it
+__device__ __forceinline__ BvhNode loadNodeStaged(const BvhNode* __restrict__ sm, uint32_t staged, const BvhNode* __restrict__ gl, int i) {
+    if ((uint32_t)i < staged) {
+        const float4* p = reinterpret_cast<const float4*>(sm + i);
+        const float4 a = p[0], b = p[1];
+        BvhNode n;
+        n.lo[0] = a.x, n.lo[1] = a.y, n.lo[2] = a.z, n.left = __float_as_int(a.w);
+        n.hi[0] = b.x, n.hi[1] = b.y, n.hi[2] = b.z, n.right = __float_as_int(b.w);
+        return n;
+    }
+    return loadNode(gl, i);
+}
+
+// ---- bulk copy global -> shared, completion on an mbarrier (TMA's 1-D form; SASS: UBLKCP)
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCopyG2S(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src),
+                 "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smemAddr(bar)),
+        "r"(parity)
+        : "memory");
 }
 
 // ------------------------------------------------------------------ flat work list + mixed frontier
@@ -213,6 +327,8 @@ struct MeshWork {
     const uint32_t* steps;           // per edge
     const unsigned long long* offs;  // exclusive prefix sums of the per-edge counts of non-coarse states, n+1 entries
     uint8_t* ok;                     // per item, preset to 1
+    uint8_t* nearOut;                // per item, preset to 0 (NEAR kernels only): some checked state came within `tol` of contact
+    float tol;                       // contact band, absolute
     DevSpace<S> sp;
 };
 
@@ -351,19 +467,32 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #endif
 
-template <typename S, int MODE>
+template <typename S, int MODE, bool NEAR>
 __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel(MeshDev m, MeshWork<S> w, unsigned long long* counter,
                                                                                 MeshPool pool, unsigned long long* stats) {
-    __shared__ uint2 sStack[MESH_WARPS][NODE_STACK];
-    __shared__ uint2 sTri[MESH_WARPS][TRI_QUEUE];
-    __shared__ __align__(16) float sXf[MESH_WARPS][MESH_SLOTS][XF_STRIDE];
-    __shared__ uint32_t sItem[MESH_WARPS][MESH_SLOTS];
+    // dynamic shared memory: [staged robot nodes][staged env nodes][per warp: stack, triangle queue, transforms, items]
+    extern __shared__ __align__(128) unsigned char meshSmem[];
+    __shared__ uint64_t stageBar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned ltMask = (1u << lane) - 1u;
-    uint2* stack = sStack[warp];
-    uint2* triQ = sTri[warp];
-    float(*xf)[XF_STRIDE] = sXf[warp];
-    uint32_t* items = sItem[warp];
+    BvhNode* sR = reinterpret_cast<BvhNode*>(meshSmem);
+    BvhNode* sE = sR + m.stageR;
+    unsigned char* wb = reinterpret_cast<unsigned char*>(sE + m.stageE) + (size_t)warp * MESH_WARP_SMEM;
+    uint2* stack = reinterpret_cast<uint2*>(wb);
+    uint2* triQ = stack + NODE_STACK;
+    float(*xf)[XF_STRIDE] = reinterpret_cast<float(*)[XF_STRIDE]>(triQ + TRI_QUEUE);
+    uint32_t* items = reinterpret_cast<uint32_t*>(xf + MESH_SLOTS);
+    {  // stage the upper levels of both hierarchies: one thread issues two bulk copies, everybody waits on the barrier
+        const unsigned bytesR = m.stageR * (unsigned)sizeof(BvhNode), bytesE = m.stageE * (unsigned)sizeof(BvhNode);
+        if (threadIdx.x == 0) mbarInit(&stageBar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbarExpectTx(&stageBar, bytesR + bytesE);
+            if (bytesR) bulkCopyG2S(sR, m.rNodes, bytesR, &stageBar);
+            if (bytesE) bulkCopyG2S(sE, m.eNodes, bytesE, &stageBar);
+        }
+        mbarWait(&stageBar, 0);
+    }
     const unsigned long long total =
         MODE == WORK_STATES ? (unsigned long long)w.n : (unsigned long long)w.n * COARSE_IDS + __ldg(w.offs + w.n);
     const unsigned long long nWarps = (unsigned long long)gridDim.x * MESH_WARPS;
@@ -547,8 +676,8 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             int kind = 0;  // 1: triangle pair, 2: expand robot node, 3: expand env node
             int c0 = 0, c1 = 0;
             if (mine) {
-                const BvhNode a = loadNode(m.rNodes, (int)(pr.x & NODE_MASK));
-                const BvhNode b = loadNode(m.eNodes, (int)pr.y);
+                const BvhNode a = loadNodeStaged(sR, m.stageR, m.rNodes, (int)(pr.x & NODE_MASK));
+                const BvhNode b = loadNodeStaged(sE, m.stageE, m.eNodes, (int)pr.y);
                 const float* X = xf[slot];
                 ++cnt.bv;
                 // robot box (centre c, half extents h in the robot frame) against the env box, separating
@@ -570,7 +699,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                     d[r] = cb - cw;
                     mag += (fabsf(cw) + hw[r]) + (fabsf(cb) + hb[r]);
                 }
-                const float pad = 64.0f * 1.1920928955078125e-07f * mag;
+                const float pad = 64.0f * 1.1920928955078125e-07f * mag + (NEAR ? w.tol : 0.0f);
                 bool ov = true;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) ov = ov && !(fabsf(d[r]) > hw[r] + hb[r] + pad);
@@ -658,14 +787,23 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                     xformPoint(R, t, loc, P[v]);
                     Q[v][0] = ev.x, Q[v][1] = ev.y, Q[v][2] = ev.z;
                 }
-                bool ov = true;
+                bool ov = true, ovBand = true;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const float plo = fminf(P[0][c], fminf(P[1][c], P[2][c])), phi = fmaxf(P[0][c], fmaxf(P[1][c], P[2][c]));
                     const float qlo = fminf(Q[0][c], fminf(Q[1][c], Q[2][c])), qhi = fmaxf(Q[0][c], fmaxf(Q[1][c], Q[2][c]));
                     ov = ov && !(plo > qhi || qlo > phi);
+                    if (NEAR) ovBand = ovBand && !(plo - w.tol > qhi || qlo - w.tol > phi);
                 }
-                if (ov && triTriIntersect(P, Q)) hitBit = 1u << slot;
+                if (NEAR) {
+                    if (ovBand) {
+                        const int r = triTriNear(P, Q, w.tol);
+                        if (ov && (r & 1)) hitBit = 1u << slot;
+                        if (r & 2) w.nearOut[items[slot]] = 1;
+                    }
+                } else if (ov && triTriIntersect(P, Q)) {
+                    hitBit = 1u << slot;
+                }
             }
             __syncwarp();
             nt -= p;
@@ -772,7 +910,38 @@ struct Builder {
     }
 };
 
-int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, void** trisDev, int* depth) {
+// Node order of the device image: the first `prefix` nodes breadth-first from the root (complete upper levels: what a
+// CTA stages in shared memory), everything below them depth-first (a subtree stays contiguous in global memory).
+std::vector<BvhNode> stagingOrder(const std::vector<BvhNode>& in, size_t prefix) {
+    const size_t n = in.size();
+    std::vector<int> order;  // new position -> old index
+    order.reserve(n);
+    std::vector<int> frontier{0};
+    size_t head = 0;
+    while (head < frontier.size() && order.size() < prefix) {  // breadth-first part
+        const int i = frontier[head++];
+        order.push_back(i);
+        if (in[i].left >= 0) frontier.push_back(in[i].left), frontier.push_back(in[i].right);
+    }
+    std::vector<int> stack;
+    for (size_t f = frontier.size(); f-- > head;) stack.push_back(frontier[f]);  // the rest, depth-first, in frontier order
+    while (!stack.empty()) {
+        const int i = stack.back();
+        stack.pop_back();
+        order.push_back(i);
+        if (in[i].left >= 0) stack.push_back(in[i].right), stack.push_back(in[i].left);
+    }
+    std::vector<int> where(n);
+    for (size_t k = 0; k < n; ++k) where[order[k]] = (int)k;
+    std::vector<BvhNode> out(n);
+    for (size_t k = 0; k < n; ++k) {
+        out[k] = in[order[k]];
+        if (out[k].left >= 0) out[k].left = where[out[k].left], out[k].right = where[out[k].right];
+    }
+    return out;
+}
+
+int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, size_t stagePrefix, void** nodesDev, void** trisDev, int* depth, uint32_t* staged) {
     std::vector<HostTri> tris(n);
     std::vector<TriPad> pad(n ? n : 1);
     for (uint32_t i = 0; i < n; ++i)
@@ -787,9 +956,13 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
         b.nodes.reserve(2 * (size_t)n);
         b.build(ids, 0, (int)n, 0);
     } else {
-        b.nodes.push_back(BvhNode{});
+        BvhNode placeholder{};  // never traversed (an empty mesh cannot collide); a leaf, so that nothing hangs off it
+        placeholder.left = placeholder.right = -1;
+        b.nodes.push_back(placeholder);
     }
     *depth = b.maxDepth;
+    if (n) b.nodes = stagingOrder(b.nodes, stagePrefix);
+    *staged = (uint32_t)std::min(stagePrefix, b.nodes.size());
     // device image: centre / half-extent form (what the box test needs), half extents rounded outwards so that
     // [c - h, c + h] contains [lo, hi]
     for (BvhNode& n : b.nodes)
@@ -813,8 +986,18 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, void** nodesDev, v
 int meshCreate(mptg_ctx* ctx, int /*scalar*/, uint32_t nr, const float* robotTris, uint32_t ne, const float* envTris,
                MeshData** out) {
     auto* m = new MeshData();
-    int rc = uploadMesh(ctx, robotTris, nr, &m->mem[0], &m->mem[1], &m->depthR);
-    if (!rc) rc = uploadMesh(ctx, envTris, ne, &m->mem[2], &m->mem[3], &m->depthE);
+    // shared-memory budget of a CTA: its warps' private arrays, then the robot's hierarchy (whole, if it fits in half of
+    // what is left), then the environment's upper levels
+    const size_t nodeBudget = (MESH_SMEM_LIMIT - 1024 - (size_t)MESH_WARPS * MESH_WARP_SMEM) / sizeof(BvhNode);
+    const size_t nodesR = nr ? 2 * (size_t)nr - 1 : 1, nodesE = ne ? 2 * (size_t)ne - 1 : 1;
+    size_t stageR = std::min(nodesR, nodeBudget / 2);
+    const size_t stageE = std::min(nodesE, nodeBudget - stageR);
+    stageR = std::min(nodesR, nodeBudget - stageE);
+    uint32_t sr = 0, se = 0;
+    int rc = uploadMesh(ctx, robotTris, nr, stageR, &m->mem[0], &m->mem[1], &m->depthR, &sr);
+    if (!rc) rc = uploadMesh(ctx, envTris, ne, stageE, &m->mem[2], &m->mem[3], &m->depthE, &se);
+    m->dev.stageR = sr;
+    m->dev.stageE = se;
     if (!rc) {
         cudaError_t e = cudaMalloc(&m->workCounter, CTL_BYTES);
         if (e == cudaSuccess) e = cudaMalloc(&m->poolBlocks, (size_t)POOL_BLOCKS * sizeof(DonBlock));
@@ -834,6 +1017,15 @@ int meshCreate(mptg_ctx* ctx, int /*scalar*/, uint32_t nr, const float* robotTri
     m->dev.eTris = (const TriPad*)m->mem[3];
     m->dev.nR = nr;
     m->dev.nE = ne;
+    if (ne) {  // contact band: 1e-6 of the diagonal of the environment's bounding box (the oracle's definition)
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (size_t i = 0; i < (size_t)ne * 3; ++i)
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = std::fmin(lo[c], (double)envTris[i * 3 + c]);
+                hi[c] = std::fmax(hi[c], (double)envTris[i * 3 + c]);
+            }
+        m->band = (float)(1e-6 * std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2])));
+    }
     *out = m;
     return MPTG_OK;
 }
@@ -849,7 +1041,7 @@ void meshDestroy(MeshData* m) {
 
 namespace {
 
-template <int MODE, typename S>
+template <int MODE, bool NEAR, typename S>
 void launchFlat(mptg_ctx* ctx, MeshData* md, const MeshWork<S>& w, unsigned long long units, int pass, unsigned long long* stats) {
     unsigned long long* counter = md->workCounter + (size_t)pass * CTL_COUNTER_STRIDE;
     unsigned int* ctl = reinterpret_cast<unsigned int*>(md->workCounter + 2 * CTL_COUNTER_STRIDE) + (size_t)pass * CTL_PASS_WORDS;
@@ -858,7 +1050,13 @@ void launchFlat(mptg_ctx* ctx, MeshData* md, const MeshWork<S>& w, unsigned long
     const unsigned long long want = units / (MESH_WARPS * REFILL_MAX) + 1ull;
     const unsigned long long cap = (unsigned long long)ctx->smCount * MESH_MIN_CTAS;
     const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-    meshFlatKernel<S, MODE><<<grid, MESH_WARPS * 32, 0, ctx->stream>>>(md->dev, w, counter, pool, stats);
+    const size_t smem = ((size_t)md->dev.stageR + md->dev.stageE) * sizeof(BvhNode) + (size_t)MESH_WARPS * MESH_WARP_SMEM;
+    static bool attrSet = false;  // per instantiation
+    if (!attrSet) {
+        cudaFuncSetAttribute(meshFlatKernel<S, MODE, NEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MESH_SMEM_LIMIT - 1024));
+        attrSet = true;
+    }
+    meshFlatKernel<S, MODE, NEAR><<<grid, MESH_WARPS * 32, smem, ctx->stream>>>(md->dev, w, counter, pool, stats);
 }
 
 int ensureEdgeWork(mptg_ctx* ctx, MeshData* md, uint32_t n) {
@@ -880,21 +1078,23 @@ int ensureEdgeWork(mptg_ctx* ctx, MeshData* md, uint32_t n) {
 }
 
 template <typename S>
-int meshValidT(mptg_geom* g, const S* states, uint32_t n, uint8_t* ok) {
+int meshValidT(mptg_geom* g, const S* states, uint32_t n, uint8_t* ok, uint8_t* nearOut) {
     mptg_ctx* ctx = g->ctx;
     MeshData* md = g->mesh;
     MPTG_CUDA(ctx, cudaMemsetAsync(ok, 1, n, ctx->stream));
+    if (nearOut) MPTG_CUDA(ctx, cudaMemsetAsync(nearOut, 0, n, ctx->stream));
     if (md->dev.nR == 0 || md->dev.nE == 0) return MPTG_OK;  // nothing can collide
     MPTG_CUDA(ctx, cudaMemsetAsync(md->workCounter, 0, CTL_BYTES, ctx->stream));
     MeshWork<S> w{};
-    w.a = states, w.n = n, w.ok = ok;
-    launchFlat<WORK_STATES>(ctx, md, w, n, 0, g->devStats);
+    w.a = states, w.n = n, w.ok = ok, w.nearOut = nearOut, w.tol = md->band;
+    if (nearOut) launchFlat<WORK_STATES, true>(ctx, md, w, n, 0, g->devStats);
+    else launchFlat<WORK_STATES, false>(ctx, md, w, n, 0, g->devStats);
     MPTG_LAUNCHED(ctx);
     return MPTG_OK;
 }
 
 template <typename S>
-int meshLinkT(mptg_geom* g, const mptg_space_desc* space, const S* from, const S* to, uint32_t n, double step, uint8_t* ok) {
+int meshLinkT(mptg_geom* g, const mptg_space_desc* space, const S* from, const S* to, uint32_t n, double step, uint8_t* ok, uint8_t* nearOut) {
     mptg_ctx* ctx = g->ctx;
     MeshData* md = g->mesh;
     if ((unsigned long long)n * COARSE_IDS > 0xffffffffull) return fail(ctx, MPTG_ERR_CAPACITY, "mptg_link_batch: at most 2^29 mesh edges per call");
@@ -904,14 +1104,16 @@ int meshLinkT(mptg_geom* g, const mptg_space_desc* space, const S* from, const S
     const S invStep = S(1) / (S)step;  // discrete_motion_validator.hpp:64
     meshStepsKernel<S><<<(n + 255) / 256, 256, 0, ctx->stream>>>(sp, from, to, n, invStep, md->steps, md->counts, ok, g->devStats);
     MPTG_LAUNCHED(ctx);
+    if (nearOut) MPTG_CUDA(ctx, cudaMemsetAsync(nearOut, 0, n, ctx->stream));
     if (md->dev.nR == 0 || md->dev.nE == 0) return MPTG_OK;
     size_t scanBytes = md->scanBytes;
     MPTG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(md->scanTemp, scanBytes, md->counts, md->offs, (int)(n + 1u), ctx->stream));
     MPTG_LAUNCHED(ctx);
     MeshWork<S> w{};
-    w.a = from, w.b = to, w.n = n, w.steps = md->steps, w.offs = md->offs, w.ok = ok, w.sp = sp;
+    w.a = from, w.b = to, w.n = n, w.steps = md->steps, w.offs = md->offs, w.ok = ok, w.sp = sp, w.nearOut = nearOut, w.tol = md->band;
     // the length of the list is only known on the device; at least the coarse ids are there
-    launchFlat<WORK_EDGES>(ctx, md, w, (unsigned long long)n * COARSE_IDS, 0, g->devStats);
+    if (nearOut) launchFlat<WORK_EDGES, true>(ctx, md, w, (unsigned long long)n * COARSE_IDS, 0, g->devStats);
+    else launchFlat<WORK_EDGES, false>(ctx, md, w, (unsigned long long)n * COARSE_IDS, 0, g->devStats);
     MPTG_LAUNCHED(ctx);
 #ifdef MESH_DEBUG_STATS
     if (getenv("MPTG_DEBUG_TIMELINE")) {
@@ -955,14 +1157,16 @@ int meshLinkT(mptg_geom* g, const mptg_space_desc* space, const S* from, const S
 
 }  // namespace
 
-int meshValidDev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok) {
-    return g->scalar == MPTG_F32 ? meshValidT<float>(g, (const float*)states, n, ok) : meshValidT<double>(g, (const double*)states, n, ok);
+int meshValidDev(mptg_geom* g, const void* states, uint32_t n, uint8_t* ok, uint8_t* nearOut) {
+    return g->scalar == MPTG_F32 ? meshValidT<float>(g, (const float*)states, n, ok, nearOut) : meshValidT<double>(g, (const double*)states, n, ok, nearOut);
 }
 
 int meshLinkDev(mptg_geom* g, const mptg_space_desc* space, const void* from, const void* to, uint32_t n, double step,
-                uint8_t* ok) {
-    return g->scalar == MPTG_F32 ? meshLinkT<float>(g, space, (const float*)from, (const float*)to, n, step, ok)
-                                 : meshLinkT<double>(g, space, (const double*)from, (const double*)to, n, step, ok);
+                uint8_t* ok, uint8_t* nearOut) {
+    return g->scalar == MPTG_F32 ? meshLinkT<float>(g, space, (const float*)from, (const float*)to, n, step, ok, nearOut)
+                                 : meshLinkT<double>(g, space, (const double*)from, (const double*)to, n, step, ok, nearOut);
 }
+
+double meshBand(const MeshData* m) { return m ? (double)m->band : 0.0; }
 
 }  // namespace mptg

@@ -354,8 +354,8 @@ int prrtWaveT(mptg_prrt* p, uint32_t W) {
                                                       (S)p->range, (S*)p->from, (S*)p->to, p->alive);
     MPTG_LAUNCHED(ctx);
     // valid, link (prrt.hpp:439-441)
-    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid)) return rc;
-    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink)) return rc;
+    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid, nullptr)) return rc;
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink, nullptr)) return rc;
     prrtFlagKernel<<<grid, 128, 0, ctx->stream>>>(p->alive, p->okValid, p->okLink, W, p->keep);
     MPTG_LAUNCHED(ctx);
     size_t bytes = p->selBytes;
@@ -676,7 +676,7 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
     cudaStream_t st = ctx->stream;
     *firstOut = p->size, *addedOut = 0;
     // valid (:299), keep the valid samples in sample order
-    if (int rc = mptg_valid_batch_dev(p->geom, p->samples, W, p->okValid)) return rc;
+    if (int rc = mptg_valid_batch_dev(p->geom, p->samples, W, p->okValid, nullptr)) return rc;
     uint32_t V = 0;
     if (int rc = selectFlagged(p, p->okValid, W, p->sel, &V)) return rc;
     if (V == 0) return MPTG_OK;
@@ -709,7 +709,7 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
         pprmEdgeKernel<S><<<(unsigned)((E + 127) / 128), 128, 0, st>>>(p->sel2, nSel, k, D, (const S*)p->cand, (const S*)p->nodes, p->nnIdx, p->nnCnt,
                                                                          (S*)p->from, (S*)p->to);
         MPTG_LAUNCHED(ctx);
-        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, (uint32_t)E, p->linkStep, p->okEdge)) return rc;
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, (uint32_t)E, p->linkStep, p->okEdge, nullptr)) return rc;
     }
     pprmAppendKernel<S><<<(nSel + 127) / 128, 128, 0, st>>>(sp, p->sel2, nSel, k, p->stride, (const S*)p->cand, p->nnIdx, (const S*)p->nnDist, p->nnCnt,
                                                           p->okEdge, p->size, p->hasGoal ? (const S*)p->goal : nullptr, (S)p->goalRadius, marks,
@@ -1216,8 +1216,8 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
     starSteerKernel<S><<<grid, 128, 0, st>>>(sp, (const S*)p->nodes, (const S*)p->samples, p->nearIdx, (const S*)p->nearDist, p->nearCnt, W,
                                              (S)p->range, (S*)p->from, (S*)p->to, (S*)p->dNew, p->alive);
     MPTG_LAUNCHED(ctx);
-    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid)) return rc;                              // :539
-    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink)) return rc;  // :545
+    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid, nullptr)) return rc;                              // :539
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink, nullptr)) return rc;  // :545
     prrtFlagKernel<<<grid, 128, 0, st>>>(p->alive, p->okValid, p->okLink, W, p->keep);
     MPTG_LAUNCHED(ctx);
     uint32_t nS = 0;
@@ -1248,7 +1248,7 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
         starEdgeKernel<S><<<(nE + 127) / 128, 128, 0, st>>>(p->ids, nE, k, D, true, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
                                                            (S*)p->eTo, p->inv);
         MPTG_LAUNCHED(ctx);
-        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nE, p->linkStep, p->okEdge)) return rc;
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nE, p->linkStep, p->okEdge, nullptr)) return rc;
     }
     starAppendKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(sp, nS, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank,
                                                          p->checked, p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
@@ -1266,7 +1266,7 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
         starEdgeKernel<S><<<(nR + 127) / 128, 128, 0, st>>>(p->ids, nR, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
                                                            (S*)p->eTo, nullptr);
         MPTG_LAUNCHED(ctx);
-        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nR, p->linkStep, p->okEdge)) return rc;
+        if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nR, p->linkStep, p->okEdge, nullptr)) return rc;
         MPTG_CUDA(ctx, cudaMemsetAsync(p->bestKey, 0xFF, (size_t)p->size * 8, st));
         MPTG_CUDA(ctx, cudaMemsetAsync(p->bestCand, 0xFF, (size_t)p->size * 4, st));
         MPTG_CUDA(ctx, cudaMemsetAsync(p->delta, 0, (size_t)total * sizeof(S), st));

@@ -555,6 +555,63 @@ bool triTriIntersect(const S P[3][3], const S Qt[3][3], double* marginOut = null
     return hit;
 }
 
+// ---- second, independent triangle-triangle formulation (test infrastructure for the contact tests).
+// FCL is absent, so the 17-axis SAT above cannot be pinned to it; what can be checked is that a formulation built from
+// different arithmetic -- orientation predicates (the determinants Guigue & Devillers' test is built from), evaluated in
+// double -- gives the same answer wherever the configuration is not within the contact band.  Closed sets: touching
+// counts as contact, as above.  Two triangles meet iff an edge of one meets the other triangle.
+inline double orient3d(const double* a, const double* b, const double* c, const double* d) {
+    const double adx = a[0] - d[0], ady = a[1] - d[1], adz = a[2] - d[2];
+    const double bdx = b[0] - d[0], bdy = b[1] - d[1], bdz = b[2] - d[2];
+    const double cdx = c[0] - d[0], cdy = c[1] - d[1], cdz = c[2] - d[2];
+    return adx * (bdy * cdz - bdz * cdy) - ady * (bdx * cdz - bdz * cdx) + adz * (bdx * cdy - bdy * cdx);
+}
+inline double orient2d(const double* a, const double* b, const double* c) {
+    return (b[0] - a[0]) * (c[1] - a[1]) - (b[1] - a[1]) * (c[0] - a[0]);
+}
+inline bool onSegment2d(const double* a, const double* b, const double* c) {  // c collinear with a,b: inside [a,b]?
+    return std::min(a[0], b[0]) <= c[0] && c[0] <= std::max(a[0], b[0]) && std::min(a[1], b[1]) <= c[1] && c[1] <= std::max(a[1], b[1]);
+}
+inline bool segSeg2d(const double* a, const double* b, const double* c, const double* d) {
+    const double o1 = orient2d(a, b, c), o2 = orient2d(a, b, d), o3 = orient2d(c, d, a), o4 = orient2d(c, d, b);
+    if (((o1 > 0 && o2 < 0) || (o1 < 0 && o2 > 0)) && ((o3 > 0 && o4 < 0) || (o3 < 0 && o4 > 0))) return true;
+    if (o1 == 0 && onSegment2d(a, b, c)) return true;
+    if (o2 == 0 && onSegment2d(a, b, d)) return true;
+    if (o3 == 0 && onSegment2d(c, d, a)) return true;
+    if (o4 == 0 && onSegment2d(c, d, b)) return true;
+    return false;
+}
+inline bool pointInTri2d(const double* x, const double* p, const double* q, const double* r) {
+    const double o1 = orient2d(p, q, x), o2 = orient2d(q, r, x), o3 = orient2d(r, p, x);
+    return (o1 >= 0 && o2 >= 0 && o3 >= 0) || (o1 <= 0 && o2 <= 0 && o3 <= 0);
+}
+// closed segment [a,b] against closed triangle (p,q,r)
+inline bool segTriPredicates(const double* a, const double* b, const double* p, const double* q, const double* r) {
+    const double sa = orient3d(p, q, r, a), sb = orient3d(p, q, r, b);
+    if ((sa > 0 && sb > 0) || (sa < 0 && sb < 0)) return false;
+    if (sa == 0 && sb == 0) {  // the segment lies in the triangle's plane: decide in 2-D, dropping the normal's largest component
+        const double e0[3] = {q[0] - p[0], q[1] - p[1], q[2] - p[2]}, e1[3] = {r[0] - p[0], r[1] - p[1], r[2] - p[2]};
+        const double n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+        int drop = 0;
+        if (std::fabs(n[1]) > std::fabs(n[drop])) drop = 1;
+        if (std::fabs(n[2]) > std::fabs(n[drop])) drop = 2;
+        const int u = (drop + 1) % 3, v = (drop + 2) % 3;
+        const double A[2] = {a[u], a[v]}, B[2] = {b[u], b[v]}, P[2] = {p[u], p[v]}, Q[2] = {q[u], q[v]}, R[2] = {r[u], r[v]};
+        return pointInTri2d(A, P, Q, R) || pointInTri2d(B, P, Q, R) || segSeg2d(A, B, P, Q) || segSeg2d(A, B, Q, R) || segSeg2d(A, B, R, P);
+    }
+    // the segment meets the plane in one point (possibly an end point): that point is inside the triangle iff the
+    // line (a,b) has the three edges on one side
+    const double o1 = orient3d(a, b, p, q), o2 = orient3d(a, b, q, r), o3 = orient3d(a, b, r, p);
+    return (o1 >= 0 && o2 >= 0 && o3 >= 0) || (o1 <= 0 && o2 <= 0 && o3 <= 0);
+}
+inline bool triTriPredicates(const double P[3][3], const double Q[3][3]) {
+    for (int i = 0; i < 3; ++i) {
+        if (segTriPredicates(P[i], P[(i + 1) % 3], Q[0], Q[1], Q[2])) return true;
+        if (segTriPredicates(Q[i], Q[(i + 1) % 3], P[0], P[1], P[2])) return true;
+    }
+    return false;
+}
+
 template <typename S>
 struct Aabb {
     S lo[3], hi[3];
@@ -640,6 +697,7 @@ template <typename S>
 struct MeshPair {
     Bvh<S> robot, env;  // robot in its local frame, env in world frame
     double scale = 1;   // env AABB diagonal, used for the relative near-contact band
+    bool predicates = false;  // decide triangle pairs with triTriPredicates (on the same transformed vertices, in double)
     struct Counters {
         uint64_t bvTests = 0, triTests = 0, states = 0;
     };
@@ -717,6 +775,11 @@ struct MeshPair {
                     bool hit = triTriIntersect<S>(P, env.tris[b.tri].v, &m);
                     if (hit && pb.overlaps(b.box, 0)) collide = true;
                     minMargin = std::min(minMargin, m);
+                } else if (predicates) {
+                    double Pd[3][3], Qd[3][3];
+                    for (int v = 0; v < 3; ++v)
+                        for (int c = 0; c < 3; ++c) Pd[v][c] = (double)P[v][c], Qd[v][c] = (double)env.tris[b.tri].v[v][c];
+                    if (triTriPredicates(Pd, Qd)) return false;
                 } else if (triTriIntersect<S>(P, env.tris[b.tri].v)) {
                     return false;
                 }

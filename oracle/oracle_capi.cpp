@@ -274,6 +274,26 @@ void* orc_mesh_pair_create(int scalar, uint32_t nr, const float* robotTris, uint
 
 void orc_geom_destroy(void* g) { delete (Geom*)g; }
 
+// decide triangle pairs of mesh states with the orientation-predicate formulation instead of the SAT (contact tests)
+void orc_mesh_use_predicates(void* geom, int on) {
+    Geom& g = *(Geom*)geom;
+    g.meshF.predicates = g.meshD.predicates = on != 0;
+}
+
+// n triangle pairs (9 doubles each, world coordinates): the 17-axis SAT with its margin, and the predicate formulation
+int orc_tri_pairs(uint32_t n, const double* P, const double* Q, uint8_t* satOut, double* marginOut, uint8_t* predOut) {
+    for (uint32_t i = 0; i < n; ++i) {
+        double p[3][3], q[3][3];
+        for (int v = 0; v < 3; ++v)
+            for (int c = 0; c < 3; ++c) p[v][c] = P[(size_t)i * 9 + v * 3 + c], q[v][c] = Q[(size_t)i * 9 + v * 3 + c];
+        double m;
+        satOut[i] = triTriIntersect<double>(p, q, &m) ? 1 : 0;
+        marginOut[i] = m;
+        predOut[i] = triTriPredicates(p, q) ? 1 : 0;
+    }
+    return 0;
+}
+
 int orc_valid_batch(void* geom, const void* states, uint32_t n, uint8_t* ok, double* margin) {
     Geom& g = *(Geom*)geom;
     return g.scalar == MPTG_F32 ? validBatch<float>(g, (const float*)states, n, ok, margin)

@@ -1,6 +1,8 @@
-"""Build the C++ host-layer programs (include/mptg/*.hpp) against libmptg.so, in-tree.
+"""TEST INFRASTRUCTURE: build the C++ host-layer test programs and demo mains (include/mptg/*.hpp) against
+libmptg.so, in-tree.  (Lives under tests/ because the mock and the reference-parity program include oracle/ headers;
+nothing under mpt_b200/ or include/ may.)
 
-    python -m mpt_b200.build_host
+    python -m tests.build_host
 
 Produces tests/cpp/_build/planner_test and the demo mains under demos/_build/.  They run on a GPU
 box only (libmptg.so has no CPU fallback); the binaries travel with the repo snapshot.
@@ -32,7 +34,7 @@ def build_program(src: Path, out: Path, lib_dir: Path, lib: str, defines=()) -> 
 
 
 def build() -> list[Path]:
-    from . import build as b
+    from mpt_b200 import build as b
 
     b.build()
     outs = [build_program(ROOT / "tests" / "cpp" / "planner_test.cpp", ROOT / "tests" / "cpp" / "_build" / "planner_test", b.LIBDIR, "mptg")]
@@ -72,7 +74,7 @@ def build_reference_parity(mock: bool = True) -> Path | None:
         build_mock()
         lib_dir, lib, defines = bdir, "mptg_mock", ["-DMPTG_TEST_MOCK_BACKEND"]
     else:
-        from . import build as b
+        from mpt_b200 import build as b
 
         b.build()
         lib_dir, lib, defines = b.LIBDIR, "mptg", []

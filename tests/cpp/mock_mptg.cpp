@@ -157,13 +157,15 @@ int mptg_geom_destroy(mptg_geom* g) {
 }
 int mptg_geom_kind(const mptg_geom* g) { return g->kind; }
 
-int mptg_valid_batch(mptg_geom* g, const void* st, uint32_t n, uint8_t* ok) {
+int mptg_valid_batch(mptg_geom* g, const void* st, uint32_t n, uint8_t* ok, uint8_t* near) {
+    if (near) memset(near, 0, n);
     for (uint32_t i = 0; i < n; ++i)
         ok[i] = g->scalar == MPTG_F32 ? validOne<float>(g, (const float*)st + (size_t)i * g->D) : validOne<double>(g, (const double*)st + (size_t)i * g->D);
     ++g->ctx->launches;
     return MPTG_OK;
 }
-int mptg_link_batch(mptg_geom* g, const mptg_space_desc* sp, const void* from, const void* to, uint32_t n, double step, uint8_t* ok) {
+int mptg_link_batch(mptg_geom* g, const mptg_space_desc* sp, const void* from, const void* to, uint32_t n, double step, uint8_t* ok, uint8_t* near) {
+    if (near) memset(near, 0, n);
     for (uint32_t i = 0; i < n; ++i) {
         if (g->scalar == MPTG_F32) {
             const float* a = (const float*)from + (size_t)i * g->D;

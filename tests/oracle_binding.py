@@ -140,6 +140,15 @@ class Oracle:
         cc = np.ascontiguousarray(circles, dtype=np.float64).reshape(-1, 3)
         return OracleGeom(self, self.lib.orc_linkarm_create(scalar, ln.shape[0], _ptr(ln), float(link_radius), cc.shape[0], _ptr(cc)), scalar, ln.shape[0])
 
+    def tri_pairs(self, P, Q):
+        """n triangle pairs [n,3,3] (double): (SAT decision, SAT margin, orientation-predicate decision)."""
+        P = np.ascontiguousarray(P, dtype=np.float64).reshape(-1, 9)
+        Q = np.ascontiguousarray(Q, dtype=np.float64).reshape(-1, 9)
+        sat, pred = np.empty(P.shape[0], np.uint8), np.empty(P.shape[0], np.uint8)
+        margin = np.empty(P.shape[0], np.float64)
+        self.lib.orc_tri_pairs(C.c_uint32(P.shape[0]), _ptr(P), _ptr(Q), _ptr(sat), _ptr(margin), _ptr(pred))
+        return sat, margin, pred
+
     def mesh_pair(self, robot_tris, env_tris, space, step):
         rt = np.ascontiguousarray(robot_tris, dtype=np.float32).reshape(-1, 9)
         et = np.ascontiguousarray(env_tris, dtype=np.float32).reshape(-1, 9)
@@ -197,6 +206,10 @@ class OracleGeom:
         self.orc.lib.orc_link_batch(self.h, sp, _ptr(a), _ptr(b), a.shape[0], float(self.step), _ptr(ok), _ptr(nc), float(tol_rel), C.byref(states))
         self.last_states = states.value
         return (ok, nc) if with_near_contact else ok
+
+    def use_predicates(self, on=True):
+        """Decide triangle pairs with the orientation-predicate formulation (oracle.hpp triTriPredicates)."""
+        self.orc.lib.orc_mesh_use_predicates(self.h, int(on))
 
     def counters(self):
         out = (C.c_uint64 * 4)()

@@ -930,3 +930,118 @@ def test_mesh_golden_and_degenerate(ctx):
     tri = m.Scenario.mesh_pair(ctx, [[[0, 0, 0], [1, 0, 0], [0, 1, 0]]], [[[0.2, 0.2, -0.5], [0.2, 0.2, 0.5], [0.8, 0.8, 0.5]]], sp, 0.5)
     st = np.array([[0, 0, 0, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0, 2.0]], dtype=np.float32)
     assert list(tri.valid(st)) == [0, 1]
+
+
+# ------------------------------------------------------------------ contact band ("0 near contact" everywhere)
+def test_mesh_constructed_contact_cases(ctx, oracle):
+    """Touching configurations built so that float arithmetic is exact (tests/contact_cases.py): vertex on face, edge on
+    edge, edge in face, coplanar overlap, coplanar corner, vertex on vertex, each displaced by 0, +-1, +-16, +-1024,
+    +-4096 ulp along the separating direction.  For float states the kernels and the oracle run the same arithmetic, so
+    the decisions must be equal INSIDE the band too, equal to the answer known by construction, and the exported
+    near-contact flags must cover every state the oracle places inside the band."""
+    from tests import contact_cases as cc
+
+    sp = m.se3_space(50, 1)
+    total_near = 0
+    for name, case in cc.CASES.items():
+        robot = np.array([case["robot"]], np.float32)
+        sc = m.Scenario.mesh_pair(ctx, robot, cc.ENV, sp, 0.5)
+        og = oracle.mesh_pair(robot, cc.ENV, sp, 0.5)
+        assert abs(sc.contact_band() - cc.BAND) < 1e-6 * cc.BAND
+        st = cc.states_for(case)
+        ok, near = sc.valid(st, with_near_contact=True)
+        want, margin = og.valid(st, with_margin=True)
+        onear = np.abs(margin) < cc.BAND
+        print(f"contact {name}: collide {list(1 - ok)}, near (gpu) {list(near)}, near (oracle) {list(onear.astype(int))}")
+        assert np.array_equal(ok, want) and np.array_equal(1 - ok, cc.expected_contact(name)), name
+        assert np.array_equal(sc.valid(st), ok)                     # the plain kernel decides the same
+        assert (near[onear] == 1).all(), name                        # the export covers the oracle's band
+        assert (near[cc.in_band()] == 1).all(), name                 # +-16 ulp of touching is inside the band
+        total_near += int(near.sum())
+        # as edges from a far, free state: `to` is always checked (discrete_motion_validator.hpp:75)
+        far = np.tile(np.array([[0, 0, 0, 1, 2.0, 2.0, 9.0]], np.float32), (len(st), 1))
+        eok, enear = sc.link(far, st, with_near_contact=True)
+        wok, wnear = og.link(far, st, with_near_contact=True)
+        assert np.array_equal(eok, wok), name
+        assert (enear[(wnear == 1) & (eok == 1)] == 1).all(), name   # valid edges: every state was examined
+        assert (eok[cc.expected_contact(name) == 1] == 0).all(), name
+    assert total_near > 0
+    # nothing near: flags stay 0
+    sc = m.Scenario.mesh_pair(ctx, np.array([cc.CASES["vertex_on_face"]["robot"]], np.float32), cc.ENV, sp, 0.5)
+    ok, near = sc.valid(np.array([[0, 0, 0, 1, 2.0, 2.0, 9.0]], np.float32), with_near_contact=True)
+    assert list(ok) == [1] and list(near) == [0]
+
+
+def _first_contact(og, start, direction, lo=0.0, hi=1.0, iters=60):
+    """bisection on the oracle: largest s in [lo, hi] with state(start + s * direction) free (translations only)"""
+    def at(s):
+        q = start.copy()
+        q[4:7] += s * direction
+        return q
+    assert og.valid(at(lo)[None])[0] == 1 and og.valid(at(hi)[None])[0] == 0
+    for _ in range(iters):
+        mid = 0.5 * (lo + hi)
+        if og.valid(at(mid)[None])[0] == 1:
+            lo = mid
+        else:
+            hi = mid
+    return lo, hi, at
+
+
+@pytest.mark.parametrize("scalar", [m.F32, m.F64])
+def test_mesh_sliding_through_first_contact(ctx, oracle, scalar):
+    """Generic rotations: the robot is pushed along random directions until the oracle reports first contact (bisection
+    to the last bit), then states are laid out at -1e-3 ... +1e-3 of that point, densest around it.  Double states are
+    where the kernels (float collision test on the rounded pose) and the double-precision oracle may disagree: only
+    inside the band, and every disagreement must carry the exported flag."""
+    dt = np.float32 if scalar == m.F32 else np.float64
+    sp = m.se3_space(50, 1, scalar)
+    robot, env, step = _mesh_scene()
+    sc = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
+    og = oracle.mesh_pair(robot, env, sp, step)
+    band = sc.contact_band()
+    rng = np.random.default_rng(31)
+    cand = W.se3_states(400, 33, -45.0, 45.0, dtype=dt)
+    free = cand[og.valid(cand) == 1]
+    states, n_contacts = [], 0
+    for q0 in free[:40]:
+        d = rng.normal(size=3)
+        d = (d / np.linalg.norm(d) * 120.0).astype(dt)
+        end = q0.copy()
+        end[4:7] += d
+        if og.valid(end[None])[0] == 1:
+            # look for a colliding point along the ray
+            ss = np.linspace(0, 1, 65)[1:]
+            hits = [s for s in ss if og.valid((q0 + np.concatenate([np.zeros(4, dt), (s * d).astype(dt)]))[None])[0] == 0]
+            if not hits:
+                continue
+            hi = hits[0]
+        else:
+            hi = 1.0
+        lo, hi, at = _first_contact(og, q0.astype(dt), d, 0.0, hi)
+        n_contacts += 1
+        for off in (0.0, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3):
+            for sgn in (-1.0, 1.0):
+                states.append(at(lo + sgn * off / 120.0))   # off in length units along the ray
+    st = np.asarray(states, dtype=dt)
+    assert n_contacts >= 10
+    ok, near = sc.valid(st, with_near_contact=True)
+    want, margin = og.valid(st, with_margin=True)
+    onear = np.abs(margin) < band
+    diff = ok != want
+    print(f"first contact ({'f32' if scalar == m.F32 else 'f64'}): {len(st)} states around {n_contacts} contacts, {int(onear.sum())} inside the band "
+          f"(oracle), {int(near.sum())} flagged by the kernel, {int(diff.sum())} decisions differ")
+    assert onear.sum() > 0 and near.sum() > 0
+    assert not (diff & ~onear).any()          # outside the band: identical
+    assert (near[diff] == 1).all()            # a differing decision is always a reported one
+    if scalar == m.F32:
+        assert not diff.any()                 # same arithmetic: identical inside the band too
+    assert np.array_equal(sc.valid(st), ok)
+    # the same as edge end points
+    a = np.repeat(free[:1], len(st), axis=0).astype(dt)
+    eok, enear = sc.link(a, st, with_near_contact=True)
+    wok, wnear = og.link(a, st, with_near_contact=True)
+    ediff = eok != wok
+    print(f"   as edges: {int(wnear.sum())} near-contact edges (oracle), {int(enear.sum())} flagged, {int(ediff.sum())} differ")
+    assert not (ediff & (wnear == 0)).any()
+    assert (enear[ediff] == 1).all()

@@ -23,7 +23,7 @@ def _run(path):
 
 
 def test_wave_planners_host_logic_with_mock_backend():
-    from mpt_b200 import build_host
+    from tests import build_host
 
     out = _run(build_host.build_mock())
     for name in ("PRRT:", "PRRT wave 64:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
@@ -37,7 +37,7 @@ def test_wave_planners_build_the_reference_planners_graphs():
     """Row a11: Planner<Scenario, PRRT / PRRTStar / PPRM <wave_size<1>>> over the CPU mock of the ABI against the
     reference's own planner classes in the same process (tests/cpp/reference_planner_parity.cpp): identical vertices,
     edges, solution paths and PRRT* solution costs.  Needs /root/reference to compile the reference side."""
-    from mpt_b200 import build_host
+    from tests import build_host
 
     prog = build_host.build_reference_parity(mock=True)
     if prog is None:
@@ -49,7 +49,7 @@ def test_wave_planners_build_the_reference_planners_graphs():
 
 def test_demo_programs_compile():
     """The demo mains and the GPU test program build against include/mptg and libmptg.so."""
-    from mpt_b200 import build_host
+    from tests import build_host
 
     for p in build_host.build():
         assert p.exists()
@@ -57,7 +57,7 @@ def test_demo_programs_compile():
 
 @pytest.mark.gpu
 def test_wave_planners_on_gpu():
-    from mpt_b200 import build_host
+    from tests import build_host
 
     prog = ROOT / "tests" / "cpp" / "_build" / "planner_test"
     if not prog.exists():
@@ -72,7 +72,7 @@ def test_wave_planners_on_gpu_build_the_reference_planners_graphs():
     """The same comparison with the wave planners running on the device (libmptg.so): the reference's planner classes
     run on the host in the same process; graphs must be identical.  The program is built where /root/reference
     exists and travels with the snapshot."""
-    from mpt_b200 import build_host
+    from tests import build_host
 
     prog = build_host.build_reference_parity(mock=False)
     if prog is None:
@@ -85,7 +85,7 @@ def test_wave_planners_on_gpu_build_the_reference_planners_graphs():
 @pytest.mark.gpu
 def test_demo_scenarios_on_gpu():
     """BASELINE.json configs[0..3]: the four demo scenarios solve on the device."""
-    from mpt_b200 import build_host
+    from tests import build_host
 
     prog = ROOT / "demos" / "_build" / "planning_demos"
     if not prog.exists():

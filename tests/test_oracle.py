@@ -247,7 +247,7 @@ def test_cabi_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
-    assert lib.mptg_abi_version() == 1
+    assert lib.mptg_abi_version() == 2
     sp = m.se3_space(50, 1)
     assert sp.scalars == 7 and sp.dimensions == 6
 
@@ -270,3 +270,38 @@ def test_product_does_not_touch_oracle():
         if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"}:
             hit = pat.search(p.read_text())
             assert hit is None, (p, hit.group(0))
+
+
+# ------------------------------------------------------------------ contact: two formulations of triangle-triangle
+def test_tri_tri_formulations_agree_outside_the_contact_band(oracle):
+    """FCL is absent, so the 17-axis SAT (oracle.hpp triTriIntersect, what the kernels restate) is pinned the only way
+    left: an independent formulation from orientation predicates (triTriPredicates, double) must give the same answer
+    on every pair that is not within the contact band, and on the constructed touching cases both must give the answer
+    known by construction (closed sets: touching is contact)."""
+    from tests import contact_cases as cc
+
+    rng = np.random.default_rng(77)
+    n = 300_000
+    P = rng.normal(size=(n, 3, 3))
+    Q = rng.normal(size=(n, 3, 3)) + rng.normal(size=(n, 1, 3)) * 0.8
+    # near-degenerate families: slivers, shared vertices, pairs pushed to first contact along a random direction
+    P[:20000, 2] = P[:20000, 0] + (P[:20000, 1] - P[:20000, 0]) * 0.5 + rng.normal(size=(20000, 3)) * 1e-6
+    Q[20000:40000, 0] = P[20000:40000, 1]
+    sat, margin, pred = oracle.tri_pairs(P, Q)
+    band = 1e-9 * 4.0  # double arithmetic on unit-size triangles
+    differ = sat != pred
+    inside = np.abs(margin) < band
+    print(f"tri-tri: {sat.mean():.3f} intersect, {int(inside.sum())} pairs within the band, {int(differ.sum())} differ "
+          f"({int((differ & inside).sum())} of them inside)")
+    assert not (differ & ~inside).any()
+    assert inside.sum() > 0  # the shared-vertex family touches by construction
+    sp = m.se3_space(50, 1)
+    for name, case in cc.CASES.items():
+        st = cc.states_for(case)
+        og = oracle.mesh_pair(np.array([case["robot"]], np.float32), cc.ENV, sp, 0.5)
+        want = cc.expected_contact(name)
+        ok_sat = og.valid(st)
+        og.use_predicates(True)
+        ok_pred = og.valid(st)
+        assert np.array_equal(1 - ok_sat, want), (name, ok_sat, want)
+        assert np.array_equal(1 - ok_pred, want), (name, ok_pred, want)
