@@ -8,10 +8,13 @@ the only configuration the metric is quoted on that needs a GPU):
       (SO(3) weight 50, L2 weight 1, float32)            -> `value` = queries/s
     * batched edge validity: E = 65,536 SE(3) edges through DiscreteMotionValidator against a synthetic
       rigid-body mesh pair (~1k robot / ~4k environment triangles) -> `edges_per_s`
-Multi-GPU (torchrun, one rank per GPU): the path shards by independent units -- every rank owns its
-own query wave and edge wave; the tree (28 MB) and the meshes are replicated, so there is no
-data-path collective (weak scaling).  The tree-sharded variant with its NCCL all-gather + merge is
-measured separately and reported under "sharded_tree" (it is what a tree too large for one HBM needs).
+Multi-GPU (torchrun, one rank per GPU), as north_star splits the path:
+    * kNN: the TREE is sharded spatially across the ranks and ONE 65,536-query wave is answered by all of them
+      (mptg_knn_query_sharded: root bounds -> home search -> bounded search -> NCCL exchange -> merge); every rank
+      returns its slice of the wave.  `value` = 65,536 / time of the slowest rank: "scaling": "strong".
+    * edges: independent units -- every rank checks its own 65,536-edge wave against replicated meshes, no collective
+      (`edges_per_s` is the aggregate, weak).
+    * `replicated_tree`: the zero-collective alternative for trees that fit one HBM (every rank its own wave), for reference.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 """
@@ -43,11 +46,17 @@ F_BV, F_TRI = 82.0, 170.0  # flop per box-pair test (box transform + world-axis 
 # stage adds 39 more when it is reached -- not counted) / per 17-axis SAT
 
 
+def _profile_json(name: str):
+    try:
+        return json.loads((ROOT / "profiles" / name).read_text())
+    except Exception:
+        return {}
+
+
 def measured_traffic(kernel: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture."""
-    p = ROOT / "profiles" / "r1_traffic.json"
     try:
-        return float(json.loads(p.read_text())[kernel]["traffic_bytes_per_launch"])
+        return float(_profile_json("r2_traffic.json")[kernel]["traffic_bytes_per_launch"])
     except Exception:
         return None
 
@@ -116,7 +125,8 @@ CONFIG = {
     "mesh_pair": "synthetic bent-tube robot (~1k tris) vs environment (~4k tris), DiscreteMotionValidator resolution 0.01",
     "edge_length": f"<= {EDGE_TRANS} units, <= {EDGE_ANGLE} rad",
     "l2": "256 MiB memset between steps (L2 flush), outside the per-step event intervals",
-    "parallelism": "one rank per GPU; queries and edges sharded, tree + meshes replicated, no data-path collective",
+    "parallelism": "one rank per GPU; kNN: tree sharded spatially, one wave answered by all ranks (NCCL exchange + merge, strong scaling); "
+                   "edges: one wave per rank, meshes replicated, no collective",
 }
 
 
@@ -127,13 +137,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import mpt_b200 as m
     from tests import oracle_binding
 
     orc = oracle_binding.load()
     orc.set_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     tree, queries, robot, env, step, ea, eb = workload(0)
-    sp = m.se3_space(SO3_W, L2_W)
+    sp = oracle_binding.se3_space(SO3_W, L2_W)  # descriptor built without loading libmptg.so: nothing of the product runs here
     t0 = time.perf_counter()
     otree = orc.tree(sp, tree)
     build_s = time.perf_counter() - t0
@@ -193,28 +202,62 @@ def run_ours(args):
     tree, queries, robot, env, step, ea, eb = workload(rank)
     ctx = m.Context(local)
     sp = m.se3_space(SO3_W, L2_W)
-    nn = m.Nearest(ctx, sp, N_TREE)
-    nn.insert(tree)
-    nn.build_index()
+    comm = None
+    q_first, q_count = 0, Q_WAVE
+    if world == 1:
+        nn = m.Nearest(ctx, sp, N_TREE)
+        nn.insert(tree)
+        nn.build_index()
+    else:
+        # the tree sharded spatially (fixed halving of the translation bounds), ONE wave for all ranks (rank 0's queries)
+        from mpt_b200 import sharding
+        from mpt_b200 import workloads as W
+
+        queries = W.se3_states(Q_WAVE, W.QUERY_SEED)
+        uid = [m.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = m.Comm(ctx, uid[0], rank, world)
+        cells = sharding.spatial_cells(tree, (4, 5, 6), -100.0, 100.0, world)
+        ids = np.nonzero(cells == rank)[0].astype(np.uint32)
+        nn = m.Nearest(ctx, sp, len(ids) + 64, m.KNN_BVH)
+        nn.insert_ids(tree[ids], ids)
+        comm.sync(nn)  # index the shard, exchange the shards' top-level boxes
+        q_first, q_count = comm.slice(Q_WAVE)
     mesh = m.Scenario.mesh_pair(ctx, robot, env, sp, step)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     # device-resident inputs / outputs for `value`
     d_q = torch.from_numpy(queries).to(dev)
-    d_idx = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
-    d_dist = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
-    d_cnt = torch.empty(Q_WAVE, dtype=torch.int32, device=dev)
+    d_idx = torch.empty((q_count, K_NN), dtype=torch.int32, device=dev)
+    d_dist = torch.empty((q_count, K_NN), dtype=torch.float32, device=dev)
+    d_cnt = torch.empty(q_count, dtype=torch.int32, device=dev)
     d_ea, d_eb = torch.from_numpy(ea).to(dev), torch.from_numpy(eb).to(dev)
     d_ok = torch.empty(E_WAVE, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # pinned host buffers for `e2e` (the reference-facing host-pointer C-ABI calls)
     h_q = torch.from_numpy(queries).pin_memory()
-    h_idx = torch.empty((Q_WAVE, K_NN), dtype=torch.int32).pin_memory()
-    h_dist = torch.empty((Q_WAVE, K_NN), dtype=torch.float32).pin_memory()
-    h_cnt = torch.empty(Q_WAVE, dtype=torch.int32).pin_memory()
+    h_idx = torch.empty((q_count, K_NN), dtype=torch.int32).pin_memory()
+    h_dist = torch.empty((q_count, K_NN), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty(q_count, dtype=torch.int32).pin_memory()
     h_ea, h_eb = torch.from_numpy(ea).pin_memory(), torch.from_numpy(eb).pin_memory()
     h_ok = torch.empty(E_WAVE, dtype=torch.uint8).pin_memory()
+    # ... and pageable ones: what a reference-side caller hands over (std::vector memory)
+    p_q, p_ea, p_eb = queries.copy(), ea.copy(), eb.copy()
+    p_idx, p_dist = np.empty((q_count, K_NN), np.uint32), np.empty((q_count, K_NN), np.float32)
+    p_cnt, p_ok = np.empty(q_count, np.uint32), np.empty(E_WAVE, np.uint8)
     torch.cuda.synchronize()
+
+    def knn_dev():
+        if comm is None:
+            nn.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, d_idx.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr())
+        else:
+            comm.nearest_dev(nn, d_q.data_ptr(), Q_WAVE, K_NN, -1.0, d_idx.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr())
+
+    def knn_host(q_ptr, i_ptr, d_ptr, c_ptr):
+        if comm is None:
+            nn.nearest_host_into(q_ptr, Q_WAVE, K_NN, -1.0, i_ptr, d_ptr, c_ptr)
+        else:
+            comm.nearest_host_into(nn, q_ptr, Q_WAVE, K_NN, -1.0, i_ptr, d_ptr, c_ptr)
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,7 +273,7 @@ def run_ours(args):
             flush.zero_()
             e0, e1, e2 = ev(), ev(), ev()
             e0.record(stream)
-            nn.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, d_idx.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr())
+            knn_dev()
             e1.record(stream)
             mesh.link_dev(d_ea.data_ptr(), d_eb.data_ptr(), E_WAVE, d_ok.data_ptr())
             e2.record(stream)
@@ -242,9 +285,21 @@ def run_ours(args):
             flush.zero_()
             e0, e1, e2 = ev(), ev(), ev()
             e0.record(stream)
-        nn.nearest_host_into(h_q.data_ptr(), Q_WAVE, K_NN, -1.0, h_idx.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
+        knn_host(h_q.data_ptr(), h_idx.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr())
         e1.record(stream)
         mesh.link_host_into(h_ea.data_ptr(), h_eb.data_ptr(), E_WAVE, h_ok.data_ptr())
+        e2.record(stream)
+        if record is not None:
+            record.append((e0, e1, e2))
+
+    def step_e2e_pageable(record):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record(stream)
+        knn_host(p_q.ctypes.data, p_idx.ctypes.data, p_dist.ctypes.data, p_cnt.ctypes.data)
+        e1.record(stream)
+        mesh.link_host_into(p_ea.ctypes.data, p_eb.ctypes.data, E_WAVE, p_ok.ctypes.data)
         e2.record(stream)
         if record is not None:
             record.append((e0, e1, e2))
@@ -274,6 +329,7 @@ def run_ours(args):
     knn_ms, edge_ms, wall, launches = timed(step_device)
     clocks = sampler.stop() if rank == 0 else None
     e2e_knn_ms, e2e_edge_ms, _, _ = timed(step_e2e)
+    pg_knn_ms, pg_edge_ms, _, _ = timed(step_e2e_pageable)
 
     knn_stats = nn.last_stats()
     mesh_stats = mesh.last_stats()
@@ -281,59 +337,86 @@ def run_ours(args):
     ok_dev = d_ok.cpu().numpy()
     assert np.array_equal(ok_dev, h_ok.numpy()), "device-pointer and host-pointer edge results differ"
     assert np.array_equal(d_idx.cpu().numpy(), h_idx.numpy()), "device-pointer and host-pointer kNN results differ"
+    assert np.array_equal(h_idx.numpy().view(np.uint32), p_idx) and np.array_equal(h_ok.numpy(), p_ok), "pinned and pageable results differ"
 
     extra = {}
     if rank == 0 and not args.no_secondary:
         extra["secondary"] = secondary(ctx, torch, dev, stream)
     if world > 1:
-        extra["sharded_tree"] = bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank)
+        extra["replicated_tree"] = bench_replicated_tree(args, ctx, sp, tree, dev, stream, world, rank)
 
     if rank != 0:
+        if comm is not None:
+            comm.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     hbm_peak, peak_src = peaks()
-    qps = world * Q_WAVE / (knn_ms * 1e-3)
+    # kNN: one structure at N = 1; at N > 1 ONE wave answered by all ranks (strong scaling).  Edges: a wave per rank.
+    qps = Q_WAVE / (knn_ms * 1e-3)
     eps = world * E_WAVE / (edge_ms * 1e-3)
     achieved = ALGO_BYTES_KNN / (knn_ms * 1e-3) / 1e9
-    edge_flops = mesh_stats["bv_tests"] * F_BV + mesh_stats["prim_tests"] * F_TRI
     launches_before_probe = ctx.launches
     fp32_peak = fp32_probe(ctx)
     assert ctx.launches == launches_before_probe + 3
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue = _profile_json("r2_knn_issue.json")  # warp instructions per query of the tree kernel, from the committed ncu capture
+    issue_slots = ctx.sm_count * 4 * sm_mhz * 1e6  # warp instructions the GPU can issue per second (4 schedulers per SM)
+    wipq = issue.get("warp_instructions_per_query")
+    # mesh roofline numerator: box-pair / triangle-pair tests of the ORACLE's traversal of the same edge wave
+    oc = _profile_json("r2_mesh_oracle_counts.json")
+    own_flops = mesh_stats["bv_tests"] * F_BV + mesh_stats["prim_tests"] * F_TRI
+    edge_flops = (oc["bv_tests"] * F_BV + oc["tri_tests"] * F_TRI) if oc else own_flops
     line = {
         "metric": "knn_queries_per_s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": knn_ms + edge_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": knn_ms + edge_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
-        "knn_ms": knn_ms, "edge_ms": edge_ms, "edges_per_s": eps,
+        "knn_ms": knn_ms, "edge_ms": edge_ms, "edges_per_s": eps, "edges_scaling": "weak (one 65,536-edge wave per rank)",
         "edge_states_per_s": world * mesh_stats["states"] / (edge_ms * 1e-3),
         "roofline": {
-            "kernel": "knnBvhKernel<float,SE3,1>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": measured_traffic("knnBvhKernel<float,SE3,1>"), "peak_source": peak_src,
+            "kernel": "knnSe3Kernel<1>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": measured_traffic("knnSe3Kernel<1>"), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ALGO_BYTES_KNN,
-            "note": "exact kNN is bound by box tests and distance evaluations, not by compulsory HBM bytes (DESIGN.md)",
+            "note": "exact kNN in a 6-dimensional space with 10 points per dimension is bound by node and point tests (instruction "
+                    "issue), not by compulsory HBM bytes (DESIGN.md 4.2); the issue-slot roofline below is the one that moves",
             "distance_evals_per_query": knn_stats["distance_evals"] / Q_WAVE,
             "nodes_visited_per_query": knn_stats["nodes_visited"] / Q_WAVE,
+            # issue-slot roofline: warp instructions per query (ncu smsp__inst_executed of the same kernel on the same wave,
+            # profiles/r2_knn_issue.json) x Q / (SMs x 4 schedulers x SM clock during this run) = time at one instruction
+            # per scheduler per cycle; frac = that time / measured time
+            "issue": {"warp_instructions_per_query": wipq, "issue_slots_per_s": issue_slots, "sm_mhz": sm_mhz,
+                      "floor_ms": (wipq * Q_WAVE / issue_slots * 1e3) if wipq else None,
+                      "frac": (wipq * Q_WAVE / issue_slots / (knn_ms * 1e-3)) if (wipq and world == 1) else None,
+                      "source": issue.get("source"), "r1": {"warp_instructions_per_query": 31600, "ms": 2.29}},
             # SURVEY.md 8(d) honesty check: which roofline binds.  F_pair = 21 flop per SE(3) distance evaluation.
             "fp32": {"achieved": knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": (knn_stats["distance_evals"] * 21.0 / (knn_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
-                     "flop_per_distance_eval": 21.0,
-                     "binds": "FP32/issue (ncu: smsp__issue_active 78%, dram throughput 0.3% -- profiles/r1_ncu_knn_bvh_d.txt)"},
+                     "flop_per_distance_eval": 21.0},
         },
         "roofline_edges": {
             "kernel": "meshFlatKernel", "bound": "fp32", "achieved": edge_flops / (edge_ms * 1e-3) / 1e12, "peak": fp32_peak,
             "unit": "TFLOP/s", "frac": edge_flops / (edge_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
             "peak_source": "FFMA microbenchmark of this library on this GPU, same run (mptg_probe_fp32_tflops)",
-            "algorithmic_flops_per_launch": edge_flops, "bv_tests": mesh_stats["bv_tests"], "tri_tests": mesh_stats["prim_tests"],
-            "states": mesh_stats["states"], "flop_per_bv_test": F_BV, "flop_per_tri_test": F_TRI,
+            "algorithmic_flops_per_launch": edge_flops,
+            "numerator": "box-pair and triangle-pair tests of the ORACLE's traversal of the same 65,536 edges (profiles/r2_mesh_oracle_counts.json, "
+                         "tools/mesh_oracle_counts.py), at the flop cost of the tests as implemented",
+            "oracle_bv_tests": oc.get("bv_tests"), "oracle_tri_tests": oc.get("tri_tests"), "oracle_states": oc.get("states"),
+            "kernel_bv_tests": mesh_stats["bv_tests"], "kernel_tri_tests": mesh_stats["prim_tests"], "kernel_states": mesh_stats["states"],
+            "work_inflation": {"bv": mesh_stats["bv_tests"] / oc["bv_tests"], "tri": mesh_stats["prim_tests"] / oc["tri_tests"],
+                               "flops": own_flops / edge_flops} if oc else None,
+            "flop_per_bv_test": F_BV, "flop_per_tri_test": F_TRI,
             "traffic": measured_traffic("meshFlatKernel"),
         },
         "e2e": {
-            "value": world * Q_WAVE / (e2e_knn_ms * 1e-3), "unit": "queries/s", "edges_per_s": world * E_WAVE / (e2e_edge_ms * 1e-3),
+            "value": Q_WAVE / (e2e_knn_ms * 1e-3), "unit": "queries/s", "edges_per_s": world * E_WAVE / (e2e_edge_ms * 1e-3),
             "ms_per_step": e2e_knn_ms + e2e_edge_ms,
             "h2d_bytes_per_step": int(h_q.numel() * 4 + h_ea.numel() * 4 + h_eb.numel() * 4),
             "d2h_bytes_per_step": int(h_idx.numel() * 4 + h_dist.numel() * 4 + h_cnt.numel() * 4 + h_ok.numel()),
-            "api": "mptg_knn_query + mptg_link_batch with pinned host buffers",
+            "api": ("mptg_knn_query" if world == 1 else "mptg_knn_query_sharded") + " + mptg_link_batch with pinned host buffers",
+            "pageable": {"value": Q_WAVE / (pg_knn_ms * 1e-3), "edges_per_s": world * E_WAVE / (pg_edge_ms * 1e-3),
+                         "ms_per_step": pg_knn_ms + pg_edge_ms, "note": "the same calls with ordinary (pageable) host memory, as a "
+                         "reference-side caller's std::vector buffers would be"},
         },
         "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall, "edge_valid_fraction": float(ok_dev.mean()),
         **extra,
@@ -341,6 +424,8 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb)
     emit(line)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -592,27 +677,22 @@ def cpu_baseline(args, sp, tree, queries, robot, env, step, ea, eb):
                       f"OpenMP over all host threads"}
 
 
-def bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank):
-    """north_star variant: tree points dealt round-robin to the ranks, every rank answers the same query
-    wave on its shard, NCCL all-gather of the [Q,k] candidates, merge by (distance, global index)."""
+def bench_replicated_tree(args, ctx, sp, tree, dev, stream, world, rank):
+    """The zero-collective alternative when the tree fits one HBM (28 MB here): every rank holds the whole tree and
+    answers its OWN wave.  Trivially linear; reported next to the sharded figure, which is the north_star's split."""
     import torch
     import torch.distributed as dist
 
     import mpt_b200 as m
     from mpt_b200 import workloads as W
 
-    q_all = W.se3_states(Q_WAVE, W.QUERY_SEED)  # identical on all ranks
-    shard = m.Nearest(ctx, sp, N_TREE // world + 1)
-    shard.set_index_map(world, rank)
-    shard.insert(tree[rank::world])
-    shard.build_index()
-    d_q = torch.from_numpy(q_all).to(dev)
+    q = W.se3_states(Q_WAVE, W.QUERY_SEED + 1000 * rank)
+    full = m.Nearest(ctx, sp, N_TREE)
+    full.insert(tree)
+    full.build_index()
+    d_q = torch.from_numpy(q).to(dev)
     loc_i = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
     loc_d = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
-    all_i = torch.empty((world, Q_WAVE, K_NN), dtype=torch.int32, device=dev)
-    all_d = torch.empty((world, Q_WAVE, K_NN), dtype=torch.float32, device=dev)
-    out_i = torch.empty((Q_WAVE, K_NN), dtype=torch.int32, device=dev)
-    out_d = torch.empty((Q_WAVE, K_NN), dtype=torch.float32, device=dev)
     times = []
     for it in range(args.warmup + args.steps):
         torch.cuda.synchronize()
@@ -620,19 +700,17 @@ def bench_sharded_tree(args, ctx, sp, tree, queries, dev, stream, world, rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
-            shard.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, loc_i.data_ptr(), loc_d.data_ptr())
-            dist.all_gather_into_tensor(all_i, loc_i)
-            dist.all_gather_into_tensor(all_d, loc_d)
-            m.knn_merge_dev(ctx, m.F32, world, Q_WAVE, K_NN, all_i.data_ptr(), all_d.data_ptr(), out_i.data_ptr(), out_d.data_ptr())
+            full.nearest_dev(d_q.data_ptr(), Q_WAVE, K_NN, -1.0, loc_i.data_ptr(), loc_d.data_ptr())
             e1.record(stream)
         torch.cuda.synchronize()
         if it >= args.warmup:
             times.append(e0.elapsed_time(e1))
+    full.close()
     t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
-    return {"queries_per_s": Q_WAVE / (ms * 1e-3), "ms_per_wave": ms, "collective": "nccl all_gather of [Q,k] (idx,dist) + merge kernel",
-            "tree_nodes_per_gpu": N_TREE // world}
+    return {"queries_per_s": world * Q_WAVE / (ms * 1e-3), "ms_per_wave": ms, "scaling": "weak", "collective": "none",
+            "tree_nodes_per_gpu": N_TREE}
 
 
 _REAL_STDOUT = None

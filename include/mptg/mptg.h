@@ -84,6 +84,8 @@ const char* mptg_last_error(const mptg_ctx* ctx);
 void* mptg_ctx_stream(mptg_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t mptg_ctx_launch_count(const mptg_ctx* ctx);
+/* Streaming multiprocessors of the context's device (grids are sized in multiples of it; bench.py's issue-slot roofline). */
+int mptg_ctx_sm_count(const mptg_ctx* ctx);
 /* Measured FP32 rate of this GPU: a register-only FFMA kernel (8 independent chains per thread, every SM full),
  * best of two timed launches of ~4 ms, in TFLOP/s (2 flop per FFMA).  The yardstick bench.py's fp32 rooflines use
  * ("FP32 peak is not in MEASURED_PEAKS.json; measure it with an FFMA microbenchmark"). */
@@ -143,6 +145,42 @@ int mptg_knn_last_stats(mptg_knn* knn, uint64_t stats_out[4]);
 int mptg_knn_merge_dev(mptg_ctx* ctx, int scalar, uint32_t parts, uint32_t Q, uint32_t k,
                        const uint32_t* idx_in_dev, const void* dist_in_dev, uint32_t* idx_out_dev,
                        void* dist_out_dev, uint32_t* count_out_dev);
+
+/* ------------------------------------------------ tree-sharded kNN across GPUs
+ * The reference has one nigh::Nigh structure per planner in host memory; a tree that is spread over the GPUs of a box
+ * keeps its interface (insert, nearest) and adds a communicator.  One process (and one mptg_ctx) per GPU.  Every rank
+ * stores a SPATIAL shard of the points -- which rank stores a point is the caller's choice (e.g. the sub-box of the
+ * sampling bounds it falls in); pruning works to the extent the shards are spatially compact, results are exact for any
+ * assignment -- and all ranks call mptg_knn_query_sharded collectively with the SAME query wave.  Rank r receives the
+ * results of its slice of the wave (mptg_comm_slice): rows ascending by (distance, global index), identical to what a
+ * single structure holding all points returns.  Collectives are NCCL (all-gather of the shards' top-level boxes at
+ * mptg_knn_shard_sync; per wave an all-reduce(min) of the per-query distance bounds and a grouped send/recv of the
+ * candidate rows), resolved at run time
+ * from libnccl.so.2; any NCCL failure returns MPTG_ERR_NCCL. */
+#define MPTG_UNIQUE_ID_BYTES 128
+typedef struct mptg_comm mptg_comm;
+/* ncclGetUniqueId: called by one rank, the 128 bytes are handed to the others by the caller (MPI, torch.distributed,
+ * a file ...) and passed to mptg_comm_init by every rank. */
+int mptg_comm_unique_id(void* id_out);
+int mptg_comm_init(mptg_ctx* ctx, const void* unique_id, int rank, int world, mptg_comm** out);
+int mptg_comm_destroy(mptg_comm* comm);
+int mptg_comm_rank(const mptg_comm* comm);
+int mptg_comm_world(const mptg_comm* comm);
+/* The contiguous slice [first, first + count) of n units (queries of a wave) owned by this rank. */
+int mptg_comm_slice(const mptg_comm* comm, uint32_t n, uint32_t* first_out, uint32_t* count_out);
+/* nn.insert for a shard: `ids[i]` is the index results report for state i (the node's global, insertion-order index in
+ * the planner's graph).  A structure takes either plain inserts or inserts with ids, not both. */
+int mptg_knn_insert_ids(mptg_knn* knn, const void* states, const uint32_t* ids, uint32_t count);
+/* Collective, after inserting and before searching: every rank indexes what its shard stores and the bounding boxes of
+ * the children of every shard's top node are exchanged (a few KB), so that each rank can bound the distance of a query
+ * to every shard by itself.  mptg_knn_query_sharded fails with MPTG_ERR_BAD_ARG if the shard has changed since. */
+int mptg_knn_shard_sync(mptg_comm* comm, mptg_knn* shard);
+/* nn.nearest over the union of all ranks' shards, for the Q queries of the wave (the same on every rank).  Outputs hold
+ * the rows of this rank's slice only: count * k entries.  Semantics of k / radius / padding as mptg_knn_query. */
+int mptg_knn_query_sharded(mptg_comm* comm, mptg_knn* shard, const void* queries, uint32_t Q, uint32_t k, double radius,
+                           uint32_t* idx_out, void* dist_out, uint32_t* count_out);
+int mptg_knn_query_sharded_dev(mptg_comm* comm, mptg_knn* shard, const void* queries_dev, uint32_t Q, uint32_t k, double radius,
+                               uint32_t* idx_out_dev, void* dist_out_dev, uint32_t* count_out_dev);
 
 /* ------------------------------------------------ scenario geometry (a7-a10) */
 /* Occupancy grid, 1 byte per cell (non-zero = obstacle), row-major width*height.

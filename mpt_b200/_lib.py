@@ -64,6 +64,7 @@ SYMBOLS = {
     "mptg_last_error": (C.c_char_p, [_P]),
     "mptg_ctx_stream": (_P, [_P]),
     "mptg_ctx_launch_count": (C.c_uint64, [_P]),
+    "mptg_ctx_sm_count": (C.c_int, [_P]),
     "mptg_probe_fp32_tflops": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "mptg_space_scalars": (C.c_int, [_SD]),
     "mptg_space_dimensions": (C.c_int, [_SD]),
@@ -82,6 +83,16 @@ SYMBOLS = {
     "mptg_knn_build_index": (C.c_int, [_P]),
     "mptg_knn_last_stats": (C.c_int, [_P, _U64P]),
     "mptg_knn_merge_dev": (C.c_int, [_P, C.c_int, _U32, _U32, _U32, _P, _P, _P, _P, _P]),
+    "mptg_comm_unique_id": (C.c_int, [_P]),
+    "mptg_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mptg_comm_destroy": (C.c_int, [_P]),
+    "mptg_comm_rank": (C.c_int, [_P]),
+    "mptg_comm_world": (C.c_int, [_P]),
+    "mptg_comm_slice": (C.c_int, [_P, _U32, _U32P, _U32P]),
+    "mptg_knn_insert_ids": (C.c_int, [_P, _P, _P, _U32]),
+    "mptg_knn_shard_sync": (C.c_int, [_P, _P]),
+    "mptg_knn_query_sharded": (C.c_int, [_P, _P, _P, _U32, _U32, C.c_double, _P, _P, _P]),
+    "mptg_knn_query_sharded_dev": (C.c_int, [_P, _P, _P, _U32, _U32, C.c_double, _P, _P, _P]),
     "mptg_grid_create": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "mptg_shapes_create": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(_P)]),
     "mptg_linkarm_create": (C.c_int, [_P, C.c_int, C.c_int32, _P, C.c_double, C.c_int32, _P, C.POINTER(_P)]),

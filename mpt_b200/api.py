@@ -106,6 +106,10 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.mptg_ctx_launch_count(self.h))
 
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.mptg_ctx_sm_count(self.h))
+
     def probe_fp32_tflops(self) -> float:
         """FFMA rate of this GPU in TFLOP/s (mptg_probe_fp32_tflops)."""
         out = C.c_double(0.0)
@@ -141,6 +145,65 @@ class Context:
         L.check(self.lib.mptg_steer_batch(self.h, space.ref, _ptr(near), _ptr(sample), _ptr(d), near.shape[0], float(rng),
                                           _ptr(out), _ptr(dist)), self.h)
         return (out, dist) if with_distance else out
+
+
+class Comm:
+    """Communicator of the tree-sharded search (mptg_comm): one per process / GPU, NCCL underneath."""
+
+    UNIQUE_ID_BYTES = 128
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.UNIQUE_ID_BYTES)
+        L.check(L.load().mptg_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, ctx: Context, unique_id: bytes, rank: int, world: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), Comm.UNIQUE_ID_BYTES)
+        L.check(ctx.lib.mptg_comm_init(ctx.h, buf, rank, world, C.byref(h)), ctx.h)
+        self.h, self.rank, self.world = h, rank, world
+
+    def slice(self, n: int):
+        first, count = C.c_uint32(), C.c_uint32()
+        L.check(self.ctx.lib.mptg_comm_slice(self.h, n, C.byref(first), C.byref(count)), self.ctx.h)
+        return first.value, count.value
+
+    def sync(self, shard: "Nearest"):
+        """Collective, after inserting: index the shard and exchange the shards' top-level boxes (mptg_knn_shard_sync)."""
+        L.check(self.ctx.lib.mptg_knn_shard_sync(self.h, shard.h), self.ctx.h)
+
+    def nearest(self, shard: "Nearest", queries, k: int = 1, radius: float = -1.0):
+        """Collective: all ranks pass the same queries; returns this rank's slice (idx, dist, count) with global indices."""
+        q = np.ascontiguousarray(queries, dtype=shard.space.dtype).reshape(-1, shard.space.scalars)
+        _, n = self.slice(q.shape[0])
+        idx = np.empty((n, k), dtype=np.uint32)
+        dist = np.empty((n, k), dtype=shard.space.dtype)
+        cnt = np.empty(n, dtype=np.uint32)
+        r = float(radius) if radius is not None and math.isfinite(radius) else -1.0
+        L.check(self.ctx.lib.mptg_knn_query_sharded(self.h, shard.h, _ptr(q), q.shape[0], k, r, _ptr(idx), _ptr(dist), _ptr(cnt)), self.ctx.h)
+        return idx, dist, cnt
+
+    def nearest_host_into(self, shard: "Nearest", q_ptr: int, Q: int, k: int, radius: float, idx_ptr: int, dist_ptr: int, cnt_ptr: int = 0):
+        """host pointers in and out (this rank's slice of the results), no numpy allocation: bench.py's e2e path"""
+        L.check(self.ctx.lib.mptg_knn_query_sharded(self.h, shard.h, C.c_void_p(q_ptr), Q, k, float(radius), C.c_void_p(idx_ptr),
+                                                    C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr) if cnt_ptr else None), self.ctx.h)
+
+    def nearest_dev(self, shard: "Nearest", q_ptr: int, Q: int, k: int, radius: float, idx_ptr: int, dist_ptr: int, cnt_ptr: int = 0):
+        L.check(self.ctx.lib.mptg_knn_query_sharded_dev(self.h, shard.h, C.c_void_p(q_ptr), Q, k, float(radius), C.c_void_p(idx_ptr),
+                                                        C.c_void_p(dist_ptr), C.c_void_p(cnt_ptr) if cnt_ptr else None), self.ctx.h)
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.mptg_comm_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Nearest:
@@ -179,6 +242,13 @@ class Nearest:
         first = C.c_uint32()
         L.check(self.ctx.lib.mptg_knn_insert(self.h, _ptr(s), s.shape[0], C.byref(first)), self.ctx.h)
         return first.value
+
+    def insert_ids(self, states, ids):
+        """Shard insert: results report ids[i] for states[i] (mptg_knn_insert_ids)."""
+        s = np.ascontiguousarray(states, dtype=self.space.dtype).reshape(-1, self.space.scalars)
+        i = np.ascontiguousarray(ids, dtype=np.uint32)
+        assert i.shape[0] == s.shape[0]
+        L.check(self.ctx.lib.mptg_knn_insert_ids(self.h, _ptr(s), _ptr(i), s.shape[0]), self.ctx.h)
 
     def insert_dev(self, ptr: int, count: int) -> int:
         first = C.c_uint32()

@@ -110,6 +110,7 @@ int mptg_probe_fp32_tflops(mptg_ctx* ctx, double* tflops_out) {
 
 const char* mptg_last_error(const mptg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_lastError.c_str(); }
 void* mptg_ctx_stream(mptg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int mptg_ctx_sm_count(const mptg_ctx* ctx) { return ctx ? ctx->smCount : 0; }
 uint64_t mptg_ctx_launch_count(const mptg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int mptg_space_scalars(const mptg_space_desc* space) { return spaceScalars(space); }
 int mptg_space_dimensions(const mptg_space_desc* space) {

@@ -397,6 +397,7 @@ struct mptg_knn {
     void* pts = nullptr;  // SoA [D][stride]
     int strategy = MPTG_KNN_AUTO;
     uint32_t idxMul = 1, idxAdd = 0;
+    uint32_t* gid = nullptr;  // optional [capacity]: reported (global) index per stored point (mptg_knn_insert_ids)
     uint64_t stats[4] = {0, 0, 0, 0};
     KnnIndex index;  // knn_bvh.cuh
     KnnTail tail;    // knn_index.cuh: Morton-sorted leaves over the points inserted since the tree was built
@@ -675,6 +676,7 @@ int mptg_knn_destroy(mptg_knn* knn) {
     cudaStreamSynchronize(knn->ctx->stream);
     knnIndexFree(knn->index);
     if (knn->tail.mem) cudaFree(knn->tail.mem);
+    cudaFree(knn->gid);
     cudaFree(knn->pts);
     delete knn;
     return MPTG_OK;
@@ -809,6 +811,19 @@ int mptg_knn_last_stats(mptg_knn* knn, uint64_t out[4]) {
     return MPTG_OK;
 }
 
+int mptg_knn_insert_ids(mptg_knn* knn, const void* states, const uint32_t* ids, uint32_t count) {
+    if (!knn || ((!states || !ids) && count)) return fail(knn ? knn->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_knn_insert_ids: bad argument");
+    if (knn->size != 0 && !knn->gid) return fail(knn->ctx, MPTG_ERR_BAD_ARG, "mptg_knn_insert_ids: the set already holds points without ids");
+    mptg_ctx* ctx = knn->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!knn->gid) MPTG_CUDA(ctx, cudaMalloc(&knn->gid, (size_t)knn->capacity * sizeof(uint32_t)));
+    uint32_t first = 0;
+    if (int rc = mptg_knn_insert(knn, states, count, &first)) return rc;
+    if (count) MPTG_CUDA(ctx, cudaMemcpyAsync(knn->gid + first, ids, (size_t)count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPTG_OK;
+}
+
 int mptg_knn_merge_dev(mptg_ctx* ctx, int scalar, uint32_t parts, uint32_t Q, uint32_t k, const uint32_t* idxIn,
                        const void* distIn, uint32_t* idxOut, void* distOut, uint32_t* countOut) {
     if (!ctx || !idxIn || !distIn || !idxOut || !distOut || parts == 0 || k == 0 || k > MPTG_MAX_K)
@@ -820,3 +835,115 @@ int mptg_knn_merge_dev(mptg_ctx* ctx, int scalar, uint32_t parts, uint32_t Q, ui
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// internal entry points of the sharded search (comm.cu)
+// ---------------------------------------------------------------------------------------------
+namespace mptg {
+
+mptg_ctx* knnShardCtx(mptg_knn* knn) { return knn->ctx; }
+int knnShardScalar(const mptg_knn* knn) { return knn->scalar; }
+int knnShardScalars(const mptg_knn* knn) { return knn->D; }
+const mptg_space_desc* knnShardSpace(const mptg_knn* knn) { return &knn->space; }
+uint32_t knnShardSize(const mptg_knn* knn) { return knn->size; }
+uint64_t knnShardBuilds(const mptg_knn* knn) { return knn->index.builds; }
+
+namespace {
+// lb[g][q] for every shard g from the synchronised shard boxes (generic box bound of knn_bvh.cuh: conservative for every
+// space), rounded down to float; home(q) = the shard with the smallest bound (lowest rank on ties); cap = +inf for this
+// rank's home queries, -1 for the others (the home search skips them).  One thread per query, one box per shard.
+template <typename S>
+__global__ void __launch_bounds__(256) shardRootKernel(DevSpace<S> sp, const S* __restrict__ shardBox, const uint32_t* __restrict__ peerN, int world, int rank,
+                                                       const S* __restrict__ queries, uint32_t Q, float* __restrict__ lbMine, uint8_t* __restrict__ home,
+                                                       S* __restrict__ cap) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int D = sp.D;
+    const S* myq = queries + (size_t)q * D;
+    int best = 0;
+    float bl = INFINITY, mine = INFINITY;
+    for (int g = 0; g < world; ++g) {
+        float v = INFINITY;
+        if (peerN[g] != 0u) {
+            const S* b = shardBox + (size_t)g * (size_t)(2 * D);
+            const S lb = dev::boxLowerBound<S>(
+                sp, [&](int c) { return b[c]; }, [&](int c) { return b[D + c]; }, [&](int c) { return myq[c]; });
+            v = __uint_as_float(boundKey<S>(lb));
+        }
+        if (v < bl) bl = v, best = g;
+        if (g == rank) mine = v;
+    }
+    lbMine[q] = mine;
+    home[q] = (uint8_t)best;
+    cap[q] = best == rank ? (S)INFINITY : S(-1);
+}
+// one box per shard: the union of the boxes of the children of its top node ([2 D][32] rows -> [2 D])
+template <typename S>
+__global__ void shardUnionKernel(const S* __restrict__ peerBox, const uint32_t* __restrict__ peerN, int world, int D, S* __restrict__ shardBox) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= world * D) return;
+    const int g = t / D, c = t % D;
+    const S* b = peerBox + (size_t)g * (size_t)(2 * D) * 32u;
+    S lo = (S)INFINITY, hi = (S)-INFINITY;
+    for (uint32_t j = 0; j < peerN[g] && j < 32u; ++j) {
+        lo = fmin(lo, b[(size_t)c * 32u + j]);
+        hi = fmax(hi, b[(size_t)(D + c) * 32u + j]);
+    }
+    shardBox[(size_t)g * 2 * D + c] = lo;
+    shardBox[(size_t)g * 2 * D + D + c] = hi;
+}
+template <typename S>
+int shardQueryT(mptg_knn* knn, const S* q, uint32_t Q, uint32_t k, double radius, const S* qcap, uint32_t* idxOut, S* distOut, bool secondPass) {
+    return knnBvhQuery<S>(knn->ctx, knn->index, knn->space, q, Q, k, radius, knn->idxMul, knn->idxAdd, idxOut, distOut, nullptr, knn->stats, knn->gid, qcap,
+                          nullptr, secondPass);
+}
+}  // namespace
+
+// The sharded search goes through the tree only (per-query radius caps live in the tree kernels): index everything stored,
+// and hand out the boxes of the top node's children (device, [2 D][32] scalars, lo rows then hi rows) and their number.
+int knnShardIndexAll(mptg_knn* knn, const void** topBoxDev, uint32_t* nTop) {
+    *topBoxDev = nullptr;
+    *nTop = 0;
+    if (knn->size == 0) return MPTG_OK;
+    if (knn->index.count != knn->size) {
+        knn->index.count = 0;
+        const int rc = knn->scalar == MPTG_F32 ? knnBuildIndex<float>(knn->ctx, knn->index, knn->space, (const float*)knn->pts, knn->stride, knn->size)
+                                               : knnBuildIndex<double>(knn->ctx, knn->index, knn->space, (const double*)knn->pts, knn->stride, knn->size);
+        if (rc) return rc;
+    }
+    *topBoxDev = knn->index.box[knn->index.top];
+    *nTop = knn->index.nNodes[knn->index.top];
+    return MPTG_OK;
+}
+// one box per shard from the synchronised top boxes (after mptg_knn_shard_sync's all-gather)
+int knnShardUnion(mptg_knn* knn, const void* peerBox, const uint32_t* peerN, int world, void* shardBox) {
+    mptg_ctx* ctx = knn->ctx;
+    const int n = world * knn->D;
+    if (knn->scalar == MPTG_F32) shardUnionKernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>((const float*)peerBox, peerN, world, knn->D, (float*)shardBox);
+    else shardUnionKernel<double><<<(n + 127) / 128, 128, 0, ctx->stream>>>((const double*)peerBox, peerN, world, knn->D, (double*)shardBox);
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+// bounds of every query to every shard, home shard, and the cap array of the home search (see shardRootKernel)
+int knnShardRootAll(mptg_knn* knn, const void* shardBox, const uint32_t* peerN, int world, int rank, const void* queriesDev, uint32_t Q, float* lbMine,
+                    uint8_t* home, void* cap) {
+    mptg_ctx* ctx = knn->ctx;
+    const dim3 grid((Q + 255) / 256), block(256);
+    if (knn->scalar == MPTG_F32)
+        shardRootKernel<float><<<grid, block, 0, ctx->stream>>>(makeDevSpace<float>(knn->space), (const float*)shardBox, peerN, world, rank, (const float*)queriesDev,
+                                                                Q, lbMine, home, (float*)cap);
+    else
+        shardRootKernel<double><<<grid, block, 0, ctx->stream>>>(makeDevSpace<double>(knn->space), (const double*)shardBox, peerN, world, rank,
+                                                                 (const double*)queriesDev, Q, lbMine, home, (double*)cap);
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+// search with a per-query radius cap (scalar type of the space; < 0: skip the query, its output row is left alone)
+int knnShardQuery(mptg_knn* knn, const void* queriesDev, uint32_t Q, uint32_t k, double radius, const void* qcapDev, uint32_t* idxOut,
+                  void* distOut, bool secondPass) {
+    if (knn->size == 0) return MPTG_OK;
+    return knn->scalar == MPTG_F32 ? shardQueryT<float>(knn, (const float*)queriesDev, Q, k, radius, (const float*)qcapDev, idxOut, (float*)distOut, secondPass)
+                                   : shardQueryT<double>(knn, (const double*)queriesDev, Q, k, radius, (const double*)qcapDev, idxOut, (double*)distOut, secondPass);
+}
+
+}  // namespace mptg

@@ -152,6 +152,10 @@ struct BvhArgs {
     uint32_t* countOut;
     unsigned long long* stats;
     uint32_t* cursor;  // next position of the wave (persistent warps), zeroed before the launch
+    bool reuseOrder;      // the processing order computed by the previous search of this wave is still in place
+    const uint32_t* gid;  // optional: reported index of stored point i is gid[i] (spatially sharded sets) instead of i * idxMul + idxAdd
+    const S* qcap;     // optional per-query radius cap (sharded search): < 0 skips the query and leaves its output row alone
+    float* rootLb;     // root-bound pass only: lower bound of every query to the whole indexed set
     DevSpace<S> sp;
 };
 
@@ -223,6 +227,9 @@ struct BvhWalk {
         refreshThr();
     }
     __device__ __forceinline__ float threshold() const { return thrF; }
+    __device__ __forceinline__ uint32_t reported(uint32_t orig) const {
+        return a.gid ? (orig != MPTG_NO_INDEX ? __ldg(a.gid + orig) : MPTG_NO_INDEX) : orig * a.idxMul + a.idxAdd;
+    }
 
     // key (float bits of a lower bound) of child `lane` of `block` at level L
     template <int L>
@@ -292,11 +299,11 @@ struct BvhWalk {
             if (a.sp.weighted[0]) dr = dr * (float)a.sp.weight[0];
             float dt = fp::sqrt_(s2);
             if (a.sp.weighted[1]) dt = dt * (float)a.sp.weight[1];
-            top.offer(maybe, (S)(dr + dt), orig * a.idxMul + a.idxAdd, rad, lane);
+            top.offer(maybe, (S)(dr + dt), reported(orig), rad, lane);
         } else {
             const S dist = dev::distance<S>(
                 a.sp, [&](int c) { return __ldg(pt + c * 32); }, [&](int c) { return myq[c]; });
-            top.offer(have, dist, orig * a.idxMul + a.idxAdd, rad, lane);
+            top.offer(have, dist, reported(orig), rad, lane);
         }
         refreshThr();
     }
@@ -373,6 +380,38 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKeyKernel(const BvhArgs<
     }
 }
 
+// Lower bound of every query to the whole indexed set: the smallest child bound of the top node (sharded search: which
+// shards a query has to visit at all).  Rounded down to float.
+template <typename S, int SHAPE>
+__global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhRootBoundKernel(const BvhArgs<S> a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    S* qsm = reinterpret_cast<S*>(smemRaw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = a.sp.D;
+    const uint32_t q = blockIdx.x * BVH_WARPS + warp;
+    if (q >= a.Q) return;
+    S* myq = qsm + warp * D;
+    for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
+    __syncwarp();
+    BvhWalk<S, SHAPE, 1> w(a, myq, lane);
+    if (SHAPE == SHAPE_SE3) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) w.qr[c] = myq[c];
+        w.w0 = a.sp.weighted[0] ? (float)a.sp.weight[0] : 1.0f;
+        w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
+    }
+    uint32_t key;
+    switch (a.top) {
+        case 4: key = w.template childKey<4>(0); break;
+        case 3: key = w.template childKey<3>(0); break;
+        case 2: key = w.template childKey<2>(0); break;
+        case 1: key = w.template childKey<1>(0); break;
+        default: key = w.template childKey<0>(0); break;
+    }
+    const uint32_t best = __reduce_min_sync(FULL_MASK, key);
+    if (lane == 0) a.rootLb[q] = best == BVH_DEAD ? INFINITY : __uint_as_float(best);
+}
+
 // exclusive scan of up to 65536 bins by one CTA
 __global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint32_t bins) {
     __shared__ uint32_t part[1024];
@@ -434,6 +473,12 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, MPTG_BVH_MIN_CTAS) knnBvhKerne
             w.w1 = a.sp.weighted[1] ? (float)a.sp.weight[1] : 1.0f;
         }
         w.start();
+        if (a.qcap) {
+            const S c = a.qcap[q];
+            if (c < S(0)) continue;
+            if (c < w.rad) w.rad = c;
+            w.refreshThr();
+        }
         switch (a.top) {
             case 0: w.template descend<0>(0); break;
             case 1: w.template descend<1>(0); break;
@@ -735,6 +780,10 @@ int orderWave(mptg_ctx* ctx, BvhArgs<S>& a, KEYK keyKernel, size_t smem) {
     int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
     if (rc) return rc;
     uint32_t* order = (uint32_t*)buf;
+    if (a.reuseOrder) {  // the caller has just searched the same wave on the same structure (sharded search, second pass)
+        a.order = order;
+        return MPTG_OK;
+    }
     a.orderKeys = order + a.Q;
     a.orderHist = order + 2 * (size_t)a.Q;
     a.orderShift = shift;
@@ -766,12 +815,19 @@ inline int launchSe3(mptg_ctx* ctx, BvhArgs<float>& a) {
     return launchPersistent(ctx, knnSe3Kernel<4>, a, a.Q, 0);
 }
 inline int launchSe3(mptg_ctx* ctx, BvhArgs<double>&) { return fail(ctx, MPTG_ERR_UNSUPPORTED, "cap image on a double-precision set"); }
+inline void launchSe3RootBound(mptg_ctx* ctx, BvhArgs<float>& a, dim3 grid, dim3 block) { knnSe3RootBoundKernel<<<grid, block, 0, ctx->stream>>>(a); }
+inline void launchSe3RootBound(mptg_ctx*, BvhArgs<double>&, dim3, dim3) {}
 
 template <typename S>
 int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const S* queries, uint32_t Q, uint32_t k,
                 double radius, uint32_t idxMul, uint32_t idxAdd, uint32_t* idxOut, S* distOut, uint32_t* countOut,
-                uint64_t* /*hostStats*/) {
+                uint64_t* /*hostStats*/, const uint32_t* gid = nullptr, const S* qcap = nullptr, float* rootLbOut = nullptr,
+                bool reuseOrder = false) {
     BvhArgs<S> a{};
+    a.reuseOrder = reuseOrder;
+    a.gid = gid;
+    a.qcap = qcap;
+    a.rootLb = rootLbOut;
     a.leafPts = (const S*)ix.leafPts;
     a.perm = ix.perm;
     a.leafH = ix.leafH;
@@ -798,6 +854,18 @@ int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const
     a.stats = ix.devStats;
     a.cursor = reinterpret_cast<uint32_t*>(ix.devStats + 4);
     a.sp = makeDevSpace<S>(space);
+    if (rootLbOut) {  // root-bound pass only
+        const dim3 grid((Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
+        const size_t smem = (size_t)BVH_WARPS * a.sp.D * sizeof(S);
+        if (classifySpace(space) == SHAPE_SE3) {
+            if (sizeof(S) == 4 && ix.leafH) launchSe3RootBound(ctx, a, grid, block);
+            else knnBvhRootBoundKernel<S, SHAPE_SE3><<<grid, block, smem, ctx->stream>>>(a);
+        } else {
+            knnBvhRootBoundKernel<S, SHAPE_GENERIC><<<grid, block, smem, ctx->stream>>>(a);
+        }
+        MPTG_LAUNCHED(ctx);
+        return MPTG_OK;
+    }
     MPTG_CUDA(ctx, cudaMemsetAsync(ix.devStats, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (classifySpace(space) == SHAPE_SE3) return (sizeof(S) == 4 && ix.leafH) ? launchSe3(ctx, a) : launchBvhShape<S, SHAPE_SE3>(ctx, a);
     return launchBvhShape<S, SHAPE_GENERIC>(ctx, a);

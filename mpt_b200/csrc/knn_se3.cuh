@@ -79,7 +79,7 @@ struct Se3Walk {
     int lane;
     __half2 hq01, hq23, hnt01, hnt2;  // query quaternion; minus the query translation in the leaf copies' scale
     __half2 hG, hKa, hKb;             // prefilter scales for the current threshold
-    float thrF;
+    float thrF, rad;
     WarpTopK<float, KPL> top;
     uint32_t& leaves;
     uint32_t& inner;
@@ -103,7 +103,7 @@ struct Se3Walk {
     //    A = B = 0, every lane of a visited leaf passes and is evaluated exactly until the threshold has come down.
     //    (0 x finite = 0: the stored copies are finite and the half query is clamped to the half range.)
     __device__ __forceinline__ void refreshThr() {
-        thrF = top.kthD < a.radius ? top.kthD : a.radius;
+        thrF = top.kthD < rad ? top.kthD : rad;
         // (recomputed here rather than kept in registers: this runs only after an insertion)
         const float u = 4.8828125e-4f;
         const float qabs = fabsf(sq[0]) + fabsf(sq[1]) + fabsf(sq[2]) + fabsf(sq[3]);
@@ -122,8 +122,9 @@ struct Se3Walk {
         hKa = __halves2half2(ha, ha);
         hKb = __halves2half2(hb, hb);
     }
-    __device__ __forceinline__ void start() {
+    __device__ __forceinline__ void start(float radius) {
         top.init(a.k);
+        rad = radius;
         hq01 = __floats2half2_rn(sq[0], sq[1]);
         hq23 = __floats2half2_rn(sq[2], sq[3]);
         const float sc = -a.tScale, lim = 60000.0f;  // clamped: an out-of-range query only under-estimates its distances
@@ -154,7 +155,8 @@ struct Se3Walk {
         if (a.sp.weighted[0]) dr = dr * a.sp.weight[0];
         float dt = fp::sqrt_(s2);
         if (a.sp.weighted[1]) dt = dt * a.sp.weight[1];
-        top.offer(maybe && orig != MPTG_NO_INDEX, dr + dt, orig * a.idxMul + a.idxAdd, a.radius, lane);
+        const uint32_t rep = a.gid ? (orig != MPTG_NO_INDEX ? __ldg(a.gid + orig) : MPTG_NO_INDEX) : orig * a.idxMul + a.idxAdd;
+        top.offer(maybe && orig != MPTG_NO_INDEX, dr + dt, rep, rad, lane);
         refreshThr();
     }
 
@@ -260,11 +262,17 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, KPL == 1 ? MPTG_SE3_MIN_CTAS :
         slot = __shfl_sync(FULL_MASK, slot, 0);
         if (slot >= a.Q) break;  // warp-uniform; no block-wide barriers in this kernel
         const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
+        float radius = a.radius;
+        if (a.qcap) {  // sharded search: per-query cap, negative = not this shard's query
+            const float c = __ldg(a.qcap + q);
+            if (c < 0.0f) continue;
+            radius = fminf(radius, c);
+        }
         __syncwarp();
         if (lane < 7) sq[lane] = a.queries[(size_t)q * 7u + lane];
         se3QueryPrep(sq, a, lane);
         Se3Walk<KPL> w(a, sq, lane, leaves, inner);
-        w.start();
+        w.start(radius);
         switch (a.top) {
             case 0: w.template descend<0>(0); break;
             case 1: w.template descend<1>(0); break;
@@ -309,6 +317,21 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnSe3KeyKernel(const BvhArgs<
         a.orderKeys[q] = node;
         atomicAdd(a.orderHist + (node >> a.orderShift), 1u);
     }
+}
+
+
+// lower bound of every query to the whole indexed set (see knnBvhRootBoundKernel)
+__global__ void __launch_bounds__(BVH_WARPS * 32) knnSe3RootBoundKernel(const BvhArgs<float> a) {
+    __shared__ __align__(16) float qsm[BVH_WARPS][SE3_QF];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * BVH_WARPS + warp;
+    if (q >= a.Q) return;
+    float* sq = qsm[warp];
+    if (lane < 7) sq[lane] = a.queries[(size_t)q * 7u + lane];
+    se3QueryPrep(sq, a, lane);
+    const uint32_t key = (uint32_t)lane < a.nNodes[a.top] ? se3CapKey(a.cap[a.top], 0, lane, sq) : BVH_DEAD;
+    const uint32_t best = __reduce_min_sync(FULL_MASK, key);
+    if (lane == 0) a.rootLb[q] = best == BVH_DEAD ? INFINITY : __uint_as_float(best);
 }
 
 }  // namespace mptg

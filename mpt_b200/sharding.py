@@ -38,6 +38,54 @@ def owner_of(global_index: int, world: int) -> Tuple[int, int]:
     return global_index % world, global_index // world
 
 
+def spatial_cells(states: np.ndarray, coords, lo, hi, world: int) -> np.ndarray:
+    """Rank of every state under a FIXED spatial partition of the box [lo, hi) over the given coordinates: the box is
+    halved along coords[0], coords[1], ... cyclically until there are `world` cells (world a power of two; otherwise
+    the last split is uneven in cell count, never in correctness).  Fixed by the bounds, not by the data, so a planner
+    can route a new node to its rank without knowing the other nodes.  For SE(3) states use the translation
+    coordinates (4, 5, 6): the rotation part of a uniform sample gives nothing to prune on at the top level."""
+    s = np.asarray(states)
+    cell = np.zeros(s.shape[0], dtype=np.int64)
+    lo = np.broadcast_to(np.asarray(lo, dtype=np.float64), (len(coords),)).copy()
+    hi = np.broadcast_to(np.asarray(hi, dtype=np.float64), (len(coords),)).copy()
+    cells, depth = 1, 0
+    # bit d of the cell index = which half along coords[d % len] at the (d // len)-th halving of that coordinate
+    while cells < world:
+        j = depth % len(coords)
+        level = depth // len(coords)
+        width = (hi[j] - lo[j]) / (2 ** level)
+        rel = (s[:, coords[j]].astype(np.float64) - lo[j]) / width
+        bit = (np.floor(rel * 2).astype(np.int64)) & 1
+        cell |= np.clip(bit, 0, 1) << depth
+        cells *= 2
+        depth += 1
+    return (cell % world).astype(np.int32)
+
+
+def sharded_knn_spatial(root_bound: Callable, local_topk: Callable, merge: Callable, all_gather: Callable, all_reduce_min: Callable,
+                        exchange: Callable, queries, k: int, rank: int, world: int):
+    """Host mirror of the protocol in csrc/comm.cu (same five steps), driven by callables so that the gloo tests can run
+    it on CPU:
+      root_bound(queries) -> [Q] lower bound of every query to this rank's shard
+      local_topk(queries, k, cap) -> (idx [Q,k], dist [Q,k]) with global indices; rows with cap < 0 are skipped
+         (NO_INDEX / inf), others are searched within radius cap
+      all_gather(x) -> [G, ...]; all_reduce_min(x) -> elementwise min over ranks
+      exchange(idx, dist) -> (idx_parts [G, n_own, k], dist_parts [G, n_own, k]) rows of this rank's slice from every rank
+      merge(idx_parts, dist_parts, k) -> (idx, dist, count) of the slice."""
+    lb_mine = np.asarray(root_bound(queries), dtype=np.float64)
+    lb_all = np.asarray(all_gather(lb_mine))                      # 1
+    home = lb_all.argmin(axis=0)                                  # lowest rank on ties
+    cap = np.where(home == rank, np.inf, -1.0)
+    idx, dist = local_topk(queries, k, cap)                       # 2
+    bound = np.asarray(all_reduce_min(dist[:, k - 1].astype(np.float64)))
+    cap2 = np.where((home != rank) & (lb_mine <= bound), bound, -1.0)
+    idx2, dist2 = local_topk(queries, k, cap2)                    # 3
+    sel = cap2 >= 0
+    idx[sel], dist[sel] = idx2[sel], dist2[sel]
+    ip, dp = exchange(idx, dist)                                  # 4
+    return merge(ip, dp, k)                                       # 5
+
+
 def sharded_knn(local_topk: Callable, merge: Callable, all_gather: Callable, queries, k: int):
     """Tree-sharded kNN step.
     local_topk(queries, k) -> (idx [Q,k] global indices, dist [Q,k]) on this rank's shard

@@ -76,6 +76,7 @@ int mptg_sync(mptg_ctx*) { return MPTG_OK; }
 const char* mptg_last_error(const mptg_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 void* mptg_ctx_stream(mptg_ctx*) { return nullptr; }
 uint64_t mptg_ctx_launch_count(const mptg_ctx* c) { return c->launches; }
+int mptg_ctx_sm_count(const mptg_ctx*) { return 1; }
 int mptg_space_scalars(const mptg_space_desc* s) { return spaceScalars(*s); }
 int mptg_space_dimensions(const mptg_space_desc* s) { return spaceDimensions(*s); }
 

@@ -31,6 +31,40 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(_P)
 
 
+class _Part(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("p", C.c_int32), ("dim", C.c_int32), ("_pad", C.c_int32), ("weight", C.c_double)]
+
+
+class _Desc(C.Structure):  # mptg_space_desc (include/mptg/mptg.h), declared here so that the CPU arm never loads libmptg.so
+    _fields_ = [("n_parts", C.c_int32), ("scalar", C.c_int32), ("part", _Part * 8)]
+
+
+class OracleSpace:
+    """A space descriptor for the oracle alone (bench.py --impl reference): same layout as mpt_b200.Space, built
+    without touching the product library."""
+
+    def __init__(self, parts, scalar=F32):
+        kinds = {"lp": 1, "so2": 2, "so3": 3}
+        self.desc = _Desc()
+        self.desc.n_parts, self.desc.scalar = len(parts), scalar
+        self.scalars = 0
+        for i, (kind, p, dim, w) in enumerate(parts):
+            self.desc.part[i].kind, self.desc.part[i].p = kinds[kind], p
+            self.desc.part[i].dim = 4 if kind == "so3" else dim
+            self.desc.part[i].weight = float(w)
+            self.scalars += 4 if kind == "so3" else dim
+        self.scalar = scalar
+        self.dtype = np.float32 if scalar == F32 else np.float64
+
+    @property
+    def ref(self):
+        return C.byref(self.desc)
+
+
+def se3_space(so3_weight=1.0, l2_weight=1.0, scalar=F32):
+    return OracleSpace([("so3", 0, 4, so3_weight), ("lp", 2, 3, l2_weight)], scalar)
+
+
 class Oracle:
     def __init__(self, lib):
         self.lib = lib

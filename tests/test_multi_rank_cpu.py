@@ -85,6 +85,44 @@ def _worker(rank, world, port, out_dir):
     wi, wd, wc = orc.knn(sp, pts, q, k)
     ok_tree = np.array_equal(idx, wi) and np.array_equal(d, wd) and np.array_equal(cnt, wc)
 
+    # spatially sharded tree, the protocol of csrc/comm.cu (root bounds -> home search -> bounded search -> exchange -> merge)
+    cells = sharding.spatial_cells(pts, (4, 5, 6), -100.0, 100.0, world)
+    mine_ids = np.nonzero(cells == rank)[0].astype(np.uint32)
+    mine_pts = pts[mine_ids]
+    tlo, thi = mine_pts[:, 4:].min(0).astype(np.float64), mine_pts[:, 4:].max(0).astype(np.float64)
+
+    def root_bound(queries):  # translation distance to the shard's bounding box: a lower bound of the SE(3) distance
+        e = np.maximum(np.maximum(tlo - queries[:, 4:], queries[:, 4:] - thi), 0.0)
+        return np.sqrt((e.astype(np.float64) ** 2).sum(1)) * (1 - 1e-6)
+
+    searched = [0]
+
+    def local_capped(queries, kk, cap):
+        idx = np.full((queries.shape[0], kk), m.NO_INDEX, dtype=np.uint32)
+        d = np.full((queries.shape[0], kk), np.inf, dtype=np.float32)
+        for r in np.unique(cap[cap >= 0]):
+            sel = np.nonzero(cap == r)[0]
+            li, ld, _ = orc.knn(sp, mine_pts, queries[sel], kk, float(r) if np.isfinite(r) else -1.0)
+            idx[sel] = np.where(li == m.NO_INDEX, li, mine_ids[np.minimum(li, len(mine_ids) - 1)])
+            d[sel] = ld
+        searched[0] += int((cap >= 0).sum())
+        return idx, d
+
+    def all_reduce_min(x):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return t.numpy()
+
+    def exchange(idx, d):
+        sl_own = sharding.unit_slice(q.shape[0], world, rank)
+        gi, gd = all_gather(idx), all_gather(d)      # gloo stand-in for the grouped send/recv: keep this rank's slice
+        return gi[:, sl_own], gd[:, sl_own]
+
+    si, sd, sc = sharding.sharded_knn_spatial(root_bound, local_capped, sharding.merge_topk_host, all_gather, all_reduce_min, exchange, q, k, rank, world)
+    sl_own = sharding.unit_slice(q.shape[0], world, rank)
+    ok_tree = ok_tree and np.array_equal(si, wi[sl_own]) and np.array_equal(sd, wd[sl_own]) and np.array_equal(sc, wc[sl_own])
+    ok_tree = ok_tree and searched[0] < 2 * q.shape[0]   # far shards are not searched: fewer than (home + all) searches
+
     # unit-sharded validity: every rank checks its slice, rank 0 gathers the bytes
     occ = W.synthetic_grid(300, 200, seed=3)
     a, b = W.grid_edges(1000, 300, 200, 5, 30.0)
