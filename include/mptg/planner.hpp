@@ -508,6 +508,11 @@ private:
         pushUpdate(n, delta);
     }
 
+    std::size_t truncatedBalls_ = 0;  // r-nearest neighbourhoods cut at MPTG_MAX_K nodes (see the wave below)
+
+public:
+    std::size_t truncatedNeighbourhoods() const { return truncatedBalls_; }
+
     // One wave == wave_ iterations of Worker::addSample (:510-657)
     void wave() {
         const std::uint32_t W = this->wave_;
@@ -577,6 +582,13 @@ private:
         const std::vector<std::uint32_t> nIdx = this->nn_->indices();
         const std::vector<Distance> nDist = this->nn_->distances();
         const std::vector<std::uint32_t> nCnt = this->nn_->counts();
+        if constexpr (std::is_same_v<Rewire, rewire_r_nearest>) {
+            // The reference asks for EVERY node within r (rrg_rewire_neighbors.hpp:125-128); the batched call returns at
+            // most MPTG_MAX_K (128) of them, the nearest ones.  A ball that held more is counted and reported with the
+            // statistics (dense trees, small free space): its farthest candidates were not offered for rewiring.
+            for (std::size_t s = 0; s < S; ++s)
+                if (nCnt[s] == k && nDist[s * k + (k - 1)] <= radius) ++truncatedBalls_;
+        }
 
         // candidate parents in (cost + distance) order up to the near node (:565-605), checked in ONE batch
         struct Cand {
@@ -891,6 +903,23 @@ class DevicePRRT {
     Distance goalBias_{0.01};
     std::vector<State> starts_;
     std::uint32_t wave_ = waveSize, size_ = 0, goalNode_ = NONE;
+    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
+    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
+    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
+    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
+    // throughout).  setWaveRamp(0) switches it off.
+    std::uint32_t ramp_ = 64, rampNow_ = 0;
+    std::uint32_t nextWave() {
+        if (ramp_ == 0) return wave_;
+        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
+        return rampNow_ < wave_ ? rampNow_ : wave_;
+    }
+
+public:
+    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+
+private:
+
     std::uint64_t waves_ = 0;
     double seconds_ = 0;
     mutable std::vector<State> states_;  // host mirror, refreshed on demand
@@ -906,7 +935,7 @@ class DevicePRRT {
         prm.space = &desc_, prm.lo = lo, prm.hi = hi;
         prm.range = std::isfinite((double)maxDistance_) ? (double)maxDistance_ : 1.7e308;
         prm.goal_bias = (double)goalBias_, prm.goal_state = g.data(), prm.goal_radius = (double)goal.radius();
-        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
+        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = (std::uint32_t)waveSize;
         check(mptg_prrt_create(ctx_.get(), geom_.get(), &prm, &prrt_), ctx_.get(), "mptg_prrt_create");
         for (const State& q : starts_) check(mptg_prrt_add_start(prrt_, q.data()), ctx_.get(), "mptg_prrt_add_start");
         size_ = (std::uint32_t)starts_.size();
@@ -947,7 +976,7 @@ public:
         create();
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_prrt_wave(prrt_, wave_, &size_, &goalNode_), ctx_.get(), "mptg_prrt_wave");
+            check(mptg_prrt_wave(prrt_, nextWave(), &size_, &goalNode_), ctx_.get(), "mptg_prrt_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1017,6 +1046,23 @@ class DevicePRRTStar {
     Distance goalBias_{0.01};
     std::vector<State> starts_;
     std::uint32_t wave_ = waveSize, size_ = 0, goalNode_ = NONE;
+    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
+    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
+    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
+    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
+    // throughout).  setWaveRamp(0) switches it off.
+    std::uint32_t ramp_ = 64, rampNow_ = 0;
+    std::uint32_t nextWave() {
+        if (ramp_ == 0) return wave_;
+        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
+        return rampNow_ < wave_ ? rampNow_ : wave_;
+    }
+
+public:
+    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+
+private:
+
     std::uint64_t waves_ = 0;
     mutable std::uint64_t mirroredWaves_ = ~0ull;
     double seconds_ = 0;
@@ -1034,7 +1080,7 @@ class DevicePRRTStar {
         prm.space = &desc_, prm.lo = lo, prm.hi = hi;
         prm.range = std::isfinite((double)maxDistance_) ? (double)maxDistance_ : 1.7e308;
         prm.goal_bias = (double)goalBias_, prm.goal_state = g.data(), prm.goal_radius = (double)goal.radius();
-        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
+        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed_, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = (std::uint32_t)waveSize;
         check(mptg_prrtstar_create(ctx_.get(), geom_.get(), &prm, (double)rewireFactor_, &prrt_), ctx_.get(), "mptg_prrtstar_create");
         if constexpr (rNearest) {  // rrg_rewire_neighbors.hpp:102-122
             const unsigned dim = scenario_.space().dimensions();
@@ -1086,7 +1132,7 @@ public:
         create();
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_prrtstar_wave(prrt_, wave_, &size_, &goalNode_), ctx_.get(), "mptg_prrtstar_wave");
+            check(mptg_prrtstar_wave(prrt_, nextWave(), &size_, &goalNode_), ctx_.get(), "mptg_prrtstar_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1162,6 +1208,23 @@ class DevicePPRM {
     mptg_space_desc desc_;
     mptg_pprm* pprm_ = nullptr;
     std::uint32_t wave_ = waveSize, size_ = 0, solved_ = 0, stride_ = 0;
+    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
+    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
+    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
+    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
+    // throughout).  setWaveRamp(0) switches it off.
+    std::uint32_t ramp_ = 64, rampNow_ = 0;
+    std::uint32_t nextWave() {
+        if (ramp_ == 0) return wave_;
+        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
+        return rampNow_ < wave_ ? rampNow_ : wave_;
+    }
+
+public:
+    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+
+private:
+
     std::size_t starts_ = 0, goals_ = 0;
     std::uint64_t waves_ = 0;
     double seconds_ = 0;
@@ -1196,7 +1259,7 @@ public:
             g = scenario_.goal().state();
             prm.goal_state = g.data(), prm.goal_radius = (double)scenario_.goal().radius();
         }
-        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = wave_;
+        prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = (std::uint32_t)waveSize;
         check(mptg_pprm_create(ctx_.get(), geom_.get(), &prm, &pprm_), ctx_.get(), "mptg_pprm_create");
         stride_ = mptg_pprm_row_stride(pprm_);
     }
@@ -1224,7 +1287,7 @@ public:
         if (goals_ == 0 || starts_ == 0) throw std::runtime_error("PPRM requires both start and goal configurations");
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_pprm_wave(pprm_, wave_, &size_, &solved_), ctx_.get(), "mptg_pprm_wave");
+            check(mptg_pprm_wave(pprm_, nextWave(), &size_, &solved_), ctx_.get(), "mptg_pprm_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

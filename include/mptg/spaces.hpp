@@ -295,7 +295,10 @@ struct UniformSampler<SE3Space<S, so3wt, l2wt>, SE3Bounds<S>> {
         }
         return q;
     }
-    S measure() const { return bounds.measure(); }
+    // Product of the parts' measures, each Scaled part times its weight (impl/uniform_sampler_scaled.hpp:59-66,
+    // impl/uniform_sampler_cartesian.hpp:93-97; SO(3): pi^2, impl/uniform_sampler_so3.hpp:79-83): pi^2 so3wt * volume l2wt.
+    // (r1 returned pi^2 * volume: with so3wt = 50 that made the r-nearest rewire radius 50^(-1/6) = 0.52x the reference's.)
+    S measure() const { return bounds.measure() * S(so3wt) * S(l2wt); }
 };
 
 }  // namespace mptg

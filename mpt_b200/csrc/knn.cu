@@ -367,16 +367,16 @@ __global__ void __launch_bounds__(256) knnMergeKernel(uint32_t parts, uint32_t Q
 // AoS -> SoA append
 template <typename S>
 __global__ void knnScatterKernel(const S* aos, uint32_t count, int D, S* pts, uint32_t stride, uint32_t first) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count * (uint32_t)D) return;
-    const uint32_t i = t / D, c = t % D;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // count * D exceeds 32 bits from 2^26 points of 64 scalars on
+    if (t >= (size_t)count * D) return;
+    const uint32_t i = (uint32_t)(t / D), c = (uint32_t)(t % D);
     pts[(size_t)c * stride + first + i] = aos[t];
 }
 template <typename S>
 __global__ void knnGatherKernel(const S* pts, uint32_t stride, uint32_t first, uint32_t count, int D, S* aos) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count * (uint32_t)D) return;
-    const uint32_t i = t / D, c = t % D;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)count * D) return;
+    const uint32_t i = (uint32_t)(t / D), c = (uint32_t)(t % D);
     aos[t] = pts[(size_t)c * stride + first + i];
 }
 
@@ -632,8 +632,8 @@ int queryDevT(mptg_knn* knn, const S* queries, uint32_t Q, uint32_t k, double ra
 
 template <typename S>
 int insertDevT(mptg_knn* knn, const S* aosDev, uint32_t count) {
-    const uint32_t total = count * (uint32_t)knn->D;
-    knnScatterKernel<S><<<(total + 255) / 256, 256, 0, knn->ctx->stream>>>(aosDev, count, knn->D, (S*)knn->pts,
+    const size_t total = (size_t)count * knn->D;
+    knnScatterKernel<S><<<(unsigned)((total + 255) / 256), 256, 0, knn->ctx->stream>>>(aosDev, count, knn->D, (S*)knn->pts,
                                                                              knn->stride, knn->size);
     MPTG_LAUNCHED(knn->ctx);
     return MPTG_OK;
@@ -741,11 +741,11 @@ int mptg_knn_get_states(mptg_knn* knn, uint32_t first, uint32_t count, void* out
     void* stage;
     int rc = scratch(ctx, 0, bytes, &stage);
     if (rc) return rc;
-    const uint32_t total = count * (uint32_t)knn->D;
+    const size_t total = (size_t)count * knn->D;
     if (knn->scalar == MPTG_F32)
-        knnGatherKernel<float><<<(total + 255) / 256, 256, 0, ctx->stream>>>((const float*)knn->pts, knn->stride, first, count, knn->D, (float*)stage);
+        knnGatherKernel<float><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const float*)knn->pts, knn->stride, first, count, knn->D, (float*)stage);
     else
-        knnGatherKernel<double><<<(total + 255) / 256, 256, 0, ctx->stream>>>((const double*)knn->pts, knn->stride, first, count, knn->D, (double*)stage);
+        knnGatherKernel<double><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const double*)knn->pts, knn->stride, first, count, knn->D, (double*)stage);
     MPTG_LAUNCHED(ctx);
     MPTG_CUDA(ctx, cudaMemcpyAsync(out, stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

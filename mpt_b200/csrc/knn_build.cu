@@ -569,7 +569,11 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     size_t memBytes = ix.memBytes;
     if (memBytes < bytes) {
         MPTG_CUDA(ctx, cudaStreamSynchronize(st));
-        if (mem) MPTG_CUDA(ctx, cudaFree(mem));
+        if (mem) {
+            // the handle must not keep a pointer to freed memory if the allocation below fails
+            ix.mem = nullptr, ix.memBytes = 0, ix.count = 0, ix.leafH = nullptr;
+            MPTG_CUDA(ctx, cudaFree(mem));
+        }
         mem = nullptr;
         memBytes = bytes + bytes / 2;
         if (ix.capacityHint > n) {  // every term of `bytes` is linear in n up to padding
@@ -583,6 +587,7 @@ int knnBuildIndexGpuT(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space,
     unsigned long long* stats = ix.devStats;
     if (!stats) {
         MPTG_CUDA(ctx, cudaMalloc(&stats, 8 * sizeof(unsigned long long)));
+        ix.devStats = stats;  // owned by the handle from here on: freed with it whatever happens below
         if (int rc = memsetSync(ctx, stats, 0, 8 * sizeof(unsigned long long))) return rc;
     }
 

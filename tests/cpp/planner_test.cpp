@@ -94,7 +94,25 @@ void testPRRTStarInvariants() {
                 worst, planner.solved() ? planner.solutionCost() : -1.0);
 }
 
+// measure of the sampled region of the SE(3) scenario: the reference multiplies the measure of every Scaled part by the
+// part's weight and the parts with each other (impl/uniform_sampler_scaled.hpp:59-66, impl/uniform_sampler_cartesian.hpp:
+// 93-97; SO(3) is pi^2, impl/uniform_sampler_so3.hpp:79-83; a box its volume).  PRRT*'s r-nearest rewire radius is built
+// from it (impl/rrg_rewire_neighbors.hpp:102-122), so a wrong measure silently shrinks every neighbourhood.
+void testSE3SamplerMeasure() {
+    mptg::BoxBounds<double, 3> box;
+    const double lo[3] = {-60.0, -60.0, -40.0}, hi[3] = {60.0, 60.0, 40.0};
+    for (int i = 0; i < 3; ++i) box.min_[i] = lo[i], box.max_[i] = hi[i];
+    const mptg::SE3Space<double, 50, 1> space;
+    const mptg::UniformSampler<mptg::SE3Space<double, 50, 1>, mptg::SE3Bounds<double>> sampler(space, mptg::SE3Bounds<double>(box));
+    const double pi = 3.14159265358979323846;
+    const double want = (pi * pi * 50.0) * ((120.0 * 120.0 * 80.0) * 1.0);
+    EXPECT(std::fabs(sampler.measure() - want) <= 1e-12 * want);
+    const mptg::UniformSampler<mptg::SE3Space<double, 1, 1>, mptg::SE3Bounds<double>> unweighted{mptg::SE3Space<double, 1, 1>(), mptg::SE3Bounds<double>(box)};
+    EXPECT(std::fabs(unweighted.measure() - want / 50.0) <= 1e-12 * want);
+}
+
 int main() {
+    testSE3SamplerMeasure();
     // test/pack_nearest_test.cpp:39-69 analogue: the strategy tag is recognised, absent -> void
     static_assert(std::is_same_v<impl::pack_nearest_t<>, void>);
     static_assert(std::is_same_v<impl::pack_nearest_t<int, report_stats<true>>, void>);
