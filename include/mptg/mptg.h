@@ -49,7 +49,7 @@ enum mptg_status {
 enum mptg_part_kind { MPTG_PART_LP = 1, MPTG_PART_SO2 = 2, MPTG_PART_SO3 = 3 };
 enum mptg_scalar { MPTG_F32 = 4, MPTG_F64 = 8 };
 enum mptg_knn_strategy { MPTG_KNN_AUTO = 0, MPTG_KNN_BRUTE = 1, MPTG_KNN_BVH = 2 };
-enum mptg_geom_kind { MPTG_GEOM_GRID = 1, MPTG_GEOM_SHAPES = 2, MPTG_GEOM_LINKARM = 3, MPTG_GEOM_MESH = 4 };
+enum mptg_geom_kind { MPTG_GEOM_GRID = 1, MPTG_GEOM_SHAPES = 2, MPTG_GEOM_LINKARM = 3, MPTG_GEOM_MESH = 4, MPTG_GEOM_NAOCUP = 5 };
 
 /* One factor of a Cartesian product space.  Replaces the compile-time metric tags
  * LP<p>, SO2<p>, SO3, Scaled<M,ratio>, Cartesian<...> (src/mpt/impl/metrics.hpp:40-42,
@@ -207,6 +207,16 @@ int mptg_linkarm_create(mptg_ctx* ctx, int scalar, int32_t n_links, const double
  * States are SE(3): qx qy qz qw tx ty tz. */
 int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t n_tri_robot, const float* robot_tris,
                           uint32_t n_tri_env, const float* env_tris, mptg_geom** out);
+/* The Nao humanoid holding a cup and a ball: 10 joint angles (right then left shoulder pitch, shoulder roll, elbow yaw,
+ * elbow roll, wrist yaw), forward kinematics of both arms, 209 sphere / capsule pair tests, the cup must stay upright.
+ * Replaces NaoCupScenario::valid / link (demo/nao_cup_planning.cpp:146-152), i.e. nao_clear and nao_link with
+ * compute / check_collisions (demo/nao_cup/src/naocup.hpp:556-730,795-840) and the primitives of
+ * demo/nao_cup/src/collide.hpp:45-115, linear.hpp:125-150.  The robot, the cup and the obstacles are the reference's
+ * constants (naocup.hpp:55-80,222-251,426-553).  States are LP(10) joint angles in radians. */
+int mptg_naocup_create(mptg_ctx* ctx, int scalar, mptg_geom** out);
+/* The reference's start, goal and joint limits (naocup.hpp:254-301), 10 doubles each (the values a float build of the
+ * reference uses are these rounded to float).  Any pointer may be NULL. */
+int mptg_naocup_configs(int scalar, double* start, double* goal, double* lo, double* hi);
 int mptg_geom_destroy(mptg_geom* geom);
 int mptg_geom_kind(const mptg_geom* geom);
 
@@ -228,6 +238,7 @@ int mptg_geom_contact_band(const mptg_geom* geom, double* band_out);
  *   GRID    valid(a) && valid(b) && midpoint bisection until |b-a|^2 < 1   (png_2d_scenario.hpp:112-117,152-165)
  *   SHAPES  balls: closed-form point-segment distance; rects: endpoints + bisection (shape_hierarchy.hpp:184-203,228-270)
  *   LINKARM valid(a) && valid(b) && bisection until |a-b|_inf < 0.02        (link_manipulator_scenario.hpp:118-138)
+ *   NAOCUP  midpoint bisection until |b-a|_2 < 1 degree; the ends are NOT checked (naocup.hpp:809-840)
  *   MESH    DiscreteMotionValidator with step size `step` over `space`      (discrete_motion_validator.hpp:71-130);
  *           `from` is assumed valid and not checked, exactly as the reference (:72-73).
  * `space` / `step` are only read for MESH (pass NULL / 0 otherwise).

@@ -22,7 +22,7 @@ OK, ERR_BAD_ARG, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_CAPACITY, ERR_UNSUPPORTED = 0,
 PART_LP, PART_SO2, PART_SO3 = 1, 2, 3
 F32, F64 = 4, 8
 KNN_AUTO, KNN_BRUTE, KNN_BVH = 0, 1, 2
-GEOM_GRID, GEOM_SHAPES, GEOM_LINKARM, GEOM_MESH = 1, 2, 3, 4
+GEOM_GRID, GEOM_SHAPES, GEOM_LINKARM, GEOM_MESH, GEOM_NAOCUP = 1, 2, 3, 4, 5
 
 
 class SpacePart(C.Structure):
@@ -96,6 +96,8 @@ SYMBOLS = {
     "mptg_grid_create": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "mptg_shapes_create": (C.c_int, [_P, C.c_int, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P, C.POINTER(_P)]),
     "mptg_linkarm_create": (C.c_int, [_P, C.c_int, C.c_int32, _P, C.c_double, C.c_int32, _P, C.POINTER(_P)]),
+    "mptg_naocup_create": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "mptg_naocup_configs": (C.c_int, [C.c_int, _P, _P, _P, _P]),
     "mptg_mesh_pair_create": (C.c_int, [_P, C.c_int, _U32, _P, _U32, _P, C.POINTER(_P)]),
     "mptg_geom_destroy": (C.c_int, [_P]),
     "mptg_geom_kind": (C.c_int, [_P]),

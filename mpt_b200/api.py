@@ -595,6 +595,20 @@ class Scenario:
         return cls(ctx, h, scalar, ln.shape[0])
 
     @classmethod
+    def nao_cup(cls, ctx: Context, scalar: int = L.F64):
+        """NaoCupScenario (demo/nao_cup_planning.cpp:50-153): 10 joint angles, the reference's robot, cup and obstacles."""
+        h = C.c_void_p()
+        L.check(ctx.lib.mptg_naocup_create(ctx.h, scalar, C.byref(h)), ctx.h)
+        return cls(ctx, h, scalar, 10)
+
+    @staticmethod
+    def nao_cup_configs(scalar: int = L.F64):
+        """(start, goal, lo, hi) of the reference (naocup.hpp:254-301) as float64 arrays of 10."""
+        out = [np.zeros(10) for _ in range(4)]
+        L.check(L.load().mptg_naocup_configs(scalar, *[_ptr(a) for a in out]), None)
+        return tuple(out)
+
+    @classmethod
     def mesh_pair(cls, ctx: Context, robot_tris, env_tris, space: Space, step: float):
         """SE3RigidBodyScenario (demo/se3_rigid_body_scenario.hpp): triangle soups [n,3,3] float32."""
         rt = np.ascontiguousarray(robot_tris, dtype=np.float32).reshape(-1, 9)

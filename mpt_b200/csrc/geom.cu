@@ -10,17 +10,35 @@
 // L (rooted at depth five) depth first with an explicit stack; a warp vote per iteration stops all
 // lanes at the first invalid probe.  All midpoints are produced by the same sequence of
 // floating point operations as the reference's recursion, so decisions are bit-identical.
+#include <cub/device/device_scan.cuh>
 #include <cstdio>
 #include <cstdlib>
 
 #include "geom.cuh"
+#include "nao.cuh"
 
 namespace mptg {
 
 // ------------------------------------------------------------------ validators
+constexpr int FLAT_MAX_LEVELS = 24;
+
+// number of levels k >= 0 with d / 2^k >= thresh - slack: no node of the recursion is deeper (see Validator::levels)
+template <typename S>
+__device__ __forceinline__ int levelsFor(S d, S t) {
+    if (!(t > S(0))) return FLAT_MAX_LEVELS + 1;
+    int L = 0;
+    if (!(d == d)) return 1;  // NaN never meets the stop test: the root is probed (and fails)
+    while (d >= t && L <= FLAT_MAX_LEVELS) {
+        d = d * S(0.5);
+        ++L;
+    }
+    return L;
+}
+
 template <typename S>
 struct GridValidator {
     static constexpr int MAXD = 2;
+    static constexpr bool CHECK_ENDS = true;
     static constexpr int MAXDEPTH = 48;
     const uint32_t* bits;
     int width, height;
@@ -45,6 +63,7 @@ struct GridValidator {
 template <typename S>
 struct ShapesValidator {
     static constexpr int MAXD = 2;
+    static constexpr bool CHECK_ENDS = true;
     static constexpr int MAXDEPTH = 48;
     const S* rects;
     int nRects;
@@ -84,6 +103,7 @@ __device__ __forceinline__ S distPointSegmentSquared2(const S* pt, const S* s0, 
 template <typename S, int MAXD_>
 struct ArmValidator {
     static constexpr int MAXD = MAXD_;
+    static constexpr bool CHECK_ENDS = true;
     static constexpr int MAXDEPTH = 8;  // beyond the 5 split levels: |a-b|_inf up to 0.02 * 2^13 rad
     const S* lengths;
     const S* circles;
@@ -132,6 +152,18 @@ struct ArmValidator {
         }
         return m < S(0.02);
     }
+    // bound of the recursion depth for the flat edge check: the ends of a node at depth k differ by maxdiff / 2^k up to
+    // the rounding of k midpoints (each within an ulp of the coordinates' magnitude); 1/64 relative + that absolute slack
+    __device__ __forceinline__ int levels(const S* a, const S* b) const {
+        S m = S(0), mag = S(1);
+        for (int i = 0; i < nLinks; ++i) {
+            const S d = fp::abs_(a[i] - b[i]);
+            m = d > m ? d : m;
+            mag = fmax(mag, fmax(fp::abs_(a[i]), fp::abs_(b[i])));
+        }
+        if (!(m == m)) return 1;
+        return levelsFor<S>(m, S(0.02) * S(63.0 / 64.0) - S(256) * fp::consts<S>::eps() * mag);
+    }
 };
 
 // ------------------------------------------------------------------ bisection edge kernel
@@ -153,8 +185,11 @@ __global__ void __launch_bounds__(256) bisectLinkKernel(const V v, const S* __re
             b[i] = to[(size_t)e * D + i];
         }
         // endpoints: lanes 0-15 probe a, lanes 16-31 probe b (one probe latency instead of two)
-        for (int i = 0; i < D; ++i) mid[i] = lane < 16 ? a[i] : b[i];
-        bool good = __all_sync(FULL_MASK_, v.valid(mid));
+        bool good = true;
+        if (V::CHECK_ENDS) {  // (the Nao scenario's link assumes valid ends and does not look at them)
+            for (int i = 0; i < D; ++i) mid[i] = lane < 16 ? a[i] : b[i];
+            good = __all_sync(FULL_MASK_, v.valid(mid));
+        }
         // Phase A -- the 31 midpoints of the five top levels, ONE per lane: lane j owns heap node j+1
         // (depth floor(log2(j+1))), walks down to it computing midpoints only, and probes just that
         // node.  A node exists iff none of its ancestors met the stop test.
@@ -266,6 +301,98 @@ __global__ void validKernel(const V v, const S* __restrict__ states, uint32_t n,
     const int D = v.dims();
     for (int c = 0; c < D; ++c) q[c] = states[(size_t)i * D + c];
     ok[i] = v.valid(q) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ flat edge check (expensive validators)
+// bisectLinkKernel gives an edge to a warp.  That suits probes of a few instructions (a grid cell); for the Nao scenario
+// (one probe = two arms of forward kinematics and 209 pair tests, ~6.5 K operations) and planner-size edges (5 - 60
+// midpoints) it left most lanes idle: 149 M midpoints/s against 2.4 G states/s of validKernel on the same validator.
+// Here ALL midpoints of ALL edges of the batch form one flat list -- edge e contributes its ends (validators that check
+// them) and the heap nodes 1 .. 2^L - 1 of its recursion tree, L a conservative bound of the tree's depth -- and a thread
+// takes one item: it finds the edge by binary search in the prefix sums, reaches its node by midpoint arithmetic alone
+// (the reference's (a+b)/2 sequence and stop test at every level, so the node exists exactly when the reference's
+// recursion creates it) and probes it.  A failed probe clears ok[e]; items of an edge already cleared are skipped.
+template <typename S, typename V>
+__global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* __restrict__ to, uint32_t n,
+                               unsigned long long* __restrict__ counts, uint8_t* __restrict__ ok, unsigned long long* __restrict__ stats) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (e == 0) counts[n] = 0;
+    S a[V::MAXD], b[V::MAXD];
+    const int D = v.dims();
+    for (int i = 0; i < D; ++i) a[i] = from[(size_t)e * D + i], b[i] = to[(size_t)e * D + i];
+    const int L = v.levels(a, b);
+    if (L > FLAT_MAX_LEVELS) {
+        atomicOr(stats + 4, (unsigned long long)GEOM_ERR_STEPS);
+        ok[e] = 0;
+        counts[e] = 0;
+        return;
+    }
+    ok[e] = 1;
+    counts[e] = (V::CHECK_ENDS ? 2ull : 0ull) + ((1ull << L) - 1ull);
+}
+
+template <typename S, typename V>
+__global__ void __launch_bounds__(256) flatLinkKernel(const V v, const S* __restrict__ from, const S* __restrict__ to, uint32_t n,
+                                                      const unsigned long long* __restrict__ offs, uint8_t* ok,
+                                                      unsigned long long* __restrict__ stats) {
+    const unsigned long long total = offs[n];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int D = v.dims();
+    unsigned long long probes = 0;
+    // The trip count is the same for the 32 lanes of a warp and every lane reaches the __syncwarp() in front of the
+    // probe: a first version that left the loop body with `continue` had its lanes drift apart for good (independent
+    // thread scheduling does not rejoin them at the back edge) and ran the probe with 5.9 of 32 lanes on average.
+    for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total; base += stride) {
+        const unsigned long long it = base + lane;
+        bool live = it < total;
+        uint32_t e = 0;
+        S a[V::MAXD], b[V::MAXD], mid[V::MAXD];
+        if (live) {
+            uint32_t lo = 0, hi = n;  // largest e with offs[e] <= it
+            while (hi - lo > 1) {
+                const uint32_t m = (lo + hi) >> 1;
+                if (__ldg(offs + m) <= it) lo = m;
+                else hi = m;
+            }
+            e = lo;
+            live = *(volatile uint8_t*)(ok + e) != 0;
+        }
+        if (live) {
+            unsigned long long j = it - __ldg(offs + e);
+            for (int i = 0; i < D; ++i) a[i] = __ldg(from + (size_t)e * D + i), b[i] = __ldg(to + (size_t)e * D + i);
+            if (V::CHECK_ENDS && j < 2) {
+                for (int i = 0; i < D; ++i) mid[i] = j == 0 ? a[i] : b[i];
+            } else {
+                if (V::CHECK_ENDS) j -= 2;
+                const unsigned long long h = j + 1;  // heap index: 1 = the edge's own midpoint
+                const int d = 63 - __clzll(h);
+                for (int level = 0; level < d; ++level) {
+                    if (v.stop(a, b)) {
+                        live = false;
+                        break;
+                    }
+                    for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
+                    if ((h >> (d - 1 - level)) & 1) {
+                        for (int i = 0; i < D; ++i) a[i] = mid[i];
+                    } else {
+                        for (int i = 0; i < D; ++i) b[i] = mid[i];
+                    }
+                }
+                if (live && v.stop(a, b)) live = false;
+                for (int i = 0; i < D; ++i) mid[i] = (a[i] + b[i]) / S(2);
+            }
+        }
+        __syncwarp();
+        if (live) {
+            ++probes;
+            if (!v.valid(mid)) ok[e] = 0;
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(FULL_MASK_, probes, o);
+    if (lane == 0 && stats && probes) atomicAdd(stats + 2, probes);
 }
 
 // ------------------------------------------------------------------ balls (any dimension)
@@ -410,8 +537,43 @@ int validDevT(mptg_geom* g, const S* states, uint32_t n, uint8_t* ok) {
 #undef MPTG_ARM_VALID
             break;
         }
+        case MPTG_GEOM_NAOCUP: {
+            nao::Validator<S> v{*(const nao::Model<S>*)g->naoModel};
+            validKernel<S, nao::Validator<S>><<<grid, block, 0, ctx->stream>>>(v, states, n, ok);
+            break;
+        }
         default: return fail(ctx, MPTG_ERR_BAD_ARG, "valid: unknown geometry kind %d", g->kind);
     }
+    MPTG_LAUNCHED(ctx);
+    return MPTG_OK;
+}
+
+// flat edge check: plan (levels per edge) -> prefix sums (cub, library code) -> one item per thread
+template <typename S, typename V>
+int flatLink(mptg_geom* g, const V& v, const S* from, const S* to, uint32_t n, uint8_t* ok) {
+    mptg_ctx* ctx = g->ctx;
+    size_t scanBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)(n + 1u));
+    const size_t listBytes = ((size_t)(n + 1u) * sizeof(unsigned long long) + 255) & ~(size_t)255;
+    const size_t want = 2 * listBytes + scanBytes;
+    if (g->flatBytes < want) {
+        MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (g->flatBuf) MPTG_CUDA(ctx, cudaFree(g->flatBuf));
+        g->flatBuf = nullptr, g->flatBytes = 0;
+        MPTG_CUDA(ctx, cudaMalloc(&g->flatBuf, want + want / 2));
+        g->flatBytes = want + want / 2;
+    }
+    auto* counts = (unsigned long long*)g->flatBuf;
+    auto* offs = (unsigned long long*)((char*)g->flatBuf + listBytes);
+    void* temp = (char*)g->flatBuf + 2 * listBytes;
+    flatPlanKernel<S, V><<<(n + 255) / 256, 256, 0, ctx->stream>>>(v, from, to, n, counts, ok, g->devStats);
+    MPTG_LAUNCHED(ctx);
+    MPTG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(temp, scanBytes, counts, offs, (int)(n + 1u), ctx->stream));
+    MPTG_LAUNCHED(ctx);
+    // the length of the list is only known on the device: a resident grid strides over it
+    int perSm = 0;
+    MPTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flatLinkKernel<S, V>, 256, 0));
+    flatLinkKernel<S, V><<<ctx->smCount * (perSm > 0 ? perSm : 1), 256, 0, ctx->stream>>>(v, from, to, n, offs, ok, g->devStats);
     MPTG_LAUNCHED(ctx);
     return MPTG_OK;
 }
@@ -444,14 +606,29 @@ int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) 
 #define MPTG_ARM_LINK(MD)                                                                                          \
     {                                                                                                              \
         ArmValidator<S, MD> v{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
-        bisectLinkKernel<S, ArmValidator<S, MD>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats); \
+        if (armFlat) {                                                                                             \
+            if (int rc = flatLink<S, ArmValidator<S, MD>>(g, v, from, to, n, ok)) return rc;                       \
+        } else {                                                                                                   \
+            bisectLinkKernel<S, ArmValidator<S, MD>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats); \
+            MPTG_LAUNCHED(ctx);                                                                                    \
+        }                                                                                                          \
     }
+            static const bool armFlat = getenv("MPTG_ARM_WARP_PER_EDGE") == nullptr;  // the earlier kernel stays selectable for comparisons
             if (g->nLinks <= 8) MPTG_ARM_LINK(8)
             else if (g->nLinks <= 16) MPTG_ARM_LINK(16)
             else if (g->nLinks <= 32) MPTG_ARM_LINK(32)
             else MPTG_ARM_LINK(64)
 #undef MPTG_ARM_LINK
-            MPTG_LAUNCHED(ctx);
+            break;
+        }
+        case MPTG_GEOM_NAOCUP: {
+            nao::Validator<S> v{*(const nao::Model<S>*)g->naoModel};
+            if (getenv("MPTG_NAO_WARP_PER_EDGE")) {  // the earlier kernel, kept for the comparison in DESIGN.md
+                bisectLinkKernel<S, nao::Validator<S>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats);
+                MPTG_LAUNCHED(ctx);
+                break;
+            }
+            if (int rc = flatLink<S, nao::Validator<S>>(g, v, from, to, n, ok)) return rc;
             break;
         }
         default: return fail(ctx, MPTG_ERR_BAD_ARG, "link: unknown geometry kind %d", g->kind);
@@ -569,6 +746,46 @@ int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t nr, const float* r
     return MPTG_OK;
 }
 
+int mptg_naocup_create(mptg_ctx* ctx, int scalar, mptg_geom** out) {
+    if (!ctx || !out || (scalar != MPTG_F32 && scalar != MPTG_F64)) return fail(ctx, MPTG_ERR_BAD_ARG, "mptg_naocup_create: bad argument");
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    mptg_geom* g;
+    int rc = newGeom(ctx, MPTG_GEOM_NAOCUP, scalar, &g);
+    if (rc) return rc;
+    g->D = nao::DIM;
+    // the model is a block of scalars evaluated on the host; it travels to the kernels as a launch parameter
+    if (scalar == MPTG_F32) g->naoModel = new nao::Model<float>(nao::makeModel<float>());
+    else g->naoModel = new nao::Model<double>(nao::makeModel<double>());
+    *out = g;
+    return MPTG_OK;
+}
+
+int mptg_naocup_configs(int scalar, double* start, double* goal, double* lo, double* hi) {
+    if (scalar != MPTG_F32 && scalar != MPTG_F64) return fail(nullptr, MPTG_ERR_BAD_ARG, "mptg_naocup_configs: scalar must be MPTG_F32 or MPTG_F64");
+    // naocup.hpp:254-301; limits in degrees :196-219, converted as RAD(x) = x * (PI / 180) in the scalar type
+    static const double startC[10] = {1.125998, -0.691876, 1.888312, 0.776246, 0.245398, 1.259372, 0.279146, -1.587732, -0.510780, -1.823800};
+    static const double goalC[10] = {0.258284303377494,  -0.2699099199363406, -0.01113121187052224, 1.2053012757652763,  1.2716626717484503,
+                                     -0.9826967097045605, 0.07355836822937814, 0.25450053440459897,  -0.9512909033938429, -0.5297424293532234};
+    static const double loDeg[10] = {-119.5, -94.5, -119.5, 0.5, -104.5, -119.5, 0.5, -119.5, -89.5, -104.5};
+    static const double hiDeg[10] = {119.5, -0.5, 119.5, 89.5, 104.5, 119.5, 94.5, 119.5, -0.5, 104.5};
+    for (int i = 0; i < 10; ++i) {
+        if (scalar == MPTG_F32) {
+            const float k = float(float(3.14159265358979323846) / float(180.0));
+            if (start) start[i] = (double)(float)startC[i];
+            if (goal) goal[i] = (double)(float)goalC[i];
+            if (lo) lo[i] = (double)(float(loDeg[i]) * k);
+            if (hi) hi[i] = (double)(float(hiDeg[i]) * k);
+        } else {
+            const double k = 3.14159265358979323846 / 180.0;
+            if (start) start[i] = startC[i];
+            if (goal) goal[i] = goalC[i];
+            if (lo) lo[i] = loDeg[i] * k;
+            if (hi) hi[i] = hiDeg[i] * k;
+        }
+    }
+    return MPTG_OK;
+}
+
 int mptg_geom_destroy(mptg_geom* g) {
     if (!g) return MPTG_OK;
     cudaSetDevice(g->ctx->device);
@@ -579,7 +796,12 @@ int mptg_geom_destroy(mptg_geom* g) {
     cudaFree(g->lengths);
     cudaFree(g->circles);
     cudaFree(g->devStats);
+    cudaFree(g->flatBuf);
     if (g->mesh) meshDestroy(g->mesh);
+    if (g->naoModel) {
+        if (g->scalar == MPTG_F32) delete (nao::Model<float>*)g->naoModel;
+        else delete (nao::Model<double>*)g->naoModel;
+    }
     delete g;
     return MPTG_OK;
 }

@@ -25,6 +25,11 @@ struct mptg_geom {
     double linkRadius = 0;
     // mesh
     MeshData* mesh = nullptr;
+    // Nao-cup scenario: nao::Model<float|double> (host; passed to the kernels by value)
+    void* naoModel = nullptr;
+    // flat edge check (geom.cu flatLink): per-edge item counts, their prefix sums, scan work space
+    void* flatBuf = nullptr;
+    size_t flatBytes = 0;
     // per-call status / counters (device), mirrored on demand
     unsigned long long* devStats = nullptr;  // [0]=states [1]=bv tests [2]=primitive tests [3]=items [4]=error flags
     uint64_t stats[4] = {0, 0, 0, 0};

@@ -222,3 +222,33 @@ def arm_edges(n: int, n_links: int, seed: int, max_delta: float = 0.5, dtype=np.
     rng = np.random.default_rng(seed + 1)
     b = np.clip(a + (rng.random((n, n_links)) * 2 - 1) * max_delta, -np.pi, np.pi)
     return np.ascontiguousarray(a.astype(dtype)), np.ascontiguousarray(b.astype(dtype))
+
+
+# ---------------------------------------------------------------------------------- Nao with cup and ball
+NAO_START = np.array([1.125998, -0.691876, 1.888312, 0.776246, 0.245398, 1.259372, 0.279146, -1.587732, -0.510780, -1.823800])
+NAO_GOAL = np.array([0.258284303377494, -0.2699099199363406, -0.01113121187052224, 1.2053012757652763, 1.2716626717484503,
+                     -0.9826967097045605, 0.07355836822937814, 0.25450053440459897, -0.9512909033938429, -0.5297424293532234])
+NAO_LO = np.deg2rad([-119.5, -94.5, -119.5, 0.5, -104.5, -119.5, 0.5, -119.5, -89.5, -104.5])
+NAO_HI = np.deg2rad([119.5, -0.5, 119.5, 89.5, 104.5, 119.5, 94.5, 119.5, -0.5, 104.5])
+
+
+def nao_states(n: int, seed: int, sigma: float = 0.3, uniform_fraction: float = 0.25, dtype=np.float64) -> np.ndarray:
+    """Joint configurations of the Nao-cup scenario (demo/nao_cup/src/naocup.hpp:254-301): a quarter uniform in the joint
+    limits (about 2 % of those are clear: the cup must stay upright), the rest scattered round the reference's start and goal
+    configurations (the region a planner works in)."""
+    rng = np.random.default_rng(seed)
+    nu = int(n * uniform_fraction)
+    q = np.empty((n, 10))
+    q[:nu] = NAO_LO + (NAO_HI - NAO_LO) * rng.random((nu, 10))
+    pick = rng.random((n - nu, 1)) < 0.5
+    q[nu:] = np.where(pick, NAO_START, NAO_GOAL) + rng.normal(0.0, sigma, (n - nu, 10))
+    return np.ascontiguousarray(np.clip(q, NAO_LO, NAO_HI).astype(dtype))
+
+
+def nao_edges(n: int, seed: int, sigma: float = 0.3, reach: float = 0.25, dtype=np.float64):
+    """Edges from nao_states to a configuration `reach`-scattered round them (|b - a| of a few tenths of a radian: some
+    tens of 1-degree bisection midpoints each)."""
+    a = nao_states(n, seed, sigma, 0.0, np.float64)
+    rng = np.random.default_rng(seed + 1)
+    b = np.clip(a + rng.normal(0.0, reach / np.sqrt(10.0), (n, 10)) * rng.random((n, 1)) * 2.0, NAO_LO, NAO_HI)
+    return np.ascontiguousarray(a.astype(dtype)), np.ascontiguousarray(b.astype(dtype))

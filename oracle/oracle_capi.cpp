@@ -7,6 +7,7 @@
 #include <memory>
 
 #include "oracle.hpp"
+#include "oracle_nao.hpp"
 #include "oracle_sample.hpp"
 #include "oracle_tree.hpp"
 
@@ -23,6 +24,8 @@ struct Geom {
     LinkArm<double> armD;
     MeshPair<float> meshF;
     MeshPair<double> meshD;
+    NaoCup<float> naoF;
+    NaoCup<double> naoD;
     uint64_t stats[4] = {0, 0, 0, 0};
 };
 
@@ -34,6 +37,7 @@ struct Pick<float> {
     static Shapes<float>& shapes(Geom& g) { return g.shapesF; }
     static LinkArm<float>& arm(Geom& g) { return g.armF; }
     static MeshPair<float>& mesh(Geom& g) { return g.meshF; }
+    static NaoCup<float>& nao(Geom& g) { return g.naoF; }
 };
 template <>
 struct Pick<double> {
@@ -41,11 +45,12 @@ struct Pick<double> {
     static Shapes<double>& shapes(Geom& g) { return g.shapesD; }
     static LinkArm<double>& arm(Geom& g) { return g.armD; }
     static MeshPair<double>& mesh(Geom& g) { return g.meshD; }
+    static NaoCup<double>& nao(Geom& g) { return g.naoD; }
 };
 
 template <typename S>
 int validBatch(Geom& g, const S* st, uint32_t n, uint8_t* ok, double* margin) {
-    int D = g.kind == MPTG_GEOM_MESH ? 7 : g.kind == MPTG_GEOM_LINKARM ? Pick<S>::arm(g).nLinks
+    int D = g.kind == MPTG_GEOM_MESH ? 7 : g.kind == MPTG_GEOM_NAOCUP ? 10 : g.kind == MPTG_GEOM_LINKARM ? Pick<S>::arm(g).nLinks
                                        : g.kind == MPTG_GEOM_SHAPES  ? Pick<S>::shapes(g).dim
                                                                      : 2;
     uint64_t bv = 0, tt = 0;
@@ -59,6 +64,12 @@ int validBatch(Geom& g, const S* st, uint32_t n, uint8_t* ok, double* margin) {
             case MPTG_GEOM_GRID: v = Pick<S>::grid(g).valid(q); break;
             case MPTG_GEOM_SHAPES: v = Pick<S>::shapes(g).valid(q); break;
             case MPTG_GEOM_LINKARM: v = Pick<S>::arm(g).valid(q); break;
+            case MPTG_GEOM_NAOCUP: {
+                uint64_t pairs = 0;
+                v = margin ? Pick<S>::nao(g).valid(q, nullptr, &m, &pairs) : Pick<S>::nao(g).valid(q, nullptr, nullptr, &pairs);
+                tt += pairs;
+                break;
+            }
             case MPTG_GEOM_MESH:
                 if (margin) v = Pick<S>::mesh(g).valid(q, &m, 1e-6 * Pick<S>::mesh(g).scale, &C);
                 else v = Pick<S>::mesh(g).valid(q, nullptr, 0, &C);
@@ -76,7 +87,7 @@ int validBatch(Geom& g, const S* st, uint32_t n, uint8_t* ok, double* margin) {
 template <typename S>
 int linkBatch(Geom& g, const mptg_space_desc* sp, const S* from, const S* to, uint32_t n, double step,
               uint8_t* ok, uint8_t* nearContact, double tolRel, uint64_t* statesOut) {
-    int D = g.kind == MPTG_GEOM_MESH ? 7 : g.kind == MPTG_GEOM_LINKARM ? Pick<S>::arm(g).nLinks
+    int D = g.kind == MPTG_GEOM_MESH ? 7 : g.kind == MPTG_GEOM_NAOCUP ? 10 : g.kind == MPTG_GEOM_LINKARM ? Pick<S>::arm(g).nLinks
                                        : g.kind == MPTG_GEOM_SHAPES  ? Pick<S>::shapes(g).dim
                                                                      : 2;
     uint64_t totalStates = 0, bv = 0, tt = 0;
@@ -91,6 +102,17 @@ int linkBatch(Geom& g, const mptg_space_desc* sp, const S* from, const S* to, ui
             case MPTG_GEOM_GRID: v = Pick<S>::grid(g).link(a, b); break;
             case MPTG_GEOM_SHAPES: v = Pick<S>::shapes(g).link(a, b); break;
             case MPTG_GEOM_LINKARM: v = Pick<S>::arm(g).link(a, b); break;
+            case MPTG_GEOM_NAOCUP: {
+                uint64_t cnt = 0;
+                v = Pick<S>::nao(g).link(a, b, &cnt);
+                totalStates += cnt;
+                if (nearContact) {  // some midpoint of the edge's whole recursion decides within tolRel of a threshold
+                    double m = std::numeric_limits<double>::infinity();
+                    Pick<S>::nao(g).linkMargin(a, b, &m);
+                    nc = m < tolRel;
+                }
+                break;
+            }
             case MPTG_GEOM_MESH: {
                 auto& mesh = Pick<S>::mesh(g);
                 uint64_t cnt = 0;
@@ -260,6 +282,13 @@ void* orc_linkarm_create(int scalar, int nLinks, const double* lengths, double l
         g->armF.circles.push_back((float)cxcyr[i]);
         g->armD.circles.push_back(cxcyr[i]);
     }
+    return g;
+}
+
+void* orc_naocup_create(int scalar) {
+    auto* g = new Geom();
+    g->kind = MPTG_GEOM_NAOCUP;
+    g->scalar = scalar;
     return g;
 }
 

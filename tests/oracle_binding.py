@@ -73,12 +73,13 @@ class Oracle:
         lib.orc_tree_create.argtypes = [_P, _P, C.c_uint32]
         lib.orc_tree_destroy.argtypes = [_P]
         lib.orc_tree_knn.argtypes = [_P, _P, C.c_uint32, C.c_uint32, C.c_double, _P, _P, _P, _P]
-        for f in ("orc_grid_create", "orc_shapes_create", "orc_linkarm_create", "orc_mesh_pair_create"):
+        for f in ("orc_grid_create", "orc_shapes_create", "orc_linkarm_create", "orc_mesh_pair_create", "orc_naocup_create"):
             getattr(lib, f).restype = _P
         lib.orc_grid_create.argtypes = [C.c_int, C.c_int, C.c_int, _P]
         lib.orc_shapes_create.argtypes = [C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P]
         lib.orc_linkarm_create.argtypes = [C.c_int, C.c_int, _P, C.c_double, C.c_int, _P]
         lib.orc_mesh_pair_create.argtypes = [C.c_int, C.c_uint32, _P, C.c_uint32, _P]
+        lib.orc_naocup_create.argtypes = [C.c_int]
         lib.orc_geom_destroy.argtypes = [_P]
         lib.orc_valid_batch.argtypes = [_P, _P, C.c_uint32, _P, _P]
         lib.orc_link_batch.argtypes = [_P, _P, _P, _P, C.c_uint32, C.c_double, _P, _P, C.c_double, _P]
@@ -173,6 +174,12 @@ class Oracle:
         ln = np.ascontiguousarray(lengths, dtype=np.float64)
         cc = np.ascontiguousarray(circles, dtype=np.float64).reshape(-1, 3)
         return OracleGeom(self, self.lib.orc_linkarm_create(scalar, ln.shape[0], _ptr(ln), float(link_radius), cc.shape[0], _ptr(cc)), scalar, ln.shape[0])
+
+    def nao_cup(self, scalar=F64):
+        """oracle/oracle_nao.hpp: valid = nao_clear, link = nao_link.  valid(..., with_margin=True) also returns the smallest
+        |distance - reach| / |cup axis - threshold| of the state; link(..., with_near_contact=True, tol_rel=t) flags the
+        edges with such a margin below t on some midpoint of their recursion."""
+        return OracleGeom(self, self.lib.orc_naocup_create(scalar), scalar, 10)
 
     def tri_pairs(self, P, Q):
         """n triangle pairs [n,3,3] (double): (SAT decision, SAT margin, orientation-predicate decision)."""

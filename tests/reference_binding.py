@@ -13,6 +13,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "oracle" / "_ref" / "libref.so"
 LIB_PLANNER = ROOT / "oracle" / "_ref" / "libref_planner.so"
+LIB_NAO = ROOT / "oracle" / "_ref" / "libref_nao.so"
 REFERENCE = Path("/root/reference")
 _P = C.c_void_p
 VALID_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_void_p)
@@ -25,7 +26,7 @@ def available() -> bool:
 def load():
     if REFERENCE.exists():
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "ref"], check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
-    return Ref(C.CDLL(str(LIB)), C.CDLL(str(LIB_PLANNER)))
+    return Ref(C.CDLL(str(LIB)), C.CDLL(str(LIB_PLANNER)), C.CDLL(str(LIB_NAO)))
 
 
 def _p(a):
@@ -33,9 +34,29 @@ def _p(a):
 
 
 class Ref:
-    def __init__(self, lib, planner_lib=None):
+    def __init__(self, lib, planner_lib=None, nao_lib=None):
         self.lib = lib
         self.planner_lib = planner_lib
+        self.nao_lib = nao_lib
+
+    # the reference's Nao-cup scenario (oracle/ref_nao.cpp): nao_clear / nao_link of demo/nao_cup/src/naocup.hpp
+    def nao_clear(self, q, scalar=8):
+        q = np.ascontiguousarray(q, dtype=np.float32 if scalar == 4 else np.float64).reshape(-1, 10)
+        ok, col = np.empty(q.shape[0], np.uint8), np.empty(q.shape[0], np.uint8)
+        self.nao_lib.ref_nao_clear(C.c_int(scalar), _p(q), C.c_uint32(q.shape[0]), _p(ok), _p(col))
+        return ok, col
+
+    def nao_link(self, a, b, scalar=8):
+        dt = np.float32 if scalar == 4 else np.float64
+        a, b = np.ascontiguousarray(a, dtype=dt).reshape(-1, 10), np.ascontiguousarray(b, dtype=dt).reshape(-1, 10)
+        ok = np.empty(a.shape[0], np.uint8)
+        self.nao_lib.ref_nao_link(C.c_int(scalar), _p(a), _p(b), C.c_uint32(a.shape[0]), _p(ok))
+        return ok
+
+    def nao_configs(self, scalar=8):
+        out = [np.zeros(10) for _ in range(4)]
+        self.nao_lib.ref_nao_configs(C.c_int(scalar), *[_p(a) for a in out])
+        return tuple(out)  # init, lo, hi, target
 
     def prrt_grid(self, occ, lo, hi, start, goal, goal_radius, goal_bias, rng, uniforms, capacity=1 << 16):
         """The reference's Planner<Scenario, PRRT<single_threaded>> (oracle/ref_planner.cpp) on an occupancy grid, one
