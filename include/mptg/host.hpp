@@ -89,6 +89,11 @@ public:
               c.get(), "mptg_linkarm_create");
         return Geometry(c.get(), g);
     }
+    static Geometry naoCup(Context& c, int scalar) {
+        mptg_geom* g;
+        check(mptg_naocup_create(c.get(), scalar, &g), c.get(), "mptg_naocup_create");
+        return Geometry(c.get(), g);
+    }
     static Geometry meshPair(Context& c, int scalar, const std::vector<float>& robotTris, const std::vector<float>& envTris) {
         mptg_geom* g;
         check(mptg_mesh_pair_create(c.get(), scalar, (std::uint32_t)(robotTris.size() / 9), robotTris.data(),

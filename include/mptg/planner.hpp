@@ -64,6 +64,11 @@ template <typename... Options>
 struct PRRTStar {};
 template <typename... Options>
 struct PPRM {};
+// PPRM with the incremental roadmap spanner (src/mpt/pprm_irs.hpp:49-99): options as PPRM plus keep_dense_edges<bool>
+template <typename... Options>
+struct PPRMIRS {};
+template <bool keep>
+struct keep_dense_edges : std::bool_constant<keep> {};  // planner_tags.hpp (tag of PPRMIRS, src/mpt/pprm_irs.hpp:58)
 
 namespace impl {
 
@@ -694,8 +699,11 @@ public:
 };
 
 // ------------------------------------------------------------------ PPRM (impl/pprm/pprm.hpp:65-389)
-template <typename Scenario, int waveSize, bool reportStats>
-class WavePPRM : public WavePlannerBase<WavePPRM<Scenario, waveSize, reportStats>, Scenario> {
+// irs = true: PPRM-IRS (impl/pprm_irs/pprm_irs.hpp:350-407) -- a validated edge (sample, neighbour) enters the roadmap as a
+// SPARSE edge only if the sparse roadmap does not already join its ends by a path shorter than stretchWeight x its length
+// (impl/pprm_irs/shortest_path_check.hpp:111-225); otherwise it is dropped, or kept as a dense edge with keepDense.
+template <typename Scenario, int waveSize, bool reportStats, bool irs = false, bool keepDense = false>
+class WavePPRM : public WavePlannerBase<WavePPRM<Scenario, waveSize, reportStats, irs, keepDense>, Scenario> {
     using Base = WavePlannerBase<WavePPRM, Scenario>;
     using typename Base::Distance;
     using typename Base::State;
@@ -704,7 +712,17 @@ class WavePPRM : public WavePlannerBase<WavePPRM<Scenario, waveSize, reportStats
         std::uint32_t to;
         Distance d;
     };
-    std::vector<std::vector<Edge>> adj_;
+    std::vector<std::vector<Edge>> adj_;    // PPRM: every edge; PPRM-IRS: the sparse edges (what solution() and visitGraph() walk)
+    std::vector<std::vector<Edge>> dense_;  // PPRM-IRS with keep_dense_edges<true>: the edges the spanner left out
+    Distance stretchWeight_{5};             // impl/pprm_irs/pprm_irs.hpp:85
+    // bounded shortest-path search from the node being added, kept between the checks of its edges (their targets grow
+    // with the neighbour distance): cost_[v] is valid where stamp_[v] == search_
+    std::vector<Distance> cost_;
+    std::vector<std::uint32_t> stamp_;
+    std::uint32_t search_ = 0;
+    using QItem = std::pair<Distance, std::uint32_t>;
+    std::priority_queue<QItem, std::vector<QItem>, std::greater<QItem>> queue_;
+    std::size_t sparseChecks_ = 0, sparseKept_ = 0, settled_ = 0;
     std::vector<std::uint32_t> comp_;  // union-find parent
     std::vector<std::uint32_t> compSize_;
     std::vector<std::uint8_t> compFlags_;
@@ -757,6 +775,13 @@ public:
         }
     }
     bool solved() const { return solved_; }
+    void setStretchWeight(Distance w) { stretchWeight_ = w; }  // impl/pprm_irs/pprm_irs.hpp:164-166
+    std::size_t sparseEdgeChecks() const { return sparseChecks_; }
+    std::size_t denseEdgeCount() const {
+        std::size_t c = 0;
+        for (auto& a : dense_) c += a.size();
+        return c / 2;
+    }
 
     // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246)
     std::vector<State> solution() const {
@@ -805,6 +830,12 @@ public:
         std::size_t c = 0;
         for (auto& a : adj_) c += a.size();
         return c / 2;
+    }
+    // PPRM-IRS with keep_dense_edges<true>: the edges the spanner left out, each from both of its ends
+    template <typename Fn>
+    void visitDenseEdges(Fn fn) const {
+        for (std::uint32_t n = 0; n < dense_.size(); ++n)
+            for (const Edge& e : dense_[n]) fn(this->states_[n], this->states_[e.to]);
     }
 
 private:
@@ -861,14 +892,68 @@ private:
             if (fl & kStart) startNodes_.push_back(id);
             if ((fl & (kStart | kGoal)) == (kStart | kGoal)) solved_ = true;
         }
+        if constexpr (irs) dense_.resize(adj_.size());
+        std::uint32_t searchFrom = 0xFFFFFFFFu;
         for (std::size_t e = 0; e < pairs.size(); ++e)
             if (eok[e]) {
                 const std::uint32_t id = first + pairs[e].first, nb = pairs[e].second;
-                adj_[id].push_back({nb, pd[e]});
-                adj_[nb].push_back({id, pd[e]});
+                if constexpr (irs) {  // addEdge, impl/pprm_irs/pprm_irs.hpp:350-368; edges of a sample arrive nearest first (:340-342)
+                    if (searchFrom != id) beginSearch(searchFrom = id);
+                    if (needsSparseEdge(id, nb, stretchWeight_ * pd[e], pd[e])) {
+                        adj_[id].push_back({nb, pd[e]});
+                        adj_[nb].push_back({id, pd[e]});
+                    } else if constexpr (keepDense) {
+                        dense_[id].push_back({nb, pd[e]});
+                        dense_[nb].push_back({id, pd[e]});
+                    } else {
+                        continue;
+                    }
+                } else {
+                    adj_[id].push_back({nb, pd[e]});
+                    adj_[nb].push_back({id, pd[e]});
+                }
                 merge(id, nb);  // :327-334
             }
         this->addNodes(fresh);  // :337
+    }
+
+    // ShortestPathCheck::reset (impl/pprm_irs/shortest_path_check.hpp:82-96)
+    void beginSearch(std::uint32_t from) {
+        cost_.resize(adj_.size());
+        stamp_.resize(adj_.size(), 0);
+        if (++search_ == 0) std::fill(stamp_.begin(), stamp_.end(), 0), search_ = 1;
+        queue_ = {};
+        cost_[from] = 0, stamp_[from] = search_;
+        queue_.push({Distance(0), from});
+    }
+    // ShortestPathCheck::operator() (:119-225): true when no path of sparse edges from `from` to `v` is shorter than
+    // `target`, i.e. the spanner needs the edge; the search is Dijkstra's, resumed where the previous check of the same
+    // node stopped (its bound only grows), and a kept edge becomes part of it at once (:219-222).
+    bool needsSparseEdge(std::uint32_t from, std::uint32_t v, Distance target, Distance edgeLength) {
+        ++sparseChecks_;
+        if (stamp_[v] == search_ && cost_[v] < target) return false;  // :133-140
+        while (!queue_.empty()) {
+            const auto [priority, top] = queue_.top();
+            const Distance pathCost = cost_[top];
+            if (pathCost >= target) break;  // :159-160
+            queue_.pop();
+            if (pathCost != priority) continue;  // a stale entry: the node was settled through a shorter path (:166-171)
+            ++settled_;
+            bool found = top == v;
+            for (const Edge& edge : adj_[top]) {
+                const Distance d = pathCost + edge.d;
+                if (edge.to == v && d < target) found = true;
+                if (stamp_[edge.to] == search_ && !(d < cost_[edge.to])) continue;
+                cost_[edge.to] = d, stamp_[edge.to] = search_;
+                queue_.push({d, edge.to});
+            }
+            if (found) return false;  // :208-209
+        }
+        (void)from;
+        cost_[v] = edgeLength, stamp_[v] = search_;  // the new sparse edge, for the checks that follow (:219-222)
+        queue_.push({edgeLength, v});
+        ++sparseKept_;
+        return true;
     }
 };
 
@@ -1404,6 +1489,12 @@ struct PlannerResolver<Scenario, PPRM<Options...>> {
                                     DevicePPRM<Scenario, pack_int_tag_v<wave_size, 4096, Options...>, pack_int_tag_v<max_nodes, 1 << 20, Options...>,
                                                pack_bool_tag_v<report_stats, false, Options...>>,
                                     WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>>>;
+};
+
+template <typename Scenario, typename... Options>
+struct PlannerResolver<Scenario, PPRMIRS<Options...>> {  // src/mpt/pprm_irs.hpp:55-72
+    using type = WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>, true,
+                          pack_bool_tag_v<keep_dense_edges, false, Options...>>;
 };
 
 }  // namespace impl

@@ -8,6 +8,7 @@
 //   LinkManipulatorScenario    demo/link_manipulator_scenario.hpp:55-152
 //   SE3RigidBodyScenario       demo/se3_rigid_body_scenario.hpp:228-362  (meshes given as triangle soups)
 //   BasicScenario              test/planner_integration_test.hpp:128-150 (N-D sphere obstacle)
+//   NaoCupScenario             demo/nao_cup_planning.cpp:50-153 (10 joints, sphere / capsule model of demo/nao_cup/src)
 #pragma once
 
 #include <algorithm>
@@ -132,6 +133,42 @@ public:
         for (auto& k : circles_) c.push_back(k.cx), c.push_back(k.cy), c.push_back(k.r);
         return Geometry::linkArm(ctx, detail::scalarTag<Scalar>(), len, radius_, c);
     }
+};
+
+// The Nao humanoid bringing a ball over a cup (demo/nao_cup_planning.cpp:50-153): L2 over the ten arm joints, the
+// reference's joint limits, start and goal configuration (demo/nao_cup/src/naocup.hpp:254-301), goal radius 1e-5 (:82).
+// valid / link are nao_clear / nao_link of naocup.hpp on the device (mptg_naocup_create).
+template <typename Scalar>
+class NaoCupScenario {
+public:
+    static constexpr int kDimensions = 10;
+    using Space = L2Space<Scalar, kDimensions>;
+    using Bounds = BoxBounds<Scalar, kDimensions>;
+    using State = typename Space::Type;
+    using Config = State;
+    using Distance = typename Space::Distance;
+    using Goal = GoalState<Space>;
+
+private:
+    Space space_;
+    Bounds bounds_;
+    Goal goal_;
+    State start_;
+    static State config(int which) {
+        double c[4][kDimensions];
+        check(mptg_naocup_configs(detail::scalarTag<Scalar>(), c[0], c[1], c[2], c[3]), nullptr, "mptg_naocup_configs");
+        State q;
+        for (int i = 0; i < kDimensions; ++i) q[i] = (Scalar)c[which][i];
+        return q;
+    }
+
+public:
+    NaoCupScenario() : bounds_(config(2), config(3)), goal_(Scalar(1e-5), config(1)), start_(config(0)) {}
+    const Space& space() const { return space_; }
+    const Bounds& bounds() const { return bounds_; }
+    const Goal& goal() const { return goal_; }
+    const State& start() const { return start_; }  // nao_init_config (nao_cup_planning.cpp:184)
+    Geometry makeGeometry(Context& ctx) const { return Geometry::naoCup(ctx, detail::scalarTag<Scalar>()); }
 };
 
 // Triangle soups: 9 floats per triangle.  The robot soup is recentred on its vertex mean, as the

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../oracle/oracle.hpp"
+#include "../../oracle/oracle_nao.hpp"
 
 using namespace oracle;
 
@@ -33,6 +34,8 @@ struct mptg_geom {
     LinkArm<float> armF;
     LinkArm<double> armD;
     MeshPair<float> meshF;
+    NaoCup<float> naoF;
+    NaoCup<double> naoD;
 };
 
 static thread_local std::string g_err;
@@ -50,6 +53,7 @@ bool validOne<float>(mptg_geom* g, const float* q) {
         case MPTG_GEOM_GRID: return g->gridF.valid(q);
         case MPTG_GEOM_SHAPES: return g->shapesF.valid(q);
         case MPTG_GEOM_LINKARM: return g->armF.valid(q);
+        case MPTG_GEOM_NAOCUP: return g->naoF.valid(q);
         default: return g->meshF.valid(q);
     }
 }
@@ -58,6 +62,7 @@ bool validOne<double>(mptg_geom* g, const double* q) {
     switch (g->kind) {
         case MPTG_GEOM_GRID: return g->gridD.valid(q);
         case MPTG_GEOM_SHAPES: return g->shapesD.valid(q);
+        case MPTG_GEOM_NAOCUP: return g->naoD.valid(q);
         default: return g->armD.valid(q);
     }
 }
@@ -152,6 +157,28 @@ int mptg_mesh_pair_create(mptg_ctx* ctx, int scalar, uint32_t nr, const float* r
     *out = g;
     return MPTG_OK;
 }
+int mptg_naocup_create(mptg_ctx* ctx, int scalar, mptg_geom** out) {
+    auto* g = new mptg_geom();
+    g->ctx = ctx, g->kind = MPTG_GEOM_NAOCUP, g->scalar = scalar, g->D = 10;
+    *out = g;
+    return MPTG_OK;
+}
+int mptg_naocup_configs(int scalar, double* start, double* goal, double* lo, double* hi) {  // naocup.hpp:196-301
+    static const double startC[10] = {1.125998, -0.691876, 1.888312, 0.776246, 0.245398, 1.259372, 0.279146, -1.587732, -0.510780, -1.823800};
+    static const double goalC[10] = {0.258284303377494,  -0.2699099199363406, -0.01113121187052224, 1.2053012757652763,  1.2716626717484503,
+                                     -0.9826967097045605, 0.07355836822937814, 0.25450053440459897,  -0.9512909033938429, -0.5297424293532234};
+    static const double loDeg[10] = {-119.5, -94.5, -119.5, 0.5, -104.5, -119.5, 0.5, -119.5, -89.5, -104.5};
+    static const double hiDeg[10] = {119.5, -0.5, 119.5, 89.5, 104.5, 119.5, 94.5, 119.5, -0.5, 104.5};
+    for (int i = 0; i < 10; ++i) {
+        const double kd = 3.14159265358979323846 / 180.0;
+        const float kf = float(float(3.14159265358979323846) / float(180.0));
+        if (start) start[i] = scalar == MPTG_F32 ? (double)(float)startC[i] : startC[i];
+        if (goal) goal[i] = scalar == MPTG_F32 ? (double)(float)goalC[i] : goalC[i];
+        if (lo) lo[i] = scalar == MPTG_F32 ? (double)(float(loDeg[i]) * kf) : loDeg[i] * kd;
+        if (hi) hi[i] = scalar == MPTG_F32 ? (double)(float(hiDeg[i]) * kf) : hiDeg[i] * kd;
+    }
+    return MPTG_OK;
+}
 int mptg_geom_destroy(mptg_geom* g) {
     delete g;
     return MPTG_OK;
@@ -175,6 +202,7 @@ int mptg_link_batch(mptg_geom* g, const mptg_space_desc* sp, const void* from, c
                 case MPTG_GEOM_GRID: ok[i] = g->gridF.link(a, b); break;
                 case MPTG_GEOM_SHAPES: ok[i] = g->shapesF.link(a, b); break;
                 case MPTG_GEOM_LINKARM: ok[i] = g->armF.link(a, b); break;
+                case MPTG_GEOM_NAOCUP: ok[i] = g->naoF.link(a, b); break;
                 default: ok[i] = discreteMotionValid<float>(*sp, (float)step, a, b, [&](const float* q) { return g->meshF.valid(q); }); break;
             }
         } else {
@@ -183,6 +211,7 @@ int mptg_link_batch(mptg_geom* g, const mptg_space_desc* sp, const void* from, c
             switch (g->kind) {
                 case MPTG_GEOM_GRID: ok[i] = g->gridD.link(a, b); break;
                 case MPTG_GEOM_SHAPES: ok[i] = g->shapesD.link(a, b); break;
+                case MPTG_GEOM_NAOCUP: ok[i] = g->naoD.link(a, b); break;
                 default: ok[i] = g->armD.link(a, b); break;
             }
         }

@@ -73,6 +73,49 @@ void testSolvingBasicScenario(const char* name) {
                 (int)planner.solved(), secs, planner.size(), edges, solution.size());
 }
 
+// The spanner property PPRM-IRS maintains (impl/pprm_irs/pprm_irs.hpp:350-368): with keep_dense_edges every validated
+// edge is in the roadmap, sparse or dense, and for every DENSE edge (u, v) the sparse roadmap joins u and v by a path
+// shorter than stretchWeight x d(u, v) -- checked here with an independent all-pairs computation on a small roadmap.
+void testSpannerStretch() {
+    using Scenario = test::BasicScenario<double, 3>;
+    using State = Scenario::State;
+    Planner<Scenario, PPRMIRS<keep_dense_edges<true>, wave_size<32>>> planner(Scenario(), 777);
+    planner.setStretchWeight(3.0);
+    planner.addStart(Scenario::startState());
+    planner.addGoal(Scenario::goalState());
+    planner.solve([&] { return planner.size() >= 400; });
+    std::vector<State> nodes;
+    std::vector<std::pair<std::size_t, std::size_t>> sparse;
+    struct Visitor {
+        std::vector<State>& nodes;
+        std::vector<std::pair<State, State>> edges;
+        void vertex(const State& q) { nodes.push_back(q); }
+        void edge(const State& q) { edges.push_back({nodes.back(), q}); }
+    } visitor{nodes, {}};
+    planner.visitGraph(visitor);
+    auto indexOf = [&](const State& q) { return (std::size_t)(std::find(nodes.begin(), nodes.end(), q) - nodes.begin()); };
+    const std::size_t n = nodes.size();
+    Scenario sc;
+    std::vector<double> dist(n * n, std::numeric_limits<double>::infinity());
+    for (std::size_t i = 0; i < n; ++i) dist[i * n + i] = 0;
+    for (auto& e : visitor.edges) {
+        const std::size_t a = indexOf(e.first), b = indexOf(e.second);
+        dist[a * n + b] = dist[b * n + a] = sc.space().distance(e.first, e.second);
+    }
+    for (std::size_t k = 0; k < n; ++k)
+        for (std::size_t i = 0; i < n; ++i)
+            for (std::size_t j = 0; j < n; ++j) dist[i * n + j] = std::min(dist[i * n + j], dist[i * n + k] + dist[k * n + j]);
+    std::size_t denseEdges = 0, violations = 0;
+    planner.visitDenseEdges([&](const State& a, const State& b) {
+        ++denseEdges;
+        if (!(dist[indexOf(a) * n + indexOf(b)] < 3.0 * sc.space().distance(a, b) * (1 + 1e-12))) ++violations;
+    });
+    EXPECT(denseEdges > 0 && denseEdges == 2 * planner.denseEdgeCount());
+    EXPECT(violations == 0);
+    std::printf("%s PPRM-IRS spanner: %zu nodes, %zu sparse + %zu dense edges, %zu dense edges without a sparse path within the stretch\n",
+                failures ? "FAIL" : "PASS", n, visitor.edges.size() / 2, denseEdges / 2, violations);
+}
+
 void testPRRTStarInvariants() {
     // cost(node) == cost(parent) + distance(parent, node) up to rounding, after rewiring
     using Scenario = test::BasicScenario<double, 3>;
@@ -111,8 +154,51 @@ void testSE3SamplerMeasure() {
     EXPECT(std::fabs(unweighted.measure() - want / 50.0) <= 1e-12 * want);
 }
 
+// The Nao-cup scenario (demo/nao_cup_planning.cpp:50-153) through the planner classes: the start and goal configurations
+// are clear, the straight edge between them is not (about a seventh of it is), trees grow from the start with every node
+// clear and every tree edge passing the scenario's own link again.
+template <typename Algorithm>
+void testNaoCupScenario(const char* name, std::size_t nodes) {
+    using Scenario = mptg::demo::NaoCupScenario<double>;
+    Scenario scenario;
+    Planner<Scenario, Algorithm> planner(scenario, 4321);
+    planner.addStart(scenario.start());
+    planner.setRange(0.5);
+    planner.solve([&] { return planner.size() >= nodes || planner.solved(); });
+    EXPECT(planner.size() >= std::min<std::size_t>(nodes, 2));
+    mptg::Context ctx(0);
+    mptg::Geometry geom = scenario.makeGeometry(ctx);
+    std::vector<Scenario::State> from, to;
+    struct Visitor {  // the reference's graph visitor protocol: vertex(q), then edge(to) for each of its edges
+        std::vector<Scenario::State>& from;
+        std::vector<Scenario::State>& to;
+        Scenario::State current;
+        Visitor(std::vector<Scenario::State>& f, std::vector<Scenario::State>& t) : from(f), to(t) {}
+        void vertex(const Scenario::State& q) { current = q; }
+        void edge(const Scenario::State& q) { from.push_back(current), to.push_back(q); }
+    } visitor(from, to);
+    planner.visitGraph(visitor);
+    std::vector<std::uint8_t> ok(from.size() + 2), valid(to.size() + 2);
+    if (!from.empty()) {
+        geom.link(nullptr, from.data(), to.data(), (std::uint32_t)from.size(), 0.0, ok.data());
+        geom.valid(to.data(), (std::uint32_t)to.size(), valid.data());
+    }
+    std::size_t bad = 0;
+    for (std::size_t i = 0; i < from.size(); ++i) bad += !(ok[i] && valid[i]);
+    EXPECT(bad == 0);
+    const Scenario::State ends[2] = {scenario.start(), scenario.goal().state()};
+    std::uint8_t endsOk[2], direct;
+    geom.valid(ends, 2, endsOk);
+    geom.link(nullptr, &ends[0], &ends[1], 1, 0.0, &direct);
+    EXPECT(endsOk[0] && endsOk[1] && !direct);
+    std::printf("%s %s on the Nao-cup scenario: %zu nodes, %zu edges re-validated (%zu bad), solved %d\n", failures ? "FAIL" : "PASS", name,
+                planner.size(), from.size(), bad, (int)planner.solved());
+}
+
 int main() {
     testSE3SamplerMeasure();
+    testNaoCupScenario<PRRT<wave_size<64>>>("PRRT", 300);
+    testNaoCupScenario<PRRTStar<wave_size<64>>>("PRRT*", 200);
     // test/pack_nearest_test.cpp:39-69 analogue: the strategy tag is recognised, absent -> void
     static_assert(std::is_same_v<impl::pack_nearest_t<>, void>);
     static_assert(std::is_same_v<impl::pack_nearest_t<int, report_stats<true>>, void>);
@@ -130,6 +216,12 @@ int main() {
     testSolvingBasicScenario<PRRTStar<report_stats<true>>>("PRRT* k-nearest");
     testSolvingBasicScenario<PRRTStar<rewire_r_nearest>>("PRRT* r-nearest");
     testSolvingBasicScenario<PPRM<report_stats<true>>>("PPRM");
+    // the reference's PPRM-IRS integration test is the same scenario (test/pprm_irs_integration_test.cpp)
+    static_assert(std::is_same_v<Planner<S, PPRMIRS<report_stats<true>, keep_dense_edges<true>>>, Planner<S, PPRMIRS<keep_dense_edges<true>, report_stats<true>>>>);
+    static_assert(!std::is_same_v<Planner<S, PPRMIRS<>>, Planner<S, PPRMIRS<keep_dense_edges<true>>>>);
+    testSolvingBasicScenario<PPRMIRS<report_stats<true>>>("PPRM-IRS");
+    testSolvingBasicScenario<PPRMIRS<keep_dense_edges<true>, wave_size<64>>>("PPRM-IRS keep_dense_edges, wave 64");
+    testSpannerStretch();
 #ifndef MPTG_TEST_MOCK_BACKEND  // the mock backs the batched calls only; the device-resident planner needs the GPU library
     static_assert(!std::is_same_v<Planner<S, PRRT<device_resident>>, Planner<S, PRRT<>>>);
     static_assert(std::is_same_v<Planner<S, PRRT<device_resident, wave_size<4096>>>, Planner<S, PRRT<wave_size<4096>, device_resident>>>);

@@ -1,14 +1,14 @@
 // reference_planner_parity.cpp -- row a11: the wave planners of include/mptg/planner.hpp against THE
 // REFERENCE'S OWN planner classes, in one process, on the same scenario and the same random stream.
 //
-// Reference side: src/mpt/impl/{prrt,prrt_star,pprm} compiled from /root/reference (never copied) against the
+// Reference side: src/mpt/impl/{prrt,prrt_star,pprm,pprm_irs} compiled from /root/reference (never copied) against the
 // stand-in Eigen / Nigh headers under oracle/shim (exhaustive-scan Nigh with the (distance, insertion order) tie
 // rule), single_threaded, scenario = the reference's PNG2dScenario::valid / link on a synthetic occupancy grid,
 // RNG = std::mt19937_64 (the Scenario's `using RNG`, impl/scenario_rng.hpp:46-54) seeded with a plain integer.
 // Our side: Planner<Scenario, Algorithm<wave_size<1>>> over the TEST-ONLY CPU mock of the C ABI
 // (tests/cpp/mock_mptg.cpp), same seed.  With one sample per wave the wave planners must consume the generator
 // exactly like the reference's worker loop and build the SAME graph: same vertices (bit-identical states), same
-// edges, same solution path -- for PRRT, PRRT* (k-nearest and r-nearest rewiring) and PPRM.
+// edges, same solution path -- for PRRT, PRRT* (k-nearest and r-nearest rewiring), PPRM and PPRM-IRS (sparse edges).
 // TEST INFRASTRUCTURE: only buildable where /root/reference exists (tests/test_host_cpp.py skips it elsewhere).
 #include <algorithm>
 #include <array>
@@ -32,6 +32,7 @@
 #include <mpt/lp_space.hpp>
 #include <mpt/planner.hpp>
 #include <mpt/pprm.hpp>
+#include <mpt/pprm_irs.hpp>
 #include <mpt/prrt.hpp>
 #include <mpt/prrt_star.hpp>
 
@@ -148,6 +149,10 @@ struct GraphDump {
     void edge(const Q& to) { edges.push_back({vertices.back(), {to[0], to[1]}}); }
 };
 
+template <class A>
+struct is_roadmap : std::bool_constant<std::is_same_v<A, ref::PPRM<ref::single_threaded>> || std::is_same_v<A, ref::PPRMIRS<ref::single_threaded>> ||
+                                       std::is_same_v<A, ref::PPRMIRS<ref::single_threaded, ref::keep_dense_edges<true>>>> {};
+
 template <class RefAlgo, class OurAlgo>
 void compare(const char* name, const Grid& g, double goalRadius, double goalBias, double range, std::uint64_t seed, std::size_t nodes,
              bool orderedVertices, bool addGoal) {
@@ -156,13 +161,13 @@ void compare(const char* name, const Grid& g, double goalRadius, double goalBias
     const int before = failures;
     ref::Planner<RefGrid, RefAlgo> rp(RefGrid(g, goalRadius), seed);
     mptg::Planner<OurGrid, OurAlgo> op(OurGrid(g, goalRadius), seed);
-    if constexpr (!std::is_same_v<RefAlgo, ref::PPRM<ref::single_threaded>>) {
+    if constexpr (!is_roadmap<RefAlgo>::value) {
         rp.setGoalBias(goalBias), op.setGoalBias(goalBias);
         if (std::isfinite(range)) rp.setRange(range), op.setRange(range);
     }
     rp.addStart(RefState(g.start[0], g.start[1]));
     op.addStart(mptg::makeState<double, 2>({g.start[0], g.start[1]}));
-    if constexpr (std::is_same_v<RefAlgo, ref::PPRM<ref::single_threaded>>) {
+    if constexpr (is_roadmap<RefAlgo>::value) {
         if (addGoal) {
             rp.addGoal(RefState(g.goal[0], g.goal[1]));
             op.addGoal(mptg::makeState<double, 2>({g.goal[0], g.goal[1]}));
@@ -207,6 +212,10 @@ int main() {
     compare<ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest>, mptg::PRRTStar<mptg::wave_size<1>, mptg::rewire_r_nearest>>(
         "PRRT* r-nearest", g, 8.0, 0.05, 25.0, 14, 1200, true, false);
     compare<ref::PPRM<ref::single_threaded>, mptg::PPRM<mptg::wave_size<1>>>("PPRM", g, 1e-6, 0.0, inf, 15, 600, false, true);
+    // PPRM with the incremental roadmap spanner (impl/pprm_irs): the sparse edges only, and with the dense edges kept
+    compare<ref::PPRMIRS<ref::single_threaded>, mptg::PPRMIRS<mptg::wave_size<1>>>("PPRM-IRS", g, 1e-6, 0.0, inf, 16, 900, false, true);
+    compare<ref::PPRMIRS<ref::single_threaded, ref::keep_dense_edges<true>>, mptg::PPRMIRS<mptg::wave_size<1>, mptg::keep_dense_edges<true>>>(
+        "PPRM-IRS keep_dense_edges", g, 1e-6, 0.0, inf, 17, 700, false, true);
     std::printf("%d failures\n", failures);
     return failures ? 1 : 0;
 }
