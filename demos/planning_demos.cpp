@@ -34,6 +34,7 @@ struct Options {
     double timeMs = 5000;
     bool check = false;
     std::string map;
+    std::string cfg;  // se3_rigid_body: an OMPL-style problem file (demo/se3_rigid_body_planning.cpp:240-262) naming .dae / .obj meshes
     std::uint64_t seed = 2026;
     bool devicePrrt = false;  // also run Planner<Scenario, PRRT<device_resident>>: tree and sampling on the GPU
 };
@@ -280,10 +281,30 @@ void se3RigidBody(const Options& opt) {
     using Scenario = demo::SE3RigidBodyScenario<Scalar>;
     using State = Scenario::State;
     std::vector<float> env, robot;
-    tube(env, 30.0, 0.35, 125, 0.3, 4.0, 16);    // ~4k triangles
-    tube(robot, 14.0, 0.45, 50, 1.7, 2.0, 10);   // ~1k triangles
     State start = State::identityAt(-52, -50, 0), goal = State::identityAt(52, 50, 5);
-    Scenario scenario(env, robot, goal, makeState<Scalar, 3>({-60, -60, -40}), makeState<Scalar, 3>({60, 60, 40}), 0.01f);
+    mptg::State<Scalar, 3> vmin = makeState<Scalar, 3>({-60, -60, -40}), vmax = makeState<Scalar, 3>({60, 60, 40});
+    Scalar range = 40;
+    if (!opt.cfg.empty()) {  // the reference's own inputs: [problem] robot / world (COLLADA through assimp there), start, goal, volume
+        const formats::ScenarioConfig cfg(opt.cfg);
+        const std::size_t slash = opt.cfg.find_last_of("\\/");
+        const std::string dir = slash == std::string::npos ? "" : opt.cfg.substr(0, slash + 1);
+        std::string world, robotName;
+        cfg.load(world, "problem", "world");
+        cfg.load(robotName, "problem", "robot");
+        env = formats::readMeshTriangles(dir + world);
+        robot = formats::readMeshTriangles(dir + robotName);  // recentred by the scenario below (se3_rigid_body_scenario.hpp:181-193)
+        cfg.loadSE3(start.data(), "problem", "start");
+        cfg.loadSE3(goal.data(), "problem", "goal");
+        cfg.loadVector3(vmin.data(), "problem", "volume.min");
+        cfg.loadVector3(vmax.data(), "problem", "volume.max");
+        if (cfg.hasProp("planner", "rrt.range")) cfg.load(range, "planner", "rrt.range");
+        std::printf("se3_rigid_body: %s -- world %s (%zu triangles), robot %s (%zu triangles)\n", opt.cfg.c_str(), world.c_str(), env.size() / 9,
+                    robotName.c_str(), robot.size() / 9);
+    } else {
+        tube(env, 30.0, 0.35, 125, 0.3, 4.0, 16);   // ~4k triangles
+        tube(robot, 14.0, 0.45, 50, 1.7, 2.0, 10);  // ~1k triangles
+    }
+    Scenario scenario(env, robot, goal, vmin, vmax, 0.01f);
     {
         Probe<Scenario> probe(scenario);
         if (!probe.valid(start) || !probe.valid(goal)) throw std::runtime_error("se3_rigid_body: start or goal in collision");
@@ -291,18 +312,18 @@ void se3RigidBody(const Options& opt) {
     }
     Planner<Scenario, PRRTStar<report_stats<true>, wave_size<1024>>> planner(scenario, opt.seed);
     planner.addStart(start);
-    planner.setRange(40);
+    planner.setRange(range);
     auto [first, total] = runUntilSolved(planner, opt.timeMs);
     report("se3_rigid_body", "PRRT*", planner, scenario, first, total, opt);
     if (opt.devicePrrt) {
         Planner<Scenario, PRRT<device_resident, report_stats<true>, wave_size<16384>, max_nodes<(1 << 22)>>> dev(scenario, opt.seed);
         dev.addStart(start);
-        dev.setRange(40);
+        dev.setRange(range);
         auto [dFirst, dTotal] = runUntilSolved(dev, opt.timeMs);
         report("se3_rigid_body", "PRRT, device-resident", dev, scenario, dFirst, dTotal, opt);
         Planner<Scenario, PRRTStar<device_resident, report_stats<true>, wave_size<8192>, max_nodes<(1 << 21)>>> star(scenario, opt.seed);
         star.addStart(start);
-        star.setRange(40);
+        star.setRange(range);
         auto [sFirst, sTotal] = runUntilSolved(star, opt.timeMs);
         report("se3_rigid_body", "PRRT*, device-resident", star, scenario, sFirst, sTotal, opt);
     }
@@ -405,9 +426,10 @@ int main(int argc, char** argv) {
         else if (a == "--device-prrt") opt.devicePrrt = true;
         else if (a == "--nodes" && i + 1 < argc) opt.nodes = g_targetNodes = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "--map" && i + 1 < argc) opt.map = argv[++i];
+        else if (a == "--cfg" && i + 1 < argc) opt.cfg = argv[++i];
         else if (a == "--seed" && i + 1 < argc) opt.seed = std::strtoull(argv[++i], nullptr, 10);
         else {
-            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator|nao_cup|nao_cup_float] [--time-ms T] [--nodes N] [--check] [--device-prrt (also run the device-resident PRRT / PPRM)] [--map file.png|file.pgm] [--seed S]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s [--all | --demo holonomic_2d_point|png_2d|se3_rigid_body|link_manipulator|nao_cup|nao_cup_float] [--time-ms T] [--nodes N] [--check] [--device-prrt (also run the device-resident PRRT / PPRM)] [--map file.png|file.pgm] [--cfg problem.cfg (se3_rigid_body: .dae / .obj meshes, start, goal, volume)] [--seed S]\n", argv[0]);
             return 2;
         }
     }

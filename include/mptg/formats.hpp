@@ -4,6 +4,10 @@
 //   ScenarioConfig                  OMPL-style .cfg files: [section] / key = value (demo/scenario_config.hpp:47-160)
 //   readObjTriangles                triangle soups for the rigid-body scenario (the reference loads meshes through
 //                                   assimp and fan-triangulates faces, demo/se3_rigid_body_scenario.hpp:164-204)
+//   readColladaTriangles            the same from COLLADA (.dae) -- the format of the reference's SE(3) inputs
+//                                   (OMPL's resources, named by the .cfg files): geometry library + scene graph with
+//                                   node transforms, visited as demo/se3_rigid_body_scenario.hpp:73-133 does
+//   readMeshTriangles               .obj / .dae by extension; recentre on the vertex mean as :181-193 does for the robot
 // libpng and assimp are not on this machine; the decoders below are written from the format specifications
 // (PNG: RFC 2083 -- chunk layout, zlib stream over IDAT, the five scan-line filters incl. Paeth; Wavefront OBJ: v / f
 // records).  The transformations libpng applies in the reference are reproduced: palette -> RGB, 16 -> 8 bits (high
@@ -21,6 +25,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -271,6 +276,376 @@ inline std::vector<float> readObjTriangles(const std::string& path) {
         }
     }
     return tris;
+}
+
+// ---------------------------------------------------------------------------------- COLLADA subset
+namespace xml {
+struct Node {
+    std::string tag, text;
+    std::map<std::string, std::string> attr;
+    std::vector<Node> children;
+    const Node* child(const std::string& t) const {
+        for (const Node& c : children)
+            if (c.tag == t) return &c;
+        return nullptr;
+    }
+    std::string get(const std::string& k) const {
+        auto it = attr.find(k);
+        return it == attr.end() ? std::string() : it->second;
+    }
+};
+// elements, attributes and character data; comments, processing instructions, DOCTYPE and CDATA markers are skipped,
+// the five predefined entities are not expanded (none occurs in the numeric content read here)
+inline Node parse(const std::string& src, const std::string& what) {
+    Node root;
+    std::vector<Node*> stack{&root};
+    std::size_t i = 0;
+    const std::size_t n = src.size();
+    auto fail = [&](const char* msg) { return std::invalid_argument(what + ": malformed XML (" + msg + ")"); };
+    while (i < n) {
+        if (src[i] != '<') {
+            const std::size_t j = src.find('<', i);
+            stack.back()->text.append(src, i, (j == std::string::npos ? n : j) - i);
+            i = j == std::string::npos ? n : j;
+            continue;
+        }
+        if (src.compare(i, 4, "<!--") == 0) {
+            const std::size_t j = src.find("-->", i + 4);
+            if (j == std::string::npos) throw fail("unterminated comment");
+            i = j + 3;
+        } else if (src.compare(i, 2, "<?") == 0 || src.compare(i, 2, "<!") == 0) {
+            const std::size_t j = src.find('>', i);
+            if (j == std::string::npos) throw fail("unterminated declaration");
+            i = j + 1;
+        } else if (src.compare(i, 2, "</") == 0) {
+            const std::size_t j = src.find('>', i);
+            if (j == std::string::npos || stack.size() < 2) throw fail("unbalanced end tag");
+            stack.pop_back();
+            i = j + 1;
+        } else {
+            std::size_t j = i + 1;
+            while (j < n && !std::isspace((unsigned char)src[j]) && src[j] != '>' && src[j] != '/') ++j;
+            Node el;
+            el.tag = src.substr(i + 1, j - i - 1);
+            bool selfClosed = false;
+            while (j < n && src[j] != '>') {
+                if (src[j] == '/') {
+                    selfClosed = true;
+                    ++j;
+                    continue;
+                }
+                if (std::isspace((unsigned char)src[j])) {
+                    ++j;
+                    continue;
+                }
+                const std::size_t eq = src.find('=', j);
+                if (eq == std::string::npos) throw fail("attribute without value");
+                std::string key = src.substr(j, eq - j);
+                while (!key.empty() && std::isspace((unsigned char)key.back())) key.pop_back();
+                std::size_t q = eq + 1;
+                while (q < n && std::isspace((unsigned char)src[q])) ++q;
+                if (q >= n || (src[q] != '"' && src[q] != '\'')) throw fail("unquoted attribute");
+                const std::size_t end = src.find(src[q], q + 1);
+                if (end == std::string::npos) throw fail("unterminated attribute");
+                el.attr[key] = src.substr(q + 1, end - q - 1);
+                j = end + 1;
+            }
+            if (j >= n) throw fail("unterminated tag");
+            i = j + 1;
+            stack.back()->children.push_back(std::move(el));
+            if (!selfClosed) stack.push_back(&stack.back()->children.back());
+        }
+    }
+    if (stack.size() != 1) throw fail("unclosed element");
+    return root;
+}
+template <typename T>
+std::vector<T> numbers(const std::string& text) {
+    std::vector<T> out;
+    const char* p = text.c_str();
+    char* end;
+    for (;;) {
+        const double v = std::strtod(p, &end);
+        if (end == p) break;
+        out.push_back((T)v);
+        p = end;
+    }
+    return out;
+}
+}  // namespace xml
+
+namespace detail {
+struct Mat4 {  // row-major affine transform
+    double m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    Mat4 operator*(const Mat4& o) const {
+        Mat4 r;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                double a = 0;
+                for (int k = 0; k < 4; ++k) a += m[i * 4 + k] * o.m[k * 4 + j];
+                r.m[i * 4 + j] = a;
+            }
+        return r;
+    }
+    std::array<double, 3> apply(const double* v) const {
+        return {m[0] * v[0] + m[1] * v[1] + m[2] * v[2] + m[3], m[4] * v[0] + m[5] * v[1] + m[6] * v[2] + m[7],
+                m[8] * v[0] + m[9] * v[1] + m[10] * v[2] + m[11]};
+    }
+};
+struct DaeGeometry {
+    std::vector<double> positions;           // xyz
+    std::vector<std::vector<std::size_t>> faces;  // position indices per polygon
+};
+}  // namespace detail
+
+// COLLADA 1.4 / 1.5 subset, enough for rigid meshes: <library_geometries> (<mesh> with <source>/<float_array>,
+// <vertices> POSITION input, <triangles> / <polylist> / <polygons> / <trifans> / <tristrips> primitives with interleaved <p>
+// indices), <library_visual_scenes> (<node> trees with <matrix>, <translate>, <rotate>, <scale> in document order,
+// <instance_geometry>, <instance_node> into <library_nodes>) and <asset><up_axis> (X_UP / Z_UP are turned to Y up at the
+// root as assimp's importer does; <unit> is not applied, as in assimp).  Every instanced geometry is visited with the
+// product of the transforms from the root down (demo/se3_rigid_body_scenario.hpp:96-133) and its polygons are fanned
+// out round corner 0 (:118-125).  Files without a scene instance every geometry once, untransformed.
+// shiftToCentre: subtract the mean of the visited vertices (:181-193; the reference's mean runs over assimp's joined
+// vertex list, here over the positions each instanced geometry references -- the same set of points unless a position
+// is shared by corners that differ in normal or texture coordinate, which assimp then counts more than once).
+inline std::vector<float> readColladaTriangles(const std::string& path, bool shiftToCentre = false) {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw std::system_error(errno, std::system_category(), "failed to open '" + path + "'");
+    std::stringstream buf;
+    buf << in.rdbuf();
+    const xml::Node doc = xml::parse(buf.str(), path);
+    const xml::Node* collada = doc.child("COLLADA");
+    if (!collada) throw std::invalid_argument(path + ": not a COLLADA document");
+    auto strip = [](std::string ref) { return !ref.empty() && ref[0] == '#' ? ref.substr(1) : ref; };
+
+    std::map<std::string, detail::DaeGeometry> geometries;
+    std::vector<std::string> geometryOrder;
+    if (const xml::Node* lib = collada->child("library_geometries"))
+        for (const xml::Node& g : lib->children) {
+            if (g.tag != "geometry") continue;
+            const xml::Node* mesh = g.child("mesh");
+            if (!mesh) continue;  // splines, convex meshes: not triangle data
+            std::map<std::string, const xml::Node*> sources;
+            for (const xml::Node& c : mesh->children)
+                if (c.tag == "source") sources[c.get("id")] = &c;
+            std::string positionSource, verticesId;
+            if (const xml::Node* v = mesh->child("vertices")) {
+                verticesId = v->get("id");
+                for (const xml::Node& inp : v->children)
+                    if (inp.tag == "input" && inp.get("semantic") == "POSITION") positionSource = strip(inp.get("source"));
+            }
+            auto src = sources.find(positionSource);
+            if (src == sources.end()) throw std::invalid_argument(path + ": geometry '" + g.get("id") + "' has no POSITION source");
+            const xml::Node* fa = src->second->child("float_array");
+            if (!fa) throw std::invalid_argument(path + ": POSITION source without <float_array>");
+            detail::DaeGeometry geo;
+            std::size_t stride = 3;
+            if (const xml::Node* tc = src->second->child("technique_common"))
+                if (const xml::Node* acc = tc->child("accessor"))
+                    if (!acc->get("stride").empty()) stride = (std::size_t)std::strtoul(acc->get("stride").c_str(), nullptr, 10);
+            const std::vector<double> raw = xml::numbers<double>(fa->text);
+            if (stride < 3) throw std::invalid_argument(path + ": POSITION stride below 3");
+            for (std::size_t i = 0; i + 3 <= raw.size(); i += stride) geo.positions.insert(geo.positions.end(), raw.begin() + i, raw.begin() + i + 3);
+            for (const xml::Node& prim : mesh->children) {
+                const bool tri = prim.tag == "triangles", plist = prim.tag == "polylist", polys = prim.tag == "polygons";
+                const bool fans = prim.tag == "trifans", strips = prim.tag == "tristrips";
+                if (!(tri || plist || polys || fans || strips)) continue;
+                std::size_t inputs = 0, vOffset = 0;
+                bool haveVertex = false;
+                for (const xml::Node& inp : prim.children)
+                    if (inp.tag == "input") {
+                        const std::size_t off = (std::size_t)std::strtoul(inp.get("offset").c_str(), nullptr, 10);
+                        inputs = std::max(inputs, off + 1);
+                        if (inp.get("semantic") == "VERTEX" && strip(inp.get("source")) == verticesId) vOffset = off, haveVertex = true;
+                    }
+                if (!haveVertex) throw std::invalid_argument(path + ": primitive without a VERTEX input");
+                auto corners = [&](const std::string& text) {
+                    const std::vector<long> all = xml::numbers<long>(text);
+                    std::vector<std::size_t> out;
+                    for (std::size_t i = vOffset; i < all.size(); i += inputs) {
+                        if (all[i] < 0 || (std::size_t)all[i] * 3 + 2 >= geo.positions.size()) throw std::invalid_argument(path + ": vertex index out of range");
+                        out.push_back((std::size_t)all[i]);
+                    }
+                    return out;
+                };
+                if (tri || plist) {
+                    const xml::Node* p = prim.child("p");
+                    if (!p) continue;
+                    const std::vector<std::size_t> idx = corners(p->text);
+                    std::vector<long> vcount;
+                    if (plist) {
+                        const xml::Node* vc = prim.child("vcount");
+                        if (!vc) throw std::invalid_argument(path + ": <polylist> without <vcount>");
+                        vcount = xml::numbers<long>(vc->text);
+                    } else {
+                        vcount.assign(idx.size() / 3, 3);
+                    }
+                    std::size_t at = 0;
+                    for (long c : vcount) {
+                        if (c < 0 || at + (std::size_t)c > idx.size()) throw std::invalid_argument(path + ": <vcount> exceeds <p>");
+                        geo.faces.emplace_back(idx.begin() + at, idx.begin() + at + c);
+                        at += (std::size_t)c;
+                    }
+                } else {
+                    for (const xml::Node& p : prim.children) {
+                        if (p.tag != "p") continue;
+                        const std::vector<std::size_t> idx = corners(p.text);
+                        if (polys || fans) {
+                            geo.faces.push_back(idx);  // a fan IS the triangulation used below
+                        } else {
+                            for (std::size_t i = 0; i + 2 < idx.size(); ++i)
+                                geo.faces.push_back(i % 2 == 0 ? std::vector<std::size_t>{idx[i], idx[i + 1], idx[i + 2]}
+                                                               : std::vector<std::size_t>{idx[i + 1], idx[i], idx[i + 2]});
+                        }
+                    }
+                }
+            }
+            geometryOrder.push_back(g.get("id"));
+            geometries[g.get("id")] = std::move(geo);
+        }
+    if (geometries.empty()) throw std::invalid_argument("mesh file '" + path + "' does not contain meshes");  // :175-176
+
+    // instances: (geometry, accumulated transform)
+    std::vector<std::pair<const detail::DaeGeometry*, detail::Mat4>> instances;
+    std::map<std::string, const xml::Node*> libraryNodes;
+    std::function<void(const xml::Node&)> indexNodes = [&](const xml::Node& nd) {
+        for (const xml::Node& c : nd.children)
+            if (c.tag == "node") {
+                if (!c.get("id").empty()) libraryNodes[c.get("id")] = &c;
+                indexNodes(c);
+            }
+    };
+    if (const xml::Node* lib = collada->child("library_nodes")) indexNodes(*lib);
+    const double pi = 3.14159265358979323846;
+    std::function<void(const xml::Node&, detail::Mat4, int)> visit = [&](const xml::Node& nd, detail::Mat4 xf, int depth) {
+        if (depth > 64) throw std::invalid_argument(path + ": node hierarchy too deep (cycle through <instance_node>?)");
+        for (const xml::Node& c : nd.children) {
+            if (c.tag == "matrix") {
+                const std::vector<double> v = xml::numbers<double>(c.text);
+                if (v.size() != 16) throw std::invalid_argument(path + ": <matrix> needs 16 numbers");
+                detail::Mat4 m;
+                std::copy(v.begin(), v.end(), m.m);
+                xf = xf * m;
+            } else if (c.tag == "translate") {
+                const std::vector<double> v = xml::numbers<double>(c.text);
+                if (v.size() != 3) throw std::invalid_argument(path + ": <translate> needs 3 numbers");
+                detail::Mat4 m;
+                m.m[3] = v[0], m.m[7] = v[1], m.m[11] = v[2];
+                xf = xf * m;
+            } else if (c.tag == "scale") {
+                const std::vector<double> v = xml::numbers<double>(c.text);
+                if (v.size() != 3) throw std::invalid_argument(path + ": <scale> needs 3 numbers");
+                detail::Mat4 m;
+                m.m[0] = v[0], m.m[5] = v[1], m.m[10] = v[2];
+                xf = xf * m;
+            } else if (c.tag == "rotate") {
+                const std::vector<double> v = xml::numbers<double>(c.text);
+                if (v.size() != 4) throw std::invalid_argument(path + ": <rotate> needs axis and angle");
+                const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+                if (len > 0) {
+                    const double x = v[0] / len, y = v[1] / len, z = v[2] / len, a = v[3] * pi / 180.0, cs = std::cos(a), sn = std::sin(a), t = 1 - cs;
+                    detail::Mat4 m;
+                    m.m[0] = t * x * x + cs, m.m[1] = t * x * y - sn * z, m.m[2] = t * x * z + sn * y;
+                    m.m[4] = t * x * y + sn * z, m.m[5] = t * y * y + cs, m.m[6] = t * y * z - sn * x;
+                    m.m[8] = t * x * z - sn * y, m.m[9] = t * y * z + sn * x, m.m[10] = t * z * z + cs;
+                    xf = xf * m;
+                }
+            }
+        }
+        for (const xml::Node& c : nd.children) {
+            if (c.tag == "instance_geometry") {
+                auto it = geometries.find(strip(c.get("url")));
+                if (it == geometries.end()) throw std::invalid_argument(path + ": <instance_geometry> of unknown geometry " + c.get("url"));
+                instances.push_back({&it->second, xf});
+            } else if (c.tag == "instance_node") {
+                auto it = libraryNodes.find(strip(c.get("url")));
+                if (it == libraryNodes.end()) throw std::invalid_argument(path + ": <instance_node> of unknown node " + c.get("url"));
+                visit(*it->second, xf, depth + 1);
+            } else if (c.tag == "node") {
+                visit(c, xf, depth + 1);
+            }
+        }
+    };
+    detail::Mat4 root;
+    if (const xml::Node* asset = collada->child("asset"))
+        if (const xml::Node* up = asset->child("up_axis")) {
+            std::string axis = up->text;
+            axis.erase(std::remove_if(axis.begin(), axis.end(), [](unsigned char ch) { return std::isspace(ch); }), axis.end());
+            if (axis == "Z_UP") {  // (x, y, z) -> (x, z, -y)
+                const double m[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 1};
+                std::copy(m, m + 16, root.m);
+            } else if (axis == "X_UP") {  // (x, y, z) -> (-y, x, z)
+                const double m[16] = {0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+                std::copy(m, m + 16, root.m);
+            }
+        }
+    const xml::Node* sceneNode = nullptr;
+    if (const xml::Node* lib = collada->child("library_visual_scenes")) {
+        std::string want;
+        if (const xml::Node* sc = collada->child("scene"))
+            if (const xml::Node* ivs = sc->child("instance_visual_scene")) want = strip(ivs->get("url"));
+        for (const xml::Node& vs : lib->children)
+            if (vs.tag == "visual_scene" && (!sceneNode || vs.get("id") == want)) sceneNode = &vs;
+    }
+    if (sceneNode) visit(*sceneNode, root, 0);
+    if (instances.empty())
+        for (const std::string& id : geometryOrder) instances.push_back({&geometries[id], root});
+
+    std::array<double, 3> centre{0, 0, 0};
+    if (shiftToCentre) {
+        std::size_t count = 0;
+        for (auto& [geo, xf] : instances) {
+            std::vector<std::uint8_t> used(geo->positions.size() / 3, 0);
+            for (auto& f : geo->faces)
+                for (std::size_t c : f) used[c] = 1;
+            for (std::size_t v = 0; v < used.size(); ++v)
+                if (used[v]) {
+                    const auto p = xf.apply(&geo->positions[3 * v]);
+                    for (int k = 0; k < 3; ++k) centre[k] += p[k];
+                    ++count;
+                }
+        }
+        if (count)
+            for (double& c : centre) c /= (double)count;
+    }
+    std::vector<float> tris;
+    for (auto& [geo, xf] : instances)
+        for (auto& f : geo->faces) {
+            if (f.size() < 3) continue;  // :109-110
+            for (std::size_t i = 1; i + 1 < f.size(); ++i)
+                for (std::size_t c : {f[0], f[i], f[i + 1]}) {
+                    const auto p = xf.apply(&geo->positions[3 * c]);
+                    for (int k = 0; k < 3; ++k) tris.push_back((float)(p[k] - centre[k]));
+                }
+        }
+    return tris;
+}
+
+// recentre a triangle soup on the mean of its corners' distinct positions (for OBJ input; the COLLADA reader does it itself)
+inline void recentreTriangles(std::vector<float>& tris) {
+    std::vector<std::array<float, 3>> pts;
+    for (std::size_t i = 0; i + 3 <= tris.size(); i += 3) pts.push_back({tris[i], tris[i + 1], tris[i + 2]});
+    std::sort(pts.begin(), pts.end());
+    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+    double c[3] = {0, 0, 0};
+    for (auto& p : pts)
+        for (int k = 0; k < 3; ++k) c[k] += p[k];
+    if (!pts.empty())
+        for (double& v : c) v /= (double)pts.size();
+    for (std::size_t i = 0; i < tris.size(); ++i) tris[i] = (float)(tris[i] - c[i % 3]);
+}
+
+// the mesh file a .cfg names (robot / world): COLLADA or OBJ by extension
+inline std::vector<float> readMeshTriangles(const std::string& path, bool shiftToCentre = false) {
+    std::string ext = path.size() >= 4 ? path.substr(path.size() - 4) : std::string();
+    std::transform(ext.begin(), ext.end(), ext.begin(), [](unsigned char ch) { return (char)std::tolower(ch); });
+    if (ext == ".dae") return readColladaTriangles(path, shiftToCentre);
+    if (ext == ".obj") {
+        std::vector<float> tris = readObjTriangles(path);
+        if (shiftToCentre) recentreTriangles(tris);
+        return tris;
+    }
+    throw std::invalid_argument("mesh file '" + path + "': only .dae and .obj are read here (the reference goes through assimp)");
 }
 
 }  // namespace mptg::formats

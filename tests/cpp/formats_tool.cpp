@@ -3,6 +3,7 @@
 //   formats_tool occ FILE OUT      OUT: int32 width, int32 height, then width*height bytes (1 = obstacle) with the colour
 //                                  filters of demo/png_2d_planning.cpp:69-72
 //   formats_tool obj FILE OUT      OUT: float32 triangles, nine per triangle
+//   formats_tool dae FILE OUT [centre]   the same from a COLLADA file (optionally recentred on the vertex mean)
 //   formats_tool cfg FILE          prints the SE(3) start / goal states, the volume and the mesh names of an OMPL .cfg
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,12 @@ int main(int argc, char** argv) {
             }
         } else if (cmd == "obj") {
             const auto tris = readObjTriangles(file);
+            std::ofstream out(argv[3], std::ios::binary);
+            out.write((const char*)tris.data(), (std::streamsize)(tris.size() * sizeof(float)));
+            std::printf("%zu triangles\n", tris.size() / 9);
+        } else if (cmd == "dae" || cmd == "mesh") {
+            const bool centre = argc > 4 && std::string(argv[4]) == "centre";
+            const auto tris = cmd == "dae" ? readColladaTriangles(file, centre) : readMeshTriangles(file, centre);
             std::ofstream out(argv[3], std::ios::binary);
             out.write((const char*)tris.data(), (std::streamsize)(tris.size() * sizeof(float)));
             std::printf("%zu triangles\n", tris.size() / 9);

@@ -149,3 +149,91 @@ this line is not a property
     tris = np.frombuffer((tmp_path / "tris.raw").read_bytes(), dtype=np.float32).reshape(4, 3, 3)
     v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 2]], dtype=np.float32)
     assert np.array_equal(tris, v[[[0, 1, 2], [0, 2, 3], [0, 1, 4], [4, 3, 2]]])  # fan triangulation, relative indices
+
+
+DAE = """<?xml version="1.0" encoding="utf-8"?>
+<!-- a cube face (polylist quad), a triangle list with interleaved normal indices, two instances -->
+<COLLADA xmlns="http://www.collada.org/2005/11/COLLADASchema" version="1.4.1">
+  <asset><unit name="centimeter" meter="0.01"/><up_axis>{up}</up_axis></asset>
+  <library_geometries>
+    <geometry id="quad-mesh" name="quad">
+      <mesh>
+        <source id="quad-pos">
+          <float_array id="quad-pos-array" count="15">0 0 0  1 0 0  1 1 0  0 1 0  0.5 0.5 2</float_array>
+          <technique_common><accessor source="#quad-pos-array" count="5" stride="3"/></technique_common>
+        </source>
+        <source id="quad-nrm"><float_array id="quad-nrm-array" count="3">0 0 1</float_array></source>
+        <vertices id="quad-vtx"><input semantic="POSITION" source="#quad-pos"/></vertices>
+        <polylist count="2">
+          <input semantic="VERTEX" source="#quad-vtx" offset="0"/>
+          <input semantic="NORMAL" source="#quad-nrm" offset="1"/>
+          <vcount>4 3</vcount>
+          <p>0 0 1 0 2 0 3 0   0 0 1 0 4 0</p>
+        </polylist>
+        <triangles count="1">
+          <input semantic="NORMAL" source="#quad-nrm" offset="0"/>
+          <input semantic="VERTEX" source="#quad-vtx" offset="1"/>
+          <p>0 2 0 3 0 4</p>
+        </triangles>
+      </mesh>
+    </geometry>
+  </library_geometries>
+  <library_nodes>
+    <node id="shared"><translate>0 0 10</translate><instance_geometry url="#quad-mesh"/></node>
+  </library_nodes>
+  <library_visual_scenes>
+    <visual_scene id="Scene">
+      <node id="a">
+        <matrix>2 0 0 1  0 2 0 2  0 0 2 3  0 0 0 1</matrix>
+        <instance_geometry url="#quad-mesh"/>
+        <node id="b">
+          <rotate>0 0 1 90</rotate>
+          <scale>1 1 0.5</scale>
+          <instance_node url="#shared"/>
+        </node>
+      </node>
+    </visual_scene>
+  </library_visual_scenes>
+  <scene><instance_visual_scene url="#Scene"/></scene>
+</COLLADA>
+"""
+
+
+def test_collada_reader(tool, tmp_path):
+    """COLLADA subset of include/mptg/formats.hpp (the reference reads .dae through assimp,
+    demo/se3_rigid_body_scenario.hpp:164-204): polylist / triangles with interleaved inputs, fan triangulation, node
+    transforms composed from the root down, <instance_node>, up-axis conversion, recentring on the vertex mean."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 2]], dtype=np.float64)
+    faces = [[0, 1, 2], [0, 2, 3], [0, 1, 4], [2, 3, 4]]  # quad fanned round corner 0, the polylist triangle, the <triangles> one
+    A = np.array([[2, 0, 0, 1], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]], dtype=np.float64)
+    Rz = np.array([[0, -1, 0, 0], [1, 0, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=np.float64)
+    S = np.diag([1, 1, 0.5, 1.0])
+    T = np.eye(4)
+    T[2, 3] = 10
+    ups = {"Y_UP": np.eye(4), "Z_UP": np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1.0]])}
+    for up, U in ups.items():
+        dae = tmp_path / f"scene_{up}.dae"
+        dae.write_text(DAE.format(up=up))
+        want = []
+        for M in (U @ A, U @ A @ Rz @ S @ T):
+            p = (M[:3, :3] @ v.T).T + M[:3, 3]
+            want.append(p[faces])
+        want = np.concatenate(want)
+        r = subprocess.run([str(tool), "dae", str(dae), str(tmp_path / "t.raw")], check=True, capture_output=True, text=True)
+        assert r.stdout.strip() == "8 triangles"
+        got = np.frombuffer((tmp_path / "t.raw").read_bytes(), dtype=np.float32).reshape(-1, 3, 3)
+        assert np.allclose(got, want, rtol=0, atol=1e-5), up
+        # recentred (the robot mesh of the reference, :181-193): mean of the 5 + 5 instanced vertices
+        subprocess.run([str(tool), "mesh", str(dae), str(tmp_path / "c.raw"), "centre"], check=True, capture_output=True)
+        gotc = np.frombuffer((tmp_path / "c.raw").read_bytes(), dtype=np.float32).reshape(-1, 3, 3)
+        pts = np.concatenate([(M[:3, :3] @ v.T).T + M[:3, 3] for M in (U @ A, U @ A @ Rz @ S @ T)])
+        assert np.allclose(gotc, want - pts.mean(axis=0), rtol=0, atol=1e-5)
+    # errors: not COLLADA, no geometry, dangling reference
+    bad = tmp_path / "bad.dae"
+    bad.write_text("<html><body/></html>")
+    assert subprocess.run([str(tool), "dae", str(bad), str(tmp_path / "x.raw")], capture_output=True).returncode == 1
+    bad.write_text('<COLLADA><library_geometries/></COLLADA>')
+    r = subprocess.run([str(tool), "dae", str(bad), str(tmp_path / "x.raw")], capture_output=True, text=True)
+    assert r.returncode == 1 and "does not contain meshes" in r.stderr
+    bad.write_text(DAE.format(up="Y_UP").replace('url="#quad-mesh"/>\n        <node', 'url="#nothing"/>\n        <node'))
+    assert subprocess.run([str(tool), "dae", str(bad), str(tmp_path / "x.raw")], capture_output=True).returncode == 1
