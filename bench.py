@@ -433,6 +433,8 @@ def run_ours(args):
 def secondary(ctx, torch, dev, stream):
     """The other back-ends of the path (C1, C2, C4), device-resident inputs, rank 0 only,
     outside the main timed region.  Reported for coverage; `value` stays the C5 kNN figure."""
+    import time
+
     import mpt_b200 as m
     from mpt_b200 import workloads as W
 
@@ -466,6 +468,39 @@ def secondary(ctx, torch, dev, stream):
         arm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
         a, b = W.arm_edges(E_WAVE, n_links, 41, 0.5)
         out[f"link_arm_{n_links}_edges"] = time_link(arm, a, b)
+    # the fifth scenario of the reference: Nao with cup and ball, 10 joints; edges between CLEAR
+    # configurations a few tenths of a radian apart (what a planner with a range links), one flat list of midpoints
+    issue_nao = _profile_json("r2_nao_issue.json")
+    for scalar, tag, dt in ((m.F32, "f32", np.float32), (m.F64, "f64", np.float64)):
+        nao = m.Scenario.nao_cup(ctx, scalar)
+        pool = W.nao_states(1 << 20, 3, dtype=dt)
+        pool = pool[nao.valid(pool) == 1]
+        rng = np.random.default_rng(4)
+        a = np.ascontiguousarray(pool[rng.integers(0, pool.shape[0], E_WAVE)])
+        b = np.ascontiguousarray(np.clip(a + rng.normal(0, 0.3 / np.sqrt(10), a.shape), W.NAO_LO, W.NAO_HI).astype(dt))
+        r = time_link(nao, a, b)
+        r["midpoints_per_s"] = r.pop("probes_per_s")
+        tipp = issue_nao.get(f"thread_instructions_per_midpoint_{tag}")
+        if tipp and r["midpoints_per_s"]:
+            lanes = ctx.sm_count * 4 * 32 * 1.965e9  # thread instructions per second at one warp instruction per scheduler per clock
+            r["issue"] = {"thread_instructions_per_midpoint": tipp, "frac_of_issue_slots": r["midpoints_per_s"] * tipp / lanes,
+                          "fp32_instructions_per_midpoint": issue_nao.get(f"fp32_instructions_per_midpoint_{tag}"),
+                          "source": issue_nao.get("source"),
+                          "note": "every test of this scenario decides, so its arithmetic is unfused (one flop per FP32 instruction): "
+                                  "the FFMA yardstick's flop rate is out of reach by construction, its instruction rate is the bound"}
+        if scalar == m.F64:  # the CPU restatement of the same edges on the host threads (bounded sample)
+            from tests import oracle_binding
+            orc = oracle_binding.load()
+            on = orc.nao_cup(m.F64)
+            t0 = time.perf_counter()
+            want = on.link(a[:8192], b[:8192])
+            dt_cpu = time.perf_counter() - t0
+            got = nao.link(a[:8192], b[:8192])
+            assert np.array_equal(got, want), "Nao edge decisions differ from the oracle"
+            r["cpu_port"] = {"edges_per_s": 8192 / dt_cpu, "threads": orc.threads, "sample": "8,192 of the 65,536 edges", "decisions_equal": True}
+        out[f"nao_cup_edges_{tag}"] = r
+        nao.close()
+
     def time_knn(sp, pts, q, strat, np_dtype=np.float32):
         nn = m.Nearest(ctx, sp, pts.shape[0], strat)
         nn.insert(pts)
@@ -562,6 +597,27 @@ def secondary(ctx, torch, dev, stream):
                                            "solution_cost": ps.solution_cost() if ps.solved() else None,
                                            "timing": "wall clock, faster of two identical runs"}
         ps.close()
+    # time to the FIRST solution (13.4 ms / 52,804 nodes with 8,192-sample waves throughout against 1.3 ms / 816 nodes
+    # for the reference's PRRT* on 16 host threads): a tree grows by at most one range per wave, so early waves are kept small
+    # and doubled -- the wave ramp of the C++ DevicePRRT / DevicePRRTStar (planner.hpp nextWave)
+    for name, cls in (("device_prrt_grid_first_solution", m.DevicePRRT), ("device_prrtstar_grid_first_solution", m.DevicePRRTStar)):
+        best = None
+        for attempt in range(3):
+            pl = cls(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], range=200.0, goal=goal, goal_radius=12.0,
+                     goal_bias=0.01, seed=17, capacity=1 << 18, max_wave=8192)
+            pl.add_start(start)
+            ctx.sync()
+            t0, w, waves = time.perf_counter(), 64, 0
+            while not pl.solved() and pl.size < 200_000:
+                pl.wave(w)
+                waves += 1
+                w = min(2 * w, 8192)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best["first_solution_s"]:
+                best = {"first_solution_s": dt, "first_solution_nodes": pl.size, "waves": waves, "solved": pl.solved(), "ramp": "64 samples, doubled per wave up to 8,192",
+                        "timing": "wall clock, fastest of three identical runs"}
+            pl.close()
+        out[name] = best
     # device-resident PPRM (BASELINE configs[3]: PPRM for the N-link arm): roadmap, components and every stage on the GPU
     for n_links in (8, 16):
         lengths, radius, circles = W.link_arm_scene(n_links)
@@ -588,6 +644,34 @@ def secondary(ctx, torch, dev, stream):
         ref_arm = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1])
         if ref_arm:
             out[f"reference_planner_cpu_arm{n_links}"] = ref_arm
+    # BASELINE configs[3] as a PLANNING problem (the scene above connects start and goal almost directly): rings of
+    # circles with narrow gaps, W.link_arm_passage_scene -- time and roadmap size to the first solution, ours and the reference's
+    for n_links in (8, 16):
+        lengths, radius, circles, a_start, a_goal = W.link_arm_passage_scene(n_links)
+        arm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64)
+        ea, eb = W.arm_edges(E_WAVE, n_links, 41, 0.5)
+        edges = time_link(arm, ea, eb)
+        best = None
+        for attempt in range(2):
+            pp = m.DevicePPRM(arm, m.lp_space(n_links, 1, m.F64), -np.pi, np.pi, seed=23, capacity=1 << 19, max_wave=4096)
+            pp.add_start(a_start)
+            pp.add_goal(a_goal)
+            ctx.sync()
+            t0, w = time.perf_counter(), 256
+            while not pp.solved() and pp.size < 400_000 and time.perf_counter() - t0 < 20.0:
+                pp.wave(w)
+                w = min(2 * w, 4096)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best["first_solution_s"]:
+                best = {"solved": pp.solved(), "first_solution_s": dt, "first_solution_nodes": pp.size, "nodes_per_s": pp.size / dt,
+                        "edge_wave": {"edges_per_s": edges["edges_per_s"], "valid_fraction": edges["valid_fraction"]},
+                        "timing": "wall clock, faster of two identical runs; waves of 256 samples doubled up to 4,096"}
+            pp.close()
+        out[f"device_pprm_arm{n_links}_passage"] = best
+        ref_arm = reference_planner_cpu_arm(lengths, radius, circles, a_start, a_goal, nodes=200_000, time_ms=15000)
+        if ref_arm:
+            out[f"reference_planner_cpu_arm{n_links}_passage"] = ref_arm
+        arm.close()
     # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
     ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)
     if ref:

@@ -453,8 +453,9 @@ int mptg_prrt_wave(mptg_prrt* p, uint32_t n_samples, uint32_t* size_out, uint32_
     if (!p || n_samples == 0 || n_samples > p->maxWave) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_prrt_wave: bad argument");
     if (p->size == 0) return fail(p->ctx, MPTG_ERR_BAD_ARG, "mptg_prrt_wave: there are no valid initial states");  // prrt.hpp:197-198
     MPTG_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
-    const uint32_t init[2] = {0u, MPTG_NO_INDEX};
-    if (int rc = uploadSync(p->ctx, p->result, init, sizeof init)) return rc;
+    // result = {0 nodes added, no goal node}: stream-ordered, no host round trip in front of the wave
+    MPTG_CUDA(p->ctx, cudaMemsetAsync(p->result, 0, 4, p->ctx->stream));
+    MPTG_CUDA(p->ctx, cudaMemsetAsync(p->result + 1, 0xFF, 4, p->ctx->stream));
     const int rc = p->scalar == MPTG_F32 ? prrtWaveT<float>(p, n_samples) : prrtWaveT<double>(p, n_samples);
     if (size_out) *size_out = p->size;
     if (goal_node_out) *goal_node_out = p->goalNode;

@@ -252,3 +252,20 @@ def nao_edges(n: int, seed: int, sigma: float = 0.3, reach: float = 0.25, dtype=
     rng = np.random.default_rng(seed + 1)
     b = np.clip(a + rng.normal(0.0, reach / np.sqrt(10.0), (n, 10)) * rng.random((n, 1)) * 2.0, NAO_LO, NAO_HI)
     return np.ascontiguousarray(a.astype(dtype)), np.ascontiguousarray(b.astype(dtype))
+
+
+def link_arm_passage_scene(n_links: int):
+    """A link-arm problem that needs a roadmap (in link_arm_scene start and goal connect almost directly): rings of
+    circles of radius 3 round the base with gaps of about one circle radius, start = the arm stretched through the gap at angle 0,
+    goal = stretched through the gap at 120 degrees.  To get from one to the other the arm has to fold back inside the inner ring.
+    8 links: the reference's own PPRM (16 host threads) needs several thousand nodes; 16 links: it does not finish in 20 s.
+    -> (lengths, link radius, circles [n, 3], start, goal)"""
+    rings = {8: ((13.0, 6),), 16: ((13.0, 6), (30.0, 12)), 32: ((13.0, 6), (30.0, 12), (60.0, 24), (100.0, 40))}[n_links]
+    circles = []
+    for radius, count in rings:
+        for i in range(count):
+            a = 2 * np.pi * (i + 0.5) / count
+            circles.append((radius * np.cos(a), radius * np.sin(a), 3.0))
+    start, goal = np.zeros(n_links), np.zeros(n_links)
+    goal[0] = 2 * np.pi / 3
+    return np.full(n_links, 4.0), 0.5, np.asarray(circles), start, goal
