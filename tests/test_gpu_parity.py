@@ -388,9 +388,10 @@ def test_knn_merge_sharded_equals_single(ctx, oracle):
 
 # ------------------------------------------------------------------ BASELINE.json configs[4] at full size
 def test_c5_full_size_knn_properties(ctx, oracle):
-    """N = 1,048,576 tree points, Q = 65,536 queries, k = 16 (the bench workload).  Too large for the oracle
-    as a whole, so: size-independent properties on the full wave, the two device strategies against each other
-    on 2,048 queries, and the oracle on 128 queries."""
+    """N = 1,048,576 tree points, Q = 65,536 queries, k = 16 (the bench workload).  Size-independent properties on the
+    full wave; the two device strategies against each other on 2,048 queries; the oracle's exhaustive scan on 128 queries;
+    and (r2) the oracle's box tree -- an independent exact search, held to the exhaustive scan by tests/test_oracle.py --
+    on ALL 65,536 queries: indices, distances and counts bit-identical."""
     sp = m.se3_space(50, 1)
     N, Q, k = 1 << 20, 1 << 16, 16
     pts, q = W.se3_states(N, W.TREE_SEED), W.se3_states(Q, W.QUERY_SEED)
@@ -425,6 +426,8 @@ def test_c5_full_size_knn_properties(ctx, oracle):
     # and the CPU oracle's exhaustive scan on 128 queries
     osel = np.arange(3, Q, 512)
     assert_knn_equal((idx[osel], dist[osel], cnt[osel]), oracle.knn(sp, pts, q[osel], k))
+    # the whole wave against the oracle's box-tree search (CPU, all host threads; about a second per 64 K queries)
+    assert_knn_equal((idx, dist, cnt), oracle.tree(sp, pts).knn(q, k))
     # radius form: exactly the neighbours within r, same order
     r = float(np.median(dist[:, 7]))
     ri, rd, rc = nn.nearest(q[bsel], k, r)
@@ -456,10 +459,19 @@ def test_c5_full_size_edge_properties(ctx, oracle):
     # number of states touched: all of a valid edge's, at least one of an invalid edge's
     full = _dmv_state_counts(ctx, sp, a, b, step)
     assert int(full[ok == 1].sum()) + int((ok == 0).sum()) <= states <= int(full.sum())
-    # the oracle on 2,048 of the edges
+    # the oracle on 2,048 of the edges with its near-contact pass (exhaustive, slow) ...
     osel = np.arange(0, E, 32)
-    want, near = oracle.mesh_pair(robot, env, sp, step).link(a[osel], b[osel], with_near_contact=True)
+    omesh = oracle.mesh_pair(robot, env, sp, step)
+    want, near = omesh.link(a[osel], b[osel], with_near_contact=True)
     assert not ((ok[osel] != want) & (near == 0)).any()
+    # ... and (r2) its decisions on ALL 65,536 edges; the few that differ must be flagged near contact by the product itself
+    want_all = omesh.link(a, b)
+    differ = np.flatnonzero(ok != want_all)
+    if differ.size:
+        _, flagged = sc.link(a[differ], b[differ], with_near_contact=True)
+        _, onear = omesh.link(a[differ], b[differ], with_near_contact=True)
+        assert (flagged == 1).all() and (onear == 1).all(), f"{differ.size} edges differ from the oracle outside the contact band"
+    print(f"C5 edges: {E} compared with the oracle, {differ.size} differ (all inside the reported contact band)")
 
 
 # ------------------------------------------------------------------ sampling and the device-resident PRRT
