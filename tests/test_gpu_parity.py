@@ -223,6 +223,48 @@ def test_knn_l1_scan_several_queries_per_warp(ctx, oracle, scalar):
         nn.close()
 
 
+def test_knn_l1_double_sets_extreme_values(ctx, oracle):
+    """Double-precision L1 sets on inputs a reduced-precision shortcut would get wrong (written for a float-prefilter
+    variant of the scan that was measured and dropped; kept for the shipped kernel): coordinates of
+    magnitude 1e4 / 1e7 whose DIFFERENCES are far below the float resolution, neighbours separated by 1e-12, a set that
+    grows between searches, values beyond the float range, NaN and infinite coordinates in points and queries, ties."""
+    rng = np.random.default_rng(8)
+    for dim, scale, spread in ((8, 1e4, 1e-3), (16, 1e7, 1e-2), (8, 1.0, 1e-12), (12, 3.0, 1.0)):
+        sp = m.lp_space(dim, 1, m.F64)
+        centre = rng.uniform(-scale, scale, dim)
+        pts = centre + rng.uniform(-spread, spread, (6000, dim))
+        pts[100:140] = pts[7]
+        q = centre + rng.uniform(-spread, spread, (700, dim))
+        q[3] = pts[7]
+        nn = m.Nearest(ctx, sp, 16384, m.KNN_BRUTE)
+        nn.insert(pts[:2500])
+        for k, radius in ((16, -1.0), (40, -1.0), (5, 0.4 * spread * dim)):
+            assert_knn_equal(nn.nearest(q, k, radius), oracle.knn(sp, pts[:2500], q, k, radius))
+        nn.insert(pts[2500:])
+        for k, radius in ((1, -1.0), (16, -1.0), (64, -1.0)):
+            assert_knn_equal(nn.nearest(q, k, radius), oracle.knn(sp, pts, q, k, radius))
+        nn.close()
+    # out-of-range and non-finite values
+    sp = m.lp_space(8, 1, m.F64)
+    pts = rng.uniform(-3, 3, (4000, 8))
+    pts[10, 2] = 1e39       # beyond float: infinite in the mirror, finite in the set
+    pts[11, 0] = np.inf
+    pts[12, 5] = np.nan
+    pts[13] = -1e39
+    q = rng.uniform(-3, 3, (600, 8))
+    q[0, 1] = np.nan
+    q[1, 1] = 1e39
+    q[2, 1] = np.inf
+    q[4] = -1e39
+    nn = m.Nearest(ctx, sp, 8192, m.KNN_BRUTE)
+    nn.insert(pts)
+    for k in (4, 16):
+        got, want = nn.nearest(q, k), oracle.knn(sp, pts, q, k)
+        assert got[2][0] == 0 and want[2][0] == 0
+        assert_knn_equal(got, want)
+    nn.close()
+
+
 def test_knn_degenerate_point_sets(ctx, oracle):
     """All points identical / on a line / two clusters: zero-extent boxes, massive ties (index order decides)."""
     sp = m.se3_space(50, 1)
