@@ -238,7 +238,8 @@ int mptg_geom_contact_band(const mptg_geom* geom, double* band_out);
  *   GRID    valid(a) && valid(b) && midpoint bisection until |b-a|^2 < 1   (png_2d_scenario.hpp:112-117,152-165)
  *   SHAPES  balls: closed-form point-segment distance; rects: endpoints + bisection (shape_hierarchy.hpp:184-203,228-270)
  *   LINKARM valid(a) && valid(b) && bisection until |a-b|_inf < 0.02        (link_manipulator_scenario.hpp:118-138)
- *   NAOCUP  midpoint bisection until |b-a|_2 < 1 degree; the ends are NOT checked (naocup.hpp:809-840)
+ *   NAOCUP  midpoint bisection until |b-a|_2 < 1 degree; the ends are NOT checked (naocup.hpp:809-840); an edge whose
+ *           length is not finite is invalid (the reference's recursion need not terminate on NaN / infinite joints)
  *   MESH    DiscreteMotionValidator with step size `step` over `space`      (discrete_motion_validator.hpp:71-130);
  *           `from` is assumed valid and not checked, exactly as the reference (:72-73).
  * `space` / `step` are only read for MESH (pass NULL / 0 otherwise).

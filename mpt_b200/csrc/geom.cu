@@ -161,7 +161,9 @@ struct ArmValidator {
             m = d > m ? d : m;
             mag = fmax(mag, fmax(fp::abs_(a[i]), fp::abs_(b[i])));
         }
-        if (!(m == m)) return 1;
+        // an infinite coordinate: the end it belongs to is invalid (its sines are NaN and no circle test passes on NaN),
+        // which the reference finds before it bisects (:118-123); said here without a 2^24-node tree
+        if (!(m < fp::consts<S>::inf())) return -1;
         return levelsFor<S>(m, S(0.02) * S(63.0 / 64.0) - S(256) * fp::consts<S>::eps() * mag);
     }
 };
@@ -322,6 +324,11 @@ __global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* _
     const int D = v.dims();
     for (int i = 0; i < D; ++i) a[i] = from[(size_t)e * D + i], b[i] = to[(size_t)e * D + i];
     const int L = v.levels(a, b);
+    if (L < 0) {  // the validator declares the edge invalid outright (a length that is not finite)
+        ok[e] = 0;
+        counts[e] = 0;
+        return;
+    }
     if (L > FLAT_MAX_LEVELS) {
         atomicOr(stats + 4, (unsigned long long)GEOM_ERR_STEPS);
         ok[e] = 0;
@@ -623,11 +630,6 @@ int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) 
         }
         case MPTG_GEOM_NAOCUP: {
             nao::Validator<S> v{*(const nao::Model<S>*)g->naoModel};
-            if (getenv("MPTG_NAO_WARP_PER_EDGE")) {  // the earlier kernel, kept for the comparison in DESIGN.md
-                bisectLinkKernel<S, nao::Validator<S>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats);
-                MPTG_LAUNCHED(ctx);
-                break;
-            }
             if (int rc = flatLink<S, nao::Validator<S>>(g, v, from, to, n, ok)) return rc;
             break;
         }

@@ -10,7 +10,7 @@
 // sums running left to right -- while the CUDA kernel (mpt_b200/csrc/nao.cuh) uses closed forms with the exact zeros
 // and ones removed.  Parity of the two is therefore a real check of both.
 // Pinned against the reference's own code compiled here (oracle/ref_nao.cpp -> oracle/_ref/libref_nao.so, golden
-// vectors in tests/golden/reference_golden.npz); the reference calls libm sin/cos, this file mptg_fpmath.h.
+// vectors in tests/golden/nao_golden.npz); the reference calls libm sin/cos, this file mptg_fpmath.h.
 #pragma once
 
 #include <cmath>
@@ -297,7 +297,12 @@ struct NaoCup {
         return mptg::fp::sqrt_(sum);
     }
     bool linkImpl(const S* a, const S* b, uint64_t* states) const {  // nao_link_impl, :809-825
-        if (dist(a, b) < discretization()) return true;
+        const S d = dist(a, b);
+        // A NaN or infinite joint value: the reference's recursion need not terminate (a NaN in a left-arm joint makes
+        // every comparison of the ball's tests false, i.e. "clear", while the stop test never holds).  Defined here and
+        // in the kernels: an edge whose length is not finite is invalid.
+        if (!(d < std::numeric_limits<S>::infinity())) return false;
+        if (d < discretization()) return true;
         S m[DIM];
         for (int i = 0; i < DIM; ++i) m[i] = (a[i] + b[i]) / S(2.0);
         if (states) ++*states;
@@ -306,7 +311,8 @@ struct NaoCup {
     bool link(const S* a, const S* b, uint64_t* states = nullptr) const { return linkImpl(a, b, states); }  // :828-840: ends not checked
     // every midpoint of the recursion regardless of the outcome: smallest margin along the edge (test support)
     void linkMargin(const S* a, const S* b, double* margin) const {
-        if (dist(a, b) < discretization()) return;
+        const S d = dist(a, b);
+        if (!(d < std::numeric_limits<S>::infinity()) || d < discretization()) return;
         S m[DIM];
         for (int i = 0; i < DIM; ++i) m[i] = (a[i] + b[i]) / S(2.0);
         double mm;

@@ -140,3 +140,35 @@ def test_device_edges_are_order_free(ctx, oracle):
     a, b = W.nao_edges(4096, 21)
     fwd, rev = sc.link(a, b), sc.link(b, a)
     assert np.array_equal(fwd, og.link(a, b)) and np.array_equal(rev, og.link(b, a))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["nao", "arm"])
+def test_flat_edge_check_limits(ctx, oracle, which):
+    """flatLinkKernel (geom.cu): NaN ends behave as in the reference's recursion (its stop test never holds, the first
+    midpoint fails: the edge is invalid; an arm edge fails on its invalid end), zero-length and sub-threshold edges need no
+    midpoint, and an edge whose recursion would be deeper than 24 levels is an ERROR (MPTG_ERR_CAPACITY), not a silent cut."""
+    if which == "nao":
+        sc, og, D = m.Scenario.nao_cup(ctx, m.F64), oracle.nao_cup(m.F64), 10
+        base = np.tile(W.NAO_START, (8, 1))
+        huge = 1e8
+    else:
+        lengths, radius, circles = W.link_arm_scene(8)
+        sc, og, D = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64), oracle.link_arm(lengths, radius, circles), 8
+        st = W.box_states(4096, 8, 3, -np.pi, np.pi)
+        base = np.tile(st[sc.valid(st) == 1][:1], (8, 1))
+        huge = 1e7
+    a, b = base.copy(), base.copy()
+    b[1, 0] += 0.3
+    a[2, 1] = np.nan
+    b[3, D - 1] = np.nan
+    a[4], b[4] = np.nan, np.nan
+    b[5, 2] += 1e-9
+    b[6, 0] += np.inf
+    got, want = sc.link(a, b), og.link(a, b)
+    assert np.array_equal(got, want) and got[0] == 1 and got[2] == 0 and got[3] == 0 and got[4] == 0 and got[5] == 1 and got[6] == 0
+    b[7, 0] += huge  # 2^24 midpoints and more
+    with pytest.raises(m.MptgError) as e:
+        sc.link(a, b)
+    assert e.value.code == -5  # MPTG_ERR_CAPACITY
+    assert np.array_equal(sc.link(a[:6], b[:6]), want[:6])  # the geometry stays usable after the error
