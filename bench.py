@@ -591,7 +591,7 @@ def secondary(ctx, torch, dev, stream):
         ps.close()
     # time to the FIRST solution (13.4 ms / 52,804 nodes with 8,192-sample waves throughout against 1.3 ms / 816 nodes
     # for the reference's PRRT* on 16 host threads): a tree grows by at most one range per wave, so early waves are kept small
-    # and doubled -- the wave ramp of the C++ DevicePRRT / DevicePRRTStar (planner.hpp nextWave)
+    # and held at 512 samples until a solution exists -- the wave ramp of the C++ DevicePRRT / DevicePRRTStar (planner.hpp impl::WaveRamp)
     for name, cls in (("device_prrt_grid_first_solution", m.DevicePRRT), ("device_prrtstar_grid_first_solution", m.DevicePRRTStar)):
         best = None
         for attempt in range(3):
@@ -600,13 +600,14 @@ def secondary(ctx, torch, dev, stream):
             pl.add_start(start)
             ctx.sync()
             t0, w, waves = time.perf_counter(), 64, 0
-            while not pl.solved() and pl.size < 200_000:
+            while not pl.solved() and pl.size < 200_000:  # impl::WaveRamp of planner.hpp: 64, 128, 256, then 512 held for 16 waves, then doubled every fourth
                 pl.wave(w)
                 waves += 1
-                w = min(2 * w, 8192)
+                if w < 512 or (waves >= 16 and (waves - 16) % 4 == 3):
+                    w = min(2 * w, 8192)
             dt = time.perf_counter() - t0
             if best is None or dt < best["first_solution_s"]:
-                best = {"first_solution_s": dt, "first_solution_nodes": pl.size, "waves": waves, "solved": pl.solved(), "ramp": "64 samples, doubled per wave up to 8,192",
+                best = {"first_solution_s": dt, "first_solution_nodes": pl.size, "waves": waves, "solved": pl.solved(), "ramp": "64, 128, 256 samples, then 512 per wave until the first solution (doubled every fourth wave after 16)",
                         "timing": "wall clock, fastest of three identical runs"}
             pl.close()
         out[name] = best
@@ -644,25 +645,34 @@ def secondary(ctx, torch, dev, stream):
         ea, eb = W.arm_edges(E_WAVE, n_links, 41, 0.5)
         edges = time_link(arm, ea, eb)
         best = None
-        for attempt in range(2):
+        for attempt in range(2 if n_links == 8 else 1):
             pp = m.DevicePPRM(arm, m.lp_space(n_links, 1, m.F64), -np.pi, np.pi, seed=23, capacity=1 << 19, max_wave=4096)
             pp.add_start(a_start)
             pp.add_goal(a_goal)
             ctx.sync()
             t0, w = time.perf_counter(), 256
-            while not pp.solved() and pp.size < 400_000 and time.perf_counter() - t0 < 20.0:
+            while not pp.solved() and pp.size < 400_000 and time.perf_counter() - t0 < 10.0:
                 pp.wave(w)
                 w = min(2 * w, 4096)
             dt = time.perf_counter() - t0
+            path_ok = None
+            if pp.solved():  # the roadmap's own answer: every edge of the shortest path passes the edge check again
+                path = pp.solution()
+                path_ok = bool(len(path) >= 2 and (arm.link(path[:-1], path[1:]) == 1).all() and np.array_equal(path[0], a_start) and np.array_equal(path[-1], a_goal))
             if best is None or dt < best["first_solution_s"]:
-                best = {"solved": pp.solved(), "first_solution_s": dt, "first_solution_nodes": pp.size, "nodes_per_s": pp.size / dt,
+                best = {"solved": pp.solved(), "first_solution_s": dt, "first_solution_nodes": pp.size, "nodes_per_s": pp.size / dt, "path_revalidated": path_ok,
                         "edge_wave": {"edges_per_s": edges["edges_per_s"], "valid_fraction": edges["valid_fraction"]},
                         "timing": "wall clock, faster of two identical runs; waves of 256 samples doubled up to 4,096"}
             pp.close()
         out[f"device_pprm_arm{n_links}_passage"] = best
-        ref_arm = reference_planner_cpu_arm(lengths, radius, circles, a_start, a_goal, nodes=200_000, time_ms=15000)
+        ref_arm = reference_planner_cpu_arm(lengths, radius, circles, a_start, a_goal, nodes=200_000, time_ms=10000)
         if ref_arm:
             out[f"reference_planner_cpu_arm{n_links}_passage"] = ref_arm
+            # the reference's roadmap connects with FEWER nodes the fewer workers build it (measured: 1 thread 160 - 900 nodes,
+            # 8 threads ~10 K, 16 threads none within 72 K): its single-threaded run is the fair time-to-solution figure
+            one = reference_planner_cpu_arm(lengths, radius, circles, a_start, a_goal, nodes=200_000, time_ms=10000, threads=1)
+            if one:
+                out[f"reference_planner_cpu_arm{n_links}_passage_1thread"] = one
         arm.close()
     # same map, same start, same range: the reference's own multi-threaded PRRT / PRRT* on the host cores
     ref = reference_planner_cpu(occ, start, goal, 12.0, 200.0)
@@ -702,7 +712,7 @@ def reference_planner_cpu(occ, start, goal, goal_radius, prrt_range, nodes=200_0
     return out
 
 
-def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_000, time_ms=6000):
+def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_000, time_ms=6000, threads=None):
     """The reference's own multi-threaded PPRM (BASELINE configs[3]) on the reference's LinkManipulatorScenario<double, N>
     (demo/link_manipulator_scenario.hpp), N = 8 or 16, on this box's host cores.  Same program and caveats as
     reference_planner_cpu."""
@@ -720,9 +730,10 @@ def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_00
         f.write(" ".join(repr(float(x)) for x in start) + "\n" + " ".join(repr(float(x)) for x in goal) + "\n")
         f.flush()
         env = dict(os.environ)
-        env["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        env["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)
         try:
-            r = subprocess.run([str(prog), "--arm", f.name, "--algo", "pprm", "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "23"],
+            r = subprocess.run([str(prog), "--arm", f.name, "--algo", "pprm", "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "23"]
+                               + (["--threads", str(threads)] if threads else []),
                                capture_output=True, text=True, timeout=time_ms / 1e3 + 60, env=env)
             return json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:

@@ -144,6 +144,27 @@ constexpr S E = S(2.71828182845904523536028747135266249775724709369995L);
 template <typename S>
 constexpr S PI = S(3.14159265358979323846264338327950288419716939937510L);
 
+// Wave sizes of the device-resident planners on the way to the configured size.  A tree grows outwards by at most one
+// `range` per wave, so the first solution needs a minimum NUMBER of waves whatever their size, and until it is found large
+// waves only add nodes (and time per wave) the young tree cannot use: 64, 128, 256 samples, then `hold` (512) samples per
+// wave; after 16 waves without a solution the size doubles every fourth wave (a hard problem needs the throughput of
+// full waves); once a solution exists it doubles every wave up to the configured size.  Measured on the 3976 x 2603
+// map, 12 waves to the first solution in every case: PRRT* 10.5 ms with waves ramped to 8,192 samples, 3.2 ms held at
+// 512 (13.4 ms with 8,192-sample waves throughout); PRRT 4.2 -> 0.93 ms (profiles/r2_ramp_caps.txt).
+struct WaveRamp {
+    std::uint32_t first = 64, hold = 512;
+    std::uint32_t now = 0, waves = 0;
+    std::uint32_t next(std::uint32_t full, bool solved) {
+        if (first == 0) return full;
+        ++waves;
+        if (now == 0) now = first;
+        else if (solved || now < hold || (waves > 16 && (waves - 16) % 4 == 0)) now *= 2;
+        const std::uint32_t limit = (solved || waves > 16) ? full : (hold < full ? hold : full);
+        if (now > limit) now = limit;
+        return now < full ? now : full;
+    }
+};
+
 struct StageTimer {
     double seconds = 0;
     std::uint64_t calls = 0, items = 0;
@@ -988,20 +1009,11 @@ class DevicePRRT {
     Distance goalBias_{0.01};
     std::vector<State> starts_;
     std::uint32_t wave_ = waveSize, size_ = 0, goalNode_ = NONE;
-    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
-    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
-    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
-    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
-    // throughout).  setWaveRamp(0) switches it off.
-    std::uint32_t ramp_ = 64, rampNow_ = 0;
-    std::uint32_t nextWave() {
-        if (ramp_ == 0) return wave_;
-        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
-        return rampNow_ < wave_ ? rampNow_ : wave_;
-    }
+    impl::WaveRamp ramp_;  // wave sizes until the configured size is reached (time to the first solution)
 
 public:
-    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+    // first wave's size (0: full-size waves from the start) and the size held until the first solution is found
+    void setWaveRamp(std::uint32_t firstWave, std::uint32_t holdAt = 512) { ramp_ = impl::WaveRamp{firstWave, holdAt}; }
 
 private:
 
@@ -1061,7 +1073,7 @@ public:
         create();
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_prrt_wave(prrt_, nextWave(), &size_, &goalNode_), ctx_.get(), "mptg_prrt_wave");
+            check(mptg_prrt_wave(prrt_, ramp_.next(wave_, goalNode_ != NONE), &size_, &goalNode_), ctx_.get(), "mptg_prrt_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1131,20 +1143,11 @@ class DevicePRRTStar {
     Distance goalBias_{0.01};
     std::vector<State> starts_;
     std::uint32_t wave_ = waveSize, size_ = 0, goalNode_ = NONE;
-    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
-    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
-    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
-    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
-    // throughout).  setWaveRamp(0) switches it off.
-    std::uint32_t ramp_ = 64, rampNow_ = 0;
-    std::uint32_t nextWave() {
-        if (ramp_ == 0) return wave_;
-        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
-        return rampNow_ < wave_ ? rampNow_ : wave_;
-    }
+    impl::WaveRamp ramp_;  // wave sizes until the configured size is reached (time to the first solution)
 
 public:
-    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+    // first wave's size (0: full-size waves from the start) and the size held until the first solution is found
+    void setWaveRamp(std::uint32_t firstWave, std::uint32_t holdAt = 512) { ramp_ = impl::WaveRamp{firstWave, holdAt}; }
 
 private:
 
@@ -1217,7 +1220,7 @@ public:
         create();
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_prrtstar_wave(prrt_, nextWave(), &size_, &goalNode_), ctx_.get(), "mptg_prrtstar_wave");
+            check(mptg_prrtstar_wave(prrt_, ramp_.next(wave_, goalNode_ != NONE), &size_, &goalNode_), ctx_.get(), "mptg_prrtstar_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -1293,20 +1296,11 @@ class DevicePPRM {
     mptg_space_desc desc_;
     mptg_pprm* pprm_ = nullptr;
     std::uint32_t wave_ = waveSize, size_ = 0, solved_ = 0, stride_ = 0;
-    // Wave ramp.  A tree grows outwards by at most one `range` per wave, so the first solution needs a minimum NUMBER of
-    // waves whatever their size; full-size waves from the start only add nodes (and time per wave) that the early tree
-    // cannot use.  The first wave draws `ramp` samples and every wave doubles it until the configured wave size is
-    // reached (measured on the 3976 x 2603 map: first PRRT* solution after 52,804 nodes / 13.4 ms with 8,192-sample waves
-    // throughout).  setWaveRamp(0) switches it off.
-    std::uint32_t ramp_ = 64, rampNow_ = 0;
-    std::uint32_t nextWave() {
-        if (ramp_ == 0) return wave_;
-        rampNow_ = rampNow_ == 0 ? ramp_ : (rampNow_ >= wave_ / 2 ? wave_ : rampNow_ * 2);
-        return rampNow_ < wave_ ? rampNow_ : wave_;
-    }
+    impl::WaveRamp ramp_;  // wave sizes until the configured size is reached (time to the first solution)
 
 public:
-    void setWaveRamp(std::uint32_t firstWave) { ramp_ = firstWave, rampNow_ = 0; }
+    // first wave's size (0: full-size waves from the start) and the size held until the first solution is found
+    void setWaveRamp(std::uint32_t firstWave, std::uint32_t holdAt = 512) { ramp_ = impl::WaveRamp{firstWave, holdAt}; }
 
 private:
 
@@ -1372,7 +1366,7 @@ public:
         if (goals_ == 0 || starts_ == 0) throw std::runtime_error("PPRM requires both start and goal configurations");
         const auto t0 = std::chrono::steady_clock::now();
         while (!doneFn() && size_ < (std::uint32_t)maxNodes) {
-            check(mptg_pprm_wave(pprm_, nextWave(), &size_, &solved_), ctx_.get(), "mptg_pprm_wave");
+            check(mptg_pprm_wave(pprm_, ramp_.next(wave_, solved_ != 0), &size_, &solved_), ctx_.get(), "mptg_pprm_wave");
             ++waves_;
         }
         seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -12,6 +12,7 @@ import mpt_b200 as m  # noqa: E402
 from mpt_b200 import workloads as W  # noqa: E402
 
 once = len(sys.argv) > 1 and sys.argv[1] == "once"
+cap = int(sys.argv[2]) if len(sys.argv) > 2 else 8192  # largest wave before the first solution
 ctx = m.Context(0)
 occ = W.synthetic_grid()
 grid = m.Scenario.grid(ctx, occ, m.F64)
@@ -29,9 +30,9 @@ for name, cls in (("PRRT", m.DevicePRRT), ("PRRT*", m.DevicePRRTStar)):
             t1 = time.perf_counter()
             pl.wave(w)
             rows.append((w, pl.size, (time.perf_counter() - t1) * 1e3))
-            w = min(2 * w, 8192)
+            w = min(2 * w, cap)
         total = (time.perf_counter() - t0) * 1e3
         pl.close()
-    print(f"{name}: first solution after {total:.3f} ms, {len(rows)} waves")
-    for w, size, ms in rows:
+    print(f"{name} (waves up to {cap}): first solution after {total:.3f} ms, {len(rows)} waves, {rows[-1][1]} nodes")
+    for w, size, ms in (rows if cap == 8192 else []):
         print(f"   wave of {w:5d} samples -> {size:6d} nodes  {ms:.3f} ms")
