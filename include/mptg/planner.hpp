@@ -119,6 +119,67 @@ struct has_link_step : std::false_type {};
 template <typename Scenario>
 struct has_link_step<Scenario, std::void_t<decltype(std::declval<const Scenario&>().linkStep())>> : std::true_type {};
 
+// ---- random generator and sampler of a scenario (impl/scenario_rng.hpp:46-54, impl/scenario_sampler.hpp:47-217)
+// RNG: Scenario::RNG if the scenario names one, else the Mersenne twister of the scalar's width (mersenne_twister.hpp:328-332).
+template <typename Scenario, typename Scalar, typename = void>
+struct scenario_rng {
+    using type = std::conditional_t<(sizeof(Scalar) <= 4), std::mt19937, std::mt19937_64>;
+};
+template <typename Scenario, typename Scalar>
+struct scenario_rng<Scenario, Scalar, std::void_t<typename Scenario::RNG>> {
+    using type = typename Scenario::RNG;
+};
+template <typename Scenario, typename Scalar>
+using scenario_rng_t = typename scenario_rng<Scenario, Scalar>::type;
+
+// Sampler, in the reference's order of preference: 1. scenario.sample(rng); 2. scenario.sampler() (an object called with the
+// generator); 4. UniformSampler<Space, Bounds> over scenario.bounds().  (3., a Scenario::Sampler type, is declared but left
+// unimplemented by the reference, scenario_sampler.hpp:206-216.)
+template <typename Scenario, typename RNG, typename = void>
+struct has_sample_method : std::false_type {};
+template <typename Scenario, typename RNG>
+struct has_sample_method<Scenario, RNG, std::void_t<decltype(std::declval<Scenario&>().sample(std::declval<RNG&>()))>> : std::true_type {};
+template <typename Scenario, typename = void>
+struct has_sampler_method : std::false_type {};
+template <typename Scenario>
+struct has_sampler_method<Scenario, std::void_t<decltype(std::declval<const Scenario&>().sampler())>> : std::true_type {};
+
+template <typename Scenario>
+class SampleMethodSampler {  // scenario_sampler.hpp:143-156
+    Scenario& scenario_;
+
+public:
+    explicit SampleMethodSampler(Scenario& scenario) : scenario_(scenario) {}
+    template <typename RNG>
+    decltype(auto) operator()(RNG& rng) {
+        return scenario_.sample(rng);
+    }
+};
+template <typename Inner>
+struct SamplerMethodSampler : Inner {  // scenario_sampler.hpp:168-175
+    template <typename Scenario>
+    explicit SamplerMethodSampler(Scenario& scenario) : Inner(scenario.sampler()) {}
+};
+template <typename Scenario>
+struct BoundsSampler : UniformSampler<typename Scenario::Space, std::decay_t<decltype(std::declval<const Scenario&>().bounds())>> {
+    using Base = UniformSampler<typename Scenario::Space, std::decay_t<decltype(std::declval<const Scenario&>().bounds())>>;
+    explicit BoundsSampler(Scenario& scenario) : Base(scenario.space(), scenario.bounds()) {}
+};
+template <typename Scenario, typename RNG, typename = void>
+struct scenario_sampler {
+    using type = BoundsSampler<Scenario>;
+};
+template <typename Scenario, typename RNG>
+struct scenario_sampler<Scenario, RNG, std::enable_if_t<has_sample_method<Scenario, RNG>::value>> {
+    using type = SampleMethodSampler<Scenario>;
+};
+template <typename Scenario, typename RNG>
+struct scenario_sampler<Scenario, RNG, std::enable_if_t<!has_sample_method<Scenario, RNG>::value && has_sampler_method<Scenario>::value>> {
+    using type = SamplerMethodSampler<std::decay_t<decltype(std::declval<const Scenario&>().sampler())>>;
+};
+template <typename Scenario, typename RNG>
+using scenario_sampler_t = typename scenario_sampler<Scenario, RNG>::type;
+
 template <typename Scenario, typename State>
 auto checkGoal(const Scenario& s, const State& q) {
     if constexpr (has_goal_fn<Scenario>::value) return s.goal()(s.space(), q);
@@ -187,9 +248,8 @@ protected:
     using Space = typename Scenario::Space;
     using State = typename Space::Type;
     using Distance = typename Space::Distance;
-    using Bounds = std::decay_t<decltype(std::declval<const Scenario&>().bounds())>;
-    using Sampler = UniformSampler<Space, Bounds>;
-    using RNG = std::mt19937_64;
+    using RNG = scenario_rng_t<Scenario, Distance>;         // Scenario::RNG, else the twister of the scalar's width
+    using Sampler = scenario_sampler_t<Scenario, RNG>;      // scenario.sample(rng) / scenario.sampler() / uniform over bounds()
 
     Scenario scenario_;
     Context ctx_;
@@ -208,7 +268,7 @@ protected:
     WavePlannerBase(const Scenario& scenario, std::uint64_t seed, std::uint32_t wave, int device)
         : scenario_(scenario), ctx_(device), geom_(scenario_.makeGeometry(ctx_)), desc_(scenario_.space().desc()), capacity_(1u << 16),
           nn_(new Nearest<std::uint32_t, Space>(ctx_, scenario_.space(), capacity_)), rng_(seed),
-          sampler_(scenario_.space(), scenario_.bounds()), wave_(wave), linkStep_(linkStepOf(scenario_)) {}
+          sampler_(scenario_), wave_(wave), linkStep_(linkStepOf(scenario_)) {}
 
     // grow the device structure (capacity doubles; states are re-inserted from the host copy)
     void reserve(std::size_t need) {

@@ -116,6 +116,48 @@ void testSpannerStretch() {
                 failures ? "FAIL" : "PASS", n, visitor.edges.size() / 2, denseEdges / 2, violations);
 }
 
+// The Scenario concept's optional members (impl/scenario_sampler.hpp:47-217, impl/scenario_rng.hpp:46-54): a scenario may
+// bring its own sample(rng), its own sampler() object, its own RNG type, and isGoal / sampleGoal instead of goal().
+struct SampleMethodScenario : test::BasicScenario<double, 3> {
+    using RNG = std::mt19937;  // not the default twister of a double space
+    mutable std::size_t* calls;
+    explicit SampleMethodScenario(std::size_t* c) : calls(c) {}
+    State sample(RNG& rng) const {
+        ++*calls;
+        std::uniform_real_distribution<double> u(-1.0, 1.0);
+        State q;
+        for (int i = 0; i < 3; ++i) q[i] = u(rng);
+        return q;
+    }
+};
+struct SamplerMethodScenario : test::BasicScenario<double, 3> {
+    struct Sampler {
+        std::size_t* calls;
+        template <typename RNG>
+        State operator()(RNG& rng) {
+            ++*calls;
+            std::uniform_real_distribution<double> u(-1.0, 1.0);
+            State q;
+            for (int i = 0; i < 3; ++i) q[i] = u(rng);
+            return q;
+        }
+    };
+    std::size_t* calls;
+    explicit SamplerMethodScenario(std::size_t* c) : calls(c) {}
+    Sampler sampler() const { return Sampler{calls}; }
+};
+template <typename Scenario>
+void testScenarioSamplerOptions(const char* name) {
+    std::size_t calls = 0;
+    Planner<Scenario, PRRT<wave_size<32>>> planner(Scenario(&calls), 5);
+    planner.addStart(Scenario::startState());
+    planner.solveFor([&] { return planner.solved(); }, 10s);
+    EXPECT(planner.solved());
+    EXPECT(calls >= planner.size() - 1);  // every node but the start came out of the scenario's own sampler
+    std::printf("%s scenario sampler option (%s): solved=%d, %zu nodes, %zu samples drawn by the scenario\n", failures ? "FAIL" : "PASS", name,
+                (int)planner.solved(), planner.size(), calls);
+}
+
 void testPRRTStarInvariants() {
     // cost(node) == cost(parent) + distance(parent, node) up to rounding, after rewiring
     using Scenario = test::BasicScenario<double, 3>;
@@ -216,6 +258,11 @@ int main() {
     testSolvingBasicScenario<PRRTStar<report_stats<true>>>("PRRT* k-nearest");
     testSolvingBasicScenario<PRRTStar<rewire_r_nearest>>("PRRT* r-nearest");
     testSolvingBasicScenario<PPRM<report_stats<true>>>("PPRM");
+    static_assert(std::is_same_v<impl::scenario_rng_t<test::BasicScenario<double, 3>, double>, std::mt19937_64>);
+    static_assert(std::is_same_v<impl::scenario_rng_t<test::BasicScenario<float, 3>, float>, std::mt19937>);  // mersenne_twister.hpp:328-332
+    static_assert(std::is_same_v<impl::scenario_rng_t<SampleMethodScenario, double>, std::mt19937>);
+    testScenarioSamplerOptions<SampleMethodScenario>("sample(rng) + RNG");
+    testScenarioSamplerOptions<SamplerMethodScenario>("sampler()");
     // the reference's PPRM-IRS integration test is the same scenario (test/pprm_irs_integration_test.cpp)
     static_assert(std::is_same_v<Planner<S, PPRMIRS<report_stats<true>, keep_dense_edges<true>>>, Planner<S, PPRMIRS<keep_dense_edges<true>, report_stats<true>>>>);
     static_assert(!std::is_same_v<Planner<S, PPRMIRS<>>, Planner<S, PPRMIRS<keep_dense_edges<true>>>>);

@@ -30,7 +30,8 @@ def test_wave_planners_host_logic_with_mock_backend():
 
     out = _run(build_host.build_mock())
     for name in ("PRRT:", "PRRT wave 64:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:", "PPRM-IRS:",
-                 "PPRM-IRS keep_dense_edges, wave 64:", "PPRM-IRS spanner:", "PRRT on the Nao-cup scenario:", "PRRT* on the Nao-cup scenario:"):
+                 "PPRM-IRS keep_dense_edges, wave 64:", "PPRM-IRS spanner:", "PRRT on the Nao-cup scenario:", "PRRT* on the Nao-cup scenario:",
+                 "scenario sampler option (sample(rng) + RNG):", "scenario sampler option (sampler()):"):
         assert f"PASS {name}" in out
 
 
