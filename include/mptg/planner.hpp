@@ -33,6 +33,7 @@
 #include <random>
 #include <type_traits>
 #include <utility>
+#include <variant>
 #include <vector>
 
 #include "host.hpp"
@@ -204,6 +205,31 @@ template <typename S>
 constexpr S E = S(2.71828182845904523536028747135266249775724709369995L);
 template <typename S>
 constexpr S PI = S(3.14159265358979323846264338327950288419716939937510L);
+
+// solution(fn): the reference accepts a waypoint callback fn(q) or a trajectory callback fn(from, trajectory, to, forward)
+// (impl/link_trajectory.hpp:76-110).  The batched back-ends answer link() with a bool, whose stored trajectory type is
+// std::monostate (:53-54), so the trajectory form is fn(const State&, const std::monostate&, const State&, bool).
+template <typename Fn, typename State>
+constexpr bool is_trajectory_callback_v = std::is_invocable_v<Fn&, const State&, const std::monostate&, const State&, bool>;
+// tree planners: edges from the start towards the goal, forward = true (impl/prrt/prrt.hpp:236-243)
+template <typename State, typename Fn>
+void emitSolution(const std::vector<State>& path, Fn& fn) {
+    if constexpr (is_trajectory_callback_v<Fn, State>) {
+        for (std::size_t i = 1; i < path.size(); ++i) fn(path[i - 1], std::monostate{}, path[i], true);
+    } else {
+        for (const State& q : path) fn(q);
+    }
+}
+// roadmap planners: an edge was created FROM the node that was being added TO its (older) neighbour, and `forward` says
+// whether the path runs along it in that direction (impl/pprm/pprm.hpp:196-215, impl/pprm/edge.hpp)
+template <typename State, typename Fn>
+void emitRoadmapSolution(const std::vector<State>& states, const std::vector<std::uint32_t>& nodes, Fn& fn) {
+    if constexpr (is_trajectory_callback_v<Fn, State>) {
+        for (std::size_t i = 1; i < nodes.size(); ++i) fn(states[nodes[i - 1]], std::monostate{}, states[nodes[i]], nodes[i - 1] > nodes[i]);
+    } else {
+        for (std::uint32_t n : nodes) fn(states[n]);
+    }
+}
 
 // Wave sizes of the device-resident planners on the way to the configured size.  A tree grows outwards by at most one
 // `range` per wave, so the first solution needs a minimum NUMBER of waves whatever their size, and until it is found large
@@ -399,8 +425,8 @@ public:
         return path;
     }
     template <typename Fn>
-    void solution(Fn fn) const {  // waypoint callback form (:244-249, 266-276)
-        for (const State& q : solution()) fn(q);
+    void solution(Fn fn) const {  // waypoint or trajectory callback form (:236-260, 266-276)
+        impl::emitSolution(solution(), fn);
     }
     void printStats() const {  // :278-289
         std::clog << "nodes in graph: " << this->size() << "\nsolutions: " << goals_.size() << "\n";
@@ -545,7 +571,7 @@ public:
     }
     template <typename Fn>
     void solution(Fn fn) const {
-        for (const State& q : solution()) fn(q);
+        impl::emitSolution(solution(), fn);
     }
     void printStats() const {  // :372-380
         std::clog << "nodes in graph: " << this->size() << "\n";
@@ -864,8 +890,8 @@ public:
         return c / 2;
     }
 
-    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246)
-    std::vector<State> solution() const {
+    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246), as node indices
+    std::vector<std::uint32_t> solutionNodes() const {
         const std::uint32_t NONE = 0xFFFFFFFFu;
         const std::size_t n = this->states_.size();
         std::vector<Distance> dist(n, std::numeric_limits<Distance>::infinity());
@@ -887,14 +913,19 @@ public:
             for (const Edge& e : adj_[u])
                 if (d + e.d < dist[e.to]) dist[e.to] = d + e.d, prev[e.to] = u, pq.push({dist[e.to], e.to});
         }
-        std::vector<State> path;
-        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(this->states_[x]);
+        std::vector<std::uint32_t> path;
+        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(x);
         std::reverse(path.begin(), path.end());
         return path;
     }
+    std::vector<State> solution() const {
+        std::vector<State> path;
+        for (std::uint32_t n : solutionNodes()) path.push_back(this->states_[n]);
+        return path;
+    }
     template <typename Fn>
-    void solution(Fn fn) const {
-        for (const State& q : solution()) fn(q);
+    void solution(Fn fn) const {  // waypoint or trajectory callback form (:196-246)
+        impl::emitRoadmapSolution(this->states_, solutionNodes(), fn);
     }
     void printStats() const {
         std::clog << "nodes in graph: " << this->size() << "\n";
@@ -1163,7 +1194,7 @@ public:
     }
     template <typename Fn>
     void solution(Fn fn) const {
-        for (const State& q : solution()) fn(q);
+        impl::emitSolution(solution(), fn);
     }
     template <typename Visitor>
     void visitGraph(Visitor&& visitor) const {
@@ -1320,7 +1351,7 @@ public:
     }
     template <typename Fn>
     void solution(Fn fn) const {
-        for (const State& q : solution()) fn(q);
+        impl::emitSolution(solution(), fn);
     }
     template <typename Visitor>
     void visitGraph(Visitor&& visitor) const {
@@ -1452,8 +1483,8 @@ public:
         for (std::uint32_t e : edgeIdx_) c += e != NONE;
         return c;
     }
-    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246)
-    std::vector<State> solution() const {
+    // shortest path over the roadmap from any start to any goal (impl/djikstras.hpp, pprm.hpp:218-246), as node indices
+    std::vector<std::uint32_t> solutionNodes() const {
         mirror();
         const std::size_t n = states_.size();
         std::vector<std::vector<std::pair<std::uint32_t, Distance>>> adj(n);
@@ -1482,14 +1513,19 @@ public:
             for (auto [v, w] : adj[u])
                 if (d + w < dist[v]) dist[v] = d + w, prev[v] = u, pq.push({dist[v], v});
         }
-        std::vector<State> path;
-        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(states_[x]);
+        std::vector<std::uint32_t> path;
+        for (std::uint32_t x = hit; x != NONE; x = prev[x]) path.push_back(x);
         std::reverse(path.begin(), path.end());
+        return path;
+    }
+    std::vector<State> solution() const {
+        std::vector<State> path;
+        for (std::uint32_t n : solutionNodes()) path.push_back(states_[n]);
         return path;
     }
     template <typename Fn>
     void solution(Fn fn) const {
-        for (const State& q : solution()) fn(q);
+        impl::emitRoadmapSolution(states_, solutionNodes(), fn);
     }
     template <typename Visitor>
     void visitGraph(Visitor&& visitor) const {  // :380-387 (each edge from both of its ends)

@@ -50,6 +50,15 @@ void testSolvingBasicScenario(const char* name) {
         ++sit;
     });
     EXPECT(sit == solution.end());
+    // the trajectory callback form (impl/link_trajectory.hpp:76-84): link() answers with a bool here, so the trajectory type
+    // is std::monostate; one call per edge of the path, consecutive, from the start to the goal
+    std::size_t edgesSeen = 0;
+    bool chained = true;
+    planner.solution([&](const State& a, const std::monostate&, const State& b, bool /*forward*/) {
+        chained = chained && edgesSeen + 1 < solution.size() && a == solution[edgesSeen] && b == solution[edgesSeen + 1];
+        ++edgesSeen;
+    });
+    EXPECT(chained && edgesSeen + 1 == solution.size());
     // every edge of the returned path re-validates on the device (stronger than the reference)
     if (solution.size() >= 2) {
         Context ctx;
