@@ -339,6 +339,15 @@ typedef struct mptg_pprm_params {
 #define MPTG_PPRM_GOAL 2u
 int mptg_pprm_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_pprm_params* params, mptg_pprm** out);
 int mptg_pprm_destroy(mptg_pprm* pprm);
+/* PPRM-IRS (src/mpt/pprm_irs.hpp:49-99; impl/pprm_irs/pprm_irs.hpp:350-368, shortest_path_check.hpp:111-225): from now on a
+ * validated edge (sample, neighbour) of length d is recorded -- as a SPARSE edge -- only if the sparse roadmap does not
+ * already join its ends by a path shorter than stretch_weight * d (Planner::setStretchWeight, default 5 in the reference);
+ * the edge rows, components, solved() and mptg_pprm_get_graph then describe the sparse roadmap.  Each new node runs the
+ * reference's bounded Dijkstra search against the roadmap as it stood when the wave began plus its own kept edges
+ * (neighbours nearest first).  Call before the first state is added.  search_capacity: nodes one search may label
+ * (0: what fits 1 GiB of working storage for a full wave, 256 .. 4096); a search that needs more fails the wave with
+ * MPTG_ERR_CAPACITY.  keep_dense_edges<true> is a host-planner option (include/mptg/planner.hpp). */
+int mptg_pprm_set_spanner(mptg_pprm* pprm, double stretch_weight, uint32_t search_capacity);
 /* Planner::addStart(state) / addGoal(state) (pprm.hpp:156-169): addSample with the start / goal mark.
  * node_out: the new node, MPTG_NO_INDEX when the state is invalid or closer than epsilon to a node. */
 int mptg_pprm_add_state(mptg_pprm* pprm, const void* state, uint32_t marks, uint32_t* node_out);

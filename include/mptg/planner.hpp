@@ -1375,7 +1375,10 @@ public:
 // Planner<Scenario, PPRM<device_resident, ...>>: the roadmap, its components and every stage of PPRM's addSample
 // (impl/pprm/pprm.hpp:298-339) stay on the GPU (mptg_pprm_*); two words come back per wave.  solution() runs the
 // reference's Dijkstra (pprm.hpp:218-246) over a host mirror fetched on demand.
-template <typename Scenario, int waveSize, int maxNodes, bool reportStats>
+// irs = true: PPRM-IRS on the device (mptg_pprm_set_spanner): the edge rows, components and solution() describe the sparse
+// roadmap of the spanner; stretch weight 5 as the reference's default (impl/pprm_irs/pprm_irs.hpp:85), setStretchWeight
+// before the first addStart / addGoal.
+template <typename Scenario, int waveSize, int maxNodes, bool reportStats, bool irs = false>
 class DevicePPRM {
     using Space = typename Scenario::Space;
     using State = typename Space::Type;
@@ -1432,6 +1435,12 @@ public:
         prm.link_step = impl::linkStepOf(scenario_), prm.seed = seed, prm.capacity = (std::uint32_t)maxNodes, prm.max_wave = (std::uint32_t)waveSize;
         check(mptg_pprm_create(ctx_.get(), geom_.get(), &prm, &pprm_), ctx_.get(), "mptg_pprm_create");
         stride_ = mptg_pprm_row_stride(pprm_);
+        if constexpr (irs) check(mptg_pprm_set_spanner(pprm_, 5.0, 0), ctx_.get(), "mptg_pprm_set_spanner");
+    }
+    // impl/pprm_irs/pprm_irs.hpp:164-166 (only with PPRMIRS<device_resident, ...>, before the first state is added)
+    void setStretchWeight(Distance w) {
+        static_assert(irs, "setStretchWeight belongs to PPRMIRS");
+        check(mptg_pprm_set_spanner(pprm_, (double)w, 0), ctx_.get(), "mptg_pprm_set_spanner");
     }
     DevicePPRM(const DevicePPRM&) = delete;
     DevicePPRM& operator=(const DevicePPRM&) = delete;
@@ -1583,8 +1592,13 @@ struct PlannerResolver<Scenario, PPRM<Options...>> {
 
 template <typename Scenario, typename... Options>
 struct PlannerResolver<Scenario, PPRMIRS<Options...>> {  // src/mpt/pprm_irs.hpp:55-72
-    using type = WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>, true,
-                          pack_bool_tag_v<keep_dense_edges, false, Options...>>;
+    static_assert(!(pack_contains_v<device_resident, Options...> && pack_bool_tag_v<keep_dense_edges, false, Options...>),
+                  "keep_dense_edges is an option of the host-driven PPRMIRS; the device-resident roadmap holds the sparse edges");
+    using type = std::conditional_t<pack_contains_v<device_resident, Options...>,
+                                    DevicePPRM<Scenario, pack_int_tag_v<wave_size, 4096, Options...>, pack_int_tag_v<max_nodes, 1 << 20, Options...>,
+                                               pack_bool_tag_v<report_stats, false, Options...>, true>,
+                                    WavePPRM<Scenario, pack_int_tag_v<wave_size, 1024, Options...>, pack_bool_tag_v<report_stats, false, Options...>, true,
+                                             pack_bool_tag_v<keep_dense_edges, false, Options...>>>;
 };
 
 }  // namespace impl

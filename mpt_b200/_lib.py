@@ -130,6 +130,7 @@ SYMBOLS = {
     "mptg_prrtstar_get_tree": (C.c_int, [_P, _U32, _U32, _P, _P, _P]),
     "mptg_pprm_create": (C.c_int, [_P, _P, _P, C.POINTER(_P)]),
     "mptg_pprm_destroy": (C.c_int, [_P]),
+    "mptg_pprm_set_spanner": (C.c_int, [_P, C.c_double, C.c_uint32]),
     "mptg_pprm_add_state": (C.c_int, [_P, _P, _U32, _U32P]),
     "mptg_pprm_wave": (C.c_int, [_P, _U32, _U32P, _U32P]),
     "mptg_pprm_size": (_U32, [_P]),

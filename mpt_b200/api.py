@@ -447,7 +447,8 @@ class DevicePPRM:
     START, GOAL = 1, 2
 
     def __init__(self, scenario: "Scenario", space: Space, lo, hi, *, goal=None, goal_radius: float = 0.0, seed: int = 1,
-                 capacity: int = 1 << 20, max_wave: int = 1 << 14, max_k: int = 0):
+                 capacity: int = 1 << 20, max_wave: int = 1 << 14, max_k: int = 0, spanner_stretch: float = 0.0, spanner_capacity: int = 0):
+        """spanner_stretch > 0: PPRM-IRS (mptg_pprm_set_spanner) -- only the sparse edges of the roadmap spanner are kept."""
         self.ctx, self.scenario, self.space = scenario.ctx, scenario, space
         self._lo, self._hi = _bounds(space, lo, hi)
         self._goal = None if goal is None else np.ascontiguousarray(goal, dtype=space.dtype).reshape(space.scalars)
@@ -455,6 +456,8 @@ class DevicePPRM:
                            float(goal_radius), float(scenario.step or 0.0), int(seed), int(capacity), int(max_wave), int(max_k))
         self.h = C.c_void_p()
         L.check(self.ctx.lib.mptg_pprm_create(self.ctx.h, scenario.h, C.byref(prm), C.byref(self.h)), self.ctx.h)
+        if spanner_stretch > 0:
+            L.check(self.ctx.lib.mptg_pprm_set_spanner(self.h, float(spanner_stretch), int(spanner_capacity)), self.ctx.h)
         self._solved = False
 
     def add_state(self, state, marks: int) -> int:

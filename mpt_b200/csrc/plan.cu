@@ -603,6 +603,143 @@ __global__ void pprmRootKernel(uint32_t* comp, uint32_t first, uint32_t count, u
     if (i < count) out[i] = pprmFind(comp, first + i);
 }
 
+// ---------------------------------------------------------------------------------------------
+// PPRM-IRS on the device (src/mpt/impl/pprm_irs/pprm_irs.hpp:350-368, shortest_path_check.hpp:111-225): of the validated
+// (sample, neighbour) edges of a wave, keep as SPARSE edges those whose ends the sparse roadmap does not already join by a
+// path shorter than stretch x the edge.  One thread per new node runs the reference's bounded Dijkstra search over the
+// roadmap as it stood when the wave began plus the node's own kept edges: neighbours nearest first, the search resumed from
+// check to check (the bound only grows), a kept edge entering it at once, stale queue entries skipped.  Path costs are the
+// left-to-right sums from the new node outwards, as Dijkstra forms them; by monotonicity of the rounded addition every
+// exact search yields the same labels, so the kept set does not depend on the order ties are settled in.
+// Working storage per node: an open-addressing table node -> best cost and a binary min-heap with lazy deletion, both
+// in global memory (cap entries / 4 cap pushes; exceeding either raises the error flag -> MPTG_ERR_CAPACITY).
+// Roadmap adjacency = the node's own row (edges to older nodes) + the reverse list through revHead / revNext (edges from
+// newer nodes; entry id = newer node * stride + slot, so an entry's neighbour is id / stride and its length edgeDist[id]).
+template <typename S>
+struct SpannerScratch {
+    uint32_t* tabNode;  // [wave][2 cap], MPTG_NO_INDEX = empty (memset before the launch)
+    S* tabCost;         // [wave][2 cap]
+    S* heapCost;        // [wave][4 cap]
+    uint32_t* heapNode; // [wave][4 cap]
+    uint32_t cap;
+};
+
+template <typename S>
+__global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, const uint32_t* __restrict__ sel, const uint32_t* __restrict__ nnIdx,
+                                  const S* __restrict__ nnDist, const uint32_t* __restrict__ nnCnt, uint8_t* __restrict__ okEdge,
+                                  const uint32_t* __restrict__ edgeIdx, const S* __restrict__ edgeDist, const uint32_t* __restrict__ revHead,
+                                  const uint32_t* __restrict__ revNext, S stretch, SpannerScratch<S> w, uint32_t* __restrict__ err) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nSel) return;
+    const uint32_t i = sel[s];
+    const uint32_t cnt = nnCnt[i] < k ? nnCnt[i] : k;
+    const uint32_t slots = 2u * w.cap, heapCap = 4u * w.cap;
+    uint32_t* tn = w.tabNode + (size_t)s * slots;
+    S* tc = w.tabCost + (size_t)s * slots;
+    S* hc = w.heapCost + (size_t)s * heapCap;
+    uint32_t* hn = w.heapNode + (size_t)s * heapCap;
+    uint32_t used = 0, heapN = 0;
+    bool overflow = false;
+    auto slotOf = [&](uint32_t node) {  // slot holding `node`, or the empty slot where it belongs
+        uint32_t h = (node * 2654435761u) & (slots - 1u);
+        while (tn[h] != MPTG_NO_INDEX && tn[h] != node) h = (h + 1u) & (slots - 1u);
+        return h;
+    };
+    auto push = [&](S c, uint32_t node) {
+        if (heapN >= heapCap) {
+            overflow = true;
+            return;
+        }
+        uint32_t x = heapN++;
+        while (x > 0) {
+            const uint32_t parent = (x - 1u) >> 1;
+            if (!(c < hc[parent])) break;
+            hc[x] = hc[parent], hn[x] = hn[parent];
+            x = parent;
+        }
+        hc[x] = c, hn[x] = node;
+    };
+    auto pop = [&]() {
+        const S c = hc[--heapN];
+        const uint32_t node = hn[heapN];
+        uint32_t x = 0;
+        for (;;) {
+            uint32_t child = 2u * x + 1u;
+            if (child >= heapN) break;
+            if (child + 1u < heapN && hc[child + 1u] < hc[child]) ++child;
+            if (!(hc[child] < c)) break;
+            hc[x] = hc[child], hn[x] = hn[child];
+            x = child;
+        }
+        if (heapN > 0) hc[x] = c, hn[x] = node;
+    };
+    auto setCost = [&](uint32_t h, uint32_t node, S c) {  // (re)label and queue
+        if (tn[h] == MPTG_NO_INDEX) {
+            if (++used > w.cap) {
+                overflow = true;
+                return;
+            }
+            tn[h] = node;
+        }
+        tc[h] = c;
+        push(c, node);
+    };
+    for (uint32_t j = 0; j < cnt && !overflow; ++j) {
+        uint8_t* flag = okEdge + (size_t)s * k + j;
+        if (!*flag) continue;
+        const uint32_t v = nnIdx[(size_t)i * k + j];
+        const S d = nnDist[(size_t)i * k + j];
+        const S target = stretch * d;  // pprm_irs.hpp:351
+        {
+            const uint32_t h = slotOf(v);
+            if (tn[h] == v && tc[h] < target) {  // shortest_path_check.hpp:133-140
+                *flag = 0;
+                continue;
+            }
+        }
+        bool found = false;
+        while (heapN > 0 && !overflow) {
+            const S priority = hc[0];
+            const uint32_t top = hn[0];
+            const S pathCost = tc[slotOf(top)];
+            if (pathCost >= target) break;  // :159-160
+            pop();
+            if (pathCost != priority) continue;  // stale: settled through a shorter path (:166-171)
+            found = top == v;
+            auto relax = [&](uint32_t nbr, S len) {
+                const S c = pathCost + len;
+                if (nbr == v && c < target) found = true;
+                const uint32_t h = slotOf(nbr);
+                if (tn[h] == nbr && !(c < tc[h])) return;
+                setCost(h, nbr, c);
+            };
+            for (uint32_t t = 0; t < stride; ++t) {  // the node's own row: edges to older nodes
+                const uint32_t nbr = edgeIdx[(size_t)top * stride + t];
+                if (nbr != MPTG_NO_INDEX) relax(nbr, edgeDist[(size_t)top * stride + t]);
+            }
+            for (uint32_t e = revHead[top]; e != MPTG_NO_INDEX; e = revNext[e]) relax(e / stride, edgeDist[e]);  // edges from newer nodes
+            if (found) break;  // :208-209
+        }
+        if (found) {
+            *flag = 0;
+            continue;
+        }
+        setCost(slotOf(v), v, d);  // a sparse edge: part of the search from here on (:219-222)
+    }
+    if (overflow) atomicOr(err, 1u);
+}
+
+// reverse lists for the sparse edges of the nodes just appended
+__global__ void pprmSpannerLinkKernel(uint32_t nSel, uint32_t stride, uint32_t size, const uint32_t* __restrict__ edgeIdx, uint32_t* revHead,
+                                      uint32_t* __restrict__ revNext) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)nSel * stride) return;
+    const uint32_t id = size + (uint32_t)(e / stride);
+    const uint32_t entry = id * stride + (uint32_t)(e % stride);
+    const uint32_t nbr = edgeIdx[entry];
+    if (nbr != MPTG_NO_INDEX) revNext[entry] = atomicExch(revHead + nbr, entry);
+}
+
 }  // namespace mptg
 
 struct mptg_pprm {
@@ -624,7 +761,12 @@ struct mptg_pprm {
     uint8_t *okValid = nullptr, *keep = nullptr, *okEdge = nullptr;
     void* selTemp = nullptr;
     size_t selBytes = 0;
-    uint32_t* host = nullptr;  // pinned: [0] selected count, [1] solved
+    uint32_t* host = nullptr;  // pinned: [0] selected count, [1] solved, [2] spanner error flag
+    // PPRM-IRS (mptg_pprm_set_spanner): stretch > 0 switches it on
+    double stretch = 0;
+    uint32_t *revHead = nullptr, *revNext = nullptr, *spanErr = nullptr, spanCap = 0;
+    void *spanTabCost = nullptr, *spanHeapCost = nullptr;
+    uint32_t *spanTabNode = nullptr, *spanHeapNode = nullptr;
 };
 
 namespace {
@@ -634,7 +776,8 @@ void pprmFree(mptg_pprm* p) {
     if (p->knn) mptg_knn_destroy(p->knn);
     for (void* q : {p->bounds, p->goal, p->nodes, p->edgeDist, (void*)p->edgeIdx, (void*)p->comp, (void*)p->lists, (void*)p->marks, p->samples,
                     p->cand, p->fresh, p->nnDist, p->from, p->to, (void*)p->nnIdx, (void*)p->nnCnt, (void*)p->sel, (void*)p->sel2, (void*)p->nSel,
-                    (void*)p->result, (void*)p->okValid, (void*)p->keep, (void*)p->okEdge, p->selTemp})
+                    (void*)p->result, (void*)p->okValid, (void*)p->keep, (void*)p->okEdge, p->selTemp, (void*)p->revHead, (void*)p->revNext,
+                    (void*)p->spanErr, p->spanTabCost, p->spanHeapCost, (void*)p->spanTabNode, (void*)p->spanHeapNode})
         cudaFree(q);
     if (p->host) cudaFreeHost(p->host);
     delete p;
@@ -711,6 +854,14 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
                                                                          (S*)p->from, (S*)p->to);
         MPTG_LAUNCHED(ctx);
         if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, (uint32_t)E, p->linkStep, p->okEdge, nullptr)) return rc;
+        if (p->stretch > 0) {  // PPRM-IRS: validated edges the spanner does not need are dropped before the rows are written
+            const size_t slots = 2 * (size_t)p->spanCap;
+            MPTG_CUDA(ctx, cudaMemsetAsync(p->spanTabNode, 0xFF, (size_t)nSel * slots * sizeof(uint32_t), st));
+            SpannerScratch<S> ws{p->spanTabNode, (S*)p->spanTabCost, (S*)p->spanHeapCost, p->spanHeapNode, p->spanCap};
+            pprmSpannerKernel<S><<<(nSel + 63) / 64, 64, 0, st>>>(nSel, k, p->stride, p->sel2, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->okEdge, p->edgeIdx,
+                                                                 (const S*)p->edgeDist, p->revHead, p->revNext, (S)p->stretch, ws, p->spanErr);
+            MPTG_LAUNCHED(ctx);
+        }
     }
     pprmAppendKernel<S><<<(nSel + 127) / 128, 128, 0, st>>>(sp, p->sel2, nSel, k, p->stride, (const S*)p->cand, p->nnIdx, (const S*)p->nnDist, p->nnCnt,
                                                           p->okEdge, p->size, p->hasGoal ? (const S*)p->goal : nullptr, (S)p->goalRadius, marks,
@@ -720,6 +871,11 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
         const size_t E = (size_t)nSel * p->stride;
         pprmUniteKernel<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(nSel, p->stride, p->size, p->edgeIdx, p->comp);
         MPTG_LAUNCHED(ctx);
+        if (p->stretch > 0) {
+            pprmSpannerLinkKernel<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(nSel, p->stride, p->size, p->edgeIdx, p->revHead, p->revNext);
+            MPTG_LAUNCHED(ctx);
+            MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 2, p->spanErr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        }
     }
     pprmSolvedKernel<<<1, 256, 0, st>>>(p->comp, p->lists, p->result);
     MPTG_LAUNCHED(ctx);
@@ -728,6 +884,8 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
     if (int rc = mptg_knn_insert_dev(p->knn, p->fresh, nSel, &first)) return rc;  // :337
     if (first != p->size) return fail(ctx, MPTG_ERR_CUDA, "mptg_pprm: node numbering out of step");
     MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (p->stretch > 0 && n > 0 && p->host[2])
+        return fail(ctx, MPTG_ERR_CAPACITY, "mptg_pprm: a spanner search left its working storage (%u nodes per new node); edges may be missing", p->spanCap);
     if (p->host[1]) p->solved = true;
     p->size += nSel;
     *addedOut = nSel;
@@ -781,12 +939,48 @@ int mptg_pprm_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_pprm_params* prm
     }
     if (!rc) rc = memsetSync(ctx, p->lists, 0, (2 + 64 + 4096) * 4);
     if (!rc) rc = memsetSync(ctx, p->result, 0, 4);
-    if (!rc && cudaMallocHost((void**)&p->host, 2 * sizeof(uint32_t)) != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_create: pinned allocation failed");
+    if (!rc && cudaMallocHost((void**)&p->host, 4 * sizeof(uint32_t)) != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_create: pinned allocation failed");
     if (rc) {
         pprmFree(p);
         return rc;
     }
     *out = p;
+    return MPTG_OK;
+}
+
+int mptg_pprm_set_spanner(mptg_pprm* p, double stretch_weight, uint32_t search_capacity) {
+    if (!p || !(stretch_weight > 0)) return fail(p ? p->ctx : nullptr, MPTG_ERR_BAD_ARG, "mptg_pprm_set_spanner: bad argument");
+    if (p->size != 0 && p->stretch == 0) return fail(p->ctx, MPTG_ERR_BAD_ARG, "mptg_pprm_set_spanner: the roadmap already holds nodes added without the spanner");
+    mptg_ctx* ctx = p->ctx;
+    MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->revHead) {
+        // working storage: 72 (double) / 56 (float) bytes per search entry; default = what fits 1 GiB for a full wave, within [256, 4096]
+        uint32_t cap = search_capacity;
+        if (cap == 0) {
+            const size_t per = 2 * (4 + (size_t)p->scalar) + 4 * (4 + (size_t)p->scalar);
+            size_t fit = ((size_t)1 << 30) / (per * p->maxWave);
+            cap = (uint32_t)(fit < 256 ? 256 : (fit > 4096 ? 4096 : fit));
+        }
+        uint32_t pow2 = 64;
+        while (pow2 < cap) pow2 <<= 1;  // the table's size is a power of two
+        cap = pow2;
+        const size_t W = p->maxWave;
+        int rc = MPTG_OK;
+        auto alloc = [&](auto** q, size_t bytes) {
+            if (rc) return;
+            cudaError_t e = cudaMalloc((void**)q, bytes ? bytes : 16);
+            if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_set_spanner: %s", cudaGetErrorString(e));
+        };
+        alloc(&p->revHead, (size_t)p->capacity * 4), alloc(&p->revNext, (size_t)p->capacity * p->stride * 4), alloc(&p->spanErr, 4);
+        alloc(&p->spanTabNode, W * 2 * cap * 4), alloc(&p->spanTabCost, W * 2 * cap * p->scalar);
+        alloc(&p->spanHeapNode, W * 4 * cap * 4), alloc(&p->spanHeapCost, W * 4 * cap * p->scalar);
+        if (!rc) rc = memsetSync(ctx, p->revHead, 0xFF, (size_t)p->capacity * 4);
+        if (!rc) rc = memsetSync(ctx, p->spanErr, 0, 4);
+        if (rc) return rc;
+        p->spanCap = cap;
+        p->host[2] = 0;
+    }
+    p->stretch = stretch_weight;
     return MPTG_OK;
 }
 

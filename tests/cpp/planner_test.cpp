@@ -307,6 +307,8 @@ int main() {
     }
     static_assert(!std::is_same_v<Planner<S, PPRM<device_resident>>, Planner<S, PPRM<>>>);
     testSolvingBasicScenario<PPRM<device_resident, report_stats<true>, wave_size<512>, max_nodes<(1 << 16)>>>("PPRM device-resident");
+    static_assert(!std::is_same_v<Planner<S, PPRMIRS<device_resident>>, Planner<S, PPRM<device_resident>>>);
+    testSolvingBasicScenario<PPRMIRS<device_resident, wave_size<512>, max_nodes<(1 << 16)>>>("PPRM-IRS device-resident");
 #endif
     testPRRTStarInvariants();
     // error behaviour (impl/prrt/prrt.hpp:197-198, impl/pprm/pprm.hpp:179-180)

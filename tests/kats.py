@@ -148,9 +148,42 @@ def pprm_k(space, n):
     return max(1, int(np.ceil((e + e / dt(space.dimensions)) * dt(math.log(n + 1.0)))))
 
 
-def replay_pprm(oracle, og, sp, lo, hi, starts, goals, goal, goal_radius, seed, waves, W, stride):
+def spanner_keeps(adj, kept, v, target, state):
+    """ShortestPathCheck::operator() (src/mpt/impl/pprm_irs/shortest_path_check.hpp:111-225) for the node being added: True
+    when no path of sparse edges to `v` is shorter than `target`.  adj: node -> [(neighbour, length)] of the roadmap before
+    the wave; state = (cost dict, heap list) of the search, resumed from check to check; kept edges enter it at once."""
+    import heapq
+
+    cost, heap = state
+    if v in cost and cost[v] < target:
+        return False
+    while heap:
+        priority, top = heap[0]
+        path_cost = cost[top]
+        if path_cost >= target:
+            break
+        heapq.heappop(heap)
+        if path_cost != priority:
+            continue
+        found = top == v
+        for nbr, length in adj.get(top, ()):
+            c = path_cost + length  # numpy scalar of the space's type: rounded as the device rounds it
+            if nbr == v and c < target:
+                found = True
+            if nbr in cost and not (c < cost[nbr]):
+                continue
+            cost[nbr] = c
+            heapq.heappush(heap, (c, nbr))
+        if found:
+            return False
+    return True
+
+
+def replay_pprm(oracle, og, sp, lo, hi, starts, goals, goal, goal_radius, seed, waves, W, stride, spanner_stretch=None):
     """PPRM's Worker::addSample (src/mpt/impl/pprm/pprm.hpp:298-339) on the oracle, one wave at a time, on the same
-    samples: -> (states, edge rows [n, stride] of neighbour indices, edge distances, marks)."""
+    samples: -> (states, edge rows [n, stride] of neighbour indices, edge distances, marks).  spanner_stretch: PPRM-IRS
+    (impl/pprm_irs/pprm_irs.hpp:300-368) -- a validated edge is recorded only if the spanner needs it, every sample of a wave
+    judged against the sparse roadmap as it stood when the wave began plus its own kept edges (mptg_pprm_set_spanner)."""
     D = sp.scalars
     states = np.empty((0, D), dtype=sp.dtype)
     rows_i, rows_d, marks = [], [], []
@@ -167,12 +200,30 @@ def replay_pprm(oracle, og, sp, lo, hi, starts, goals, goal, goal_radius, seed, 
             idx, dist, cnt = oracle.knn(sp, states, cand, k)
             keep = ~((cnt > 0) & (dist[:, 0] < np.finfo(sp.dtype).eps))
             cand, idx, dist, cnt = cand[keep], idx[keep], dist[keep], cnt[keep]
+        adj = {}
+        if spanner_stretch is not None and n > 0:  # the sparse roadmap before this wave, both directions
+            for r, row in enumerate(rows_i):
+                for t in np.nonzero(row != NO_INDEX)[0]:
+                    adj.setdefault(r, []).append((int(row[t]), rows_d[r][t]))
+                    adj.setdefault(int(row[t]), []).append((r, rows_d[r][t]))
         for s in range(cand.shape[0]):
             ri = np.full(stride, NO_INDEX, dtype=np.uint32)
             rd = np.zeros(stride, dtype=sp.dtype)
             if n > 0 and cnt[s] > 0:
                 c = int(cnt[s])
                 ok = og.link(np.repeat(cand[s:s + 1], c, axis=0), states[idx[s, :c]]) != 0
+                if spanner_stretch is not None:
+                    search = ({}, [])
+                    for j in range(c):
+                        if not ok[j]:
+                            continue
+                        v, d = int(idx[s, j]), dist[s, j]
+                        if spanner_keeps(adj, None, v, sp.dtype(spanner_stretch) * d, search):
+                            import heapq
+                            search[0][v] = d
+                            heapq.heappush(search[1], (d, v))
+                        else:
+                            ok[j] = False
                 ri[:c][ok] = idx[s, :c][ok]
                 rd[:c][ok] = dist[s, :c][ok]
             mk = forced

@@ -722,14 +722,15 @@ def test_device_planner_argument_errors(ctx):
     pp.close()
 
 
-def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W):
-    pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W)
+def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W, spanner_stretch=None):
+    pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W,
+                      spanner_stretch=spanner_stretch or 0.0)
     assert pl.add_start(start) == 0 and pl.add_goal(goal) == 1
     assert pl.add_goal(goal) == m.NO_INDEX  # closer than epsilon to a node: rejected (pprm.hpp:306-308)
     for _ in range(waves):
         pl.wave(W)
     st, ei, ed, mk, cp = pl.graph()
-    ws, wi, wd, wm = kats.replay_pprm(oracle, og, sp, lo, hi, [start], [goal], goal, goal_radius, seed, waves, W, pl.row_stride)
+    ws, wi, wd, wm = kats.replay_pprm(oracle, og, sp, lo, hi, [start], [goal], goal, goal_radius, seed, waves, W, pl.row_stride, spanner_stretch)
     assert pl.samples_drawn == waves * W and st.shape[0] > 100
     assert np.array_equal(st, ws) and np.array_equal(ei, wi) and np.array_equal(ed, wd) and np.array_equal(mk, wm)
     # components: same partition as a host union-find over the same edges; solved() <=> start and goal connected
@@ -764,6 +765,31 @@ def test_device_pprm_replays_the_reference_loop(ctx, oracle):
     cand = W.box_states(256, 8, 3, -np.pi, np.pi)
     free8 = cand[oarm.valid(cand) != 0]
     _check_device_pprm(ctx, oracle, sp8, arm, oarm, -np.pi, np.pi, free8[0], free8[1], 1e-6, 11, 4, 200)
+
+
+def test_device_pprm_irs_replays_the_reference_spanner(ctx, oracle):
+    """PPRM-IRS on the device (mptg_pprm_set_spanner): the SPARSE roadmap after every wave equals the one the reference's
+    addSample / addEdge / ShortestPathCheck build on the oracle from the same samples (impl/pprm_irs/pprm_irs.hpp:300-368,
+    shortest_path_check.hpp:111-225) -- states, sparse edge rows, distances, marks, components, solved(); waves of one sample
+    (the reference's own order of events) and of 128 / 200 samples; stretch 5 (the default) and 2."""
+    occ = W.synthetic_grid(500, 400, seed=2)
+    sp = m.lp_space(2, 2, m.F64)
+    free = np.argwhere(occ == 0)
+    start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
+    grid, ogrid = m.Scenario.grid(ctx, occ, m.F64), oracle.grid(occ)
+    lo, hi = [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1]
+    n1, e1 = _check_device_pprm(ctx, oracle, sp, grid, ogrid, lo, hi, start, goal, 1e-6, 5, 300, 1, spanner_stretch=5.0)
+    n2, e2 = _check_device_pprm(ctx, oracle, sp, grid, ogrid, lo, hi, start, goal, 1e-6, 5, 6, 128, spanner_stretch=5.0)
+    n3, e3 = _check_device_pprm(ctx, oracle, sp, grid, ogrid, lo, hi, start, goal, 1e-6, 5, 6, 128, spanner_stretch=2.0)
+    n0, e0 = _check_device_pprm(ctx, oracle, sp, grid, ogrid, lo, hi, start, goal, 1e-6, 5, 6, 128)
+    assert n0 == n2 == n3 and e2 < e3 < e0 and e2 < 4 * n2  # the spanner is sparse; a smaller stretch keeps more
+    print(f"PPRM-IRS device: {n2} nodes, sparse edges {e2} (stretch 5) / {e3} (stretch 2) of {e0} valid ones; one-sample waves {n1} nodes, {e1} edges")
+    lengths, radius, circles = W.link_arm_scene(8)
+    sp8 = m.lp_space(8, 1, m.F64)
+    arm, oarm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64), oracle.link_arm(lengths, radius, circles)
+    cand = W.box_states(256, 8, 3, -np.pi, np.pi)
+    free8 = cand[oarm.valid(cand) != 0]
+    _check_device_pprm(ctx, oracle, sp8, arm, oarm, -np.pi, np.pi, free8[0], free8[1], 1e-6, 11, 4, 200, spanner_stretch=5.0)
 
 
 # ------------------------------------------------------------------ grid / shapes / link arm

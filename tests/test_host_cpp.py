@@ -69,7 +69,7 @@ def test_wave_planners_on_gpu():
         build_host.build()
     out = _run(prog)
     for name in ("PRRT on the Nao-cup scenario:", "PRRT* on the Nao-cup scenario:", "PPRM-IRS:", "PPRM-IRS keep_dense_edges, wave 64:", "PPRM-IRS spanner:",
-                 "PRRT:", "PRRT device-resident:", "PRRT* device-resident:", "PRRT* device-resident r-nearest:", "PRRT* device-resident invariants:", "PPRM device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
+                 "PRRT:", "PRRT device-resident:", "PPRM-IRS device-resident:", "PRRT* device-resident:", "PRRT* device-resident r-nearest:", "PRRT* device-resident invariants:", "PPRM device-resident:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PRRT* invariants:"):
         assert f"PASS {name}" in out
 
 
