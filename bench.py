@@ -637,6 +637,23 @@ def secondary(ctx, torch, dev, stream):
         ref_arm = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1])
         if ref_arm:
             out[f"reference_planner_cpu_arm{n_links}"] = ref_arm
+        if n_links == 8:  # PPRM-IRS: the same waves with the spanner's bounded search per new node on the device
+            pp = m.DevicePPRM(arm, spn, -np.pi, np.pi, seed=23, capacity=1 << 18, max_wave=4096, spanner_stretch=5.0)
+            pp.add_start(cand[ok][0])
+            pp.add_goal(cand[ok][1])
+            pp.wave(4096)
+            ctx.sync()
+            t0, n0 = time.perf_counter(), pp.size
+            while pp.size < 100_000:
+                pp.wave(4096)
+            dt = time.perf_counter() - t0
+            ei = pp.graph(n0, pp.size - n0)[1]
+            out["device_pprm_irs_arm8"] = {"nodes_per_s": (pp.size - n0) / dt, "nodes": pp.size, "sparse_edges": int((ei != m.NO_INDEX).sum()), "solved": pp.solved(), "s": dt,
+                                           "stretch": 5.0, "timing": "wall clock, one run"}
+            pp.close()
+            ref_irs = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1], algo="pprmirs")
+            if ref_irs:
+                out["reference_planner_cpu_irs_arm8"] = ref_irs
     # BASELINE configs[3] as a PLANNING problem (the scene above connects start and goal almost directly): rings of
     # circles with narrow gaps, W.link_arm_passage_scene -- time and roadmap size to the first solution, ours and the reference's
     for n_links in (8, 16):
@@ -712,7 +729,7 @@ def reference_planner_cpu(occ, start, goal, goal_radius, prrt_range, nodes=200_0
     return out
 
 
-def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_000, time_ms=6000, threads=None):
+def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_000, time_ms=6000, threads=None, algo="pprm"):
     """The reference's own multi-threaded PPRM (BASELINE configs[3]) on the reference's LinkManipulatorScenario<double, N>
     (demo/link_manipulator_scenario.hpp), N = 8 or 16, on this box's host cores.  Same program and caveats as
     reference_planner_cpu."""
@@ -732,7 +749,7 @@ def reference_planner_cpu_arm(lengths, radius, circles, start, goal, nodes=30_00
         env = dict(os.environ)
         env["OMP_NUM_THREADS"] = str(threads or os.cpu_count() or 1)
         try:
-            r = subprocess.run([str(prog), "--arm", f.name, "--algo", "pprm", "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "23"]
+            r = subprocess.run([str(prog), "--arm", f.name, "--algo", algo, "--nodes", str(nodes), "--time-ms", str(time_ms), "--seed", "23"]
                                + (["--threads", str(threads)] if threads else []),
                                capture_output=True, text=True, timeout=time_ms / 1e3 + 60, env=env)
             return json.loads(r.stdout.strip().splitlines()[-1])

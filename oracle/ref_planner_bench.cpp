@@ -9,7 +9,7 @@
 //
 // usage: ref_planner_bench --map file.pgm --start X Y --goal X Y [--goal-radius R] [--range R] [--algo prrt|prrtstar]
 //                          [--threads N] [--nodes N] [--time-ms T] [--seed S]
-//        ref_planner_bench --arm scene.txt --algo pprm|prrtstar [--threads N] [--nodes N] [--time-ms T] [--seed S]
+//        ref_planner_bench --arm scene.txt --algo pprm|pprmirs|prrtstar [--threads N] [--nodes N] [--time-ms T] [--seed S]
 //            (the reference's LinkManipulatorScenario<double, N>, N = 8 or 16; scene.txt: N radius / N lengths /
 //             C / C lines "cx cy r" / start (N angles) / goal (N angles))
 // Phase 1 runs until the first solution (or the node / time limit); phase 2 continues to the node / time limit.
@@ -40,6 +40,7 @@
 #include <mpt/planner.hpp>
 #include <mpt/prrt.hpp>
 #include <mpt/pprm.hpp>
+#include <mpt/pprm_irs.hpp>
 #include <mpt/prrt_star.hpp>
 
 #include <link_manipulator_scenario.hpp>
@@ -149,7 +150,7 @@ int runArm(const Options& o, const char* algoName) {
     Scenario scenario(goal, circles, lengths, radius);
     mpt::Planner<Scenario, AlgoT<>> planner(scenario, o.seed);
     planner.addStart(start);
-    if constexpr (std::is_same_v<AlgoT<>, mpt::PPRM<>>) planner.addGoal(goal);
+    if constexpr (std::is_same_v<AlgoT<>, mpt::PPRM<>> || std::is_same_v<AlgoT<>, mpt::PPRMIRS<>>) planner.addGoal(goal);
     const auto t0 = Clock::now();
     auto elapsed = [&] { return std::chrono::duration<double>(Clock::now() - t0).count(); };
     planner.solve([&] { return planner.solved() || planner.size() >= o.nodes || elapsed() * 1e3 >= o.timeMs; });
@@ -194,8 +195,9 @@ int main(int argc, char** argv) {
         f >> n;
         int rc = 2;
         if (o.algo == "pprm") rc = n == 8 ? runArm<8, mpt::PPRM>(o, "pprm") : n == 16 ? runArm<16, mpt::PPRM>(o, "pprm") : 2;
+        else if (o.algo == "pprmirs") rc = n == 8 ? runArm<8, mpt::PPRMIRS>(o, "pprmirs") : n == 16 ? runArm<16, mpt::PPRMIRS>(o, "pprmirs") : 2;
         else if (o.algo == "prrtstar") rc = n == 8 ? runArm<8, mpt::PRRTStar>(o, "prrtstar") : n == 16 ? runArm<16, mpt::PRRTStar>(o, "prrtstar") : 2;
-        if (rc == 2) std::fprintf(stderr, "cannot run the arm scene %s (N = 8 or 16; algo pprm or prrtstar)\n", o.arm.c_str());
+        if (rc == 2) std::fprintf(stderr, "cannot run the arm scene %s (N = 8 or 16; algo pprm, pprmirs or prrtstar)\n", o.arm.c_str());
         return rc;
     }
     int w = 0, h = 0;
