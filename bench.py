@@ -340,7 +340,7 @@ def run_ours(args):
     assert np.array_equal(h_idx.numpy().view(np.uint32), p_idx) and np.array_equal(h_ok.numpy(), p_ok), "pinned and pageable results differ"
 
     extra = {}
-    if rank == 0 and not args.no_secondary:
+    if rank == 0 and world == 1 and not args.no_secondary:  # one-GPU figures: not repeated while the other ranks of a larger run wait
         extra["secondary"] = secondary(ctx, torch, dev, stream)
     if world > 1:
         extra["replicated_tree"] = bench_replicated_tree(args, ctx, sp, tree, dev, stream, world, rank)
@@ -637,23 +637,52 @@ def secondary(ctx, torch, dev, stream):
         ref_arm = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1])
         if ref_arm:
             out[f"reference_planner_cpu_arm{n_links}"] = ref_arm
-        if n_links == 8:  # PPRM-IRS: the same waves with the spanner's bounded search per new node on the device
-            pp = m.DevicePPRM(arm, spn, -np.pi, np.pi, seed=23, capacity=1 << 18, max_wave=4096, spanner_stretch=5.0)
+        if n_links == 8:  # PPRM-IRS: the same waves with the spanner's bounded search per new node on the device.
+            # In 8 dimensions a ball of 5 x the neighbour distance holds most of the roadmap, so a search that KEEPS an edge
+            # labels most nodes (for the reference as for us): small roadmap, short waves
+            pp = m.DevicePPRM(arm, spn, -np.pi, np.pi, seed=23, capacity=1 << 15, max_wave=512, spanner_stretch=5.0)
             pp.add_start(cand[ok][0])
             pp.add_goal(cand[ok][1])
-            pp.wave(4096)
+            pp.wave(512)
             ctx.sync()
             t0, n0 = time.perf_counter(), pp.size
-            while pp.size < 100_000:
-                pp.wave(4096)
+            while pp.size < 8_000 and time.perf_counter() - t0 < 20.0:
+                pp.wave(512)
             dt = time.perf_counter() - t0
             ei = pp.graph(n0, pp.size - n0)[1]
             out["device_pprm_irs_arm8"] = {"nodes_per_s": (pp.size - n0) / dt, "nodes": pp.size, "sparse_edges": int((ei != m.NO_INDEX).sum()), "solved": pp.solved(), "s": dt,
                                            "stretch": 5.0, "timing": "wall clock, one run"}
             pp.close()
-            ref_irs = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1], algo="pprmirs")
+            ref_irs = reference_planner_cpu_arm(lengths, radius, circles, cand[ok][0], cand[ok][1], nodes=8_000, time_ms=20000, algo="pprmirs")
             if ref_irs:
                 out["reference_planner_cpu_irs_arm8"] = ref_irs
+    # PPRM-IRS where the spanner's searches are local: the PNG-size occupancy grid (planar L2)
+    pp = m.DevicePPRM(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], seed=23, capacity=1 << 18, max_wave=4096, spanner_stretch=5.0)
+    pp.add_start(start)
+    pp.add_goal(goal)
+    pp.wave(4096)
+    ctx.sync()
+    t0, n0 = time.perf_counter(), pp.size
+    while pp.size < 100_000:
+        pp.wave(4096)
+    dt = time.perf_counter() - t0
+    ei = pp.graph(n0, pp.size - n0)[1]
+    out["device_pprm_irs_grid"] = {"nodes_per_s": (pp.size - n0) / dt, "nodes": pp.size, "sparse_edges_per_node": float((ei != m.NO_INDEX).sum()) / (pp.size - n0),
+                                   "solved": pp.solved(), "s": dt, "stretch": 5.0, "timing": "wall clock, one run"}
+    pp.close()
+    pp = m.DevicePPRM(grid, m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], seed=23, capacity=1 << 18, max_wave=4096)
+    pp.add_start(start)
+    pp.add_goal(goal)
+    pp.wave(4096)
+    ctx.sync()
+    t0, n0 = time.perf_counter(), pp.size
+    while pp.size < 100_000:
+        pp.wave(4096)
+    dt = time.perf_counter() - t0
+    ei = pp.graph(n0, pp.size - n0)[1]
+    out["device_pprm_grid"] = {"nodes_per_s": (pp.size - n0) / dt, "nodes": pp.size, "edges_per_node": float((ei != m.NO_INDEX).sum()) / (pp.size - n0), "solved": pp.solved(),
+                               "s": dt, "timing": "wall clock, one run"}
+    pp.close()
     # BASELINE configs[3] as a PLANNING problem (the scene above connects start and goal almost directly): rings of
     # circles with narrow gaps, W.link_arm_passage_scene -- time and roadmap size to the first solution, ours and the reference's
     for n_links in (8, 16):

@@ -344,9 +344,11 @@ int mptg_pprm_destroy(mptg_pprm* pprm);
  * already join its ends by a path shorter than stretch_weight * d (Planner::setStretchWeight, default 5 in the reference);
  * the edge rows, components, solved() and mptg_pprm_get_graph then describe the sparse roadmap.  Each new node runs the
  * reference's bounded Dijkstra search against the roadmap as it stood when the wave began plus its own kept edges
- * (neighbours nearest first).  Call before the first state is added.  search_capacity: nodes one search may label
- * (0: what fits 1 GiB of working storage for a full wave, 256 .. 4096); a search that needs more fails the wave with
- * MPTG_ERR_CAPACITY.  keep_dense_edges<true> is a host-planner option (include/mptg/planner.hpp). */
+ * (neighbours nearest first).  Call before the first state is added.  search_capacity: nodes one search may label at
+ * first (0: what fits 1 GiB of working storage for a full wave, 256 .. 4096); a wave in which a search needs more is run
+ * again with four times the storage (up to one entry per node of `capacity` and 32 GiB in all -- in spaces of many
+ * dimensions a search within stretch_weight * d reaches most of the roadmap, for the reference as for this library),
+ * beyond that the wave fails with MPTG_ERR_CAPACITY.  keep_dense_edges<true> is a host-planner option (planner.hpp). */
 int mptg_pprm_set_spanner(mptg_pprm* pprm, double stretch_weight, uint32_t search_capacity);
 /* Planner::addStart(state) / addGoal(state) (pprm.hpp:156-169): addSample with the start / goal mark.
  * node_out: the new node, MPTG_NO_INDEX when the state is invalid or closer than epsilon to a node. */

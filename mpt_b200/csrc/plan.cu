@@ -765,6 +765,7 @@ struct mptg_pprm {
     // PPRM-IRS (mptg_pprm_set_spanner): stretch > 0 switches it on
     double stretch = 0;
     uint32_t *revHead = nullptr, *revNext = nullptr, *spanErr = nullptr, spanCap = 0;
+    uint8_t* okEdgeRaw = nullptr;  // the edge batch's answers before the spanner stage (a search that outgrows its storage is rerun)
     void *spanTabCost = nullptr, *spanHeapCost = nullptr;
     uint32_t *spanTabNode = nullptr, *spanHeapNode = nullptr;
 };
@@ -777,7 +778,7 @@ void pprmFree(mptg_pprm* p) {
     for (void* q : {p->bounds, p->goal, p->nodes, p->edgeDist, (void*)p->edgeIdx, (void*)p->comp, (void*)p->lists, (void*)p->marks, p->samples,
                     p->cand, p->fresh, p->nnDist, p->from, p->to, (void*)p->nnIdx, (void*)p->nnCnt, (void*)p->sel, (void*)p->sel2, (void*)p->nSel,
                     (void*)p->result, (void*)p->okValid, (void*)p->keep, (void*)p->okEdge, p->selTemp, (void*)p->revHead, (void*)p->revNext,
-                    (void*)p->spanErr, p->spanTabCost, p->spanHeapCost, (void*)p->spanTabNode, (void*)p->spanHeapNode})
+                    (void*)p->spanErr, p->spanTabCost, p->spanHeapCost, (void*)p->spanTabNode, (void*)p->spanHeapNode, (void*)p->okEdgeRaw})
         cudaFree(q);
     if (p->host) cudaFreeHost(p->host);
     delete p;
@@ -809,6 +810,39 @@ int selectFlagged(mptg_pprm* p, const uint8_t* flags, uint32_t n, T* out, uint32
     MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *countHost = p->host[0];
     return MPTG_OK;
+}
+
+// (re)allocate the spanner's search storage for `cap` labelled nodes per new node (rounded up to a power of two)
+int spannerScratch(mptg_pprm* p, uint32_t cap) {
+    mptg_ctx* ctx = p->ctx;
+    uint32_t pow2 = 64;
+    while (pow2 < cap) pow2 <<= 1;
+    MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (void** q : {(void**)&p->spanTabNode, &p->spanTabCost, (void**)&p->spanHeapNode, &p->spanHeapCost}) {
+        if (*q) cudaFree(*q);
+        *q = nullptr;
+    }
+    const size_t W = p->maxWave;
+    const size_t bytes[4] = {W * 2 * pow2 * 4, W * 2 * pow2 * (size_t)p->scalar, W * 4 * pow2 * 4, W * 4 * pow2 * (size_t)p->scalar};
+    void** dst[4] = {(void**)&p->spanTabNode, &p->spanTabCost, (void**)&p->spanHeapNode, &p->spanHeapCost};
+    for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaMalloc(dst[i], bytes[i]);
+        if (e != cudaSuccess) return fail(ctx, MPTG_ERR_OOM, "PPRM-IRS search storage (%u nodes per new node, %zu MiB): %s", pow2, (bytes[0] + bytes[1] + bytes[2] + bytes[3]) >> 20,
+                                          cudaGetErrorString(e));
+    }
+    p->spanCap = pow2;
+    return MPTG_OK;
+}
+// four times the storage, at most one entry per node the roadmap can hold and 32 GiB in all
+int spannerGrow(mptg_pprm* p) {
+    uint32_t limit = 64;
+    while (limit < p->capacity) limit <<= 1;
+    const size_t per = 6 * (4 + (size_t)p->scalar);
+    while ((size_t)limit * per * p->maxWave > ((size_t)32 << 30) && limit > 64) limit >>= 1;
+    if (p->spanCap >= limit)
+        return fail(p->ctx, MPTG_ERR_CAPACITY, "mptg_pprm: a spanner search labelled more than %u nodes (the limit for waves of %u samples); use smaller waves", p->spanCap, p->maxWave);
+    const uint32_t next = p->spanCap > limit / 4 ? limit : p->spanCap * 4;
+    return spannerScratch(p, next);
 }
 
 // Worker::addSample for the W states in p->samples (pprm.hpp:298-339); marks: start / goal marks forced on them
@@ -855,12 +889,22 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
         MPTG_LAUNCHED(ctx);
         if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, (uint32_t)E, p->linkStep, p->okEdge, nullptr)) return rc;
         if (p->stretch > 0) {  // PPRM-IRS: validated edges the spanner does not need are dropped before the rows are written
-            const size_t slots = 2 * (size_t)p->spanCap;
-            MPTG_CUDA(ctx, cudaMemsetAsync(p->spanTabNode, 0xFF, (size_t)nSel * slots * sizeof(uint32_t), st));
-            SpannerScratch<S> ws{p->spanTabNode, (S*)p->spanTabCost, (S*)p->spanHeapCost, p->spanHeapNode, p->spanCap};
-            pprmSpannerKernel<S><<<(nSel + 63) / 64, 64, 0, st>>>(nSel, k, p->stride, p->sel2, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->okEdge, p->edgeIdx,
-                                                                 (const S*)p->edgeDist, p->revHead, p->revNext, (S)p->stretch, ws, p->spanErr);
-            MPTG_LAUNCHED(ctx);
+            MPTG_CUDA(ctx, cudaMemcpyAsync(p->okEdgeRaw, p->okEdge, E, cudaMemcpyDeviceToDevice, st));
+            for (;;) {
+                const size_t slots = 2 * (size_t)p->spanCap;
+                MPTG_CUDA(ctx, cudaMemsetAsync(p->spanTabNode, 0xFF, (size_t)nSel * slots * sizeof(uint32_t), st));
+                SpannerScratch<S> ws{p->spanTabNode, (S*)p->spanTabCost, (S*)p->spanHeapCost, p->spanHeapNode, p->spanCap};
+                pprmSpannerKernel<S><<<(nSel + 63) / 64, 64, 0, st>>>(nSel, k, p->stride, p->sel2, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->okEdge,
+                                                                     p->edgeIdx, (const S*)p->edgeDist, p->revHead, p->revNext, (S)p->stretch, ws, p->spanErr);
+                MPTG_LAUNCHED(ctx);
+                MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 2, p->spanErr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+                if (!p->host[2]) break;
+                // some search outgrew its table or heap: nothing has been written to the roadmap yet -- more storage, same wave again
+                if (int rc = spannerGrow(p)) return rc;
+                MPTG_CUDA(ctx, cudaMemcpyAsync(p->okEdge, p->okEdgeRaw, E, cudaMemcpyDeviceToDevice, st));
+                MPTG_CUDA(ctx, cudaMemsetAsync(p->spanErr, 0, sizeof(uint32_t), st));
+            }
         }
     }
     pprmAppendKernel<S><<<(nSel + 127) / 128, 128, 0, st>>>(sp, p->sel2, nSel, k, p->stride, (const S*)p->cand, p->nnIdx, (const S*)p->nnDist, p->nnCnt,
@@ -874,7 +918,6 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
         if (p->stretch > 0) {
             pprmSpannerLinkKernel<<<(unsigned)((E + 127) / 128), 128, 0, st>>>(nSel, p->stride, p->size, p->edgeIdx, p->revHead, p->revNext);
             MPTG_LAUNCHED(ctx);
-            MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 2, p->spanErr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         }
     }
     pprmSolvedKernel<<<1, 256, 0, st>>>(p->comp, p->lists, p->result);
@@ -884,8 +927,6 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
     if (int rc = mptg_knn_insert_dev(p->knn, p->fresh, nSel, &first)) return rc;  // :337
     if (first != p->size) return fail(ctx, MPTG_ERR_CUDA, "mptg_pprm: node numbering out of step");
     MPTG_CUDA(ctx, cudaStreamSynchronize(st));
-    if (p->stretch > 0 && n > 0 && p->host[2])
-        return fail(ctx, MPTG_ERR_CAPACITY, "mptg_pprm: a spanner search left its working storage (%u nodes per new node); edges may be missing", p->spanCap);
     if (p->host[1]) p->solved = true;
     p->size += nSel;
     *addedOut = nSel;
@@ -954,17 +995,14 @@ int mptg_pprm_set_spanner(mptg_pprm* p, double stretch_weight, uint32_t search_c
     mptg_ctx* ctx = p->ctx;
     MPTG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!p->revHead) {
-        // working storage: 72 (double) / 56 (float) bytes per search entry; default = what fits 1 GiB for a full wave, within [256, 4096]
+        // working storage: 72 (double) / 48 (float) bytes per search entry; default = what fits 1 GiB for a full wave, within
+        // [256, 4096]; a wave whose searches outgrow it is rerun with four times as much (spannerGrow)
         uint32_t cap = search_capacity;
         if (cap == 0) {
             const size_t per = 2 * (4 + (size_t)p->scalar) + 4 * (4 + (size_t)p->scalar);
             size_t fit = ((size_t)1 << 30) / (per * p->maxWave);
             cap = (uint32_t)(fit < 256 ? 256 : (fit > 4096 ? 4096 : fit));
         }
-        uint32_t pow2 = 64;
-        while (pow2 < cap) pow2 <<= 1;  // the table's size is a power of two
-        cap = pow2;
-        const size_t W = p->maxWave;
         int rc = MPTG_OK;
         auto alloc = [&](auto** q, size_t bytes) {
             if (rc) return;
@@ -972,12 +1010,11 @@ int mptg_pprm_set_spanner(mptg_pprm* p, double stretch_weight, uint32_t search_c
             if (e != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_pprm_set_spanner: %s", cudaGetErrorString(e));
         };
         alloc(&p->revHead, (size_t)p->capacity * 4), alloc(&p->revNext, (size_t)p->capacity * p->stride * 4), alloc(&p->spanErr, 4);
-        alloc(&p->spanTabNode, W * 2 * cap * 4), alloc(&p->spanTabCost, W * 2 * cap * p->scalar);
-        alloc(&p->spanHeapNode, W * 4 * cap * 4), alloc(&p->spanHeapCost, W * 4 * cap * p->scalar);
+        alloc(&p->okEdgeRaw, (size_t)p->maxWave * p->stride);
         if (!rc) rc = memsetSync(ctx, p->revHead, 0xFF, (size_t)p->capacity * 4);
         if (!rc) rc = memsetSync(ctx, p->spanErr, 0, 4);
+        if (!rc) rc = spannerScratch(p, cap);
         if (rc) return rc;
-        p->spanCap = cap;
         p->host[2] = 0;
     }
     p->stretch = stretch_weight;

@@ -722,9 +722,9 @@ def test_device_planner_argument_errors(ctx):
     pp.close()
 
 
-def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W, spanner_stretch=None):
+def _check_device_pprm(ctx, oracle, sp, sc, og, lo, hi, start, goal, goal_radius, seed, waves, W, spanner_stretch=None, spanner_capacity=0):
     pl = m.DevicePPRM(sc, sp, lo, hi, goal=goal, goal_radius=goal_radius, seed=seed, capacity=1 << 14, max_wave=W,
-                      spanner_stretch=spanner_stretch or 0.0)
+                      spanner_stretch=spanner_stretch or 0.0, spanner_capacity=spanner_capacity)
     assert pl.add_start(start) == 0 and pl.add_goal(goal) == 1
     assert pl.add_goal(goal) == m.NO_INDEX  # closer than epsilon to a node: rejected (pprm.hpp:306-308)
     for _ in range(waves):
@@ -789,7 +789,10 @@ def test_device_pprm_irs_replays_the_reference_spanner(ctx, oracle):
     arm, oarm = m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64), oracle.link_arm(lengths, radius, circles)
     cand = W.box_states(256, 8, 3, -np.pi, np.pi)
     free8 = cand[oarm.valid(cand) != 0]
-    _check_device_pprm(ctx, oracle, sp8, arm, oarm, -np.pi, np.pi, free8[0], free8[1], 1e-6, 11, 4, 200, spanner_stretch=5.0)
+    # 8 dimensions: a search within 5 x the neighbour distance reaches most of the roadmap; started with room for 64 labelled
+    # nodes per search, the waves are rerun with more storage until every search fits -- same roadmap
+    _check_device_pprm(ctx, oracle, sp8, arm, oarm, -np.pi, np.pi, free8[0], free8[1], 1e-6, 11, 4, 200, spanner_stretch=5.0, spanner_capacity=64)
+    _check_device_pprm(ctx, oracle, sp, grid, ogrid, lo, hi, start, goal, 1e-6, 5, 6, 128, spanner_stretch=5.0, spanner_capacity=64)
 
 
 # ------------------------------------------------------------------ grid / shapes / link arm
