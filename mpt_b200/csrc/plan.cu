@@ -606,7 +606,7 @@ __global__ void pprmRootKernel(uint32_t* comp, uint32_t first, uint32_t count, u
 // ---------------------------------------------------------------------------------------------
 // PPRM-IRS on the device (src/mpt/impl/pprm_irs/pprm_irs.hpp:350-368, shortest_path_check.hpp:111-225): of the validated
 // (sample, neighbour) edges of a wave, keep as SPARSE edges those whose ends the sparse roadmap does not already join by a
-// path shorter than stretch x the edge.  One thread per new node runs the reference's bounded Dijkstra search over the
+// path shorter than stretch x the edge.  One warp per new node runs the reference's bounded Dijkstra search over the
 // roadmap as it stood when the wave began plus the node's own kept edges: neighbours nearest first, the search resumed from
 // check to check (the bound only grows), a kept edge entering it at once, stale queue entries skipped.  Path costs are the
 // left-to-right sums from the new node outwards, as Dijkstra forms them; by monotonicity of the rounded addition every
@@ -624,12 +624,20 @@ struct SpannerScratch {
     uint32_t cap;
 };
 
+constexpr int SPANNER_WARPS = 4;
+
+// One WARP per new node.  Lane 0 owns the heap; the 32 lanes read a settled node's edge row together (one coalesced load
+// per 32 slots), probe the table for their neighbours in parallel (distinct nodes: a row lists a node once, and the reverse
+// list holds edges from NEWER nodes only) and hand their improvements to lane 0 for queueing.  Same labels as a sequential
+// search (each relaxation touches its own node), so the same kept set.
 template <typename S>
-__global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, const uint32_t* __restrict__ sel, const uint32_t* __restrict__ nnIdx,
-                                  const S* __restrict__ nnDist, const uint32_t* __restrict__ nnCnt, uint8_t* __restrict__ okEdge,
-                                  const uint32_t* __restrict__ edgeIdx, const S* __restrict__ edgeDist, const uint32_t* __restrict__ revHead,
-                                  const uint32_t* __restrict__ revNext, S stretch, SpannerScratch<S> w, uint32_t* __restrict__ err) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(SPANNER_WARPS * 32) pprmSpannerKernel(
+    uint32_t nSel, uint32_t k, uint32_t stride, const uint32_t* __restrict__ sel, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+    const uint32_t* __restrict__ nnCnt, uint8_t* __restrict__ okEdge, const uint32_t* __restrict__ edgeIdx, const S* __restrict__ edgeDist,
+    const uint32_t* __restrict__ revHead, const uint32_t* __restrict__ revNext, S stretch, SpannerScratch<S> w, uint32_t* __restrict__ err) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nSel) return;
     const uint32_t i = sel[s];
     const uint32_t cnt = nnCnt[i] < k ? nnCnt[i] : k;
@@ -638,19 +646,36 @@ __global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, co
     S* tc = w.tabCost + (size_t)s * slots;
     S* hc = w.heapCost + (size_t)s * heapCap;
     uint32_t* hn = w.heapNode + (size_t)s * heapCap;
-    uint32_t used = 0, heapN = 0;
+    uint32_t used = 0;   // labelled nodes (the same value in every lane)
+    uint32_t heapN = 0;  // the same value in every lane; the heap itself is touched by lane 0 only
     bool overflow = false;
-    auto slotOf = [&](uint32_t node) {  // slot holding `node`, or the empty slot where it belongs
+    // slot of `node` for reading: the slot holding it or an empty one
+    auto slotOf = [&](uint32_t node) {
         uint32_t h = (node * 2654435761u) & (slots - 1u);
-        while (tn[h] != MPTG_NO_INDEX && tn[h] != node) h = (h + 1u) & (slots - 1u);
-        return h;
-    };
-    auto push = [&](S c, uint32_t node) {
-        if (heapN >= heapCap) {
-            overflow = true;
-            return;
+        for (;;) {
+            const uint32_t t = *(volatile uint32_t*)(tn + h);
+            if (t == MPTG_NO_INDEX || t == node) return h;
+            h = (h + 1u) & (slots - 1u);
         }
-        uint32_t x = heapN++;
+    };
+    // slot of `node`, claiming an empty one (lanes insert different nodes at the same time); fresh = it was not there before
+    auto claim = [&](uint32_t node, bool& fresh) {
+        uint32_t h = (node * 2654435761u) & (slots - 1u);
+        for (;;) {
+            const uint32_t t = atomicCAS(tn + h, MPTG_NO_INDEX, node);
+            if (t == MPTG_NO_INDEX) {
+                fresh = true;
+                return h;
+            }
+            if (t == node) {
+                fresh = false;
+                return h;
+            }
+            h = (h + 1u) & (slots - 1u);
+        }
+    };
+    auto push0 = [&](S c, uint32_t node) {  // lane 0
+        uint32_t x = heapN;
         while (x > 0) {
             const uint32_t parent = (x - 1u) >> 1;
             if (!(c < hc[parent])) break;
@@ -659,8 +684,8 @@ __global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, co
         }
         hc[x] = c, hn[x] = node;
     };
-    auto pop = [&]() {
-        const S c = hc[--heapN];
+    auto pop0 = [&]() {  // lane 0; heapN already decremented
+        const S c = hc[heapN];
         const uint32_t node = hn[heapN];
         uint32_t x = 0;
         for (;;) {
@@ -673,16 +698,21 @@ __global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, co
         }
         if (heapN > 0) hc[x] = c, hn[x] = node;
     };
-    auto setCost = [&](uint32_t h, uint32_t node, S c) {  // (re)label and queue
-        if (tn[h] == MPTG_NO_INDEX) {
-            if (++used > w.cap) {
+    // queue the improvements of the lanes in `mask` (their labels are already in the table)
+    auto queue = [&](unsigned mask, S c, uint32_t node) {
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const S cc = __shfl_sync(FULL, c, src);
+            const uint32_t nn = __shfl_sync(FULL, node, src);
+            if (heapN >= heapCap) {
                 overflow = true;
                 return;
             }
-            tn[h] = node;
+            if (lane == 0) push0(cc, nn);
+            ++heapN;
         }
-        tc[h] = c;
-        push(c, node);
+        __syncwarp();
     };
     for (uint32_t j = 0; j < cnt && !overflow; ++j) {
         uint8_t* flag = okEdge + (size_t)s * k + j;
@@ -692,41 +722,91 @@ __global__ void pprmSpannerKernel(uint32_t nSel, uint32_t k, uint32_t stride, co
         const S target = stretch * d;  // pprm_irs.hpp:351
         {
             const uint32_t h = slotOf(v);
-            if (tn[h] == v && tc[h] < target) {  // shortest_path_check.hpp:133-140
-                *flag = 0;
+            if (*(volatile uint32_t*)(tn + h) == v && *(volatile S*)(tc + h) < target) {  // shortest_path_check.hpp:133-140
+                __syncwarp();
+                if (lane == 0) *flag = 0;
                 continue;
             }
         }
         bool found = false;
         while (heapN > 0 && !overflow) {
-            const S priority = hc[0];
-            const uint32_t top = hn[0];
-            const S pathCost = tc[slotOf(top)];
+            S priority = S(0);
+            uint32_t top = 0;
+            if (lane == 0) priority = hc[0], top = hn[0];
+            priority = __shfl_sync(FULL, priority, 0);
+            top = __shfl_sync(FULL, top, 0);
+            const S pathCost = *(volatile S*)(tc + slotOf(top));
             if (pathCost >= target) break;  // :159-160
-            pop();
+            --heapN;
+            if (lane == 0) pop0();
+            __syncwarp();
             if (pathCost != priority) continue;  // stale: settled through a shorter path (:166-171)
             found = top == v;
-            auto relax = [&](uint32_t nbr, S len) {
-                const S c = pathCost + len;
-                if (nbr == v && c < target) found = true;
-                const uint32_t h = slotOf(nbr);
-                if (tn[h] == nbr && !(c < tc[h])) return;
-                setCost(h, nbr, c);
-            };
-            for (uint32_t t = 0; t < stride; ++t) {  // the node's own row: edges to older nodes
-                const uint32_t nbr = edgeIdx[(size_t)top * stride + t];
-                if (nbr != MPTG_NO_INDEX) relax(nbr, edgeDist[(size_t)top * stride + t]);
+            // the node's own row: edges to older nodes, 32 slots at a time
+            for (uint32_t base = 0; base < stride && !overflow; base += 32) {
+                const uint32_t t = base + lane;
+                uint32_t nbr = MPTG_NO_INDEX;
+                S c = S(0);
+                if (t < stride) {
+                    nbr = edgeIdx[(size_t)top * stride + t];
+                    if (nbr != MPTG_NO_INDEX) c = pathCost + edgeDist[(size_t)top * stride + t];
+                }
+                const bool live = nbr != MPTG_NO_INDEX;
+                found = found || __any_sync(FULL, live && nbr == v && c < target);
+                bool fresh = false, better = false;
+                if (live) {
+                    const uint32_t h = claim(nbr, fresh);
+                    better = fresh || c < *(volatile S*)(tc + h);
+                    if (better) tc[h] = c;
+                }
+                used += __popc(__ballot_sync(FULL, fresh));
+                if (used > w.cap) overflow = true;
+                __syncwarp();
+                queue(__ballot_sync(FULL, better), c, nbr);
             }
-            for (uint32_t e = revHead[top]; e != MPTG_NO_INDEX; e = revNext[e]) relax(e / stride, edgeDist[e]);  // edges from newer nodes
+            // edges from newer nodes: the reverse list, gathered 32 entries at a time (every lane walks the same chain)
+            uint32_t e = revHead[top];
+            while (e != MPTG_NO_INDEX && !overflow) {
+                uint32_t nbr = MPTG_NO_INDEX;
+                S c = S(0);
+                for (int got = 0; got < 32 && e != MPTG_NO_INDEX; ++got) {
+                    if (got == lane) nbr = e / stride, c = pathCost + edgeDist[e];
+                    e = revNext[e];
+                }
+                const bool live = nbr != MPTG_NO_INDEX;
+                found = found || __any_sync(FULL, live && nbr == v && c < target);
+                bool fresh = false, better = false;
+                if (live) {
+                    const uint32_t h = claim(nbr, fresh);
+                    better = fresh || c < *(volatile S*)(tc + h);
+                    if (better) tc[h] = c;
+                }
+                used += __popc(__ballot_sync(FULL, fresh));
+                if (used > w.cap) overflow = true;
+                __syncwarp();
+                queue(__ballot_sync(FULL, better), c, nbr);
+            }
             if (found) break;  // :208-209
         }
+        if (overflow) break;
         if (found) {
-            *flag = 0;
+            if (lane == 0) *flag = 0;
             continue;
         }
-        setCost(slotOf(v), v, d);  // a sparse edge: part of the search from here on (:219-222)
+        // a sparse edge: part of the search from here on (:219-222)
+        bool fresh = false;
+        uint32_t h = 0;
+        if (lane == 0) {
+            h = claim(v, fresh);
+            tc[h] = d;
+        }
+        fresh = __shfl_sync(FULL, (int)fresh, 0) != 0;
+        used += fresh ? 1u : 0u;
+        if (used > w.cap) overflow = true;
+        __syncwarp();
+        queue(1u, d, v);
     }
-    if (overflow) atomicOr(err, 1u);
+    if (overflow && lane == 0) atomicOr(err, 1u);
 }
 
 // reverse lists for the sparse edges of the nodes just appended
@@ -894,7 +974,7 @@ int pprmProcessT(mptg_pprm* p, uint32_t W, uint32_t marks, uint32_t* firstOut, u
                 const size_t slots = 2 * (size_t)p->spanCap;
                 MPTG_CUDA(ctx, cudaMemsetAsync(p->spanTabNode, 0xFF, (size_t)nSel * slots * sizeof(uint32_t), st));
                 SpannerScratch<S> ws{p->spanTabNode, (S*)p->spanTabCost, (S*)p->spanHeapCost, p->spanHeapNode, p->spanCap};
-                pprmSpannerKernel<S><<<(nSel + 63) / 64, 64, 0, st>>>(nSel, k, p->stride, p->sel2, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->okEdge,
+                pprmSpannerKernel<S><<<(nSel + SPANNER_WARPS - 1) / SPANNER_WARPS, SPANNER_WARPS * 32, 0, st>>>(nSel, k, p->stride, p->sel2, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->okEdge,
                                                                      p->edgeIdx, (const S*)p->edgeDist, p->revHead, p->revNext, (S)p->stretch, ws, p->spanErr);
                 MPTG_LAUNCHED(ctx);
                 MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 2, p->spanErr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
