@@ -314,9 +314,13 @@ __global__ void validKernel(const V v, const S* __restrict__ states, uint32_t n,
 // takes one item: it finds the edge by binary search in the prefix sums, reaches its node by midpoint arithmetic alone
 // (the reference's (a+b)/2 sequence and stop test at every level, so the node exists exactly when the reference's
 // recursion creates it) and probes it.  A failed probe clears ok[e]; items of an edge already cleared are skipped.
+// `coarse`: the most tree nodes an edge contributes to the FIRST list (heap nodes 1 .. coarse); the rest, 2^L - 1 - coarse
+// per edge, form a second list that is built after the first has been checked -- from the edges that are still valid
+// (flatPlanRestKernel).  Large batches use coarse = 7 (the three top levels), see flatLink.
 template <typename S, typename V>
-__global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* __restrict__ to, uint32_t n,
-                               unsigned long long* __restrict__ counts, uint8_t* __restrict__ ok, unsigned long long* __restrict__ stats) {
+__global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* __restrict__ to, uint32_t n, uint32_t coarse,
+                               unsigned long long* __restrict__ counts, int8_t* __restrict__ levelsOut, uint8_t* __restrict__ ok,
+                               unsigned long long* __restrict__ stats) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     if (e == 0) counts[n] = 0;
@@ -324,6 +328,7 @@ __global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* _
     const int D = v.dims();
     for (int i = 0; i < D; ++i) a[i] = from[(size_t)e * D + i], b[i] = to[(size_t)e * D + i];
     const int L = v.levels(a, b);
+    levelsOut[e] = (int8_t)(L < 0 || L > FLAT_MAX_LEVELS ? 0 : L);
     if (L < 0) {  // the validator declares the edge invalid outright (a length that is not finite)
         ok[e] = 0;
         counts[e] = 0;
@@ -336,13 +341,23 @@ __global__ void flatPlanKernel(const V v, const S* __restrict__ from, const S* _
         return;
     }
     ok[e] = 1;
-    counts[e] = (V::CHECK_ENDS ? 2ull : 0ull) + ((1ull << L) - 1ull);
+    const unsigned long long nodes = (1ull << L) - 1ull;
+    counts[e] = (V::CHECK_ENDS ? 2ull : 0ull) + (nodes < coarse ? nodes : (unsigned long long)coarse);
+}
+// second list: tree nodes coarse + 1 .. 2^L - 1 of the edges the first list left valid
+__global__ void flatPlanRestKernel(uint32_t n, uint32_t coarse, const int8_t* __restrict__ levels, const uint8_t* __restrict__ ok,
+                                   unsigned long long* __restrict__ counts) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (e == 0) counts[n] = 0;
+    const unsigned long long nodes = (1ull << levels[e]) - 1ull;
+    counts[e] = ok[e] && nodes > coarse ? nodes - coarse : 0ull;
 }
 
 template <typename S, typename V>
 __global__ void __launch_bounds__(256) flatLinkKernel(const V v, const S* __restrict__ from, const S* __restrict__ to, uint32_t n,
                                                       const unsigned long long* __restrict__ offs, uint8_t* ok,
-                                                      unsigned long long* __restrict__ stats) {
+                                                      unsigned long long* __restrict__ stats, bool withEnds, uint32_t firstNode) {
     const unsigned long long total = offs[n];
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -369,11 +384,11 @@ __global__ void __launch_bounds__(256) flatLinkKernel(const V v, const S* __rest
         if (live) {
             unsigned long long j = it - __ldg(offs + e);
             for (int i = 0; i < D; ++i) a[i] = __ldg(from + (size_t)e * D + i), b[i] = __ldg(to + (size_t)e * D + i);
-            if (V::CHECK_ENDS && j < 2) {
+            if (V::CHECK_ENDS && withEnds && j < 2) {
                 for (int i = 0; i < D; ++i) mid[i] = j == 0 ? a[i] : b[i];
             } else {
-                if (V::CHECK_ENDS) j -= 2;
-                const unsigned long long h = j + 1;  // heap index: 1 = the edge's own midpoint
+                if (V::CHECK_ENDS && withEnds) j -= 2;
+                const unsigned long long h = j + firstNode;  // heap index: 1 = the edge's own midpoint
                 const int d = 63 - __clzll(h);
                 for (int level = 0; level < d; ++level) {
                     if (v.stop(a, b)) {
@@ -562,7 +577,8 @@ int flatLink(mptg_geom* g, const V& v, const S* from, const S* to, uint32_t n, u
     size_t scanBytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)(n + 1u));
     const size_t listBytes = ((size_t)(n + 1u) * sizeof(unsigned long long) + 255) & ~(size_t)255;
-    const size_t want = 2 * listBytes + scanBytes;
+    const size_t levBytes = ((size_t)n + 255) & ~(size_t)255;
+    const size_t want = 2 * listBytes + levBytes + scanBytes;
     if (g->flatBytes < want) {
         MPTG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (g->flatBuf) MPTG_CUDA(ctx, cudaFree(g->flatBuf));
@@ -572,16 +588,31 @@ int flatLink(mptg_geom* g, const V& v, const S* from, const S* to, uint32_t n, u
     }
     auto* counts = (unsigned long long*)g->flatBuf;
     auto* offs = (unsigned long long*)((char*)g->flatBuf + listBytes);
-    void* temp = (char*)g->flatBuf + 2 * listBytes;
-    flatPlanKernel<S, V><<<(n + 255) / 256, 256, 0, ctx->stream>>>(v, from, to, n, counts, ok, g->devStats);
+    auto* levels = (int8_t*)((char*)g->flatBuf + 2 * listBytes);
+    void* temp = (char*)g->flatBuf + 2 * listBytes + levBytes;
+    // Large batches go coarse to fine: the three top levels of every edge first (7 midpoints and the ends), then the deeper
+    // nodes of the edges that survived -- an invalid edge (most of a roadmap planner's long candidate edges) rarely gets
+    // past the first list, as it rarely gets past its first midpoints in the reference's recursion.  Small batches (the
+    // waves of a young tree) take one list: three launches less.
+    const uint32_t coarse = n >= 4096 ? 7u : 0xFFFFFFFFu;
+    int perSm = 0;
+    MPTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flatLinkKernel<S, V>, 256, 0));
+    const unsigned grid = (unsigned)ctx->smCount * (perSm > 0 ? perSm : 1);
+    flatPlanKernel<S, V><<<(n + 255) / 256, 256, 0, ctx->stream>>>(v, from, to, n, coarse, counts, levels, ok, g->devStats);
     MPTG_LAUNCHED(ctx);
     MPTG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(temp, scanBytes, counts, offs, (int)(n + 1u), ctx->stream));
     MPTG_LAUNCHED(ctx);
-    // the length of the list is only known on the device: a resident grid strides over it
-    int perSm = 0;
-    MPTG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, flatLinkKernel<S, V>, 256, 0));
-    flatLinkKernel<S, V><<<ctx->smCount * (perSm > 0 ? perSm : 1), 256, 0, ctx->stream>>>(v, from, to, n, offs, ok, g->devStats);
+    // the length of a list is only known on the device: a resident grid strides over it
+    flatLinkKernel<S, V><<<grid, 256, 0, ctx->stream>>>(v, from, to, n, offs, ok, g->devStats, true, 1u);
     MPTG_LAUNCHED(ctx);
+    if (coarse != 0xFFFFFFFFu) {
+        flatPlanRestKernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, coarse, levels, ok, counts);
+        MPTG_LAUNCHED(ctx);
+        MPTG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(temp, scanBytes, counts, offs, (int)(n + 1u), ctx->stream));
+        MPTG_LAUNCHED(ctx);
+        flatLinkKernel<S, V><<<grid, 256, 0, ctx->stream>>>(v, from, to, n, offs, ok, g->devStats, false, coarse + 1u);
+        MPTG_LAUNCHED(ctx);
+    }
     return MPTG_OK;
 }
 
