@@ -1394,9 +1394,11 @@ __global__ void starRewireApplyKernel(const uint32_t* __restrict__ ids, const ui
 }
 // nonConcurrentPushUpdate (:664-688) for all re-parented nodes at once
 template <typename S>
-__global__ void starPushKernel(uint32_t n, const uint32_t* __restrict__ parent, const S* __restrict__ delta, S* __restrict__ cost) {
+__global__ void starPushKernel(uint32_t n, const uint32_t* __restrict__ parent, const S* __restrict__ delta, S* __restrict__ cost,
+                               const uint32_t* __restrict__ applied) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (*applied == 0u) return;  // no node was re-parented in this wave: every decrease is zero, nothing to push
     S c = cost[i];
     bool changed = false;
     uint32_t steps = 0;  // a path has fewer than n nodes; the bound keeps a corrupted tree from hanging the device
@@ -1592,7 +1594,7 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
         starRewireApplyKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestCand,
                                                      p->parent, (S*)p->delta, p->result + 1);
         MPTG_LAUNCHED(ctx);
-        starPushKernel<S><<<(total + 127) / 128, 128, 0, st>>>(total, p->parent, (const S*)p->delta, (S*)p->cost);
+        starPushKernel<S><<<(total + 127) / 128, 128, 0, st>>>(total, p->parent, (const S*)p->delta, (S*)p->cost, p->result + 1);
         MPTG_LAUNCHED(ctx);
     } else {
         MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
