@@ -172,3 +172,23 @@ def test_flat_edge_check_limits(ctx, oracle, which):
         sc.link(a, b)
     assert e.value.code == -5  # MPTG_ERR_CAPACITY
     assert np.array_equal(sc.link(a[:6], b[:6]), want[:6])  # the geometry stays usable after the error
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scalar", [m.F64, m.F32])
+def test_device_matches_oracle_at_bench_size(ctx, oracle, scalar):
+    """The wave bench.py times (secondary.nao_cup_edges_*): 65,536 edges between clear configurations 0.3 rad apart, two
+    lists (coarse to fine) on the device -- every decision equal to the oracle's, and the same edges answered in small
+    batches (one list) give the same bytes."""
+    _, dt = TAGS[scalar]
+    sc, og = m.Scenario.nao_cup(ctx, scalar), oracle.nao_cup(scalar)
+    pool = W.nao_states(1 << 20, 3, dtype=dt)
+    pool = pool[sc.valid(pool) == 1]
+    rng = np.random.default_rng(4)
+    a = np.ascontiguousarray(pool[rng.integers(0, pool.shape[0], 65536)])
+    b = np.ascontiguousarray(np.clip(a + rng.normal(0, 0.3 / np.sqrt(10), a.shape), W.NAO_LO, W.NAO_HI).astype(dt))
+    got = sc.link(a, b)
+    assert np.array_equal(got, og.link(a, b))
+    small = np.concatenate([sc.link(a[i:i + 2048], b[i:i + 2048]) for i in range(0, 16384, 2048)])
+    assert np.array_equal(small, got[:16384])
+    assert 0.5 < got.mean() < 0.75
