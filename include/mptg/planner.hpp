@@ -38,6 +38,7 @@
 
 #include "host.hpp"
 #include "spaces.hpp"
+#include "tags.hpp"
 
 namespace mptg {
 
@@ -52,8 +53,7 @@ using single_threaded = max_threads<1>;
 using hardware_concurrency = max_threads<0>;
 template <int n>
 struct wave_size {};
-// the nearest-neighbour strategy tag of this library (the analogue of nigh::KDTreeBatch<> etc.)
-struct GpuBatch {};
+// the nearest-neighbour strategy tag of this library, GpuBatch (the analogue of nigh::KDTreeBatch<> etc.): tags.hpp
 // PRRT<device_resident, ...> / PPRM<device_resident, ...>: keep the tree / roadmap on the GPU (mptg_prrt_*, mptg_pprm_*), sample on the device
 struct device_resident {};
 template <int n>

@@ -39,6 +39,7 @@
 #include <png_2d_scenario.hpp>
 
 // ---- ours
+#include "mptg/nigh_binding.hpp"  // the reference-side binding: pack_nearest + nigh::Nigh for the strategy tag mptg::GpuBatch
 #include "mptg/planner.hpp"
 #include "mptg/scenarios.hpp"
 
@@ -203,6 +204,41 @@ void compare(const char* name, const Grid& g, double goalRadius, double goalBias
                 (int)rp.solved(), (int)op.solved(), rs.size(), os.size());
 }
 
+// The reference's OWN planner class, unmodified, with its nearest-neighbour strategy switched to mptg::GpuBatch through
+// include/mptg/nigh_binding.hpp (every nn_.nearest / nn_.insert of its loop goes through the C ABI) against the same class
+// with the stand-in exhaustive-scan Nigh: same random stream, the graphs must be identical.
+template <class RefAlgoLinear, class RefAlgoGpu>
+void compareStrategies(const char* name, const Grid& g, double goalRadius, double goalBias, double range, std::uint64_t seed, std::size_t nodes) {
+    using RefState = RefGrid::State;
+    const int before = failures;
+    ref::Planner<RefGrid, RefAlgoLinear> a(RefGrid(g, goalRadius), seed);
+    ref::Planner<RefGrid, RefAlgoGpu> b(RefGrid(g, goalRadius), seed);
+    static_assert(!std::is_same_v<decltype(a), decltype(b)>, "the strategy tag must select another planner type");
+    if constexpr (!is_roadmap<RefAlgoLinear>::value) {
+        a.setGoalBias(goalBias), b.setGoalBias(goalBias);
+        if (std::isfinite(range)) a.setRange(range), b.setRange(range);
+    } else {
+        a.addGoal(RefState(g.goal[0], g.goal[1])), b.addGoal(RefState(g.goal[0], g.goal[1]));
+    }
+    a.addStart(RefState(g.start[0], g.start[1]));
+    b.addStart(RefState(g.start[0], g.start[1]));
+    a.solve([&] { return a.size() >= nodes; });
+    b.solve([&] { return b.size() >= nodes; });
+    GraphDump ga, gb;
+    a.visitGraph(ga);
+    b.visitGraph(gb);
+    std::sort(ga.vertices.begin(), ga.vertices.end()), std::sort(gb.vertices.begin(), gb.vertices.end());
+    std::sort(ga.edges.begin(), ga.edges.end()), std::sort(gb.edges.begin(), gb.edges.end());
+    EXPECT(ga.vertices == gb.vertices);
+    EXPECT(ga.edges == gb.edges);
+    EXPECT(a.solved() == b.solved());
+    std::vector<RefState> sa = a.solution(), sb = b.solution();
+    EXPECT(sa.size() == sb.size());
+    for (std::size_t i = 0; i < sa.size() && i < sb.size(); ++i) EXPECT(sa[i][0] == sb[i][0] && sa[i][1] == sb[i][1]);
+    std::printf("%s reference %s with mptg::GpuBatch: %zu / %zu vertices, %zu / %zu edges, solved %d / %d (stand-in Nigh / libmptg through the binding)\n",
+                failures == before ? "PASS" : "FAIL", name, ga.vertices.size(), gb.vertices.size(), ga.edges.size(), gb.edges.size(), (int)a.solved(), (int)b.solved());
+}
+
 int main() {
     const Grid g = makeGrid(400, 300, 5);
     const double inf = std::numeric_limits<double>::infinity();
@@ -216,6 +252,12 @@ int main() {
     compare<ref::PPRMIRS<ref::single_threaded>, mptg::PPRMIRS<mptg::wave_size<1>>>("PPRM-IRS", g, 1e-6, 0.0, inf, 16, 900, false, true);
     compare<ref::PPRMIRS<ref::single_threaded, ref::keep_dense_edges<true>>, mptg::PPRMIRS<mptg::wave_size<1>, mptg::keep_dense_edges<true>>>(
         "PPRM-IRS keep_dense_edges", g, 1e-6, 0.0, inf, 17, 700, false, true);
+    // the reference's own planners over include/mptg/nigh_binding.hpp
+    compareStrategies<ref::PRRT<ref::single_threaded>, ref::PRRT<ref::single_threaded, mptg::GpuBatch>>("PRRT", g, 8.0, 0.05, 20.0, 21, 800);
+    compareStrategies<ref::PRRTStar<ref::single_threaded>, ref::PRRTStar<mptg::GpuBatch, ref::single_threaded>>("PRRT*", g, 8.0, 0.05, 25.0, 22, 600);
+    compareStrategies<ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest>, ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest, mptg::GpuBatch>>(
+        "PRRT* r-nearest", g, 8.0, 0.05, 25.0, 23, 600);
+    compareStrategies<ref::PPRM<ref::single_threaded>, ref::PPRM<ref::single_threaded, mptg::GpuBatch>>("PPRM", g, 1e-6, 0.0, inf, 24, 400);
     std::printf("%d failures\n", failures);
     return failures ? 1 : 0;
 }
