@@ -79,30 +79,34 @@ void describe(const nm::Space<T, nm::Cartesian<M...>>*, double w, mptg_space_des
     describeTuple<T, M...>(w, d, std::index_sequence_for<M...>{});
 }
 
-// ---- state codec: the scalars of a state in the order of its parts (quaternions as x, y, z, w)
-template <class S, int N>
-S* pack(const Eigen::Matrix<S, N, 1>& q, S* out) {
+// ---- state codec, driven by the space type: the scalars of a state in the order of its parts (quaternions as x, y, z, w)
+template <class S, int N, class M>
+S* pack(const nm::Space<Eigen::Matrix<S, N, 1>, M>*, const Eigen::Matrix<S, N, 1>& q, S* out) {
     for (int i = 0; i < N; ++i) *out++ = q[i];
     return out;
 }
-template <class S>
-S* pack(const Eigen::Quaternion<S>& q, S* out) {
-    for (int i = 0; i < 4; ++i) *out++ = q.coeffs()[i];
-    return out;
-}
-template <class S, class = std::enable_if_t<std::is_arithmetic_v<S>>>
-S* pack(const S& q, S* out) {
+template <class S, int p>
+S* pack(const nm::Space<S, nm::SO2<p>>*, const S& q, S* out) {
     *out++ = q;
     return out;
 }
-template <class S, class T, std::size_t... I>
-S* packTuple(const T& q, S* out, std::index_sequence<I...>) {
-    ((out = pack(nm::cartesian_state_element<I, T>::get(q), out)), ...);
+template <class S>
+S* pack(const nm::Space<Eigen::Quaternion<S>, nm::SO3>*, const Eigen::Quaternion<S>& q, typename nm::Space<Eigen::Quaternion<S>, nm::SO3>::Distance* out) {
+    for (int i = 0; i < 4; ++i) *out++ = q.coeffs()[i];
     return out;
 }
-template <class S, class T, class = std::enable_if_t<(std::tuple_size<T>::value > 0)>>
-S* pack(const T& q, S* out) {
-    return packTuple<S>(q, out, std::make_index_sequence<std::tuple_size<T>::value>{});
+template <class T, class M, std::intmax_t num, std::intmax_t den, class S>
+S* pack(const nm::Space<T, nm::Scaled<M, std::ratio<num, den>>>*, const T& q, S* out) {
+    return pack(static_cast<const nm::Space<T, M>*>(nullptr), q, out);
+}
+template <class T, class S, class... M, std::size_t... I>
+S* packTuple(const T& q, S* out, std::index_sequence<I...>) {
+    ((out = pack(static_cast<const nm::Space<nm::cartesian_state_element_t<I, T>, M>*>(nullptr), nm::cartesian_state_element<I, T>::get(q), out)), ...);
+    return out;
+}
+template <class T, class... M, class S>
+S* pack(const nm::Space<T, nm::Cartesian<M...>>*, const T& q, S* out) {
+    return packTuple<T, S, M...>(q, out, std::index_sequence_for<M...>{});
 }
 }  // namespace mptg::nighbind
 
@@ -145,7 +149,7 @@ private:
     template <class Key>
     void query(const Key& q, std::uint32_t k, double r, std::uint32_t& count) const {
         q_.resize((std::size_t)scalars_);
-        mptg::nighbind::pack<Distance>(q, q_.data());
+        mptg::nighbind::pack(static_cast<const Space*>(nullptr), q, q_.data());
         idx_.resize(k), dist_.resize(k);
         if (mptg_knn_query(knn_, q_.data(), 1, k, r, idx_.data(), dist_.data(), &count) != MPTG_OK) mptg::nighbind::fail(ctx_, "mptg_knn_query");
     }
@@ -174,7 +178,7 @@ public:
         std::lock_guard<std::mutex> lock(mutex_);
         const std::size_t at = packed_.size();
         packed_.resize(at + (std::size_t)scalars_);
-        mptg::nighbind::pack<Distance>(key_(t), packed_.data() + at);
+        mptg::nighbind::pack(static_cast<const Space*>(nullptr), key_(t), packed_.data() + at);
         handles_.push_back(t);
         if (handles_.size() > capacity_) {  // grow: a new structure of twice the size, every point again
             mptg_knn_destroy(knn_);

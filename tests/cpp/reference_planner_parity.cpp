@@ -35,6 +35,7 @@
 #include <mpt/pprm_irs.hpp>
 #include <mpt/prrt.hpp>
 #include <mpt/prrt_star.hpp>
+#include <mpt/se3_space.hpp>
 
 #include <png_2d_scenario.hpp>
 
@@ -239,6 +240,59 @@ void compareStrategies(const char* name, const Grid& g, double goalRadius, doubl
                 failures == before ? "PASS" : "FAIL", name, ga.vertices.size(), gb.vertices.size(), ga.edges.size(), gb.edges.size(), (int)a.solved(), (int)b.solved());
 }
 
+// the binding's space descriptor and state codec on a compound space: the reference's SE3Space<double, 50> (tuple state,
+// Cartesian<Scaled<SO3, 50>, L2>) -- nearest and k-nearest through libmptg against the stand-in exhaustive scan.  The two
+// evaluate acos differently (libm there, mptg_fpmath.h here): distances agree to a few ulps, the order wherever
+// neighbours are not closer to each other than that.
+void compareSE3Binding() {
+    using Space = ref::SE3Space<double, 50, 1>;
+    using State = Space::Type;
+    struct Key {
+        const std::vector<State>* states;
+        const State& operator()(std::size_t i) const { return (*states)[i]; }
+    };
+    const int before = failures;
+    std::mt19937_64 rng(77);
+    std::uniform_real_distribution<double> u(-1.0, 1.0);
+    auto randomState = [&] {
+        double q[4], n = 0;
+        for (double& c : q) c = u(rng), n += c * c;
+        n = std::sqrt(n);
+        return State(Eigen::Quaternion<double>(q[3] / n, q[0] / n, q[1] / n, q[2] / n), Eigen::Matrix<double, 3, 1>(100 * u(rng), 100 * u(rng), 100 * u(rng)));
+    };
+    std::vector<State> states;
+    for (int i = 0; i < 3000; ++i) states.push_back(randomState());
+    Key key{&states};
+    unc::robotics::nigh::Nigh<std::size_t, Space, Key, unc::robotics::nigh::NoThreadSafety, unc::robotics::nigh::Linear> linear(Space(), key);
+    unc::robotics::nigh::Nigh<std::size_t, Space, Key, unc::robotics::nigh::NoThreadSafety, mptg::GpuBatch> gpu(Space(), key);
+    for (std::size_t i = 0; i < states.size(); ++i) linear.insert(i), gpu.insert(i);
+    EXPECT(gpu.size() == linear.size());
+    std::size_t sameNearest = 0, sameLists = 0;
+    double worst = 0;
+    const int Q = 200;
+    for (int t = 0; t < Q; ++t) {
+        const State q = randomState();
+        auto a = linear.nearest(q), b = gpu.nearest(q);
+        EXPECT(a && b);
+        if (a && b) {
+            sameNearest += a->first == b->first;
+            worst = std::max(worst, std::abs(a->second - b->second) / a->second);
+        }
+        std::vector<std::tuple<double, std::size_t>> la, lb;
+        linear.nearest(la, q, 12), gpu.nearest(lb, q, 12);
+        EXPECT(la.size() == 12 && lb.size() == 12);
+        bool same = la.size() == lb.size();
+        for (std::size_t i = 0; same && i < la.size(); ++i) same = std::get<1>(la[i]) == std::get<1>(lb[i]);
+        sameLists += same;
+        std::vector<std::tuple<std::size_t, double>> ra, rb;  // the (T, Distance) tuple order and the radius form
+        linear.nearest(ra, q, std::numeric_limits<std::size_t>::max(), 40.0), gpu.nearest(rb, q, std::numeric_limits<std::size_t>::max(), 40.0);
+        EXPECT(ra.size() == rb.size() || ra.size() > 128);
+    }
+    EXPECT(sameNearest == (std::size_t)Q && sameLists >= (std::size_t)Q - 1 && worst < 1e-12);
+    std::printf("%s binding on SE3Space<double, 50>: %zu / %d nearest and %zu / %d 12-nearest lists identical, largest relative distance difference %.2g\n",
+                failures == before ? "PASS" : "FAIL", sameNearest, Q, sameLists, Q, worst);
+}
+
 int main() {
     const Grid g = makeGrid(400, 300, 5);
     const double inf = std::numeric_limits<double>::infinity();
@@ -252,6 +306,7 @@ int main() {
     compare<ref::PPRMIRS<ref::single_threaded>, mptg::PPRMIRS<mptg::wave_size<1>>>("PPRM-IRS", g, 1e-6, 0.0, inf, 16, 900, false, true);
     compare<ref::PPRMIRS<ref::single_threaded, ref::keep_dense_edges<true>>, mptg::PPRMIRS<mptg::wave_size<1>, mptg::keep_dense_edges<true>>>(
         "PPRM-IRS keep_dense_edges", g, 1e-6, 0.0, inf, 17, 700, false, true);
+    compareSE3Binding();
     // the reference's own planners over include/mptg/nigh_binding.hpp
     compareStrategies<ref::PRRT<ref::single_threaded>, ref::PRRT<ref::single_threaded, mptg::GpuBatch>>("PRRT", g, 8.0, 0.05, 20.0, 21, 800);
     compareStrategies<ref::PRRTStar<ref::single_threaded>, ref::PRRTStar<mptg::GpuBatch, ref::single_threaded>>("PRRT*", g, 8.0, 0.05, 25.0, 22, 600);
