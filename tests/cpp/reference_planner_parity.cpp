@@ -113,6 +113,45 @@ struct RefGrid {
     const Goal& goal() const { return goal_; }
 };
 
+// The same scenario for the reference's planners, but with BOTH halves of the hot path behind the C ABI: valid / link are
+// answered by mptg_valid_batch / mptg_link_batch on the registered grid (one item per call, the reference's calling
+// convention), nearest-neighbour search by the strategy tag.  Copied once per worker like any reference scenario; the
+// geometry handle is shared.
+struct GpuGrid {
+    using Space = RefGrid::Space;
+    using Bounds = RefGrid::Bounds;
+    using State = RefGrid::State;
+    using Distance = RefGrid::Distance;
+    using Goal = ref::GoalState<Space>;
+    using RNG = std::mt19937_64;
+    struct Device {
+        mptg::Context ctx;
+        mptg::Geometry geom;
+        Device(const Grid& g) : ctx(-1), geom(mptg::Geometry::grid(ctx, MPTG_F64, g.w, g.h, g.occ.data())) {}
+    };
+    std::shared_ptr<Device> dev;
+    Space space_;
+    Bounds bounds_;
+    Goal goal_;
+    GpuGrid(const Grid& g, double radius)
+        : dev(std::make_shared<Device>(g)), bounds_(State(0, 0), State(g.w - 1, g.h - 1)), goal_(radius, State(g.goal[0], g.goal[1])) {}
+    bool valid(const State& q) const {
+        const double s[2] = {q[0], q[1]};
+        std::uint8_t ok = 0;
+        dev->geom.valid(s, 1, &ok);
+        return ok != 0;
+    }
+    bool link(const State& a, const State& b) const {
+        const double from[2] = {a[0], a[1]}, to[2] = {b[0], b[1]};
+        std::uint8_t ok = 0;
+        dev->geom.link(nullptr, from, to, 1, 0.0, &ok);
+        return ok != 0;
+    }
+    const Space& space() const { return space_; }
+    const Bounds& bounds() const { return bounds_; }
+    const Goal& goal() const { return goal_; }
+};
+
 struct OurGrid {
     using Space = mptg::L2Space<double, 2>;
     using Bounds = mptg::BoxBounds<double, 2>;
@@ -208,12 +247,12 @@ void compare(const char* name, const Grid& g, double goalRadius, double goalBias
 // The reference's OWN planner class, unmodified, with its nearest-neighbour strategy switched to mptg::GpuBatch through
 // include/mptg/nigh_binding.hpp (every nn_.nearest / nn_.insert of its loop goes through the C ABI) against the same class
 // with the stand-in exhaustive-scan Nigh: same random stream, the graphs must be identical.
-template <class RefAlgoLinear, class RefAlgoGpu>
+template <class RefAlgoLinear, class RefAlgoGpu, class GpuScenario = RefGrid>
 void compareStrategies(const char* name, const Grid& g, double goalRadius, double goalBias, double range, std::uint64_t seed, std::size_t nodes) {
     using RefState = RefGrid::State;
     const int before = failures;
     ref::Planner<RefGrid, RefAlgoLinear> a(RefGrid(g, goalRadius), seed);
-    ref::Planner<RefGrid, RefAlgoGpu> b(RefGrid(g, goalRadius), seed);
+    ref::Planner<GpuScenario, RefAlgoGpu> b(GpuScenario(g, goalRadius), seed);
     static_assert(!std::is_same_v<decltype(a), decltype(b)>, "the strategy tag must select another planner type");
     if constexpr (!is_roadmap<RefAlgoLinear>::value) {
         a.setGoalBias(goalBias), b.setGoalBias(goalBias);
@@ -313,6 +352,10 @@ int main() {
     compareStrategies<ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest>, ref::PRRTStar<ref::single_threaded, ref::rewire_r_nearest, mptg::GpuBatch>>(
         "PRRT* r-nearest", g, 8.0, 0.05, 25.0, 23, 600);
     compareStrategies<ref::PPRM<ref::single_threaded>, ref::PPRM<ref::single_threaded, mptg::GpuBatch>>("PPRM", g, 1e-6, 0.0, inf, 24, 400);
+    // ... and with the scenario's valid / link behind the C ABI as well: the whole hot path of the reference's loop swapped
+    compareStrategies<ref::PRRTStar<ref::single_threaded>, ref::PRRTStar<ref::single_threaded, mptg::GpuBatch>, GpuGrid>("PRRT* (kNN + validity)", g, 8.0, 0.05, 25.0,
+                                                                                                                  25, 500);
+    compareStrategies<ref::PPRM<ref::single_threaded>, ref::PPRM<ref::single_threaded, mptg::GpuBatch>, GpuGrid>("PPRM (kNN + validity)", g, 1e-6, 0.0, inf, 26, 300);
     std::printf("%d failures\n", failures);
     return failures ? 1 : 0;
 }

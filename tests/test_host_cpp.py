@@ -37,7 +37,8 @@ def test_wave_planners_host_logic_with_mock_backend():
 
 PARITY_CASES = ("PRRT range 20:", "PRRT unbounded:", "PRRT* k-nearest:", "PRRT* r-nearest:", "PPRM:", "PPRM-IRS:", "PPRM-IRS keep_dense_edges:",
                 "reference PRRT with mptg::GpuBatch:", "reference PRRT* with mptg::GpuBatch:", "reference PRRT* r-nearest with mptg::GpuBatch:",
-                "reference PPRM with mptg::GpuBatch:", "binding on SE3Space<double, 50>:")
+                "reference PPRM with mptg::GpuBatch:", "binding on SE3Space<double, 50>:",
+                "reference PRRT* (kNN + validity) with mptg::GpuBatch:", "reference PPRM (kNN + validity) with mptg::GpuBatch:")
 
 
 def test_wave_planners_build_the_reference_planners_graphs():
