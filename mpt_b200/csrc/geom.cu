@@ -100,7 +100,9 @@ __device__ __forceinline__ S distPointSegmentSquared2(const S* pt, const S* s0, 
     return ex * ex + ey * ey;
 }
 
-template <typename S, int MAXD_>
+// EXACT: the arm has exactly MAXD_ links, so every loop over the links has a compile-time trip count and the state arrays
+// of the edge kernels sit in registers (with a run-time count they are indexed dynamically and live in local memory)
+template <typename S, int MAXD_, bool EXACT = false>
 struct ArmValidator {
     static constexpr int MAXD = MAXD_;
     static constexpr bool CHECK_ENDS = true;
@@ -109,12 +111,13 @@ struct ArmValidator {
     const S* circles;
     int nLinks, nCircles;
     S linkRadius;
-    __device__ __forceinline__ int dims() const { return nLinks; }
+    __device__ __forceinline__ int dims() const { return EXACT ? MAXD_ : nLinks; }
     // demo/link_manipulator_scenario.hpp:99-116
     __device__ bool valid(const S* q) const {
         S from[2] = {S(0), S(0)}, to[2];
         S angle = S(0);
-        for (int i = 0; i < nLinks; ++i) {
+#pragma unroll
+        for (int i = 0; i < (EXACT ? MAXD_ : nLinks); ++i) {
             angle = angle + q[i];
             S sn, cs;
             fp::sincos_(angle, &sn, &cs);
@@ -146,7 +149,8 @@ struct ArmValidator {
     // :127-131  (a - b).lpNorm<Infinity>() < 0.02
     __device__ __forceinline__ bool stop(const S* a, const S* b) const {
         S m = S(0);
-        for (int i = 0; i < nLinks; ++i) {
+#pragma unroll
+        for (int i = 0; i < (EXACT ? MAXD_ : nLinks); ++i) {
             const S d = fp::abs_(a[i] - b[i]);
             m = d > m ? d : m;
         }
@@ -156,7 +160,8 @@ struct ArmValidator {
     // the rounding of k midpoints (each within an ulp of the coordinates' magnitude); 1/64 relative + that absolute slack
     __device__ __forceinline__ int levels(const S* a, const S* b) const {
         S m = S(0), mag = S(1);
-        for (int i = 0; i < nLinks; ++i) {
+#pragma unroll
+        for (int i = 0; i < (EXACT ? MAXD_ : nLinks); ++i) {
             const S d = fp::abs_(a[i] - b[i]);
             m = d > m ? d : m;
             mag = fmax(mag, fmax(fp::abs_(a[i]), fp::abs_(b[i])));
@@ -644,7 +649,10 @@ int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) 
 #define MPTG_ARM_LINK(MD)                                                                                          \
     {                                                                                                              \
         ArmValidator<S, MD> v{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
-        if (armFlat) {                                                                                             \
+        if (armFlat && g->nLinks == MD && MD <= armExactMax) {                                                     \
+            ArmValidator<S, MD, true> ve{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
+            if (int rc = flatLink<S, ArmValidator<S, MD, true>>(g, ve, from, to, n, ok)) return rc;                \
+        } else if (armFlat) {                                                                                      \
             if (int rc = flatLink<S, ArmValidator<S, MD>>(g, v, from, to, n, ok)) return rc;                       \
         } else {                                                                                                   \
             bisectLinkKernel<S, ArmValidator<S, MD>><<<wgrid, wblock, 0, ctx->stream>>>(v, from, to, n, ok, g->devStats); \
@@ -652,6 +660,7 @@ int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) 
         }                                                                                                          \
     }
             static const bool armFlat = getenv("MPTG_ARM_WARP_PER_EDGE") == nullptr;  // the earlier kernel stays selectable for comparisons
+            static const int armExactMax = getenv("MPTG_ARM_EXACT_MAX") ? atoi(getenv("MPTG_ARM_EXACT_MAX")) : 16;
             if (g->nLinks <= 8) MPTG_ARM_LINK(8)
             else if (g->nLinks <= 16) MPTG_ARM_LINK(16)
             else if (g->nLinks <= 32) MPTG_ARM_LINK(32)
