@@ -773,8 +773,11 @@ template <typename S, typename KEYK>
 int orderWave(mptg_ctx* ctx, BvhArgs<S>& a, KEYK keyKernel, size_t smem) {
     if (!(a.Q >= 4096 && a.top >= 1)) return MPTG_OK;
     const dim3 grid((a.Q + BVH_WARPS - 1) / BVH_WARPS), block(BVH_WARPS * 32);
+    // bins of a few neighbouring leaves: the unit of locality is the level-0 block of 32 leaves, and the one-CTA scan of
+    // the histogram is on the critical path of every wave (32,769 bins: 28 us; 4,097: a few)
+    static const uint32_t maxBins = getenv("MPTG_ORDER_BINS") ? (uint32_t)atoi(getenv("MPTG_ORDER_BINS")) : 4096u;
     uint32_t shift = 0;
-    while ((a.nNodes[0] >> shift) > 65536u) ++shift;
+    while ((a.nNodes[0] >> shift) > maxBins) ++shift;
     const uint32_t bins = (a.nNodes[0] >> shift) + 1u;
     void* buf;
     int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
