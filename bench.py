@@ -70,40 +70,77 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed regions (B200_PROFILING.md recipe): NVML polled every millisecond from
+    a thread (the timed region of the default run is ~20 ms, too short for `nvidia-smi -lms 100`, which is the fallback)."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []  # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
         self.proc = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.source = None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.rows.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "nvml, 1 ms"
+            return
+        except Exception:
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi -lms 100"
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            try:
+                mask = sum(bit for i, (_, bit) in enumerate(self.REASONS) if len(c) > 3 + i and c[3 + i].lower().startswith("active"))
+                self.rows.append((float(c[0]), mask))
+                self.max_mhz = max(self.max_mhz or 0.0, float(c[1]))
+            except (ValueError, IndexError):
+                pass
 
     def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=1)
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except subprocess.TimeoutExpired:
                 self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = [n for n, bit in self.REASONS if any(r[1] & bit for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "source": self.source, "covers": "the device-timed steps and the two end-to-end passes"}
 
 
 def workload(rank: int):
@@ -327,9 +364,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     knn_ms, edge_ms, wall, launches = timed(step_device)
-    clocks = sampler.stop() if rank == 0 else None
     e2e_knn_ms, e2e_edge_ms, _, _ = timed(step_e2e)
     pg_knn_ms, pg_edge_ms, _, _ = timed(step_e2e_pageable)
+    clocks = sampler.stop() if rank == 0 else None
 
     knn_stats = nn.last_stats()
     mesh_stats = mesh.last_stats()
