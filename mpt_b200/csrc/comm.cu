@@ -273,7 +273,7 @@ int queryShardedT(mptg_comm* c, mptg_knn* shard, const S* queries, uint32_t Q, u
     MPTG_LAUNCHED(ctx);
     MARK(1);
     // 2. home search
-    if (int rc = knnShardQuery(shard, queries, Q, k, radius, cap, idx, dist, false)) return rc;
+    if (int rc = knnShardQuery(shard, queries, Q, k, radius, cap, idx, dist)) return rc;
     MARK(2);
     if (G > 1) {
         shardBoundKernel<S><<<g256, 256, 0, st>>>(dist, Q, k, bound);
@@ -285,7 +285,7 @@ int queryShardedT(mptg_comm* c, mptg_knn* shard, const S* queries, uint32_t Q, u
         // 3. bounded search of the queries of other homes that reach this shard
         shardCapKernel<S><<<g256, 256, 0, st>>>(lbMine, home, bound, me, Q, cap);
         MPTG_LAUNCHED(ctx);
-        if (int rc = knnShardQuery(shard, queries, Q, k, radius, cap, idx, dist, true)) return rc;
+        if (int rc = knnShardQuery(shard, queries, Q, k, radius, cap, idx, dist)) return rc;
     }
     MARK(4);
     if (G > 1) {

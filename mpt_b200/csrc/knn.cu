@@ -893,9 +893,9 @@ __global__ void shardUnionKernel(const S* __restrict__ peerBox, const uint32_t* 
     shardBox[(size_t)g * 2 * D + D + c] = hi;
 }
 template <typename S>
-int shardQueryT(mptg_knn* knn, const S* q, uint32_t Q, uint32_t k, double radius, const S* qcap, uint32_t* idxOut, S* distOut, bool secondPass) {
+int shardQueryT(mptg_knn* knn, const S* q, uint32_t Q, uint32_t k, double radius, const S* qcap, uint32_t* idxOut, S* distOut) {
     return knnBvhQuery<S>(knn->ctx, knn->index, knn->space, q, Q, k, radius, knn->idxMul, knn->idxAdd, idxOut, distOut, nullptr, knn->stats, knn->gid, qcap,
-                          nullptr, secondPass);
+                          nullptr);
 }
 }  // namespace
 
@@ -940,10 +940,10 @@ int knnShardRootAll(mptg_knn* knn, const void* shardBox, const uint32_t* peerN, 
 }
 // search with a per-query radius cap (scalar type of the space; < 0: skip the query, its output row is left alone)
 int knnShardQuery(mptg_knn* knn, const void* queriesDev, uint32_t Q, uint32_t k, double radius, const void* qcapDev, uint32_t* idxOut,
-                  void* distOut, bool secondPass) {
+                  void* distOut) {
     if (knn->size == 0) return MPTG_OK;
-    return knn->scalar == MPTG_F32 ? shardQueryT<float>(knn, (const float*)queriesDev, Q, k, radius, (const float*)qcapDev, idxOut, (float*)distOut, secondPass)
-                                   : shardQueryT<double>(knn, (const double*)queriesDev, Q, k, radius, (const double*)qcapDev, idxOut, (double*)distOut, secondPass);
+    return knn->scalar == MPTG_F32 ? shardQueryT<float>(knn, (const float*)queriesDev, Q, k, radius, (const float*)qcapDev, idxOut, (float*)distOut)
+                                   : shardQueryT<double>(knn, (const double*)queriesDev, Q, k, radius, (const double*)qcapDev, idxOut, (double*)distOut);
 }
 
 }  // namespace mptg

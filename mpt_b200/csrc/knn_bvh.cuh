@@ -152,7 +152,7 @@ struct BvhArgs {
     uint32_t* countOut;
     unsigned long long* stats;
     uint32_t* cursor;  // next position of the wave (persistent warps), zeroed before the launch
-    bool reuseOrder;      // the processing order computed by the previous search of this wave is still in place
+    const uint32_t* nActive;  // ordered waves with a per-query cap: the order lists only the queries whose cap is >= 0, this many
     const uint32_t* gid;  // optional: reported index of stored point i is gid[i] (spatially sharded sets) instead of i * idxMul + idxAdd
     const S* qcap;     // optional per-query radius cap (sharded search): < 0 skips the query and leaves its output row alone
     float* rootLb;     // root-bound pass only: lower bound of every query to the whole indexed set
@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhKeyKernel(const BvhArgs<
     const int D = a.sp.D;
     const uint32_t q = blockIdx.x * BVH_WARPS + warp;
     if (q >= a.Q) return;
+    if (a.qcap && a.qcap[q] < S(0)) return;  // not searched in this pass: not in the order
     S* myq = qsm + warp * D;
     for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
     __syncwarp();
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnBvhRootBoundKernel(const Bv
 }
 
 // exclusive scan of up to 65536 bins by one CTA
-__global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint32_t bins) {
+__global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint32_t bins, uint32_t* total) {
     __shared__ uint32_t part[1024];
     const uint32_t per = (bins + 1023u) / 1024u;
     const uint32_t b0 = threadIdx.x * per;
@@ -427,6 +428,7 @@ __global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint3
         part[threadIdx.x] += v;
         __syncthreads();
     }
+    if (threadIdx.x == 1023) *total = part[1023];
     uint32_t run = part[threadIdx.x] - sum;
     for (uint32_t i = b0; i < b0 + per && i < bins; ++i) {
         const uint32_t c = hist[i];
@@ -435,9 +437,11 @@ __global__ void __launch_bounds__(1024) knnOrderScanKernel(uint32_t* hist, uint3
     }
 }
 
-__global__ void knnOrderScatterKernel(const uint32_t* keys, uint32_t* cursor, uint32_t shift, uint32_t Q, uint32_t* order) {
+template <typename S>
+__global__ void knnOrderScatterKernel(const uint32_t* keys, uint32_t* cursor, uint32_t shift, uint32_t Q, const S* __restrict__ qcap, uint32_t* order) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
+    if (qcap && qcap[q] < S(0)) return;
     order[atomicAdd(cursor + (keys[q] >> shift), 1u)] = q;
 }
 
@@ -456,11 +460,12 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, MPTG_BVH_MIN_CTAS) knnBvhKerne
     const int D = a.sp.D;
     S* myq = qsm + warp * D;
     uint32_t leaves = 0, inner = 0;
+    const uint32_t nSlots = a.nActive ? __ldg(a.nActive) : a.Q;
     for (;;) {
         uint32_t slot = 0;
         if (lane == 0) slot = atomicAdd(a.cursor, 1u);
         slot = __shfl_sync(FULL_MASK, slot, 0);
-        if (slot >= a.Q) break;  // warp-uniform; no block-wide barriers in this kernel
+        if (slot >= nSlots) break;  // warp-uniform; no block-wide barriers in this kernel
         const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
         __syncwarp();
         for (int c = lane; c < D; c += 32) myq[c] = a.queries[(size_t)q * D + c];
@@ -780,24 +785,24 @@ int orderWave(mptg_ctx* ctx, BvhArgs<S>& a, KEYK keyKernel, size_t smem) {
     while ((a.nNodes[0] >> shift) > maxBins) ++shift;
     const uint32_t bins = (a.nNodes[0] >> shift) + 1u;
     void* buf;
-    int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins) * sizeof(uint32_t), &buf);
+    int rc = scratch(ctx, 6, ((size_t)2 * a.Q + bins + 1) * sizeof(uint32_t), &buf);
     if (rc) return rc;
     uint32_t* order = (uint32_t*)buf;
-    if (a.reuseOrder) {  // the caller has just searched the same wave on the same structure (sharded search, second pass)
-        a.order = order;
-        return MPTG_OK;
-    }
     a.orderKeys = order + a.Q;
     a.orderHist = order + 2 * (size_t)a.Q;
     a.orderShift = shift;
+    uint32_t* total = a.orderHist + bins;
+    // With a per-query cap (sharded search) the order lists only the queries this pass searches -- at 8 GPUs one in
+    // eight -- so the persistent warps do not draw, look up and skip the others one counter increment at a time.
     MPTG_CUDA(ctx, cudaMemsetAsync(a.orderHist, 0, bins * sizeof(uint32_t), ctx->stream));
     keyKernel<<<grid, block, smem, ctx->stream>>>(a);
     MPTG_LAUNCHED(ctx);
-    knnOrderScanKernel<<<1, 1024, 0, ctx->stream>>>(a.orderHist, bins);
+    knnOrderScanKernel<<<1, 1024, 0, ctx->stream>>>(a.orderHist, bins, total);
     MPTG_LAUNCHED(ctx);
-    knnOrderScatterKernel<<<(a.Q + 255) / 256, 256, 0, ctx->stream>>>(a.orderKeys, a.orderHist, shift, a.Q, order);
+    knnOrderScatterKernel<S><<<(a.Q + 255) / 256, 256, 0, ctx->stream>>>(a.orderKeys, a.orderHist, shift, a.Q, a.qcap, order);
     MPTG_LAUNCHED(ctx);
     a.order = order;
+    if (a.qcap) a.nActive = total;
     return MPTG_OK;
 }
 
@@ -824,10 +829,8 @@ inline void launchSe3RootBound(mptg_ctx*, BvhArgs<double>&, dim3, dim3) {}
 template <typename S>
 int knnBvhQuery(mptg_ctx* ctx, KnnIndex& ix, const mptg_space_desc& space, const S* queries, uint32_t Q, uint32_t k,
                 double radius, uint32_t idxMul, uint32_t idxAdd, uint32_t* idxOut, S* distOut, uint32_t* countOut,
-                uint64_t* /*hostStats*/, const uint32_t* gid = nullptr, const S* qcap = nullptr, float* rootLbOut = nullptr,
-                bool reuseOrder = false) {
+                uint64_t* /*hostStats*/, const uint32_t* gid = nullptr, const S* qcap = nullptr, float* rootLbOut = nullptr) {
     BvhArgs<S> a{};
-    a.reuseOrder = reuseOrder;
     a.gid = gid;
     a.qcap = qcap;
     a.rootLb = rootLbOut;

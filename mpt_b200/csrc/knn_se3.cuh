@@ -256,11 +256,12 @@ __global__ void __launch_bounds__(BVH_WARPS * 32, KPL == 1 ? MPTG_SE3_MIN_CTAS :
 #ifdef MPTG_KNN_PROBE
     uint32_t useful = 0, cand = 0;
 #endif
+    const uint32_t nSlots = a.nActive ? __ldg(a.nActive) : a.Q;
     for (;;) {
         uint32_t slot = 0;
         if (lane == 0) slot = atomicAdd(a.cursor, 1u);
         slot = __shfl_sync(FULL_MASK, slot, 0);
-        if (slot >= a.Q) break;  // warp-uniform; no block-wide barriers in this kernel
+        if (slot >= nSlots) break;  // warp-uniform; no block-wide barriers in this kernel
         const uint32_t q = a.order ? __ldg(a.order + slot) : slot;
         float radius = a.radius;
         if (a.qcap) {  // sharded search: per-query cap, negative = not this shard's query
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(BVH_WARPS * 32) knnSe3KeyKernel(const BvhArgs<
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x * BVH_WARPS + warp;
     if (q >= a.Q) return;
+    if (a.qcap && a.qcap[q] < 0.0f) return;  // not searched in this pass: not in the order
     float* sq = qsm[warp];
     if (lane < 7) sq[lane] = a.queries[(size_t)q * 7u + lane];
     se3QueryPrep(sq, a, lane);

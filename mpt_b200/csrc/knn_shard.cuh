@@ -18,8 +18,8 @@ int knnShardUnion(mptg_knn* knn, const void* peerBox, const uint32_t* peerN, int
 // boxes, cap[q] = +inf where home == rank, -1 elsewhere
 int knnShardRootAll(mptg_knn* knn, const void* shardBox, const uint32_t* peerN, int world, int rank, const void* queriesDev, uint32_t Q, float* lbMine,
                     uint8_t* home, void* cap);
-// search with a per-query radius cap (< 0: skip the query, its output row is left alone).  secondPass: the same wave has
-// just been searched on this structure (its processing order is reused).
+// search with a per-query radius cap (< 0: skip the query, its output row is left alone; large waves are ordered over the
+// queries that are searched only).
 int knnShardQuery(mptg_knn* knn, const void* queriesDev, uint32_t Q, uint32_t k, double radius, const void* qcapDev, uint32_t* idxOut,
-                  void* distOut, bool secondPass);
+                  void* distOut);
 }  // namespace mptg
