@@ -649,9 +649,11 @@ int linkDevT(mptg_geom* g, const S* from, const S* to, uint32_t n, uint8_t* ok) 
 #define MPTG_ARM_LINK(MD)                                                                                          \
     {                                                                                                              \
         ArmValidator<S, MD> v{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
-        if (armFlat && g->nLinks == MD && MD <= armExactMax) {                                                     \
-            ArmValidator<S, MD, true> ve{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
-            if (int rc = flatLink<S, ArmValidator<S, MD, true>>(g, ve, from, to, n, ok)) return rc;                \
+        if (armFlat && g->nLinks == MD && MD <= armExactMax && MD <= 32) {                                         \
+            if constexpr (MD <= 32) { /* the register form of a 64-link arm does not exist */                      \
+                ArmValidator<S, MD, true> ve{(const S*)g->lengths, (const S*)g->circles, g->nLinks, g->nCircles, (S)g->linkRadius}; \
+                if (int rc = flatLink<S, ArmValidator<S, MD, true>>(g, ve, from, to, n, ok)) return rc;            \
+            }                                                                                                      \
         } else if (armFlat) {                                                                                      \
             if (int rc = flatLink<S, ArmValidator<S, MD>>(g, v, from, to, n, ok)) return rc;                       \
         } else {                                                                                                   \

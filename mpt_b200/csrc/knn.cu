@@ -475,6 +475,16 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
     // split the scan so that the grid fills the machine (~4 CTAs per SM) when there are few queries
     uint32_t splits = 1;
     const uint32_t wantCtas = (uint32_t)ctx->smCount * 4;
+    if (!multiQuery && qBlocks < wantCtas) {
+        // ... and over a small set (a young planner tree: a few hundred queries, a few thousand points) in pieces shorter than
+        // a full tile, up to 16 of them: one warp's pass over 1,024 points with its insertions is a serial chain of ~50 us for
+        // k > 32 -- the whole cost of such a wave
+        uint32_t ws = (wantCtas + qBlocks - 1) / qBlocks;
+        if (ws > 16) ws = 16;
+        uint32_t per = (((n + ws - 1) / ws + 31) / 32) * 32;
+        if (per < 128) per = 128;
+        if (per < tile) tile = per;
+    }
     if (qBlocks < wantCtas) {
         splits = (wantCtas + qBlocks - 1) / qBlocks;
         const uint32_t maxSplits = (n + tile - 1) / tile;

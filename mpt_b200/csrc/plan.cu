@@ -20,6 +20,8 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "geom.cuh"
@@ -1186,6 +1188,69 @@ int mptg_pprm_get_graph(mptg_pprm* p, uint32_t first, uint32_t count, void* stat
 // nearest ancestor first.
 namespace mptg {
 
+// Item counts of the steps of a wave.  A wave with host synchronisation launches exactly `rows` items (nDev null); a QUEUED
+// wave launches an upper bound and the kernels read the count the previous step left on the device (starWaveQueuedT).
+__device__ __forceinline__ uint32_t starCount(uint32_t rows, const uint32_t* nDev) {
+    const uint32_t n = nDev ? *nDev : rows;
+    return n < rows ? n : rows;
+}
+
+// Ordered compaction of up to a few ten thousand flags by ONE CTA (queued waves: cub::DeviceSelect is two launches and a
+// dispatch on the host per call, three calls per wave): out[] = the indices i < n with f0[i] && f1[i] && f2[i] (f1, f2 may be
+// null) in increasing order, *count = how many.  16 flags per thread and pass.  `init`: words to preset for the wave
+// (init[0] = no goal node yet, init[1] = no rewires yet), null to leave alone.
+constexpr int COMPACT_THREADS = 1024, COMPACT_PER = 16;
+__global__ void __launch_bounds__(COMPACT_THREADS) starCompactKernel(const uint8_t* __restrict__ f0, const uint8_t* __restrict__ f1,
+                                                                     const uint8_t* __restrict__ f2, uint32_t n, uint32_t* __restrict__ out,
+                                                                     uint32_t* __restrict__ count, uint32_t* __restrict__ init) {
+    __shared__ uint32_t warpSum[COMPACT_THREADS / 32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry = 0;
+        if (init) init[0] = MPTG_NO_INDEX, init[1] = 0u;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += COMPACT_THREADS * COMPACT_PER) {
+        const uint32_t first = base + threadIdx.x * COMPACT_PER;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < COMPACT_PER; ++j) {
+            const uint32_t i = first + j;
+            if (i < n && f0[i] && (!f1 || f1[i]) && (!f2 || f2[i])) bits |= 1u << j;
+        }
+        const uint32_t mine = __popc(bits);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) warpSum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warpSum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += v;
+            }
+            warpSum[lane] = w;  // inclusive over the warps
+        }
+        __syncthreads();
+        uint32_t pos = carry + (warp ? warpSum[warp - 1] : 0u) + incl - mine;
+        while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            out[pos++] = first + (uint32_t)j;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warpSum[COMPACT_THREADS / 32 - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = carry;
+}
+
 template <typename S>
 __global__ void starSteerKernel(DevSpace<S> sp, const S* __restrict__ nodes, const S* __restrict__ samples, const uint32_t* __restrict__ nearIdx,
                                 const S* __restrict__ nearDist, const uint32_t* __restrict__ nearCnt, uint32_t n, S range, S* __restrict__ from,
@@ -1219,10 +1284,17 @@ __global__ void starSteerKernel(DevSpace<S> sp, const S* __restrict__ nodes, con
 }
 
 template <typename S>
-__global__ void starGatherKernel(const uint32_t* __restrict__ sel, uint32_t n, int D, const S* __restrict__ to, const uint32_t* __restrict__ nearIdx,
-                                 const S* __restrict__ dNew, S* __restrict__ fresh, uint32_t* __restrict__ nearOf, S* __restrict__ dOf) {
+__global__ void starGatherKernel(const uint32_t* __restrict__ sel, uint32_t rows, const uint32_t* __restrict__ nDev, int D, const S* __restrict__ to,
+                                 const uint32_t* __restrict__ nearIdx, const S* __restrict__ dNew, S* __restrict__ fresh, uint32_t* __restrict__ nearOf,
+                                 S* __restrict__ dOf, const S* __restrict__ filler) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    if (s >= rows) return;
+    if (s >= starCount(rows, nDev)) {  // queued wave: a defined state in the rows past the survivors (their results are never read)
+        for (int c = 0; c < D; ++c) fresh[(size_t)s * D + c] = filler[c];
+        nearOf[s] = 0;
+        dOf[s] = S(0);
+        return;
+    }
     const uint32_t i = sel[s];
     for (int c = 0; c < D; ++c) fresh[(size_t)s * D + c] = to[(size_t)i * D + c];
     nearOf[s] = nearIdx[i];
@@ -1232,7 +1304,7 @@ __global__ void starGatherKernel(const uint32_t* __restrict__ sel, uint32_t n, i
 // one warp per survivor: rank the neighbours by cost + distance (stable), mark the ones the reference's loop could
 // test before it stops (cost cut-off or the near node), :565-605
 template <typename S>
-__global__ void __launch_bounds__(128) starRankKernel(uint32_t nS, uint32_t k, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+__global__ void __launch_bounds__(128) starRankKernel(uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
                                                       const uint32_t* __restrict__ nnCnt, const uint32_t* __restrict__ nearOf,
                                                       const S* __restrict__ dOf, const S* __restrict__ cost, uint8_t* __restrict__ order,
                                                       uint8_t* __restrict__ candFlag, uint8_t* __restrict__ checked, uint32_t* __restrict__ limit,
@@ -1240,7 +1312,11 @@ __global__ void __launch_bounds__(128) starRankKernel(uint32_t nS, uint32_t k, c
     __shared__ S sc[4][MPTG_MAX_K];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t s = blockIdx.x * 4 + warp;
-    if (s >= nS) return;
+    if (s >= rows) return;
+    if (s >= starCount(rows, nDev)) {  // queued wave: no candidates in the rows past the survivors
+        for (uint32_t j = lane; j < k; j += 32) candFlag[(size_t)s * k + j] = 0;
+        return;
+    }
     const uint32_t cnt = nnCnt[s], near = nearOf[s];
     const S parentCost = cost[near] + dOf[s];
     for (uint32_t j = lane; j < cnt; j += 32) sc[warp][j] = cost[nnIdx[(size_t)s * k + j]] + nnDist[(size_t)s * k + j];
@@ -1292,11 +1368,15 @@ __global__ void __launch_bounds__(128) starRankKernel(uint32_t nS, uint32_t k, c
 
 // edges for the flagged (survivor, slot) pairs; fromNode: neighbour -> new state (parent candidates) or new state -> neighbour (rewiring)
 template <typename S>
-__global__ void starEdgeKernel(const uint32_t* __restrict__ ids, uint32_t nE, uint32_t k, int D, bool towardsFresh, const S* __restrict__ fresh,
-                               const S* __restrict__ nodes, const uint32_t* __restrict__ nnIdx, S* __restrict__ from, S* __restrict__ to,
-                               uint32_t* __restrict__ inv) {
+__global__ void starEdgeKernel(const uint32_t* __restrict__ ids, uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, int D, bool towardsFresh,
+                               const S* __restrict__ fresh, const S* __restrict__ nodes, const uint32_t* __restrict__ nnIdx, S* __restrict__ from,
+                               S* __restrict__ to, uint32_t* __restrict__ inv) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nE) return;
+    if (e >= rows) return;
+    if (e >= starCount(rows, nDev)) {  // queued wave: the edges past the count go from the root to itself (one state to check)
+        for (int c = 0; c < D; ++c) from[(size_t)e * D + c] = to[(size_t)e * D + c] = nodes[c];
+        return;
+    }
     const uint32_t id = ids[e], s = id / k;
     if (inv) inv[id] = e;
     const S* pf = fresh + (size_t)s * D;
@@ -1308,13 +1388,13 @@ __global__ void starEdgeKernel(const uint32_t* __restrict__ ids, uint32_t nE, ui
 
 // first valid candidate in rank order becomes the parent; append node, parent, cost; goal test (:607-622)
 template <typename S>
-__global__ void starAppendKernel(DevSpace<S> sp, uint32_t nS, uint32_t k, const S* __restrict__ fresh, const uint32_t* __restrict__ nnIdx,
+__global__ void starAppendKernel(DevSpace<S> sp, uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, const S* __restrict__ fresh, const uint32_t* __restrict__ nnIdx,
                                  const S* __restrict__ nnDist, const uint8_t* __restrict__ order, const uint32_t* __restrict__ limit,
                                  const uint32_t* __restrict__ nearRank, uint8_t* __restrict__ checked, const uint32_t* __restrict__ inv,
                                  const uint8_t* __restrict__ okCand, const uint32_t* __restrict__ nearOf, const S* __restrict__ defCost, uint32_t size, const S* __restrict__ goal, S goalRadius, S* __restrict__ nodes,
                                  uint32_t* __restrict__ parent, S* __restrict__ cost, uint32_t* __restrict__ goalList) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nS) return;
+    if (s >= starCount(rows, nDev)) return;
     const int D = sp.D;
     uint32_t par = nearOf[s];
     S c = defCost[s];
@@ -1346,14 +1426,14 @@ __global__ void starAppendKernel(DevSpace<S> sp, uint32_t nS, uint32_t k, const 
 
 // rewiring offers: unchecked neighbours whose cost would drop (:626-637)
 template <typename S>
-__global__ void starRewireFlagKernel(uint32_t nS, uint32_t k, uint32_t size, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+__global__ void starRewireFlagKernel(uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, uint32_t size, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
                                      const uint32_t* __restrict__ nnCnt, const uint8_t* __restrict__ checked, const S* __restrict__ cost,
                                      uint8_t* __restrict__ flag) {
     const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= (size_t)nS * k) return;
+    if (id >= (size_t)rows * k) return;
     const uint32_t s = (uint32_t)(id / k), j = (uint32_t)(id % k);
     bool f = false;
-    if (j < nnCnt[s] && !checked[id]) f = cost[size + s] + nnDist[id] < cost[nnIdx[id]];
+    if (s < starCount(rows, nDev) && j < nnCnt[s] && !checked[id]) f = cost[size + s] + nnDist[id] < cost[nnIdx[id]];
     flag[id] = f ? 1 : 0;
 }
 
@@ -1361,30 +1441,30 @@ __device__ __forceinline__ unsigned long long starCostKey(double c) {  // costs 
     return (unsigned long long)__double_as_longlong(c + 0.0);
 }
 template <typename S>
-__global__ void starRewireMinKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+__global__ void starRewireMinKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, uint32_t size,
                                     const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
                                     unsigned long long* __restrict__ bestKey) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nR || !ok[e]) return;
+    if (e >= starCount(rows, nDev) || !ok[e]) return;
     const uint32_t id = ids[e];
     atomicMin(bestKey + nnIdx[id], starCostKey((double)(cost[size + id / k] + nnDist[id])));
 }
 template <typename S>
-__global__ void starRewirePickKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+__global__ void starRewirePickKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, uint32_t size,
                                      const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
                                      const unsigned long long* __restrict__ bestKey, uint32_t* __restrict__ bestCand) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nR || !ok[e]) return;
+    if (e >= starCount(rows, nDev) || !ok[e]) return;
     const uint32_t id = ids[e], nb = nnIdx[id];
     if (starCostKey((double)(cost[size + id / k] + nnDist[id])) == bestKey[nb]) atomicMin(bestCand + nb, e);
 }
 template <typename S>
-__global__ void starRewireApplyKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t nR, uint32_t k, uint32_t size,
+__global__ void starRewireApplyKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t rows, const uint32_t* __restrict__ nDev, uint32_t k, uint32_t size,
                                       const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist, const S* __restrict__ cost,
                                       const uint32_t* __restrict__ bestCand, uint32_t* __restrict__ parent, S* __restrict__ delta,
                                       uint32_t* __restrict__ counters) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nR || !ok[e]) return;
+    if (e >= starCount(rows, nDev) || !ok[e]) return;
     const uint32_t id = ids[e], nb = nnIdx[id];
     if (bestCand[nb] != e) return;
     const uint32_t from = size + id / k;
@@ -1394,11 +1474,16 @@ __global__ void starRewireApplyKernel(const uint32_t* __restrict__ ids, const ui
 }
 // nonConcurrentPushUpdate (:664-688) for all re-parented nodes at once
 template <typename S>
-__global__ void starPushKernel(uint32_t n, const uint32_t* __restrict__ parent, const S* __restrict__ delta, S* __restrict__ cost,
-                               const uint32_t* __restrict__ applied) {
+__global__ void starPushKernel(uint32_t nBefore, uint32_t rows, const uint32_t* __restrict__ nDev, const uint32_t* __restrict__ parent,
+                               const S* __restrict__ delta, S* __restrict__ cost, const uint32_t* __restrict__ applied,
+                               unsigned long long* __restrict__ bestKey, uint32_t* __restrict__ bestCand) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = nBefore + starCount(rows, nDev);  // the tree after this wave's appends
     if (i >= n) return;
     if (*applied == 0u) return;  // no node was re-parented in this wave: every decrease is zero, nothing to push
+    // the offers of this wave are spent (an offer exists only where something was applied): leave the per-node slots of the
+    // old nodes as the next wave expects them, so that a queued wave needs no memset for them
+    if (i < nBefore) bestKey[i] = ~0ull, bestCand[i] = MPTG_NO_INDEX;
     S c = cost[i];
     bool changed = false;
     uint32_t steps = 0;  // a path has fewer than n nodes; the bound keeps a corrupted tree from hanging the device
@@ -1427,6 +1512,78 @@ __global__ void starGoalKernel(const uint32_t* __restrict__ goalList, const S* _
     if (mineIdx != MPTG_NO_INDEX && mine == best) atomicMin(result, mineIdx);
 }
 
+// The rewiring tail of a queued wave on a young tree as ONE CTA: clear the decreases, best offer per old node (the three
+// passes of starRewireMin/Pick/ApplyKernel), push the decreases down the subtrees, restore the offer slots, best goal node.
+// Same arithmetic and the same atomics as the separate kernels -- the barriers stand where the launches were; six
+// operations of a wave whose cost is its number of operations.  result[0] / result[1] are preset by the
+// wave's first compaction.
+constexpr int TAIL_THREADS = 1024;
+template <typename S>
+__global__ void __launch_bounds__(TAIL_THREADS) starRewireTailKernel(const uint32_t* __restrict__ ids, const uint8_t* __restrict__ ok, uint32_t rows,
+                                                                    const uint32_t* __restrict__ nRDev, uint32_t waveRows, const uint32_t* __restrict__ nSDev,
+                                                                    uint32_t k, uint32_t size, const uint32_t* __restrict__ nnIdx, const S* __restrict__ nnDist,
+                                                                    S* cost, unsigned long long* bestKey, uint32_t* bestCand, uint32_t* parent, S* delta,
+                                                                    const uint32_t* goalList, uint32_t* result) {
+    __shared__ unsigned long long best;
+    __shared__ uint32_t applied;
+    const uint32_t nR = starCount(rows, nRDev), n = size + starCount(waveRows, nSDev);
+    if (threadIdx.x == 0) best = ~0ull, applied = 0u;
+    for (uint32_t i = threadIdx.x; i < n; i += TAIL_THREADS) delta[i] = S(0);
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < nR; e += TAIL_THREADS) {  // starRewireMinKernel
+        if (!ok[e]) continue;
+        const uint32_t id = ids[e];
+        atomicMin(bestKey + nnIdx[id], starCostKey((double)(cost[size + id / k] + nnDist[id])));
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < nR; e += TAIL_THREADS) {  // starRewirePickKernel
+        if (!ok[e]) continue;
+        const uint32_t id = ids[e], nb = nnIdx[id];
+        if (starCostKey((double)(cost[size + id / k] + nnDist[id])) == *(volatile unsigned long long*)(bestKey + nb)) atomicMin(bestCand + nb, e);
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < nR; e += TAIL_THREADS) {  // starRewireApplyKernel
+        if (!ok[e]) continue;
+        const uint32_t id = ids[e], nb = nnIdx[id];
+        if (*(volatile uint32_t*)(bestCand + nb) != e) continue;
+        const uint32_t from = size + id / k;
+        parent[nb] = from;
+        delta[nb] = cost[nb] - (cost[from] + nnDist[id]);  // :647
+        atomicAdd(&applied, 1u);
+    }
+    __syncthreads();
+    if (applied != 0u) {  // starPushKernel
+        if (threadIdx.x == 0) result[1] = applied;
+        // two passes: every node reads the OLD costs of nobody but itself, yet the decreases must all be read before the
+        // offer slots are restored -- they are different arrays, so one loop does both
+        for (uint32_t i = threadIdx.x; i < n; i += TAIL_THREADS) {
+            S c = cost[i];
+            bool changed = false;
+            uint32_t steps = 0;
+            for (uint32_t a = i; a != MPTG_NO_INDEX && steps < n; a = *(volatile uint32_t*)(parent + a), ++steps) {
+                const S d = *(volatile S*)(delta + a);
+                if (d > S(0)) c = c - d, changed = true;
+            }
+            if (changed) cost[i] = c;
+            if (i < size) bestKey[i] = ~0ull, bestCand[i] = MPTG_NO_INDEX;
+        }
+    }
+    __syncthreads();
+    if (goalList != nullptr) {  // starGoalKernel
+        const uint32_t ng = min(goalList[0], 65535u);
+        unsigned long long mine = ~0ull;
+        uint32_t mineIdx = MPTG_NO_INDEX;
+        for (uint32_t g = threadIdx.x; g < ng; g += TAIL_THREADS) {
+            const uint32_t id = goalList[1 + g];
+            const unsigned long long key = starCostKey((double)*(volatile S*)(cost + id));
+            if (key < mine || (key == mine && id < mineIdx)) mine = key, mineIdx = id;
+        }
+        atomicMin(&best, mine);
+        __syncthreads();
+        if (mineIdx != MPTG_NO_INDEX && mine == best) atomicMin(result, mineIdx);
+    }
+}
+
 }  // namespace mptg
 
 struct mptg_prrtstar {
@@ -1451,7 +1608,12 @@ struct mptg_prrtstar {
     uint8_t *alive = nullptr, *okValid = nullptr, *okLink = nullptr, *keep = nullptr, *order = nullptr, *flag = nullptr, *checked = nullptr, *okEdge = nullptr;
     void* selTemp = nullptr;
     size_t selBytes = 0;
-    uint32_t* host = nullptr;  // pinned: [0] select count, [1] best goal node, [2] rewires applied
+    uint32_t* host = nullptr;  // pinned: [0] select count, [1] best goal node, [2] rewires applied, [3] survivors of a queued wave
+    uint32_t* cnt = nullptr;   // device: survivors, candidate-parent edges, rewiring edges of a queued wave
+    uint32_t queuedMax = 1024; // waves up to this size run without host synchronisation between their steps (starWaveQueuedT)
+    bool timing = false;       // MPTG_STAR_TIMING=1: host time spent issuing the queued waves / waiting for them, printed at destroy
+    double issueUs = 0, waitUs = 0;
+    uint64_t queuedWaves = 0, queuedLaunches = 0;
 };
 
 namespace {
@@ -1463,7 +1625,7 @@ void starFree(mptg_prrtstar* p) {
                     p->samples, p->from, p->to, p->fresh, p->nearDist, p->dNew, p->dOf, p->defCost, p->nnDist, p->eFrom, p->eTo, (void*)p->nearIdx,
                     (void*)p->nearCnt, (void*)p->sel, (void*)p->nSel, (void*)p->nearOf, (void*)p->nnIdx, (void*)p->nnCnt, (void*)p->limit, (void*)p->nearRank,
                     (void*)p->ids, (void*)p->inv, (void*)p->result, (void*)p->alive, (void*)p->okValid, (void*)p->okLink, (void*)p->keep,
-                    (void*)p->order, (void*)p->flag, (void*)p->checked, (void*)p->okEdge, p->selTemp})
+                    (void*)p->order, (void*)p->flag, (void*)p->checked, (void*)p->okEdge, p->selTemp, (void*)p->cnt})
         cudaFree(q);
     if (p->host) cudaFreeHost(p->host);
     delete p;
@@ -1514,8 +1676,120 @@ int starAllocNeighbourBuffers(mptg_prrtstar* p) {
     return rc;
 }
 
+// A wave WITHOUT host synchronisation between its steps, for the small waves of a young tree: the
+// three compaction counts (survivors, candidate-parent edges, rewiring edges) stay on the device, every step is launched
+// over an upper bound of its items -- W survivors, W k edges -- and reads the count the step before it left (starCount);
+// rows past a count hold defined filler whose results nobody reads.  Same kernels, same arithmetic, same tree as
+// starWaveT (tests/test_gpu_parity.py compares the two on the same seed); one synchronisation at the end, for the new size.
+// Launching the bounds costs nothing while W k is a few ten thousand edges; larger waves keep the exact launches.
+template <typename S>
+int starWaveQueuedT(mptg_prrtstar* p, uint32_t W) {
+    mptg_ctx* ctx = p->ctx;
+    cudaStream_t st = ctx->stream;
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint64_t launches0 = ctx->launches;
+    const DevSpace<S> sp = makeDevSpace<S>(p->space);
+    const int D = p->D;
+    const uint32_t grid = (W + 127) / 128;
+    const bool biased = p->hasGoal && p->goalBias > 0 && p->goalNode == MPTG_NO_INDEX;  // :468-481
+    sampleKernel<S><<<grid, 128, 0, st>>>(sp, (const S*)p->bounds, (const S*)p->bounds + D, p->seed, p->drawn, W, biased ? (const S*)p->goal : nullptr,
+                                          (S)p->goalBias, (S*)p->samples);
+    MPTG_LAUNCHED(ctx);
+    p->drawn += W;
+    if (int rc = mptg_knn_query_dev(p->knn, p->samples, W, 1, -1.0, p->nearIdx, p->nearDist, p->nearCnt)) return rc;  // :517
+    starSteerKernel<S><<<grid, 128, 0, st>>>(sp, (const S*)p->nodes, (const S*)p->samples, p->nearIdx, (const S*)p->nearDist, p->nearCnt, W,
+                                             (S)p->range, (S*)p->from, (S*)p->to, (S*)p->dNew, p->alive);
+    MPTG_LAUNCHED(ctx);
+    if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid, nullptr)) return rc;                              // :539
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink, nullptr)) return rc;  // :545
+    // result[0] best goal node, [1] rewires applied, [2] survivors: one copy to the host at the end
+    uint32_t *nS = p->result + 2, *nE = p->cnt, *nR = p->cnt + 1;
+    auto select = [&](const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, uint32_t n, uint32_t* out, uint32_t* count, uint32_t* init) {
+        starCompactKernel<<<1, COMPACT_THREADS, 0, st>>>(f0, f1, f2, n, out, count, init);
+        MPTG_LAUNCHED(ctx);
+    };
+    select(p->alive, p->okValid, p->okLink, W, p->sel, nS, p->result);
+    ++p->waves;
+    starGatherKernel<S><<<grid, 128, 0, st>>>(p->sel, W, nS, D, (const S*)p->to, p->nearIdx, (const S*)p->dNew, (S*)p->fresh, p->nearOf, (S*)p->dOf,
+                                              (const S*)p->nodes);
+    MPTG_LAUNCHED(ctx);
+    // neighbourhoods (:559-562)
+    uint32_t k = starK<S>(p->rewireFactor, p->dims, p->size);
+    double radius = -1.0;
+    if (p->rRRG > 0) {
+        const S n1 = (S)(p->size + 1.0);
+        radius = (double)((S)p->rRRG * std::pow(std::log(n1) / n1, S(1) / (S)p->dims));
+        k = p->stride;
+    }
+    if (k > p->stride) k = p->stride;
+    if (int rc = mptg_knn_query_dev(p->knn, p->fresh, W, k, radius, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
+    starRankKernel<S><<<(W + 3) / 4, 128, 0, st>>>(W, nS, k, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->nearOf, (const S*)p->dOf, (const S*)p->cost, p->order,
+                                                  p->flag, p->checked, p->limit, p->nearRank, (S*)p->defCost);
+    MPTG_LAUNCHED(ctx);
+    // candidate parents, one link batch (:580-605)
+    const uint32_t WK = W * k, gridE = (WK + 127) / 128;
+    select(p->flag, nullptr, nullptr, WK, p->ids, nE, nullptr);
+    starEdgeKernel<S><<<gridE, 128, 0, st>>>(p->ids, WK, nE, k, D, true, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom, (S*)p->eTo, p->inv);
+    MPTG_LAUNCHED(ctx);
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, WK, p->linkStep, p->okEdge, nullptr)) return rc;
+    starAppendKernel<S><<<grid, 128, 0, st>>>(sp, W, nS, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank, p->checked,
+                                              p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
+                                              (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList);
+    MPTG_LAUNCHED(ctx);
+    // rewire (:626-656)
+    starRewireFlagKernel<S><<<gridE, 128, 0, st>>>(W, nS, k, p->size, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->checked, (const S*)p->cost, p->flag);
+    MPTG_LAUNCHED(ctx);
+    select(p->flag, nullptr, nullptr, WK, p->ids, nR, nullptr);
+    starEdgeKernel<S><<<gridE, 128, 0, st>>>(p->ids, WK, nR, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom, (S*)p->eTo, nullptr);
+    MPTG_LAUNCHED(ctx);
+    if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, WK, p->linkStep, p->okEdge, nullptr)) return rc;
+    const uint32_t bound = p->size + W;  // <= capacity (checked by the caller)
+    if (bound <= (1u << 15)) {  // young tree: the whole tail in one CTA
+        starRewireTailKernel<S><<<1, TAIL_THREADS, 0, st>>>(p->ids, p->okEdge, WK, nR, W, nS, k, p->size, p->nnIdx, (const S*)p->nnDist, (S*)p->cost, p->bestKey,
+                                                           p->bestCand, p->parent, (S*)p->delta, p->hasGoal ? p->goalList : nullptr, p->result);
+        MPTG_LAUNCHED(ctx);
+    } else {
+    MPTG_CUDA(ctx, cudaMemsetAsync(p->delta, 0, (size_t)bound * sizeof(S), st));  // (bestKey / bestCand: left clean by every push pass)
+    starRewireMinKernel<S><<<gridE, 128, 0, st>>>(p->ids, p->okEdge, WK, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey);
+    MPTG_LAUNCHED(ctx);
+    starRewirePickKernel<S><<<gridE, 128, 0, st>>>(p->ids, p->okEdge, WK, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey,
+                                                  p->bestCand);
+    MPTG_LAUNCHED(ctx);
+    starRewireApplyKernel<S><<<gridE, 128, 0, st>>>(p->ids, p->okEdge, WK, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestCand,
+                                                   p->parent, (S*)p->delta, p->result + 1);
+    MPTG_LAUNCHED(ctx);
+    starPushKernel<S><<<(bound + 127) / 128, 128, 0, st>>>(p->size, W, nS, p->parent, (const S*)p->delta, (S*)p->cost, p->result + 1, p->bestKey, p->bestCand);
+    MPTG_LAUNCHED(ctx);
+    if (p->hasGoal) {
+        starGoalKernel<S><<<1, 256, 0, st>>>(p->goalList, (const S*)p->cost, p->result);
+        MPTG_LAUNCHED(ctx);
+    }
+    }
+    MPTG_CUDA(ctx, cudaMemcpyAsync(p->host + 1, p->result, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    const auto t1 = std::chrono::steady_clock::now();
+    MPTG_CUDA(ctx, cudaStreamSynchronize(st));
+    if (p->timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        p->issueUs += std::chrono::duration<double, std::micro>(t1 - t0).count();
+        p->waitUs += std::chrono::duration<double, std::micro>(t2 - t1).count();
+        p->queuedLaunches += ctx->launches - launches0;
+        ++p->queuedWaves;
+    }
+    const uint32_t added = p->host[3];
+    p->goalNode = p->host[1];
+    p->rewires += p->host[2];
+    if (added) {
+        uint32_t first = 0;
+        if (int rc = mptg_knn_insert_dev(p->knn, p->fresh, added, &first)) return rc;  // :619 (asynchronous: the next wave's search follows it on the stream)
+        if (first != p->size) return fail(ctx, MPTG_ERR_CUDA, "mptg_prrtstar_wave: node numbering out of step");
+    }
+    p->size += added;
+    return MPTG_OK;
+}
+
 template <typename S>
 int starWaveT(mptg_prrtstar* p, uint32_t W) {
+    if (W <= p->queuedMax && (uint64_t)p->size + W <= p->capacity && (uint64_t)W * p->stride <= (1u << 16)) return starWaveQueuedT<S>(p, W);
     mptg_ctx* ctx = p->ctx;
     cudaStream_t st = ctx->stream;
     const DevSpace<S> sp = makeDevSpace<S>(p->space);
@@ -1539,8 +1813,8 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
     if (nS > p->capacity - p->size) nS = p->capacity - p->size;
     ++p->waves;
     if (nS == 0) return MPTG_OK;
-    starGatherKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(p->sel, nS, D, (const S*)p->to, p->nearIdx, (const S*)p->dNew, (S*)p->fresh, p->nearOf,
-                                                         (S*)p->dOf);
+    starGatherKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(p->sel, nS, nullptr, D, (const S*)p->to, p->nearIdx, (const S*)p->dNew, (S*)p->fresh, p->nearOf,
+                                                         (S*)p->dOf, nullptr);
     MPTG_LAUNCHED(ctx);
     // neighbourhoods (:559-562)
     uint32_t k = starK<S>(p->rewireFactor, p->dims, p->size);
@@ -1552,32 +1826,32 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
     }
     if (k > p->stride) k = p->stride;
     if (int rc = mptg_knn_query_dev(p->knn, p->fresh, nS, k, radius, p->nnIdx, p->nnDist, p->nnCnt)) return rc;
-    starRankKernel<S><<<(nS + 3) / 4, 128, 0, st>>>(nS, k, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->nearOf, (const S*)p->dOf, (const S*)p->cost,
+    starRankKernel<S><<<(nS + 3) / 4, 128, 0, st>>>(nS, nullptr, k, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->nearOf, (const S*)p->dOf, (const S*)p->cost,
                                                    p->order, p->flag, p->checked, p->limit, p->nearRank, (S*)p->defCost);
     MPTG_LAUNCHED(ctx);
     // candidate parents, one link batch (:580-605)
     uint32_t nE = 0;
     if (int rc = starSelect(p, p->flag, (size_t)nS * k, p->ids, &nE)) return rc;
     if (nE) {
-        starEdgeKernel<S><<<(nE + 127) / 128, 128, 0, st>>>(p->ids, nE, k, D, true, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
+        starEdgeKernel<S><<<(nE + 127) / 128, 128, 0, st>>>(p->ids, nE, nullptr, k, D, true, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
                                                            (S*)p->eTo, p->inv);
         MPTG_LAUNCHED(ctx);
         if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nE, p->linkStep, p->okEdge, nullptr)) return rc;
     }
-    starAppendKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(sp, nS, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank,
+    starAppendKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(sp, nS, nullptr, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank,
                                                          p->checked, p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
                                                          (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList);
     MPTG_LAUNCHED(ctx);
     // rewire (:626-656)
     const size_t nSK = (size_t)nS * k;
-    starRewireFlagKernel<S><<<(unsigned)((nSK + 127) / 128), 128, 0, st>>>(nS, k, p->size, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->checked,
+    starRewireFlagKernel<S><<<(unsigned)((nSK + 127) / 128), 128, 0, st>>>(nS, nullptr, k, p->size, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->checked,
                                                                           (const S*)p->cost, p->flag);
     MPTG_LAUNCHED(ctx);
     uint32_t nR = 0;
     if (int rc = starSelect(p, p->flag, nSK, p->ids, &nR)) return rc;
     const uint32_t total = p->size + nS;
     if (nR) {
-        starEdgeKernel<S><<<(nR + 127) / 128, 128, 0, st>>>(p->ids, nR, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
+        starEdgeKernel<S><<<(nR + 127) / 128, 128, 0, st>>>(p->ids, nR, nullptr, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom,
                                                            (S*)p->eTo, nullptr);
         MPTG_LAUNCHED(ctx);
         if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nR, p->linkStep, p->okEdge, nullptr)) return rc;
@@ -1586,15 +1860,16 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
         MPTG_CUDA(ctx, cudaMemsetAsync(p->delta, 0, (size_t)total * sizeof(S), st));
         MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
         const uint32_t gr = (nR + 127) / 128;
-        starRewireMinKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey);
+        starRewireMinKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, nullptr, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey);
         MPTG_LAUNCHED(ctx);
-        starRewirePickKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey,
+        starRewirePickKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, nullptr, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestKey,
                                                     p->bestCand);
         MPTG_LAUNCHED(ctx);
-        starRewireApplyKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestCand,
+        starRewireApplyKernel<S><<<gr, 128, 0, st>>>(p->ids, p->okEdge, nR, nullptr, k, p->size, p->nnIdx, (const S*)p->nnDist, (const S*)p->cost, p->bestCand,
                                                      p->parent, (S*)p->delta, p->result + 1);
         MPTG_LAUNCHED(ctx);
-        starPushKernel<S><<<(total + 127) / 128, 128, 0, st>>>(total, p->parent, (const S*)p->delta, (S*)p->cost, p->result + 1);
+        starPushKernel<S><<<(total + 127) / 128, 128, 0, st>>>(p->size, nS, nullptr, p->parent, (const S*)p->delta, (S*)p->cost, p->result + 1, p->bestKey,
+                                                               p->bestCand);
         MPTG_LAUNCHED(ctx);
     } else {
         MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
@@ -1647,15 +1922,19 @@ int mptg_prrtstar_create(mptg_ctx* ctx, mptg_geom* geom, const mptg_prrt_params*
     alloc(&p->samples, W * sb), alloc(&p->from, W * sb), alloc(&p->to, W * sb), alloc(&p->fresh, W * sb);
     alloc(&p->nearDist, W * sc), alloc(&p->dNew, W * sc), alloc(&p->dOf, W * sc), alloc(&p->defCost, W * sc);
     alloc(&p->nearIdx, W * 4), alloc(&p->nearCnt, W * 4), alloc(&p->sel, W * 4), alloc(&p->nearOf, W * 4), alloc(&p->limit, W * 4), alloc(&p->nearRank, W * 4);
-    alloc(&p->nSel, 4), alloc(&p->result, 8);
+    alloc(&p->nSel, 4), alloc(&p->result, 16), alloc(&p->cnt, 16);
     alloc(&p->alive, W), alloc(&p->okValid, W), alloc(&p->okLink, W), alloc(&p->keep, W);
     alloc(&p->nnCnt, W * 4);
+    p->timing = getenv("MPTG_STAR_TIMING") != nullptr;
+    if (const char* e = getenv("MPTG_STAR_QUEUED_MAX")) p->queuedMax = (uint32_t)atoi(e);  // 0: every wave with host synchronisation (comparisons, tests)
     if (!rc) rc = starAllocNeighbourBuffers(p);
     if (!rc && p->hasGoal) {
         alloc(&p->goal, sb);
         if (!rc) rc = uploadSync(ctx, p->goal, prm->goal_state, sb);
     }
     if (!rc) rc = memsetSync(ctx, p->goalList, 0, 65536 * 4);
+    if (!rc) rc = memsetSync(ctx, p->bestKey, 0xFF, (size_t)p->capacity * 8);  // "no offer": the state every push pass restores
+    if (!rc) rc = memsetSync(ctx, p->bestCand, 0xFF, (size_t)p->capacity * 4);
     if (!rc && cudaMallocHost((void**)&p->host, 4 * sizeof(uint32_t)) != cudaSuccess) rc = fail(ctx, MPTG_ERR_OOM, "mptg_prrtstar_create: pinned allocation failed");
     if (rc) {
         starFree(p);
@@ -1681,6 +1960,9 @@ int mptg_prrtstar_destroy(mptg_prrtstar* p) {
     if (!p) return MPTG_OK;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    if (p->timing && p->queuedWaves)
+        fprintf(stderr, "[mptg prrt*] %llu queued waves: %.1f us issuing + %.1f us waiting per wave, %.1f kernel launches per wave\n",
+                (unsigned long long)p->queuedWaves, p->issueUs / p->queuedWaves, p->waitUs / p->queuedWaves, (double)p->queuedLaunches / p->queuedWaves);
     starFree(p);
     return MPTG_OK;
 }

@@ -641,6 +641,45 @@ def test_device_prrtstar_replays_its_wave_semantics_on_the_oracle(ctx, oracle):
         pl.close()
 
 
+def test_device_prrtstar_queued_waves_build_the_same_tree(ctx, oracle, monkeypatch):
+    """Waves of up to 1,024 samples run without host synchronisation between their steps (plan.cu starWaveQueuedT: counts
+    stay on the device, launches cover upper bounds); MPTG_STAR_QUEUED_MAX=0 keeps the synchronised wave.  Same seed,
+    same waves: states, parents, costs, rewires and goal node must be identical -- on the grid (k nearest and radius
+    rewiring) and on the 8-link arm (flat edge check behind the same calls)."""
+    occ = W.synthetic_grid(500, 400, seed=2)
+    free = np.argwhere(occ == 0)
+    start, goal = free[len(free) // 7][::-1].astype(np.float64), free[-len(free) // 9][::-1].astype(np.float64)
+    r_rrg = 1.1 * (2 * 1.5 * (occ.shape[1] - 1) * (occ.shape[0] - 1) / np.pi) ** 0.5
+    lengths, radius, circles = W.link_arm_scene(8)
+    cand = W.box_states(256, 8, 3, -np.pi, np.pi)
+    free8 = cand[oracle.link_arm(lengths, radius, circles).valid(cand) != 0]
+    cases = [
+        ("grid", lambda: m.Scenario.grid(ctx, occ, m.F64), m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], start, goal, 12.0, 30.0, None,
+         (64, 128, 256, 512, 512, 1024, 37, 1, 512)),
+        ("grid, radius", lambda: m.Scenario.grid(ctx, occ, m.F64), m.lp_space(2, 2, m.F64), [0, 0], [occ.shape[1] - 1, occ.shape[0] - 1], start, goal, 12.0, 30.0,
+         r_rrg, (64, 128, 256, 256, 256)),
+        ("arm", lambda: m.Scenario.link_arm(ctx, lengths, radius, circles, m.F64), m.lp_space(8, 1, m.F64), [-np.pi] * 8, [np.pi] * 8, free8[0],
+         free8[1], 0.5, 2.0, None, (64, 128, 256, 512, 512)),
+    ]
+    for name, make, sp, lo, hi, s0, g, g_rad, rng, rr, waves in cases:
+        trees = []
+        for queued_max in ("0", "1024"):
+            monkeypatch.setenv("MPTG_STAR_QUEUED_MAX", queued_max)
+            sc = make()
+            pl = m.DevicePRRTStar(sc, sp, lo, hi, range=rng, goal=g, goal_radius=g_rad, goal_bias=0.05, rewire_radius=rr, seed=5, capacity=1 << 13,
+                                  max_wave=1024)
+            pl.add_start(s0)
+            for w in waves:
+                pl.wave(w)
+            trees.append(pl.tree(with_costs=True) + (pl.rewires, pl.goal_node, pl.samples_drawn))
+            pl.close()
+            sc.close()
+        (st, pa, co, rew, gn, drawn), other = trees
+        assert st.shape[0] > 100 and (rew > 0 or name == "arm"), (name, st.shape, rew)  # (8-D: few offers lower a cost this early)
+        assert np.array_equal(st, other[0]) and np.array_equal(pa, other[1]) and np.array_equal(co, other[2]), name
+        assert (rew, gn, drawn) == other[3:], name
+
+
 def test_device_prrtstar_and_pprm_on_meshes_se3_f32(ctx, oracle):
     """SE(3) rigid body among meshes, float32 states (BASELINE configs[2]): the device-resident PRRT* and PPRM build
     graphs whose every node is valid and every edge a valid motion on the oracle (near-contact items excepted and
