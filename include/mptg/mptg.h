@@ -384,7 +384,9 @@ int mptg_prrtstar_set_rewire_radius(mptg_prrtstar* star, double r_rrg);
 int mptg_prrtstar_destroy(mptg_prrtstar* star);
 int mptg_prrtstar_add_start(mptg_prrtstar* star, const void* state);
 /* goal_node_out: the goal node of smallest cost so far (Planner::solution() / solutionCost(), :317-337), MPTG_NO_INDEX
- * while unsolved. */
+ * while unsolved.  Waves of up to 1,024 samples are queued on the device without host synchronisation between their steps
+ * (one at the end); the tree is the same either way.  Environment: MPTG_STAR_QUEUED_MAX=n moves that limit (0: never),
+ * MPTG_STAR_TIMING=1 prints the host time spent issuing / waiting per queued wave when the planner is destroyed. */
 int mptg_prrtstar_wave(mptg_prrtstar* star, uint32_t n_samples, uint32_t* size_out, uint32_t* goal_node_out);
 uint32_t mptg_prrtstar_size(const mptg_prrtstar* star);
 uint64_t mptg_prrtstar_samples_drawn(const mptg_prrtstar* star);

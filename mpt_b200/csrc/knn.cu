@@ -364,6 +364,87 @@ __global__ void __launch_bounds__(256) knnMergeKernel(uint32_t parts, uint32_t Q
     if (countOut && lane == 0) countOut[q] = count;
 }
 
+// The same merge for up to 64 lists, using that every list is ASCENDING in (distance, index) with its empty slots at the
+// end (the contract of mptg_knn_merge_dev and what every search stores): lane p holds the head of list p (and of list
+// p + 32), one step picks the smallest head of the warp -- three or two REDUX over the key words, the bit patterns of
+// non-negative distances order like unsigned integers -- and only the winner advances, its next entry already loaded.
+// k steps of ~100 cycles, where inserting parts x k candidates one by one into a WarpTopK costs ~500 cycles each
+// (16 lists of 36: 63 us -> a few; profiles/r2_launches_ramp_prrtstar_queued.txt).
+__device__ __forceinline__ int warpArgMin(float d, uint32_t i, bool& none) {
+    const uint32_t ub = __float_as_uint(d + 0.0f);
+    const uint32_t m = __reduce_min_sync(FULL_MASK, ub);
+    const uint32_t mi = __reduce_min_sync(FULL_MASK, ub == m ? i : MPTG_NO_INDEX);
+    none = mi == MPTG_NO_INDEX;
+    return __ffs(__ballot_sync(FULL_MASK, ub == m && i == mi)) - 1;
+}
+__device__ __forceinline__ int warpArgMin(double d, uint32_t i, bool& none) {
+    const unsigned long long ub = (unsigned long long)__double_as_longlong(d + 0.0);
+    const uint32_t hi = (uint32_t)(ub >> 32), lo = (uint32_t)ub;
+    const uint32_t mh = __reduce_min_sync(FULL_MASK, hi);
+    const uint32_t ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xFFFFFFFFu);
+    const bool at = hi == mh && lo == ml;
+    const uint32_t mi = __reduce_min_sync(FULL_MASK, at ? i : MPTG_NO_INDEX);
+    none = mi == MPTG_NO_INDEX;
+    return __ffs(__ballot_sync(FULL_MASK, at && i == mi)) - 1;
+}
+template <typename S>
+__global__ void __launch_bounds__(256) knnMergeHeadsKernel(uint32_t parts, uint32_t Q, uint32_t k, const uint32_t* __restrict__ idxIn,
+                                                           const S* __restrict__ distIn, uint32_t* __restrict__ idxOut, S* __restrict__ distOut,
+                                                           uint32_t* __restrict__ countOut) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= Q) return;
+    const S inf = fp::consts<S>::inf();
+    const bool liveA = (uint32_t)lane < parts, liveB = (uint32_t)lane + 32u < parts;
+    const size_t rowA = ((size_t)(liveA ? lane : 0) * Q + q) * k, rowB = ((size_t)(liveB ? lane + 32 : 0) * Q + q) * k;
+    auto load = [&](bool live, size_t row, uint32_t pos, S& d, uint32_t& i) {
+        const bool have = live && pos < k;
+        d = have ? distIn[row + pos] : inf;
+        i = have ? idxIn[row + pos] : MPTG_NO_INDEX;
+        if (i == MPTG_NO_INDEX) d = inf;  // an empty slot: nothing follows it in its list
+    };
+    S dA, dB, ndA, ndB;
+    uint32_t iA, iB, niA, niB, posA = 2, posB = 2;
+    load(liveA, rowA, 0, dA, iA), load(liveA, rowA, 1, ndA, niA);
+    load(liveB, rowB, 0, dB, iB), load(liveB, rowB, 1, ndB, niB);
+    S outD = inf;
+    uint32_t outI = MPTG_NO_INDEX;
+    uint32_t t = 0;
+    for (; t < k; ++t) {
+        const bool useB = dB < dA || (dB == dA && iB < iA);
+        const S d = useB ? dB : dA;
+        const uint32_t i = useB ? iB : iA;
+        bool none;
+        const int src = warpArgMin(d, i, none);
+        if (none) break;  // every head is an empty slot
+        const S wd = __shfl_sync(FULL_MASK, d, src);
+        const uint32_t wi = __shfl_sync(FULL_MASK, i, src);
+        if ((t & 31u) == (uint32_t)lane) outD = wd, outI = wi;
+        if (lane == src) {
+            if (useB) {
+                dB = ndB, iB = niB;
+                load(liveB, rowB, posB++, ndB, niB);
+            } else {
+                dA = ndA, iA = niA;
+                load(liveA, rowA, posA++, ndA, niA);
+            }
+        }
+        if ((t & 31u) == 31u) {  // 32 results: one coalesced store
+            idxOut[(size_t)q * k + (t - 31u) + lane] = outI;
+            distOut[(size_t)q * k + (t - 31u) + lane] = outD;
+            outD = inf, outI = MPTG_NO_INDEX;
+        }
+    }
+    // the results of the last, partial group of 32 and the empty slots behind them
+    const uint32_t base = t & ~31u;
+    for (uint32_t j = base + lane; j < k; j += 32) {
+        const bool mine = j < t;  // only the first round of this loop can hold results
+        idxOut[(size_t)q * k + j] = mine ? outI : MPTG_NO_INDEX;
+        distOut[(size_t)q * k + j] = mine ? outD : inf;
+    }
+    if (countOut && lane == 0) countOut[q] = t;
+}
+
 // AoS -> SoA append
 template <typename S>
 __global__ void knnScatterKernel(const S* aos, uint32_t count, int D, S* pts, uint32_t stride, uint32_t first) {
@@ -411,6 +492,12 @@ int launchMerge(mptg_ctx* ctx, uint32_t parts, uint32_t Q, uint32_t k, const uin
                 uint32_t* idxOut, S* distOut, uint32_t* countOut) {
     if (Q == 0) return MPTG_OK;
     const dim3 grid((Q + 7) / 8), block(256);
+    static const bool insertionMerge = getenv("MPTG_KNN_INSERTION_MERGE") != nullptr;  // the earlier kernel, for comparisons
+    if (parts <= 64 && !insertionMerge) {
+        knnMergeHeadsKernel<S><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
+        MPTG_LAUNCHED(ctx);
+        return MPTG_OK;
+    }
     if (k <= 32) knnMergeKernel<S, 1><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
     else if (k <= 64) knnMergeKernel<S, 2><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
     else knnMergeKernel<S, 4><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
@@ -475,7 +562,7 @@ int bruteScan(mptg_knn* knn, uint32_t begin, uint32_t end, const S* queries, uin
     // split the scan so that the grid fills the machine (~4 CTAs per SM) when there are few queries
     uint32_t splits = 1;
     const uint32_t wantCtas = (uint32_t)ctx->smCount * 4;
-    if (!multiQuery && qBlocks < wantCtas) {
+    if (!multiQuery && qBlocks < wantCtas && n > 1024) {
         // ... and over a small set (a young planner tree: a few hundred queries, a few thousand points) in pieces shorter than
         // a full tile, up to 16 of them: one warp's pass over 1,024 points with its insertions is a serial chain of ~50 us for
         // k > 32 -- the whole cost of such a wave

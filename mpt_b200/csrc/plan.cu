@@ -155,6 +155,10 @@ __global__ void prrtSteerKernel(DevSpace<S> sp, const S* __restrict__ nodes, con
     }
 }
 
+// ordered compaction by one CTA (defined with the PRRT* kernels below)
+__global__ void starCompactKernel(const uint8_t* __restrict__ f0, const uint8_t* __restrict__ f1, const uint8_t* __restrict__ f2, uint32_t n,
+                                  uint32_t* __restrict__ out, uint32_t* __restrict__ count, uint32_t* __restrict__ init);
+
 __global__ void prrtFlagKernel(const uint8_t* __restrict__ alive, const uint8_t* __restrict__ okValid, const uint8_t* __restrict__ okLink,
                                uint32_t n, uint8_t* __restrict__ keep) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -358,12 +362,17 @@ int prrtWaveT(mptg_prrt* p, uint32_t W) {
     // valid, link (prrt.hpp:439-441)
     if (int rc = mptg_valid_batch_dev(p->geom, p->to, W, p->okValid, nullptr)) return rc;
     if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->from, p->to, W, p->linkStep, p->okLink, nullptr)) return rc;
-    prrtFlagKernel<<<grid, 128, 0, ctx->stream>>>(p->alive, p->okValid, p->okLink, W, p->keep);
-    MPTG_LAUNCHED(ctx);
-    size_t bytes = p->selBytes;
-    MPTG_CUDA(ctx, cub::DeviceSelect::Flagged(p->selTemp, bytes, thrust::counting_iterator<uint32_t>(0), p->keep, p->sel, p->nSel, (int)W,
-                                              ctx->stream));
-    MPTG_LAUNCHED(ctx);
+    if (W <= 16384) {  // young tree, small wave: the wave costs its number of launches -- flags and compaction in one, by one CTA
+        starCompactKernel<<<1, 1024, 0, ctx->stream>>>(p->alive, p->okValid, p->okLink, W, p->sel, p->nSel, nullptr);
+        MPTG_LAUNCHED(ctx);
+    } else {
+        prrtFlagKernel<<<grid, 128, 0, ctx->stream>>>(p->alive, p->okValid, p->okLink, W, p->keep);
+        MPTG_LAUNCHED(ctx);
+        size_t bytes = p->selBytes;
+        MPTG_CUDA(ctx, cub::DeviceSelect::Flagged(p->selTemp, bytes, thrust::counting_iterator<uint32_t>(0), p->keep, p->sel, p->nSel, (int)W,
+                                                  ctx->stream));
+        MPTG_LAUNCHED(ctx);
+    }
     prrtAppendKernel<S><<<grid, 128, 0, ctx->stream>>>(sp, p->sel, p->nSel, (const S*)p->to, p->nearIdx, p->size, p->capacity,
                                                        p->hasGoal ? (const S*)p->goal : nullptr, (S)p->goalRadius, (S*)p->nodes, p->parent,
                                                        (S*)p->fresh, p->result);
@@ -1392,9 +1401,14 @@ __global__ void starAppendKernel(DevSpace<S> sp, uint32_t rows, const uint32_t* 
                                  const S* __restrict__ nnDist, const uint8_t* __restrict__ order, const uint32_t* __restrict__ limit,
                                  const uint32_t* __restrict__ nearRank, uint8_t* __restrict__ checked, const uint32_t* __restrict__ inv,
                                  const uint8_t* __restrict__ okCand, const uint32_t* __restrict__ nearOf, const S* __restrict__ defCost, uint32_t size, const S* __restrict__ goal, S goalRadius, S* __restrict__ nodes,
-                                 uint32_t* __restrict__ parent, S* __restrict__ cost, uint32_t* __restrict__ goalList) {
+                                 uint32_t* __restrict__ parent, S* __restrict__ cost, uint32_t* __restrict__ goalList,
+                                 const uint32_t* __restrict__ nnCnt, uint8_t* __restrict__ rewireFlag) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= starCount(rows, nDev)) return;
+    if (s >= starCount(rows, nDev)) {
+        if (rewireFlag && s < rows)
+            for (uint32_t j = 0; j < k; ++j) rewireFlag[(size_t)s * k + j] = 0;
+        return;
+    }
     const int D = sp.D;
     uint32_t par = nearOf[s];
     S c = defCost[s];
@@ -1420,6 +1434,15 @@ __global__ void starAppendKernel(DevSpace<S> sp, uint32_t rows, const uint32_t* 
         if (dg <= goalRadius) {
             const uint32_t slot = atomicAdd(goalList, 1u);
             if (slot < 65535u) goalList[1 + slot] = id;
+        }
+    }
+    if (rewireFlag) {  // queued wave: the offers of this row (starRewireFlagKernel) -- they need this row's cost and marks only
+        const uint32_t cnt = nnCnt[s];
+        for (uint32_t j = 0; j < k; ++j) {
+            const size_t e = (size_t)s * k + j;
+            bool f = false;
+            if (j < cnt && !checked[e]) f = c + nnDist[e] < cost[nnIdx[e]];
+            rewireFlag[e] = f ? 1 : 0;
         }
     }
 }
@@ -1734,11 +1757,9 @@ int starWaveQueuedT(mptg_prrtstar* p, uint32_t W) {
     if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, WK, p->linkStep, p->okEdge, nullptr)) return rc;
     starAppendKernel<S><<<grid, 128, 0, st>>>(sp, W, nS, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank, p->checked,
                                               p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
-                                              (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList);
+                                              (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList, p->nnCnt, p->flag);
     MPTG_LAUNCHED(ctx);
-    // rewire (:626-656)
-    starRewireFlagKernel<S><<<gridE, 128, 0, st>>>(W, nS, k, p->size, p->nnIdx, (const S*)p->nnDist, p->nnCnt, p->checked, (const S*)p->cost, p->flag);
-    MPTG_LAUNCHED(ctx);
+    // rewire (:626-656): the offers were flagged by the append kernel, row by row
     select(p->flag, nullptr, nullptr, WK, p->ids, nR, nullptr);
     starEdgeKernel<S><<<gridE, 128, 0, st>>>(p->ids, WK, nR, k, D, false, (const S*)p->fresh, (const S*)p->nodes, p->nnIdx, (S*)p->eFrom, (S*)p->eTo, nullptr);
     MPTG_LAUNCHED(ctx);
@@ -1840,7 +1861,7 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
     }
     starAppendKernel<S><<<(nS + 127) / 128, 128, 0, st>>>(sp, nS, nullptr, k, (const S*)p->fresh, p->nnIdx, (const S*)p->nnDist, p->order, p->limit, p->nearRank,
                                                          p->checked, p->inv, p->okEdge, p->nearOf, (const S*)p->defCost, p->size, p->hasGoal ? (const S*)p->goal : nullptr,
-                                                         (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList);
+                                                         (S)p->goalRadius, (S*)p->nodes, p->parent, (S*)p->cost, p->goalList, nullptr, nullptr);
     MPTG_LAUNCHED(ctx);
     // rewire (:626-656)
     const size_t nSK = (size_t)nS * k;
