@@ -493,7 +493,7 @@ int launchMerge(mptg_ctx* ctx, uint32_t parts, uint32_t Q, uint32_t k, const uin
     if (Q == 0) return MPTG_OK;
     const dim3 grid((Q + 7) / 8), block(256);
     static const bool insertionMerge = getenv("MPTG_KNN_INSERTION_MERGE") != nullptr;  // the earlier kernel, for comparisons
-    if (parts <= 64 && !insertionMerge) {
+    if (parts <= 64 && (parts >= 4 || k > 32) && !insertionMerge) {  // (two or three short lists: the insertions are as quick)
         knnMergeHeadsKernel<S><<<grid, block, 0, ctx->stream>>>(parts, Q, k, idxIn, distIn, idxOut, distOut, countOut);
         MPTG_LAUNCHED(ctx);
         return MPTG_OK;
