@@ -428,6 +428,51 @@ def test_knn_merge_sharded_equals_single(ctx, oracle):
     assert_knn_equal(got, oracle.tree(sp, pts).knn(q, k))
 
 
+def test_knn_merge_constructed_lists(ctx):
+    """mptg_knn_merge_dev on constructed lists against a plain sort: 1 to 64 lists (one and two heads per lane of the
+    head-selection kernel, and the insertion kernel for two or three short lists), k on both sides of every register
+    layout, lists of ragged length with their empty slots at the end, distances drawn from a handful of values so that
+    ties within and across lists are decided by the index, all-empty queries, zero and infinite distances; float32 and
+    float64."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    NO = np.uint32(0xFFFFFFFF)
+    for dt, scalar in ((np.float32, m.F32), (np.float64, m.F64)):
+        for parts, k, Q in ((1, 16, 50), (2, 1, 64), (3, 16, 33), (4, 16, 100), (8, 36, 77), (16, 36, 40), (33, 5, 31), (64, 49, 20), (64, 128, 9),
+                            (7, 64, 25), (32, 32, 17)):
+            values = np.concatenate(([0.0, np.inf], rng.random(6) * 10)).astype(dt)
+            idx = np.full((parts, Q, k), NO, dtype=np.uint32)
+            dist = np.full((parts, Q, k), np.inf, dtype=dt)
+            want_i = np.full((Q, k), NO, dtype=np.uint32)
+            want_d = np.full((Q, k), np.inf, dtype=dt)
+            want_c = np.zeros(Q, dtype=np.uint32)
+            for q in range(Q):
+                ids = rng.permutation(parts * k + 7).astype(np.uint32)  # distinct indices over the lists of a query
+                rows = []
+                for p_ in range(parts):
+                    n = 0 if q % 11 == 0 else int(rng.integers(0, k + 1))
+                    d = rng.choice(values, n) if q % 3 else (rng.random(n) * 5).astype(dt)
+                    i = ids[p_ * k:p_ * k + n]
+                    o = np.lexsort((i, d))
+                    idx[p_, q, :n], dist[p_, q, :n] = i[o], d[o]
+                    rows.append((d[o], i[o]))
+                d_all, i_all = np.concatenate([r[0] for r in rows]), np.concatenate([r[1] for r in rows])
+                o = np.lexsort((i_all, d_all))[:k]
+                want_i[q, :o.size], want_d[q, :o.size], want_c[q] = i_all[o], d_all[o], o.size
+            t_i, t_d = torch.from_numpy(idx.view(np.int32)).cuda(), torch.from_numpy(dist).cuda()
+            o_i = torch.empty((Q, k), dtype=torch.int32, device="cuda")
+            o_d = torch.empty((Q, k), dtype=t_d.dtype, device="cuda")
+            o_c = torch.empty(Q, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+            m.knn_merge_dev(ctx, scalar, parts, Q, k, t_i.data_ptr(), t_d.data_ptr(), o_i.data_ptr(), o_d.data_ptr(), o_c.data_ptr())
+            ctx.sync()
+            got = (o_i.cpu().numpy().view(np.uint32), o_d.cpu().numpy(), o_c.cpu().numpy().view(np.uint32))
+            assert np.array_equal(got[2], want_c), (parts, k, "counts")
+            assert np.array_equal(got[0], want_i), (parts, k, np.nonzero((got[0] != want_i).any(axis=1))[0][:5])
+            assert np.array_equal(got[1], want_d), (parts, k, "distances")
+
+
 # ------------------------------------------------------------------ BASELINE.json configs[4] at full size
 def test_c5_full_size_knn_properties(ctx, oracle):
     """N = 1,048,576 tree points, Q = 65,536 queries, k = 16 (the bench workload).  Size-independent properties on the
