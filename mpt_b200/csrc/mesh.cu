@@ -43,6 +43,8 @@ struct MeshDev {
     const TriPad* eTris;
     uint32_t nR, nE;  // triangle counts
     uint32_t stageR, stageE;  // nodes [0, stage) of each tree are copied into shared memory by every CTA (breadth-first prefix)
+    uint32_t rootX, rootY;    // the first entry of every state (meshRootEntry): the children of one root against the other root ...
+    uint32_t rootIsTri;       // ... or, when both hierarchies are a single triangle, that triangle pair
 };
 
 }  // namespace mptg
@@ -82,9 +84,9 @@ constexpr int MESH_WARPS = MESH_WARPS_PER_CTA;
 constexpr int MESH_MIN_CTAS = MESH_CTAS;  // resident CTAs per SM (caps registers per thread)
 constexpr size_t MESH_SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 constexpr int NODE_STACK = 512;
-constexpr size_t MESH_WARP_SMEM = 512 * 8 + 64 * 8 + 32 * 12 * 4 + 32 * 4;  // stack + triangle queue + transforms + items
+constexpr size_t MESH_WARP_SMEM = 512 * 8 + 96 * 8 + 32 * 12 * 4 + 32 * 4;  // stack + triangle queue + transforms + items
 constexpr int STACK_SOFT = NODE_STACK - 64 - 60;  // see the pop rule in meshFlatKernel
-constexpr int TRI_QUEUE = 64;
+constexpr int TRI_QUEUE = 96;  // fewer than 32 pending when a round starts, at most two more per lane in it
 
 struct WarpCounters {
     unsigned int bv = 0, tri = 0, states = 0;  // per lane (bv, tri) / per warp (states); summed into 64-bit totals at exit
@@ -311,7 +313,8 @@ __device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
 //         checked, and an edge already found invalid is skipped.
 constexpr int MESH_SLOTS = 32;
 constexpr unsigned SLOT_SHIFT = 27;
-constexpr unsigned NODE_MASK = (1u << SLOT_SHIFT) - 1u;
+constexpr unsigned SIDE_ENV = 1u << 26;  // stack entry: the pair of siblings to test is on the environment's side
+constexpr unsigned NODE_MASK = SIDE_ENV - 1u;
 constexpr int XF_STRIDE = 12;   // 48-byte rows: three 128-bit loads per box test, conflict-free for 8 consecutive slots
 constexpr int REFILL_AT = 16;   // refill when at most this many node pairs are pending
 constexpr int REFILL_MAX = 16;  // states started per refill
@@ -547,8 +550,14 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
                 const unsigned mp = __ballot_sync(FULL_MASK_, push);
                 dead &= ~mp;
                 fresh |= mp;
-                if (push) stack[n + __popc(mp & ltMask)] = make_uint2((unsigned)lane << SLOT_SHIFT, 0u);
-                n += __popc(mp);
+                // (the roots are not tested against each other: bounds only prune)
+                if (m.rootIsTri) {
+                    if (push) triQ[nt + __popc(mp & ltMask)] = make_uint2(m.rootX | ((unsigned)lane << SLOT_SHIFT), m.rootY);
+                    nt += __popc(mp);
+                } else {
+                    if (push) stack[n + __popc(mp & ltMask)] = make_uint2(m.rootX | ((unsigned)lane << SLOT_SHIFT), m.rootY);
+                    n += __popc(mp);
+                }
                 cnt.states += __popc(mp);
                 if (base + (unsigned long long)cap >= total) exhausted = true;
                 __syncwarp();
@@ -655,9 +664,13 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             }
         }
         if (n > 0) {
-            // Pop up to 32 pairs, fewer as the stack nears STACK_SOFT (each pop pushes at most two); from
-            // STACK_SOFT on it is one pair per round, a depth-first descent that can add at most
+            // Pop up to 32 entries, fewer as the stack nears STACK_SOFT (each pop pushes at most two); from
+            // STACK_SOFT on it is one entry per round, a depth-first descent that can add at most
             // depthR + depthE <= 56 more entries (checked at creation), which stays below the hard limit.
+            // An entry is a pair of nodes KNOWN to overlap, one of them already replaced by the first of its two children
+            // (siblings are neighbours in the node array): the lane tests both children against the other node -- two
+            // independent box tests in flight -- and pushes only what survives.  (r1/r2a pushed both children untested and
+            // popped them again, one test per lane and round: twice the stack traffic, rounds and votes per test.)
             int p = STACK_SOFT - n;
             p = p < 1 ? 1 : (p > 32 ? 32 : p);
             p = p < n ? p : n;
@@ -672,85 +685,87 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             __syncwarp();
             n -= p;
             const unsigned slot = pr.x >> SLOT_SHIFT;
+            const unsigned tag = slot << SLOT_SHIFT;
             mine = mine && !((dead >> slot) & 1u);
-            int kind = 0;  // 1: triangle pair, 2: expand robot node, 3: expand env node
-            int c0 = 0, c1 = 0;
+            int kind0 = 0, kind1 = 0;  // per test: 1 triangle pair, 2 stack entry
+            unsigned ex0 = 0u, ey0 = 0u, ex1 = 0u, ey1 = 0u;
             if (mine) {
-                const BvhNode a = loadNodeStaged(sR, m.stageR, m.rNodes, (int)(pr.x & NODE_MASK));
-                const BvhNode b = loadNodeStaged(sE, m.stageE, m.eNodes, (int)pr.y);
+                const bool sideE = (pr.x & SIDE_ENV) != 0u;
+                const int rid = (int)(pr.x & NODE_MASK), eid = (int)pr.y;
+                const BvhNode r0 = loadNodeStaged(sR, m.stageR, m.rNodes, rid);
+                const BvhNode e0 = loadNodeStaged(sE, m.stageE, m.eNodes, eid);
+                const BvhNode sib = loadNodeStaged(sideE ? sE : sR, sideE ? m.stageE : m.stageR, sideE ? m.eNodes : m.rNodes, (sideE ? eid : rid) + 1);
                 const float* X = xf[slot];
-                ++cnt.bv;
-                // robot box (centre c, half extents h in the robot frame) against the env box, separating
-                // axes = the three world axes and the three robot-frame axes; all bounds padded
-                const float cx = a.lo[0], cy = a.lo[1], cz = a.lo[2];  // device image: lo = centre, hi = half extent
-                const float hx = a.hi[0], hy = a.hi[1], hz = a.hi[2];
+                cnt.bv += 2;
                 const float4 x0 = *reinterpret_cast<const float4*>(X), x1 = *reinterpret_cast<const float4*>(X + 4),
                              x2 = *reinterpret_cast<const float4*>(X + 8);
                 const float R[9] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w, x2.x};
                 const float T[3] = {x2.y, x2.z, x2.w};
-                float d[3], hb[3], hw[3];
-                float mag = 0.0f;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const float cw = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, T[r])));
-                    hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
-                    const float cb = b.lo[r];
-                    hb[r] = b.hi[r];
-                    d[r] = cb - cw;
-                    mag += (fabsf(cw) + hw[r]) + (fabsf(cb) + hb[r]);
-                }
-                const float pad = 64.0f * 1.1920928955078125e-07f * mag + (NEAR ? w.tol : 0.0f);
-                bool ov = true;
+                for (int t = 0; t < 2; ++t) {
+                    // test 0: (r0, e0); test 1: the sibling on the entry's side against the other node
+                    const bool second = t == 1;
+                    const bool robotSib = second && !sideE, envSib = second && sideE;
+                    const float cx = robotSib ? sib.lo[0] : r0.lo[0], cy = robotSib ? sib.lo[1] : r0.lo[1], cz = robotSib ? sib.lo[2] : r0.lo[2];
+                    const float hx = robotSib ? sib.hi[0] : r0.hi[0], hy = robotSib ? sib.hi[1] : r0.hi[1], hz = robotSib ? sib.hi[2] : r0.hi[2];
+                    const int aLeft = robotSib ? sib.left : r0.left, bLeft = envSib ? sib.left : e0.left;
+                    const unsigned aId = (unsigned)(robotSib ? rid + 1 : rid), bId = (unsigned)(envSib ? eid + 1 : eid);
+                    // robot box (centre c, half extents h in the robot frame) against the env box, separating
+                    // axes = the three world axes and the three robot-frame axes; all bounds padded
+                    float d[3], hb[3], hw[3];
+                    float mag = 0.0f;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) ov = ov && !(fabsf(d[r]) > hw[r] + hb[r] + pad);
-                if (ov) {
-                    const float ha[3] = {hx, hy, hz};
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {  // robot-frame axis j = column j of R
-                        const float dl = __fmaf_rn(R[6 + j], d[2], __fmaf_rn(R[3 + j], d[1], R[j] * d[0]));
-                        const float el = __fmaf_rn(fabsf(R[6 + j]), hb[2], __fmaf_rn(fabsf(R[3 + j]), hb[1], fabsf(R[j]) * hb[0]));
-                        ov = ov && !(fabsf(dl) > ha[j] + el + pad);
+                    for (int r = 0; r < 3; ++r) {
+                        const float cw = __fmaf_rn(R[3 * r + 2], cz, __fmaf_rn(R[3 * r + 1], cy, __fmaf_rn(R[3 * r], cx, T[r])));
+                        hw[r] = __fmaf_rn(fabsf(R[3 * r + 2]), hz, __fmaf_rn(fabsf(R[3 * r + 1]), hy, fabsf(R[3 * r]) * hx));
+                        const float cb = envSib ? sib.lo[r] : e0.lo[r];
+                        hb[r] = envSib ? sib.hi[r] : e0.hi[r];
+                        d[r] = cb - cw;
+                        mag += (fabsf(cw) + hw[r]) + (fabsf(cb) + hb[r]);
                     }
-                }
-                if (ov) {
-                    const bool leafA = a.left < 0, leafB = b.left < 0;
-                    if (leafA && leafB) {
-                        kind = 1;
-                        c0 = -1 - a.left;
-                        c1 = -1 - b.left;
-                    } else {
-                        bool descendRobot;
-                        if (leafA) descendRobot = false;
-                        else if (leafB) descendRobot = true;
-                        else descendRobot = fmaxf(hx, fmaxf(hy, hz)) > fmaxf(hb[0], fmaxf(hb[1], hb[2]));
-                        if (descendRobot) {
-                            kind = 2;
-                            c0 = a.left;
-                            c1 = a.right;
-                        } else {
-                            kind = 3;
-                            c0 = b.left;
-                            c1 = b.right;
+                    const float pad = 64.0f * 1.1920928955078125e-07f * mag + (NEAR ? w.tol : 0.0f);
+                    bool ov = true;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) ov = ov && !(fabsf(d[r]) > hw[r] + hb[r] + pad);
+                    if (ov) {
+                        const float ha[3] = {hx, hy, hz};
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {  // robot-frame axis j = column j of R
+                            const float dl = __fmaf_rn(R[6 + j], d[2], __fmaf_rn(R[3 + j], d[1], R[j] * d[0]));
+                            const float el = __fmaf_rn(fabsf(R[6 + j]), hb[2], __fmaf_rn(fabsf(R[3 + j]), hb[1], fabsf(R[j]) * hb[0]));
+                            ov = ov && !(fabsf(dl) > ha[j] + el + pad);
                         }
                     }
+                    int kind = 0;
+                    unsigned ex = 0u, ey = 0u;
+                    if (ov) {
+                        const bool leafA = aLeft < 0, leafB = bLeft < 0;
+                        if (leafA && leafB) {
+                            kind = 1;
+                            ex = (unsigned)(-1 - aLeft) | tag;
+                            ey = (unsigned)(-1 - bLeft);
+                        } else {
+                            bool descendRobot;
+                            if (leafA) descendRobot = false;
+                            else if (leafB) descendRobot = true;
+                            else descendRobot = fmaxf(hx, fmaxf(hy, hz)) > fmaxf(hb[0], fmaxf(hb[1], hb[2]));
+                            kind = 2;
+                            ex = descendRobot ? ((unsigned)aLeft | tag) : (aId | tag | SIDE_ENV);
+                            ey = descendRobot ? bId : (unsigned)bLeft;
+                        }
+                    }
+                    if (second) kind1 = kind, ex1 = ex, ey1 = ey;
+                    else kind0 = kind, ex0 = ex, ey0 = ey;
                 }
             }
-            const unsigned tag = slot << SLOT_SHIFT;
-            const unsigned mt = __ballot_sync(FULL_MASK_, kind == 1);
-            const unsigned mx = __ballot_sync(FULL_MASK_, kind >= 2);
-            if (kind == 1) triQ[nt + __popc(mt & ltMask)] = make_uint2((unsigned)c0 | tag, (unsigned)c1);
-            if (kind >= 2) {
-                const int o = n + 2 * __popc(mx & ltMask);
-                if (kind == 2) {
-                    stack[o] = make_uint2((unsigned)c0 | tag, pr.y);
-                    stack[o + 1] = make_uint2((unsigned)c1 | tag, pr.y);
-                } else {
-                    stack[o] = make_uint2(pr.x, (unsigned)c0);
-                    stack[o + 1] = make_uint2(pr.x, (unsigned)c1);
-                }
-            }
-            nt += __popc(mt);
-            n += 2 * __popc(mx);
+            const unsigned t0 = __ballot_sync(FULL_MASK_, kind0 == 1), t1 = __ballot_sync(FULL_MASK_, kind1 == 1);
+            const unsigned s0 = __ballot_sync(FULL_MASK_, kind0 == 2), s1 = __ballot_sync(FULL_MASK_, kind1 == 2);
+            if (kind0 == 1) triQ[nt + __popc(t0 & ltMask)] = make_uint2(ex0, ey0);
+            if (kind1 == 1) triQ[nt + __popc(t0) + __popc(t1 & ltMask)] = make_uint2(ex1, ey1);
+            if (kind0 == 2) stack[n + __popc(s0 & ltMask)] = make_uint2(ex0, ey0);
+            if (kind1 == 2) stack[n + __popc(s0) + __popc(s1 & ltMask)] = make_uint2(ex1, ey1);
+            nt += __popc(t0) + __popc(t1);
+            n += __popc(s0) + __popc(s1);
             if (n > NODE_STACK - 64) {  // cannot happen with the throttle above unless trees are > ~60 deep
                 err |= GEOM_ERR_STACK;
                 if (lane == 0) atomicAdd(pool.ctl + CTL_IDLE, 1u);  // leaving: keep the termination count right
@@ -758,7 +773,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             }
             __syncwarp();
         }
-        if (nt >= 32 || (n == 0 && nt > 0 && exhausted)) {
+        while (nt >= 32 || (n == 0 && nt > 0 && exhausted)) {  // (a round adds up to 64: drain below 32 before the next one)
             const int p = nt < 32 ? nt : 32;
 #ifdef MESH_DEBUG_STATS
             ++dbgTriRounds;
@@ -911,7 +926,9 @@ struct Builder {
 };
 
 // Node order of the device image: the first `prefix` nodes breadth-first from the root (complete upper levels: what a
-// CTA stages in shared memory), everything below them depth-first (a subtree stays contiguous in global memory).
+// CTA stages in shared memory), then the rest of the breadth-first frontier, then the subtrees below it depth-first, the
+// two children of a node placed TOGETHER before either subtree.  Everywhere the right child follows the left one
+// (right == left + 1): a traversal entry names a pair of siblings by the first.
 std::vector<BvhNode> stagingOrder(const std::vector<BvhNode>& in, size_t prefix) {
     const size_t n = in.size();
     std::vector<int> order;  // new position -> old index
@@ -923,13 +940,16 @@ std::vector<BvhNode> stagingOrder(const std::vector<BvhNode>& in, size_t prefix)
         order.push_back(i);
         if (in[i].left >= 0) frontier.push_back(in[i].left), frontier.push_back(in[i].right);
     }
+    const size_t firstBelow = order.size();
+    for (size_t f = head; f < frontier.size(); ++f) order.push_back(frontier[f]);  // sibling pairs stay together across the cut
     std::vector<int> stack;
-    for (size_t f = frontier.size(); f-- > head;) stack.push_back(frontier[f]);  // the rest, depth-first, in frontier order
+    for (size_t k = order.size(); k-- > firstBelow;) stack.push_back(order[k]);
     while (!stack.empty()) {
         const int i = stack.back();
         stack.pop_back();
-        order.push_back(i);
-        if (in[i].left >= 0) stack.push_back(in[i].right), stack.push_back(in[i].left);
+        if (in[i].left < 0) continue;
+        order.push_back(in[i].left), order.push_back(in[i].right);
+        stack.push_back(in[i].right), stack.push_back(in[i].left);
     }
     std::vector<int> where(n);
     for (size_t k = 0; k < n; ++k) where[order[k]] = (int)k;
@@ -941,7 +961,8 @@ std::vector<BvhNode> stagingOrder(const std::vector<BvhNode>& in, size_t prefix)
     return out;
 }
 
-int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, size_t stagePrefix, void** nodesDev, void** trisDev, int* depth, uint32_t* staged) {
+int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, size_t stagePrefix, void** nodesDev, void** trisDev, int* depth, uint32_t* staged,
+               int* rootLeft) {
     std::vector<HostTri> tris(n);
     std::vector<TriPad> pad(n ? n : 1);
     for (uint32_t i = 0; i < n; ++i)
@@ -963,6 +984,7 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, size_t stagePrefix
     *depth = b.maxDepth;
     if (n) b.nodes = stagingOrder(b.nodes, stagePrefix);
     *staged = (uint32_t)std::min(stagePrefix, b.nodes.size());
+    *rootLeft = b.nodes[0].left;
     // device image: centre / half-extent form (what the box test needs), half extents rounded outwards so that
     // [c - h, c + h] contains [lo, hi]
     for (BvhNode& n : b.nodes)
@@ -994,8 +1016,15 @@ int meshCreate(mptg_ctx* ctx, int /*scalar*/, uint32_t nr, const float* robotTri
     const size_t stageE = std::min(nodesE, nodeBudget - stageR);
     stageR = std::min(nodesR, nodeBudget - stageE);
     uint32_t sr = 0, se = 0;
-    int rc = uploadMesh(ctx, robotTris, nr, stageR, &m->mem[0], &m->mem[1], &m->depthR, &sr);
-    if (!rc) rc = uploadMesh(ctx, envTris, ne, stageE, &m->mem[2], &m->mem[3], &m->depthE, &se);
+    int rootR = -1, rootE = -1;
+    int rc = (nodesR > NODE_MASK || nodesE > NODE_MASK) ? fail(ctx, MPTG_ERR_CAPACITY, "meshCreate: more than 2^25 triangles in a mesh") : MPTG_OK;
+    if (!rc) rc = uploadMesh(ctx, robotTris, nr, stageR, &m->mem[0], &m->mem[1], &m->depthR, &sr, &rootR);
+    if (!rc) rc = uploadMesh(ctx, envTris, ne, stageE, &m->mem[2], &m->mem[3], &m->depthE, &se, &rootE);
+    // the entry every state starts from (meshFlatKernel): the children of the robot's root against the environment's
+    // root; a one-triangle robot: the children of the environment's root against it; two single triangles: that pair
+    if (rootR >= 0) m->dev.rootX = (uint32_t)rootR, m->dev.rootY = 0u, m->dev.rootIsTri = 0u;
+    else if (rootE >= 0) m->dev.rootX = SIDE_ENV, m->dev.rootY = (uint32_t)rootE, m->dev.rootIsTri = 0u;
+    else m->dev.rootX = (uint32_t)(-1 - rootR), m->dev.rootY = (uint32_t)(-1 - rootE), m->dev.rootIsTri = 1u;
     m->dev.stageR = sr;
     m->dev.stageE = se;
     if (!rc) {
