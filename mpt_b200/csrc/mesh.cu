@@ -75,7 +75,7 @@ namespace mptg {
 // persistent CTA starts.  r1 ran 6 CTAs of 4 warps per SM and fetched every node pair through L1/L2 (ncu: 2.06 warps
 // per issue waiting on the long scoreboard, 19 of 64 warps active).
 #ifndef MESH_WARPS_PER_CTA
-#define MESH_WARPS_PER_CTA 16
+#define MESH_WARPS_PER_CTA 20
 #endif
 constexpr int MESH_WARPS = MESH_WARPS_PER_CTA;
 #ifndef MESH_CTAS
@@ -316,8 +316,14 @@ constexpr unsigned SLOT_SHIFT = 27;
 constexpr unsigned SIDE_ENV = 1u << 26;  // stack entry: the pair of siblings to test is on the environment's side
 constexpr unsigned NODE_MASK = SIDE_ENV - 1u;
 constexpr int XF_STRIDE = 12;   // 48-byte rows: three 128-bit loads per box test, conflict-free for 8 consecutive slots
-constexpr int REFILL_AT = 16;   // refill when at most this many node pairs are pending
-constexpr int REFILL_MAX = 16;  // states started per refill
+#ifndef MESH_REFILL_AT
+#define MESH_REFILL_AT 24
+#endif
+#ifndef MESH_REFILL_MAX
+#define MESH_REFILL_MAX 24
+#endif
+constexpr int REFILL_AT = MESH_REFILL_AT;    // refill when at most this many node pairs are pending
+constexpr int REFILL_MAX = MESH_REFILL_MAX;  // states started per refill
 constexpr int COARSE_IDS = 8;   // work ids per edge in pass 1
 
 enum { WORK_STATES = 0, WORK_EDGES = 1 };
@@ -343,13 +349,14 @@ struct MeshWork {
 // adopts it as is.  Both sides may then work on the same state; a hit by either clears ok[item], which
 // the other notices at its next periodic look at ok[] (also how warps learn that ANOTHER warp has
 // already invalidated an edge).
-// tuned on the C5 edge wave (B200): see profiles/r1_mesh_donation_tuning.txt
+// tuned on the C5 edge wave (B200): profiles/r1_mesh_donation_tuning.txt, and again for the two-test round
+// (profiles/r2_mesh_two_test_sweep.txt: 20 warps per CTA, refill at 24, a look at the ring every second round)
 #ifndef MESH_DON_MAX
 #define MESH_DON_MAX 128
 #define MESH_DON_MIN 64
 #define MESH_DON_KEEP 32
-#define MESH_DON_EVERY 3u
-#define MESH_MAX_POLLERS 128
+#define MESH_DON_EVERY 1u
+#define MESH_MAX_POLLERS 256
 #endif
 constexpr int DON_MAX = MESH_DON_MAX;        // pairs per block
 constexpr int DON_MIN_STACK = MESH_DON_MIN;  // only stacks at least this deep are split
@@ -618,7 +625,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             continue;
         }
         if ((++roundNo & MESH_DON_EVERY) == 0u) {
-            // Every 8th round: a look at ok[] (items invalidated by another warp are finished here too) and at
+            // Every (MESH_DON_EVERY + 1)-th round: a look at ok[] (items invalidated by another warp are finished here too) and at
             // the donation ring.  The values used are the ones requested at the PREVIOUS look, so the loads
             // never stall the traversal; slots refilled since then are skipped.
             dead |= __ballot_sync(FULL_MASK_, okSeen == 0) & ~fresh;
