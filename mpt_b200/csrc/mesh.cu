@@ -86,6 +86,10 @@ constexpr size_t MESH_SMEM_LIMIT = 227 * 1024;  // opt-in dynamic shared memory 
 constexpr int NODE_STACK = 512;
 constexpr size_t MESH_WARP_SMEM = 512 * 8 + 96 * 8 + 32 * 12 * 4 + 32 * 4;  // stack + triangle queue + transforms + items
 constexpr int STACK_SOFT = NODE_STACK - 64 - 60;  // see the pop rule in meshFlatKernel
+#ifndef MESH_TRI_DRAIN_AT
+#define MESH_TRI_DRAIN_AT 32
+#endif
+constexpr int TRI_DRAIN_AT = MESH_TRI_DRAIN_AT;  // triangle pairs pending before the SAT runs (<= 32: at most 31 + 64 are ever queued)
 constexpr int TRI_QUEUE = 96;  // fewer than 32 pending when a round starts, at most two more per lane in it
 
 struct WarpCounters {
@@ -780,7 +784,7 @@ __global__ void __launch_bounds__(MESH_WARPS * 32, MESH_MIN_CTAS) meshFlatKernel
             }
             __syncwarp();
         }
-        while (nt >= 32 || (n == 0 && nt > 0 && exhausted)) {  // (a round adds up to 64: drain below 32 before the next one)
+        while (nt >= TRI_DRAIN_AT || (n == 0 && nt > 0 && exhausted)) {  // (a round adds up to 64: drain below 32 before the next one)
             const int p = nt < 32 ? nt : 32;
 #ifdef MESH_DEBUG_STATS
             ++dbgTriRounds;
