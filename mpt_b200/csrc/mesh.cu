@@ -899,7 +899,10 @@ struct Builder {
     const std::vector<HostTri>& tris;
     std::vector<BvhNode> nodes;
     int maxDepth = 0;
+    bool sah = true;  // false: median splits along the longest axis (the r1 / early r2 builder)
+    static constexpr int sahMin = 2;
     explicit Builder(const std::vector<HostTri>& t) : tris(t) {}
+    float centroid(int id, int ax) const { return tris[id].v[0][ax] + tris[id].v[1][ax] + tris[id].v[2][ax]; }
 
     int build(std::vector<int>& ids, int lo, int hi, int depth) {
         if (depth > maxDepth) maxDepth = depth;
@@ -922,12 +925,71 @@ struct Builder {
         float ext = -1;
         for (int c = 0; c < 3; ++c)
             if (n.hi[c] - n.lo[c] > ext) ext = n.hi[c] - n.lo[c], axis = c;
-        const int mid = (lo + hi) / 2;
-        std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int x, int y) {
-            const float cx = tris[x].v[0][axis] + tris[x].v[1][axis] + tris[x].v[2][axis];
-            const float cy = tris[y].v[0][axis] + tris[y].v[1][axis] + tris[y].v[2][axis];
-            return cx < cy || (cx == cy && x < y);
-        });
+        int mid = (lo + hi) / 2;
+        bool split = false;
+        if (sah && hi - lo > sahMin && depth < 24) {
+            // binned surface-area heuristic over the three axes (16 bins of the centroid range): the split that minimises
+            // count(left) area(left) + count(right) area(right); ties and degenerate ranges fall back to the median split
+            constexpr int BINS = 16, MAXBINS = BINS;
+            double best = INFINITY;
+            int bestAxis = -1;
+            float bestPos = 0;
+            for (int ax = 0; ax < 3; ++ax) {
+                float cmin = INFINITY, cmax = -INFINITY;
+                for (int i = lo; i < hi; ++i) {
+                    const float c = centroid(ids[i], ax);
+                    cmin = std::fmin(cmin, c), cmax = std::fmax(cmax, c);
+                }
+                if (!(cmax > cmin)) continue;
+                struct Bin { int n = 0; float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; } bins[MAXBINS];
+                const float scale = BINS / (cmax - cmin);
+                for (int i = lo; i < hi; ++i) {
+                    int bi = (int)((centroid(ids[i], ax) - cmin) * scale);
+                    bi = bi < 0 ? 0 : (bi >= BINS ? BINS - 1 : bi);
+                    Bin& bn = bins[bi];
+                    ++bn.n;
+                    for (int v = 0; v < 3; ++v)
+                        for (int c = 0; c < 3; ++c) bn.lo[c] = std::fmin(bn.lo[c], tris[ids[i]].v[v][c]), bn.hi[c] = std::fmax(bn.hi[c], tris[ids[i]].v[v][c]);
+                }
+                auto area = [](const float* l, const float* h) {
+                    const double dx = (double)h[0] - l[0], dy = (double)h[1] - l[1], dz = (double)h[2] - l[2];
+                    return dx * dy + dy * dz + dz * dx;
+                };
+                double rightArea[MAXBINS];
+                int rightN[MAXBINS];
+                {
+                    float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+                    int cnt = 0;
+                    for (int k = BINS - 1; k > 0; --k) {
+                        for (int c = 0; c < 3; ++c) l[c] = std::fmin(l[c], bins[k].lo[c]), h[c] = std::fmax(h[c], bins[k].hi[c]);
+                        cnt += bins[k].n;
+                        rightN[k] = cnt, rightArea[k] = cnt ? area(l, h) : 0.0;
+                    }
+                }
+                float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+                int cnt = 0;
+                for (int k = 0; k + 1 < BINS; ++k) {
+                    for (int c = 0; c < 3; ++c) l[c] = std::fmin(l[c], bins[k].lo[c]), h[c] = std::fmax(h[c], bins[k].hi[c]);
+                    cnt += bins[k].n;
+                    if (cnt == 0 || rightN[k + 1] == 0) continue;
+                    const double cost = cnt * area(l, h) + rightN[k + 1] * rightArea[k + 1];
+                    if (cost < best) best = cost, bestAxis = ax, bestPos = cmin + (k + 1) / scale;
+                }
+            }
+            if (bestAxis >= 0) {
+                const auto it = std::stable_partition(ids.begin() + lo, ids.begin() + hi, [&](int x) { return centroid(x, bestAxis) < bestPos; });
+                const int m = (int)(it - ids.begin());
+                if (m > lo && m < hi) mid = m, split = true;
+            }
+        }
+        if (!split) {
+            mid = (lo + hi) / 2;
+            std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int x, int y) {
+                const float cx = tris[x].v[0][axis] + tris[x].v[1][axis] + tris[x].v[2][axis];
+                const float cy = tris[y].v[0][axis] + tris[y].v[1][axis] + tris[y].v[2][axis];
+                return cx < cy || (cx == cy && x < y);
+            });
+        }
         const int l = build(ids, lo, mid, depth + 1);
         const int r = build(ids, mid, hi, depth + 1);
         nodes[me].left = l;
@@ -982,11 +1044,17 @@ int uploadMesh(mptg_ctx* ctx, const float* tris9, uint32_t n, size_t stagePrefix
             pad[i].v[v][3] = 0.0f;
         }
     Builder b(tris);
+    b.sah = getenv("MPTG_MESH_MEDIAN_SPLIT") == nullptr;  // (the earlier builder stays selectable for comparisons)
     if (n) {
         std::vector<int> ids(n);
         for (uint32_t i = 0; i < n; ++i) ids[i] = (int)i;
         b.nodes.reserve(2 * (size_t)n);
         b.build(ids, 0, (int)n, 0);
+        if (b.sah && b.maxDepth > 28) {  // a degenerate mesh: the balanced tree instead (depth <= 25 + 1), so that two trees always fit the stack budget
+            b.sah = false, b.maxDepth = 0, b.nodes.clear();
+            for (uint32_t i = 0; i < n; ++i) ids[i] = (int)i;
+            b.build(ids, 0, (int)n, 0);
+        }
     } else {
         BvhNode placeholder{};  // never traversed (an empty mesh cannot collide); a leaf, so that nothing hangs off it
         placeholder.left = placeholder.right = -1;
