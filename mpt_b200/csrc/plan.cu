@@ -1876,8 +1876,7 @@ int starWaveT(mptg_prrtstar* p, uint32_t W) {
                                                            (S*)p->eTo, nullptr);
         MPTG_LAUNCHED(ctx);
         if (int rc = mptg_link_batch_dev(p->geom, &p->space, p->eFrom, p->eTo, nR, p->linkStep, p->okEdge, nullptr)) return rc;
-        MPTG_CUDA(ctx, cudaMemsetAsync(p->bestKey, 0xFF, (size_t)p->size * 8, st));
-        MPTG_CUDA(ctx, cudaMemsetAsync(p->bestCand, 0xFF, (size_t)p->size * 4, st));
+        // (bestKey / bestCand are in their "no offer" state: set at creation, restored by every push pass that follows offers -- ADVICE r1)
         MPTG_CUDA(ctx, cudaMemsetAsync(p->delta, 0, (size_t)total * sizeof(S), st));
         MPTG_CUDA(ctx, cudaMemsetAsync(p->result + 1, 0, 4, st));
         const uint32_t gr = (nR + 127) / 128;
